@@ -1,0 +1,185 @@
+// Weight-gradient tap-GEMM (the K dimension is pixels):
+//
+//   dW[tap][a][b] = sum_{pixel} A[pixel, a] * B_tap[pixel + shift(tap), b]
+//
+// A (unshifted, e.g. dY) and B (shifted per tap through the same parity-view tensor maps the forward uses,
+// e.g. X) are NHWC fp32, so both UMMA operands are MN-major: a TMA box (32 channels x 32 pixels) lands in smem
+// as one swizzled "atom" [32 pixel rows][128 bytes]; M = 128 spans 4 atoms (LBO = atom size), and each
+// tcgen05.mma.kind::tf32 consumes K = 8 pixel rows. MN-major tf32 operands must use the 128B swizzle with 32-byte
+// atomicity (UMMA layout SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4-row groups, SBO = 512. A CTA owns one
+// (128 x BN) x TPC-taps output block and a contiguous range of pixel tiles (split-K); partial sums leave through
+// vectorised red.global.add.f32.
+//
+// Replaces autograd's cuDNN wgrad for nn.Conv2d / nn.ConvTranspose2d (reference: torch autograd over
+// opencood/models/common_modules/base_bev_backbone.py:41-105, downsample_conv.py:18-32).
+#pragma once
+#include "a2x_ptx.cuh"
+#include "tapgemm.cuh"
+
+namespace a2x {
+
+constexpr int WG_PIX = 32;                  // pixels per k-step
+constexpr int WG_ATOM_BYTES = WG_PIX * 128;  // one (32 px x 32 ch) atom
+
+struct WgParams {
+    CUtensorMap amap;
+    CUtensorMap bmap[TG_MAX_MAPS];
+    TgTap taps[TG_MAX_TAPS];
+    int ntaps;
+    int ca, cb;  // channel counts (multiples of 32)
+    int n_img, tiles_h, tiles_w, tw_log2;  // 32-pixel tiles: (32 >> tw_log2) rows x (1 << tw_log2) cols
+    int tiles_per_cta;
+    int n_tiles_b;  // number of BN-wide column tiles
+    float* dw;      // [ntaps][ca][cb], accumulated with red.add (caller zeroes)
+    uint32_t lbo_bytes, sbo_bytes;  // MN-major descriptor strides (debug-overridable)
+    int scalar_atomics;             // debug: plain atomicAdd instead of red.v4
+    uint32_t layout;                // UMMA smem layout type (1 = SWIZZLE_128B_BASE32B)
+};
+
+template <int BN, int TPC, int STAGES>
+struct WgSmem {
+    static constexpr int A_BYTES = 4 * WG_ATOM_BYTES;
+    static constexpr int B_BYTES = TPC * (BN / 32) * WG_ATOM_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static constexpr int TMEM_COLS = (TPC * BN <= 32) ? 32 : (TPC * BN <= 64) ? 64 : (TPC * BN <= 128) ? 128
+                                     : (TPC * BN <= 256) ? 256 : 512;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+template <int BN, int TPC, int STAGES>
+__global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgParams p) {
+    using L = WgSmem<BN, TPC, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m0 = (blockIdx.y / p.n_tiles_b) * 128;
+    const int n0 = (blockIdx.y % p.n_tiles_b) * BN;
+    const int tap0 = blockIdx.z * TPC;
+    const int a_atoms = min(4, (p.ca - m0) / 32);
+    const int b_atoms = min(BN / 32, (p.cb - n0) / 32);
+    const int total_tiles = p.n_img * p.tiles_h * p.tiles_w;
+    const int tile_begin = blockIdx.x * p.tiles_per_cta;
+    const int tile_end = min(total_tiles, tile_begin + p.tiles_per_cta);
+    const int ntiles = tile_end - tile_begin;
+    if (ntiles <= 0) return;  // uniform for the whole CTA
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<L::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const int TW = 1 << p.tw_log2;
+            const int TH = WG_PIX >> p.tw_log2;
+            const uint32_t tx_bytes = (a_atoms + TPC * b_atoms) * WG_ATOM_BYTES;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                int t = tile;
+                const int tw_i = t % p.tiles_w;
+                t /= p.tiles_w;
+                const int th_i = t % p.tiles_h;
+                const int img = t / p.tiles_h;
+                const int h0 = th_i * TH, w0 = tw_i * TW;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                uint8_t* sb = sa + L::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                for (int a = 0; a < a_atoms; ++a)
+                    tma_load_5d(sa + a * WG_ATOM_BYTES, &p.amap, &full_bar[stage], m0 + a * 32, w0, 0, h0, img);
+                for (int tt = 0; tt < TPC; ++tt) {
+                    const TgTap tp = p.taps[tap0 + tt];
+                    for (int b = 0; b < b_atoms; ++b)
+                        tma_load_5d(sb + (tt * (BN / 32) + b) * WG_ATOM_BYTES, &p.bmap[tp.map], &full_bar[stage],
+                                    n0 + b * 32, w0 + tp.dw, tp.dx, h0 + tp.dh, img);
+                }
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < ntiles; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < WG_PIX / 8; ++k) {  // K = 8 pixel rows per MMA = one 1024-byte swizzle group
+                    const uint64_t ad = make_smem_desc_sw128(sa + k * 1024, p.lbo_bytes, p.sbo_bytes, p.layout);
+#pragma unroll
+                    for (int tt = 0; tt < TPC; ++tt) {
+                        const uint64_t bd = make_smem_desc_sw128(sb + tt * (BN / 32) * WG_ATOM_BYTES + k * 1024,
+                                                                 p.lbo_bytes, p.sbo_bytes, p.layout);
+                        umma_tf32(tmem_base + tt * BN, ad, bd, idesc, (it | k) != 0);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int tt = 0; tt < TPC; ++tt) {
+            float* orow = p.dw + ((long long)(tap0 + tt) * p.ca + row) * p.cb + n0;
+#pragma unroll 1
+            for (int j = 0; j < BN / 32; ++j) {
+                if (j >= b_atoms) break;
+                float v[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tt * BN + j * 32), v);
+                tmem_ld_wait();
+                if (row < p.ca) {
+                    if (p.scalar_atomics) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) atomicAdd(orow + j * 32 + i, v[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            red_add_v4(orow + j * 32 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<L::TMEM_COLS>(tmem_base);
+}
+
+}  // namespace a2x
