@@ -21,6 +21,21 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// round-to-nearest (ties away) fp32 -> tf32, result kept in an fp32 container with 13 zero low bits.
+// kind::tf32 MMAs read raw fp32 bits and ignore the low 13, i.e. truncate; pre-rounding removes that bias.
+__host__ __device__ __forceinline__ float tf32_rn(float x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t u = __float_as_uint(x);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c;
+    c.f = x;
+    c.u = (c.u + 0x1000u) & 0xFFFFE000u;
+    return c.f;
+#endif
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

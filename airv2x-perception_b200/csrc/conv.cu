@@ -172,22 +172,23 @@ static int build_fwd_maps(const a2x_conv_shape* s, const float* x, int x_cs, CUt
     return 0;
 }
 
-template <int BN, int TPC, int STAGES>
+template <int BN, int TPC, int STAGES, bool SPLIT>
 static int launch_wg(const WgParams& p, int ksplit, int tiles_a, int tap_groups, cudaStream_t st) {
-    using L = WgSmem<BN, TPC, STAGES>;
+    using L = WgSmem<BN, TPC, STAGES, SPLIT>;
     static bool configured = false;
     if (!configured) {
-        A2X_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, TPC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            L::TOTAL));
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, TPC, STAGES, SPLIT>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
     dim3 grid(ksplit, tiles_a * p.n_tiles_b, tap_groups);
-    wgrad_kernel<BN, TPC, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
+    wgrad_kernel<BN, TPC, STAGES, SPLIT><<<grid, 192, L::TOTAL, st>>>(p);
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-static int run_wg(WgParams& p, int gh, int gw, int n_img, int tpc, cudaStream_t st) {
+// tpc = taps sharing one A tile per CTA (3 for a 3x3 kernel row in single-plane mode, else 1)
+static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream_t st) {
     p.n_img = n_img;
     const int TW = 1 << p.tw_log2, TH = WG_PIX >> p.tw_log2;
     p.tiles_h = (gh + TH - 1) / TH;
@@ -197,26 +198,46 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, int tpc, cudaStream_t 
     p.layout = g_debug[5] > 0 ? (uint32_t)g_debug[5] : 1u;
     p.scalar_atomics = g_debug[4];
     const int bn = p.cb >= 128 ? 128 : (p.cb >= 64 ? 64 : 32);
+    const int tpc = (!split && p.ntaps % 3 == 0) ? 3 : 1;
     p.n_tiles_b = (p.cb + bn - 1) / bn;
     const int tiles_a = (p.ca + 127) / 128;
     const int tap_groups = p.ntaps / tpc;
     const int total_tiles = n_img * p.tiles_h * p.tiles_w;
-    int sms = 148;
+    const int sms = 148;
     const int blocks_mn = tiles_a * p.n_tiles_b * tap_groups;
     int ksplit = (2 * sms + blocks_mn - 1) / blocks_mn;
     if (ksplit > total_tiles) ksplit = total_tiles;
     if (ksplit < 1) ksplit = 1;
     p.tiles_per_cta = (total_tiles + ksplit - 1) / ksplit;
     ksplit = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-    if (tpc == 3) {
-        if (bn == 128) return launch_wg<128, 3, 3>(p, ksplit, tiles_a, tap_groups, st);
-        if (bn == 64) return launch_wg<64, 3, 4>(p, ksplit, tiles_a, tap_groups, st);
-        return launch_wg<32, 3, 4>(p, ksplit, tiles_a, tap_groups, st);
-    } else {
-        if (bn == 128) return launch_wg<128, 1, 4>(p, ksplit, tiles_a, tap_groups, st);
-        if (bn == 64) return launch_wg<64, 1, 4>(p, ksplit, tiles_a, tap_groups, st);
-        return launch_wg<32, 1, 4>(p, ksplit, tiles_a, tap_groups, st);
+    if (split) {
+        if (bn == 128) return launch_wg<128, 1, 3, true>(p, ksplit, tiles_a, tap_groups, st);
+        if (bn == 64) return launch_wg<64, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
+        return launch_wg<32, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
     }
+    if (tpc == 3) {
+        if (bn == 128) return launch_wg<128, 3, 3, false>(p, ksplit, tiles_a, tap_groups, st);
+        if (bn == 64) return launch_wg<64, 3, 4, false>(p, ksplit, tiles_a, tap_groups, st);
+        return launch_wg<32, 3, 4, false>(p, ksplit, tiles_a, tap_groups, st);
+    }
+    if (bn == 128) return launch_wg<128, 1, 4, false>(p, ksplit, tiles_a, tap_groups, st);
+    if (bn == 64) return launch_wg<64, 1, 4, false>(p, ksplit, tiles_a, tap_groups, st);
+    return launch_wg<32, 1, 4, false>(p, ksplit, tiles_a, tap_groups, st);
+}
+
+// 3xTF32: D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo. Base taps reference base maps [0, nmaps) and weight taps
+// [0, ntaps_w); lo activation views live at map + nmaps, lo weights at btap + ntaps_w.
+static int expand_split_taps(TgTap* taps, int ntaps, int nmaps, int ntaps_w) {
+    for (int i = ntaps - 1; i >= 0; --i) {
+        const TgTap t = taps[i];
+        TgTap a = t, b = t, c = t;
+        b.map = (int16_t)(t.map + nmaps);
+        c.btap = t.btap + ntaps_w;
+        taps[3 * i] = a;
+        taps[3 * i + 1] = b;
+        taps[3 * i + 2] = c;
+    }
+    return 3 * ntaps;
 }
 
 // ------------------------------------------------------------------ small re-layout kernels
@@ -229,8 +250,16 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, int cout, int ci
         const int co = (int)((i / cin) % cout_pad);
         const int tap = (int)(i / ((long long)cin * cout_pad));
         const float v = co < cout ? w[((long long)co * cin + ci) * kk + tap] : 0.f;
-        if (wf) wf[i] = v;                                                   // [tap][co][ci]
-        if (wd) wd[((long long)tap * cin + ci) * cout_pad + co] = v;          // [tap][ci][co]
+        const float hi = tf32_rn(v), lo = v - hi;
+        if (wf) {  // [2][tap][co][ci]
+            wf[i] = hi;
+            wf[total + i] = lo;
+        }
+        if (wd) {  // [2][tap][ci][co]
+            const long long j = ((long long)tap * cin + ci) * cout_pad + co;
+            wd[j] = hi;
+            wd[total + j] = lo;
+        }
     }
 }
 __global__ void unpack_conv_dw_kernel(const float* __restrict__ dwp, int cout, int cin, int kk, int cout_pad,
@@ -254,9 +283,18 @@ __global__ void pack_deconv_w_kernel(const float* __restrict__ w, int cin, int c
         const int ij = (int)(i % ss);
         const int co = (int)((i / ss) % cout);
         const int ci = (int)(i / ((long long)ss * cout));
-        const float v = w[i];                                              // [ci][co][i][j]
-        if (wf) wf[((long long)ij * cout + co) * cin + ci] = v;              // [(ij, co)][ci]
-        if (wd) wd[((long long)ij * cin + ci) * cout + co] = v;              // [ij][ci][co]
+        const float v = w[i];  // [ci][co][i][j]
+        const float hi = tf32_rn(v), lo = v - hi;
+        if (wf) {  // [2][(ij, co)][ci]
+            const long long j = ((long long)ij * cout + co) * cin + ci;
+            wf[j] = hi;
+            wf[total + j] = lo;
+        }
+        if (wd) {  // [2][ij][ci][co]
+            const long long j = ((long long)ij * cin + ci) * cout + co;
+            wd[j] = hi;
+            wd[total + j] = lo;
+        }
     }
 }
 __global__ void unpack_deconv_dw_kernel(const float* __restrict__ dwp, int cin, int cout, int s,
@@ -324,20 +362,27 @@ int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, fl
     return 0;
 }
 
-int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, int x_cs, const float* w_fwd, float* y, int y_cs,
-                   const float* scale, const float* shift, int relu, a2x_stream_t stream) {
+int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
+                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
     A2X_REQUIRE(x && w_fwd && y && x_cs >= s->cin && y_cs >= s->cout && x_cs % 4 == 0 && y_cs % 4 == 0,
                 "bad conv2d_fwd pointers/strides");
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
+    const int kk = s->ksize * s->ksize;
     TgParams p{};
     p.tw_log2 = pick_tw_log2(ho, wo, TG_BM, 4, 7);
     const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
+    const int nmaps = s->stride == 1 ? 1 : 4;
     if (int r = build_fwd_maps(s, x, x_cs, p.amap, TW, TH)) return r;
     p.ntaps = build_fwd_taps(s, p.taps);
+    if (x_lo) {
+        if (int r = build_fwd_maps(s, x_lo, x_cs, p.amap + nmaps, TW, TH)) return r;
+        p.ntaps = expand_split_taps(p.taps, p.ntaps, nmaps, kk);
+    }
     p.kchunks = s->cin / 32;
-    if (int r = make_w_map(&p.bmap, w_fwd, p.ntaps, s->cout, s->cin, bn_for(s->cout))) return r;
+    if (int r = make_w_map(&p.bmap, w_fwd, 2 * kk, s->cout, s->cin, bn_for(s->cout))) return r;
     set_plain_out(p, y, ho, wo, y_cs, 1, 0, 0);
+    p.out_lo = y_lo;
     p.scale = scale;
     p.shift = shift;
     p.relu = relu;
@@ -345,85 +390,80 @@ int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, int x_cs, const floa
     return run_tg(p, ho, wo, s->n, s->cout, (cudaStream_t)stream);
 }
 
-int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, int dy_cs, const float* w_dgrad, float* dx, int dx_cs,
-                     int accumulate, a2x_stream_t stream) {
+int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
+                     float* dx, int dx_cs, int accumulate, a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
     A2X_REQUIRE(dy && w_dgrad && dx && dy_cs >= s->cout && dx_cs >= s->cin && dy_cs % 4 == 0 && dx_cs % 4 == 0,
                 "bad conv2d_dgrad pointers/strides");
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
     const int kk = s->ksize * s->ksize;
-    if (s->stride == 1) {
+    const int n_class = s->stride == 1 ? 1 : 4;
+    for (int cls = 0; cls < n_class; ++cls) {
+        const int hp = cls >> 1, wp = cls & 1;
+        const int step = s->stride;
+        const int gh = (s->h - hp + step - 1) / step, gw = (s->w - wp + step - 1) / step;
+        if (gh <= 0 || gw <= 0) continue;
         TgParams p{};
-        p.tw_log2 = pick_tw_log2(s->h, s->w, TG_BM, 4, 7);
+        p.tw_log2 = pick_tw_log2(gh, gw, TG_BM, 4, 7);
         const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
         if (int r = make_act_map(&p.amap[0], dy, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH)) return r;
         p.ntaps = 0;
-        for (int r = 0; r < s->ksize; ++r)
+        for (int r = 0; r < s->ksize; ++r) {
+            if (step == 2 && ((r + 1) & 1) != hp) continue;  // (r - 1) parity must equal hp
             for (int c = 0; c < s->ksize; ++c) {
+                if (step == 2 && ((c + 1) & 1) != wp) continue;
                 TgTap t{};
                 t.map = 0;
-                t.dh = (int16_t)(s->ksize == 3 ? 1 - r : 0);
-                t.dw = (int16_t)(s->ksize == 3 ? 1 - c : 0);
+                if (step == 1) {
+                    t.dh = (int16_t)(s->ksize == 3 ? 1 - r : 0);
+                    t.dw = (int16_t)(s->ksize == 3 ? 1 - c : 0);
+                } else {
+                    t.dh = (int16_t)((hp == 1 && r == 0) ? 1 : 0);
+                    t.dw = (int16_t)((wp == 1 && c == 0) ? 1 : 0);
+                }
                 t.btap = r * s->ksize + c;
                 p.taps[p.ntaps++] = t;
             }
-        p.kchunks = s->cout / 32;
-        if (int r = make_w_map(&p.bmap, w_dgrad, kk, s->cin, s->cout, bn_for(s->cin))) return r;
-        set_plain_out(p, dx, s->h, s->w, dx_cs, 1, 0, 0);
-        p.accumulate = accumulate;
-        return run_tg(p, s->h, s->w, s->n, s->cin, (cudaStream_t)stream);
-    }
-    // stride 2: one launch per input-pixel parity class
-    for (int hp = 0; hp < 2; ++hp)
-        for (int wp = 0; wp < 2; ++wp) {
-            const int gh = (s->h - hp + 1) / 2, gw = (s->w - wp + 1) / 2;
-            if (gh <= 0 || gw <= 0) continue;
-            TgParams p{};
-            p.tw_log2 = pick_tw_log2(gh, gw, TG_BM, 4, 7);
-            const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
-            if (int r = make_act_map(&p.amap[0], dy, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH)) return r;
-            p.ntaps = 0;
-            for (int r = 0; r < 3; ++r) {
-                if (((r + 1) & 1) != hp) continue;  // (r - 1) parity must equal hp
-                for (int c = 0; c < 3; ++c) {
-                    if (((c + 1) & 1) != wp) continue;
-                    TgTap t{};
-                    t.map = 0;
-                    t.dh = (int16_t)((hp == 1 && r == 0) ? 1 : 0);
-                    t.dw = (int16_t)((wp == 1 && c == 0) ? 1 : 0);
-                    t.btap = r * 3 + c;
-                    p.taps[p.ntaps++] = t;
-                }
-            }
-            p.kchunks = s->cout / 32;
-            if (int r = make_w_map(&p.bmap, w_dgrad, kk, s->cin, s->cout, bn_for(s->cin))) return r;
-            set_plain_out(p, dx, s->h, s->w, dx_cs, 2, hp, wp);
-            p.accumulate = accumulate;
-            if (int r = run_tg(p, gh, gw, s->n, s->cin, (cudaStream_t)stream)) return r;
         }
+        if (dy_lo) {
+            if (int r = make_act_map(&p.amap[1], dy_lo, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH)) return r;
+            p.ntaps = expand_split_taps(p.taps, p.ntaps, 1, kk);
+        }
+        p.kchunks = s->cout / 32;
+        if (int r = make_w_map(&p.bmap, w_dgrad, 2 * kk, s->cin, s->cout, bn_for(s->cin))) return r;
+        set_plain_out(p, dx, s->h, s->w, dx_cs, step, hp, wp);
+        p.accumulate = accumulate;
+        if (int r = run_tg(p, gh, gw, s->n, s->cin, (cudaStream_t)stream)) return r;
+    }
     return 0;
 }
 
-int a2x_conv2d_wgrad(const a2x_conv_shape* s, const float* x, int x_cs, const float* dy, int dy_cs, float* dw_packed,
-                     a2x_stream_t stream) {
+int a2x_conv2d_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,
+                     const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
     A2X_REQUIRE(x && dy && dw_packed && x_cs >= s->cin && dy_cs >= s->cout && x_cs % 4 == 0 && dy_cs % 4 == 0,
                 "bad conv2d_wgrad pointers/strides");
+    A2X_REQUIRE((x_lo == nullptr) == (dy_lo == nullptr), "wgrad needs both or neither lo planes");
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
     WgParams p{};
     p.tw_log2 = pick_tw_log2(ho, wo, WG_PIX, 2, 5);
     const int TW = 1 << p.tw_log2, TH = WG_PIX >> p.tw_log2;
-    if (int r = make_act_map(&p.amap, dy, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH, 1)) return r;
+    p.nmaps_b = s->stride == 1 ? 1 : 4;
+    if (int r = make_act_map(&p.amap[0], dy, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH, 1)) return r;
     if (int r = build_fwd_maps(s, x, x_cs, p.bmap, TW, TH, 1)) return r;
+    if (x_lo) {
+        if (int r = make_act_map(&p.amap[1], dy_lo, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH, 1)) return r;
+        if (int r = build_fwd_maps(s, x_lo, x_cs, p.bmap + p.nmaps_b, TW, TH, 1)) return r;
+    }
     p.ntaps = build_fwd_taps(s, p.taps);
     p.ca = s->cout;
     p.cb = s->cin;
     p.dw = dw_packed;
-    return run_wg(p, ho, wo, s->n, s->ksize == 3 ? 3 : 1, (cudaStream_t)stream);
+    return run_wg(p, ho, wo, s->n, x_lo != nullptr, (cudaStream_t)stream);
 }
 
-int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, int x_cs, const float* w_fwd, float* y, int y_cs,
-                   const float* scale, const float* shift, int relu, a2x_stream_t stream) {
+int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
+                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, a2x_stream_t stream) {
     if (int r = check_shape(s, true)) return r;
     A2X_REQUIRE(x && w_fwd && y && x_cs >= s->cin && y_cs >= s->cout && x_cs % 4 == 0 && y_cs % 4 == 0,
                 "bad deconv_fwd pointers/strides");
@@ -434,11 +474,16 @@ int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, int x_cs, const floa
     if (int r = make_act_map(&p.amap[0], x, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH)) return r;
     p.ntaps = 1;
     p.taps[0] = TgTap{0, 0, 0, 0, 0, 0};
+    if (x_lo) {
+        if (int r = make_act_map(&p.amap[1], x_lo, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH)) return r;
+        p.ntaps = expand_split_taps(p.taps, 1, 1, 1);
+    }
     p.kchunks = s->cin / 32;
     const int ncols = st * st * s->cout;
-    if (int r = make_w_map(&p.bmap, w_fwd, 1, ncols, s->cin, bn_for(ncols))) return r;
+    if (int r = make_w_map(&p.bmap, w_fwd, 2, ncols, s->cin, bn_for(ncols))) return r;
     const long long W2 = (long long)s->w * st;
     p.out = y;
+    p.out_lo = y_lo;
     p.osn = (long long)s->h * st * W2 * y_cs;
     p.osh = (long long)st * W2 * y_cs;
     p.osw = (long long)st * y_cs;
@@ -453,8 +498,8 @@ int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, int x_cs, const floa
     return run_tg(p, s->h, s->w, s->n, ncols, (cudaStream_t)stream);
 }
 
-int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, int dy_cs, const float* w_dgrad, float* dx, int dx_cs,
-                     int accumulate, a2x_stream_t stream) {
+int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
+                     float* dx, int dx_cs, int accumulate, a2x_stream_t stream) {
     if (int r = check_shape(s, true)) return r;
     A2X_REQUIRE(dy && w_dgrad && dx && dy_cs >= s->cout && dx_cs >= s->cin && dy_cs % 4 == 0 && dx_cs % 4 == 0,
                 "bad deconv_dgrad pointers/strides");
@@ -468,13 +513,18 @@ int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, int dy_cs, const 
         for (int j = 0; j < st; ++j) {
             if (int r = make_act_map(&p.amap[j], dy, s->n, s->h * st, s->w * st, s->cout, dy_cs, st, i, j, TW, TH))
                 return r;
+            if (dy_lo)
+                if (int r = make_act_map(&p.amap[st + j], dy_lo, s->n, s->h * st, s->w * st, s->cout, dy_cs, st, i, j,
+                                         TW, TH))
+                    return r;
             TgTap t{};
             t.map = (int16_t)j;
             t.btap = i * st + j;
             p.taps[p.ntaps++] = t;
         }
+        if (dy_lo) p.ntaps = expand_split_taps(p.taps, p.ntaps, st, st * st);
         p.kchunks = s->cout / 32;
-        if (int r = make_w_map(&p.bmap, w_dgrad, st * st, s->cin, s->cout, bn_for(s->cin))) return r;
+        if (int r = make_w_map(&p.bmap, w_dgrad, 2 * st * st, s->cin, s->cout, bn_for(s->cin))) return r;
         set_plain_out(p, dx, s->h, s->w, dx_cs, 1, 0, 0);
         p.accumulate = (i > 0) ? 1 : accumulate;
         if (int r = run_tg(p, s->h, s->w, s->n, s->cin, (cudaStream_t)stream)) return r;
@@ -482,21 +532,29 @@ int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, int dy_cs, const 
     return 0;
 }
 
-int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, int x_cs, const float* dy, int dy_cs, float* dw_packed,
-                     a2x_stream_t stream) {
+int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,
+                     const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream) {
     if (int r = check_shape(s, true)) return r;
     A2X_REQUIRE(x && dy && dw_packed && x_cs >= s->cin && dy_cs >= s->cout && x_cs % 4 == 0 && dy_cs % 4 == 0,
                 "bad deconv_wgrad pointers/strides");
+    A2X_REQUIRE((x_lo == nullptr) == (dy_lo == nullptr), "wgrad needs both or neither lo planes");
     const int st = s->stride;
     for (int i = 0; i < st; ++i) {
         WgParams p{};
         p.tw_log2 = pick_tw_log2(s->h, s->w, WG_PIX, 2, 5);
         const int TW = 1 << p.tw_log2, TH = WG_PIX >> p.tw_log2;
-        if (int r = make_act_map(&p.amap, x, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH, 1)) return r;
+        p.nmaps_b = st;
+        if (int r = make_act_map(&p.amap[0], x, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH, 1)) return r;
+        if (x_lo)
+            if (int r = make_act_map(&p.amap[1], x_lo, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH, 1)) return r;
         p.ntaps = 0;
         for (int j = 0; j < st; ++j) {
             if (int r = make_act_map(&p.bmap[j], dy, s->n, s->h * st, s->w * st, s->cout, dy_cs, st, i, j, TW, TH, 1))
                 return r;
+            if (dy_lo)
+                if (int r = make_act_map(&p.bmap[st + j], dy_lo, s->n, s->h * st, s->w * st, s->cout, dy_cs, st, i, j,
+                                         TW, TH, 1))
+                    return r;
             TgTap t{};
             t.map = (int16_t)j;
             p.taps[p.ntaps++] = t;
@@ -504,7 +562,7 @@ int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, int x_cs, const fl
         p.ca = s->cin;
         p.cb = s->cout;
         p.dw = dw_packed + (long long)i * st * s->cin * s->cout;  // [(i, j)][ci][co]
-        if (int r = run_wg(p, s->h, s->w, s->n, 1, (cudaStream_t)stream)) return r;
+        if (int r = run_wg(p, s->h, s->w, s->n, x_lo != nullptr, (cudaStream_t)stream)) return r;
     }
     return 0;
 }

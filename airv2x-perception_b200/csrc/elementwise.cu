@@ -1,0 +1,389 @@
+// HBM-bound elementwise / per-channel-reduction kernels around the tensor-core contractions:
+// BatchNorm (train-mode batch statistics, eval-mode affine), ReLU, their backward passes, mask multiply,
+// operand splitting for 3xTF32. All tensors are fp32 NHWC with an explicit pixel stride.
+//
+// Reference semantics: nn.BatchNorm2d(eps=1e-3, momentum=0.01) + nn.ReLU in
+// opencood/models/common_modules/base_bev_backbone.py:52-66, :82-90; bias+ReLU in downsample_conv.py:18-32.
+#include "../../include/airv2x_b200.h"
+#include "a2x_host.h"
+#include "a2x_ptx.cuh"
+
+namespace a2x {
+
+__device__ __forceinline__ void store_split(float* hi_p, float* lo_p, float4 v) {
+    if (lo_p != nullptr) {
+        float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+        *reinterpret_cast<float4*>(hi_p) = h;
+        *reinterpret_cast<float4*>(lo_p) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    } else {
+        *reinterpret_cast<float4*>(hi_p) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- split
+__global__ void split_kernel(const float* __restrict__ x, long long n4, float* __restrict__ hi, float* __restrict__ lo) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        store_split(hi + 4 * i, lo + 4 * i, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- channel stats
+// sums[c] += sum_p x[p][c] ; sums[C + c] += sum_p x[p][c]^2     (double accumulators)
+// optional second operand: MODE 1 computes g = dy * (z*scale+shift > 0), zhat = (z-mean)*invstd and accumulates
+// sums[c] += g, sums[C+c] += g*zhat  (BatchNorm+ReLU backward reductions)
+template <int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(const float* __restrict__ x, int x_cs,
+                                                             const float* __restrict__ z, int z_cs,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ shift,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, long long npix, int C,
+                                                             double* __restrict__ sums) {
+    extern __shared__ float red[];  // [2][256][4]
+    const int q = C >> 2;                  // float4 groups per pixel
+    const int cq = threadIdx.x % q;        // my channel quad
+    const int prow = threadIdx.x / q;      // my pixel lane within the block
+    const int ppb = blockDim.x / q;        // pixels per block iteration
+    float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+    float sc[4], sh[4], mu[4], is[4];
+    if (MODE == 1 && prow < ppb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            sc[e] = scale[cq * 4 + e];
+            sh[e] = shift[cq * 4 + e];
+            mu[e] = mean[cq * 4 + e];
+            is[e] = invstd[cq * 4 + e];
+        }
+    }
+    if (prow < ppb) {
+        for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
+            const float4 v = *reinterpret_cast<const float4*>(x + p * x_cs + cq * 4);
+            const float a[4] = {v.x, v.y, v.z, v.w};
+            if (MODE == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    s0[e] += a[e];
+                    s1[e] += a[e] * a[e];
+                }
+            } else {
+                const float4 zz = *reinterpret_cast<const float4*>(z + p * z_cs + cq * 4);
+                const float b[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float g = (b[e] * sc[e] + sh[e] > 0.f) ? a[e] : 0.f;
+                    s0[e] += g;
+                    s1[e] += g * (b[e] - mu[e]) * is[e];
+                }
+            }
+        }
+    }
+    float* r0 = red;
+    float* r1 = red + blockDim.x * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        r0[threadIdx.x * 4 + e] = s0[e];
+        r1[threadIdx.x * 4 + e] = s1[e];
+    }
+    __syncthreads();
+    if (threadIdx.x < q) {
+        double d0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0};
+        for (int r = 0; r < ppb; ++r) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                d0[e] += r0[(r * q + threadIdx.x) * 4 + e];
+                d1[e] += r1[(r * q + threadIdx.x) * 4 + e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            atomicAdd(&sums[threadIdx.x * 4 + e], d0[e]);
+            atomicAdd(&sums[C + threadIdx.x * 4 + e], d1[e]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- BN finalize
+// batch stats -> (scale, shift, mean, invstd); running stats updated `n_updates` times (the reference evaluates the
+// backbone several times per step on identical data: airv2x_where2com.py:119,124, where2comm_fuse.py:218).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, int n_updates,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, int C,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c] / count;
+    double var = sums[C + c] / count - m * m;
+    if (var < 0) var = 0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    scale[c] = g * invstd;
+    shift[c] = b - (float)m * g * invstd;
+    if (mean_out) mean_out[c] = (float)m;
+    if (invstd_out) invstd_out[c] = invstd;
+    if (running_mean != nullptr && n_updates > 0) {
+        const float unbiased = (float)(count > 1 ? var * count / (count - 1) : var);
+        float rm = running_mean[c], rv = running_var[c];
+        for (int i = 0; i < n_updates; ++i) {
+            rm = (1.f - momentum) * rm + momentum * (float)m;
+            rv = (1.f - momentum) * rv + momentum * unbiased;
+        }
+        running_mean[c] = rm;
+        running_var[c] = rv;
+    }
+}
+
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float invstd = 1.f / sqrtf(rv[c] + eps);
+    const float s = gamma[c] * invstd;
+    scale[c] = s;
+    shift[c] = beta[c] - rm[c] * s;
+}
+
+// dgamma = sum g*zhat, dbeta = sum g
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float dg = (float)sums[C + c], db = (float)sums[c];
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
+}
+
+// ---------------------------------------------------------------------------------------------- affine + relu
+// y = relu?(x * scale[c] + shift[c]) * (mask[pixel])   -> split store
+__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int x_cs,
+                                                         const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, int relu,
+                                                         const float* __restrict__ mask, float* __restrict__ y,
+                                                         float* __restrict__ y_lo, int y_cs, long long npix, int C) {
+    const int q = C >> 2;
+    const long long total = npix * q;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / q;
+        const int c = (int)(i - p * q) * 4;
+        float4 v = *reinterpret_cast<const float4*>(x + p * x_cs + c);
+        if (scale != nullptr) {
+            const float4 s = *reinterpret_cast<const float4*>(scale + c);
+            v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+        }
+        if (shift != nullptr) {
+            const float4 b = *reinterpret_cast<const float4*>(shift + c);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (relu) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        if (mask != nullptr) {
+            const float m = mask[p];
+            v.x *= m; v.y *= m; v.z *= m; v.w *= m;
+        }
+        store_split(y + p * y_cs + c, y_lo ? y_lo + p * y_cs + c : nullptr, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- BN+ReLU backward
+// g = dy * (z*scale+shift > 0); dz = gamma*invstd * (g - sum_g/m - zhat * sum_gz/m)        (train mode)
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __restrict__ dy, int dy_cs,
+                                                                const float* __restrict__ z, int z_cs,
+                                                                const float* __restrict__ scale,
+                                                                const float* __restrict__ shift,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd,
+                                                                const double* __restrict__ sums, double count,
+                                                                float* __restrict__ dz, float* __restrict__ dz_lo,
+                                                                int dz_cs, long long npix, int C) {
+    const int q = C >> 2;
+    const long long total = npix * q;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / q;
+        const int c = (int)(i - p * q) * 4;
+        const float4 d4 = *reinterpret_cast<const float4*>(dy + p * dy_cs + c);
+        const float4 z4 = *reinterpret_cast<const float4*>(z + p * z_cs + c);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float sc = scale[c + e], sh = shift[c + e];
+            const float g = (zz[e] * sc + sh > 0.f) ? d[e] : 0.f;
+            const float zh = (zz[e] - mean[c + e]) * invstd[c + e];
+            const float mg = (float)(sums[c + e] / count), mgz = (float)(sums[C + c + e] / count);
+            o[e] = sc * (g - mg - zh * mgz);  // scale = gamma * invstd
+        }
+        store_split(dz + p * dz_cs + c, dz_lo ? dz_lo + p * dz_cs + c : nullptr, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+// g = dy * (y > 0) * mask[pixel]  -> split store        (bias+ReLU convs; mask multiply backward)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, int dy_cs,
+                                                       const float* __restrict__ y, int y_cs,
+                                                       const float* __restrict__ mask, float* __restrict__ g,
+                                                       float* __restrict__ g_lo, int g_cs, long long npix, int C) {
+    const int q = C >> 2;
+    const long long total = npix * q;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / q;
+        const int c = (int)(i - p * q) * 4;
+        float4 d = *reinterpret_cast<const float4*>(dy + p * dy_cs + c);
+        if (y != nullptr) {
+            const float4 v = *reinterpret_cast<const float4*>(y + p * y_cs + c);
+            d.x = v.x > 0.f ? d.x : 0.f;
+            d.y = v.y > 0.f ? d.y : 0.f;
+            d.z = v.z > 0.f ? d.z : 0.f;
+            d.w = v.w > 0.f ? d.w : 0.f;
+        }
+        if (mask != nullptr) {
+            const float m = mask[p];
+            d.x *= m; d.y *= m; d.z *= m; d.w *= m;
+        }
+        store_split(g + p * g_cs + c, g_lo ? g_lo + p * g_cs + c : nullptr, d);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- count_nonzero
+__global__ void count_nonzero_kernel(const float* __restrict__ x, long long n4, unsigned long long* __restrict__ out) {
+    unsigned int cnt = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        cnt += (v.x != 0.f) + (v.y != 0.f) + (v.z != 0.f) + (v.w != 0.f);
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
+static int ew_grid(long long total) {
+    long long b = (total + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace a2x
+
+using namespace a2x;
+
+extern "C" {
+
+int a2x_split_tf32(const float* x, long long n, float* hi, float* lo, a2x_stream_t stream) {
+    A2X_REQUIRE(x && hi && lo && n % 4 == 0, "split_tf32: bad args (n must be a multiple of 4)");
+    split_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, n / 4, hi, lo);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int check_c(int C) {
+    if (C <= 0 || C % 4 != 0 || C > 1024) {
+        set_error("channel count %d must be a multiple of 4 in (0, 1024]", C);
+        return 1;
+    }
+    return 0;
+}
+
+int a2x_channel_stats(const float* x, int x_cs, long long npix, int C, double* sums, a2x_stream_t stream) {
+    if (int r = check_c(C)) return r;
+    A2X_REQUIRE(x && sums && npix > 0, "channel_stats: bad args");
+    const int ppb = 256 / (C / 4);
+    long long blocks = (npix + ppb - 1) / ppb;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    channel_reduce_kernel<0><<<(int)blocks, 256, 2 * 256 * 4 * sizeof(float), (cudaStream_t)stream>>>(
+        x, x_cs, nullptr, 0, nullptr, nullptr, nullptr, nullptr, npix, C, sums);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
+                    int n_updates, float* running_mean, float* running_var, int C, float* scale, float* shift,
+                    float* mean_out, float* invstd_out, a2x_stream_t stream) {
+    A2X_REQUIRE(sums && scale && shift && C > 0 && count > 0, "bn_finalize: bad args");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, gamma, beta, eps, momentum,
+                                                                        n_updates, running_mean, running_var, C, scale,
+                                                                        shift, mean_out, invstd_out);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, int C, float* scale, float* shift, a2x_stream_t stream) {
+    A2X_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && C > 0, "bn_eval_affine: bad args");
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var,
+                                                                           eps, C, scale, shift);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_affine_act(const float* x, int x_cs, const float* scale, const float* shift, int relu, const float* mask,
+                   float* y, float* y_lo, int y_cs, long long npix, int C, a2x_stream_t stream) {
+    if (int r = check_c(C)) return r;
+    A2X_REQUIRE(x && y && npix > 0, "affine_act: bad args");
+    affine_act_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_cs, scale, shift, relu, mask, y,
+                                                                               y_lo, y_cs, npix, C);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, long long npix, int C, double* sums,
+                           a2x_stream_t stream) {
+    if (int r = check_c(C)) return r;
+    A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && npix > 0, "bn_relu_bwd_reduce: bad args");
+    const int ppb = 256 / (C / 4);
+    long long blocks = (npix + ppb - 1) / ppb;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    channel_reduce_kernel<1><<<(int)blocks, 256, 2 * 256 * 4 * sizeof(float), (cudaStream_t)stream>>>(
+        dy, dy_cs, z, z_cs, scale, shift, mean, invstd, npix, C, sums);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, const double* sums, double count, float* dz,
+                          float* dz_lo, int dz_cs, long long npix, int C, float* dgamma, float* dbeta,
+                          int accumulate_param_grads, a2x_stream_t stream) {
+    if (int r = check_c(C)) return r;
+    A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && dz && npix > 0, "bn_relu_bwd_apply: bad args");
+    bn_relu_bwd_apply_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        dy, dy_cs, z, z_cs, scale, shift, mean, invstd, sums, count, dz, dz_lo, dz_cs, npix, C);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    if (dgamma || dbeta) {
+        bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta,
+                                                                                accumulate_param_grads);
+        A2X_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int a2x_relu_bwd(const float* dy, int dy_cs, const float* y, int y_cs, const float* mask, float* g, float* g_lo,
+                 int g_cs, long long npix, int C, a2x_stream_t stream) {
+    if (int r = check_c(C)) return r;
+    A2X_REQUIRE(dy && g && npix > 0, "relu_bwd: bad args");
+    relu_bwd_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dy, dy_cs, y, y_cs, mask, g, g_lo, g_cs,
+                                                                             npix, C);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_sums_to_float(const double* sums, int C, float* out, int accumulate, a2x_stream_t stream) {
+    A2X_REQUIRE(sums && out && C > 0, "sums_to_float: bad args");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, nullptr, out, accumulate);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_count_nonzero(const float* x, long long n, unsigned long long* out, a2x_stream_t stream) {
+    A2X_REQUIRE(x && out && n % 4 == 0, "count_nonzero: bad args");
+    A2X_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    count_nonzero_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, n / 4, out);
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -21,8 +21,8 @@ namespace a2x {
 constexpr int TG_BM = 128;         // pixels per tile (UMMA M)
 constexpr int TG_KC = 32;          // fp32 elements per k-chunk = one 128-byte swizzle row
 constexpr int TG_A_BYTES = TG_BM * 128;
-constexpr int TG_MAX_TAPS = 9;
-constexpr int TG_MAX_MAPS = 4;
+constexpr int TG_MAX_TAPS = 27;  // 9 window taps x 3 split products (hi*hi, lo*hi, hi*lo) in 3xTF32 mode
+constexpr int TG_MAX_MAPS = 8;   // 4 parity views x {hi, lo}
 
 struct TgTap {
     int16_t map;   // which A tensor map
@@ -45,6 +45,7 @@ struct TgParams {
     int tiles_h, tiles_w;
     // output addressing (elements)
     float* out;
+    float* out_lo;  // if non-null: out = tf32_rn(v), out_lo = v - out (operand split for a following 3xTF32 GEMM)
     long long osn, osh, osw;
     int sub_c, sub_s;          // column -> (sub, c) split for deconv scatter; sub_c >= total cols otherwise
     long long sub_sh, sub_sw;
@@ -197,8 +198,24 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
+                if (p.out_lo != nullptr) {
+                    float4* l4 = reinterpret_cast<float4*>(p.out_lo + (o - p.out));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 8; ++i) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            hi[e] = tf32_rn(v[4 * i + e]);
+                            lo[e] = v[4 * i + e] - hi[e];
+                        }
+                        o4[i] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        l4[i] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
             }
         }
     }

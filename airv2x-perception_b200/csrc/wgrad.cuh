@@ -22,11 +22,12 @@ constexpr int WG_PIX = 32;                  // pixels per k-step
 constexpr int WG_ATOM_BYTES = WG_PIX * 128;  // one (32 px x 32 ch) atom
 
 struct WgParams {
-    CUtensorMap amap;
-    CUtensorMap bmap[TG_MAX_MAPS];
+    CUtensorMap amap[2];            // [0] = hi (or the only) plane, [1] = lo plane (3xTF32 split mode)
+    CUtensorMap bmap[TG_MAX_MAPS];  // base views first, then their lo twins at +nmaps_b
     TgTap taps[TG_MAX_TAPS];
     int ntaps;
-    int ca, cb;  // channel counts (multiples of 32)
+    int nmaps_b;  // number of base B views (lo twin of view m is m + nmaps_b)
+    int ca, cb;   // channel counts (multiples of 32)
     int n_img, tiles_h, tiles_w, tw_log2;  // 32-pixel tiles: (32 >> tw_log2) rows x (1 << tw_log2) cols
     int tiles_per_cta;
     int n_tiles_b;  // number of BN-wide column tiles
@@ -36,10 +37,13 @@ struct WgParams {
     uint32_t layout;                // UMMA smem layout type (1 = SWIZZLE_128B_BASE32B)
 };
 
-template <int BN, int TPC, int STAGES>
+template <int BN, int TPC, int STAGES, bool SPLIT>
 struct WgSmem {
-    static constexpr int A_BYTES = 4 * WG_ATOM_BYTES;
-    static constexpr int B_BYTES = TPC * (BN / 32) * WG_ATOM_BYTES;
+    static constexpr int NP = SPLIT ? 2 : 1;  // operand planes (hi, lo)
+    static constexpr int A_PLANE = 4 * WG_ATOM_BYTES;
+    static constexpr int B_PLANE = TPC * (BN / 32) * WG_ATOM_BYTES;
+    static constexpr int A_BYTES = NP * A_PLANE;
+    static constexpr int B_BYTES = NP * B_PLANE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
@@ -52,9 +56,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  : "memory");
 }
 
-template <int BN, int TPC, int STAGES>
+template <int BN, int TPC, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgParams p) {
-    using L = WgSmem<BN, TPC, STAGES>;
+    using L = WgSmem<BN, TPC, STAGES, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
         if (elect_one()) {
             const int TW = 1 << p.tw_log2;
             const int TH = WG_PIX >> p.tw_log2;
-            const uint32_t tx_bytes = (a_atoms + TPC * b_atoms) * WG_ATOM_BYTES;
+            const uint32_t tx_bytes = L::NP * (a_atoms + TPC * b_atoms) * WG_ATOM_BYTES;
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -108,13 +112,17 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 uint8_t* sa = smem + stage * L::STAGE_BYTES;
                 uint8_t* sb = sa + L::A_BYTES;
                 mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                for (int a = 0; a < a_atoms; ++a)
-                    tma_load_5d(sa + a * WG_ATOM_BYTES, &p.amap, &full_bar[stage], m0 + a * 32, w0, 0, h0, img);
-                for (int tt = 0; tt < TPC; ++tt) {
-                    const TgTap tp = p.taps[tap0 + tt];
-                    for (int b = 0; b < b_atoms; ++b)
-                        tma_load_5d(sb + (tt * (BN / 32) + b) * WG_ATOM_BYTES, &p.bmap[tp.map], &full_bar[stage],
-                                    n0 + b * 32, w0 + tp.dw, tp.dx, h0 + tp.dh, img);
+                for (int pl = 0; pl < L::NP; ++pl) {
+                    for (int a = 0; a < a_atoms; ++a)
+                        tma_load_5d(sa + pl * L::A_PLANE + a * WG_ATOM_BYTES, &p.amap[pl], &full_bar[stage],
+                                    m0 + a * 32, w0, 0, h0, img);
+                    for (int tt = 0; tt < TPC; ++tt) {
+                        const TgTap tp = p.taps[tap0 + tt];
+                        for (int b = 0; b < b_atoms; ++b)
+                            tma_load_5d(sb + pl * L::B_PLANE + (tt * (BN / 32) + b) * WG_ATOM_BYTES,
+                                        &p.bmap[tp.map + pl * p.nmaps_b], &full_bar[stage], n0 + b * 32, w0 + tp.dw,
+                                        tp.dx, h0 + tp.dh, img);
+                    }
                 }
                 if (++stage == STAGES) {
                     stage = 0;
@@ -133,13 +141,21 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
                 const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < WG_PIX / 8; ++k) {  // K = 8 pixel rows per MMA = one 1024-byte swizzle group
+                for (int k = 0; k < WG_PIX / 8; ++k) {  // K = 8 pixel rows per MMA (two 4-row swizzle groups)
                     const uint64_t ad = make_smem_desc_sw128(sa + k * 1024, p.lbo_bytes, p.sbo_bytes, p.layout);
 #pragma unroll
                     for (int tt = 0; tt < TPC; ++tt) {
-                        const uint64_t bd = make_smem_desc_sw128(sb + tt * (BN / 32) * WG_ATOM_BYTES + k * 1024,
-                                                                 p.lbo_bytes, p.sbo_bytes, p.layout);
+                        const uint32_t boff = tt * (BN / 32) * WG_ATOM_BYTES + k * 1024;
+                        const uint64_t bd = make_smem_desc_sw128(sb + boff, p.lbo_bytes, p.sbo_bytes, p.layout);
                         umma_tf32(tmem_base + tt * BN, ad, bd, idesc, (it | k) != 0);
+                        if (SPLIT) {  // + A_lo * B_hi + A_hi * B_lo
+                            const uint64_t adl =
+                                make_smem_desc_sw128(sa + L::A_PLANE + k * 1024, p.lbo_bytes, p.sbo_bytes, p.layout);
+                            const uint64_t bdl =
+                                make_smem_desc_sw128(sb + L::B_PLANE + boff, p.lbo_bytes, p.sbo_bytes, p.layout);
+                            umma_tf32(tmem_base + tt * BN, adl, bd, idesc, 1);
+                            umma_tf32(tmem_base + tt * BN, ad, bdl, idesc, 1);
+                        }
                     }
                 }
                 umma_commit(&empty_bar[stage]);

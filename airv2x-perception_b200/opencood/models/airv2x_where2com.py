@@ -1,0 +1,233 @@
+"""`opencood.models.airv2x_where2com.Airv2xWhere2com` on the B200 kernels.
+
+Same registry name / class name / constructor (`cls(hypes["model"]["args"])`), same `hypes_yaml` keys, same
+`state_dict` key names and shapes, same `forward(data_dict) -> {"psm","rm","obj","mask","com","comm_rate"}` as
+opencood/models/airv2x_where2com.py:20-179 of the reference, so `train_utils.create_model`
+(opencood/tools/train_utils.py:288-325) dispatches here unchanged once `install()` has registered the module.
+The torch.nn layers below are parameter containers only (names + default init); their forward is never called.
+There is no CPU / eager fallback: without a CUDA device or the built library the forward raises.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ...w2c_engine import AGENT_TYPES, HEAD_PAD, TYPE_PREFIX, W2CEngine
+
+
+class _PFNParams(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear = nn.Linear(cin, cout, bias=False)
+        self.norm = nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01)
+
+
+class _PillarVFEParams(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        assert cfg["use_norm"] and cfg["use_absolute_xyz"] and not cfg["with_distance"] and list(cfg["num_filters"]) == [64], \
+            "only the airv2x PillarVFE configuration (10 -> 64, BN, absolute xyz) is implemented"
+        self.pfn_layers = nn.ModuleList([_PFNParams(10, 64)])
+
+
+def _backbone_params(cfg, cin):
+    blocks, deblocks = nn.ModuleList(), nn.ModuleList()
+    chans = [cin] + list(cfg["num_filters"])[:-1]
+    for i, (ln, st, cf) in enumerate(zip(cfg["layer_nums"], cfg["layer_strides"], cfg["num_filters"])):
+        layers = [nn.ZeroPad2d(1), nn.Conv2d(chans[i], cf, 3, stride=st, padding=0, bias=False),
+                  nn.BatchNorm2d(cf, eps=1e-3, momentum=0.01), nn.ReLU()]
+        for _ in range(ln):
+            layers += [nn.Conv2d(cf, cf, 3, padding=1, bias=False), nn.BatchNorm2d(cf, eps=1e-3, momentum=0.01), nn.ReLU()]
+        blocks.append(nn.Sequential(*layers))
+        us, uf = cfg["upsample_strides"][i], cfg["num_upsample_filter"][i]
+        deblocks.append(nn.Sequential(nn.ConvTranspose2d(cf, uf, us, stride=us, bias=False),
+                                      nn.BatchNorm2d(uf, eps=1e-3, momentum=0.01), nn.ReLU()))
+    m = nn.Module()
+    m.blocks, m.deblocks = blocks, deblocks
+    return m
+
+
+def _shrink_params(cfg):
+    m = nn.Module()
+    m.layers = nn.ModuleList()
+    cin = cfg["input_dim"]
+    for k, d, s, p in zip(cfg["kernal_size"], cfg["dim"], cfg["stride"], cfg["padding"]):
+        dc = nn.Module()
+        dc.double_conv = nn.Sequential(nn.Conv2d(cin, d, k, stride=s, padding=p), nn.ReLU(inplace=True),
+                                       nn.Conv2d(d, d, 3, padding=1), nn.ReLU(inplace=True))
+        m.layers.append(dc)
+        cin = d
+    return m
+
+
+def _comm_params(cfg):
+    fusion = nn.Module()
+    comm = nn.Module()
+    if "gaussian_smooth" in cfg["communication"]:
+        k = cfg["communication"]["gaussian_smooth"]["k_size"]
+        sigma = cfg["communication"]["gaussian_smooth"]["c_sigma"]
+        comm.gaussian_filter = nn.Conv2d(1, 1, k, stride=1, padding=(k - 1) // 2)
+        c = k // 2
+        ys, xs = np.mgrid[0 - c:k - c, 0 - c:k - c]
+        g = 1 / (2 * np.pi * sigma) * np.exp(-(np.square(ys) + np.square(xs)) / (2 * np.square(sigma)))
+        comm.gaussian_filter.weight.data = torch.Tensor(g).unsqueeze(0).unsqueeze(0)
+        comm.gaussian_filter.bias.data.zero_()
+    fusion.naive_communication = comm
+    return fusion
+
+
+class _Step(torch.autograd.Function):
+    """Autograd boundary: inputs are all trainable parameters, outputs are the NHWC head logits."""
+
+    @staticmethod
+    def forward(ctx, model, lidar, layout, k_list, names, *params):
+        P = model._param_dict()
+        heads, aux = model.engine.forward(P, lidar, layout, model.training, k_list)
+        ctx.model = model
+        ctx.names = names
+        ctx.aux = aux
+        model._last_aux = aux
+        return heads
+
+    @staticmethod
+    def backward(ctx, dheads):
+        model = ctx.model
+        P = model._param_dict()
+        grads = {n: torch.zeros_like(P[n]) for n in ctx.names}
+        model.engine.backward(P, dheads.contiguous(), grads)
+        return (None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+class Airv2xWhere2com(nn.Module):
+    def __init__(self, args, precision="tf32x3"):
+        super().__init__()
+        self.args = args
+        self.collaborators = args["collaborators"]
+        self.active_sensors = args["active_sensors"]
+        self.veh_models, self.rsu_models, self.drone_models = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        for t in AGENT_TYPES:
+            if t not in self.collaborators:
+                continue
+            for m in args[t]["modalities"]:
+                if m != "lidar":
+                    raise NotImplementedError("modality %r is outside the B200 hot path (lidar only)" % m)
+                enc = nn.Sequential(_PillarVFEParams(args[t]["lidar"]["pillar_vfe"]), nn.Identity())
+                getattr(self, TYPE_PREFIX[t]).append(enc)
+        mf = args["modality_fusion"]
+        self.backbone = _backbone_params(mf["base_bev_backbone"], 64)
+        self.shrink_flag = bool(mf.get("shrink_header", {}).get("use", False))
+        if self.shrink_flag:
+            self.shrink_conv = _shrink_params(mf["shrink_header"])
+        self.compression = mf["compression"] > 0
+        self.fusion_net = _comm_params(args["where2com_fusion"])
+        self.multi_scale = args["where2com_fusion"]["multi_scale"]
+        self.outC = args["outC"]
+        if args["task"] != "det":
+            raise NotImplementedError("task %r is outside the B200 hot path (det only)" % args["task"])
+        self.cls_head = nn.Conv2d(self.outC, args["anchor_number"] * args["num_class"], kernel_size=1)
+        self.reg_head = nn.Conv2d(self.outC, 7 * args["anchor_number"], kernel_size=1)
+        if args["obj_head"]:
+            self.obj_head = nn.Conv2d(self.outC, args["anchor_number"], kernel_size=1)
+        self.precision = precision
+        self._engine = None
+        self._last_aux = None
+        if args.get("backbone_fix", False):
+            self.backbone_fix()
+
+    def backbone_fix(self):
+        for n, p in self.named_parameters():
+            if not n.startswith("fusion_net"):
+                p.requires_grad = False
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def engine(self):
+        if self._engine is None:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("Airv2xWhere2com (B200) needs its parameters on a CUDA device; there is no CPU path")
+            self._engine = W2CEngine(self.args, dev, self.precision)
+        return self._engine
+
+    def _param_dict(self):
+        d = {n: p.data for n, p in self.named_parameters()}
+        d.update({n: b for n, b in self.named_buffers()})
+        return d
+
+    def _layout(self, data_dict, device):
+        """Scene-major agent order (vehicles, RSUs, drones per scene): airv2x_base_model.py:179-248."""
+        rl, idxs = {}, {}
+        for t in AGENT_TYPES:
+            if t in self.collaborators and len(data_dict[t]["batch_idxs"]) > 0 and \
+                    data_dict[t].get("batch_merged_lidar_features_torch") is not None:
+                r = data_dict[t]["record_len"]
+                rl[t] = [int(v) for v in (r.tolist() if torch.is_tensor(r) else r)]
+                idxs[t] = list(data_dict[t]["batch_idxs"])
+        B = max(len(v) for v in idxs.values())
+        starts = {}
+        for t in rl:
+            pos, st = 0, {}
+            for b in idxs[t]:
+                st[b] = pos
+                pos += rl[t][b]
+            starts[t] = st
+        amap = {t: [0] * sum(rl[t][b] for b in idxs[t]) for t in rl}
+        record_len, row = [], 0
+        for b in range(B):
+            n_b = 0
+            for t in AGENT_TYPES:
+                if t in rl and b in idxs[t]:
+                    for j in range(rl[t][b]):
+                        amap[t][starts[t][b] + j] = row
+                        row += 1
+                    n_b += rl[t][b]
+            record_len.append(n_b)
+        first = next(iter(rl))
+        nx, ny, _ = [int(v) for v in self.args[first]["lidar"]["point_pillar_scatter"]["grid_size"]]
+        scene_start = np.concatenate([[0], np.cumsum(record_len)[:-1]]).astype(np.int32)
+        return dict(n_total=row, nx=nx, ny=ny, record_len=record_len,
+                    agent_map={t: torch.tensor(v, dtype=torch.int32, device=device) for t, v in amap.items()},
+                    scene_start=torch.tensor(scene_start, dtype=torch.int32, device=device),
+                    scene_len=torch.tensor(record_len, dtype=torch.int32, device=device))
+
+    def _lidar(self, data_dict, device, layout):
+        out = {}
+        for t in layout["agent_map"]:
+            d = data_dict[t]["batch_merged_lidar_features_torch"]
+            out[t] = {"voxel_features": d["voxel_features"].to(device=device, dtype=torch.float32).contiguous(),
+                      "voxel_num_points": d["voxel_num_points"].to(device=device, dtype=torch.int32).contiguous(),
+                      "voxel_coords": d["voxel_coords"].to(device=device, dtype=torch.int32).contiguous()}
+        return out
+
+    # ------------------------------------------------------------------ reference-facing API
+    def forward(self, data_dict):
+        dev = next(self.parameters()).device
+        layout = self._layout(data_dict, dev)
+        lidar = self._lidar(data_dict, dev, layout)
+        B = len(layout["record_len"])
+        k_list = None
+        if self.training and not self.engine.fully:
+            hw = None  # drawn inside the engine from Python `random`, same call order as the reference
+        names = [n for n, p in self.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
+        params = [p for n, p in self.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
+        if self.training and torch.is_grad_enabled():
+            heads = _Step.apply(self, lidar, layout, k_list, names, *params)
+        else:
+            heads, self._last_aux = self.engine.forward(self._param_dict(), lidar, layout, self.training, k_list)
+        return self._output_dict(heads, layout)
+
+    def _output_dict(self, heads, layout):
+        A, K = self.args["anchor_number"], self.args["num_class"]
+        nc, nr = A * K, 7 * A
+        nchw = heads.permute(0, 3, 1, 2)  # logical NCHW views of the NHWC logits (values identical)
+        out = {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A]}
+        aux = self._last_aux
+        rl = torch.tensor(layout["record_len"], dtype=torch.float32, device=heads.device)
+        if self.engine.fully:
+            com = torch.tensor(1, device=heads.device)
+        else:
+            com = (aux["ones"] / (rl * aux["hw"])).sum() / len(layout["record_len"])
+        out.update({"mask": 0, "com": com, "comm_rate": int(aux["comm_rate"].item())})
+        return out

@@ -30,18 +30,22 @@ def _f32(t):
 
 
 # ----------------------------------------------------------------------------- weights
-def pack_conv_weight(w, cout_pad=None):
-    """OIHW -> ([kk][cout_pad][cin], [kk][cin][cout_pad])"""
+def pack_conv_weight(w, cout_pad=None, out=None):
+    """OIHW -> (wf [2][kk][cout_pad][cin], wd [2][kk][cin][cout_pad]); plane 0 = tf32_rn(w), plane 1 = residual."""
     cout, cin, k, _ = w.shape
     cout_pad = cout_pad or cout
-    wf = torch.empty(k * k, cout_pad, cin, device=w.device, dtype=torch.float32)
-    wd = torch.empty(k * k, cin, cout_pad, device=w.device, dtype=torch.float32)
+    if out is None:
+        wf = torch.empty(2, k * k, cout_pad, cin, device=w.device, dtype=torch.float32)
+        wd = torch.empty(2, k * k, cin, cout_pad, device=w.device, dtype=torch.float32)
+    else:
+        wf, wd = out
     call("a2x_pack_conv_weight", _ptr(_f32(w.contiguous())), c_int(cout), c_int(cin), c_int(k), c_int(cout_pad),
          _ptr(wf), _ptr(wd), stream_ptr())
     return wf, wd
 
 
 def unpack_conv_wgrad(dwp, cout, cin, k, out=None, accumulate=False):
+    """packed [kk][cout_pad][cin] -> OIHW"""
     cout_pad = dwp.shape[1]
     if out is None:
         out = torch.empty(cout, cin, k, k, device=dwp.device, dtype=torch.float32)
@@ -50,11 +54,14 @@ def unpack_conv_wgrad(dwp, cout, cin, k, out=None, accumulate=False):
     return out
 
 
-def pack_deconv_weight(w):
-    """[cin][cout][s][s] -> ([(ij,co)][ci], [ij][ci][co])"""
+def pack_deconv_weight(w, out=None):
+    """[cin][cout][s][s] -> (wf [2][1][(ij,co)][ci], wd [2][ss][ci][co])"""
     cin, cout, s, _ = w.shape
-    wf = torch.empty(s * s * cout, cin, device=w.device, dtype=torch.float32)
-    wd = torch.empty(s * s, cin, cout, device=w.device, dtype=torch.float32)
+    if out is None:
+        wf = torch.empty(2, 1, s * s * cout, cin, device=w.device, dtype=torch.float32)
+        wd = torch.empty(2, s * s, cin, cout, device=w.device, dtype=torch.float32)
+    else:
+        wf, wd = out
     call("a2x_pack_deconv_weight", _ptr(_f32(w.contiguous())), c_int(cin), c_int(cout), c_int(s), _ptr(wf), _ptr(wd),
          stream_ptr())
     return wf, wd
@@ -68,70 +75,240 @@ def unpack_deconv_wgrad(dwp, cin, cout, s, out=None, accumulate=False):
     return out
 
 
-# ----------------------------------------------------------------------------- conv
-def conv2d_fwd(x, wf, k, stride, out=None, scale=None, shift=None, relu=False):
+# ============================================================================= split-plane activations
+class Act:
+    """An NHWC activation as GEMM operand: `hi` (+ optional `lo`) planes. hi + lo is the fp32 value."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(shape, device, split):
+        if split:
+            t = torch.empty((2,) + tuple(shape), device=device, dtype=torch.float32)
+            return Act(t[0], t[1])
+        return Act(torch.empty(tuple(shape), device=device, dtype=torch.float32))
+
+    @staticmethod
+    def zeros(shape, device, split):
+        if split:
+            t = torch.zeros((2,) + tuple(shape), device=device, dtype=torch.float32)
+            return Act(t[0], t[1])
+        return Act(torch.zeros(tuple(shape), device=device, dtype=torch.float32))
+
+    def value(self):
+        return self.hi if self.lo is None else self.hi + self.lo
+
+    def slice_c(self, c0, c1):
+        return Act(self.hi[..., c0:c1], None if self.lo is None else self.lo[..., c0:c1])
+
+    def narrow_n(self, n0, n):
+        return Act(self.hi[n0:n0 + n], None if self.lo is None else self.lo[n0:n0 + n])
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+
+def split_tf32(x):
+    x = x.contiguous()
+    out = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.float32)
+    call("a2x_split_tf32", _ptr(x), ctypes.c_longlong(x.numel()), _ptr(out[0]), _ptr(out[1]), stream_ptr())
+    return Act(out[0], out[1])
+
+
+def _lo(a):
+    return _ptr(a.lo) if a.lo is not None else _ptr(None)
+
+
+# split-aware conv family ------------------------------------------------------------------------------------
+def conv_fwd(x, wf, k, stride, out, scale=None, shift=None, relu=False):
+    """x, out: Act. wf: packed [2][kk][cout][cin]."""
     n, h, w, cin = x.shape
-    cout = wf.shape[1]
-    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
-    if out is None:
-        out = torch.empty(n, ho, wo, cout, device=x.device, dtype=torch.float32)
+    cout = wf.shape[2]
     sh = _shape(n, h, w, cin, cout, k, stride)
-    call("a2x_conv2d_fwd", ctypes.byref(sh), _ptr(_f32(x)), c_int(_cs(x)), _ptr(wf), _ptr(out), c_int(_cs(out)),
-         _ptr(scale), _ptr(shift), c_int(int(relu)), stream_ptr())
+    call("a2x_conv2d_fwd", ctypes.byref(sh), _ptr(x.hi), _lo(x), c_int(_cs(x.hi)), _ptr(wf), _ptr(out.hi), _lo(out),
+         c_int(_cs(out.hi)), _ptr(scale), _ptr(shift), c_int(int(relu)), stream_ptr())
     return out
 
 
-def conv2d_dgrad(dy, wd, k, stride, h, w, out=None, accumulate=False):
-    n, ho, wo, cout = dy.shape
-    cin = wd.shape[1]
-    if out is None:
-        out = torch.empty(n, h, w, cin, device=dy.device, dtype=torch.float32)
+def conv_dgrad(dy, wd, k, stride, dx, accumulate=False):
+    """dy: Act; dx: plain NHWC tensor [n,h,w,cin]; wd packed [2][kk][cin][cout]."""
+    n, h, w, cin = dx.shape
+    cout = dy.shape[3]
     sh = _shape(n, h, w, cin, cout, k, stride)
-    call("a2x_conv2d_dgrad", ctypes.byref(sh), _ptr(_f32(dy)), c_int(_cs(dy)), _ptr(wd), _ptr(out), c_int(_cs(out)),
-         c_int(int(accumulate)), stream_ptr())
-    return out
+    call("a2x_conv2d_dgrad", ctypes.byref(sh), _ptr(dy.hi), _lo(dy), c_int(_cs(dy.hi)), _ptr(wd), _ptr(dx),
+         c_int(_cs(dx)), c_int(int(accumulate)), stream_ptr())
+    return dx
 
 
-def conv2d_wgrad(x, dy, k, stride, out=None):
-    """returns packed [kk][cout][cin] (accumulates into `out` if given)"""
+def conv_wgrad(x, dy, k, stride, dwp):
+    """x, dy: Act (both split or both single); dwp: zeroed packed [kk][cout][cin]."""
     n, h, w, cin = x.shape
     cout = dy.shape[3]
-    if out is None:
-        out = torch.zeros(k * k, cout, cin, device=x.device, dtype=torch.float32)
     sh = _shape(n, h, w, cin, cout, k, stride)
-    call("a2x_conv2d_wgrad", ctypes.byref(sh), _ptr(_f32(x)), c_int(_cs(x)), _ptr(_f32(dy)), c_int(_cs(dy)), _ptr(out),
-         stream_ptr())
-    return out
+    both = x.lo is not None and dy.lo is not None
+    call("a2x_conv2d_wgrad", ctypes.byref(sh), _ptr(x.hi), _lo(x) if both else _ptr(None), c_int(_cs(x.hi)), _ptr(dy.hi),
+         _lo(dy) if both else _ptr(None), c_int(_cs(dy.hi)), _ptr(dwp), stream_ptr())
+    return dwp
 
 
-def deconv_fwd(x, wf, cout, s, out=None, scale=None, shift=None, relu=False):
+def deconv_fwd(x, wf, cout, s, out, scale=None, shift=None, relu=False):
     n, h, w, cin = x.shape
-    if out is None:
-        out = torch.empty(n, h * s, w * s, cout, device=x.device, dtype=torch.float32)
     sh = _shape(n, h, w, cin, cout, s, s)
-    call("a2x_deconv_fwd", ctypes.byref(sh), _ptr(_f32(x)), c_int(_cs(x)), _ptr(wf), _ptr(out), c_int(_cs(out)),
-         _ptr(scale), _ptr(shift), c_int(int(relu)), stream_ptr())
+    call("a2x_deconv_fwd", ctypes.byref(sh), _ptr(x.hi), _lo(x), c_int(_cs(x.hi)), _ptr(wf), _ptr(out.hi), _lo(out),
+         c_int(_cs(out.hi)), _ptr(scale), _ptr(shift), c_int(int(relu)), stream_ptr())
     return out
 
 
-def deconv_dgrad(dy, wd, s, out=None, accumulate=False):
-    n, h2, w2, cout = dy.shape
-    cin = wd.shape[1]
-    h, w = h2 // s, w2 // s
-    if out is None:
-        out = torch.empty(n, h, w, cin, device=dy.device, dtype=torch.float32)
+def deconv_dgrad(dy, wd, s, dx, accumulate=False):
+    n, h, w, cin = dx.shape
+    cout = dy.shape[3]
     sh = _shape(n, h, w, cin, cout, s, s)
-    call("a2x_deconv_dgrad", ctypes.byref(sh), _ptr(_f32(dy)), c_int(_cs(dy)), _ptr(wd), _ptr(out), c_int(_cs(out)),
-         c_int(int(accumulate)), stream_ptr())
-    return out
+    call("a2x_deconv_dgrad", ctypes.byref(sh), _ptr(dy.hi), _lo(dy), c_int(_cs(dy.hi)), _ptr(wd), _ptr(dx),
+         c_int(_cs(dx)), c_int(int(accumulate)), stream_ptr())
+    return dx
 
 
-def deconv_wgrad(x, dy, s, out=None):
+def deconv_wgrad(x, dy, s, dwp):
     n, h, w, cin = x.shape
     cout = dy.shape[3]
-    if out is None:
-        out = torch.zeros(s * s, cin, cout, device=x.device, dtype=torch.float32)
     sh = _shape(n, h, w, cin, cout, s, s)
-    call("a2x_deconv_wgrad", ctypes.byref(sh), _ptr(_f32(x)), c_int(_cs(x)), _ptr(_f32(dy)), c_int(_cs(dy)), _ptr(out),
+    both = x.lo is not None and dy.lo is not None
+    call("a2x_deconv_wgrad", ctypes.byref(sh), _ptr(x.hi), _lo(x) if both else _ptr(None), c_int(_cs(x.hi)),
+         _ptr(dy.hi), _lo(dy) if both else _ptr(None), c_int(_cs(dy.hi)), _ptr(dwp), stream_ptr())
+    return dwp
+
+
+# BN / elementwise ---------------------------------------------------------------------------------------------
+c_ll = ctypes.c_longlong
+c_f = ctypes.c_float
+c_d = ctypes.c_double
+
+
+def _npix(t):
+    return t.shape[0] * t.shape[1] * t.shape[2]
+
+
+def channel_stats(x, sums):
+    call("a2x_channel_stats", _ptr(x), c_int(_cs(x)), c_ll(_npix(x)), c_int(x.shape[3]), _ptr(sums), stream_ptr())
+
+
+def bn_finalize(sums, count, gamma, beta, n_updates, rm, rv, scale, shift, mean, invstd, eps=1e-3, momentum=0.01):
+    call("a2x_bn_finalize", _ptr(sums), c_d(float(count)), _ptr(gamma), _ptr(beta), c_f(eps), c_f(momentum),
+         c_int(n_updates), _ptr(rm), _ptr(rv), c_int(scale.numel()), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
          stream_ptr())
+
+
+def bn_eval_affine(gamma, beta, rm, rv, scale, shift, eps=1e-3):
+    call("a2x_bn_eval_affine", _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), c_f(eps), c_int(scale.numel()), _ptr(scale),
+         _ptr(shift), stream_ptr())
+
+
+def affine_act(x, scale, shift, relu, out, mask=None):
+    """x: NHWC tensor; out: Act"""
+    call("a2x_affine_act", _ptr(x), c_int(_cs(x)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(mask), _ptr(out.hi),
+         _lo(out), c_int(_cs(out.hi)), c_ll(_npix(x)), c_int(x.shape[3]), stream_ptr())
     return out
+
+
+def bn_relu_bwd(dy, z, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, accumulate=False):
+    """dy, z: NHWC tensors; dz: Act; sums: zeroed [2C] double"""
+    npix, C = _npix(dy), dy.shape[3]
+    call("a2x_bn_relu_bwd_reduce", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift), _ptr(mean),
+         _ptr(invstd), c_ll(npix), c_int(C), _ptr(sums), stream_ptr())
+    call("a2x_bn_relu_bwd_apply", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift), _ptr(mean),
+         _ptr(invstd), _ptr(sums), c_d(float(npix)), _ptr(dz.hi), _lo(dz), c_int(_cs(dz.hi)), c_ll(npix), c_int(C),
+         _ptr(dgamma), _ptr(dbeta), c_int(int(accumulate)), stream_ptr())
+    return dz
+
+
+def relu_bwd(dy, y, out, mask=None):
+    """g = dy * (y > 0) * mask ; dy, y NHWC tensors (y may be None); out: Act"""
+    call("a2x_relu_bwd", _ptr(dy), c_int(_cs(dy)), _ptr(y), c_int(_cs(y) if y is not None else 0), _ptr(mask),
+         _ptr(out.hi), _lo(out), c_int(_cs(out.hi)), c_ll(_npix(dy)), c_int(dy.shape[3]), stream_ptr())
+    return out
+
+
+def sums_to_float(sums, C, out, accumulate=False):
+    call("a2x_sums_to_float", _ptr(sums), c_int(C), _ptr(out), c_int(int(accumulate)), stream_ptr())
+
+
+def count_nonzero(x, out_u64):
+    call("a2x_count_nonzero", _ptr(x), c_ll(x.numel()), _ptr(out_u64), stream_ptr())
+
+
+# PFN ------------------------------------------------------------------------------------------------------------
+class PfnGeom(ctypes.Structure):
+    _fields_ = [("voxel_x", c_f), ("voxel_y", c_f), ("voxel_z", c_f), ("x_offset", c_f), ("y_offset", c_f),
+                ("z_offset", c_f), ("nx", c_int), ("ny", c_int)]
+
+
+def pfn_geom(voxel_size, lidar_range, nx, ny):
+    """airv2x_pillar_vfe.py:84-89 (offsets computed in double like the reference, then cast to fp32)."""
+    vx, vy, vz = [float(v) for v in voxel_size]
+    return PfnGeom(vx, vy, vz, vx / 2 + lidar_range[0], vy / 2 + lidar_range[1], vz / 2 + lidar_range[2], nx, ny)
+
+
+def pfn_moments(vox, num, coords, geom, moments):
+    call("a2x_pfn_moments", _ptr(vox), _ptr(num), _ptr(coords), c_ll(vox.shape[0]), ctypes.byref(geom), _ptr(moments),
+         stream_ptr())
+
+
+def pfn_stats_finalize(moments, rows, w, gamma, beta, n_updates, rm, rv, scale, shift, mean, invstd, eps=1e-3,
+                       momentum=0.01):
+    call("a2x_pfn_stats_finalize", _ptr(moments), c_d(float(rows)), _ptr(w), _ptr(gamma), _ptr(beta), c_f(eps),
+         c_f(momentum), c_int(n_updates), _ptr(rm), _ptr(rv), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+         stream_ptr())
+
+
+def pfn_scatter(vox, num, coords, geom, w, scale, shift, agent_map, canvas, pillar_out=None, amax=None):
+    call("a2x_pfn_scatter", _ptr(vox), _ptr(num), _ptr(coords), c_ll(vox.shape[0]), ctypes.byref(geom), _ptr(w),
+         _ptr(scale), _ptr(shift), _ptr(agent_map), _ptr(canvas.hi), _lo(canvas), _ptr(pillar_out), _ptr(amax),
+         stream_ptr())
+
+
+def pfn_bwd(vox, num, coords, geom, w, scale, shift, mean, invstd, agent_map, dcanvas, amax, moments, rows, acc_ws, dw,
+            dgamma, dbeta, accumulate=False):
+    call("a2x_pfn_bwd", _ptr(vox), _ptr(num), _ptr(coords), c_ll(vox.shape[0]), ctypes.byref(geom), _ptr(w), _ptr(scale),
+         _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(agent_map), _ptr(dcanvas), _ptr(amax), _ptr(moments),
+         c_d(float(rows)), _ptr(acc_ws), _ptr(dw), _ptr(dgamma), _ptr(dbeta), c_int(int(accumulate)), stream_ptr())
+
+
+# communication / fusion -----------------------------------------------------------------------------------------
+def comm_confidence(psm, ncls, conf):
+    call("a2x_comm_confidence", _ptr(psm), c_int(_cs(psm)), c_int(ncls), c_ll(_npix(psm)), _ptr(conf), stream_ptr())
+
+
+def comm_smooth_mask(conf, gw, gb, ksz, n, h, w, thr, write_mask, smooth, mask):
+    call("a2x_comm_smooth_mask", _ptr(conf), _ptr(gw), _ptr(gb), c_int(ksz), c_int(n), c_int(h), c_int(w), c_f(thr),
+         c_int(int(write_mask)), _ptr(smooth), _ptr(mask), stream_ptr())
+
+
+def comm_topk_mask(smooth, n, hw, k_dev, mask):
+    call("a2x_comm_topk_mask", _ptr(smooth), c_int(n), c_int(hw), _ptr(k_dev), _ptr(mask), stream_ptr())
+
+
+def comm_rate_ego(mask, hw, n_scenes, scene_start, scene_len, ones):
+    call("a2x_comm_rate_ego", _ptr(mask), c_int(hw), c_int(n_scenes), _ptr(scene_start), _ptr(scene_len), _ptr(ones),
+         stream_ptr())
+
+
+def att_fuse_fwd(x, out):
+    """x: dense NHWC tensor [n_agents,h,w,c] of one scene; out: Act [1,h,w,c] (or [h,w,c])"""
+    n, h, w, c = x.shape
+    call("a2x_att_fuse_fwd", _ptr(x), c_int(n), c_int(h * w), c_int(c), _ptr(out.hi), _lo(out), stream_ptr())
+
+
+def att_fuse_bwd(x, dout, dx):
+    n, h, w, c = x.shape
+    call("a2x_att_fuse_bwd", _ptr(x), _ptr(dout), c_int(n), c_int(h * w), c_int(c), _ptr(dx), stream_ptr())
+
+
+def det_loss(heads, A, K, targets, pos, class_ids, cls_weight, reg_coe, npos_ws, dheads, loss3):
+    B, H, W, cs = heads.shape[0], heads.shape[1], heads.shape[2], _cs(heads)
+    call("a2x_det_loss", _ptr(heads), c_int(cs), c_int(B), c_ll(H * W), c_int(A), c_int(K), _ptr(targets), _ptr(pos),
+         _ptr(class_ids), c_f(cls_weight), c_f(reg_coe), _ptr(npos_ws), _ptr(dheads),
+         c_int(_cs(dheads) if dheads is not None else 0), _ptr(loss3), stream_ptr())

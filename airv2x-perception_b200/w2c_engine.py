@@ -1,0 +1,500 @@
+"""Host-side orchestration of the Where2comm hot path on the C-ABI kernels.
+
+One `W2CEngine` owns every activation / gradient buffer (allocated once per shape signature, so addresses are
+stable and the step can be captured in a CUDA graph) and issues the kernel sequence for
+
+    voxels -> PillarVFE+scatter -> BEV backbone -> shrink -> cls head (single-agent confidence)
+           -> communication mask -> multi-scale attention fusion -> deblocks -> shrink -> heads
+
+forward (eval or train-mode BatchNorm) and backward (all parameter gradients). torch is used only for device
+memory, streams and tiny parameter concatenations. Mirrors
+opencood/models/airv2x_where2com.py:117-179 and where2comm_modules/where2comm_fuse.py:198-263 with the redundant
+second backbone evaluation (airv2x_where2com.py:124) folded into a repeated running-stat update.
+"""
+import random
+
+import torch
+
+from . import ops
+from .ops import Act
+
+AGENT_TYPES = ("vehicle", "rsu", "drone")
+TYPE_PREFIX = {"vehicle": "veh_models", "rsu": "rsu_models", "drone": "drone_models"}
+HEAD_PAD = 32
+
+
+class W2CEngine:
+    def __init__(self, args, device, precision="tf32x3"):
+        assert precision in ("tf32x3", "tf32"), precision
+        self.args = args
+        self.device = torch.device(device)
+        self.split = precision == "tf32x3"
+        self.precision = precision
+        mf = args["modality_fusion"]
+        bb = mf["base_bev_backbone"]
+        self.layer_nums = list(bb["layer_nums"])
+        self.layer_strides = list(bb["layer_strides"])
+        self.num_filters = list(bb["num_filters"])
+        self.up_strides = list(bb["upsample_strides"])
+        self.up_filters = list(bb["num_upsample_filter"])
+        assert all(s == 2 for s in self.layer_strides), "backbone blocks must have stride 2"
+        assert len(self.up_strides) == len(self.layer_nums), "extra deblock not supported"
+        sh = mf["shrink_header"]
+        assert sh["use"] and list(sh["kernal_size"]) == [1] and list(sh["stride"]) == [1] and list(sh["padding"]) == [0], \
+            "only the airv2x shrink header (1x1 s1 + 3x3) is implemented"
+        assert not mf.get("compression", 0), "NaiveCompressor (compression > 0) is not implemented"
+        self.c_cat = sum(self.up_filters)
+        self.c_shrink = sh["dim"][0]
+        assert sh["input_dim"] == self.c_cat
+        self.A = args["anchor_number"]
+        self.K = args["num_class"]
+        self.n_head = self.A * self.K + 7 * self.A + (self.A if args["obj_head"] else 0)
+        assert args["obj_head"], "obj_head: false not implemented"
+        assert self.n_head <= HEAD_PAD
+        fa = args["where2com_fusion"]
+        assert fa["multi_scale"], "single-scale Where2comm not implemented"
+        self.fully = bool(fa["fully"])
+        self.comm = fa["communication"]
+        self.bufs = {}
+        self.saved = None
+        self._arena_off = 0
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name, shape, dtype=torch.float32):
+        key = (name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), device=self.device, dtype=dtype)
+            self.bufs[key] = t
+        return t
+
+    def _act(self, name, shape, split=None):
+        split = self.split if split is None else split
+        if split:
+            t = self._buf(name, (2,) + tuple(shape))
+            return Act(t[0], t[1])
+        return Act(self._buf(name, shape))
+
+    def _zeroed(self, name, nbytes_elems, dtype):
+        """A slice of a per-step arena that is zeroed once per step (sums, packed weight gradients)."""
+        arena = self.bufs.get(("arena", dtype))
+        off = self._arena_off_map.setdefault(dtype, 0)
+        need = off + nbytes_elems
+        if arena is None or arena.numel() < need:
+            # first pass discovers the size; grow and re-zero
+            new = torch.zeros(max(need * 2, 1 << 16), device=self.device, dtype=dtype)
+            self.bufs[("arena", dtype)] = new
+            arena = new
+        self._arena_off_map[dtype] = need
+        return arena[off:need]
+
+    def _begin_step(self):
+        self._arena_off_map = {}
+        for dt in (torch.float64, torch.float32):
+            a = self.bufs.get(("arena", dt))
+            if a is not None:
+                a.zero_()
+
+    # ------------------------------------------------------------------ weights
+    def _pack_weights(self, P):
+        W = {}
+        for i, ln in enumerate(self.layer_nums):
+            for k in range(ln + 1):
+                name = "backbone.blocks.%d.%d.weight" % (i, 1 + 3 * k)
+                w = P[name]
+                W[name] = ops.pack_conv_weight(w, out=(self._buf(name + ".wf", (2, 9, w.shape[0], w.shape[1])),
+                                                       self._buf(name + ".wd", (2, 9, w.shape[1], w.shape[0]))))
+            name = "backbone.deblocks.%d.0.weight" % i
+            w = P[name]
+            s = self.up_strides[i]
+            W[name] = ops.pack_deconv_weight(w, out=(self._buf(name + ".wf", (2, 1, s * s * w.shape[1], w.shape[0])),
+                                                     self._buf(name + ".wd", (2, s * s, w.shape[0], w.shape[1]))))
+        for idx, k in ((0, 1), (2, 3)):
+            name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
+            w = P[name]
+            W[name] = ops.pack_conv_weight(w, out=(self._buf(name + ".wf", (2, k * k, w.shape[0], w.shape[1])),
+                                                   self._buf(name + ".wd", (2, k * k, w.shape[1], w.shape[0]))))
+        hw = self._buf("heads.w", (HEAD_PAD, self.c_shrink, 1, 1))
+        hb = self._buf("heads.b", (HEAD_PAD,))
+        nc, nr = self.A * self.K, 7 * self.A
+        hw.zero_()
+        hb.zero_()
+        hw[:nc].copy_(P["cls_head.weight"])
+        hw[nc:nc + nr].copy_(P["reg_head.weight"])
+        hw[nc + nr:self.n_head].copy_(P["obj_head.weight"])
+        hb[:nc].copy_(P["cls_head.bias"])
+        hb[nc:nc + nr].copy_(P["reg_head.bias"])
+        hb[nc + nr:self.n_head].copy_(P["obj_head.bias"])
+        W["heads"] = ops.pack_conv_weight(hw, out=(self._buf("heads.wf", (2, 1, HEAD_PAD, self.c_shrink)),
+                                                   self._buf("heads.wd", (2, 1, self.c_shrink, HEAD_PAD))))
+        W["heads.bias"] = hb
+        return W
+
+    # ------------------------------------------------------------------ layers
+    def _bn_params(self, P, bn, training, z, n_updates, tag):
+        C = z.shape[3]
+        scale = self._buf(tag + ".scale", (C,))
+        shift = self._buf(tag + ".shift", (C,))
+        if not training:
+            ops.bn_eval_affine(P[bn + ".weight"], P[bn + ".bias"], P[bn + ".running_mean"], P[bn + ".running_var"],
+                               scale, shift)
+            return scale, shift, None, None
+        mean = self._buf(tag + ".mean", (C,))
+        invstd = self._buf(tag + ".invstd", (C,))
+        sums = self._zeroed(tag + ".sums", 2 * C, torch.float64)
+        ops.channel_stats(z, sums)
+        count = z.shape[0] * z.shape[1] * z.shape[2]
+        ops.bn_finalize(sums, count, P[bn + ".weight"], P[bn + ".bias"], n_updates, P[bn + ".running_mean"],
+                        P[bn + ".running_var"], scale, shift, mean, invstd)
+        return scale, shift, mean, invstd
+
+    def _conv_bn_relu(self, P, W, conv, bn, x, stride, training, n_updates, tag, record):
+        n, h, w, _ = x.shape
+        cout = P[conv].shape[0]
+        ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+        y = self._act(tag + ".y", (n, ho, wo, cout))
+        wf, _ = W[conv]
+        if not training:
+            scale, shift, _, _ = self._bn_params(P, bn, False, y.hi, 0, tag)
+            ops.conv_fwd(x, wf, 3, stride, y, scale=scale, shift=shift, relu=True)
+            return y
+        z = self._buf(tag + ".z", (n, ho, wo, cout))
+        ops.conv_fwd(x, wf, 3, stride, Act(z))
+        scale, shift, mean, invstd = self._bn_params(P, bn, True, z, n_updates, tag)
+        ops.affine_act(z, scale, shift, True, y)
+        if record is not None:
+            record.append(dict(kind="conv", conv=conv, bn=bn, x=x, z=z, y=y, stride=stride, scale=scale, shift=shift,
+                               mean=mean, invstd=invstd, tag=tag))
+        return y
+
+    def _block(self, P, W, i, x, training, n_updates, tag, record):
+        p = "backbone.blocks.%d" % i
+        x = self._conv_bn_relu(P, W, p + ".1.weight", p + ".2", x, 2, training, n_updates, "%s.b%d.0" % (tag, i), record)
+        for k in range(self.layer_nums[i]):
+            x = self._conv_bn_relu(P, W, "%s.%d.weight" % (p, 4 + 3 * k), "%s.%d" % (p, 5 + 3 * k), x, 1, training,
+                                   n_updates, "%s.b%d.%d" % (tag, i, k + 1), record)
+        return x
+
+    def _deblock(self, P, W, i, x, out_slice, training, n_updates, tag, record):
+        """ConvTranspose(k = s) + BN + ReLU written into a channel slice of the concat buffer."""
+        conv = "backbone.deblocks.%d.0.weight" % i
+        bn = "backbone.deblocks.%d.1" % i
+        s = self.up_strides[i]
+        cout = self.up_filters[i]
+        wf, _ = W[conv]
+        n, h, w, _ = x.shape
+        tg = "%s.d%d" % (tag, i)
+        if not training:
+            scale, shift, _, _ = self._bn_params(P, bn, False, out_slice.hi, 0, tg)
+            ops.deconv_fwd(x, wf, cout, s, out_slice, scale=scale, shift=shift, relu=True)
+            return
+        z = self._buf(tg + ".z", (n, h * s, w * s, cout))
+        ops.deconv_fwd(x, wf, cout, s, Act(z))
+        scale, shift, mean, invstd = self._bn_params(P, bn, True, z, n_updates, tg)
+        ops.affine_act(z, scale, shift, True, out_slice)
+        if record is not None:
+            record.append(dict(kind="deconv", conv=conv, bn=bn, x=x, z=z, y=out_slice, stride=s, scale=scale,
+                               shift=shift, mean=mean, invstd=invstd, tag=tg, level=i))
+
+    def _shrink_heads(self, P, W, cat, tag, heads_only_cls=False):
+        """shrink (1x1+bias+ReLU, 3x3+bias+ReLU) then the fused 1x1 heads (cls | reg | obj | pad) -> [n,h,w,32]."""
+        n, h, w, _ = cat.shape
+        y1 = self._act(tag + ".s1", (n, h, w, self.c_shrink))
+        y2 = self._act(tag + ".s2", (n, h, w, self.c_shrink))
+        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"][0], 1, 1, y1,
+                     shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
+        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"][0], 3, 1, y2,
+                     shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
+        heads = self._buf(tag + ".heads", (n, h, w, HEAD_PAD))
+        ops.conv_fwd(y2, W["heads"][0], 1, 1, Act(heads), shift=W["heads.bias"])
+        return y1, y2, heads
+
+    # ------------------------------------------------------------------ encoder (PillarVFE + scatter)
+    def _encode(self, P, lidar, layout, training, record):
+        n_total, ny, nx = layout["n_total"], layout["ny"], layout["nx"]
+        canvas = self._act("canvas", (n_total, ny, nx, 64))
+        canvas.hi.zero_()
+        if canvas.lo is not None:
+            canvas.lo.zero_()
+        for t in AGENT_TYPES:
+            if t not in lidar:
+                continue
+            vox, num, coords = lidar[t]["voxel_features"], lidar[t]["voxel_num_points"], lidar[t]["voxel_coords"]
+            la = self.args[t]["lidar"]
+            geom = ops.pfn_geom(la["voxel_size"], la["lidar_range"], nx, ny)
+            pre = TYPE_PREFIX[t] + ".0.0.pfn_layers.0"
+            w = P[pre + ".linear.weight"]
+            scale = self._buf("pfn.%s.scale" % t, (64,))
+            shift = self._buf("pfn.%s.shift" % t, (64,))
+            amap = layout["agent_map"][t]
+            if training:
+                mean = self._buf("pfn.%s.mean" % t, (64,))
+                invstd = self._buf("pfn.%s.invstd" % t, (64,))
+                moments = self._buf("pfn.%s.moments" % t, (65,), torch.float64)
+                ops.pfn_moments(vox, num, coords, geom, moments)
+                rows = vox.shape[0] * 32
+                ops.pfn_stats_finalize(moments, rows, w, P[pre + ".norm.weight"], P[pre + ".norm.bias"], 1,
+                                       P[pre + ".norm.running_mean"], P[pre + ".norm.running_var"], scale, shift, mean,
+                                       invstd)
+                amax = self._buf("pfn.%s.amax" % t, (vox.shape[0], 64), torch.uint8)
+                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax)
+                if record is not None:
+                    record.append(dict(kind="pfn", type=t, vox=vox, num=num, coords=coords, geom=geom, pre=pre,
+                                       scale=scale, shift=shift, mean=mean, invstd=invstd, amap=amap, amax=amax,
+                                       moments=moments, rows=rows))
+            else:
+                ops.bn_eval_affine(P[pre + ".norm.weight"], P[pre + ".norm.bias"], P[pre + ".norm.running_mean"],
+                                   P[pre + ".norm.running_var"], scale, shift)
+                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas)
+        return canvas
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, P, lidar, layout, training, k_list=None):
+        """lidar: {type: {voxel_features, voxel_num_points, voxel_coords}} device tensors.
+        layout: dict(n_total, ny, nx, record_len=[...], agent_map={type: int32 device tensor}).
+        Returns heads [B, H/2, W/2, 32] (NHWC, channels cls|reg|obj|pad) and an aux dict of device scalars."""
+        self._begin_step()
+        rec = [] if training else None
+        W = self._pack_weights(P)
+        record_len = layout["record_len"]
+        B, N = len(record_len), layout["n_total"]
+        canvas = self._encode(P, lidar, layout, training, rec)
+        nz = self._buf("comm_rate", (1,), torch.int64)
+        ops.count_nonzero(canvas.hi, nz)
+
+        # ---- pass A: un-masked backbone on every agent map (single-agent confidence for the mask)
+        # block 0 is shared with the fusion pass; in train mode its BNs see 3 identical running-stat updates
+        # (airv2x_where2com.py:119,124 + where2comm_fuse.py:218), the other pass-A BNs 2.
+        x0 = self._block(P, W, 0, canvas, training, 3, "A", rec)
+        h2, w2 = x0.shape[1], x0.shape[2]
+        catA = self._act("A.cat", (N, h2, w2, self.c_cat))
+        xa = x0
+        for i in range(len(self.layer_nums)):
+            if i > 0:
+                xa = self._block(P, W, i, xa, training, 2, "A", None)
+            c0 = sum(self.up_filters[:i])
+            self._deblock(P, W, i, xa, catA.slice_c(c0, c0 + self.up_filters[i]), training, 2, "A", None)
+        _, _, headsA = self._shrink_heads(P, W, catA, "A")
+
+        # ---- communication mask (where2comm_fuse.py:83-149)
+        hw = h2 * w2
+        mask = self._buf("mask", (N, h2, w2))
+        ones = self._buf("mask.ones", (B,))
+        if self.fully:
+            mask.fill_(1.0)
+            ones.fill_(float("nan"))
+        else:
+            assert headsA.shape[1] == h2 and headsA.shape[2] == w2, "mask interpolation not implemented"
+            conf = self._buf("conf", (N, h2, w2))
+            smooth = self._buf("smooth", (N, h2, w2))
+            ops.comm_confidence(headsA, self.A * self.K, conf)
+            gs = self.comm.get("gaussian_smooth")
+            ksz = gs["k_size"] if gs else 0
+            gw = P.get("fusion_net.naive_communication.gaussian_filter.weight")
+            gb = P.get("fusion_net.naive_communication.gaussian_filter.bias")
+            thr = float(self.comm["threshold"])
+            if training:
+                # K per scene from Python's `random` exactly like the reference (where2comm_fuse.py:106)
+                if k_list is None:
+                    k_list = [int(hw * random.uniform(0, 1)) for _ in range(B)]
+                k_host = self._pinned("k_host", (N,), torch.int32)
+                pos = 0
+                for b, n in enumerate(record_len):
+                    k_host[pos:pos + n] = k_list[b]
+                    pos += n
+                k_dev = self._buf("k_dev", (N,), torch.int32)
+                k_dev.copy_(k_host, non_blocking=True)
+                ops.comm_smooth_mask(conf, gw, gb, ksz, N, h2, w2, thr, False, smooth, mask)
+                ops.comm_topk_mask(smooth, N, hw, k_dev, mask)
+            elif thr:
+                ops.comm_smooth_mask(conf, gw, gb, ksz, N, h2, w2, thr, True, smooth, mask)
+            else:
+                mask.fill_(1.0)
+            ops.comm_rate_ego(mask, hw, B, layout["scene_start"], layout["scene_len"], ones)
+
+        # ---- pass B: masked multi-scale fusion (where2comm_fuse.py:214-262)
+        x0m = self._act("B.x0m", x0.shape)
+        ops.affine_act(self._full(x0, "B.x0full"), None, None, False, x0m, mask=mask)
+        catB = self._act("B.cat", (B, h2, w2, self.c_cat))
+        xb = x0m
+        levels = []
+        for i in range(len(self.layer_nums)):
+            if i > 0:
+                xb = self._block(P, W, i, xb, training, 1, "B", rec)
+            n_, hh, ww, cc = xb.shape
+            fused = self._act("B.fuse%d" % i, (B, hh, ww, cc))
+            xfull = self._full(xb, "B.xfull%d" % i)
+            pos = 0
+            for b, n in enumerate(record_len):
+                ops.att_fuse_fwd(xfull[pos:pos + n], fused.narrow_n(b, 1))
+                pos += n
+            levels.append(dict(x=xb, xfull=xfull, fused=fused))
+            c0 = sum(self.up_filters[:i])
+            self._deblock(P, W, i, fused, catB.slice_c(c0, c0 + self.up_filters[i]), training, 1, "B", rec)
+        y1, y2, heads = self._shrink_heads(P, W, catB, "B")
+        if training:
+            self.saved = dict(rec=rec, W=W, levels=levels, mask=mask, x0=x0, x0m=x0m, catB=catB, y1=y1, y2=y2,
+                              heads=heads, layout=layout, canvas=canvas)
+        aux = dict(comm_rate=nz, ones=ones, hw=hw)
+        return heads, aux
+
+    def _pinned(self, name, shape, dtype):
+        key = ("pinned", name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+            self.bufs[key] = t
+        return t
+
+    def _full(self, act, name):
+        """fp32 value of a (possibly split) activation as one dense tensor (fusion consumes full precision)."""
+        if act.lo is None:
+            return act.hi
+        out = self._buf(name, act.shape)
+        torch.add(act.hi, act.lo, out=out)
+        return out
+
+    # ------------------------------------------------------------------ loss (fused value + gradient)
+    def loss(self, heads, labels, cls_weight=1.0, reg_coe=2.0, want_grad=True):
+        B = heads.shape[0]
+        dheads = self._buf("dheads", heads.shape) if want_grad else None
+        loss3 = self._buf("loss3", (3,), torch.float64)
+        npos = self._buf("npos", (B,))
+        ops.det_loss(heads, self.A, self.K, labels["targets"], labels["pos_equal_one"], labels["class_ids"],
+                     float(cls_weight), float(reg_coe), npos, dheads, loss3)
+        return loss3, dheads
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, P, dheads, grads):
+        """dheads: [B,h,w,32] gradient w.r.t. the head logits. grads: dict name -> fp32 tensor (written)."""
+        S = self.saved
+        assert S is not None, "backward() needs a train-mode forward first"
+        W, rec = S["W"], S["rec"]
+        nc, nr = self.A * self.K, 7 * self.A
+        B, h2, w2, _ = dheads.shape
+
+        def wgrad_conv(x, dy, name, k, stride):
+            cout = dy.shape[3]
+            cin = x.shape[3]
+            dwp = self._zeroed(name + ".dwp", k * k * cout * cin, torch.float32).view(k * k, cout, cin)
+            ops.conv_wgrad(x, dy, k, stride, dwp)
+            return dwp
+
+        def bias_grad(g_hi, g_lo, C, out):
+            sums = self._zeroed("bias.sums.%d" % id(out), 2 * C, torch.float64)
+            ops.channel_stats(g_hi, sums)
+            ops.sums_to_float(sums, C, out)
+            if g_lo is not None:
+                sums2 = self._zeroed("bias.sums2.%d" % id(out), 2 * C, torch.float64)
+                ops.channel_stats(g_lo, sums2)
+                ops.sums_to_float(sums2, C, out, accumulate=True)
+
+        # ---- heads
+        dh = self._act("bwd.dheads", dheads.shape)
+        ops.affine_act(dheads, None, None, False, dh)
+        dwp = wgrad_conv(S["y2"], dh, "heads", 1, 1)
+        hg = self._buf("heads.wgrad", (HEAD_PAD, self.c_shrink, 1, 1))
+        ops.unpack_conv_wgrad(dwp, HEAD_PAD, self.c_shrink, 1, out=hg)
+        grads["cls_head.weight"].copy_(hg[:nc])
+        grads["reg_head.weight"].copy_(hg[nc:nc + nr])
+        grads["obj_head.weight"].copy_(hg[nc + nr:self.n_head])
+        hbg = self._buf("heads.bgrad", (HEAD_PAD,))
+        bias_grad(dheads, None, HEAD_PAD, hbg)
+        grads["cls_head.bias"].copy_(hbg[:nc])
+        grads["reg_head.bias"].copy_(hbg[nc:nc + nr])
+        grads["obj_head.bias"].copy_(hbg[nc + nr:self.n_head])
+        d_y2 = self._buf("bwd.d_y2", S["y2"].shape)
+        ops.conv_dgrad(dh, W["heads"][1], 1, 1, d_y2)
+
+        # ---- shrink conv 2 (3x3 + bias + ReLU)
+        y2full = self._full(S["y2"], "bwd.y2full")
+        g2 = self._act("bwd.g2", S["y2"].shape)
+        ops.relu_bwd(d_y2, y2full, g2)
+        n2 = "shrink_conv.layers.0.double_conv.2"
+        dwp = wgrad_conv(S["y1"], g2, n2 + ".weight", 3, 1)
+        ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_shrink, 3, out=grads[n2 + ".weight"])
+        bias_grad(g2.hi, g2.lo, self.c_shrink, grads[n2 + ".bias"])
+        d_y1 = self._buf("bwd.d_y1", S["y1"].shape)
+        ops.conv_dgrad(g2, W[n2 + ".weight"][1], 3, 1, d_y1)
+
+        # ---- shrink conv 1 (1x1 + bias + ReLU)
+        y1full = self._full(S["y1"], "bwd.y1full")
+        g1 = self._act("bwd.g1", S["y1"].shape)
+        ops.relu_bwd(d_y1, y1full, g1)
+        n1 = "shrink_conv.layers.0.double_conv.0"
+        dwp = wgrad_conv(S["catB"], g1, n1 + ".weight", 1, 1)
+        ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_cat, 1, out=grads[n1 + ".weight"])
+        bias_grad(g1.hi, g1.lo, self.c_shrink, grads[n1 + ".bias"])
+        d_cat = self._buf("bwd.d_cat", (B, h2, w2, self.c_cat))
+        ops.conv_dgrad(g1, W[n1 + ".weight"][1], 1, 1, d_cat)
+
+        # ---- deblocks (pass B) -> d(fused_i); fusion backward -> d(x_i) for every agent
+        levels = S["levels"]
+        record_len = S["layout"]["record_len"]
+        d_levels = [None] * len(levels)
+        deconv_recs = {r["level"]: r for r in rec if r["kind"] == "deconv"}
+        for i, lv in enumerate(levels):
+            r = deconv_recs[i]
+            c0 = sum(self.up_filters[:i])
+            dy = d_cat[..., c0:c0 + self.up_filters[i]]
+            dz = self._act("bwd.dz.d%d" % i, r["z"].shape)
+            sums = self._zeroed(r["tag"] + ".bsums", 2 * r["z"].shape[3], torch.float64)
+            ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
+                            grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
+            s = r["stride"]
+            cin, cout = r["x"].shape[3], r["z"].shape[3]
+            dwp = self._zeroed(r["conv"] + ".dwp", s * s * cin * cout, torch.float32).view(s * s, cin, cout)
+            ops.deconv_wgrad(r["x"], dz, s, dwp)
+            ops.unpack_deconv_wgrad(dwp, cin, cout, s, out=grads[r["conv"]])
+            d_fused = self._buf("bwd.d_fused%d" % i, lv["fused"].shape)
+            ops.deconv_dgrad(dz, W[r["conv"]][1], s, d_fused)
+            dx = self._buf("bwd.dx%d" % i, lv["x"].shape)
+            pos = 0
+            for b, n in enumerate(record_len):
+                ops.att_fuse_bwd(lv["xfull"][pos:pos + n], d_fused[b:b + 1], dx[pos:pos + n])
+                pos += n
+            d_levels[i] = dx
+
+        # ---- backbone blocks in reverse (pass B for levels >= 1, then block 0 through the mask)
+        conv_recs = [r for r in rec if r["kind"] == "conv"]
+        by_tag = {r["tag"]: r for r in conv_recs}
+
+        def block_bwd(tag, i, dy, dx_first, accumulate_first, mask=None):
+            """dy: gradient w.r.t. the block output; returns nothing, writes the input gradient into dx_first."""
+            nl = self.layer_nums[i]
+            for k in range(nl, -1, -1):
+                r = by_tag["%s.b%d.%d" % (tag, i, k)]
+                dz = self._act("bwd.dz." + r["tag"], r["z"].shape)
+                sums = self._zeroed(r["tag"] + ".bsums", 2 * r["z"].shape[3], torch.float64)
+                ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
+                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
+                cout, cin = r["z"].shape[3], r["x"].shape[3]
+                dwp = self._zeroed(r["conv"] + ".dwp." + tag, 9 * cout * cin, torch.float32).view(9, cout, cin)
+                ops.conv_wgrad(r["x"], dz, 3, r["stride"], dwp)
+                ops.unpack_conv_wgrad(dwp, cout, cin, 3, out=grads[r["conv"]])
+                if k > 0:
+                    dprev = self._buf("bwd.dprev.%s.b%d.%d" % (tag, i, k), r["x"].shape)
+                    ops.conv_dgrad(dz, W[r["conv"]][1], 3, r["stride"], dprev)
+                    dy = dprev
+                else:
+                    ops.conv_dgrad(dz, W[r["conv"]][1], 3, r["stride"], dx_first, accumulate=accumulate_first)
+
+        nlev = len(levels)
+        for i in range(nlev - 1, 0, -1):
+            block_bwd("B", i, d_levels[i], d_levels[i - 1], True)
+        # level 0: d(x0m) -> mask -> d(x0) ; block 0 ran in pass "A" (shared)
+        d_x0 = self._buf("bwd.d_x0", S["x0"].shape)
+        ops.relu_bwd(d_levels[0], None, Act(d_x0), mask=S["mask"])
+        d_canvas = self._buf("bwd.d_canvas", S["canvas"].shape)
+        block_bwd("A", 0, d_x0, d_canvas, False)
+
+        # ---- PillarVFE
+        for r in rec:
+            if r["kind"] != "pfn":
+                continue
+            pre = r["pre"]
+            acc = self._buf("pfn.%s.acc" % r["type"], (64 * 12,), torch.float64)
+            ops.pfn_bwd(r["vox"], r["num"], r["coords"], r["geom"], P[pre + ".linear.weight"], r["scale"], r["shift"],
+                        r["mean"], r["invstd"], r["amap"], d_canvas, r["amax"], r["moments"], r["rows"], acc,
+                        grads[pre + ".linear.weight"], grads[pre + ".norm.weight"], grads[pre + ".norm.bias"])
+        return grads

@@ -42,35 +42,136 @@ typedef struct {
     int n, h, w, cin, cout, ksize, stride;
 } a2x_conv_shape;
 
-/* weight re-layout (tiny, HBM-bound):  OIHW -> [tap][cout][cin] (forward B operand) and [tap][cin][cout] (dgrad) */
+/* weight re-layout (tiny, HBM-bound):  OIHW -> [2][tap][cout_pad][cin] (forward B operand) and
+ * [2][tap][cin][cout_pad] (dgrad); plane 0 = tf32_rn(w), plane 1 = w - plane 0 */
 int a2x_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, float* w_fwd, float* w_dgrad,
                          a2x_stream_t stream);
 /* [tap][cout_pad][cin] -> OIHW (first `cout` rows) ; accumulate != 0 adds into dw_oihw */
 int a2x_unpack_conv_wgrad(const float* dw_packed, int cout, int cin, int ksize, int cout_pad, float* dw_oihw,
                           int accumulate, a2x_stream_t stream);
-/* ConvTranspose2d weight [cin][cout][s][s] -> [(i*s+j)*cout+co][ci] (forward) and [(i*s+j)][ci][co] (dgrad) */
+/* ConvTranspose2d weight [cin][cout][s][s] -> [2][(i*s+j)*cout+co][ci] (forward) and [2][(i*s+j)][ci][co] (dgrad) */
 int a2x_pack_deconv_weight(const float* w_iohw, int cin, int cout, int s, float* w_fwd, float* w_dgrad,
                            a2x_stream_t stream);
 /* [(i*s+j)][ci][co] -> [cin][cout][s][s] */
 int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, float* dw_iohw, int accumulate,
                             a2x_stream_t stream);
 
-/* y = act(scale[c] * conv(x, w) + shift[c]); scale/shift may be NULL; y has pixel stride y_cs */
-int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, int x_cs, const float* w_fwd, float* y, int y_cs,
-                   const float* scale, const float* shift, int relu, a2x_stream_t stream);
-/* dx (+)= conv_transpose(dy, w) */
-int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, int dy_cs, const float* w_dgrad, float* dx, int dx_cs,
-                     int accumulate, a2x_stream_t stream);
-/* dw_packed[tap][cout][cin] += sum_pixels dy (x) x   (caller zeroes dw_packed) */
-int a2x_conv2d_wgrad(const a2x_conv_shape* s, const float* x, int x_cs, const float* dy, int dy_cs, float* dw_packed,
-                     a2x_stream_t stream);
+/* Precision: every GEMM operand may be given as one plane (1xTF32: values should be pre-rounded with
+ * round-to-nearest, which every producer kernel in this library does) or as a (hi, lo) pair with
+ * hi = tf32_rn(v), lo = v - hi ("3xTF32": hi*hi + lo*hi + hi*lo, fp32-equivalent accuracy, 3x the MMAs).
+ * `*_lo == NULL` selects the single-plane mode. Packed weights always carry both planes: [2][...].
+ * Outputs: y (+ y_lo if non-NULL, written as the split pair so the next GEMM can consume it). */
 
-int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, int x_cs, const float* w_fwd, float* y, int y_cs,
-                   const float* scale, const float* shift, int relu, a2x_stream_t stream);
-int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, int dy_cs, const float* w_dgrad, float* dx, int dx_cs,
-                     int accumulate, a2x_stream_t stream);
-int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, int x_cs, const float* dy, int dy_cs, float* dw_packed,
-                     a2x_stream_t stream);
+/* y = act(scale[c] * conv(x, w) + shift[c]); scale/shift may be NULL; y has pixel stride y_cs */
+int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
+                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, a2x_stream_t stream);
+/* dx (+)= conv_transpose(dy, w) */
+int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
+                     float* dx, int dx_cs, int accumulate, a2x_stream_t stream);
+/* dw_packed[tap][cout][cin] += sum_pixels dy (x) x   (caller zeroes dw_packed) */
+int a2x_conv2d_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,
+                     const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream);
+
+int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
+                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, a2x_stream_t stream);
+int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
+                     float* dx, int dx_cs, int accumulate, a2x_stream_t stream);
+int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,
+                     const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream);
+
+
+/* ---------------------------------------------------------------- operand split
+ * hi = tf32_rn(x), lo = x - hi (n multiple of 4). */
+int a2x_split_tf32(const float* x, long long n, float* hi, float* lo, a2x_stream_t stream);
+
+/* ---------------------------------------------------------------- BatchNorm / ReLU / masks (HBM-bound)
+ * Replace nn.BatchNorm2d(eps 1e-3, momentum 0.01) + nn.ReLU and their autograd
+ * (opencood/models/common_modules/base_bev_backbone.py:52-66, :82-90) and the bias+ReLU of
+ * downsample_conv.py:18-32. x/y/z/dy are NHWC with pixel strides *_cs; npix = n*h*w; C multiple of 4.
+ */
+/* sums[c] += sum x, sums[C+c] += sum x^2 (double; caller zeroes) */
+int a2x_channel_stats(const float* x, int x_cs, long long npix, int C, double* sums, a2x_stream_t stream);
+/* batch stats -> scale = gamma*invstd, shift = beta - mean*scale; running stats updated n_updates times */
+int a2x_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps, float momentum,
+                    int n_updates, float* running_mean, float* running_var, int C, float* scale, float* shift,
+                    float* mean_out, float* invstd_out, a2x_stream_t stream);
+int a2x_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, int C, float* scale, float* shift, a2x_stream_t stream);
+/* y = relu?(x*scale[c] + shift[c]) * mask[pixel]   (scale/shift/mask may be NULL; y_lo != NULL -> split pair) */
+int a2x_affine_act(const float* x, int x_cs, const float* scale, const float* shift, int relu, const float* mask,
+                   float* y, float* y_lo, int y_cs, long long npix, int C, a2x_stream_t stream);
+/* BN(train)+ReLU backward, pass 1: sums[c] += sum g, sums[C+c] += sum g*zhat with g = dy*(z*scale+shift > 0) */
+int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, long long npix, int C, double* sums,
+                           a2x_stream_t stream);
+/* pass 2: dz = scale*(g - sum_g/count - zhat*sum_gz/count); dgamma/dbeta (may be NULL) from the sums */
+int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, const double* sums, double count, float* dz,
+                          float* dz_lo, int dz_cs, long long npix, int C, float* dgamma, float* dbeta,
+                          int accumulate_param_grads, a2x_stream_t stream);
+/* g = dy * (y > 0) * mask[pixel]  (y, mask may be NULL) */
+int a2x_relu_bwd(const float* dy, int dy_cs, const float* y, int y_cs, const float* mask, float* g, float* g_lo,
+                 int g_cs, long long npix, int C, a2x_stream_t stream);
+/* out[c] (+)= (float) sums[c] : bias gradients from a2x_channel_stats sums */
+int a2x_sums_to_float(const double* sums, int C, float* out, int accumulate, a2x_stream_t stream);
+/* torch.count_nonzero (airv2x_where2com.py:122) */
+int a2x_count_nonzero(const float* x, long long n, unsigned long long* out, a2x_stream_t stream);
+
+/* ---------------------------------------------------------------- PillarVFE + PointPillarScatter
+ * Replace PillarVFE.forward / PFNLayer.forward / PointPillarScatter.forward
+ * (opencood/models/common_modules/airv2x_pillar_vfe.py:105-160, :27-49; point_pillar_scatter.py:15-82).
+ * voxels [M][32][4] f32 zero padded, num_points [M] i32, coords [M][4] i32 (agent,z,y,x) — the dict
+ * SpVoxelPreprocessor.collate_batch emits (data_utils/pre_processor/sp_voxel_preprocessor.py:142-175).
+ * agent_map[agent] = row of that agent in the scene-major canvas [n_total][ny][nx][64].
+ */
+typedef struct {
+    float voxel_x, voxel_y, voxel_z;    /* per agent type (airv2x_pillar_vfe.py:84-89) */
+    float x_offset, y_offset, z_offset; /* voxel/2 + range_lo */
+    int nx, ny;
+} a2x_pfn_geom;
+/* moments65 = [sum f (10), upper triangle of sum f f^T (55)] over all M*32 rows (zeroed here) */
+int a2x_pfn_moments(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
+                    double* moments65, a2x_stream_t stream);
+/* BatchNorm1d batch statistics of W f from the moments (rows = M*32) */
+int a2x_pfn_stats_finalize(const double* moments65, double rows, const float* w, const float* gamma, const float* beta,
+                           float eps, float momentum, int n_updates, float* running_mean, float* running_var,
+                           float* scale, float* shift, float* mean_out, float* invstd_out, a2x_stream_t stream);
+/* canvas[agent_map[a]][y][x][:] = max_slot relu(scale*(W f)+shift); optional pillar_out [M][64], amax [M][64] u8 */
+int a2x_pfn_scatter(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
+                    const float* w, const float* scale, const float* shift, const int* agent_map, float* canvas,
+                    float* canvas_lo, float* pillar_out, unsigned char* amax, a2x_stream_t stream);
+/* train-mode backward to (W, gamma, beta) given d(canvas); acc_ws = 64*12 doubles of workspace */
+int a2x_pfn_bwd(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
+                const float* w, const float* scale, const float* shift, const float* mean, const float* invstd,
+                const int* agent_map, const float* dcanvas, const unsigned char* amax, const double* moments65,
+                double rows, double* acc_ws, float* dw, float* dgamma, float* dbeta, int accumulate,
+                a2x_stream_t stream);
+
+/* ---------------------------------------------------------------- Where2comm communication + fusion
+ * Replace Communication.forward (opencood/models/where2comm_modules/where2comm_fuse.py:83-149) and
+ * AttentionFusion.forward (:152-164, :14-45).
+ */
+/* conf[p] = max_{c<ncls} sigmoid(psm[p][c]) */
+int a2x_comm_confidence(const float* psm, int psm_cs, int ncls, long long npix, float* conf, a2x_stream_t stream);
+/* smooth = gaussian_filter(conf) (ksz x ksz weights + bias; ksz = 0 -> identity); write_mask: mask = smooth > thr */
+int a2x_comm_smooth_mask(const float* conf, const float* gauss_w, const float* gauss_b, int ksz, int n, int h, int w,
+                         float threshold, int write_mask, float* smooth, float* mask, a2x_stream_t stream);
+/* train mode: mask[a] = 1 on the k_per_agent[a] largest smooth values of agent a (device array) */
+int a2x_comm_topk_mask(const float* smooth, int n, int hw, const int* k_per_agent, float* mask, a2x_stream_t stream);
+/* ones[b] = sum of the scene's mask (before ego override); then mask[ego of scene b] = 1 */
+int a2x_comm_rate_ego(float* mask, int hw, int n_scenes, const int* scene_start, const int* scene_len, float* ones,
+                      a2x_stream_t stream);
+/* x: [n_agents][hw][c] of ONE scene (agent 0 = ego) -> out [hw][c] = row 0 of softmax(x x^T / sqrt(c)) x */
+int a2x_att_fuse_fwd(const float* x, int n_agents, int hw, int c, float* out, float* out_lo, a2x_stream_t stream);
+int a2x_att_fuse_bwd(const float* x, const float* dout, int n_agents, int hw, int c, float* dx, a2x_stream_t stream);
+
+/* ---------------------------------------------------------------- detection loss
+ * Replace PointPillarLossMultiClass.forward (opencood/loss/point_pillar_loss_multiclass.py:96-215, :273-289):
+ * value (reg, cls, obj terms) and gradient w.r.t. the NHWC head logits [psm(A*K) | rm(7A) | obj(A)] in one pass.
+ */
+int a2x_det_loss(const float* heads, int heads_cs, int B, long long HW, int A, int K, const float* targets,
+                 const float* pos_equal_one, const int* class_ids, float cls_weight, float reg_coe, float* npos_ws,
+                 float* dheads, int dheads_cs, double* loss3, a2x_stream_t stream);
 
 #ifdef __cplusplus
 }
