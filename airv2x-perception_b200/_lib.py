@@ -26,6 +26,7 @@ def load():
         raise RuntimeError("libairv2x_b200.so is missing and could not be built; there is no CPU fallback")
     lib = ctypes.CDLL(LIB_PATH)
     lib.a2x_last_error.restype = ctypes.c_char_p
+    lib.a2x_launch_count.restype = ctypes.c_ulonglong
     _lib = lib
     return lib
 
@@ -39,11 +40,23 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+PROFILE = None  # set to a list to record (name, args, start_event, end_event) per C-ABI call (bench roofline pass)
+
+
 def call(name, *args):
     """Call a C-ABI entry point; raise RuntimeError with a2x_last_error() on a non-zero status."""
     lib = load()
     fn = getattr(lib, name)
-    rc = fn(*args)
+    if PROFILE is not None:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.append((name, args, e0, e1))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.a2x_last_error().decode()))
     return rc

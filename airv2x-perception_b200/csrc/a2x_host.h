@@ -11,6 +11,8 @@
 namespace a2x {
 
 void set_error(const char* fmt, ...);  // thread-local message, read through a2x_last_error()
+extern unsigned long long g_launches;  // kernels launched by this library (a2x_launch_count)
+#define A2X_LAUNCHED() (++a2x::g_launches)
 
 #define A2X_CHECK_CUDA(expr)                                                                   \
     do {                                                                                       \

@@ -8,6 +8,7 @@ namespace a2x {
 
 static thread_local char g_err[1024] = "";
 int g_debug[16] = {0};
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -80,6 +81,8 @@ int a2x_version(void) { return 100; }
 void a2x_debug_set(int key, int value) {
     if (key >= 0 && key < 16) a2x::g_debug[key] = value;
 }
+
+unsigned long long a2x_launch_count(void) { return a2x::g_launches; }
 
 int a2x_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;

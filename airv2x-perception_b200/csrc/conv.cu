@@ -61,6 +61,7 @@ static int launch_tg(const TgParams& p, int n_col_tiles, cudaStream_t st) {
     }
     dim3 grid(p.n_img * p.tiles_h * p.tiles_w, n_col_tiles, 1);
     tapgemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -183,6 +184,7 @@ static int launch_wg(const WgParams& p, int ksplit, int tiles_a, int tap_groups,
     }
     dim3 grid(ksplit, tiles_a * p.n_tiles_b, tap_groups);
     wgrad_kernel<BN, TPC, STAGES, SPLIT><<<grid, 192, L::TOTAL, st>>>(p);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -330,6 +332,7 @@ int a2x_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int 
     const int kk = ksize * ksize;
     pack_conv_w_kernel<<<grid_for((long long)kk * cout_pad * cin), 256, 0, (cudaStream_t)stream>>>(
         w_oihw, cout, cin, kk, cout_pad, w_fwd, w_dgrad);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -340,6 +343,7 @@ int a2x_unpack_conv_wgrad(const float* dw_packed, int cout, int cin, int ksize, 
     const int kk = ksize * ksize;
     unpack_conv_dw_kernel<<<grid_for((long long)kk * cout * cin), 256, 0, (cudaStream_t)stream>>>(
         dw_packed, cout, cin, kk, cout_pad, dw_oihw, accumulate);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -349,6 +353,7 @@ int a2x_pack_deconv_weight(const float* w_iohw, int cin, int cout, int s, float*
     A2X_REQUIRE(w_iohw && cin > 0 && cout > 0 && s > 0, "bad pack args");
     pack_deconv_w_kernel<<<grid_for((long long)cin * cout * s * s), 256, 0, (cudaStream_t)stream>>>(w_iohw, cin, cout,
                                                                                                   s, w_fwd, w_dgrad);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -358,6 +363,7 @@ int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, fl
     A2X_REQUIRE(dw_packed && dw_iohw && cin > 0 && cout > 0 && s > 0, "bad unpack args");
     unpack_deconv_dw_kernel<<<grid_for((long long)cin * cout * s * s), 256, 0, (cudaStream_t)stream>>>(
         dw_packed, cin, cout, s, dw_iohw, accumulate);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -28,6 +28,13 @@ __global__ void split_kernel(const float* __restrict__ x, long long n4, float* _
     }
 }
 
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float* __restrict__ o) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+        reinterpret_cast<float4*>(o)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- channel stats
 // sums[c] += sum_p x[p][c] ; sums[C + c] += sum_p x[p][c]^2     (double accumulators)
 // optional second operand: MODE 1 computes g = dy * (z*scale+shift > 0), zhat = (z-mean)*invstd and accumulates
@@ -276,6 +283,15 @@ extern "C" {
 int a2x_split_tf32(const float* x, long long n, float* hi, float* lo, a2x_stream_t stream) {
     A2X_REQUIRE(x && hi && lo && n % 4 == 0, "split_tf32: bad args (n must be a multiple of 4)");
     split_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, n / 4, hi, lo);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_add2(const float* a, const float* b, long long n, float* out, a2x_stream_t stream) {
+    A2X_REQUIRE(a && b && out && n % 4 == 0, "add2: bad args (n must be a multiple of 4)");
+    add2_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4, out);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -296,6 +312,7 @@ int a2x_channel_stats(const float* x, int x_cs, long long npix, int C, double* s
     if (blocks > 148 * 4) blocks = 148 * 4;
     channel_reduce_kernel<0><<<(int)blocks, 256, 2 * 256 * 4 * sizeof(float), (cudaStream_t)stream>>>(
         x, x_cs, nullptr, 0, nullptr, nullptr, nullptr, nullptr, npix, C, sums);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -307,6 +324,7 @@ int a2x_bn_finalize(const double* sums, double count, const float* gamma, const 
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, gamma, beta, eps, momentum,
                                                                         n_updates, running_mean, running_var, C, scale,
                                                                         shift, mean_out, invstd_out);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -316,6 +334,7 @@ int a2x_bn_eval_affine(const float* gamma, const float* beta, const float* runni
     A2X_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && C > 0, "bn_eval_affine: bad args");
     bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var,
                                                                            eps, C, scale, shift);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -326,6 +345,7 @@ int a2x_affine_act(const float* x, int x_cs, const float* scale, const float* sh
     A2X_REQUIRE(x && y && npix > 0, "affine_act: bad args");
     affine_act_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_cs, scale, shift, relu, mask, y,
                                                                                y_lo, y_cs, npix, C);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -340,6 +360,7 @@ int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs,
     if (blocks > 148 * 4) blocks = 148 * 4;
     channel_reduce_kernel<1><<<(int)blocks, 256, 2 * 256 * 4 * sizeof(float), (cudaStream_t)stream>>>(
         dy, dy_cs, z, z_cs, scale, shift, mean, invstd, npix, C, sums);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -352,10 +373,12 @@ int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, 
     A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && dz && npix > 0, "bn_relu_bwd_apply: bad args");
     bn_relu_bwd_apply_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
         dy, dy_cs, z, z_cs, scale, shift, mean, invstd, sums, count, dz, dz_lo, dz_cs, npix, C);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     if (dgamma || dbeta) {
         bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta,
                                                                                 accumulate_param_grads);
+    A2X_LAUNCHED();
         A2X_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
@@ -367,6 +390,7 @@ int a2x_relu_bwd(const float* dy, int dy_cs, const float* y, int y_cs, const flo
     A2X_REQUIRE(dy && g && npix > 0, "relu_bwd: bad args");
     relu_bwd_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dy, dy_cs, y, y_cs, mask, g, g_lo, g_cs,
                                                                              npix, C);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -374,6 +398,7 @@ int a2x_relu_bwd(const float* dy, int dy_cs, const float* y, int y_cs, const flo
 int a2x_sums_to_float(const double* sums, int C, float* out, int accumulate, a2x_stream_t stream) {
     A2X_REQUIRE(sums && out && C > 0, "sums_to_float: bad args");
     bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, nullptr, out, accumulate);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -382,6 +407,7 @@ int a2x_count_nonzero(const float* x, long long n, unsigned long long* out, a2x_
     A2X_REQUIRE(x && out && n % 4 == 0, "count_nonzero: bad args");
     A2X_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     count_nonzero_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, n / 4, out);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

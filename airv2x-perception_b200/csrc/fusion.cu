@@ -312,6 +312,7 @@ extern "C" {
 int a2x_comm_confidence(const float* psm, int psm_cs, int ncls, long long npix, float* conf, a2x_stream_t stream) {
     A2X_REQUIRE(psm && conf && ncls > 0 && npix > 0, "comm_confidence: bad args");
     conf_map_kernel<<<grid1d(npix), 256, 0, (cudaStream_t)stream>>>(psm, psm_cs, ncls, npix, conf);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -321,6 +322,7 @@ int a2x_comm_smooth_mask(const float* conf, const float* gauss_w, const float* g
     A2X_REQUIRE(conf && smooth && (ksz == 0 || (gauss_w && gauss_b)) && (!write_mask || mask), "comm_smooth_mask: bad args");
     gauss_mask_kernel<<<grid1d((long long)n * h * w), 256, 0, (cudaStream_t)stream>>>(conf, gauss_w, gauss_b, ksz, n, h, w,
                                                                                    threshold, write_mask, smooth, mask);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -328,6 +330,7 @@ int a2x_comm_smooth_mask(const float* conf, const float* gauss_w, const float* g
 int a2x_comm_topk_mask(const float* smooth, int n, int hw, const int* k_per_agent, float* mask, a2x_stream_t stream) {
     A2X_REQUIRE(smooth && k_per_agent && mask && n > 0 && hw > 0, "comm_topk_mask: bad args");
     topk_mask_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(smooth, hw, k_per_agent, mask);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -338,6 +341,7 @@ int a2x_comm_rate_ego(float* mask, int hw, int n_scenes, const int* scene_start,
     A2X_CHECK_CUDA(cudaMemsetAsync(ones, 0, sizeof(float) * n_scenes, (cudaStream_t)stream));
     dim3 grid(64, n_scenes);
     mask_rate_ego_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, hw, scene_start, scene_len, ones);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -364,6 +368,7 @@ int a2x_att_fuse_fwd(const float* x, int n_agents, int hw, int c, float* out, fl
     const int g = c / 4 < 32 ? c / 4 : 32;
     const float isc = 1.0f / sqrtf((float)c);
     A2X_ATT_DISPATCH(att_fuse_fwd_kernel, x, hw, c, n_agents, isc, out, out_lo);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -373,6 +378,7 @@ int a2x_att_fuse_bwd(const float* x, const float* dout, int n_agents, int hw, in
     const int g = c / 4 < 32 ? c / 4 : 32;
     const float isc = 1.0f / sqrtf((float)c);
     A2X_ATT_DISPATCH(att_fuse_bwd_kernel, x, dout, hw, c, n_agents, isc, dx);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -145,10 +145,12 @@ int a2x_det_loss(const float* heads, int heads_cs, int B, long long HW, int A, i
     A2X_CHECK_CUDA(cudaMemsetAsync(loss3, 0, sizeof(double) * 3, st));
     dim3 g1(32, B);
     count_pos_kernel<<<g1, 256, 0, st>>>(pos_equal_one, HW * A, B, npos_ws);
+    A2X_LAUNCHED();
     long long blocks = (B * HW + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     det_loss_kernel<<<(int)blocks, 256, 0, st>>>(heads, heads_cs, A, K, targets, pos_equal_one, class_ids, npos_ws, B, HW,
                                                 cls_weight, reg_coe, dheads, dheads_cs, loss3);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -21,6 +21,30 @@ struct PfnGeom {
     int nx, ny;
 };
 
+// Optional segmented addressing for voxeliser slabs: flat index p in [0, nseg*cap) -> slab seg_ids[p / cap],
+// pillar p % cap, valid while < seg_counts[slab]. Null counts => plain [0, M) addressing.
+struct PfnSeg {
+    const int* ids;
+    const int* counts;
+    int cap, nseg;
+};
+__device__ __forceinline__ bool seg_resolve(const PfnSeg& sg, long long p, long long& pil) {
+    if (sg.counts == nullptr) {
+        pil = p;
+        return true;
+    }
+    const int seg = (int)(p / sg.cap), idx = (int)(p % sg.cap);
+    const int slab = sg.ids ? sg.ids[seg] : seg;
+    pil = (long long)slab * sg.cap + idx;
+    return idx < sg.counts[slab];
+}
+__device__ __forceinline__ double seg_rows(const PfnSeg& sg, double rows) {
+    if (sg.counts == nullptr) return rows;
+    double r = 0;
+    for (int i = 0; i < sg.nseg; ++i) r += 32.0 * sg.counts[sg.ids ? sg.ids[i] : i];
+    return r;
+}
+
 constexpr int NF = 10;    // point features
 constexpr int NC = 64;    // PFN channels
 constexpr int NS2 = 55;   // upper triangle of the 10x10 moment
@@ -62,14 +86,16 @@ __device__ __forceinline__ void pillar_features(const float* __restrict__ voxels
 __global__ void __launch_bounds__(256) pfn_moments_kernel(const float* __restrict__ voxels,
                                                           const int* __restrict__ num_points,
                                                           const int* __restrict__ coords, PfnGeom g, long long M,
-                                                          double* __restrict__ moments /* [10 + 55] */) {
+                                                          PfnSeg sg, double* __restrict__ moments /* [10 + 55] */) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     float acc[NF + NS2];
 #pragma unroll
     for (int i = 0; i < NF + NS2; ++i) acc[i] = 0.f;
-    for (long long pil = warp0; pil < M; pil += nwarps) {
+    for (long long pp = warp0; pp < M; pp += nwarps) {
+        long long pil;
+        if (!seg_resolve(sg, pp, pil)) continue;
         float f[NF];
         int num, agent, cy, cx;
         pillar_features(voxels, num_points, coords, g, pil, lane, f, num, agent, cy, cx);
@@ -100,7 +126,8 @@ __device__ __forceinline__ int s2_index(int i, int j) {  // i <= j, row-major up
 }
 
 // batch statistics of y_c = W_c . f over `rows` rows, from the moments
-__global__ void pfn_stats_finalize_kernel(const double* __restrict__ moments, double rows, const float* __restrict__ W,
+__global__ void pfn_stats_finalize_kernel(const double* __restrict__ moments, double rows_in, PfnSeg sg,
+                                          const float* __restrict__ W,
                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                           float momentum, int n_updates, float* __restrict__ running_mean,
                                           float* __restrict__ running_var, float* __restrict__ scale,
@@ -108,6 +135,7 @@ __global__ void pfn_stats_finalize_kernel(const double* __restrict__ moments, do
                                           float* __restrict__ invstd_out) {
     const int c = threadIdx.x;
     if (c >= NC) return;
+    const double rows = seg_rows(sg, rows_in);
     double w[NF];
     for (int k = 0; k < NF; ++k) w[k] = (double)W[c * NF + k];
     double m = 0;
@@ -143,7 +171,8 @@ __global__ void pfn_stats_finalize_kernel(const double* __restrict__ moments, do
 __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restrict__ voxels,
                                                           const int* __restrict__ num_points,
                                                           const int* __restrict__ coords, PfnGeom g, long long M,
-                                                          const float* __restrict__ W, const float* __restrict__ scale,
+                                                          PfnSeg sg, const float* __restrict__ W,
+                                                          const float* __restrict__ scale,
                                                           const float* __restrict__ shift,
                                                           const int* __restrict__ agent_map,
                                                           float* __restrict__ canvas, float* __restrict__ canvas_lo,
@@ -163,7 +192,9 @@ __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restric
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long pil = warp0; pil < M; pil += nwarps) {
+    for (long long pp = warp0; pp < M; pp += nwarps) {
+        long long pil;
+        if (!seg_resolve(sg, pp, pil)) continue;
         float f[NF];
         int num, agent, cy, cx;
         pillar_features(voxels, num_points, coords, g, pil, lane, f, num, agent, cy, cx);
@@ -228,7 +259,8 @@ __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restric
 __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float* __restrict__ voxels,
                                                       const int* __restrict__ num_points,
                                                       const int* __restrict__ coords, PfnGeom g, long long M,
-                                                      const float* __restrict__ W, const float* __restrict__ scale,
+                                                      PfnSeg sg, const float* __restrict__ W,
+                                                      const float* __restrict__ scale,
                                                       const float* __restrict__ shift, const float* __restrict__ mean,
                                                       const float* __restrict__ invstd,
                                                       const int* __restrict__ agent_map,
@@ -252,7 +284,9 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 12; ++k) a[h][k] = 0.f;
     }
-    for (long long pil = warp0; pil < M; pil += nwarps) {
+    for (long long pp = warp0; pp < M; pp += nwarps) {
+        long long pil;
+        if (!seg_resolve(sg, pp, pil)) continue;
         float f[NF];
         int num, agent, cy, cx;
         pillar_features(voxels, num_points, coords, g, pil, lane, f, num, agent, cy, cx);
@@ -284,13 +318,14 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float* __restrict__ 
 }
 
 // dW_c = gamma*invstd * (G - (A/m) S1 - (Bz/m) * invstd * (S2 W_c - mu S1)),  dgamma = Bz, dbeta = A
-__global__ void pfn_bwd_finalize_kernel(const double* __restrict__ acc, const double* __restrict__ moments, double rows,
-                                        const float* __restrict__ W, const float* __restrict__ scale,
+__global__ void pfn_bwd_finalize_kernel(const double* __restrict__ acc, const double* __restrict__ moments,
+                                        double rows_in, PfnSeg sg, const float* __restrict__ W, const float* __restrict__ scale,
                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                         float* __restrict__ dW, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                         int accumulate) {
     const int c = threadIdx.x;
     if (c >= NC) return;
+    const double rows = seg_rows(sg, rows_in);
     const double A = acc[c * 12], Bz = acc[c * 12 + 1];
     const double is = (double)invstd[c], mu = (double)mean[c], gs = (double)scale[c];  // scale = gamma*invstd
     for (int k = 0; k < NF; ++k) {
@@ -320,6 +355,18 @@ using namespace a2x;
 
 extern "C" {
 
+static PfnSeg make_seg(const a2x_pfn_segments* s, long long* m) {
+    PfnSeg r{nullptr, nullptr, 0, 0};
+    if (s != nullptr && s->seg_counts != nullptr) {
+        r.ids = s->seg_ids;
+        r.counts = s->seg_counts;
+        r.cap = s->seg_cap;
+        r.nseg = s->nseg;
+        *m = (long long)s->seg_cap * s->nseg;
+    }
+    return r;
+}
+
 static PfnGeom make_geom(const a2x_pfn_geom* g) {
     PfnGeom r;
     r.vx = g->voxel_x;
@@ -334,52 +381,64 @@ static PfnGeom make_geom(const a2x_pfn_geom* g) {
 }
 
 int a2x_pfn_moments(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
-                    double* moments65, a2x_stream_t stream) {
+                    const a2x_pfn_segments* seg, double* moments65, a2x_stream_t stream) {
+    const PfnSeg sg = make_seg(seg, &m);
     A2X_REQUIRE(voxels && num_points && coords && geom && moments65 && m > 0, "pfn_moments: bad args");
     A2X_CHECK_CUDA(cudaMemsetAsync(moments65, 0, sizeof(double) * (NF + NS2), (cudaStream_t)stream));
     pfn_moments_kernel<<<warp_grid(m), 256, 0, (cudaStream_t)stream>>>(voxels, num_points, coords, make_geom(geom), m,
-                                                                     moments65);
+                                                                     sg, moments65);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int a2x_pfn_stats_finalize(const double* moments65, double rows, const float* w, const float* gamma, const float* beta,
+int a2x_pfn_stats_finalize(const double* moments65, double rows, const a2x_pfn_segments* seg, const float* w,
+                           const float* gamma, const float* beta,
                            float eps, float momentum, int n_updates, float* running_mean, float* running_var,
                            float* scale, float* shift, float* mean_out, float* invstd_out, a2x_stream_t stream) {
-    A2X_REQUIRE(moments65 && w && gamma && beta && scale && shift && rows > 0, "pfn_stats_finalize: bad args");
-    pfn_stats_finalize_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(moments65, rows, w, gamma, beta, eps, momentum,
+    long long m_unused = 1;
+    const PfnSeg sg = make_seg(seg, &m_unused);
+    A2X_REQUIRE(moments65 && w && gamma && beta && scale && shift && (rows > 0 || sg.counts), "pfn_stats_finalize: bad args");
+    pfn_stats_finalize_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(moments65, rows, sg, w, gamma, beta, eps, momentum,
                                                                 n_updates, running_mean, running_var, scale, shift,
                                                                 mean_out, invstd_out);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int a2x_pfn_scatter(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
-                    const float* w, const float* scale, const float* shift, const int* agent_map, float* canvas,
-                    float* canvas_lo, float* pillar_out, unsigned char* amax, a2x_stream_t stream) {
+                    const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift,
+                    const int* agent_map, float* canvas, float* canvas_lo, float* pillar_out, unsigned char* amax,
+                    a2x_stream_t stream) {
+    const PfnSeg sg = make_seg(seg, &m);
     A2X_REQUIRE(voxels && num_points && coords && geom && w && scale && shift && agent_map && canvas && m > 0,
                 "pfn_scatter: bad args");
-    pfn_scatter_kernel<<<warp_grid(m), 256, 0, (cudaStream_t)stream>>>(voxels, num_points, coords, make_geom(geom), m, w,
-                                                                     scale, shift, agent_map, canvas, canvas_lo,
+    pfn_scatter_kernel<<<warp_grid(m), 256, 0, (cudaStream_t)stream>>>(voxels, num_points, coords, make_geom(geom), m,
+                                                                     sg, w, scale, shift, agent_map, canvas, canvas_lo,
                                                                      pillar_out, amax);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int a2x_pfn_bwd(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
-                const float* w, const float* scale, const float* shift, const float* mean, const float* invstd,
+                const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift, const float* mean, const float* invstd,
                 const int* agent_map, const float* dcanvas, const unsigned char* amax, const double* moments65,
                 double rows, double* acc_ws /* 64*12 doubles */, float* dw, float* dgamma, float* dbeta, int accumulate,
                 a2x_stream_t stream) {
+    const PfnSeg sg = make_seg(seg, &m);
     A2X_REQUIRE(voxels && num_points && coords && geom && w && scale && shift && mean && invstd && agent_map && dcanvas &&
                     amax && moments65 && acc_ws && dw && dgamma && dbeta && m > 0,
                 "pfn_bwd: bad args");
     cudaStream_t st = (cudaStream_t)stream;
     A2X_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, sizeof(double) * NC * 12, st));
-    pfn_bwd_kernel<<<warp_grid(m), 256, 0, st>>>(voxels, num_points, coords, make_geom(geom), m, w, scale, shift, mean,
-                                                invstd, agent_map, dcanvas, amax, acc_ws);
-    pfn_bwd_finalize_kernel<<<1, 64, 0, st>>>(acc_ws, moments65, rows, w, scale, mean, invstd, dw, dgamma, dbeta,
+    pfn_bwd_kernel<<<warp_grid(m), 256, 0, st>>>(voxels, num_points, coords, make_geom(geom), m, sg, w, scale, shift,
+                                                mean, invstd, agent_map, dcanvas, amax, acc_ws);
+    A2X_LAUNCHED();
+    pfn_bwd_finalize_kernel<<<1, 64, 0, st>>>(acc_ws, moments65, rows, sg, w, scale, mean, invstd, dw, dgamma, dbeta,
                                              accumulate);
+    A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

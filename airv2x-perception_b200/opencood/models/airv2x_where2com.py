@@ -159,9 +159,10 @@ class Airv2xWhere2com(nn.Module):
     def _layout(self, data_dict, device):
         """Scene-major agent order (vehicles, RSUs, drones per scene): airv2x_base_model.py:179-248."""
         rl, idxs = {}, {}
+        raw = data_dict.get("raw_points")
         for t in AGENT_TYPES:
             if t in self.collaborators and len(data_dict[t]["batch_idxs"]) > 0 and \
-                    data_dict[t].get("batch_merged_lidar_features_torch") is not None:
+                    (raw is not None or data_dict[t].get("batch_merged_lidar_features_torch") is not None):
                 r = data_dict[t]["record_len"]
                 rl[t] = [int(v) for v in (r.tolist() if torch.is_tensor(r) else r)]
                 idxs[t] = list(data_dict[t]["batch_idxs"])
@@ -187,12 +188,38 @@ class Airv2xWhere2com(nn.Module):
         first = next(iter(rl))
         nx, ny, _ = [int(v) for v in self.args[first]["lidar"]["point_pillar_scatter"]["grid_size"]]
         scene_start = np.concatenate([[0], np.cumsum(record_len)[:-1]]).astype(np.int32)
-        return dict(n_total=row, nx=nx, ny=ny, record_len=record_len,
+        types = [None] * row
+        for t in amap:
+            for r in amap[t]:
+                types[r] = t
+        return dict(n_total=row, nx=nx, ny=ny, record_len=record_len, types=types,
+                    identity_map=torch.arange(row, dtype=torch.int32, device=device),
+                    ego_flags=torch.tensor([1 if i in set(int(v) for v in scene_start) else 0 for i in range(row)],
+                                           dtype=torch.uint8, device=device),
                     agent_map={t: torch.tensor(v, dtype=torch.int32, device=device) for t, v in amap.items()},
                     scene_start=torch.tensor(scene_start, dtype=torch.int32, device=device),
                     scene_len=torch.tensor(record_len, dtype=torch.int32, device=device))
 
     def _lidar(self, data_dict, device, layout):
+        raw = data_dict.get("raw_points")
+        if raw is not None:
+            # B200 extension of the boundary: raw per-agent clouds instead of CPU-voxelised pillars.
+            # raw_points = {"points": [sum P, 4] f32 (all agents, scene-major order), "offsets": int32 [N+1],
+            #               optional "preprocess": hypes["preprocess"], optional "filter": True -> apply the dataset's
+            #               mask_ego_points (first agent of every scene) + mask_points_by_range on the GPU}
+            pre = raw.get("preprocess")
+            first = next(iter(layout["agent_map"]))
+            la = self.args[first]["lidar"]
+            vs = pre["args"]["voxel_size"] if pre else la["voxel_size"]
+            rng = pre["cav_lidar_range"] if pre else la["lidar_range"]
+            mp = pre["args"]["max_points_per_voxel"] if pre else 32
+            mv = (pre["args"]["max_voxel_train" if self.training else "max_voxel_test"] if pre
+                  else (32000 if self.training else 70000))
+            return {"raw": {"points": raw["points"].to(device=device, dtype=torch.float32, non_blocking=True).contiguous(),
+                            "offsets": raw["offsets"].to(device=device, dtype=torch.int32, non_blocking=True).contiguous(),
+                            "types": layout["types"], "voxel_size": vs, "lidar_range": rng, "max_points": mp,
+                            "max_voxels": mv, "filter": bool(raw.get("filter", False)),
+                            "ego_flags": layout["ego_flags"] if raw.get("filter", False) else None}}
         out = {}
         for t in layout["agent_map"]:
             d = data_dict[t]["batch_merged_lidar_features_torch"]
@@ -217,6 +244,42 @@ class Airv2xWhere2com(nn.Module):
         else:
             heads, self._last_aux = self.engine.forward(self._param_dict(), lidar, layout, self.training, k_list)
         return self._output_dict(heads, layout)
+
+    # ------------------------------------------------------------------ fused training step (public fast path)
+    def _grad_buffers(self):
+        """Persistent .grad tensors (overwritten every step; same effect as zero_grad() + backward())."""
+        g = {}
+        for n, p in self.named_parameters():
+            if n.startswith("fusion_net") or not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            g[n] = p.grad
+        return g
+
+    def prepare_labels(self, label_dict, device):
+        """label tensors of the reference's collate (fp64 targets / pos_equal_one, int64 class_ids:
+        data_utils/post_processor/voxel_postprocessor.py:392-430) -> device fp32 / int32, contiguous."""
+        return {"targets": label_dict["targets"].to(device=device, dtype=torch.float32, non_blocking=True).contiguous(),
+                "pos_equal_one": label_dict["pos_equal_one"].to(device=device, dtype=torch.float32,
+                                                                non_blocking=True).contiguous(),
+                "class_ids": label_dict["class_ids"].to(device=device, dtype=torch.int32, non_blocking=True).contiguous()}
+
+    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, k_list=None):
+        """forward (train-mode BN) + PointPillarLossMultiClass + backward in one call, all on the CUDA kernels.
+        Inputs may live on the host (pinned memory -> async H2D here) or on the device. Parameter gradients land
+        in p.grad; returns the device tensor [reg, cls, obj] loss terms (float64) — total = .sum()."""
+        assert self.training, "train_step() needs model.train()"
+        dev = next(self.parameters()).device
+        layout = self._layout(data_dict, dev)
+        lidar = self._lidar(data_dict, dev, layout)
+        labels = self.prepare_labels(label_dict, dev)
+        P = self._param_dict()
+        heads, self._last_aux = self.engine.forward(P, lidar, layout, True, k_list)
+        loss3, dheads = self.engine.loss(heads, labels, cls_weight, reg_coe)
+        self.engine.backward(P, dheads, self._grad_buffers())
+        self._last_layout = layout
+        return loss3
 
     def _output_dict(self, heads, layout):
         A, K = self.args["anchor_number"], self.args["num_class"]

@@ -119,6 +119,11 @@ def split_tf32(x):
     return Act(out[0], out[1])
 
 
+def add2(a, b, out):
+    call("a2x_add2", _ptr(a), _ptr(b), ctypes.c_longlong(a.numel()), _ptr(out), stream_ptr())
+    return out
+
+
 def _lo(a):
     return _ptr(a.lo) if a.lo is not None else _ptr(None)
 
@@ -252,27 +257,45 @@ def pfn_geom(voxel_size, lidar_range, nx, ny):
     return PfnGeom(vx, vy, vz, vx / 2 + lidar_range[0], vy / 2 + lidar_range[1], vz / 2 + lidar_range[2], nx, ny)
 
 
-def pfn_moments(vox, num, coords, geom, moments):
-    call("a2x_pfn_moments", _ptr(vox), _ptr(num), _ptr(coords), c_ll(vox.shape[0]), ctypes.byref(geom), _ptr(moments),
-         stream_ptr())
+class PfnSegments(ctypes.Structure):
+    _fields_ = [("seg_ids", ctypes.c_void_p), ("seg_counts", ctypes.c_void_p), ("seg_cap", c_int), ("nseg", c_int)]
+
+
+def pfn_segments(seg_ids, seg_counts, cap):
+    """seg_ids: int32 device tensor (slab index per segment); seg_counts: int32 device tensor indexed by slab"""
+    return PfnSegments(seg_ids.data_ptr(), seg_counts.data_ptr(), cap, seg_ids.numel())
+
+
+def _seg(seg):
+    return ctypes.byref(seg) if seg is not None else ctypes.c_void_p(0)
+
+
+def _m(vox, seg):
+    return 0 if seg is not None else vox.shape[0]
+
+
+def pfn_moments(vox, num, coords, geom, moments, seg=None):
+    call("a2x_pfn_moments", _ptr(vox), _ptr(num), _ptr(coords), c_ll(_m(vox, seg)), ctypes.byref(geom), _seg(seg),
+         _ptr(moments), stream_ptr())
 
 
 def pfn_stats_finalize(moments, rows, w, gamma, beta, n_updates, rm, rv, scale, shift, mean, invstd, eps=1e-3,
-                       momentum=0.01):
-    call("a2x_pfn_stats_finalize", _ptr(moments), c_d(float(rows)), _ptr(w), _ptr(gamma), _ptr(beta), c_f(eps),
+                       momentum=0.01, seg=None):
+    call("a2x_pfn_stats_finalize", _ptr(moments), c_d(float(rows)), _seg(seg), _ptr(w), _ptr(gamma), _ptr(beta), c_f(eps),
          c_f(momentum), c_int(n_updates), _ptr(rm), _ptr(rv), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
          stream_ptr())
 
 
-def pfn_scatter(vox, num, coords, geom, w, scale, shift, agent_map, canvas, pillar_out=None, amax=None):
-    call("a2x_pfn_scatter", _ptr(vox), _ptr(num), _ptr(coords), c_ll(vox.shape[0]), ctypes.byref(geom), _ptr(w),
+def pfn_scatter(vox, num, coords, geom, w, scale, shift, agent_map, canvas, pillar_out=None, amax=None, seg=None):
+    call("a2x_pfn_scatter", _ptr(vox), _ptr(num), _ptr(coords), c_ll(_m(vox, seg)), ctypes.byref(geom), _seg(seg), _ptr(w),
          _ptr(scale), _ptr(shift), _ptr(agent_map), _ptr(canvas.hi), _lo(canvas), _ptr(pillar_out), _ptr(amax),
          stream_ptr())
 
 
 def pfn_bwd(vox, num, coords, geom, w, scale, shift, mean, invstd, agent_map, dcanvas, amax, moments, rows, acc_ws, dw,
-            dgamma, dbeta, accumulate=False):
-    call("a2x_pfn_bwd", _ptr(vox), _ptr(num), _ptr(coords), c_ll(vox.shape[0]), ctypes.byref(geom), _ptr(w), _ptr(scale),
+            dgamma, dbeta, accumulate=False, seg=None):
+    call("a2x_pfn_bwd", _ptr(vox), _ptr(num), _ptr(coords), c_ll(_m(vox, seg)), ctypes.byref(geom), _seg(seg), _ptr(w),
+         _ptr(scale),
          _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(agent_map), _ptr(dcanvas), _ptr(amax), _ptr(moments),
          c_d(float(rows)), _ptr(acc_ws), _ptr(dw), _ptr(dgamma), _ptr(dbeta), c_int(int(accumulate)), stream_ptr())
 
@@ -312,3 +335,21 @@ def det_loss(heads, A, K, targets, pos, class_ids, cls_weight, reg_coe, npos_ws,
     call("a2x_det_loss", _ptr(heads), c_int(cs), c_int(B), c_ll(H * W), c_int(A), c_int(K), _ptr(targets), _ptr(pos),
          _ptr(class_ids), c_f(cls_weight), c_f(reg_coe), _ptr(npos_ws), _ptr(dheads),
          c_int(_cs(dheads) if dheads is not None else 0), _ptr(loss3), stream_ptr())
+
+
+# voxelisation ---------------------------------------------------------------------------------------------------
+def voxelize_workspace_bytes(n_agents, total_points, nx, ny, nz, cap):
+    lib = _lib.load()
+    lib.a2x_voxelize_workspace_bytes.restype = ctypes.c_size_t
+    return lib.a2x_voxelize_workspace_bytes(c_int(n_agents), c_ll(total_points), c_int(nx), c_int(ny), c_int(nz), c_int(cap))
+
+
+def voxelize(points, offsets_dev, n_agents, lidar_range, voxel_size, max_points, max_voxels, cap, workspace, voxels,
+             coords, num_points, counts, ego_flags=None, strict_range=False):
+    """points: [total,4] f32 device; offsets_dev: int32 [n_agents+1] device. Slab outputs (see include/airv2x_b200.h)."""
+    rng = (c_f * 6)(*[float(v) for v in lidar_range])
+    vs = (c_f * 3)(*[float(v) for v in voxel_size])
+    call("a2x_voxelize", _ptr(points), _ptr(offsets_dev), c_int(n_agents), c_ll(points.shape[0]), rng, vs,
+         c_int(max_points), c_int(max_voxels), c_int(cap), _ptr(ego_flags), c_int(int(strict_range)), _ptr(workspace),
+         ctypes.c_size_t(workspace.numel()),
+         _ptr(voxels), _ptr(coords), _ptr(num_points), _ptr(counts), stream_ptr())

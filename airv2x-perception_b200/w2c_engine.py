@@ -209,6 +209,39 @@ class W2CEngine:
         ops.conv_fwd(y2, W["heads"][0], 1, 1, Act(heads), shift=W["heads.bias"])
         return y1, y2, heads
 
+    # ------------------------------------------------------------------ voxelisation (raw point clouds)
+    def _voxelize(self, raw, layout):
+        """raw: dict(points [P,4] f32 device, offsets int32 device [N+1], types [N] (scene-major), voxel_size,
+        lidar_range, max_points, max_voxels). Returns the per-type lidar dict over shared per-agent slabs."""
+        N = layout["n_total"]
+        pts = raw["points"]
+        cap = int(raw["max_voxels"])
+        nx, ny = layout["nx"], layout["ny"]
+        nz = 1
+        ws_bytes = ops.voxelize_workspace_bytes(N, pts.shape[0], nx, ny, nz, cap)
+        ws = self._buf("vox.ws", (ws_bytes,), torch.uint8)
+        vox = self._buf("vox.voxels", (N * cap, 32, 4))
+        coords = self._buf("vox.coords", (N * cap, 4), torch.int32)
+        num = self._buf("vox.num", (N * cap,), torch.int32)
+        counts = self._buf("vox.counts", (N,), torch.int32)
+        ops.voxelize(pts, raw["offsets"], N, raw["lidar_range"], raw["voxel_size"], int(raw["max_points"]), cap, cap, ws,
+                     vox, coords, num, counts, ego_flags=raw.get("ego_flags"),
+                     strict_range=bool(raw.get("filter", False)))
+        ident = layout.get("identity_map")
+        out = {}
+        for t in AGENT_TYPES:
+            ids = [i for i, tt in enumerate(raw["types"]) if tt == t]
+            if not ids:
+                continue
+            key = ("seg_ids", t, tuple(ids))
+            seg_ids = self.bufs.get(key)
+            if seg_ids is None:
+                seg_ids = torch.tensor(ids, dtype=torch.int32, device=self.device)
+                self.bufs[key] = seg_ids
+            out[t] = {"voxel_features": vox, "voxel_num_points": num, "voxel_coords": coords,
+                      "seg": ops.pfn_segments(seg_ids, counts, cap), "agent_map": ident, "counts": counts}
+        return out
+
     # ------------------------------------------------------------------ encoder (PillarVFE + scatter)
     def _encode(self, P, lidar, layout, training, record):
         n_total, ny, nx = layout["n_total"], layout["ny"], layout["nx"]
@@ -216,36 +249,41 @@ class W2CEngine:
         canvas.hi.zero_()
         if canvas.lo is not None:
             canvas.lo.zero_()
+        if "raw" in lidar:
+            lidar = self._voxelize(lidar["raw"], layout)
         for t in AGENT_TYPES:
             if t not in lidar:
                 continue
             vox, num, coords = lidar[t]["voxel_features"], lidar[t]["voxel_num_points"], lidar[t]["voxel_coords"]
+            seg = lidar[t].get("seg")
             la = self.args[t]["lidar"]
             geom = ops.pfn_geom(la["voxel_size"], la["lidar_range"], nx, ny)
             pre = TYPE_PREFIX[t] + ".0.0.pfn_layers.0"
             w = P[pre + ".linear.weight"]
             scale = self._buf("pfn.%s.scale" % t, (64,))
             shift = self._buf("pfn.%s.shift" % t, (64,))
-            amap = layout["agent_map"][t]
+            amap = lidar[t].get("agent_map")
+            if amap is None:
+                amap = layout["agent_map"][t]
             if training:
                 mean = self._buf("pfn.%s.mean" % t, (64,))
                 invstd = self._buf("pfn.%s.invstd" % t, (64,))
                 moments = self._buf("pfn.%s.moments" % t, (65,), torch.float64)
-                ops.pfn_moments(vox, num, coords, geom, moments)
+                ops.pfn_moments(vox, num, coords, geom, moments, seg=seg)
                 rows = vox.shape[0] * 32
                 ops.pfn_stats_finalize(moments, rows, w, P[pre + ".norm.weight"], P[pre + ".norm.bias"], 1,
                                        P[pre + ".norm.running_mean"], P[pre + ".norm.running_var"], scale, shift, mean,
-                                       invstd)
+                                       invstd, seg=seg)
                 amax = self._buf("pfn.%s.amax" % t, (vox.shape[0], 64), torch.uint8)
-                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax)
+                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax, seg=seg)
                 if record is not None:
                     record.append(dict(kind="pfn", type=t, vox=vox, num=num, coords=coords, geom=geom, pre=pre,
                                        scale=scale, shift=shift, mean=mean, invstd=invstd, amap=amap, amax=amax,
-                                       moments=moments, rows=rows))
+                                       moments=moments, rows=rows, seg=seg))
             else:
                 ops.bn_eval_affine(P[pre + ".norm.weight"], P[pre + ".norm.bias"], P[pre + ".norm.running_mean"],
                                    P[pre + ".norm.running_var"], scale, shift)
-                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas)
+                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, seg=seg)
         return canvas
 
     # ------------------------------------------------------------------ forward
@@ -351,7 +389,7 @@ class W2CEngine:
         if act.lo is None:
             return act.hi
         out = self._buf(name, act.shape)
-        torch.add(act.hi, act.lo, out=out)
+        ops.add2(act.hi, act.lo, out)
         return out
 
     # ------------------------------------------------------------------ loss (fused value + gradient)
@@ -496,5 +534,6 @@ class W2CEngine:
             acc = self._buf("pfn.%s.acc" % r["type"], (64 * 12,), torch.float64)
             ops.pfn_bwd(r["vox"], r["num"], r["coords"], r["geom"], P[pre + ".linear.weight"], r["scale"], r["shift"],
                         r["mean"], r["invstd"], r["amap"], d_canvas, r["amax"], r["moments"], r["rows"], acc,
-                        grads[pre + ".linear.weight"], grads[pre + ".norm.weight"], grads[pre + ".norm.bias"])
+                        grads[pre + ".linear.weight"], grads[pre + ".norm.weight"], grads[pre + ".norm.bias"],
+                        seg=r["seg"])
         return grads

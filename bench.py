@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — scenes/sec (forward + backward) of the Where2comm hot path, BASELINE.json configs[1]:
+airv2x_intermediate_where2com.yaml, 5 agents (2 vehicles, 2 RSUs, 1 drone) x 60k synthetic points, 200 x 704 BEV.
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 path (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm (oracle port) on the host CPUs
+
+A step = raw point clouds (resident in HBM) -> voxelise -> PillarVFE/scatter -> backbone -> mask -> fusion -> heads
+-> PointPillarLossMultiClass -> full backward (all parameter gradients), one scene per GPU, no optimizer.
+Prints ONE JSON line (see the driver contract). `e2e` times the same step through the public call with HOST
+(pinned) buffers: H2D of the clouds + labels and D2H of the loss inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+AGENTS = ["vehicle", "vehicle", "rsu", "rsu", "drone"]
+N_POINTS = 60000
+
+
+# ------------------------------------------------------------------------------------------------ synthetic workload
+def synth_cloud(seed, n, rng):
+    """x~N(0,35), y~N(0,15) clipped to the range, z~U(z range), intensity~U(0,1); fp32."""
+    g = np.random.default_rng(seed)
+    x = np.clip(g.normal(0.0, 35.0, n), rng[0] + 1e-3, rng[3] - 1e-3)
+    y = np.clip(g.normal(0.0, 15.0, n), rng[1] + 1e-3, rng[4] - 1e-3)
+    z = g.uniform(rng[2] + 1e-3, rng[5] - 1e-3, n)
+    i = g.uniform(0.0, 1.0, n)
+    return np.stack([x, y, z, i], 1).astype(np.float32)
+
+
+def synth_labels(seed, H, W, A, n_pos=40):
+    """planted positives: pos_equal_one / class_ids / regression targets in the collate layout of the reference
+    (data_utils/post_processor/voxel_postprocessor.py:392-430)."""
+    g = np.random.default_rng(seed)
+    pos = np.zeros((1, H, W, A), np.float32)
+    idx = g.choice(H * W * A, n_pos, replace=False)
+    pos.reshape(-1)[idx] = 1.0
+    cls = np.zeros((1, H, W, A), np.int32)
+    cls.reshape(-1)[idx] = g.integers(1, 7, n_pos)
+    tg = (g.normal(0, 0.3, (1, H, W, A * 7)).astype(np.float32)) * np.repeat(pos, 7, axis=-1)
+    return {"targets": tg, "pos_equal_one": pos, "class_ids": cls}
+
+
+def load_config():
+    return json.load(open(os.path.join(ROOT, "configs", "airv2x_intermediate_where2com.json")))
+
+
+def make_raw_scene(cfg, seed):
+    rng = cfg["preprocess"]["cav_lidar_range"]
+    clouds = [synth_cloud(seed * 100 + k, N_POINTS, rng) for k in range(len(AGENTS))]
+    offsets = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    return np.concatenate(clouds, 0), offsets
+
+
+def data_dict_from_raw(points, offsets, cfg, torch, pin=False):
+    def t(a):
+        x = torch.from_numpy(a)
+        return x.pin_memory() if pin else x
+
+    dd = {"raw_points": {"points": t(points), "offsets": t(offsets), "preprocess": cfg["preprocess"], "filter": True}}
+    for ty in ("vehicle", "rsu", "drone"):
+        n = sum(1 for a in AGENTS if a == ty)
+        dd[ty] = {"record_len": [n], "batch_idxs": [0] if n else []}
+    return dd
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.stop = False
+        self.max_mhz = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(o[0]))
+                self.max_mhz = float(o[1])
+                for n, v in zip(names, o[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, cfg, cores=None):
+    """The reference algorithm on the host CPUs: oracle port (torch CPU fp32 restatement, pinned bit-exact to the
+    real reference modules) — voxelise (C restatement) + forward (train mode) + loss + backward per step."""
+    import random
+
+    import torch
+
+    from oracle import voxelize as V, w2c_oracle as O
+
+    cores = cores or os.cpu_count()
+    torch.set_num_threads(cores)
+    margs = cfg["model_args"]
+    pts, offs = make_raw_scene(cfg, seed=0)
+    import a2x_import
+
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    shapes = {k: tuple(v.shape) for k, v in M.Airv2xWhere2com(margs).state_dict().items()}
+    sd = O.det_init_state_dict(shapes, seed=1)
+    gw, gb = O.gaussian_filter_params(5, 1.0)
+    sd["fusion_net.naive_communication.gaussian_filter.weight"] = gw
+    sd["fusion_net.naive_communication.gaussian_filter.bias"] = gb
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "gaussian" not in k
+              else v) for k, v in sd.items()}
+    pre = cfg["preprocess"]
+    H, W = 100, 352
+    lab = synth_labels(3, H, W, margs["anchor_number"])
+    labels = {"targets": torch.from_numpy(lab["targets"]).double(), "pos_equal_one": torch.from_numpy(lab["pos_equal_one"]).double(),
+              "class_ids": torch.from_numpy(lab["class_ids"]).long()}
+
+    def step():
+        per_type = {t: [] for t in O.AGENT_TYPES}
+        for k, ty in enumerate(AGENTS):
+            p = pts[offs[k]:offs[k + 1]]
+            p = V.mask_points(p, pre["cav_lidar_range"], ego_box=(k == 0))
+            per_type[ty].append(V.voxelize(p, pre["cav_lidar_range"], pre["args"]["voxel_size"], 32,
+                                           pre["args"]["max_voxel_train"]))
+        dd = {}
+        for ty in O.AGENT_TYPES:
+            col = V.collate(per_type[ty])
+            dd[ty] = {"batch_merged_lidar_features_torch": {k2: torch.from_numpy(v) for k2, v in col.items()},
+                      "record_len": torch.tensor([len(per_type[ty])], dtype=torch.int32), "batch_idxs": [0]}
+        for v in sd.values():
+            if v.requires_grad:
+                v.grad = None
+        out, _ = O.where2com_forward(sd, margs, dd, training=True)
+        loss = O.point_pillar_loss_multiclass(out, labels, margs["num_class"], cfg["loss_args"]["cls_weight"],
+                                              cfg["loss_args"]["reg"])[0]
+        loss.backward()
+        return float(loss)
+
+    # bounded sample: at most 1 warm-up + 3 timed full-size steps (each ~10-25 s of CPU work)
+    w_eff, k_eff = min(args.warmup, 1), max(1, min(args.steps, 3))
+    random.seed(0)
+    for _ in range(w_eff):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(k_eff):
+        step()
+    dt = (time.perf_counter() - t0) / k_eff
+    return {"value": 1.0 / dt, "ms_per_step": dt * 1e3, "cores": cores, "steps": k_eff, "warmup": w_eff,
+            "sample": "%d full-size scene step(s) (5 agents x 60k pts, voxelise + fwd + loss + bwd), %d warm-up" % (k_eff, w_eff)}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    cfg = load_config()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "scenes/sec (fwd+bwd) Where2Comm 5-agent 60k-pt"
+    config = {"workload": "airv2x_intermediate_where2com.yaml: 5 agents (2 veh, 2 rsu, 1 drone) x 60k pts, 200x704 BEV, "
+                          "1 scene per GPU, train-mode fwd + PointPillarLossMultiClass + bwd",
+              "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_reference(args, cfg)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "scenes/s", "n_gpus": args.gpus,
+                "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "scenes/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import a2x_import
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    libmod = a2x_import.pkg("_lib")
+    lib = libmod.load()
+    margs = cfg["model_args"]
+    torch.manual_seed(1)
+    model = M.Airv2xWhere2com(margs, precision=args.precision).to(dev)
+    model.train()
+    pts, offs = make_raw_scene(cfg, seed=rank)
+    H, W = 100, 352
+    lab_np = synth_labels(3 + rank, H, W, margs["anchor_number"])
+    dd_host = data_dict_from_raw(pts, offs, cfg, torch, pin=True)
+    lab_host = {k: torch.from_numpy(v).pin_memory() for k, v in lab_np.items()}
+    dd_dev = {k: (dict(v) if isinstance(v, dict) else v) for k, v in dd_host.items()}
+    dd_dev["raw_points"] = dict(dd_host["raw_points"])
+    dd_dev["raw_points"]["points"] = dd_host["raw_points"]["points"].to(dev)
+    dd_dev["raw_points"]["offsets"] = dd_host["raw_points"]["offsets"].to(dev)
+    lab_dev = {k: v.to(dev) for k, v in lab_host.items()}
+    cw, rc = cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"]
+    # data-parallel over scenes (the reference's DDP, tools/train.py:161-163): average parameter gradients
+    allreduce_grads = a2x_import.pkg("dist").GradAverager(model.parameters())
+
+    def step(dd, lab):
+        loss3 = model.train_step(dd, lab, cw, rc)
+        allreduce_grads()
+        return loss3
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(dd, lab, n, read_loss):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        last = None
+        for _ in range(n):
+            last = step(dd, lab)
+            if read_loss:
+                last = float(last.sum().item())  # D2H read of the step's result
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for _ in range(max(args.warmup, 3)):
+        step(dd_dev, lab_dev)
+    sync_all()
+    l0 = lib.a2x_launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms, loss3 = timed(dd_dev, lab_dev, args.steps, False)
+    launches = lib.a2x_launch_count() - l0
+    # end-to-end: host pinned clouds + labels -> H2D, loss -> D2H, every step
+    for _ in range(2):
+        step(dd_host, lab_host)
+    ms_e2e, loss_val = timed(dd_host, lab_host, args.steps, True)
+    h2d = pts.nbytes + offs.nbytes + sum(v.nbytes for v in lab_np.values())
+    value = world * 1000.0 / ms
+    line = {"metric": metric, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32x3 (3-pass split TF32 tensor-core GEMMs, fp32-equivalent; fp32 elsewhere)"
+            if args.precision == "tf32x3" else "tf32", "data": "synthetic", "config": config,
+            "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "scenes/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 24, "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "loss": loss_val, "clocks": clk.summary()}
+
+    if rank == 0 and not args.no_roofline:
+        line["roofline"] = roofline_pass(model, libmod, dd_dev, lab_dev, cw, rc, args.precision, torch)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_reference(argparse.Namespace(steps=1, warmup=0), cfg)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "scenes/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_pass(model, libmod, dd, lab, cw, rc, precision, torch):
+    """One instrumented step: CUDA events around every C-ABI call on the launching stream. The dominant kernel is the
+    tcgen05 tap-GEMM (conv fwd / dgrad / deconv): achieved = algorithmic FLOPs (2*M*N*K of the convolution, counted
+    once regardless of the 3 split passes) / summed launch durations."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        pk = json.load(open(peaks_path))
+        peak, src = float(pk["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    else:
+        peak, src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+    libmod.PROFILE = []
+    model.train_step(dd, lab, cw, rc)
+    torch.cuda.synchronize()
+    prof, libmod.PROFILE = libmod.PROFILE, None
+    groups = {}
+    total_ms = 0.0
+    for name, cargs, e0, e1 in prof:
+        ms = e0.elapsed_time(e1)
+        total_ms += ms
+        g = groups.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0})
+        g["ms"] += ms
+        g["calls"] += 1
+        if name in ("a2x_conv2d_fwd", "a2x_conv2d_dgrad", "a2x_conv2d_wgrad", "a2x_deconv_fwd", "a2x_deconv_dgrad",
+                    "a2x_deconv_wgrad"):
+            s = cargs[0]._obj
+            if name.startswith("a2x_conv2d"):
+                ho, wo = (s.h - 1) // s.stride + 1, (s.w - 1) // s.stride + 1
+                g["flops"] += 2.0 * s.n * ho * wo * s.cout * s.cin * s.ksize * s.ksize
+            else:
+                g["flops"] += 2.0 * s.n * s.h * s.w * s.cin * s.cout * s.stride * s.stride
+    tg = [groups[k] for k in ("a2x_conv2d_fwd", "a2x_conv2d_dgrad", "a2x_deconv_fwd", "a2x_deconv_dgrad") if k in groups]
+    tg_ms = sum(g["ms"] for g in tg)
+    tg_fl = sum(g["flops"] for g in tg)
+    achieved = tg_fl / (tg_ms * 1e-3) / 1e12 if tg_ms > 0 else 0.0
+    hw_mult = 3.0 if precision == "tf32x3" else 1.0
+    top = sorted(((k, round(v["ms"], 3), v["calls"]) for k, v in groups.items()), key=lambda x: -x[1])[:8]
+    return {"bound": "tensor", "kernel": "tapgemm_kernel (tcgen05.mma.kind::tf32; conv fwd + dgrad + deconv launches)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": src, "algorithmic_gflop_per_step": tg_fl / 1e9, "kernel_ms_per_step": tg_ms,
+            "share_of_step": tg_ms / total_ms if total_ms else None,
+            "hw_tflops_executed": achieved * hw_mult,
+            "note": "peak is the measured dense bf16 number; kind::tf32 runs at half the bf16 rate and tf32x3 executes "
+                    "3 MMAs per algorithmic FLOP, so the hardware-side tensor utilisation is hw_tflops_executed / (peak/2)",
+            "wgrad": {"ms": groups.get("a2x_conv2d_wgrad", {}).get("ms"),
+                      "tflops": (groups["a2x_conv2d_wgrad"]["flops"] / (groups["a2x_conv2d_wgrad"]["ms"] * 1e-3) / 1e12)
+                      if "a2x_conv2d_wgrad" in groups else None},
+            "top_calls_ms": top}
+
+
+if __name__ == "__main__":
+    main()

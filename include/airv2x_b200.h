@@ -27,6 +27,7 @@ const char* a2x_last_error(void);
 int a2x_version(void);
 void a2x_debug_set(int key, int value);
 int a2x_device_info(int* sm_count, int* cc_major, int* cc_minor);
+unsigned long long a2x_launch_count(void); /* kernels launched by this library since load */
 
 /* ---------------------------------------------------------------- dense contractions
  * Replace nn.Conv2d / nn.ConvTranspose2d forward + autograd on the path:
@@ -83,6 +84,8 @@ int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo,
 /* ---------------------------------------------------------------- operand split
  * hi = tf32_rn(x), lo = x - hi (n multiple of 4). */
 int a2x_split_tf32(const float* x, long long n, float* hi, float* lo, a2x_stream_t stream);
+/* out = a + b (recombine a split pair) */
+int a2x_add2(const float* a, const float* b, long long n, float* out, a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- BatchNorm / ReLU / masks (HBM-bound)
  * Replace nn.BatchNorm2d(eps 1e-3, momentum 0.01) + nn.ReLU and their autograd
@@ -117,6 +120,22 @@ int a2x_sums_to_float(const double* sums, int C, float* out, int accumulate, a2x
 /* torch.count_nonzero (airv2x_where2com.py:122) */
 int a2x_count_nonzero(const float* x, long long n, unsigned long long* out, a2x_stream_t stream);
 
+/* ---------------------------------------------------------------- voxelisation
+ * Replaces SpVoxelPreprocessor.preprocess -> spconv Point2VoxelCPU3d.point_to_voxel + collate_batch
+ * (opencood/data_utils/pre_processor/sp_voxel_preprocessor.py:59-72, :96-116, :142-175), bit-exact with the
+ * sequential first-come algorithm. points: [total][4] f32 of all agents concatenated, offsets_dev[n_agents+1]
+ * (device). Outputs are fixed-capacity slabs per agent (cap >= max_voxels): voxels [n][cap][32][4],
+ * coords [n][cap][4] (agent,z,y,x), num_points [n][cap], counts [n] (voxels per agent, device).
+ */
+size_t a2x_voxelize_workspace_bytes(int n_agents, long long total_points, int nx, int ny, int nz, int cap);
+/* ego_flags (device u8 per agent, may be NULL) / strict_range fold the dataset's point filters in
+ * (mask_ego_points / mask_points_by_range, opencood/utils/pcd_utils.py:136-190): dropped points keep their place in
+ * the input order, so the first-come semantics are unchanged. */
+int a2x_voxelize(const float* points, const int* offsets_dev, int n_agents, long long total_points, const float* range6,
+                 const float* vsize3, int max_points, int max_voxels, int cap, const unsigned char* ego_flags,
+                 int strict_range, void* workspace, size_t workspace_bytes, float* voxels, int* coords, int* num_points,
+                 int* counts, a2x_stream_t stream);
+
 /* ---------------------------------------------------------------- PillarVFE + PointPillarScatter
  * Replace PillarVFE.forward / PFNLayer.forward / PointPillarScatter.forward
  * (opencood/models/common_modules/airv2x_pillar_vfe.py:105-160, :27-49; point_pillar_scatter.py:15-82).
@@ -129,20 +148,30 @@ typedef struct {
     float x_offset, y_offset, z_offset; /* voxel/2 + range_lo */
     int nx, ny;
 } a2x_pfn_geom;
+/* Optional segmented addressing (voxeliser slabs, no host sync): flat pillar p in [0, nseg*seg_cap) lives in slab
+ * seg_ids[p / seg_cap] (NULL ids = identity) at index p % seg_cap and is valid while < seg_counts[slab] (device
+ * array). Pass seg == NULL for the reference dict layout (plain [0, m)). With segments, `m` / `rows` are ignored. */
+typedef struct {
+    const int* seg_ids;
+    const int* seg_counts;
+    int seg_cap, nseg;
+} a2x_pfn_segments;
 /* moments65 = [sum f (10), upper triangle of sum f f^T (55)] over all M*32 rows (zeroed here) */
 int a2x_pfn_moments(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
-                    double* moments65, a2x_stream_t stream);
+                    const a2x_pfn_segments* seg, double* moments65, a2x_stream_t stream);
 /* BatchNorm1d batch statistics of W f from the moments (rows = M*32) */
-int a2x_pfn_stats_finalize(const double* moments65, double rows, const float* w, const float* gamma, const float* beta,
+int a2x_pfn_stats_finalize(const double* moments65, double rows, const a2x_pfn_segments* seg, const float* w,
+                           const float* gamma, const float* beta,
                            float eps, float momentum, int n_updates, float* running_mean, float* running_var,
                            float* scale, float* shift, float* mean_out, float* invstd_out, a2x_stream_t stream);
 /* canvas[agent_map[a]][y][x][:] = max_slot relu(scale*(W f)+shift); optional pillar_out [M][64], amax [M][64] u8 */
 int a2x_pfn_scatter(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
-                    const float* w, const float* scale, const float* shift, const int* agent_map, float* canvas,
-                    float* canvas_lo, float* pillar_out, unsigned char* amax, a2x_stream_t stream);
+                    const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift,
+                    const int* agent_map, float* canvas, float* canvas_lo, float* pillar_out, unsigned char* amax,
+                    a2x_stream_t stream);
 /* train-mode backward to (W, gamma, beta) given d(canvas); acc_ws = 64*12 doubles of workspace */
 int a2x_pfn_bwd(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
-                const float* w, const float* scale, const float* shift, const float* mean, const float* invstd,
+                const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift, const float* mean, const float* invstd,
                 const int* agent_map, const float* dcanvas, const unsigned char* amax, const double* moments65,
                 double rows, double* acc_ws, float* dw, float* dgamma, float* dbeta, int accumulate,
                 a2x_stream_t stream);

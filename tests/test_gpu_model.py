@@ -1,0 +1,142 @@
+"""GPU (-m gpu): the drop-in Airv2xWhere2com against the golden vectors recorded from the REAL reference and against
+the oracle, plus size-independent properties at the BASELINE size.
+Tolerance (north_star): BEV features / logits max-abs <= 1e-3 (fp32 reference); integer outputs exact."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import w2c_common as C
+from oracle import w2c_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def small():
+    import a2x_import
+
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    cfg, gold = C.load_small()
+    model = M.Airv2xWhere2com(cfg["model_args"])
+    sd = C.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda()
+    dd = C.golden_scene(cfg, gold)
+    return cfg, gold, model, sd, dd
+
+
+def test_eval_matches_reference_golden(small):
+    cfg, gold, model, sd, dd = small
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        out = model(C.to_device(dd, "cuda"))
+    for k in ("psm", "rm", "obj"):
+        assert out[k].shape == gold["eval_" + k].shape
+        assert np.abs(out[k].cpu().numpy() - gold["eval_" + k]).max() < TOL, k
+    assert abs(float(out["com"]) - float(gold["eval_com"])) < 1e-6
+    assert out["comm_rate"] == int(gold["eval_comm_rate"]) and out["mask"] == 0
+
+
+def test_raw_point_path_equals_voxel_dict_path(small):
+    """GPU voxelisation + filters feed the same pillars as the CPU-voxelised reference dict"""
+    cfg, gold, model, sd, dd = small
+    model.load_state_dict(sd)
+    model.eval()
+    rng = cfg["preprocess"]["cav_lidar_range"]
+    agents = [str(a) for a in gold["agents"]]
+    clouds = [O.synth_points(int(gold["scene_seed"]) * 100 + k, int(gold["n_points"]), rng, (10.0, 5.0)) for k in range(len(agents))]
+    offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    pre = dict(cfg["preprocess"])
+    pre["args"] = dict(pre["args"])
+    pre["args"]["max_voxel_test"] = pre["args"]["max_voxel_train"]           # the golden scene used the train cap
+    raw = {"raw_points": {"points": torch.from_numpy(np.concatenate(clouds, 0)), "offsets": torch.from_numpy(offs),
+                          "preprocess": pre, "filter": True}}
+    for t in O.AGENT_TYPES:
+        n = sum(1 for a in agents if a == t)
+        raw[t] = {"record_len": [n], "batch_idxs": [0] if n else []}
+    with torch.no_grad():
+        a = model(raw)
+        b = model(C.to_device(dd, "cuda"))
+    for k in ("psm", "rm", "obj"):
+        assert torch.equal(a[k], b[k]), k
+    assert a["comm_rate"] == b["comm_rate"]
+
+
+def test_train_step_matches_reference_golden(small):
+    cfg, gold, model, sd, dd = small
+    model.load_state_dict(sd)
+    model.train()
+    H, W = gold["train_psm"].shape[2:]
+    labels = O.make_labels(int(gold["label_seed"]), 1, H, W, cfg["model_args"]["anchor_number"])
+    # (1) reference-style use: forward -> the reference's loss (oracle restatement, torch ops) -> autograd backward
+    random.seed(int(gold["train_K_seed"]))
+    out = model(C.to_device(dd, "cuda"))
+    for k in ("psm", "rm", "obj"):
+        assert np.abs(out[k].detach().cpu().numpy() - gold["train_" + k]).max() < TOL, k
+    assert abs(float(out["com"]) - float(gold["train_com"])) < 1e-6
+    cpu_out = {k: out[k].cpu() for k in ("psm", "rm", "obj")}
+    loss = O.point_pillar_loss_multiclass(cpu_out, labels, cfg["model_args"]["num_class"], cfg["loss_args"]["cls_weight"],
+                                          cfg["loss_args"]["reg"])[0]
+    assert abs(float(loss) - float(gold["train_loss"])) < 1e-3 * abs(float(gold["train_loss"]))
+    model.zero_grad()
+    loss.backward()
+    g_auto = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    # running statistics after one step (block 0 updated three times, pass-A BNs twice, then the fused pass)
+    for n, b in model.named_buffers():
+        if "buf_" + n in gold.files:
+            assert np.abs(C.sample(b, 64) - gold["buf_" + n]).max() < 1e-4, n
+    # (2) fused fast path: same forward + fused loss kernel + backward
+    model.load_state_dict(sd)
+    random.seed(int(gold["train_K_seed"]))
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])
+    assert abs(float(loss3.sum()) - float(gold["train_loss"])) < 1e-3 * abs(float(gold["train_loss"]))
+    # gradients. Heads / shrink / deblock gradients are tight; deeper ones pass through ReLU / max / top-K pattern
+    # flips, where the oracle itself moves by ~1% between fp32 and fp64 (DESIGN.md "gradient parity"), hence the
+    # norm-wise bound there. Per-op backward kernels are checked tightly in test_gpu_kernels.py.
+    errs = {}
+    for n, p in model.named_parameters():
+        if "grad_" + n not in gold.files:
+            continue
+        ref = gold["grad_" + n]
+        got = C.sample(p.grad, 512)
+        errs[n] = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30)
+        assert np.abs(C.sample(g_auto[n], 512) - got).max() <= 1e-5 * (np.abs(ref).max() + 1e-30) + 1e-7, n  # both paths agree
+    for n in ("cls_head.weight", "cls_head.bias", "reg_head.weight", "obj_head.weight"):
+        assert errs[n] < 1e-3, (n, errs[n])
+    assert max(errs.values()) < 0.15 and float(np.median(list(errs.values()))) < 0.03, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_baseline_size_properties():
+    """BASELINE config 1 (5 agents x 60k points, 200 x 704): determinism, invariance of the fused output to the order
+    of the NON-ego agents of one type, and the documented output contract."""
+    import a2x_import
+    import bench
+
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    cfg = bench.load_config()
+    torch.manual_seed(0)
+    model = M.Airv2xWhere2com(cfg["model_args"]).cuda().eval()
+    with torch.no_grad():
+        model.cls_head.bias -= 4.0
+    pts, offs = bench.make_raw_scene(cfg, seed=0)
+    dd = bench.data_dict_from_raw(pts, offs, cfg, torch)
+    with torch.no_grad():
+        a = model(dd)
+        b = model(dd)
+    assert a["psm"].shape == (1, 14, 100, 352) and a["rm"].shape == (1, 14, 100, 352) and a["obj"].shape == (1, 2, 100, 352)
+    for k in ("psm", "rm", "obj"):
+        assert torch.equal(a[k], b[k])                                     # deterministic
+        assert torch.isfinite(a[k]).all()
+    assert 0.0 < float(a["com"]) <= 1.0 and a["comm_rate"] > 0
+    # swap the two RSU agents (agents 2 and 3): fusion only distinguishes the ego row
+    p2 = np.concatenate([pts[offs[0]:offs[2]], pts[offs[3]:offs[4]], pts[offs[2]:offs[3]], pts[offs[4]:offs[5]]], 0)
+    o2 = np.array([offs[0], offs[1], offs[2], offs[2] + (offs[4] - offs[3]), offs[4], offs[5]], np.int32)
+    with torch.no_grad():
+        c = model(bench.data_dict_from_raw(p2, o2, cfg, torch))
+    for k in ("psm", "rm", "obj"):
+        assert float((a[k] - c[k]).abs().max()) < 1e-4, k
+    assert a["comm_rate"] == c["comm_rate"]

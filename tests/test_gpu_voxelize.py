@@ -1,0 +1,83 @@
+"""GPU (-m gpu): the parallel voxeliser is bit-exact with the sequential oracle (pillar set, (z,y,x), voxel ids,
+per-pillar point membership AND order), including the dataset's point filters, ragged / empty agents, the
+max_voxels cap and > 32 points per pillar, at small and at BASELINE (60k points, 704 x 200) sizes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(ops, clouds, rng, vs, max_voxels, filt):
+    n = len(clouds)
+    offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    pts = torch.from_numpy(np.concatenate(clouds, 0) if offs[-1] > 0 else np.zeros((0, 4), np.float32)).cuda()
+    if pts.shape[0] == 0:
+        pts = torch.zeros(1, 4, device="cuda")[:0]
+    grid = [int(round((rng[3 + j] - rng[j]) / vs[j])) for j in range(3)]
+    cap = max_voxels
+    ws = torch.empty(ops.voxelize_workspace_bytes(n, max(int(offs[-1]), 1), grid[0], grid[1], grid[2], cap), dtype=torch.uint8, device="cuda")
+    vox = torch.full((n * cap, 32, 4), 7.0, device="cuda")
+    coords = torch.full((n * cap, 4), -9, dtype=torch.int32, device="cuda")
+    num = torch.full((n * cap,), -9, dtype=torch.int32, device="cuda")
+    counts = torch.full((n,), -9, dtype=torch.int32, device="cuda")
+    ego = torch.tensor([1] + [0] * (n - 1), dtype=torch.uint8, device="cuda") if filt else None
+    ops.voxelize(pts, torch.from_numpy(offs).cuda(), n, rng, vs, 32, max_voxels, cap, ws, vox, coords, num, counts,
+                 ego_flags=ego, strict_range=filt)
+    torch.cuda.synchronize()
+    return vox.cpu().numpy().reshape(n, cap, 32, 4), coords.cpu().numpy().reshape(n, cap, 4), num.cpu().numpy().reshape(n, cap), counts.cpu().numpy()
+
+
+def check(ops, clouds, rng, vs, max_voxels, filt):
+    from oracle import voxelize as V
+
+    vox, coords, num, counts = run_gpu(ops, clouds, rng, vs, max_voxels, filt)
+    for a, c in enumerate(clouds):
+        p = V.mask_points(c, rng, ego_box=(a == 0)) if filt else c
+        o = V.voxelize(p, rng, vs, 32, max_voxels)
+        m = o["voxel_features"].shape[0]
+        assert counts[a] == m, (a, counts[a], m)
+        assert np.array_equal(coords[a, :m, 1:], o["voxel_coords"])
+        assert np.all(coords[a, :m, 0] == a)
+        assert np.array_equal(num[a, :m], o["voxel_num_points"])
+        assert np.array_equal(vox[a, :m].view(np.uint32), o["voxel_features"].view(np.uint32))   # bit-exact incl. order
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import a2x_import
+
+    return a2x_import.pkg("ops")
+
+
+def test_small_ragged_and_empty_agents(ops):
+    from oracle import w2c_oracle as O
+
+    rng, vs = [-25.6, -12.8, -3, 25.6, 12.8, 1], [0.4, 0.4, 4]
+    clouds = [O.synth_points(1, 3000, rng, (10, 5)), np.zeros((0, 4), np.float32), O.synth_points(2, 17, rng, (10, 5)),
+              O.synth_points(3, 5000, rng, (3, 2))]
+    check(ops, clouds, rng, vs, 32000, False)
+    check(ops, clouds, rng, vs, 32000, True)
+
+
+def test_cap_and_dense_pillars(ops):
+    rng, vs = [-25.6, -12.8, -3, 25.6, 12.8, 1], [0.4, 0.4, 4]
+    g = np.random.default_rng(5)
+    dense = np.concatenate([g.uniform(-1, 1, (4000, 2)), g.uniform(-2.9, 0.9, (4000, 1)), g.uniform(0, 1, (4000, 1))], 1).astype(np.float32)
+    one = np.tile(np.array([[5.05, 5.05, 0, 0]], np.float32), (200, 1))
+    one[:, 3] = np.arange(200)
+    wide = np.concatenate([g.uniform(-30, 30, (6000, 2)), g.uniform(-4, 2, (6000, 1)), g.uniform(0, 1, (6000, 1))], 1).astype(np.float32)
+    wide[7] = np.nan
+    check(ops, [dense, one, wide], rng, vs, 32000, False)      # up to hundreds of points per pillar, NaN, out of range
+    check(ops, [wide, dense], rng, vs, 100, False)             # max_voxels cap: later pillars dropped with all points
+    check(ops, [wide, dense], rng, vs, 100, True)
+
+
+def test_baseline_size(ops):
+    import bench
+
+    cfg = bench.load_config()
+    rng, vs = cfg["preprocess"]["cav_lidar_range"], cfg["preprocess"]["args"]["voxel_size"]
+    clouds = [bench.synth_cloud(k, 60000, rng) for k in range(5)]
+    check(ops, clouds, rng, vs, 32000, True)                   # train cap is hit with 60k points
+    check(ops, clouds[:2], rng, vs, 70000, False)
