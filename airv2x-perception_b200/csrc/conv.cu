@@ -369,7 +369,8 @@ int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, fl
 }
 
 int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
-                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, a2x_stream_t stream) {
+                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, double* stats,
+                   a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
     A2X_REQUIRE(x && w_fwd && y && x_cs >= s->cin && y_cs >= s->cout && x_cs % 4 == 0 && y_cs % 4 == 0,
                 "bad conv2d_fwd pointers/strides");
@@ -393,6 +394,9 @@ int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, i
     p.shift = shift;
     p.relu = relu;
     p.accumulate = 0;
+    p.stats = stats;
+    p.stat_c = s->cout;
+    A2X_REQUIRE(!stats || (!scale && !shift && !relu), "conv2d_fwd: fused statistics are of the raw conv output");
     return run_tg(p, ho, wo, s->n, s->cout, (cudaStream_t)stream);
 }
 
@@ -469,7 +473,8 @@ int a2x_conv2d_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo,
 }
 
 int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
-                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, a2x_stream_t stream) {
+                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, double* stats,
+                   a2x_stream_t stream) {
     if (int r = check_shape(s, true)) return r;
     A2X_REQUIRE(x && w_fwd && y && x_cs >= s->cin && y_cs >= s->cout && x_cs % 4 == 0 && y_cs % 4 == 0,
                 "bad deconv_fwd pointers/strides");
@@ -501,6 +506,9 @@ int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, i
     p.shift = shift;
     p.relu = relu;
     p.accumulate = 0;
+    p.stats = stats;
+    p.stat_c = s->cout;
+    A2X_REQUIRE(!stats || (!scale && !shift && !relu), "deconv_fwd: fused statistics are of the raw output");
     return run_tg(p, s->h, s->w, s->n, ncols, (cudaStream_t)stream);
 }
 

@@ -64,23 +64,36 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const float* __rest
         }
     }
     if (prow < ppb) {
-        for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
-            const float4 v = *reinterpret_cast<const float4*>(x + p * x_cs + cq * 4);
-            const float a[4] = {v.x, v.y, v.z, v.w};
-            if (MODE == 0) {
+        constexpr int U = 4;  // pixels in flight per thread
+        const long long pstride = (long long)gridDim.x * ppb;
+        for (long long p0 = (long long)blockIdx.x * ppb + prow; p0 < npix; p0 += pstride * U) {
+            float4 xv[U], zv[U];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    s0[e] += a[e];
-                    s1[e] += a[e] * a[e];
+            for (int u = 0; u < U; ++u) {
+                const long long p = p0 + u * pstride;
+                if (p < npix) {
+                    xv[u] = *reinterpret_cast<const float4*>(x + p * x_cs + cq * 4);
+                    if (MODE == 1) zv[u] = *reinterpret_cast<const float4*>(z + p * z_cs + cq * 4);
                 }
-            } else {
-                const float4 zz = *reinterpret_cast<const float4*>(z + p * z_cs + cq * 4);
-                const float b[4] = {zz.x, zz.y, zz.z, zz.w};
+            }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float g = (b[e] * sc[e] + sh[e] > 0.f) ? a[e] : 0.f;
-                    s0[e] += g;
-                    s1[e] += g * (b[e] - mu[e]) * is[e];
+            for (int u = 0; u < U; ++u) {
+                if (p0 + u * pstride >= npix) break;
+                const float a[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                if (MODE == 0) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s0[e] += a[e];
+                        s1[e] += a[e] * a[e];
+                    }
+                } else {
+                    const float b[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float g = (b[e] * sc[e] + sh[e] > 0.f) ? a[e] : 0.f;
+                        s0[e] += g;
+                        s1[e] += g * (b[e] - mu[e]) * is[e];
+                    }
                 }
             }
         }
@@ -171,27 +184,40 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
                                                          float* __restrict__ y_lo, int y_cs, long long npix, int C) {
     const int q = C >> 2;
     const long long total = npix * q;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / q;
-        const int c = (int)(i - p * q) * 4;
-        float4 v = *reinterpret_cast<const float4*>(x + p * x_cs + c);
-        if (scale != nullptr) {
-            const float4 s = *reinterpret_cast<const float4*>(scale + c);
-            v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+        float4 v[U];
+        long long p[U];
+        int c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            p[u] = i / q;
+            c[u] = (int)(i - p[u] * q) * 4;
+            if (i < total) v[u] = *reinterpret_cast<const float4*>(x + p[u] * x_cs + c[u]);
         }
-        if (shift != nullptr) {
-            const float4 b = *reinterpret_cast<const float4*>(shift + c);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride >= total) break;
+            float4 t = v[u];
+            if (scale != nullptr) {
+                const float4 s = *reinterpret_cast<const float4*>(scale + c[u]);
+                t.x *= s.x; t.y *= s.y; t.z *= s.z; t.w *= s.w;
+            }
+            if (shift != nullptr) {
+                const float4 b = *reinterpret_cast<const float4*>(shift + c[u]);
+                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+            }
+            if (relu) {
+                t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+            if (mask != nullptr) {
+                const float m = mask[p[u]];
+                t.x *= m; t.y *= m; t.z *= m; t.w *= m;
+            }
+            store_split(y + p[u] * y_cs + c[u], y_lo ? y_lo + p[u] * y_cs + c[u] : nullptr, t);
         }
-        if (relu) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-        }
-        if (mask != nullptr) {
-            const float m = mask[p];
-            v.x *= m; v.y *= m; v.z *= m; v.w *= m;
-        }
-        store_split(y + p * y_cs + c, y_lo ? y_lo + p * y_cs + c : nullptr, v);
     }
 }
 
@@ -208,24 +234,40 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
                                                                 int dz_cs, long long npix, int C) {
     const int q = C >> 2;
     const long long total = npix * q;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / q;
-        const int c = (int)(i - p * q) * 4;
-        const float4 d4 = *reinterpret_cast<const float4*>(dy + p * dy_cs + c);
-        const float4 z4 = *reinterpret_cast<const float4*>(z + p * z_cs + c);
-        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-        const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-        float o[4];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    constexpr int U = 2;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+        float4 d4[U], z4[U];
+        long long p[U];
+        int c[U];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float sc = scale[c + e], sh = shift[c + e];
-            const float g = (zz[e] * sc + sh > 0.f) ? d[e] : 0.f;
-            const float zh = (zz[e] - mean[c + e]) * invstd[c + e];
-            const float mg = (float)(sums[c + e] / count), mgz = (float)(sums[C + c + e] / count);
-            o[e] = sc * (g - mg - zh * mgz);  // scale = gamma * invstd
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            p[u] = i / q;
+            c[u] = (int)(i - p[u] * q) * 4;
+            if (i < total) {
+                d4[u] = *reinterpret_cast<const float4*>(dy + p[u] * dy_cs + c[u]);
+                z4[u] = *reinterpret_cast<const float4*>(z + p[u] * z_cs + c[u]);
+            }
         }
-        store_split(dz + p * dz_cs + c, dz_lo ? dz_lo + p * dz_cs + c : nullptr, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride >= total) break;
+            const float d[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+            const float zz[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ch = c[u] + e;
+                const float sc = scale[ch], sh = shift[ch];
+                const float g = (zz[e] * sc + sh > 0.f) ? d[e] : 0.f;
+                const float zh = (zz[e] - mean[ch]) * invstd[ch];
+                const float mg = (float)(sums[ch] / count), mgz = (float)(sums[C + ch] / count);
+                o[e] = sc * (g - mg - zh * mgz);  // scale = gamma * invstd
+            }
+            store_split(dz + p[u] * dz_cs + c[u], dz_lo ? dz_lo + p[u] * dz_cs + c[u] : nullptr,
+                        make_float4(o[0], o[1], o[2], o[3]));
+        }
     }
 }
 
@@ -309,7 +351,7 @@ int a2x_channel_stats(const float* x, int x_cs, long long npix, int C, double* s
     A2X_REQUIRE(x && sums && npix > 0, "channel_stats: bad args");
     const int ppb = 256 / (C / 4);
     long long blocks = (npix + ppb - 1) / ppb;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 2) blocks = 148 * 2;  // few blocks: the tail is 2C same-address double atomics per block
     channel_reduce_kernel<0><<<(int)blocks, 256, 2 * 256 * 4 * sizeof(float), (cudaStream_t)stream>>>(
         x, x_cs, nullptr, 0, nullptr, nullptr, nullptr, nullptr, npix, C, sums);
     A2X_LAUNCHED();
@@ -357,7 +399,7 @@ int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs,
     A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && npix > 0, "bn_relu_bwd_reduce: bad args");
     const int ppb = 256 / (C / 4);
     long long blocks = (npix + ppb - 1) / ppb;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 2) blocks = 148 * 2;  // few blocks: the tail is 2C same-address double atomics per block
     channel_reduce_kernel<1><<<(int)blocks, 256, 2 * 256 * 4 * sizeof(float), (cudaStream_t)stream>>>(
         dy, dy_cs, z, z_cs, scale, shift, mean, invstd, npix, C, sums);
     A2X_LAUNCHED();

@@ -310,11 +310,17 @@ __global__ void __launch_bounds__(256) pfn_bwd_kernel(const float* __restrict__ 
             for (int k = 0; k < NF; ++k) a[h][2 + k] += gg * fs[k];
         }
     }
+    // block-level reduction first: 8 warps -> one smem copy -> 768 global double atomics per block
+    __shared__ float sacc[NC * 12];
+    for (int i = threadIdx.x; i < NC * 12; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int k = 0; k < 12; ++k)
-            if (a[h][k] != 0.f) atomicAdd(&acc[(lane + 32 * h) * 12 + k], (double)a[h][k]);
+        for (int k = 0; k < 12; ++k) atomicAdd(&sacc[(lane + 32 * h) * 12 + k], a[h][k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NC * 12; i += blockDim.x)
+        if (sacc[i] != 0.f) atomicAdd(&acc[i], (double)sacc[i]);
 }
 
 // dW_c = gamma*invstd * (G - (A/m) S1 - (Bz/m) * invstd * (S2 W_c - mu S1)),  dgamma = Bz, dbeta = A
@@ -342,9 +348,9 @@ __global__ void pfn_bwd_finalize_kernel(const double* __restrict__ acc, const do
     dbeta[c] = accumulate ? dbeta[c] + (float)A : (float)A;
 }
 
-static int warp_grid(long long M) {
+static int warp_grid(long long M, int cap_blocks = 148 * 8) {
     long long b = (M + 7) / 8;  // 8 warps per block
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > cap_blocks) b = cap_blocks;
     if (b < 1) b = 1;
     return (int)b;
 }
@@ -433,7 +439,7 @@ int a2x_pfn_bwd(const float* voxels, const int* num_points, const int* coords, l
                 "pfn_bwd: bad args");
     cudaStream_t st = (cudaStream_t)stream;
     A2X_CHECK_CUDA(cudaMemsetAsync(acc_ws, 0, sizeof(double) * NC * 12, st));
-    pfn_bwd_kernel<<<warp_grid(m), 256, 0, st>>>(voxels, num_points, coords, make_geom(geom), m, sg, w, scale, shift,
+    pfn_bwd_kernel<<<warp_grid(m, 148 * 4), 256, 0, st>>>(voxels, num_points, coords, make_geom(geom), m, sg, w, scale, shift,
                                                 mean, invstd, agent_map, dcanvas, amax, acc_ws);
     A2X_LAUNCHED();
     pfn_bwd_finalize_kernel<<<1, 64, 0, st>>>(acc_ws, moments65, rows, sg, w, scale, mean, invstd, dw, dgamma, dbeta,

@@ -55,6 +55,10 @@ struct TgParams {
     const float* shift;  // may be null
     int relu;
     int accumulate;      // out += result
+    // fused BatchNorm batch statistics of the raw result: stats[ch] += sum, stats[stat_c + ch] += sum of squares,
+    // ch = col % sub_c (or col when sub_c >= ncols). Null = off.
+    double* stats;
+    int stat_c;
 };
 
 template <int BN, int STAGES>
@@ -62,8 +66,24 @@ struct TgSmem {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = TG_A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+    static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int TOTAL = STAT_OFF + 4 * 2 * BN * 4 + 1024;  // [4 warps][2][BN] stats + alignment slack
 };
+
+// lane L ends up with the sum over the warp's 32 lanes of v[L] (31 shuffles); v is destroyed
+__device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ TgParams p) {
@@ -74,6 +94,7 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    float* sstat = reinterpret_cast<float*>(smem + L::STAT_OFF);  // [4 warps][2][BN] per-tile channel sums
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -162,6 +183,7 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
         const int w = w0 + (row & (TW - 1));
         const bool valid = (h < p.gh) && (w < p.gw);
         float* orow = p.out + (long long)img * p.osn + (long long)h * p.osh + (long long)w * p.osw;
+        const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
         mbar_wait(accum_bar, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -215,6 +237,31 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+            if (p.stats != nullptr) {  // warp-uniform
+                float sq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = valid ? v[i] : 0.f;
+                    sq[i] = v[i] * v[i];
+                }
+                const float s1 = warp_transpose_sum(v, lane);
+                const float s2 = warp_transpose_sum(sq, lane);
+                sstat[(q * 2 + 0) * BN + j * 32 + lane] = s1;  // each (warp, column) written exactly once:
+                sstat[(q * 2 + 1) * BN + j * 32 + lane] = s2;  // fixed-order combine below => deterministic
+            }
+        }
+        if (p.stats != nullptr) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = et; i < BN; i += 128) {
+                const int col = n0 + i;
+                if (col < p.ncols) {
+                    const int ch = col % p.sub_c;
+                    const float t1 = (sstat[i] + sstat[2 * BN + i]) + (sstat[4 * BN + i] + sstat[6 * BN + i]);
+                    const float t2 = (sstat[BN + i] + sstat[3 * BN + i]) + (sstat[5 * BN + i] + sstat[7 * BN + i]);
+                    atomicAdd(&p.stats[ch], (double)t1);
+                    atomicAdd(&p.stats[p.stat_c + ch], (double)t2);
                 }
             }
         }

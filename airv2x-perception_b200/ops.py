@@ -129,13 +129,13 @@ def _lo(a):
 
 
 # split-aware conv family ------------------------------------------------------------------------------------
-def conv_fwd(x, wf, k, stride, out, scale=None, shift=None, relu=False):
+def conv_fwd(x, wf, k, stride, out, scale=None, shift=None, relu=False, stats=None):
     """x, out: Act. wf: packed [2][kk][cout][cin]."""
     n, h, w, cin = x.shape
     cout = wf.shape[2]
     sh = _shape(n, h, w, cin, cout, k, stride)
     call("a2x_conv2d_fwd", ctypes.byref(sh), _ptr(x.hi), _lo(x), c_int(_cs(x.hi)), _ptr(wf), _ptr(out.hi), _lo(out),
-         c_int(_cs(out.hi)), _ptr(scale), _ptr(shift), c_int(int(relu)), stream_ptr())
+         c_int(_cs(out.hi)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(stats), stream_ptr())
     return out
 
 
@@ -160,11 +160,11 @@ def conv_wgrad(x, dy, k, stride, dwp):
     return dwp
 
 
-def deconv_fwd(x, wf, cout, s, out, scale=None, shift=None, relu=False):
+def deconv_fwd(x, wf, cout, s, out, scale=None, shift=None, relu=False, stats=None):
     n, h, w, cin = x.shape
     sh = _shape(n, h, w, cin, cout, s, s)
     call("a2x_deconv_fwd", ctypes.byref(sh), _ptr(x.hi), _lo(x), c_int(_cs(x.hi)), _ptr(wf), _ptr(out.hi), _lo(out),
-         c_int(_cs(out.hi)), _ptr(scale), _ptr(shift), c_int(int(relu)), stream_ptr())
+         c_int(_cs(out.hi)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(stats), stream_ptr())
     return out
 
 

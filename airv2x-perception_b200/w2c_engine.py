@@ -58,6 +58,8 @@ class W2CEngine:
         self.bufs = {}
         self.saved = None
         self._arena_off = 0
+        self.side = None  # second stream: weight gradients run beside the data-gradient chain (fills idle SMs)
+        self.use_side_stream = True
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name, shape, dtype=torch.float32):
@@ -131,7 +133,7 @@ class W2CEngine:
         return W
 
     # ------------------------------------------------------------------ layers
-    def _bn_params(self, P, bn, training, z, n_updates, tag):
+    def _bn_params(self, P, bn, training, z, n_updates, tag, sums=None):
         C = z.shape[3]
         scale = self._buf(tag + ".scale", (C,))
         shift = self._buf(tag + ".shift", (C,))
@@ -141,8 +143,9 @@ class W2CEngine:
             return scale, shift, None, None
         mean = self._buf(tag + ".mean", (C,))
         invstd = self._buf(tag + ".invstd", (C,))
-        sums = self._zeroed(tag + ".sums", 2 * C, torch.float64)
-        ops.channel_stats(z, sums)
+        if sums is None:
+            sums = self._zeroed(tag + ".sums", 2 * C, torch.float64)
+            ops.channel_stats(z, sums)
         count = z.shape[0] * z.shape[1] * z.shape[2]
         ops.bn_finalize(sums, count, P[bn + ".weight"], P[bn + ".bias"], n_updates, P[bn + ".running_mean"],
                         P[bn + ".running_var"], scale, shift, mean, invstd)
@@ -159,8 +162,9 @@ class W2CEngine:
             ops.conv_fwd(x, wf, 3, stride, y, scale=scale, shift=shift, relu=True)
             return y
         z = self._buf(tag + ".z", (n, ho, wo, cout))
-        ops.conv_fwd(x, wf, 3, stride, Act(z))
-        scale, shift, mean, invstd = self._bn_params(P, bn, True, z, n_updates, tag)
+        sums = self._zeroed(tag + ".sums", 2 * cout, torch.float64)
+        ops.conv_fwd(x, wf, 3, stride, Act(z), stats=sums)  # BN batch statistics come out of the GEMM epilogue
+        scale, shift, mean, invstd = self._bn_params(P, bn, True, z, n_updates, tag, sums)
         ops.affine_act(z, scale, shift, True, y)
         if record is not None:
             record.append(dict(kind="conv", conv=conv, bn=bn, x=x, z=z, y=y, stride=stride, scale=scale, shift=shift,
@@ -189,8 +193,9 @@ class W2CEngine:
             ops.deconv_fwd(x, wf, cout, s, out_slice, scale=scale, shift=shift, relu=True)
             return
         z = self._buf(tg + ".z", (n, h * s, w * s, cout))
-        ops.deconv_fwd(x, wf, cout, s, Act(z))
-        scale, shift, mean, invstd = self._bn_params(P, bn, True, z, n_updates, tg)
+        sums = self._zeroed(tg + ".sums", 2 * cout, torch.float64)
+        ops.deconv_fwd(x, wf, cout, s, Act(z), stats=sums)
+        scale, shift, mean, invstd = self._bn_params(P, bn, True, z, n_updates, tg, sums)
         ops.affine_act(z, scale, shift, True, out_slice)
         if record is not None:
             record.append(dict(kind="deconv", conv=conv, bn=bn, x=x, z=z, y=out_slice, stride=s, scale=scale,
@@ -403,6 +408,30 @@ class W2CEngine:
         return loss3, dheads
 
     # ------------------------------------------------------------------ backward
+    class _Side:
+        """`with self._on_side():` issues the enclosed launches on the side stream, ordered after everything issued so
+        far on the main stream (event fork). backward() joins the side stream back at its end."""
+
+        def __init__(self, eng):
+            self.eng = eng
+
+        def __enter__(self):
+            e = self.eng
+            if not e.use_side_stream:
+                return
+            if e.side is None:
+                e.side = torch.cuda.Stream(device=e.device)
+            e.side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(e.side)
+            self.ctx.__enter__()
+
+        def __exit__(self, *a):
+            if self.eng.use_side_stream:
+                self.ctx.__exit__(*a)
+
+    def _on_side(self):
+        return W2CEngine._Side(self)
+
     def backward(self, P, dheads, grads):
         """dheads: [B,h,w,32] gradient w.r.t. the head logits. grads: dict name -> fp32 tensor (written)."""
         S = self.saved
@@ -430,17 +459,18 @@ class W2CEngine:
         # ---- heads
         dh = self._act("bwd.dheads", dheads.shape)
         ops.affine_act(dheads, None, None, False, dh)
-        dwp = wgrad_conv(S["y2"], dh, "heads", 1, 1)
-        hg = self._buf("heads.wgrad", (HEAD_PAD, self.c_shrink, 1, 1))
-        ops.unpack_conv_wgrad(dwp, HEAD_PAD, self.c_shrink, 1, out=hg)
-        grads["cls_head.weight"].copy_(hg[:nc])
-        grads["reg_head.weight"].copy_(hg[nc:nc + nr])
-        grads["obj_head.weight"].copy_(hg[nc + nr:self.n_head])
-        hbg = self._buf("heads.bgrad", (HEAD_PAD,))
-        bias_grad(dheads, None, HEAD_PAD, hbg)
-        grads["cls_head.bias"].copy_(hbg[:nc])
-        grads["reg_head.bias"].copy_(hbg[nc:nc + nr])
-        grads["obj_head.bias"].copy_(hbg[nc + nr:self.n_head])
+        with self._on_side():
+            dwp = wgrad_conv(S["y2"], dh, "heads", 1, 1)
+            hg = self._buf("heads.wgrad", (HEAD_PAD, self.c_shrink, 1, 1))
+            ops.unpack_conv_wgrad(dwp, HEAD_PAD, self.c_shrink, 1, out=hg)
+            grads["cls_head.weight"].copy_(hg[:nc])
+            grads["reg_head.weight"].copy_(hg[nc:nc + nr])
+            grads["obj_head.weight"].copy_(hg[nc + nr:self.n_head])
+            hbg = self._buf("heads.bgrad", (HEAD_PAD,))
+            bias_grad(dheads, None, HEAD_PAD, hbg)
+            grads["cls_head.bias"].copy_(hbg[:nc])
+            grads["reg_head.bias"].copy_(hbg[nc:nc + nr])
+            grads["obj_head.bias"].copy_(hbg[nc + nr:self.n_head])
         d_y2 = self._buf("bwd.d_y2", S["y2"].shape)
         ops.conv_dgrad(dh, W["heads"][1], 1, 1, d_y2)
 
@@ -449,9 +479,10 @@ class W2CEngine:
         g2 = self._act("bwd.g2", S["y2"].shape)
         ops.relu_bwd(d_y2, y2full, g2)
         n2 = "shrink_conv.layers.0.double_conv.2"
-        dwp = wgrad_conv(S["y1"], g2, n2 + ".weight", 3, 1)
-        ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_shrink, 3, out=grads[n2 + ".weight"])
-        bias_grad(g2.hi, g2.lo, self.c_shrink, grads[n2 + ".bias"])
+        with self._on_side():
+            dwp = wgrad_conv(S["y1"], g2, n2 + ".weight", 3, 1)
+            ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_shrink, 3, out=grads[n2 + ".weight"])
+            bias_grad(g2.hi, g2.lo, self.c_shrink, grads[n2 + ".bias"])
         d_y1 = self._buf("bwd.d_y1", S["y1"].shape)
         ops.conv_dgrad(g2, W[n2 + ".weight"][1], 3, 1, d_y1)
 
@@ -460,9 +491,10 @@ class W2CEngine:
         g1 = self._act("bwd.g1", S["y1"].shape)
         ops.relu_bwd(d_y1, y1full, g1)
         n1 = "shrink_conv.layers.0.double_conv.0"
-        dwp = wgrad_conv(S["catB"], g1, n1 + ".weight", 1, 1)
-        ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_cat, 1, out=grads[n1 + ".weight"])
-        bias_grad(g1.hi, g1.lo, self.c_shrink, grads[n1 + ".bias"])
+        with self._on_side():
+            dwp = wgrad_conv(S["catB"], g1, n1 + ".weight", 1, 1)
+            ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_cat, 1, out=grads[n1 + ".weight"])
+            bias_grad(g1.hi, g1.lo, self.c_shrink, grads[n1 + ".bias"])
         d_cat = self._buf("bwd.d_cat", (B, h2, w2, self.c_cat))
         ops.conv_dgrad(g1, W[n1 + ".weight"][1], 1, 1, d_cat)
 
@@ -482,8 +514,9 @@ class W2CEngine:
             s = r["stride"]
             cin, cout = r["x"].shape[3], r["z"].shape[3]
             dwp = self._zeroed(r["conv"] + ".dwp", s * s * cin * cout, torch.float32).view(s * s, cin, cout)
-            ops.deconv_wgrad(r["x"], dz, s, dwp)
-            ops.unpack_deconv_wgrad(dwp, cin, cout, s, out=grads[r["conv"]])
+            with self._on_side():
+                ops.deconv_wgrad(r["x"], dz, s, dwp)
+                ops.unpack_deconv_wgrad(dwp, cin, cout, s, out=grads[r["conv"]])
             d_fused = self._buf("bwd.d_fused%d" % i, lv["fused"].shape)
             ops.deconv_dgrad(dz, W[r["conv"]][1], s, d_fused)
             dx = self._buf("bwd.dx%d" % i, lv["x"].shape)
@@ -508,8 +541,9 @@ class W2CEngine:
                                 grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
                 cout, cin = r["z"].shape[3], r["x"].shape[3]
                 dwp = self._zeroed(r["conv"] + ".dwp." + tag, 9 * cout * cin, torch.float32).view(9, cout, cin)
-                ops.conv_wgrad(r["x"], dz, 3, r["stride"], dwp)
-                ops.unpack_conv_wgrad(dwp, cout, cin, 3, out=grads[r["conv"]])
+                with self._on_side():
+                    ops.conv_wgrad(r["x"], dz, 3, r["stride"], dwp)
+                    ops.unpack_conv_wgrad(dwp, cout, cin, 3, out=grads[r["conv"]])
                 if k > 0:
                     dprev = self._buf("bwd.dprev.%s.b%d.%d" % (tag, i, k), r["x"].shape)
                     ops.conv_dgrad(dz, W[r["conv"]][1], 3, r["stride"], dprev)
@@ -536,4 +570,6 @@ class W2CEngine:
                         r["mean"], r["invstd"], r["amap"], d_canvas, r["amax"], r["moments"], r["rows"], acc,
                         grads[pre + ".linear.weight"], grads[pre + ".norm.weight"], grads[pre + ".norm.bias"],
                         seg=r["seg"])
+        if self.use_side_stream and self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
         return grads

@@ -63,9 +63,12 @@ int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, fl
  * `*_lo == NULL` selects the single-plane mode. Packed weights always carry both planes: [2][...].
  * Outputs: y (+ y_lo if non-NULL, written as the split pair so the next GEMM can consume it). */
 
-/* y = act(scale[c] * conv(x, w) + shift[c]); scale/shift may be NULL; y has pixel stride y_cs */
+/* y = act(scale[c] * conv(x, w) + shift[c]); scale/shift may be NULL; y has pixel stride y_cs.
+ * stats != NULL (requires no scale/shift/relu): the epilogue also accumulates the BatchNorm batch statistics of the
+ * raw output, stats[c] += sum, stats[cout + c] += sum of squares (doubles, caller zeroes) — no extra HBM pass. */
 int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
-                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, a2x_stream_t stream);
+                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, double* stats,
+                   a2x_stream_t stream);
 /* dx (+)= conv_transpose(dy, w) */
 int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
                      float* dx, int dx_cs, int accumulate, a2x_stream_t stream);
@@ -74,7 +77,8 @@ int a2x_conv2d_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo,
                      const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream);
 
 int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
-                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, a2x_stream_t stream);
+                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, double* stats,
+                   a2x_stream_t stream);
 int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
                      float* dx, int dx_cs, int accumulate, a2x_stream_t stream);
 int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,

@@ -269,3 +269,31 @@ def test_pfn_forward_backward_matches_oracle(ops):
             assert rel(dw.cpu(), sd["p.pfn_layers.0.linear.weight"].grad) < 1e-4
             assert rel(dg.cpu(), sd["p.pfn_layers.0.norm.weight"].grad) < 1e-4
             assert rel(db.cpu(), sd["p.pfn_layers.0.norm.bias"].grad) < 1e-4
+
+
+@pytest.mark.parametrize("case", [(2, 12, 40, 64, 64, 3, 1), (2, 21, 45, 64, 128, 3, 2), (1, 25, 88, 128, 256, 3, 1)])
+def test_conv_epilogue_batch_statistics(ops, case):
+    """BN batch statistics fused into the GEMM epilogue == a separate reduction over the written output
+    (partial tiles and out-of-image rows excluded)."""
+    n, h, w, cin, cout, k, s = case
+    g = _g(12)
+    x, wt = rnd(g, n, cin, h, w), rnd(g, cout, cin, k, k) * 0.1
+    wf, _ = ops.pack_conv_weight(wt)
+    ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
+    y = ops.Act(torch.empty(n, ho, wo, cout, device="cuda"))
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    ops.conv_fwd(ops.split_tf32(nhwc(x)), wf, k, s, y, stats=stats)
+    ref = torch.cat([y.hi.double().sum((0, 1, 2)), (y.hi.double() ** 2).sum((0, 1, 2))])
+    assert float((stats - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_deconv_epilogue_batch_statistics(ops):
+    g = _g(13)
+    n, h, w, cin, cout, s = 2, 5, 9, 256, 128, 4
+    x, wt = rnd(g, n, cin, h, w), rnd(g, cin, cout, s, s) * 0.1
+    wf, _ = ops.pack_deconv_weight(wt)
+    y = ops.Act(torch.empty(n, h * s, w * s, cout, device="cuda"))
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    ops.deconv_fwd(ops.split_tf32(nhwc(x)), wf, cout, s, y, stats=stats)
+    ref = torch.cat([y.hi.double().sum((0, 1, 2)), (y.hi.double() ** 2).sum((0, 1, 2))])
+    assert float((stats - ref).abs().max() / ref.abs().max()) < 1e-5
