@@ -34,7 +34,8 @@ extern unsigned long long g_launches;  // kernels launched by this library (a2x_
 // Encode a rank-`rank` fp32 tiled tensor map with 128-byte swizzle. dims/box are in elements (dim 0 innermost,
 // contiguous); strides_bytes[i] is the byte stride of dim i+1 (rank-1 entries). Returns 0 on success.
 // swizzle_atom32 != 0 selects CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (for MN-major tf32 UMMA operands).
+// bf16 != 0 encodes a bfloat16 tensor (dims/box still in elements, strides in bytes).
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle_atom32 = 0);
+                    const uint32_t* box, int swizzle_atom32 = 0, int bf16 = 0);
 
 }  // namespace a2x

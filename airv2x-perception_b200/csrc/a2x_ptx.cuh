@@ -2,6 +2,7 @@
 // Everything here is device-side; host-side tensor-map encoding lives in a2x_tmap.h.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -111,6 +112,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 with bf16 operands (fp32 accumulate): used for the two correction products
+// of the 3-term operand split at twice the tf32 rate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -155,6 +167,40 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, u
                                                        uint32_t b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
            ((M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulate (a_format = b_format = 1 = BF16).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major,
+                                                       uint32_t b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+           ((M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- 3-term operand split
+// v  ~=  hi + lo,  hi = tf32_rn(v) kept in fp32,  (h16, l16) = (bf16(hi), bf16(v - hi)).
+// A GEMM  sum a*b  is evaluated as  hi_a*hi_b [tf32]  +  l16_a*h16_b [bf16]  +  h16_a*l16_b [bf16]: the dropped
+// lo*lo term and the bf16 roundings of the two correction products are each <= 2^-20 relative.
+struct SplitOut {
+    float* hi;            // fp32 plane (may be the only one)
+    __nv_bfloat16* b16;   // null = single-plane mode; else plane 0 = h16, plane 1 = l16 (plane stride `ps` elements)
+    long long ps;
+};
+__device__ __forceinline__ void store_split4(const SplitOut& o, long long off, float4 v) {
+    if (o.b16 != nullptr) {
+        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+        *reinterpret_cast<float4*>(o.hi + off) = h;
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(h.x, h.y), h23 = __floats2bfloat162_rn(h.z, h.w);
+        __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - h.x, v.y - h.y), l23 = __floats2bfloat162_rn(v.z - h.z, v.w - h.w);
+        uint2 hp, lp;
+        hp.x = *reinterpret_cast<uint32_t*>(&h01);
+        hp.y = *reinterpret_cast<uint32_t*>(&h23);
+        lp.x = *reinterpret_cast<uint32_t*>(&l01);
+        lp.y = *reinterpret_cast<uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(o.b16 + off) = hp;
+        *reinterpret_cast<uint2*>(o.b16 + o.ps + off) = lp;
+    } else {
+        *reinterpret_cast<float4*>(o.hi + off) = v;
+    }
 }
 
 }  // namespace a2x

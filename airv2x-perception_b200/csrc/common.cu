@@ -36,7 +36,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle_atom32) {
+                    const uint32_t* box, int swizzle_atom32, int bf16) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return 2;
     cuuint64_t gdims[5], gstr[4];
@@ -51,7 +51,7 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
         set_error("tensor map base %p not 16-byte aligned", base);
         return 1;
     }
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+    CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -10,29 +10,32 @@ namespace a2x {
 extern int g_debug[16];
 
 // ------------------------------------------------------------------ tensor-map views of an NHWC tensor
-// Rank-5 view (c, w, x, h, n) of every `step`-th pixel starting at (h_off, w_off). box = (32, box_w, 1, box_h, 1).
-static int make_act_map(CUtensorMap* m, const float* base, int n, int h, int w, int c, int cs, int step, int h_off,
-                        int w_off, int box_w, int box_h, int atom32 = 0) {
+// Rank-5 view (c, w, x, h, n) of every `step`-th pixel starting at (h_off, w_off).
+// fp32: box = (32, box_w, 1, box_h, 1); bf16: box = (64, ...). `cs` = pixel stride in elements.
+static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int cs, int step, int h_off,
+                        int w_off, int box_w, int box_h, int atom32 = 0, int bf16 = 0) {
     const int hp = (h - h_off + step - 1) / step;
     const int wp = (w - w_off + step - 1) / step;
     if (hp <= 0 || wp <= 0) {
         set_error("empty activation view");
         return 1;
     }
-    const float* b = base + ((long long)h_off * w + w_off) * cs;
+    const size_t es = bf16 ? 2 : 4;
+    const char* b = (const char*)base + ((long long)h_off * w + w_off) * cs * es;
     uint64_t dims[5] = {(uint64_t)c, (uint64_t)wp, 1, (uint64_t)hp, (uint64_t)n};
-    uint64_t str[4] = {(uint64_t)step * cs * 4, (uint64_t)step * cs * 4, (uint64_t)step * w * cs * 4,
-                       (uint64_t)h * w * cs * 4};
-    uint32_t box[5] = {32, (uint32_t)box_w, 1, (uint32_t)box_h, 1};
-    return encode_tmap_f32(m, b, 5, dims, str, box, atom32);
+    uint64_t str[4] = {(uint64_t)step * cs * es, (uint64_t)step * cs * es, (uint64_t)step * w * cs * es,
+                       (uint64_t)h * w * cs * es};
+    uint32_t box[5] = {(uint32_t)(bf16 ? 64 : 32), (uint32_t)box_w, 1, (uint32_t)box_h, 1};
+    return encode_tmap_f32(m, b, 5, dims, str, box, atom32, bf16);
 }
 
-// weights [taps][rows][k] (k contiguous); box = (32, bn, 1)
-static int make_w_map(CUtensorMap* m, const float* base, int taps, int rows, int k, int bn) {
+// weights [taps][rows][k] (k contiguous); box = (32 | 64, bn, 1)
+static int make_w_map(CUtensorMap* m, const void* base, int taps, int rows, int k, int bn, int bf16 = 0) {
+    const size_t es = bf16 ? 2 : 4;
     uint64_t dims[3] = {(uint64_t)k, (uint64_t)rows, (uint64_t)taps};
-    uint64_t str[2] = {(uint64_t)k * 4, (uint64_t)rows * k * 4};
-    uint32_t box[3] = {32, (uint32_t)(bn < rows ? bn : rows), 1};
-    return encode_tmap_f32(m, base, 3, dims, str, box);
+    uint64_t str[2] = {(uint64_t)k * es, (uint64_t)rows * k * es};
+    uint32_t box[3] = {(uint32_t)(bf16 ? 64 : 32), (uint32_t)(bn < rows ? bn : rows), 1};
+    return encode_tmap_f32(m, base, 3, dims, str, box, 0, bf16);
 }
 
 static int pick_tw_log2(int gh, int gw, int pix, int lo, int hi) {
@@ -66,6 +69,12 @@ static int launch_tg(const TgParams& p, int n_col_tiles, cudaStream_t st) {
     return 0;
 }
 
+static int bn_for(int ncols) {
+    int bn = ncols >= 256 ? 256 : ncols >= 128 ? 128 : ncols >= 64 ? 64 : 32;
+    if (g_debug[1] > 0) bn = g_debug[1];
+    return bn;
+}
+
 // Fill grid/tile fields and dispatch on the column-tile width.
 static int run_tg(TgParams& p, int gh, int gw, int n_img, int ncols, cudaStream_t st) {
     p.n_img = n_img;
@@ -75,10 +84,9 @@ static int run_tg(TgParams& p, int gh, int gw, int n_img, int ncols, cudaStream_
     const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
     p.tiles_h = (gh + TH - 1) / TH;
     p.tiles_w = (gw + TW - 1) / TW;
-    int bn = ncols >= 256 ? 256 : ncols >= 128 ? 128 : ncols >= 64 ? 64 : 32;
-    if (g_debug[1] > 0) bn = g_debug[1];
-    if (ncols % 32 != 0) {
-        set_error("column count %d not a multiple of 32", ncols);
+    const int bn = bn_for(ncols);
+    if (ncols % 32 != 0 || bn > ncols) {
+        set_error("column count %d not a multiple of 32 (tile %d)", ncols, bn);
         return 1;
     }
     const int tiles_n = (ncols + bn - 1) / bn;
@@ -92,17 +100,14 @@ static int run_tg(TgParams& p, int gh, int gw, int n_img, int ncols, cudaStream_
     return 1;
 }
 
-static int bn_for(int ncols) {
-    int bn = ncols >= 256 ? 256 : ncols >= 128 ? 128 : ncols >= 64 ? 64 : 32;
-    if (g_debug[1] > 0) bn = g_debug[1];
-    return bn;
-}
-
-static void set_plain_out(TgParams& p, float* out, int h, int w, int cs, int step, int h_off, int w_off) {
-    p.out = out + ((long long)h_off * w + w_off) * cs;
-    p.osn = (long long)h * w * cs;
-    p.osh = (long long)step * w * cs;
-    p.osw = (long long)step * cs;
+static void set_plain_out(TgParams& p, const a2x_output* y, int h, int w, int step, int h_off, int w_off) {
+    const long long o = ((long long)h_off * w + w_off) * y->cs;
+    p.out.hi = y->hi + o;
+    p.out.b16 = y->b16 ? (__nv_bfloat16*)y->b16 + o : nullptr;
+    p.out.ps = y->b16_plane;
+    p.osn = (long long)h * w * y->cs;
+    p.osh = (long long)step * w * y->cs;
+    p.osw = (long long)step * y->cs;
     p.sub_c = 1 << 30;
     p.sub_s = 1;
     p.sub_sh = 0;
@@ -129,6 +134,18 @@ static int check_shape(const a2x_conv_shape* s, bool transposed) {
             set_error("conv needs (k=1,s=1) or (k=3,s in {1,2}), got k=%d s=%d", s->ksize, s->stride);
             return 1;
         }
+    }
+    return 0;
+}
+
+static int check_operand(const a2x_operand* x, int c, const char* what) {
+    if (!x || !x->hi || x->cs < c || x->cs % 4) {
+        set_error("%s: bad operand (null / pixel stride < channels / stride not a multiple of 4)", what);
+        return 1;
+    }
+    if (x->b16 && (c % 64 || x->cs % 8)) {
+        set_error("%s: split operands need channel counts that are multiples of 64 (got %d)", what, c);
+        return 1;
     }
     return 0;
 }
@@ -160,17 +177,45 @@ static int build_fwd_taps(const a2x_conv_shape* s, TgTap* taps) {
     return nt;
 }
 
-static int build_fwd_maps(const a2x_conv_shape* s, const float* x, int x_cs, CUtensorMap* maps, int box_w, int box_h,
-                          int atom32 = 0) {
-    if (s->stride == 1)
-        return make_act_map(&maps[0], x, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, box_w, box_h, atom32);
-    for (int hp = 0; hp < 2; ++hp)
-        for (int wp = 0; wp < 2; ++wp) {
-            if (hp >= s->h || wp >= s->w) continue;
-            int r = make_act_map(&maps[hp * 2 + wp], x, s->n, s->h, s->w, s->cin, x_cs, 2, hp, wp, box_w, box_h, atom32);
-            if (r) return r;
+// maps of the input x for a forward conv: [0, nmaps) fp32 hi; in split mode [nmaps, 2 nmaps) h16, [2 nmaps, 3 nmaps) l16
+static int build_fwd_maps(const a2x_conv_shape* s, const a2x_operand* x, CUtensorMap* maps, int box_w, int box_h,
+                          int atom32 = 0, CUtensorMap* maps_h16 = nullptr, CUtensorMap* maps_l16 = nullptr) {
+    const int nm = s->stride == 1 ? 1 : 4;
+    for (int i = 0; i < nm; ++i) {
+        const int step = s->stride, hp = step == 1 ? 0 : i >> 1, wp = step == 1 ? 0 : i & 1;
+        if (hp >= s->h || wp >= s->w) continue;
+        if (int r = make_act_map(&maps[i], x->hi, s->n, s->h, s->w, s->cin, x->cs, step, hp, wp, box_w, box_h, atom32))
+            return r;
+        if (x->b16 && maps_h16) {
+            const __nv_bfloat16* b = (const __nv_bfloat16*)x->b16;
+            if (int r = make_act_map(&maps_h16[i], b, s->n, s->h, s->w, s->cin, x->cs, step, hp, wp, box_w, box_h, 0, 1))
+                return r;
+            if (int r = make_act_map(&maps_l16[i], b + x->b16_plane, s->n, s->h, s->w, s->cin, x->cs, step, hp, wp,
+                                     box_w, box_h, 0, 1))
+                return r;
         }
+    }
     return 0;
+}
+
+// split mode: D = A_hi*B_hi [tf32] + A_l16*B_h16 [bf16] + A_h16*B_l16 [bf16]. Base taps reference fp32 maps
+// [0, nmaps) and weight taps [0, ntaps_w); h16 views live at map + nmaps, l16 views at map + 2 nmaps; bf16 weights
+// carry the h16 taps first, then the l16 taps (+ ntaps_w).
+static int expand_split_taps(TgTap* taps, int ntaps, int nmaps, int ntaps_w) {
+    for (int i = ntaps - 1; i >= 0; --i) {
+        const TgTap t = taps[i];
+        TgTap a = t, b = t, c = t;
+        a.kind = 0;
+        b.kind = 1;
+        b.map = (int16_t)(t.map + 2 * nmaps);  // A l16 x W h16
+        c.kind = 1;
+        c.map = (int16_t)(t.map + nmaps);      // A h16 x W l16
+        c.btap = t.btap + ntaps_w;
+        taps[3 * i] = a;
+        taps[3 * i + 1] = b;
+        taps[3 * i + 2] = c;
+    }
+    return 3 * ntaps;
 }
 
 template <int BN, int TPC, int STAGES, bool SPLIT>
@@ -189,7 +234,6 @@ static int launch_wg(const WgParams& p, int ksplit, int tiles_a, int tap_groups,
     return 0;
 }
 
-// tpc = taps sharing one A tile per CTA (3 for a 3x3 kernel row in single-plane mode, else 1)
 static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream_t st) {
     p.n_img = n_img;
     const int TW = 1 << p.tw_log2, TH = WG_PIX >> p.tw_log2;
@@ -198,7 +242,6 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream
     p.lbo_bytes = g_debug[2] > 0 ? (uint32_t)g_debug[2] : (uint32_t)WG_ATOM_BYTES;
     p.sbo_bytes = g_debug[3] > 0 ? (uint32_t)g_debug[3] : 512u;
     p.layout = g_debug[5] > 0 ? (uint32_t)g_debug[5] : 1u;
-    p.scalar_atomics = g_debug[4];
     const int bn = p.cb >= 128 ? 128 : (p.cb >= 64 ? 64 : 32);
     const int tpc = (!split && p.ntaps % 3 == 0) ? 3 : 1;
     p.n_tiles_b = (p.cb + bn - 1) / bn;
@@ -215,7 +258,8 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream
     if (split) {
         if (bn == 128) return launch_wg<128, 1, 3, true>(p, ksplit, tiles_a, tap_groups, st);
         if (bn == 64) return launch_wg<64, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
-        return launch_wg<32, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
+        set_error("split wgrad needs cb >= 64");
+        return 1;
     }
     if (tpc == 3) {
         if (bn == 128) return launch_wg<128, 3, 3, false>(p, ksplit, tiles_a, tap_groups, st);
@@ -227,24 +271,18 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream
     return launch_wg<32, 1, 4, false>(p, ksplit, tiles_a, tap_groups, st);
 }
 
-// 3xTF32: D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo. Base taps reference base maps [0, nmaps) and weight taps
-// [0, ntaps_w); lo activation views live at map + nmaps, lo weights at btap + ntaps_w.
-static int expand_split_taps(TgTap* taps, int ntaps, int nmaps, int ntaps_w) {
-    for (int i = ntaps - 1; i >= 0; --i) {
-        const TgTap t = taps[i];
-        TgTap a = t, b = t, c = t;
-        b.map = (int16_t)(t.map + nmaps);
-        c.btap = t.btap + ntaps_w;
-        taps[3 * i] = a;
-        taps[3 * i + 1] = b;
-        taps[3 * i + 2] = c;
-    }
-    return 3 * ntaps;
-}
-
 // ------------------------------------------------------------------ small re-layout kernels
+__device__ __forceinline__ void put_w(float* w32, __nv_bfloat16* w16, long long plane, long long j, float v) {
+    const float hi = tf32_rn(v);
+    if (w32) w32[j] = hi;
+    if (w16) {
+        w16[j] = __float2bfloat16_rn(hi);
+        w16[plane + j] = __float2bfloat16_rn(v - hi);
+    }
+}
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, int cout, int cin, int kk, int cout_pad,
-                                   float* __restrict__ wf, float* __restrict__ wd) {
+                                   float* __restrict__ wf, __nv_bfloat16* __restrict__ wf16, float* __restrict__ wd,
+                                   __nv_bfloat16* __restrict__ wd16) {
     const long long total = (long long)kk * cout_pad * cin;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -252,16 +290,8 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, int cout, int ci
         const int co = (int)((i / cin) % cout_pad);
         const int tap = (int)(i / ((long long)cin * cout_pad));
         const float v = co < cout ? w[((long long)co * cin + ci) * kk + tap] : 0.f;
-        const float hi = tf32_rn(v), lo = v - hi;
-        if (wf) {  // [2][tap][co][ci]
-            wf[i] = hi;
-            wf[total + i] = lo;
-        }
-        if (wd) {  // [2][tap][ci][co]
-            const long long j = ((long long)tap * cin + ci) * cout_pad + co;
-            wd[j] = hi;
-            wd[total + j] = lo;
-        }
+        put_w(wf, wf16, total, i, v);                                                  // [tap][co][ci]
+        put_w(wd, wd16, total, ((long long)tap * cin + ci) * cout_pad + co, v);        // [tap][ci][co]
     }
 }
 __global__ void unpack_conv_dw_kernel(const float* __restrict__ dwp, int cout, int cin, int kk, int cout_pad,
@@ -277,7 +307,8 @@ __global__ void unpack_conv_dw_kernel(const float* __restrict__ dwp, int cout, i
     }
 }
 __global__ void pack_deconv_w_kernel(const float* __restrict__ w, int cin, int cout, int s, float* __restrict__ wf,
-                                     float* __restrict__ wd) {
+                                     __nv_bfloat16* __restrict__ wf16, float* __restrict__ wd,
+                                     __nv_bfloat16* __restrict__ wd16) {
     const int ss = s * s;
     const long long total = (long long)cin * cout * ss;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -285,18 +316,9 @@ __global__ void pack_deconv_w_kernel(const float* __restrict__ w, int cin, int c
         const int ij = (int)(i % ss);
         const int co = (int)((i / ss) % cout);
         const int ci = (int)(i / ((long long)ss * cout));
-        const float v = w[i];  // [ci][co][i][j]
-        const float hi = tf32_rn(v), lo = v - hi;
-        if (wf) {  // [2][(ij, co)][ci]
-            const long long j = ((long long)ij * cout + co) * cin + ci;
-            wf[j] = hi;
-            wf[total + j] = lo;
-        }
-        if (wd) {  // [2][ij][ci][co]
-            const long long j = ((long long)ij * cin + ci) * cout + co;
-            wd[j] = hi;
-            wd[total + j] = lo;
-        }
+        const float v = w[i];                                                          // [ci][co][i][j]
+        put_w(wf, wf16, total, ((long long)ij * cout + co) * cin + ci, v);             // [(ij, co)][ci]
+        put_w(wd, wd16, total, ((long long)ij * cin + ci) * cout + co, v);             // [ij][ci][co]
     }
 }
 __global__ void unpack_deconv_dw_kernel(const float* __restrict__ dwp, int cin, int cout, int s,
@@ -326,12 +348,12 @@ using namespace a2x;
 
 extern "C" {
 
-int a2x_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, float* w_fwd, float* w_dgrad,
-                         a2x_stream_t stream) {
+int a2x_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, float* w_fwd, void* w_fwd16,
+                         float* w_dgrad, void* w_dgrad16, a2x_stream_t stream) {
     A2X_REQUIRE(w_oihw && cout > 0 && cin > 0 && (ksize == 1 || ksize == 3) && cout_pad >= cout, "bad pack args");
     const int kk = ksize * ksize;
     pack_conv_w_kernel<<<grid_for((long long)kk * cout_pad * cin), 256, 0, (cudaStream_t)stream>>>(
-        w_oihw, cout, cin, kk, cout_pad, w_fwd, w_dgrad);
+        w_oihw, cout, cin, kk, cout_pad, w_fwd, (__nv_bfloat16*)w_fwd16, w_dgrad, (__nv_bfloat16*)w_dgrad16);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -348,11 +370,11 @@ int a2x_unpack_conv_wgrad(const float* dw_packed, int cout, int cin, int ksize, 
     return 0;
 }
 
-int a2x_pack_deconv_weight(const float* w_iohw, int cin, int cout, int s, float* w_fwd, float* w_dgrad,
-                           a2x_stream_t stream) {
+int a2x_pack_deconv_weight(const float* w_iohw, int cin, int cout, int s, float* w_fwd, void* w_fwd16, float* w_dgrad,
+                           void* w_dgrad16, a2x_stream_t stream) {
     A2X_REQUIRE(w_iohw && cin > 0 && cout > 0 && s > 0, "bad pack args");
-    pack_deconv_w_kernel<<<grid_for((long long)cin * cout * s * s), 256, 0, (cudaStream_t)stream>>>(w_iohw, cin, cout,
-                                                                                                  s, w_fwd, w_dgrad);
+    pack_deconv_w_kernel<<<grid_for((long long)cin * cout * s * s), 256, 0, (cudaStream_t)stream>>>(
+        w_iohw, cin, cout, s, w_fwd, (__nv_bfloat16*)w_fwd16, w_dgrad, (__nv_bfloat16*)w_dgrad16);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -368,28 +390,29 @@ int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, fl
     return 0;
 }
 
-int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
-                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, double* stats,
-                   a2x_stream_t stream) {
+int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
+                   const float* scale, const float* shift, int relu, double* stats, a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
-    A2X_REQUIRE(x && w_fwd && y && x_cs >= s->cin && y_cs >= s->cout && x_cs % 4 == 0 && y_cs % 4 == 0,
-                "bad conv2d_fwd pointers/strides");
+    if (int r = check_operand(x, s->cin, "conv2d_fwd x")) return r;
+    A2X_REQUIRE(w && w->w32 && y && y->hi && y->cs >= s->cout && y->cs % 4 == 0, "conv2d_fwd: bad weights/output");
+    A2X_REQUIRE(!x->b16 || w->w16, "conv2d_fwd: split input needs bf16 weight planes");
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
     const int kk = s->ksize * s->ksize;
     TgParams p{};
     p.tw_log2 = pick_tw_log2(ho, wo, TG_BM, 4, 7);
     const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
     const int nmaps = s->stride == 1 ? 1 : 4;
-    if (int r = build_fwd_maps(s, x, x_cs, p.amap, TW, TH)) return r;
+    if (int r = build_fwd_maps(s, x, p.amap, TW, TH, 0, p.amap + nmaps, p.amap + 2 * nmaps)) return r;
     p.ntaps = build_fwd_taps(s, p.taps);
-    if (x_lo) {
-        if (int r = build_fwd_maps(s, x_lo, x_cs, p.amap + nmaps, TW, TH)) return r;
+    const int bn = bn_for(s->cout);
+    if (int r = make_w_map(&p.bmap, w->w32, kk, s->cout, s->cin, bn)) return r;
+    if (x->b16) {
         p.ntaps = expand_split_taps(p.taps, p.ntaps, nmaps, kk);
+        if (int r = make_w_map(&p.bmap16, w->w16, 2 * kk, s->cout, s->cin, bn, 1)) return r;
     }
-    p.kchunks = s->cin / 32;
-    if (int r = make_w_map(&p.bmap, w_fwd, 2 * kk, s->cout, s->cin, bn_for(s->cout))) return r;
-    set_plain_out(p, y, ho, wo, y_cs, 1, 0, 0);
-    p.out_lo = y_lo;
+    p.kchunks32 = s->cin / 32;
+    p.kchunks16 = s->cin / 64;
+    set_plain_out(p, y, ho, wo, 1, 0, 0);
     p.scale = scale;
     p.shift = shift;
     p.relu = relu;
@@ -400,14 +423,16 @@ int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, i
     return run_tg(p, ho, wo, s->n, s->cout, (cudaStream_t)stream);
 }
 
-int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
-                     float* dx, int dx_cs, int accumulate, a2x_stream_t stream) {
+int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
+                     int accumulate, a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
-    A2X_REQUIRE(dy && w_dgrad && dx && dy_cs >= s->cout && dx_cs >= s->cin && dy_cs % 4 == 0 && dx_cs % 4 == 0,
-                "bad conv2d_dgrad pointers/strides");
+    if (int r = check_operand(dy, s->cout, "conv2d_dgrad dy")) return r;
+    A2X_REQUIRE(w && w->w32 && dx && dx_cs >= s->cin && dx_cs % 4 == 0, "conv2d_dgrad: bad weights/output");
+    A2X_REQUIRE(!dy->b16 || w->w16, "conv2d_dgrad: split input needs bf16 weight planes");
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
     const int kk = s->ksize * s->ksize;
     const int n_class = s->stride == 1 ? 1 : 4;
+    a2x_output out{dx, nullptr, 0, dx_cs};
     for (int cls = 0; cls < n_class; ++cls) {
         const int hp = cls >> 1, wp = cls & 1;
         const int step = s->stride;
@@ -416,7 +441,7 @@ int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_l
         TgParams p{};
         p.tw_log2 = pick_tw_log2(gh, gw, TG_BM, 4, 7);
         const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
-        if (int r = make_act_map(&p.amap[0], dy, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH)) return r;
+        if (int r = make_act_map(&p.amap[0], dy->hi, s->n, ho, wo, s->cout, dy->cs, 1, 0, 0, TW, TH)) return r;
         p.ntaps = 0;
         for (int r = 0; r < s->ksize; ++r) {
             if (step == 2 && ((r + 1) & 1) != hp) continue;  // (r - 1) parity must equal hp
@@ -435,73 +460,95 @@ int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_l
                 p.taps[p.ntaps++] = t;
             }
         }
-        if (dy_lo) {
-            if (int r = make_act_map(&p.amap[1], dy_lo, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH)) return r;
+        const int bn = bn_for(s->cin);
+        if (int r = make_w_map(&p.bmap, w->w32, kk, s->cin, s->cout, bn)) return r;
+        if (dy->b16) {
+            const __nv_bfloat16* b = (const __nv_bfloat16*)dy->b16;
+            if (int r = make_act_map(&p.amap[1], b, s->n, ho, wo, s->cout, dy->cs, 1, 0, 0, TW, TH, 0, 1)) return r;
+            if (int r = make_act_map(&p.amap[2], b + dy->b16_plane, s->n, ho, wo, s->cout, dy->cs, 1, 0, 0, TW, TH, 0, 1))
+                return r;
             p.ntaps = expand_split_taps(p.taps, p.ntaps, 1, kk);
+            if (int r = make_w_map(&p.bmap16, w->w16, 2 * kk, s->cin, s->cout, bn, 1)) return r;
         }
-        p.kchunks = s->cout / 32;
-        if (int r = make_w_map(&p.bmap, w_dgrad, 2 * kk, s->cin, s->cout, bn_for(s->cin))) return r;
-        set_plain_out(p, dx, s->h, s->w, dx_cs, step, hp, wp);
+        p.kchunks32 = s->cout / 32;
+        p.kchunks16 = s->cout / 64;
+        set_plain_out(p, &out, s->h, s->w, step, hp, wp);
         p.accumulate = accumulate;
         if (int r = run_tg(p, gh, gw, s->n, s->cin, (cudaStream_t)stream)) return r;
     }
     return 0;
 }
 
-int a2x_conv2d_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,
-                     const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream) {
+// shared by conv and deconv weight gradients: fill the A-side maps of `a` (unshifted operand)
+static int wg_a_maps(WgParams& p, const a2x_operand* a, int n, int h, int w, int c, int TW, int TH) {
+    if (int r = make_act_map(&p.amap, a->hi, n, h, w, c, a->cs, 1, 0, 0, TW, TH, 1)) return r;
+    if (a->b16) {
+        const __nv_bfloat16* b = (const __nv_bfloat16*)a->b16;
+        if (int r = make_act_map(&p.amap16[0], b, n, h, w, c, a->cs, 1, 0, 0, TW, TH, 0, 1)) return r;
+        if (int r = make_act_map(&p.amap16[1], b + a->b16_plane, n, h, w, c, a->cs, 1, 0, 0, TW, TH, 0, 1)) return r;
+    }
+    return 0;
+}
+
+int a2x_conv2d_wgrad(const a2x_conv_shape* s, const a2x_operand* x, const a2x_operand* dy, float* dw_packed,
+                     a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
-    A2X_REQUIRE(x && dy && dw_packed && x_cs >= s->cin && dy_cs >= s->cout && x_cs % 4 == 0 && dy_cs % 4 == 0,
-                "bad conv2d_wgrad pointers/strides");
-    A2X_REQUIRE((x_lo == nullptr) == (dy_lo == nullptr), "wgrad needs both or neither lo planes");
+    if (int r = check_operand(x, s->cin, "conv2d_wgrad x")) return r;
+    if (int r = check_operand(dy, s->cout, "conv2d_wgrad dy")) return r;
+    A2X_REQUIRE(dw_packed, "conv2d_wgrad: null output");
+    const bool split = x->b16 && dy->b16;
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
     WgParams p{};
     p.tw_log2 = pick_tw_log2(ho, wo, WG_PIX, 2, 5);
     const int TW = 1 << p.tw_log2, TH = WG_PIX >> p.tw_log2;
-    p.nmaps_b = s->stride == 1 ? 1 : 4;
-    if (int r = make_act_map(&p.amap[0], dy, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH, 1)) return r;
-    if (int r = build_fwd_maps(s, x, x_cs, p.bmap, TW, TH, 1)) return r;
-    if (x_lo) {
-        if (int r = make_act_map(&p.amap[1], dy_lo, s->n, ho, wo, s->cout, dy_cs, 1, 0, 0, TW, TH, 1)) return r;
-        if (int r = build_fwd_maps(s, x_lo, x_cs, p.bmap + p.nmaps_b, TW, TH, 1)) return r;
-    }
+    a2x_operand dyo = *dy, xo = *x;
+    if (!split) dyo.b16 = xo.b16 = nullptr;
+    if (int r = wg_a_maps(p, &dyo, s->n, ho, wo, s->cout, TW, TH)) return r;
+    if (int r = build_fwd_maps(s, &xo, p.bmap, TW, TH, 1, p.bmap16[0], p.bmap16[1])) return r;
     p.ntaps = build_fwd_taps(s, p.taps);
     p.ca = s->cout;
     p.cb = s->cin;
     p.dw = dw_packed;
-    return run_wg(p, ho, wo, s->n, x_lo != nullptr, (cudaStream_t)stream);
+    return run_wg(p, ho, wo, s->n, split, (cudaStream_t)stream);
 }
 
-int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
-                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, double* stats,
-                   a2x_stream_t stream) {
+int a2x_deconv_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
+                   const float* scale, const float* shift, int relu, double* stats, a2x_stream_t stream) {
     if (int r = check_shape(s, true)) return r;
-    A2X_REQUIRE(x && w_fwd && y && x_cs >= s->cin && y_cs >= s->cout && x_cs % 4 == 0 && y_cs % 4 == 0,
-                "bad deconv_fwd pointers/strides");
+    if (int r = check_operand(x, s->cin, "deconv_fwd x")) return r;
+    A2X_REQUIRE(w && w->w32 && y && y->hi && y->cs >= s->cout && y->cs % 4 == 0, "deconv_fwd: bad weights/output");
+    A2X_REQUIRE(!x->b16 || w->w16, "deconv_fwd: split input needs bf16 weight planes");
     const int st = s->stride;
     TgParams p{};
     p.tw_log2 = pick_tw_log2(s->h, s->w, TG_BM, 4, 7);
     const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
-    if (int r = make_act_map(&p.amap[0], x, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH)) return r;
+    if (int r = make_act_map(&p.amap[0], x->hi, s->n, s->h, s->w, s->cin, x->cs, 1, 0, 0, TW, TH)) return r;
     p.ntaps = 1;
     p.taps[0] = TgTap{0, 0, 0, 0, 0, 0};
-    if (x_lo) {
-        if (int r = make_act_map(&p.amap[1], x_lo, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH)) return r;
-        p.ntaps = expand_split_taps(p.taps, 1, 1, 1);
-    }
-    p.kchunks = s->cin / 32;
     const int ncols = st * st * s->cout;
-    if (int r = make_w_map(&p.bmap, w_fwd, 2, ncols, s->cin, bn_for(ncols))) return r;
+    const int bn = bn_for(ncols);
+    if (int r = make_w_map(&p.bmap, w->w32, 1, ncols, s->cin, bn)) return r;
+    if (x->b16) {
+        const __nv_bfloat16* b = (const __nv_bfloat16*)x->b16;
+        if (int r = make_act_map(&p.amap[1], b, s->n, s->h, s->w, s->cin, x->cs, 1, 0, 0, TW, TH, 0, 1)) return r;
+        if (int r = make_act_map(&p.amap[2], b + x->b16_plane, s->n, s->h, s->w, s->cin, x->cs, 1, 0, 0, TW, TH, 0, 1))
+            return r;
+        p.ntaps = expand_split_taps(p.taps, 1, 1, 1);
+        if (int r = make_w_map(&p.bmap16, w->w16, 2, ncols, s->cin, bn, 1)) return r;
+    }
+    p.kchunks32 = s->cin / 32;
+    p.kchunks16 = s->cin / 64;
     const long long W2 = (long long)s->w * st;
-    p.out = y;
-    p.out_lo = y_lo;
-    p.osn = (long long)s->h * st * W2 * y_cs;
-    p.osh = (long long)st * W2 * y_cs;
-    p.osw = (long long)st * y_cs;
+    p.out.hi = y->hi;
+    p.out.b16 = (__nv_bfloat16*)y->b16;
+    p.out.ps = y->b16_plane;
+    p.osn = (long long)s->h * st * W2 * y->cs;
+    p.osh = (long long)st * W2 * y->cs;
+    p.osw = (long long)st * y->cs;
     p.sub_c = s->cout;
     p.sub_s = st;
-    p.sub_sh = W2 * y_cs;
-    p.sub_sw = y_cs;
+    p.sub_sh = W2 * y->cs;
+    p.sub_sw = y->cs;
     p.scale = scale;
     p.shift = shift;
     p.relu = relu;
@@ -512,12 +559,14 @@ int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, i
     return run_tg(p, s->h, s->w, s->n, ncols, (cudaStream_t)stream);
 }
 
-int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
-                     float* dx, int dx_cs, int accumulate, a2x_stream_t stream) {
+int a2x_deconv_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
+                     int accumulate, a2x_stream_t stream) {
     if (int r = check_shape(s, true)) return r;
-    A2X_REQUIRE(dy && w_dgrad && dx && dy_cs >= s->cout && dx_cs >= s->cin && dy_cs % 4 == 0 && dx_cs % 4 == 0,
-                "bad deconv_dgrad pointers/strides");
+    if (int r = check_operand(dy, s->cout, "deconv_dgrad dy")) return r;
+    A2X_REQUIRE(w && w->w32 && dx && dx_cs >= s->cin && dx_cs % 4 == 0, "deconv_dgrad: bad weights/output");
+    A2X_REQUIRE(!dy->b16 || w->w16, "deconv_dgrad: split input needs bf16 weight planes");
     const int st = s->stride;
+    a2x_output out{dx, nullptr, 0, dx_cs};
     // one launch per sub-row i; its s sub-columns j are the taps, each through its own strided view of dy
     for (int i = 0; i < st; ++i) {
         TgParams p{};
@@ -525,50 +574,65 @@ int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_l
         const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
         p.ntaps = 0;
         for (int j = 0; j < st; ++j) {
-            if (int r = make_act_map(&p.amap[j], dy, s->n, s->h * st, s->w * st, s->cout, dy_cs, st, i, j, TW, TH))
+            if (int r = make_act_map(&p.amap[j], dy->hi, s->n, s->h * st, s->w * st, s->cout, dy->cs, st, i, j, TW, TH))
                 return r;
-            if (dy_lo)
-                if (int r = make_act_map(&p.amap[st + j], dy_lo, s->n, s->h * st, s->w * st, s->cout, dy_cs, st, i, j,
-                                         TW, TH))
+            if (dy->b16) {
+                const __nv_bfloat16* b = (const __nv_bfloat16*)dy->b16;
+                if (int r = make_act_map(&p.amap[st + j], b, s->n, s->h * st, s->w * st, s->cout, dy->cs, st, i, j, TW,
+                                         TH, 0, 1))
                     return r;
+                if (int r = make_act_map(&p.amap[2 * st + j], b + dy->b16_plane, s->n, s->h * st, s->w * st, s->cout,
+                                         dy->cs, st, i, j, TW, TH, 0, 1))
+                    return r;
+            }
             TgTap t{};
             t.map = (int16_t)j;
             t.btap = i * st + j;
             p.taps[p.ntaps++] = t;
         }
-        if (dy_lo) p.ntaps = expand_split_taps(p.taps, p.ntaps, st, st * st);
-        p.kchunks = s->cout / 32;
-        if (int r = make_w_map(&p.bmap, w_dgrad, 2 * st * st, s->cin, s->cout, bn_for(s->cin))) return r;
-        set_plain_out(p, dx, s->h, s->w, dx_cs, 1, 0, 0);
+        const int bn = bn_for(s->cin);
+        if (int r = make_w_map(&p.bmap, w->w32, st * st, s->cin, s->cout, bn)) return r;
+        if (dy->b16) {
+            p.ntaps = expand_split_taps(p.taps, p.ntaps, st, st * st);
+            if (int r = make_w_map(&p.bmap16, w->w16, 2 * st * st, s->cin, s->cout, bn, 1)) return r;
+        }
+        p.kchunks32 = s->cout / 32;
+        p.kchunks16 = s->cout / 64;
+        set_plain_out(p, &out, s->h, s->w, 1, 0, 0);
         p.accumulate = (i > 0) ? 1 : accumulate;
         if (int r = run_tg(p, s->h, s->w, s->n, s->cin, (cudaStream_t)stream)) return r;
     }
     return 0;
 }
 
-int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,
-                     const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream) {
+int a2x_deconv_wgrad(const a2x_conv_shape* s, const a2x_operand* x, const a2x_operand* dy, float* dw_packed,
+                     a2x_stream_t stream) {
     if (int r = check_shape(s, true)) return r;
-    A2X_REQUIRE(x && dy && dw_packed && x_cs >= s->cin && dy_cs >= s->cout && x_cs % 4 == 0 && dy_cs % 4 == 0,
-                "bad deconv_wgrad pointers/strides");
-    A2X_REQUIRE((x_lo == nullptr) == (dy_lo == nullptr), "wgrad needs both or neither lo planes");
+    if (int r = check_operand(x, s->cin, "deconv_wgrad x")) return r;
+    if (int r = check_operand(dy, s->cout, "deconv_wgrad dy")) return r;
+    A2X_REQUIRE(dw_packed, "deconv_wgrad: null output");
+    const bool split = x->b16 && dy->b16;
     const int st = s->stride;
+    a2x_operand xo = *x;
+    if (!split) xo.b16 = nullptr;
     for (int i = 0; i < st; ++i) {
         WgParams p{};
         p.tw_log2 = pick_tw_log2(s->h, s->w, WG_PIX, 2, 5);
         const int TW = 1 << p.tw_log2, TH = WG_PIX >> p.tw_log2;
-        p.nmaps_b = st;
-        if (int r = make_act_map(&p.amap[0], x, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH, 1)) return r;
-        if (x_lo)
-            if (int r = make_act_map(&p.amap[1], x_lo, s->n, s->h, s->w, s->cin, x_cs, 1, 0, 0, TW, TH, 1)) return r;
+        if (int r = wg_a_maps(p, &xo, s->n, s->h, s->w, s->cin, TW, TH)) return r;
         p.ntaps = 0;
         for (int j = 0; j < st; ++j) {
-            if (int r = make_act_map(&p.bmap[j], dy, s->n, s->h * st, s->w * st, s->cout, dy_cs, st, i, j, TW, TH, 1))
+            if (int r = make_act_map(&p.bmap[j], dy->hi, s->n, s->h * st, s->w * st, s->cout, dy->cs, st, i, j, TW, TH, 1))
                 return r;
-            if (dy_lo)
-                if (int r = make_act_map(&p.bmap[st + j], dy_lo, s->n, s->h * st, s->w * st, s->cout, dy_cs, st, i, j,
-                                         TW, TH, 1))
+            if (split) {
+                const __nv_bfloat16* b = (const __nv_bfloat16*)dy->b16;
+                if (int r = make_act_map(&p.bmap16[0][j], b, s->n, s->h * st, s->w * st, s->cout, dy->cs, st, i, j, TW,
+                                         TH, 0, 1))
                     return r;
+                if (int r = make_act_map(&p.bmap16[1][j], b + dy->b16_plane, s->n, s->h * st, s->w * st, s->cout, dy->cs,
+                                         st, i, j, TW, TH, 0, 1))
+                    return r;
+            }
             TgTap t{};
             t.map = (int16_t)j;
             p.taps[p.ntaps++] = t;
@@ -576,7 +640,7 @@ int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo,
         p.ca = s->cin;
         p.cb = s->cout;
         p.dw = dw_packed + (long long)i * st * s->cin * s->cout;  // [(i, j)][ci][co]
-        if (int r = run_wg(p, s->h, s->w, s->n, x_lo != nullptr, (cudaStream_t)stream)) return r;
+        if (int r = run_wg(p, s->h, s->w, s->n, split, (cudaStream_t)stream)) return r;
     }
     return 0;
 }

@@ -10,28 +10,29 @@
 
 namespace a2x {
 
-__device__ __forceinline__ void store_split(float* hi_p, float* lo_p, float4 v) {
-    if (lo_p != nullptr) {
-        float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-        *reinterpret_cast<float4*>(hi_p) = h;
-        *reinterpret_cast<float4*>(lo_p) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-    } else {
-        *reinterpret_cast<float4*>(hi_p) = v;
-    }
+static __host__ SplitOut to_split(const a2x_output* o) {
+    SplitOut r;
+    r.hi = o->hi;
+    r.b16 = (__nv_bfloat16*)o->b16;
+    r.ps = o->b16_plane;
+    return r;
 }
 
-// ---------------------------------------------------------------------------------------------- split
-__global__ void split_kernel(const float* __restrict__ x, long long n4, float* __restrict__ hi, float* __restrict__ lo) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = reinterpret_cast<const float4*>(x)[i];
-        store_split(hi + 4 * i, lo + 4 * i, v);
-    }
+// ---------------------------------------------------------------------------------------------- split / combine
+__global__ void split_kernel(const float* __restrict__ x, long long n4, SplitOut o) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        store_split4(o, 4 * i, reinterpret_cast<const float4*>(x)[i]);
 }
 
-__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float* __restrict__ o) {
+__global__ void combine_kernel(const float* __restrict__ a, const __nv_bfloat16* __restrict__ l16, long long n4,
+                               float* __restrict__ o) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
-        reinterpret_cast<float4*>(o)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        const float4 x = reinterpret_cast<const float4*>(a)[i];
+        const uint2 u = reinterpret_cast<const uint2*>(l16)[i];
+        const __nv_bfloat162 l01 = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+        const __nv_bfloat162 l23 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        const float2 f01 = __bfloat1622float2(l01), f23 = __bfloat1622float2(l23);
+        reinterpret_cast<float4*>(o)[i] = make_float4(x.x + f01.x, x.y + f01.y, x.z + f23.x, x.w + f23.y);
     }
 }
 
@@ -180,8 +181,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int C, f
 __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int x_cs,
                                                          const float* __restrict__ scale,
                                                          const float* __restrict__ shift, int relu,
-                                                         const float* __restrict__ mask, float* __restrict__ y,
-                                                         float* __restrict__ y_lo, int y_cs, long long npix, int C) {
+                                                         const float* __restrict__ mask, SplitOut y, int y_cs,
+                                                         long long npix, int C) {
     const int q = C >> 2;
     const long long total = npix * q;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
                 const float m = mask[p[u]];
                 t.x *= m; t.y *= m; t.z *= m; t.w *= m;
             }
-            store_split(y + p[u] * y_cs + c[u], y_lo ? y_lo + p[u] * y_cs + c[u] : nullptr, t);
+            store_split4(y, p[u] * y_cs + c[u], t);
         }
     }
 }
@@ -230,8 +231,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
                                                                 const float* __restrict__ mean,
                                                                 const float* __restrict__ invstd,
                                                                 const double* __restrict__ sums, double count,
-                                                                float* __restrict__ dz, float* __restrict__ dz_lo,
-                                                                int dz_cs, long long npix, int C) {
+                                                                SplitOut dz, int dz_cs, long long npix, int C) {
     const int q = C >> 2;
     const long long total = npix * q;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -265,8 +265,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
                 const float mg = (float)(sums[ch] / count), mgz = (float)(sums[C + ch] / count);
                 o[e] = sc * (g - mg - zh * mgz);  // scale = gamma * invstd
             }
-            store_split(dz + p[u] * dz_cs + c[u], dz_lo ? dz_lo + p[u] * dz_cs + c[u] : nullptr,
-                        make_float4(o[0], o[1], o[2], o[3]));
+            store_split4(dz, p[u] * dz_cs + c[u], make_float4(o[0], o[1], o[2], o[3]));
         }
     }
 }
@@ -274,8 +273,8 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
 // g = dy * (y > 0) * mask[pixel]  -> split store        (bias+ReLU convs; mask multiply backward)
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, int dy_cs,
                                                        const float* __restrict__ y, int y_cs,
-                                                       const float* __restrict__ mask, float* __restrict__ g,
-                                                       float* __restrict__ g_lo, int g_cs, long long npix, int C) {
+                                                       const float* __restrict__ mask, SplitOut g, int g_cs,
+                                                       long long npix, int C) {
     const int q = C >> 2;
     const long long total = npix * q;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -294,7 +293,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
             const float m = mask[p];
             d.x *= m; d.y *= m; d.z *= m; d.w *= m;
         }
-        store_split(g + p * g_cs + c, g_lo ? g_lo + p * g_cs + c : nullptr, d);
+        store_split4(g, p * g_cs + c, d);
     }
 }
 
@@ -322,17 +321,17 @@ using namespace a2x;
 
 extern "C" {
 
-int a2x_split_tf32(const float* x, long long n, float* hi, float* lo, a2x_stream_t stream) {
-    A2X_REQUIRE(x && hi && lo && n % 4 == 0, "split_tf32: bad args (n must be a multiple of 4)");
-    split_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, n / 4, hi, lo);
+int a2x_split(const float* x, long long n, const a2x_output* out, a2x_stream_t stream) {
+    A2X_REQUIRE(x && out && out->hi && out->b16 && n % 4 == 0, "split: bad args (n must be a multiple of 4)");
+    split_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, n / 4, to_split(out));
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int a2x_add2(const float* a, const float* b, long long n, float* out, a2x_stream_t stream) {
-    A2X_REQUIRE(a && b && out && n % 4 == 0, "add2: bad args (n must be a multiple of 4)");
-    add2_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4, out);
+int a2x_combine(const float* hi, const void* l16, long long n, float* out, a2x_stream_t stream) {
+    A2X_REQUIRE(hi && l16 && out && n % 4 == 0, "combine: bad args (n must be a multiple of 4)");
+    combine_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(hi, (const __nv_bfloat16*)l16, n / 4, out);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -382,11 +381,11 @@ int a2x_bn_eval_affine(const float* gamma, const float* beta, const float* runni
 }
 
 int a2x_affine_act(const float* x, int x_cs, const float* scale, const float* shift, int relu, const float* mask,
-                   float* y, float* y_lo, int y_cs, long long npix, int C, a2x_stream_t stream) {
+                   const a2x_output* y, long long npix, int C, a2x_stream_t stream) {
     if (int r = check_c(C)) return r;
-    A2X_REQUIRE(x && y && npix > 0, "affine_act: bad args");
-    affine_act_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_cs, scale, shift, relu, mask, y,
-                                                                               y_lo, y_cs, npix, C);
+    A2X_REQUIRE(x && y && y->hi && npix > 0, "affine_act: bad args");
+    affine_act_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_cs, scale, shift, relu, mask,
+                                                                               to_split(y), y->cs, npix, C);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -408,13 +407,14 @@ int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs,
 }
 
 int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
-                          const float* mean, const float* invstd, const double* sums, double count, float* dz,
-                          float* dz_lo, int dz_cs, long long npix, int C, float* dgamma, float* dbeta,
+                          const float* mean, const float* invstd, const double* sums, double count,
+                          const a2x_output* dz, long long npix, int C, float* dgamma, float* dbeta,
                           int accumulate_param_grads, a2x_stream_t stream) {
     if (int r = check_c(C)) return r;
-    A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && dz && npix > 0, "bn_relu_bwd_apply: bad args");
+    A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && dz && dz->hi && npix > 0,
+                "bn_relu_bwd_apply: bad args");
     bn_relu_bwd_apply_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
-        dy, dy_cs, z, z_cs, scale, shift, mean, invstd, sums, count, dz, dz_lo, dz_cs, npix, C);
+        dy, dy_cs, z, z_cs, scale, shift, mean, invstd, sums, count, to_split(dz), dz->cs, npix, C);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     if (dgamma || dbeta) {
@@ -426,12 +426,12 @@ int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, 
     return 0;
 }
 
-int a2x_relu_bwd(const float* dy, int dy_cs, const float* y, int y_cs, const float* mask, float* g, float* g_lo,
-                 int g_cs, long long npix, int C, a2x_stream_t stream) {
+int a2x_relu_bwd(const float* dy, int dy_cs, const float* y, int y_cs, const float* mask, const a2x_output* g,
+                 long long npix, int C, a2x_stream_t stream) {
     if (int r = check_c(C)) return r;
-    A2X_REQUIRE(dy && g && npix > 0, "relu_bwd: bad args");
-    relu_bwd_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dy, dy_cs, y, y_cs, mask, g, g_lo, g_cs,
-                                                                             npix, C);
+    A2X_REQUIRE(dy && g && g->hi && npix > 0, "relu_bwd: bad args");
+    relu_bwd_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dy, dy_cs, y, y_cs, mask, to_split(g),
+                                                                             g->cs, npix, C);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

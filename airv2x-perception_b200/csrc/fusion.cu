@@ -168,8 +168,7 @@ constexpr int ATT_MAX_AGENTS = 16;
 
 template <int G, int V>
 __global__ void __launch_bounds__(256) att_fuse_fwd_kernel(const float* __restrict__ x, int HW, int C, int n_agents,
-                                                           float inv_sqrt_c, float* __restrict__ out,
-                                                           float* __restrict__ out_lo) {
+                                                           float inv_sqrt_c, SplitOut out) {
     const int gid_raw = (blockIdx.x * blockDim.x + threadIdx.x) / G;  // pixel
     const int gl = threadIdx.x % G;
     const bool active = gid_raw < HW;  // inactive groups compute on a clamped pixel (full-warp shuffles stay legal)
@@ -212,18 +211,7 @@ __global__ void __launch_bounds__(256) att_fuse_fwd_kernel(const float* __restri
     }
     if (!active) return;
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        float* o = out + (long long)gid * C + (v * G + gl) * 4;
-        if (out_lo != nullptr) {
-            float* l = out_lo + (long long)gid * C + (v * G + gl) * 4;
-            const float4 h = make_float4(tf32_rn(acc[v].x), tf32_rn(acc[v].y), tf32_rn(acc[v].z), tf32_rn(acc[v].w));
-            *reinterpret_cast<float4*>(o) = h;
-            *reinterpret_cast<float4*>(l) =
-                make_float4(acc[v].x - h.x, acc[v].y - h.y, acc[v].z - h.z, acc[v].w - h.w);
-        } else {
-            *reinterpret_cast<float4*>(o) = acc[v];
-        }
-    }
+    for (int v = 0; v < V; ++v) store_split4(out, (long long)gid * C + (v * G + gl) * 4, acc[v]);
 }
 
 // backward: given dout (per pixel, C), write dx for every agent of the scene.
@@ -363,11 +351,15 @@ int a2x_comm_rate_ego(float* mask, int hw, int n_scenes, const int* scene_start,
     } while (0)
 
 /* x: [n_agents][hw][c] dense NHWC of ONE scene (agent 0 = ego); out: [hw][c] */
-int a2x_att_fuse_fwd(const float* x, int n_agents, int hw, int c, float* out, float* out_lo, a2x_stream_t stream) {
-    A2X_REQUIRE(x && out && n_agents > 0 && n_agents <= ATT_MAX_AGENTS && hw > 0, "att_fuse_fwd: bad args (<= 16 agents)");
+int a2x_att_fuse_fwd(const float* x, int n_agents, int hw, int c, const a2x_output* out, a2x_stream_t stream) {
+    A2X_REQUIRE(x && out && out->hi && n_agents > 0 && n_agents <= ATT_MAX_AGENTS && hw > 0, "att_fuse_fwd: bad args (<= 16 agents)");
     const int g = c / 4 < 32 ? c / 4 : 32;
     const float isc = 1.0f / sqrtf((float)c);
-    A2X_ATT_DISPATCH(att_fuse_fwd_kernel, x, hw, c, n_agents, isc, out, out_lo);
+    SplitOut so;
+    so.hi = out->hi;
+    so.b16 = (__nv_bfloat16*)out->b16;
+    so.ps = out->b16_plane;
+    A2X_ATT_DISPATCH(att_fuse_fwd_kernel, x, hw, c, n_agents, isc, so);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

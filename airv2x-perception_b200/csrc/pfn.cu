@@ -174,8 +174,7 @@ __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restric
                                                           PfnSeg sg, const float* __restrict__ W,
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ shift,
-                                                          const int* __restrict__ agent_map,
-                                                          float* __restrict__ canvas, float* __restrict__ canvas_lo,
+                                                          const int* __restrict__ agent_map, SplitOut canvas,
                                                           float* __restrict__ pillar_out /* [M][64] or null */,
                                                           unsigned char* __restrict__ amax /* [M][64] or null */) {
     __shared__ float sW[NC * 12];  // rows padded to 12 floats for float4 reads
@@ -231,14 +230,17 @@ __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restric
             }
         }
         const long long cell = ((long long)agent_map[agent] * g.ny + cy) * g.nx + cx;
-        float* o = canvas + cell * NC;
-        if (canvas_lo != nullptr) {
+        float* o = canvas.hi + cell * NC;
+        if (canvas.b16 != nullptr) {
             const float h0 = tf32_rn(out0), h1 = tf32_rn(out1);
             o[lane] = h0;
             o[lane + 32] = h1;
-            float* l = canvas_lo + cell * NC;
-            l[lane] = out0 - h0;
-            l[lane + 32] = out1 - h1;
+            __nv_bfloat16* hb = canvas.b16 + cell * NC;
+            __nv_bfloat16* lb = hb + canvas.ps;
+            hb[lane] = __float2bfloat16_rn(h0);
+            hb[lane + 32] = __float2bfloat16_rn(h1);
+            lb[lane] = __float2bfloat16_rn(out0 - h0);
+            lb[lane + 32] = __float2bfloat16_rn(out1 - h1);
         } else {
             o[lane] = out0;
             o[lane + 32] = out1;
@@ -415,14 +417,18 @@ int a2x_pfn_stats_finalize(const double* moments65, double rows, const a2x_pfn_s
 
 int a2x_pfn_scatter(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
                     const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift,
-                    const int* agent_map, float* canvas, float* canvas_lo, float* pillar_out, unsigned char* amax,
+                    const int* agent_map, const a2x_output* canvas, float* pillar_out, unsigned char* amax,
                     a2x_stream_t stream) {
     const PfnSeg sg = make_seg(seg, &m);
-    A2X_REQUIRE(voxels && num_points && coords && geom && w && scale && shift && agent_map && canvas && m > 0,
+    A2X_REQUIRE(voxels && num_points && coords && geom && w && scale && shift && agent_map && canvas && canvas->hi &&
+                    m > 0,
                 "pfn_scatter: bad args");
+    SplitOut so;
+    so.hi = canvas->hi;
+    so.b16 = (__nv_bfloat16*)canvas->b16;
+    so.ps = canvas->b16_plane;
     pfn_scatter_kernel<<<warp_grid(m), 256, 0, (cudaStream_t)stream>>>(voxels, num_points, coords, make_geom(geom), m,
-                                                                     sg, w, scale, shift, agent_map, canvas, canvas_lo,
-                                                                     pillar_out, amax);
+                                                                     sg, w, scale, shift, agent_map, so, pillar_out, amax);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

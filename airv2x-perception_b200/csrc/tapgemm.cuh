@@ -2,13 +2,18 @@
 //
 //   D[pixel, col] = sum_{tap} sum_{k} A_tap[pixel + shift(tap), k] * B[tap][col, k]
 //
-// A is an NHWC fp32 activation tensor seen through up to 4 rank-5 TMA tensor maps (c, w, x, h, n); TMA's
-// out-of-bounds zero fill implements the conv zero padding, per-tap coordinate shifts implement the 3x3 window,
-// and "parity view" maps (same memory, doubled strides) implement stride-2 convs and their data gradients.
-// B is a packed weight tensor [tap][col][k] (K-major). One CTA computes a 128-pixel x BN-column tile:
-// a TMA producer lane fills a STAGES-deep smem ring (128B-swizzled), one elected lane issues
-// tcgen05.mma.kind::tf32 into a TMEM accumulator, four epilogue warps drain it with tcgen05.ld, apply the
-// per-channel affine / ReLU and store NHWC rows (each thread owns one pixel => full 128-byte lines).
+// A is an NHWC activation tensor seen through rank-5 TMA tensor maps (c, w, x, h, n); TMA's out-of-bounds zero
+// fill implements the conv zero padding, per-tap coordinate shifts implement the 3x3 window, and "parity view" maps
+// (same memory, doubled strides) implement stride-2 convs and their data gradients. B is a packed weight tensor
+// [tap][col][k] (K-major). One CTA computes a 128-pixel x BN-column tile: a TMA producer lane fills a STAGES-deep
+// smem ring (128B-swizzled), one elected lane issues tcgen05.mma into a TMEM accumulator, four epilogue warps drain
+// it with tcgen05.ld, apply the per-channel affine / ReLU, optionally reduce the BatchNorm batch statistics, and
+// store NHWC rows (each thread owns one pixel => full 128-byte lines).
+//
+// Precision ("split" mode): every operand v is carried as hi = tf32_rn(v) (fp32) plus a bf16 pair
+// (h16, l16) = (bf16(hi), bf16(v - hi)). Each window tap expands to three tap entries accumulating into the SAME fp32
+// TMEM tile: hi*hi with kind::tf32 (K = 8 / instruction), l16*h16 and h16*l16 with kind::f16 bf16 (K = 16 /
+// instruction, i.e. twice the rate and half the bytes). Error budget ~2^-20 relative per product.
 //
 // Replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.ConvTranspose2d on the reference path
 // (opencood/models/common_modules/base_bev_backbone.py:41-105, downsample_conv.py:18-32,
@@ -18,45 +23,44 @@
 
 namespace a2x {
 
-constexpr int TG_BM = 128;         // pixels per tile (UMMA M)
-constexpr int TG_KC = 32;          // fp32 elements per k-chunk = one 128-byte swizzle row
+constexpr int TG_BM = 128;  // pixels per tile (UMMA M)
 constexpr int TG_A_BYTES = TG_BM * 128;
-constexpr int TG_MAX_TAPS = 27;  // 9 window taps x 3 split products (hi*hi, lo*hi, hi*lo) in 3xTF32 mode
-constexpr int TG_MAX_MAPS = 8;   // 4 parity views x {hi, lo}
+constexpr int TG_MAX_TAPS = 27;  // 9 window taps x 3 split products
+constexpr int TG_MAX_MAPS = 12;  // 4 parity views x {hi fp32, h16, l16}
 
 struct TgTap {
     int16_t map;   // which A tensor map
     int16_t dw;    // shift along tensor-map dim 1 (w)
-    int16_t dx;    // coordinate along dim 2 (x: 1 for plain convs, sub-row index for deconv dgrad)
+    int16_t dx;    // coordinate along dim 2 (x)
     int16_t dh;    // shift along dim 3 (h)
     int32_t btap;  // coordinate along B dim 2
-    int32_t pad;
+    int32_t kind;  // 0 = tf32 (fp32 maps, 32 channels / 128-byte row), 1 = bf16 (64 channels / row)
 };
 
 struct TgParams {
     CUtensorMap amap[TG_MAX_MAPS];
-    CUtensorMap bmap;
+    CUtensorMap bmap;    // fp32 weights  [taps][cols][k]       (hi plane)
+    CUtensorMap bmap16;  // bf16 weights  [2*taps][cols][k]     (h16 taps, then l16 taps)
     TgTap taps[TG_MAX_TAPS];
     int ntaps;
-    int kchunks;  // K per tap / 32
+    int kchunks32;  // K / 32 (tf32 taps)
+    int kchunks16;  // K / 64 (bf16 taps)
     // GEMM pixel grid
     int n_img, gh, gw;
     int tw_log2;  // tile is (128 >> tw_log2) rows x (1 << tw_log2) cols
     int tiles_h, tiles_w;
     // output addressing (elements)
-    float* out;
-    float* out_lo;  // if non-null: out = tf32_rn(v), out_lo = v - out (operand split for a following 3xTF32 GEMM)
+    SplitOut out;
     long long osn, osh, osw;
-    int sub_c, sub_s;          // column -> (sub, c) split for deconv scatter; sub_c >= total cols otherwise
+    int sub_c, sub_s;  // column -> (sub, c) split for deconv scatter; sub_c >= total cols otherwise
     long long sub_sh, sub_sw;
-    int ncols;                 // valid columns (multiple of 32)
+    int ncols;  // valid columns (multiple of 32)
     // epilogue
     const float* scale;  // per output channel (index = col % sub_c), may be null
     const float* shift;  // may be null
     int relu;
-    int accumulate;      // out += result
-    // fused BatchNorm batch statistics of the raw result: stats[ch] += sum, stats[stat_c + ch] += sum of squares,
-    // ch = col % sub_c (or col when sub_c >= ncols). Null = off.
+    int accumulate;  // out += result (single-plane outputs only)
+    // fused BatchNorm batch statistics of the raw result: stats[ch] += sum, stats[stat_c + ch] += sum of squares
     double* stats;
     int stat_c;
 };
@@ -126,8 +130,6 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int ksteps = p.ntaps * p.kchunks;
-
     if (warp == 0) {
         if (elect_one()) {
             tma_prefetch_desc(&p.bmap);
@@ -137,13 +139,16 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
             for (int tap = 0; tap < p.ntaps; ++tap) {
                 const TgTap tp = p.taps[tap];
                 const CUtensorMap* am = &p.amap[tp.map];
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                const CUtensorMap* bm = tp.kind ? &p.bmap16 : &p.bmap;
+                const int nk = tp.kind ? p.kchunks16 : p.kchunks32;
+                const int kw = tp.kind ? 64 : 32;  // channels per 128-byte row
+                for (int kc = 0; kc < nk; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + TG_A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    tma_load_5d(sa, am, &full_bar[stage], kc * TG_KC, w0 + tp.dw, tp.dx, h0 + tp.dh, img);
-                    tma_load_3d(sb, &p.bmap, &full_bar[stage], kc * TG_KC, n0, tp.btap);
+                    tma_load_5d(sa, am, &full_bar[stage], kc * kw, w0 + tp.dw, tp.dx, h0 + tp.dh, img);
+                    tma_load_3d(sb, bm, &full_bar[stage], kc * kw, n0, tp.btap);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -153,24 +158,33 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_tf32(TG_BM, BN, 0, 0);
+            constexpr uint32_t idesc32 = make_idesc_tf32(TG_BM, BN, 0, 0);
+            constexpr uint32_t idesc16 = make_idesc_bf16(TG_BM, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                const uint32_t sb = sa + TG_A_BYTES;
+            uint32_t first = 1;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int kind = p.taps[tap].kind;
+                const int nk = kind ? p.kchunks16 : p.kchunks32;
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t sb = sa + TG_A_BYTES;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row
-                    const uint64_t ad = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                    const uint64_t bd = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                    umma_tf32(tmem_base, ad, bd, idesc, (ks | k) != 0);
-                }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-                if (++stage == STAGES) {
-                    stage = 0;
-                    phase ^= 1;
+                    for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte row (8 tf32 or 16 bf16)
+                        const uint64_t ad = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t bd = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                        const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                        if (kind) umma_bf16(tmem_base, ad, bd, idesc16, acc);
+                        else umma_tf32(tmem_base, ad, bd, idesc32, acc);
+                    }
+                    first = 0;
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
             umma_commit(accum_bar);
@@ -182,7 +196,7 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
         const int h = h0 + (row >> p.tw_log2);
         const int w = w0 + (row & (TW - 1));
         const bool valid = (h < p.gh) && (w < p.gw);
-        float* orow = p.out + (long long)img * p.osn + (long long)h * p.osh + (long long)w * p.osw;
+        const long long obase = (long long)img * p.osn + (long long)h * p.osh + (long long)w * p.osw;
         const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
         mbar_wait(accum_bar, 0);
         tc_fence_after();
@@ -204,9 +218,10 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
                 for (int i = 0; i < 32; ++i) v[i] += __ldg(p.shift + cc + i);
             }
             if (valid) {
-                float* o = orow + (long long)(sub / p.sub_s) * p.sub_sh + (long long)(sub % p.sub_s) * p.sub_sw + cc;
-                float4* o4 = reinterpret_cast<float4*>(o);
+                const long long off =
+                    obase + (long long)(sub / p.sub_s) * p.sub_sh + (long long)(sub % p.sub_s) * p.sub_sw + cc;
                 if (p.accumulate) {
+                    const float4* o4 = reinterpret_cast<const float4*>(p.out.hi + off);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 prev = o4[i];
@@ -220,24 +235,9 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
-                if (p.out_lo != nullptr) {
-                    float4* l4 = reinterpret_cast<float4*>(p.out_lo + (o - p.out));
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float hi[4], lo[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            hi[e] = tf32_rn(v[4 * i + e]);
-                            lo[e] = v[4 * i + e] - hi[e];
-                        }
-                        o4[i] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        l4[i] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
+                for (int i = 0; i < 8; ++i)
+                    store_split4(p.out, off + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
             }
             if (p.stats != nullptr) {  // warp-uniform
                 float sq[32];

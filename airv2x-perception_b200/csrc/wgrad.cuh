@@ -2,13 +2,16 @@
 //
 //   dW[tap][a][b] = sum_{pixel} A[pixel, a] * B_tap[pixel + shift(tap), b]
 //
-// A (unshifted, e.g. dY) and B (shifted per tap through the same parity-view tensor maps the forward uses,
-// e.g. X) are NHWC fp32, so both UMMA operands are MN-major: a TMA box (32 channels x 32 pixels) lands in smem
-// as one swizzled "atom" [32 pixel rows][128 bytes]; M = 128 spans 4 atoms (LBO = atom size), and each
-// tcgen05.mma.kind::tf32 consumes K = 8 pixel rows. MN-major tf32 operands must use the 128B swizzle with 32-byte
-// atomicity (UMMA layout SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4-row groups, SBO = 512. A CTA owns one
-// (128 x BN) x TPC-taps output block and a contiguous range of pixel tiles (split-K); partial sums leave through
-// vectorised red.global.add.f32.
+// A (unshifted, e.g. dY) and B (shifted per tap through the same parity-view tensor maps the forward uses, e.g. X)
+// are NHWC, so both UMMA operands are MN-major: a TMA box (one 128-byte channel row x 32 pixels) lands in smem as one
+// swizzled "atom" [32 pixel rows][128 bytes]; M = 128 spans several atoms (LBO = atom size).
+//   * tf32 main product (hi * hi): atoms hold 32 fp32 channels; MN-major tf32 operands MUST use the 128B swizzle with
+//     32-byte atomicity (UMMA layout SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4-row groups,
+//     SBO = 512, K = 8 pixels per MMA.
+//   * bf16 correction products (l16 * h16, h16 * l16; "split" mode): atoms hold 64 bf16 channels, plain 128B swizzle,
+//     8-row groups, SBO = 1024, K = 16 pixels per MMA.
+// All three products accumulate into the same fp32 TMEM tile. A CTA owns one (128 x BN) x TPC-taps output block and a
+// contiguous range of 32-pixel tiles (split-K); partial sums leave through vectorised red.global.add.f32.
 //
 // Replaces autograd's cuDNN wgrad for nn.Conv2d / nn.ConvTranspose2d (reference: torch autograd over
 // opencood/models/common_modules/base_bev_backbone.py:41-105, downsample_conv.py:18-32).
@@ -18,33 +21,35 @@
 
 namespace a2x {
 
-constexpr int WG_PIX = 32;                  // pixels per k-step
-constexpr int WG_ATOM_BYTES = WG_PIX * 128;  // one (32 px x 32 ch) atom
+constexpr int WG_PIX = 32;                   // pixels per k-step
+constexpr int WG_ATOM_BYTES = WG_PIX * 128;  // one (32 px x 128 B) atom
+constexpr int WG_MAX_BMAPS = 4;              // parity views (conv stride 2) or sub-columns (deconv)
 
 struct WgParams {
-    CUtensorMap amap[2];            // [0] = hi (or the only) plane, [1] = lo plane (3xTF32 split mode)
-    CUtensorMap bmap[TG_MAX_MAPS];  // base views first, then their lo twins at +nmaps_b
-    TgTap taps[TG_MAX_TAPS];
+    CUtensorMap amap;                  // A hi (fp32)
+    CUtensorMap amap16[2];             // A h16, l16 (bf16)
+    CUtensorMap bmap[WG_MAX_BMAPS];    // B hi views
+    CUtensorMap bmap16[2][WG_MAX_BMAPS];  // B h16 / l16 views
+    TgTap taps[9];
     int ntaps;
-    int nmaps_b;  // number of base B views (lo twin of view m is m + nmaps_b)
-    int ca, cb;   // channel counts (multiples of 32)
+    int ca, cb;  // channel counts (multiples of 32; of 64 in split mode)
     int n_img, tiles_h, tiles_w, tw_log2;  // 32-pixel tiles: (32 >> tw_log2) rows x (1 << tw_log2) cols
     int tiles_per_cta;
     int n_tiles_b;  // number of BN-wide column tiles
     float* dw;      // [ntaps][ca][cb], accumulated with red.add (caller zeroes)
-    uint32_t lbo_bytes, sbo_bytes;  // MN-major descriptor strides (debug-overridable)
-    int scalar_atomics;             // debug: plain atomicAdd instead of red.v4
-    uint32_t layout;                // UMMA smem layout type (1 = SWIZZLE_128B_BASE32B)
+    uint32_t lbo_bytes, sbo_bytes, layout;  // tf32 MN-major descriptor fields (debug-overridable)
 };
 
 template <int BN, int TPC, int STAGES, bool SPLIT>
 struct WgSmem {
-    static constexpr int NP = SPLIT ? 2 : 1;  // operand planes (hi, lo)
-    static constexpr int A_PLANE = 4 * WG_ATOM_BYTES;
-    static constexpr int B_PLANE = TPC * (BN / 32) * WG_ATOM_BYTES;
-    static constexpr int A_BYTES = NP * A_PLANE;
-    static constexpr int B_BYTES = NP * B_PLANE;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int A32 = 4 * WG_ATOM_BYTES;                                   // 128 ch fp32
+    static constexpr int B32 = TPC * (BN / 32) * WG_ATOM_BYTES;
+    static constexpr int A16 = SPLIT ? 2 * WG_ATOM_BYTES : 0;                        // 128 ch bf16, per plane
+    static constexpr int B16 = SPLIT ? TPC * (BN / 64) * WG_ATOM_BYTES : 0;          // per plane
+    static constexpr int OFF_B32 = A32;
+    static constexpr int OFF_A16 = OFF_B32 + B32;   // h16 then l16
+    static constexpr int OFF_B16 = OFF_A16 + 2 * A16;
+    static constexpr int STAGE_BYTES = OFF_B16 + 2 * B16;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
     static constexpr int TMEM_COLS = (TPC * BN <= 32) ? 32 : (TPC * BN <= 64) ? 64 : (TPC * BN <= 128) ? 128
@@ -98,7 +103,9 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
         if (elect_one()) {
             const int TW = 1 << p.tw_log2;
             const int TH = WG_PIX >> p.tw_log2;
-            const uint32_t tx_bytes = L::NP * (a_atoms + TPC * b_atoms) * WG_ATOM_BYTES;
+            const int a16 = a_atoms / 2, b16 = b_atoms / 2;  // 64-channel bf16 atoms
+            const uint32_t tx_bytes =
+                ((a_atoms + TPC * b_atoms) + (SPLIT ? 2 * (a16 + TPC * b16) : 0)) * WG_ATOM_BYTES;
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -109,19 +116,28 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 const int img = t / p.tiles_h;
                 const int h0 = th_i * TH, w0 = tw_i * TW;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                uint8_t* sb = sa + L::A_BYTES;
+                uint8_t* st = smem + stage * L::STAGE_BYTES;
                 mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                for (int pl = 0; pl < L::NP; ++pl) {
-                    for (int a = 0; a < a_atoms; ++a)
-                        tma_load_5d(sa + pl * L::A_PLANE + a * WG_ATOM_BYTES, &p.amap[pl], &full_bar[stage],
-                                    m0 + a * 32, w0, 0, h0, img);
-                    for (int tt = 0; tt < TPC; ++tt) {
-                        const TgTap tp = p.taps[tap0 + tt];
-                        for (int b = 0; b < b_atoms; ++b)
-                            tma_load_5d(sb + pl * L::B_PLANE + (tt * (BN / 32) + b) * WG_ATOM_BYTES,
-                                        &p.bmap[tp.map + pl * p.nmaps_b], &full_bar[stage], n0 + b * 32, w0 + tp.dw,
-                                        tp.dx, h0 + tp.dh, img);
+                for (int a = 0; a < a_atoms; ++a)
+                    tma_load_5d(st + a * WG_ATOM_BYTES, &p.amap, &full_bar[stage], m0 + a * 32, w0, 0, h0, img);
+                for (int tt = 0; tt < TPC; ++tt) {
+                    const TgTap tp = p.taps[tap0 + tt];
+                    for (int b = 0; b < b_atoms; ++b)
+                        tma_load_5d(st + L::OFF_B32 + (tt * (BN / 32) + b) * WG_ATOM_BYTES, &p.bmap[tp.map],
+                                    &full_bar[stage], n0 + b * 32, w0 + tp.dw, tp.dx, h0 + tp.dh, img);
+                }
+                if (SPLIT) {
+                    for (int pl = 0; pl < 2; ++pl) {
+                        for (int a = 0; a < a16; ++a)
+                            tma_load_5d(st + L::OFF_A16 + pl * L::A16 + a * WG_ATOM_BYTES, &p.amap16[pl],
+                                        &full_bar[stage], m0 + a * 64, w0, 0, h0, img);
+                        for (int tt = 0; tt < TPC; ++tt) {
+                            const TgTap tp = p.taps[tap0 + tt];
+                            for (int b = 0; b < b16; ++b)
+                                tma_load_5d(st + L::OFF_B16 + pl * L::B16 + (tt * (BN / 64) + b) * WG_ATOM_BYTES,
+                                            &p.bmap16[pl][tp.map], &full_bar[stage], n0 + b * 64, w0 + tp.dw, tp.dx,
+                                            h0 + tp.dh, img);
+                        }
                     }
                 }
                 if (++stage == STAGES) {
@@ -132,29 +148,36 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);
+            constexpr uint32_t idesc32 = make_idesc_tf32(128, BN, 1, 1);
+            constexpr uint32_t idesc16 = make_idesc_bf16(128, BN, 1, 1);
             int stage = 0;
             uint32_t phase = 0;
             for (int it = 0; it < ntiles; ++it) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                const uint32_t sb = sa + L::A_BYTES;
+                const uint32_t st = smem_u32(smem + stage * L::STAGE_BYTES);
 #pragma unroll
-                for (int k = 0; k < WG_PIX / 8; ++k) {  // K = 8 pixel rows per MMA (two 4-row swizzle groups)
-                    const uint64_t ad = make_smem_desc_sw128(sa + k * 1024, p.lbo_bytes, p.sbo_bytes, p.layout);
+                for (int k = 0; k < WG_PIX / 8; ++k) {  // tf32: K = 8 pixel rows per MMA (two 4-row swizzle groups)
+                    const uint64_t ad = make_smem_desc_sw128(st + k * 1024, p.lbo_bytes, p.sbo_bytes, p.layout);
 #pragma unroll
                     for (int tt = 0; tt < TPC; ++tt) {
-                        const uint32_t boff = tt * (BN / 32) * WG_ATOM_BYTES + k * 1024;
-                        const uint64_t bd = make_smem_desc_sw128(sb + boff, p.lbo_bytes, p.sbo_bytes, p.layout);
-                        umma_tf32(tmem_base + tt * BN, ad, bd, idesc, (it | k) != 0);
-                        if (SPLIT) {  // + A_lo * B_hi + A_hi * B_lo
-                            const uint64_t adl =
-                                make_smem_desc_sw128(sa + L::A_PLANE + k * 1024, p.lbo_bytes, p.sbo_bytes, p.layout);
-                            const uint64_t bdl =
-                                make_smem_desc_sw128(sb + L::B_PLANE + boff, p.lbo_bytes, p.sbo_bytes, p.layout);
-                            umma_tf32(tmem_base + tt * BN, adl, bd, idesc, 1);
-                            umma_tf32(tmem_base + tt * BN, ad, bdl, idesc, 1);
+                        const uint64_t bd = make_smem_desc_sw128(st + L::OFF_B32 + tt * (BN / 32) * WG_ATOM_BYTES + k * 1024,
+                                                                 p.lbo_bytes, p.sbo_bytes, p.layout);
+                        umma_tf32(tmem_base + tt * BN, ad, bd, idesc32, (it | k) != 0);
+                    }
+                }
+                if (SPLIT) {
+#pragma unroll
+                    for (int k = 0; k < WG_PIX / 16; ++k) {  // bf16: K = 16 pixel rows per MMA (two 8-row groups)
+                        const uint64_t ah = make_smem_desc_sw128(st + L::OFF_A16 + k * 2048, WG_ATOM_BYTES, 1024, 2);
+                        const uint64_t al = make_smem_desc_sw128(st + L::OFF_A16 + L::A16 + k * 2048, WG_ATOM_BYTES, 1024, 2);
+#pragma unroll
+                        for (int tt = 0; tt < TPC; ++tt) {
+                            const uint32_t bo = L::OFF_B16 + tt * (BN / 64) * WG_ATOM_BYTES + k * 2048;
+                            const uint64_t bh = make_smem_desc_sw128(st + bo, WG_ATOM_BYTES, 1024, 2);
+                            const uint64_t bl = make_smem_desc_sw128(st + bo + L::B16, WG_ATOM_BYTES, 1024, 2);
+                            umma_bf16(tmem_base + tt * BN, al, bh, idesc16, 1);  // A_lo * B_hi
+                            umma_bf16(tmem_base + tt * BN, ah, bl, idesc16, 1);  // A_hi * B_lo
                         }
                     }
                 }
@@ -181,14 +204,9 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
                 tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tt * BN + j * 32), v);
                 tmem_ld_wait();
                 if (row < p.ca) {
-                    if (p.scalar_atomics) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) atomicAdd(orow + j * 32 + i, v[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            red_add_v4(orow + j * 32 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        red_add_v4(orow + j * 32 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
         }

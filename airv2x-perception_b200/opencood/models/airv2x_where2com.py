@@ -101,7 +101,7 @@ class _Step(torch.autograd.Function):
 
 
 class Airv2xWhere2com(nn.Module):
-    def __init__(self, args, precision="tf32x3"):
+    def __init__(self, args, precision="split3"):
         super().__init__()
         self.args = args
         self.collaborators = args["collaborators"]

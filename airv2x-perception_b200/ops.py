@@ -30,18 +30,32 @@ def _f32(t):
 
 
 # ----------------------------------------------------------------------------- weights
+class Weights(ctypes.Structure):
+    _fields_ = [("w32", ctypes.c_void_p), ("w16", ctypes.c_void_p)]
+
+
+class PackedW:
+    """packed conv / deconv weights: forward (f32, f16) and data-gradient (d32, d16) layouts; *16 are bf16 [2,...]"""
+
+    __slots__ = ("f32", "f16", "d32", "d16", "fwd", "dgrad")
+
+    def __init__(self, f32, f16, d32, d16):
+        self.f32, self.f16, self.d32, self.d16 = f32, f16, d32, d16
+        self.fwd = Weights(f32.data_ptr(), f16.data_ptr())
+        self.dgrad = Weights(d32.data_ptr(), d16.data_ptr())
+
+
 def pack_conv_weight(w, cout_pad=None, out=None):
-    """OIHW -> (wf [2][kk][cout_pad][cin], wd [2][kk][cin][cout_pad]); plane 0 = tf32_rn(w), plane 1 = residual."""
+    """OIHW -> PackedW with f32 [kk][cout_pad][cin], f16 [2][kk][cout_pad][cin], d32 [kk][cin][cout_pad], d16 [2][...]"""
     cout, cin, k, _ = w.shape
     cout_pad = cout_pad or cout
     if out is None:
-        wf = torch.empty(2, k * k, cout_pad, cin, device=w.device, dtype=torch.float32)
-        wd = torch.empty(2, k * k, cin, cout_pad, device=w.device, dtype=torch.float32)
-    else:
-        wf, wd = out
+        dev = w.device
+        out = PackedW(torch.empty(k * k, cout_pad, cin, device=dev), torch.empty(2, k * k, cout_pad, cin, device=dev, dtype=torch.bfloat16),
+                      torch.empty(k * k, cin, cout_pad, device=dev), torch.empty(2, k * k, cin, cout_pad, device=dev, dtype=torch.bfloat16))
     call("a2x_pack_conv_weight", _ptr(_f32(w.contiguous())), c_int(cout), c_int(cin), c_int(k), c_int(cout_pad),
-         _ptr(wf), _ptr(wd), stream_ptr())
-    return wf, wd
+         _ptr(out.f32), _ptr(out.f16), _ptr(out.d32), _ptr(out.d16), stream_ptr())
+    return out
 
 
 def unpack_conv_wgrad(dwp, cout, cin, k, out=None, accumulate=False):
@@ -55,16 +69,15 @@ def unpack_conv_wgrad(dwp, cout, cin, k, out=None, accumulate=False):
 
 
 def pack_deconv_weight(w, out=None):
-    """[cin][cout][s][s] -> (wf [2][1][(ij,co)][ci], wd [2][ss][ci][co])"""
+    """[cin][cout][s][s] -> PackedW with f32 [1][(ij,co)][ci], d32 [ss][ci][co] (+ bf16 pairs)"""
     cin, cout, s, _ = w.shape
     if out is None:
-        wf = torch.empty(2, 1, s * s * cout, cin, device=w.device, dtype=torch.float32)
-        wd = torch.empty(2, s * s, cin, cout, device=w.device, dtype=torch.float32)
-    else:
-        wf, wd = out
-    call("a2x_pack_deconv_weight", _ptr(_f32(w.contiguous())), c_int(cin), c_int(cout), c_int(s), _ptr(wf), _ptr(wd),
-         stream_ptr())
-    return wf, wd
+        dev = w.device
+        out = PackedW(torch.empty(1, s * s * cout, cin, device=dev), torch.empty(2, 1, s * s * cout, cin, device=dev, dtype=torch.bfloat16),
+                      torch.empty(s * s, cin, cout, device=dev), torch.empty(2, s * s, cin, cout, device=dev, dtype=torch.bfloat16))
+    call("a2x_pack_deconv_weight", _ptr(_f32(w.contiguous())), c_int(cin), c_int(cout), c_int(s), _ptr(out.f32),
+         _ptr(out.f16), _ptr(out.d32), _ptr(out.d16), stream_ptr())
+    return out
 
 
 def unpack_deconv_wgrad(dwp, cin, cout, s, out=None, accumulate=False):
@@ -76,114 +89,120 @@ def unpack_deconv_wgrad(dwp, cin, cout, s, out=None, accumulate=False):
 
 
 # ============================================================================= split-plane activations
+class Operand(ctypes.Structure):
+    _fields_ = [("hi", ctypes.c_void_p), ("b16", ctypes.c_void_p), ("b16_plane", ctypes.c_longlong), ("cs", c_int)]
+
+
 class Act:
-    """An NHWC activation as GEMM operand: `hi` (+ optional `lo`) planes. hi + lo is the fp32 value."""
+    """An NHWC activation as GEMM operand: `hi` fp32 (tf32-rounded when split) and, in split mode, `b16`: a bf16 tensor
+    [2, n, h, w, c] with plane 0 = bf16(hi), plane 1 = bf16(v - hi)."""
 
-    __slots__ = ("hi", "lo")
+    __slots__ = ("hi", "b16")
 
-    def __init__(self, hi, lo=None):
-        self.hi, self.lo = hi, lo
+    def __init__(self, hi, b16=None):
+        self.hi, self.b16 = hi, b16
 
     @staticmethod
     def empty(shape, device, split):
-        if split:
-            t = torch.empty((2,) + tuple(shape), device=device, dtype=torch.float32)
-            return Act(t[0], t[1])
-        return Act(torch.empty(tuple(shape), device=device, dtype=torch.float32))
-
-    @staticmethod
-    def zeros(shape, device, split):
-        if split:
-            t = torch.zeros((2,) + tuple(shape), device=device, dtype=torch.float32)
-            return Act(t[0], t[1])
-        return Act(torch.zeros(tuple(shape), device=device, dtype=torch.float32))
+        hi = torch.empty(tuple(shape), device=device, dtype=torch.float32)
+        b16 = torch.empty((2,) + tuple(shape), device=device, dtype=torch.bfloat16) if split else None
+        return Act(hi, b16)
 
     def value(self):
-        return self.hi if self.lo is None else self.hi + self.lo
+        return self.hi if self.b16 is None else self.hi + self.b16[1].float()
 
     def slice_c(self, c0, c1):
-        return Act(self.hi[..., c0:c1], None if self.lo is None else self.lo[..., c0:c1])
+        return Act(self.hi[..., c0:c1], None if self.b16 is None else self.b16[..., c0:c1])
 
     def narrow_n(self, n0, n):
-        return Act(self.hi[n0:n0 + n], None if self.lo is None else self.lo[n0:n0 + n])
+        return Act(self.hi[n0:n0 + n], None if self.b16 is None else self.b16[:, n0:n0 + n])
 
     @property
     def shape(self):
         return self.hi.shape
 
+    def operand(self):
+        cs = _cs(self.hi)
+        if self.b16 is None:
+            return Operand(self.hi.data_ptr(), None, 0, cs)
+        assert _cs(self.b16[0]) == cs
+        return Operand(self.hi.data_ptr(), self.b16.data_ptr(), self.b16.stride(0), cs)
 
-def split_tf32(x):
+
+def _op(a):
+    return ctypes.byref(a.operand())
+
+
+def split(x):
+    """fp32 NHWC tensor -> split Act"""
     x = x.contiguous()
-    out = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.float32)
-    call("a2x_split_tf32", _ptr(x), ctypes.c_longlong(x.numel()), _ptr(out[0]), _ptr(out[1]), stream_ptr())
-    return Act(out[0], out[1])
-
-
-def add2(a, b, out):
-    call("a2x_add2", _ptr(a), _ptr(b), ctypes.c_longlong(a.numel()), _ptr(out), stream_ptr())
+    out = Act.empty(x.shape, x.device, True)
+    o = out.operand()
+    call("a2x_split", _ptr(x), ctypes.c_longlong(x.numel()), ctypes.byref(o), stream_ptr())
     return out
 
 
-def _lo(a):
-    return _ptr(a.lo) if a.lo is not None else _ptr(None)
+split_tf32 = split
+
+
+def combine(act, out):
+    """out = hi + float(l16) (fp32 value of a split activation; identity copy target for consumers that are not GEMMs)"""
+    call("a2x_combine", _ptr(act.hi), _ptr(act.b16[1]), ctypes.c_longlong(act.hi.numel()), _ptr(out), stream_ptr())
+    return out
 
 
 # split-aware conv family ------------------------------------------------------------------------------------
-def conv_fwd(x, wf, k, stride, out, scale=None, shift=None, relu=False, stats=None):
-    """x, out: Act. wf: packed [2][kk][cout][cin]."""
-    n, h, w, cin = x.shape
-    cout = wf.shape[2]
-    sh = _shape(n, h, w, cin, cout, k, stride)
-    call("a2x_conv2d_fwd", ctypes.byref(sh), _ptr(x.hi), _lo(x), c_int(_cs(x.hi)), _ptr(wf), _ptr(out.hi), _lo(out),
-         c_int(_cs(out.hi)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(stats), stream_ptr())
+def conv_fwd(x, w, k, stride, out, scale=None, shift=None, relu=False, stats=None):
+    """x, out: Act; w: PackedW"""
+    n, h, ww, cin = x.shape
+    cout = w.f32.shape[1]
+    sh = _shape(n, h, ww, cin, cout, k, stride)
+    call("a2x_conv2d_fwd", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _op(out), _ptr(scale), _ptr(shift),
+         c_int(int(relu)), _ptr(stats), stream_ptr())
     return out
 
 
-def conv_dgrad(dy, wd, k, stride, dx, accumulate=False):
-    """dy: Act; dx: plain NHWC tensor [n,h,w,cin]; wd packed [2][kk][cin][cout]."""
-    n, h, w, cin = dx.shape
+def conv_dgrad(dy, w, k, stride, dx, accumulate=False):
+    """dy: Act; dx: plain NHWC tensor [n,h,w,cin]"""
+    n, h, ww, cin = dx.shape
     cout = dy.shape[3]
-    sh = _shape(n, h, w, cin, cout, k, stride)
-    call("a2x_conv2d_dgrad", ctypes.byref(sh), _ptr(dy.hi), _lo(dy), c_int(_cs(dy.hi)), _ptr(wd), _ptr(dx),
-         c_int(_cs(dx)), c_int(int(accumulate)), stream_ptr())
+    sh = _shape(n, h, ww, cin, cout, k, stride)
+    call("a2x_conv2d_dgrad", ctypes.byref(sh), _op(dy), ctypes.byref(w.dgrad), _ptr(dx), c_int(_cs(dx)),
+         c_int(int(accumulate)), stream_ptr())
     return dx
 
 
 def conv_wgrad(x, dy, k, stride, dwp):
-    """x, dy: Act (both split or both single); dwp: zeroed packed [kk][cout][cin]."""
-    n, h, w, cin = x.shape
+    """x, dy: Act (split only if both are); dwp: zeroed packed [kk][cout][cin]"""
+    n, h, ww, cin = x.shape
     cout = dy.shape[3]
-    sh = _shape(n, h, w, cin, cout, k, stride)
-    both = x.lo is not None and dy.lo is not None
-    call("a2x_conv2d_wgrad", ctypes.byref(sh), _ptr(x.hi), _lo(x) if both else _ptr(None), c_int(_cs(x.hi)), _ptr(dy.hi),
-         _lo(dy) if both else _ptr(None), c_int(_cs(dy.hi)), _ptr(dwp), stream_ptr())
+    sh = _shape(n, h, ww, cin, cout, k, stride)
+    call("a2x_conv2d_wgrad", ctypes.byref(sh), _op(x), _op(dy), _ptr(dwp), stream_ptr())
     return dwp
 
 
-def deconv_fwd(x, wf, cout, s, out, scale=None, shift=None, relu=False, stats=None):
-    n, h, w, cin = x.shape
-    sh = _shape(n, h, w, cin, cout, s, s)
-    call("a2x_deconv_fwd", ctypes.byref(sh), _ptr(x.hi), _lo(x), c_int(_cs(x.hi)), _ptr(wf), _ptr(out.hi), _lo(out),
-         c_int(_cs(out.hi)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(stats), stream_ptr())
+def deconv_fwd(x, w, cout, s, out, scale=None, shift=None, relu=False, stats=None):
+    n, h, ww, cin = x.shape
+    sh = _shape(n, h, ww, cin, cout, s, s)
+    call("a2x_deconv_fwd", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _op(out), _ptr(scale), _ptr(shift),
+         c_int(int(relu)), _ptr(stats), stream_ptr())
     return out
 
 
-def deconv_dgrad(dy, wd, s, dx, accumulate=False):
-    n, h, w, cin = dx.shape
+def deconv_dgrad(dy, w, s, dx, accumulate=False):
+    n, h, ww, cin = dx.shape
     cout = dy.shape[3]
-    sh = _shape(n, h, w, cin, cout, s, s)
-    call("a2x_deconv_dgrad", ctypes.byref(sh), _ptr(dy.hi), _lo(dy), c_int(_cs(dy.hi)), _ptr(wd), _ptr(dx),
-         c_int(_cs(dx)), c_int(int(accumulate)), stream_ptr())
+    sh = _shape(n, h, ww, cin, cout, s, s)
+    call("a2x_deconv_dgrad", ctypes.byref(sh), _op(dy), ctypes.byref(w.dgrad), _ptr(dx), c_int(_cs(dx)),
+         c_int(int(accumulate)), stream_ptr())
     return dx
 
 
 def deconv_wgrad(x, dy, s, dwp):
-    n, h, w, cin = x.shape
+    n, h, ww, cin = x.shape
     cout = dy.shape[3]
-    sh = _shape(n, h, w, cin, cout, s, s)
-    both = x.lo is not None and dy.lo is not None
-    call("a2x_deconv_wgrad", ctypes.byref(sh), _ptr(x.hi), _lo(x) if both else _ptr(None), c_int(_cs(x.hi)),
-         _ptr(dy.hi), _lo(dy) if both else _ptr(None), c_int(_cs(dy.hi)), _ptr(dwp), stream_ptr())
+    sh = _shape(n, h, ww, cin, cout, s, s)
+    call("a2x_deconv_wgrad", ctypes.byref(sh), _op(x), _op(dy), _ptr(dwp), stream_ptr())
     return dwp
 
 
@@ -214,8 +233,8 @@ def bn_eval_affine(gamma, beta, rm, rv, scale, shift, eps=1e-3):
 
 def affine_act(x, scale, shift, relu, out, mask=None):
     """x: NHWC tensor; out: Act"""
-    call("a2x_affine_act", _ptr(x), c_int(_cs(x)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(mask), _ptr(out.hi),
-         _lo(out), c_int(_cs(out.hi)), c_ll(_npix(x)), c_int(x.shape[3]), stream_ptr())
+    call("a2x_affine_act", _ptr(x), c_int(_cs(x)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(mask), _op(out),
+         c_ll(_npix(x)), c_int(x.shape[3]), stream_ptr())
     return out
 
 
@@ -225,7 +244,7 @@ def bn_relu_bwd(dy, z, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, accu
     call("a2x_bn_relu_bwd_reduce", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift), _ptr(mean),
          _ptr(invstd), c_ll(npix), c_int(C), _ptr(sums), stream_ptr())
     call("a2x_bn_relu_bwd_apply", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift), _ptr(mean),
-         _ptr(invstd), _ptr(sums), c_d(float(npix)), _ptr(dz.hi), _lo(dz), c_int(_cs(dz.hi)), c_ll(npix), c_int(C),
+         _ptr(invstd), _ptr(sums), c_d(float(npix)), _op(dz), c_ll(npix), c_int(C),
          _ptr(dgamma), _ptr(dbeta), c_int(int(accumulate)), stream_ptr())
     return dz
 
@@ -233,7 +252,7 @@ def bn_relu_bwd(dy, z, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, accu
 def relu_bwd(dy, y, out, mask=None):
     """g = dy * (y > 0) * mask ; dy, y NHWC tensors (y may be None); out: Act"""
     call("a2x_relu_bwd", _ptr(dy), c_int(_cs(dy)), _ptr(y), c_int(_cs(y) if y is not None else 0), _ptr(mask),
-         _ptr(out.hi), _lo(out), c_int(_cs(out.hi)), c_ll(_npix(dy)), c_int(dy.shape[3]), stream_ptr())
+         _op(out), c_ll(_npix(dy)), c_int(dy.shape[3]), stream_ptr())
     return out
 
 
@@ -288,8 +307,7 @@ def pfn_stats_finalize(moments, rows, w, gamma, beta, n_updates, rm, rv, scale, 
 
 def pfn_scatter(vox, num, coords, geom, w, scale, shift, agent_map, canvas, pillar_out=None, amax=None, seg=None):
     call("a2x_pfn_scatter", _ptr(vox), _ptr(num), _ptr(coords), c_ll(_m(vox, seg)), ctypes.byref(geom), _seg(seg), _ptr(w),
-         _ptr(scale), _ptr(shift), _ptr(agent_map), _ptr(canvas.hi), _lo(canvas), _ptr(pillar_out), _ptr(amax),
-         stream_ptr())
+         _ptr(scale), _ptr(shift), _ptr(agent_map), _op(canvas), _ptr(pillar_out), _ptr(amax), stream_ptr())
 
 
 def pfn_bwd(vox, num, coords, geom, w, scale, shift, mean, invstd, agent_map, dcanvas, amax, moments, rows, acc_ws, dw,
@@ -322,7 +340,7 @@ def comm_rate_ego(mask, hw, n_scenes, scene_start, scene_len, ones):
 def att_fuse_fwd(x, out):
     """x: dense NHWC tensor [n_agents,h,w,c] of one scene; out: Act [1,h,w,c] (or [h,w,c])"""
     n, h, w, c = x.shape
-    call("a2x_att_fuse_fwd", _ptr(x), c_int(n), c_int(h * w), c_int(c), _ptr(out.hi), _lo(out), stream_ptr())
+    call("a2x_att_fuse_fwd", _ptr(x), c_int(n), c_int(h * w), c_int(c), _op(out), stream_ptr())
 
 
 def att_fuse_bwd(x, dout, dx):

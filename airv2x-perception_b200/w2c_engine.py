@@ -20,15 +20,15 @@ from .ops import Act
 
 AGENT_TYPES = ("vehicle", "rsu", "drone")
 TYPE_PREFIX = {"vehicle": "veh_models", "rsu": "rsu_models", "drone": "drone_models"}
-HEAD_PAD = 32
+HEAD_PAD = 64  # fused head GEMM width (cls | reg | obj | zero pad); 64 keeps split-mode K a multiple of 64
 
 
 class W2CEngine:
-    def __init__(self, args, device, precision="tf32x3"):
-        assert precision in ("tf32x3", "tf32"), precision
+    def __init__(self, args, device, precision="split3"):
+        assert precision in ("split3", "tf32"), precision
         self.args = args
         self.device = torch.device(device)
-        self.split = precision == "tf32x3"
+        self.split = precision == "split3"
         self.precision = precision
         mf = args["modality_fusion"]
         bb = mf["base_bev_backbone"]
@@ -72,10 +72,8 @@ class W2CEngine:
 
     def _act(self, name, shape, split=None):
         split = self.split if split is None else split
-        if split:
-            t = self._buf(name, (2,) + tuple(shape))
-            return Act(t[0], t[1])
-        return Act(self._buf(name, shape))
+        hi = self._buf(name, shape)
+        return Act(hi, self._buf(name + ".b16", (2,) + tuple(shape), torch.bfloat16) if split else None)
 
     def _zeroed(self, name, nbytes_elems, dtype):
         """A slice of a per-step arena that is zeroed once per step (sums, packed weight gradients)."""
@@ -98,24 +96,33 @@ class W2CEngine:
                 a.zero_()
 
     # ------------------------------------------------------------------ weights
+    def _packed(self, name, f_shape, d_shape):
+        pk = self.bufs.get(("packed", name))
+        if pk is None:
+            bf = torch.bfloat16
+            pk = ops.PackedW(self._buf(name + ".f32", f_shape), self._buf(name + ".f16", (2,) + tuple(f_shape), bf),
+                             self._buf(name + ".d32", d_shape), self._buf(name + ".d16", (2,) + tuple(d_shape), bf))
+            self.bufs[("packed", name)] = pk
+        return pk
+
     def _pack_weights(self, P):
         W = {}
         for i, ln in enumerate(self.layer_nums):
             for k in range(ln + 1):
                 name = "backbone.blocks.%d.%d.weight" % (i, 1 + 3 * k)
                 w = P[name]
-                W[name] = ops.pack_conv_weight(w, out=(self._buf(name + ".wf", (2, 9, w.shape[0], w.shape[1])),
-                                                       self._buf(name + ".wd", (2, 9, w.shape[1], w.shape[0]))))
+                co, ci = w.shape[0], w.shape[1]
+                W[name] = ops.pack_conv_weight(w, out=self._packed(name, (9, co, ci), (9, ci, co)))
             name = "backbone.deblocks.%d.0.weight" % i
             w = P[name]
             s = self.up_strides[i]
-            W[name] = ops.pack_deconv_weight(w, out=(self._buf(name + ".wf", (2, 1, s * s * w.shape[1], w.shape[0])),
-                                                     self._buf(name + ".wd", (2, s * s, w.shape[0], w.shape[1]))))
+            ci, co = w.shape[0], w.shape[1]
+            W[name] = ops.pack_deconv_weight(w, out=self._packed(name, (1, s * s * co, ci), (s * s, ci, co)))
         for idx, k in ((0, 1), (2, 3)):
             name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
             w = P[name]
-            W[name] = ops.pack_conv_weight(w, out=(self._buf(name + ".wf", (2, k * k, w.shape[0], w.shape[1])),
-                                                   self._buf(name + ".wd", (2, k * k, w.shape[1], w.shape[0]))))
+            co, ci = w.shape[0], w.shape[1]
+            W[name] = ops.pack_conv_weight(w, out=self._packed(name, (k * k, co, ci), (k * k, ci, co)))
         hw = self._buf("heads.w", (HEAD_PAD, self.c_shrink, 1, 1))
         hb = self._buf("heads.b", (HEAD_PAD,))
         nc, nr = self.A * self.K, 7 * self.A
@@ -127,8 +134,8 @@ class W2CEngine:
         hb[:nc].copy_(P["cls_head.bias"])
         hb[nc:nc + nr].copy_(P["reg_head.bias"])
         hb[nc + nr:self.n_head].copy_(P["obj_head.bias"])
-        W["heads"] = ops.pack_conv_weight(hw, out=(self._buf("heads.wf", (2, 1, HEAD_PAD, self.c_shrink)),
-                                                   self._buf("heads.wd", (2, 1, self.c_shrink, HEAD_PAD))))
+        W["heads"] = ops.pack_conv_weight(hw, out=self._packed("heads", (1, HEAD_PAD, self.c_shrink),
+                                                               (1, self.c_shrink, HEAD_PAD)))
         W["heads.bias"] = hb
         return W
 
@@ -156,7 +163,7 @@ class W2CEngine:
         cout = P[conv].shape[0]
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
         y = self._act(tag + ".y", (n, ho, wo, cout))
-        wf, _ = W[conv]
+        wf = W[conv]
         if not training:
             scale, shift, _, _ = self._bn_params(P, bn, False, y.hi, 0, tag)
             ops.conv_fwd(x, wf, 3, stride, y, scale=scale, shift=shift, relu=True)
@@ -185,7 +192,7 @@ class W2CEngine:
         bn = "backbone.deblocks.%d.1" % i
         s = self.up_strides[i]
         cout = self.up_filters[i]
-        wf, _ = W[conv]
+        wf = W[conv]
         n, h, w, _ = x.shape
         tg = "%s.d%d" % (tag, i)
         if not training:
@@ -206,12 +213,12 @@ class W2CEngine:
         n, h, w, _ = cat.shape
         y1 = self._act(tag + ".s1", (n, h, w, self.c_shrink))
         y2 = self._act(tag + ".s2", (n, h, w, self.c_shrink))
-        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"][0], 1, 1, y1,
+        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,
                      shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
-        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"][0], 3, 1, y2,
+        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, y2,
                      shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
         heads = self._buf(tag + ".heads", (n, h, w, HEAD_PAD))
-        ops.conv_fwd(y2, W["heads"][0], 1, 1, Act(heads), shift=W["heads.bias"])
+        ops.conv_fwd(y2, W["heads"], 1, 1, Act(heads), shift=W["heads.bias"])
         return y1, y2, heads
 
     # ------------------------------------------------------------------ voxelisation (raw point clouds)
@@ -252,8 +259,8 @@ class W2CEngine:
         n_total, ny, nx = layout["n_total"], layout["ny"], layout["nx"]
         canvas = self._act("canvas", (n_total, ny, nx, 64))
         canvas.hi.zero_()
-        if canvas.lo is not None:
-            canvas.lo.zero_()
+        if canvas.b16 is not None:
+            canvas.b16.zero_()
         if "raw" in lidar:
             lidar = self._voxelize(lidar["raw"], layout)
         for t in AGENT_TYPES:
@@ -391,10 +398,10 @@ class W2CEngine:
 
     def _full(self, act, name):
         """fp32 value of a (possibly split) activation as one dense tensor (fusion consumes full precision)."""
-        if act.lo is None:
+        if act.b16 is None:
             return act.hi
         out = self._buf(name, act.shape)
-        ops.add2(act.hi, act.lo, out)
+        ops.combine(act, out)
         return out
 
     # ------------------------------------------------------------------ loss (fused value + gradient)
@@ -447,14 +454,16 @@ class W2CEngine:
             ops.conv_wgrad(x, dy, k, stride, dwp)
             return dwp
 
-        def bias_grad(g_hi, g_lo, C, out):
-            sums = self._zeroed("bias.sums.%d" % id(out), 2 * C, torch.float64)
-            ops.channel_stats(g_hi, sums)
+        def bias_grad(g, C, out):
+            """out[c] = sum over pixels of the gradient; g: Act (the exact value is hi + l16) or plain tensor"""
+            sums = self._zeroed("bias.sums", 2 * C, torch.float64)
+            if isinstance(g, Act) and g.b16 is not None:
+                full = self._buf("bwd.biasfull.%d" % C, g.shape)
+                ops.combine(g, full)
+                ops.channel_stats(full, sums)
+            else:
+                ops.channel_stats(g.hi if isinstance(g, Act) else g, sums)
             ops.sums_to_float(sums, C, out)
-            if g_lo is not None:
-                sums2 = self._zeroed("bias.sums2.%d" % id(out), 2 * C, torch.float64)
-                ops.channel_stats(g_lo, sums2)
-                ops.sums_to_float(sums2, C, out, accumulate=True)
 
         # ---- heads
         dh = self._act("bwd.dheads", dheads.shape)
@@ -467,36 +476,34 @@ class W2CEngine:
             grads["reg_head.weight"].copy_(hg[nc:nc + nr])
             grads["obj_head.weight"].copy_(hg[nc + nr:self.n_head])
             hbg = self._buf("heads.bgrad", (HEAD_PAD,))
-            bias_grad(dheads, None, HEAD_PAD, hbg)
+            bias_grad(dheads, HEAD_PAD, hbg)
             grads["cls_head.bias"].copy_(hbg[:nc])
             grads["reg_head.bias"].copy_(hbg[nc:nc + nr])
             grads["obj_head.bias"].copy_(hbg[nc + nr:self.n_head])
         d_y2 = self._buf("bwd.d_y2", S["y2"].shape)
-        ops.conv_dgrad(dh, W["heads"][1], 1, 1, d_y2)
+        ops.conv_dgrad(dh, W["heads"], 1, 1, d_y2)
 
         # ---- shrink conv 2 (3x3 + bias + ReLU)
-        y2full = self._full(S["y2"], "bwd.y2full")
         g2 = self._act("bwd.g2", S["y2"].shape)
-        ops.relu_bwd(d_y2, y2full, g2)
+        ops.relu_bwd(d_y2, S["y2"].hi, g2)  # y > 0 <=> hi > 0 (rounding keeps the sign)
         n2 = "shrink_conv.layers.0.double_conv.2"
         with self._on_side():
             dwp = wgrad_conv(S["y1"], g2, n2 + ".weight", 3, 1)
             ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_shrink, 3, out=grads[n2 + ".weight"])
-            bias_grad(g2.hi, g2.lo, self.c_shrink, grads[n2 + ".bias"])
+            bias_grad(g2, self.c_shrink, grads[n2 + ".bias"])
         d_y1 = self._buf("bwd.d_y1", S["y1"].shape)
-        ops.conv_dgrad(g2, W[n2 + ".weight"][1], 3, 1, d_y1)
+        ops.conv_dgrad(g2, W[n2 + ".weight"], 3, 1, d_y1)
 
         # ---- shrink conv 1 (1x1 + bias + ReLU)
-        y1full = self._full(S["y1"], "bwd.y1full")
         g1 = self._act("bwd.g1", S["y1"].shape)
-        ops.relu_bwd(d_y1, y1full, g1)
+        ops.relu_bwd(d_y1, S["y1"].hi, g1)
         n1 = "shrink_conv.layers.0.double_conv.0"
         with self._on_side():
             dwp = wgrad_conv(S["catB"], g1, n1 + ".weight", 1, 1)
             ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_cat, 1, out=grads[n1 + ".weight"])
-            bias_grad(g1.hi, g1.lo, self.c_shrink, grads[n1 + ".bias"])
+            bias_grad(g1, self.c_shrink, grads[n1 + ".bias"])
         d_cat = self._buf("bwd.d_cat", (B, h2, w2, self.c_cat))
-        ops.conv_dgrad(g1, W[n1 + ".weight"][1], 1, 1, d_cat)
+        ops.conv_dgrad(g1, W[n1 + ".weight"], 1, 1, d_cat)
 
         # ---- deblocks (pass B) -> d(fused_i); fusion backward -> d(x_i) for every agent
         levels = S["levels"]
@@ -518,7 +525,7 @@ class W2CEngine:
                 ops.deconv_wgrad(r["x"], dz, s, dwp)
                 ops.unpack_deconv_wgrad(dwp, cin, cout, s, out=grads[r["conv"]])
             d_fused = self._buf("bwd.d_fused%d" % i, lv["fused"].shape)
-            ops.deconv_dgrad(dz, W[r["conv"]][1], s, d_fused)
+            ops.deconv_dgrad(dz, W[r["conv"]], s, d_fused)
             dx = self._buf("bwd.dx%d" % i, lv["x"].shape)
             pos = 0
             for b, n in enumerate(record_len):
@@ -546,10 +553,10 @@ class W2CEngine:
                     ops.unpack_conv_wgrad(dwp, cout, cin, 3, out=grads[r["conv"]])
                 if k > 0:
                     dprev = self._buf("bwd.dprev.%s.b%d.%d" % (tag, i, k), r["x"].shape)
-                    ops.conv_dgrad(dz, W[r["conv"]][1], 3, r["stride"], dprev)
+                    ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], dprev)
                     dy = dprev
                 else:
-                    ops.conv_dgrad(dz, W[r["conv"]][1], 3, r["stride"], dx_first, accumulate=accumulate_first)
+                    ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], dx_first, accumulate=accumulate_first)
 
         nlev = len(levels)
         for i in range(nlev - 1, 0, -1):

@@ -43,53 +43,67 @@ typedef struct {
     int n, h, w, cin, cout, ksize, stride;
 } a2x_conv_shape;
 
-/* weight re-layout (tiny, HBM-bound):  OIHW -> [2][tap][cout_pad][cin] (forward B operand) and
- * [2][tap][cin][cout_pad] (dgrad); plane 0 = tf32_rn(w), plane 1 = w - plane 0 */
-int a2x_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, float* w_fwd, float* w_dgrad,
-                         a2x_stream_t stream);
+/* Precision. Every GEMM operand v may be given as one plane (`b16 == NULL`: plain TF32, values should be pre-rounded
+ * to TF32 with round-to-nearest, which every producer kernel here does) or as the 3-term SPLIT:
+ *     hi = tf32_rn(v) (fp32),   b16 plane 0 = bf16(hi),   b16 plane 1 = bf16(v - hi)
+ * and the contraction is evaluated as  hi*hi [kind::tf32]  +  l16*h16 [kind::f16 bf16]  +  h16*l16 [bf16]  into one
+ * fp32 TMEM accumulator: fp32-equivalent accuracy (~2^-20 relative per product) at 2 TF32-MMA-equivalents instead of 3.
+ * Split operands need channel counts that are multiples of 64. */
+typedef struct {
+    const float* hi;     /* NHWC fp32, pixel stride `cs` elements */
+    const void* b16;     /* NHWC bf16 [2 planes], same pixel stride; NULL = single-plane mode */
+    long long b16_plane; /* elements between the two bf16 planes */
+    int cs;
+} a2x_operand;
+typedef struct {
+    float* hi;
+    void* b16;           /* NULL: write the fp32 value only (not rounded) */
+    long long b16_plane;
+    int cs;
+} a2x_output;
+typedef struct {
+    const float* w32;    /* packed fp32 plane (tf32-rounded) */
+    const void* w16;     /* packed bf16 planes [2][...] (h16, l16); may be NULL in single-plane mode */
+} a2x_weights;
+
+/* weight re-layout (tiny, HBM-bound):  OIHW -> [tap][cout_pad][cin] (forward B operand) and [tap][cin][cout_pad]
+ * (dgrad); each as an fp32 plane (tf32_rn) and a bf16 pair [2][...]. Any output pointer may be NULL. */
+int a2x_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, float* w_fwd, void* w_fwd16,
+                         float* w_dgrad, void* w_dgrad16, a2x_stream_t stream);
 /* [tap][cout_pad][cin] -> OIHW (first `cout` rows) ; accumulate != 0 adds into dw_oihw */
 int a2x_unpack_conv_wgrad(const float* dw_packed, int cout, int cin, int ksize, int cout_pad, float* dw_oihw,
                           int accumulate, a2x_stream_t stream);
-/* ConvTranspose2d weight [cin][cout][s][s] -> [2][(i*s+j)*cout+co][ci] (forward) and [2][(i*s+j)][ci][co] (dgrad) */
-int a2x_pack_deconv_weight(const float* w_iohw, int cin, int cout, int s, float* w_fwd, float* w_dgrad,
-                           a2x_stream_t stream);
+/* ConvTranspose2d weight [cin][cout][s][s] -> [(i*s+j)*cout+co][ci] (forward) and [(i*s+j)][ci][co] (dgrad) */
+int a2x_pack_deconv_weight(const float* w_iohw, int cin, int cout, int s, float* w_fwd, void* w_fwd16, float* w_dgrad,
+                           void* w_dgrad16, a2x_stream_t stream);
 /* [(i*s+j)][ci][co] -> [cin][cout][s][s] */
 int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, float* dw_iohw, int accumulate,
                             a2x_stream_t stream);
 
-/* Precision: every GEMM operand may be given as one plane (1xTF32: values should be pre-rounded with
- * round-to-nearest, which every producer kernel in this library does) or as a (hi, lo) pair with
- * hi = tf32_rn(v), lo = v - hi ("3xTF32": hi*hi + lo*hi + hi*lo, fp32-equivalent accuracy, 3x the MMAs).
- * `*_lo == NULL` selects the single-plane mode. Packed weights always carry both planes: [2][...].
- * Outputs: y (+ y_lo if non-NULL, written as the split pair so the next GEMM can consume it). */
-
-/* y = act(scale[c] * conv(x, w) + shift[c]); scale/shift may be NULL; y has pixel stride y_cs.
+/* y = act(scale[c] * conv(x, w) + shift[c]); scale/shift may be NULL.
  * stats != NULL (requires no scale/shift/relu): the epilogue also accumulates the BatchNorm batch statistics of the
  * raw output, stats[c] += sum, stats[cout + c] += sum of squares (doubles, caller zeroes) — no extra HBM pass. */
-int a2x_conv2d_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
-                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, double* stats,
-                   a2x_stream_t stream);
-/* dx (+)= conv_transpose(dy, w) */
-int a2x_conv2d_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
-                     float* dx, int dx_cs, int accumulate, a2x_stream_t stream);
+int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
+                   const float* scale, const float* shift, int relu, double* stats, a2x_stream_t stream);
+/* dx (+)= conv_transpose(dy, w)   (dx: fp32 NHWC, pixel stride dx_cs) */
+int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
+                     int accumulate, a2x_stream_t stream);
 /* dw_packed[tap][cout][cin] += sum_pixels dy (x) x   (caller zeroes dw_packed) */
-int a2x_conv2d_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,
-                     const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream);
+int a2x_conv2d_wgrad(const a2x_conv_shape* s, const a2x_operand* x, const a2x_operand* dy, float* dw_packed,
+                     a2x_stream_t stream);
 
-int a2x_deconv_fwd(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* w_fwd, float* y,
-                   float* y_lo, int y_cs, const float* scale, const float* shift, int relu, double* stats,
-                   a2x_stream_t stream);
-int a2x_deconv_dgrad(const a2x_conv_shape* s, const float* dy, const float* dy_lo, int dy_cs, const float* w_dgrad,
-                     float* dx, int dx_cs, int accumulate, a2x_stream_t stream);
-int a2x_deconv_wgrad(const a2x_conv_shape* s, const float* x, const float* x_lo, int x_cs, const float* dy,
-                     const float* dy_lo, int dy_cs, float* dw_packed, a2x_stream_t stream);
-
+int a2x_deconv_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
+                   const float* scale, const float* shift, int relu, double* stats, a2x_stream_t stream);
+int a2x_deconv_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
+                     int accumulate, a2x_stream_t stream);
+int a2x_deconv_wgrad(const a2x_conv_shape* s, const a2x_operand* x, const a2x_operand* dy, float* dw_packed,
+                     a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- operand split
- * hi = tf32_rn(x), lo = x - hi (n multiple of 4). */
-int a2x_split_tf32(const float* x, long long n, float* hi, float* lo, a2x_stream_t stream);
-/* out = a + b (recombine a split pair) */
-int a2x_add2(const float* a, const float* b, long long n, float* out, a2x_stream_t stream);
+ * hi = tf32_rn(x), b16 = (bf16(hi), bf16(x - hi))  (n multiple of 4; out->cs ignored) */
+int a2x_split(const float* x, long long n, const a2x_output* out, a2x_stream_t stream);
+/* out = hi + float(l16): the fp32 value of a split pair to ~2^-20 (for consumers that are not GEMMs) */
+int a2x_combine(const float* hi, const void* l16, long long n, float* out, a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- BatchNorm / ReLU / masks (HBM-bound)
  * Replace nn.BatchNorm2d(eps 1e-3, momentum 0.01) + nn.ReLU and their autograd
@@ -104,21 +118,21 @@ int a2x_bn_finalize(const double* sums, double count, const float* gamma, const 
                     float* mean_out, float* invstd_out, a2x_stream_t stream);
 int a2x_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                        float eps, int C, float* scale, float* shift, a2x_stream_t stream);
-/* y = relu?(x*scale[c] + shift[c]) * mask[pixel]   (scale/shift/mask may be NULL; y_lo != NULL -> split pair) */
+/* y = relu?(x*scale[c] + shift[c]) * mask[pixel]   (scale/shift/mask may be NULL; y->b16 != NULL -> split) */
 int a2x_affine_act(const float* x, int x_cs, const float* scale, const float* shift, int relu, const float* mask,
-                   float* y, float* y_lo, int y_cs, long long npix, int C, a2x_stream_t stream);
+                   const a2x_output* y, long long npix, int C, a2x_stream_t stream);
 /* BN(train)+ReLU backward, pass 1: sums[c] += sum g, sums[C+c] += sum g*zhat with g = dy*(z*scale+shift > 0) */
 int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
                            const float* mean, const float* invstd, long long npix, int C, double* sums,
                            a2x_stream_t stream);
 /* pass 2: dz = scale*(g - sum_g/count - zhat*sum_gz/count); dgamma/dbeta (may be NULL) from the sums */
 int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
-                          const float* mean, const float* invstd, const double* sums, double count, float* dz,
-                          float* dz_lo, int dz_cs, long long npix, int C, float* dgamma, float* dbeta,
+                          const float* mean, const float* invstd, const double* sums, double count,
+                          const a2x_output* dz, long long npix, int C, float* dgamma, float* dbeta,
                           int accumulate_param_grads, a2x_stream_t stream);
 /* g = dy * (y > 0) * mask[pixel]  (y, mask may be NULL) */
-int a2x_relu_bwd(const float* dy, int dy_cs, const float* y, int y_cs, const float* mask, float* g, float* g_lo,
-                 int g_cs, long long npix, int C, a2x_stream_t stream);
+int a2x_relu_bwd(const float* dy, int dy_cs, const float* y, int y_cs, const float* mask, const a2x_output* g,
+                 long long npix, int C, a2x_stream_t stream);
 /* out[c] (+)= (float) sums[c] : bias gradients from a2x_channel_stats sums */
 int a2x_sums_to_float(const double* sums, int C, float* out, int accumulate, a2x_stream_t stream);
 /* torch.count_nonzero (airv2x_where2com.py:122) */
@@ -171,7 +185,7 @@ int a2x_pfn_stats_finalize(const double* moments65, double rows, const a2x_pfn_s
 /* canvas[agent_map[a]][y][x][:] = max_slot relu(scale*(W f)+shift); optional pillar_out [M][64], amax [M][64] u8 */
 int a2x_pfn_scatter(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
                     const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift,
-                    const int* agent_map, float* canvas, float* canvas_lo, float* pillar_out, unsigned char* amax,
+                    const int* agent_map, const a2x_output* canvas, float* pillar_out, unsigned char* amax,
                     a2x_stream_t stream);
 /* train-mode backward to (W, gamma, beta) given d(canvas); acc_ws = 64*12 doubles of workspace */
 int a2x_pfn_bwd(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
@@ -195,7 +209,7 @@ int a2x_comm_topk_mask(const float* smooth, int n, int hw, const int* k_per_agen
 int a2x_comm_rate_ego(float* mask, int hw, int n_scenes, const int* scene_start, const int* scene_len, float* ones,
                       a2x_stream_t stream);
 /* x: [n_agents][hw][c] of ONE scene (agent 0 = ego) -> out [hw][c] = row 0 of softmax(x x^T / sqrt(c)) x */
-int a2x_att_fuse_fwd(const float* x, int n_agents, int hw, int c, float* out, float* out_lo, a2x_stream_t stream);
+int a2x_att_fuse_fwd(const float* x, int n_agents, int hw, int c, const a2x_output* out, a2x_stream_t stream);
 int a2x_att_fuse_bwd(const float* x, const float* dout, int n_agents, int hw, int c, float* dx, a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- detection loss

@@ -7,7 +7,7 @@ import a2x_import
 import w2c_common as C
 from oracle import w2c_oracle as O
 M = a2x_import.pkg("opencood.models.airv2x_where2com")
-prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+prec = sys.argv[1] if len(sys.argv) > 1 else "split3"
 cfg, gold = C.load_small()
 args = cfg["model_args"]
 model = M.Airv2xWhere2com(args, precision=prec)
@@ -37,13 +37,13 @@ def fullbuf(name, shape):
         if n == name: return t
     return None
 canv = fullbuf("canvas", None)
-cv = (canv[0] + canv[1]) if prec == "tf32x3" else canv
+cv = canv
 print("canvas err", (nchw(cv) - keep["spatial_features"]).abs().max().item(), "max", keep["spatial_features"].abs().max().item())
 m = fullbuf("mask", None)
 print("mask mismatches", int((m.cpu().unsqueeze(1) != keep["mask"]).sum()), "of", m.numel())
 for i in range(3):
     f = fullbuf("B.fuse%d" % i, None)
-    fv = (f[0] + f[1]) if prec == "tf32x3" else f
+    fv = f
     print("fused level", i, "err", (nchw(fv) - keep["fused_l%d" % i]).abs().max().item(), "max", keep["fused_l%d" % i].abs().max().item())
 
 # ---- train step through autograd + oracle loss

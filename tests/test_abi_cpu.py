@@ -31,10 +31,10 @@ def test_bad_arguments_fail_loudly_without_gpu(pkg):
     libm = a2x_import.pkg("_lib")
     lib = libm.load()
     sh = libm.ConvShape(1, 8, 8, 30, 32, 3, 1)  # cin not a multiple of 32
-    rc = lib.a2x_conv2d_fwd(ctypes.byref(sh), None, None, 32, None, None, None, 32, None, None, 0, None, None)
+    rc = lib.a2x_conv2d_fwd(ctypes.byref(sh), None, None, None, None, None, 0, None, None)
     assert rc == 1
     assert b"multiples of 32" in lib.a2x_last_error()
-    rc = lib.a2x_split_tf32(None, ctypes.c_longlong(8), None, None, None)
+    rc = lib.a2x_split(None, ctypes.c_longlong(8), None, None)
     assert rc == 1
 
 

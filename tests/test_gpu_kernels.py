@@ -48,15 +48,17 @@ def test_conv_fwd_dgrad_wgrad(ops, case, split):
     dy = rnd(g, *yref.shape)
     dxref = torch.nn.grad.conv2d_input(x.shape, wt, dy, stride=s, padding=k // 2)
     dwref = torch.nn.grad.conv2d_weight(x, wt.shape, dy, stride=s, padding=k // 2)
-    wf, wd = ops.pack_conv_weight(wt)
+    if split and (cin % 64 or cout % 64):
+        pytest.skip("split operands need channel counts that are multiples of 64")
+    pw = ops.pack_conv_weight(wt)
     if split:
-        xs, dys, tol = ops.split_tf32(nhwc(x)), ops.split_tf32(nhwc(dy)), 5e-5
+        xs, dys, tol = ops.split(nhwc(x)), ops.split(nhwc(dy)), 5e-5
     else:
         xs, dys, tol = ops.Act(nhwc(x)), ops.Act(nhwc(dy)), 5e-3
     y = ops.Act(torch.empty_like(nhwc(yref)))
-    ops.conv_fwd(xs, wf, k, s, y)
+    ops.conv_fwd(xs, pw, k, s, y)
     dx = torch.empty_like(nhwc(x))
-    ops.conv_dgrad(dys, wd, k, s, dx)
+    ops.conv_dgrad(dys, pw, k, s, dx)
     dwp = torch.zeros(k * k, cout, cin, device="cuda")
     ops.conv_wgrad(xs, dys, k, s, dwp)
     dw = ops.unpack_conv_wgrad(dwp, cout, cin, k)
@@ -74,29 +76,34 @@ def test_deconv(ops, case):
     yref = F.conv_transpose2d(x, wt, stride=s)
     dy = rnd(g, *yref.shape)
     yref.backward(dy)
-    wf, wd = ops.pack_deconv_weight(wt.detach())
-    xs, dys = ops.split_tf32(nhwc(x.detach())), ops.split_tf32(nhwc(dy))
+    pw = ops.pack_deconv_weight(wt.detach())
+    xs, dys = ops.split(nhwc(x.detach())), ops.split(nhwc(dy))
     # forward into a channel slice of a wider (concat) buffer, with fused affine + ReLU epilogue
     buf = torch.zeros(n, h * s, w * s, 384, device="cuda")
     scale = torch.rand(cout, generator=g).cuda() + 0.5
     shift = torch.randn(cout, generator=g).cuda() * 0.1
-    ops.deconv_fwd(xs, wf, cout, s, ops.Act(buf[..., 128:128 + cout]), scale=scale, shift=shift, relu=True)
+    ops.deconv_fwd(xs, pw, cout, s, ops.Act(buf[..., 128:128 + cout]), scale=scale, shift=shift, relu=True)
     want = F.relu(yref.detach() * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     assert rel(buf[..., 128:128 + cout], nhwc(want)) < 5e-5
     assert float(buf[..., :128].abs().max()) == 0.0 and float(buf[..., 128 + cout:].abs().max()) == 0.0
     dx = torch.empty_like(nhwc(x.detach()))
-    ops.deconv_dgrad(dys, wd, s, dx)
+    ops.deconv_dgrad(dys, pw, s, dx)
     dwp = torch.zeros(s * s, cin, cout, device="cuda")
     ops.deconv_wgrad(xs, dys, s, dwp)
     assert rel(dx, nhwc(x.grad)) < 5e-5
     assert rel(ops.unpack_deconv_wgrad(dwp, cin, cout, s), wt.grad) < 5e-5
 
 
-def test_split_pair_is_exact(ops):
-    x = rnd(_g(3), 1, 4, 8, 32) * 100
-    a = ops.split_tf32(x)
-    assert torch.equal(a.hi + a.lo, x)                                     # hi + lo reproduces fp32 exactly
-    assert int((a.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0         # hi has 13 zero low mantissa bits
+def test_split_representation(ops):
+    x = rnd(_g(3), 1, 4, 8, 64) * 100
+    a = ops.split(x)
+    assert int((a.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0         # hi is a tf32 value (13 zero low bits)
+    assert float((a.hi - x).abs().max() / x.abs().max()) < 2.0 ** -11      # round-to-nearest
+    assert torch.equal(a.b16[0], a.hi.to(torch.bfloat16))                  # plane 0 = bf16(hi)
+    assert torch.equal(a.b16[1], (x - a.hi).to(torch.bfloat16))            # plane 1 = bf16(v - hi)
+    out = torch.empty_like(x)
+    ops.combine(a, out)
+    assert float((out - x).abs().max() / x.abs().max()) < 2.0 ** -19       # hi + l16 ~ v to 2^-20
 
 
 @pytest.mark.parametrize("case", [(4, 64, 9, 13), (3, 128, 5, 7), (5, 256, 4, 6), (1, 64, 3, 5), (16, 64, 2, 3)])
@@ -134,13 +141,13 @@ def test_batchnorm_relu_train(ops, case):
     scale, shift, mean, invstd = [torch.empty(C, device="cuda") for _ in range(4)]
     ops.channel_stats(z.detach(), sums)
     ops.bn_finalize(sums, N * H * W, gam.detach(), bet.detach(), 3, rm, rv, scale, shift, mean, invstd)
-    yo = ops.Act(torch.empty(2, N, H, W, C, device="cuda")[0], torch.empty(N, H, W, C, device="cuda"))
+    yo = ops.Act.empty((N, H, W, C), "cuda", True)
     ops.affine_act(z.detach(), scale, shift, True, yo)
     bs = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
     dz = ops.Act(torch.empty(N, H, W, C, device="cuda"))
     dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     ops.bn_relu_bwd(dy, z.detach(), scale, shift, mean, invstd, bs, dz, dg, db)
-    assert rel(yo.hi + yo.lo, y.detach()) < 1e-5
+    assert rel(yo.value(), y.detach()) < 1e-5
     assert rel(dz.hi, z.grad) < 1e-5 and rel(dg, gam.grad) < 1e-5 and rel(db, bet.grad) < 1e-5
     assert rel(rm, rm_ref) < 1e-5 and rel(rv, rv_ref) < 1e-5
 
@@ -278,11 +285,11 @@ def test_conv_epilogue_batch_statistics(ops, case):
     n, h, w, cin, cout, k, s = case
     g = _g(12)
     x, wt = rnd(g, n, cin, h, w), rnd(g, cout, cin, k, k) * 0.1
-    wf, _ = ops.pack_conv_weight(wt)
+    pw = ops.pack_conv_weight(wt)
     ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
     y = ops.Act(torch.empty(n, ho, wo, cout, device="cuda"))
     stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
-    ops.conv_fwd(ops.split_tf32(nhwc(x)), wf, k, s, y, stats=stats)
+    ops.conv_fwd(ops.split(nhwc(x)), pw, k, s, y, stats=stats)
     ref = torch.cat([y.hi.double().sum((0, 1, 2)), (y.hi.double() ** 2).sum((0, 1, 2))])
     assert float((stats - ref).abs().max() / ref.abs().max()) < 1e-5
 
@@ -291,9 +298,9 @@ def test_deconv_epilogue_batch_statistics(ops):
     g = _g(13)
     n, h, w, cin, cout, s = 2, 5, 9, 256, 128, 4
     x, wt = rnd(g, n, cin, h, w), rnd(g, cin, cout, s, s) * 0.1
-    wf, _ = ops.pack_deconv_weight(wt)
+    pw = ops.pack_deconv_weight(wt)
     y = ops.Act(torch.empty(n, h * s, w * s, cout, device="cuda"))
     stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
-    ops.deconv_fwd(ops.split_tf32(nhwc(x)), wf, cout, s, y, stats=stats)
+    ops.deconv_fwd(ops.split(nhwc(x)), pw, cout, s, y, stats=stats)
     ref = torch.cat([y.hi.double().sum((0, 1, 2)), (y.hi.double() ** 2).sum((0, 1, 2))])
     assert float((stats - ref).abs().max() / ref.abs().max()) < 1e-5
