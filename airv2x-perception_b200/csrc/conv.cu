@@ -3,6 +3,7 @@
 #include "../../include/airv2x_b200.h"
 #include "a2x_host.h"
 #include "tapgemm.cuh"
+#include "tapgemm_halo.cuh"
 #include "wgrad.cuh"
 
 namespace a2x {
@@ -62,7 +63,9 @@ static int launch_tg(const TgParams& p, int n_col_tiles, cudaStream_t st) {
                                             L::TOTAL));
         configured = true;
     }
-    dim3 grid(p.n_img * p.tiles_h * p.tiles_w, n_col_tiles, 1);
+    int n_tiles = p.n_img * p.tiles_h * p.tiles_w * n_col_tiles;
+    const int cap = g_debug[8] > 0 ? g_debug[8] : 148;  // persistent: one CTA per SM
+    dim3 grid(n_tiles < cap ? n_tiles : cap, 1, 1);
     tapgemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
@@ -92,9 +95,9 @@ static int run_tg(TgParams& p, int gh, int gw, int n_img, int ncols, cudaStream_
     const int tiles_n = (ncols + bn - 1) / bn;
     switch (bn) {
         case 256: return launch_tg<256, 4>(p, tiles_n, st);
-        case 128: return launch_tg<128, 3>(p, tiles_n, st);
-        case 64: return launch_tg<64, 4>(p, tiles_n, st);
-        case 32: return launch_tg<32, 4>(p, tiles_n, st);
+        case 128: return launch_tg<128, 6>(p, tiles_n, st);
+        case 64: return launch_tg<64, 8>(p, tiles_n, st);
+        case 32: return launch_tg<32, 8>(p, tiles_n, st);
     }
     set_error("bad bn %d", bn);
     return 1;
@@ -148,6 +151,87 @@ static int check_operand(const a2x_operand* x, int c, const char* what) {
         return 1;
     }
     return 0;
+}
+
+template <int BN, int NB>
+static int launch_th(const ThParams& p, int n_col_tiles, cudaStream_t st) {
+    using L = ThSmem<BN, NB>;
+    static bool configured = false;
+    if (!configured) {
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_halo_kernel<BN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            L::TOTAL));
+        configured = true;
+    }
+    int n_tiles = p.n_img * p.tiles_h * p.tiles_w * n_col_tiles;
+    const int cap = g_debug[8] > 0 ? g_debug[8] : 148;
+    dim3 grid(n_tiles < cap ? n_tiles : cap, 1, 1);
+    tapgemm_halo_kernel<BN, NB><<<grid, 192, L::TOTAL, st>>>(p);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// halo-box view (c, w, x, h, n) of a dense (step 1) NHWC tensor: box = (32|64, 10, 1, 18, 1)
+static int make_halo_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int cs, int bf16) {
+    const size_t es = bf16 ? 2 : 4;
+    uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, 1, (uint64_t)h, (uint64_t)n};
+    uint64_t str[4] = {(uint64_t)cs * es, (uint64_t)cs * es, (uint64_t)w * cs * es, (uint64_t)h * w * cs * es};
+    uint32_t box[5] = {(uint32_t)(bf16 ? 64 : 32), TH_COLS, 1, TH_ROWS, 1};
+    return encode_tmap_f32(m, base, 5, dims, str, box, 0, bf16);
+}
+
+// 3x3 stride-1 window GEMM through the halo kernel. sign = +1: forward taps (r-1, c-1); -1: data-gradient (1-r, 1-c).
+static int run_halo(const a2x_operand* a, int n, int h, int w, int k_ch, int ncols, const a2x_weights* wts, int sign,
+                    const a2x_output* y, const float* scale, const float* shift, int relu, int accumulate,
+                    double* stats, cudaStream_t st) {
+    ThParams p{};
+    if (int r = make_halo_map(&p.amap[0], a->hi, n, h, w, k_ch, a->cs, 0)) return r;
+    const int bn = bn_for(ncols);
+    if (int r = make_w_map(&p.bmap, wts->w32, 9, ncols, k_ch, bn)) return r;
+    p.npass = 1;
+    if (a->b16) {
+        const __nv_bfloat16* b = (const __nv_bfloat16*)a->b16;
+        if (int r = make_halo_map(&p.amap[1], b + a->b16_plane, n, h, w, k_ch, a->cs, 1)) return r;  // l16
+        if (int r = make_halo_map(&p.amap[2], b, n, h, w, k_ch, a->cs, 1)) return r;                // h16
+        if (int r = make_w_map(&p.bmap16, wts->w16, 18, ncols, k_ch, bn, 1)) return r;
+        p.npass = 3;
+    }
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            p.dh[r * 3 + c] = (int8_t)(sign * (r - 1));
+            p.dw[r * 3 + c] = (int8_t)(sign * (c - 1));
+        }
+    p.kchunks32 = k_ch / 32;
+    p.kchunks16 = k_ch / 64;
+    p.n_img = n;
+    p.gh = h;
+    p.gw = w;
+    p.tiles_h = (h + 15) / 16;
+    p.tiles_w = (w + 7) / 8;
+    p.out.hi = y->hi;
+    p.out.b16 = (__nv_bfloat16*)y->b16;
+    p.out.ps = y->b16_plane;
+    p.osn = (long long)h * w * y->cs;
+    p.osh = (long long)w * y->cs;
+    p.osw = y->cs;
+    p.ncols = ncols;
+    p.scale = scale;
+    p.shift = shift;
+    p.relu = relu;
+    p.accumulate = accumulate;
+    p.stats = stats;
+    p.stat_c = ncols;
+    p.base_offset_mode = g_debug[6];
+    if (g_debug[9]) p.relu = 77;
+    const int tiles_n = (ncols + bn - 1) / bn;
+    switch (bn) {
+        case 256: return launch_th<256, 5>(p, tiles_n, st);
+        case 128: return launch_th<128, 10>(p, tiles_n, st);
+        case 64: return launch_th<64, 18>(p, tiles_n, st);
+        case 32: return launch_th<32, 18>(p, tiles_n, st);
+    }
+    set_error("bad bn %d", bn);
+    return 1;
 }
 
 // forward taps of a k x k conv with padding k/2 and stride s over the input parity maps
@@ -398,6 +482,10 @@ int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weig
     A2X_REQUIRE(!x->b16 || w->w16, "conv2d_fwd: split input needs bf16 weight planes");
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
     const int kk = s->ksize * s->ksize;
+    A2X_REQUIRE(!stats || (!scale && !shift && !relu), "conv2d_fwd: fused statistics are of the raw conv output");
+    if (s->ksize == 3 && s->stride == 1 && g_debug[7] != 1)
+        return run_halo(x, s->n, s->h, s->w, s->cin, s->cout, w, +1, y, scale, shift, relu, 0, stats,
+                        (cudaStream_t)stream);
     TgParams p{};
     p.tw_log2 = pick_tw_log2(ho, wo, TG_BM, 4, 7);
     const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
@@ -433,6 +521,9 @@ int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_w
     const int kk = s->ksize * s->ksize;
     const int n_class = s->stride == 1 ? 1 : 4;
     a2x_output out{dx, nullptr, 0, dx_cs};
+    if (s->ksize == 3 && s->stride == 1 && g_debug[7] != 1)
+        return run_halo(dy, s->n, s->h, s->w, s->cout, s->cin, w, -1, &out, nullptr, nullptr, 0, accumulate, nullptr,
+                        (cudaStream_t)stream);
     for (int cls = 0; cls < n_class; ++cls) {
         const int hp = cls >> 1, wp = cls & 1;
         const int step = s->stride;

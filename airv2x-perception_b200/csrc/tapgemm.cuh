@@ -70,8 +70,11 @@ struct TgSmem {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = TG_A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int STAT_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int NBAR = 2 * STAGES + 4;  // full/empty per stage + tmem_full[2] + tmem_empty[2]
+    static constexpr int STAT_OFF = BAR_OFF + NBAR * 8 + 16;
     static constexpr int TOTAL = STAT_OFF + 4 * 2 * BN * 4 + 1024;  // [4 warps][2][BN] stats + alignment slack
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                     : (2 * BN <= 256) ? 256 : 512;  // two accumulator buffers
 };
 
 // lane L ends up with the sum over the warp's 32 lanes of v[L] (31 shuffles); v is destroyed
@@ -89,6 +92,101 @@ __device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
     return v[0];
 }
 
+// Common epilogue arguments (tapgemm and its halo variant share the drain code)
+struct TgEpi {
+    SplitOut out;
+    long long osn, osh, osw;
+    int sub_c, sub_s;
+    long long sub_sh, sub_sw;
+    int ncols;
+    const float* scale;
+    const float* shift;
+    int relu, accumulate;
+    double* stats;
+    int stat_c;
+    int gh, gw;
+};
+
+// Drain one 128 x BN accumulator (TMEM buffer at `tacc`) for the tile at (img, h0, w0), column offset n0.
+// Called by the 4 epilogue warps (128 threads); `q` = warp % 4 selects the TMEM lane quadrant.
+template <int BN>
+__device__ __forceinline__ void tg_epilogue(const TgEpi& e, uint32_t tacc, int q, int lane, int et, int img, int h0,
+                                            int w0, int tw_log2, int n0, float* sstat) {
+    const int row = q * 32 + lane;
+    const int h = h0 + (row >> tw_log2);
+    const int w = w0 + (row & ((1 << tw_log2) - 1));
+    const bool valid = (h < e.gh) && (w < e.gw);
+    const long long obase = (long long)img * e.osn + (long long)h * e.osh + (long long)w * e.osw;
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+        const int c0 = n0 + j * 32;
+        if (c0 >= e.ncols) break;
+        float v[32];
+        tmem_ld_32x32(tacc + (uint32_t(q * 32) << 16) + uint32_t(j * 32), v);
+        tmem_ld_wait();
+        const int sub = c0 / e.sub_c;
+        const int cc = c0 - sub * e.sub_c;
+        if (e.scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= __ldg(e.scale + cc + i);
+        }
+        if (e.shift != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __ldg(e.shift + cc + i);
+        }
+        if (valid && e.relu != 77) {  // relu == 77: debug switch, skip the stores (epilogue cost experiment)
+            const long long off =
+                obase + (long long)(sub / e.sub_s) * e.sub_sh + (long long)(sub % e.sub_s) * e.sub_sw + cc;
+            if (e.accumulate) {
+                const float4* o4 = reinterpret_cast<const float4*>(e.out.hi + off);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 prev = o4[i];
+                    v[4 * i] += prev.x;
+                    v[4 * i + 1] += prev.y;
+                    v[4 * i + 2] += prev.z;
+                    v[4 * i + 3] += prev.w;
+                }
+            }
+            if (e.relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                store_split4(e.out, off + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        }
+        if (e.stats != nullptr) {  // warp-uniform
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                v[i] = valid ? v[i] : 0.f;
+                sq[i] = v[i] * v[i];
+            }
+            const float s1 = warp_transpose_sum(v, lane);
+            const float s2 = warp_transpose_sum(sq, lane);
+            sstat[(q * 2 + 0) * BN + j * 32 + lane] = s1;  // each (warp, column) written exactly once:
+            sstat[(q * 2 + 1) * BN + j * 32 + lane] = s2;  // fixed-order combine below => deterministic
+        }
+    }
+    if (e.stats != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < BN; i += 128) {
+            const int col = n0 + i;
+            if (col < e.ncols) {
+                const int ch = col % e.sub_c;
+                const float t1 = (sstat[i] + sstat[2 * BN + i]) + (sstat[4 * BN + i] + sstat[6 * BN + i]);
+                const float t2 = (sstat[BN + i] + sstat[3 * BN + i]) + (sstat[5 * BN + i] + sstat[7 * BN + i]);
+                atomicAdd(&e.stats[ch], (double)t1);
+                atomicAdd(&e.stats[e.stat_c + ch], (double)t2);
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // sstat is reused by the next tile
+    }
+}
+
+// Persistent: gridDim.x CTAs loop over (pixel tile, column tile) pairs; the smem ring runs across tiles and the
+// TMEM accumulator is double buffered, so the epilogue of tile i overlaps the MMAs of tile i + 1.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ TgParams p) {
     using L = TgSmem<BN, STAGES>;
@@ -96,35 +194,31 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-    float* sstat = reinterpret_cast<float*>(smem + L::STAT_OFF);  // [4 warps][2][BN] per-tile channel sums
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* sstat = reinterpret_cast<float*>(smem + L::STAT_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tw_i = t % p.tiles_w;
-    t /= p.tiles_w;
-    const int th_i = t % p.tiles_h;
-    const int img = t / p.tiles_h;
     const int TW = 1 << p.tw_log2;
     const int TH = TG_BM >> p.tw_log2;
-    const int h0 = th_i * TH, w0 = tw_i * TW;
-    const int n0 = blockIdx.y * BN;
+    const int tiles_m = p.n_img * p.tiles_h * p.tiles_w;
+    const int tiles_n = (p.ncols + BN - 1) / BN;
+    const int n_tiles = tiles_m * tiles_n;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 4);  // one arrival per epilogue warp
+        }
         fence_mbar_init();
     }
-    if (warp == 1) {
-        tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
-    }
+    if (warp == 1) tmem_alloc<L::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -136,22 +230,31 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
             tma_prefetch_desc(&p.amap[0]);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-                const TgTap tp = p.taps[tap];
-                const CUtensorMap* am = &p.amap[tp.map];
-                const CUtensorMap* bm = tp.kind ? &p.bmap16 : &p.bmap;
-                const int nk = tp.kind ? p.kchunks16 : p.kchunks32;
-                const int kw = tp.kind ? 64 : 32;  // channels per 128-byte row
-                for (int kc = 0; kc < nk; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                    uint8_t* sb = sa + TG_A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    tma_load_5d(sa, am, &full_bar[stage], kc * kw, w0 + tp.dw, tp.dx, h0 + tp.dh, img);
-                    tma_load_3d(sb, bm, &full_bar[stage], kc * kw, n0, tp.btap);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int t = tile % tiles_m;
+                const int n0 = (tile / tiles_m) * BN;
+                const int tw_i = t % p.tiles_w;
+                t /= p.tiles_w;
+                const int th_i = t % p.tiles_h;
+                const int img = t / p.tiles_h;
+                const int h0 = th_i * TH, w0 = tw_i * TW;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const TgTap tp = p.taps[tap];
+                    const CUtensorMap* am = &p.amap[tp.map];
+                    const CUtensorMap* bm = tp.kind ? &p.bmap16 : &p.bmap;
+                    const int nk = tp.kind ? p.kchunks16 : p.kchunks32;
+                    const int kw = tp.kind ? 64 : 32;  // channels per 128-byte row
+                    for (int kc = 0; kc < nk; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                        uint8_t* sb = sa + TG_A_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                        tma_load_5d(sa, am, &full_bar[stage], kc * kw, w0 + tp.dw, tp.dx, h0 + tp.dh, img);
+                        tma_load_3d(sb, bm, &full_bar[stage], kc * kw, n0, tp.btap);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
             }
@@ -160,117 +263,78 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
         if (elect_one()) {
             constexpr uint32_t idesc32 = make_idesc_tf32(TG_BM, BN, 0, 0);
             constexpr uint32_t idesc16 = make_idesc_bf16(TG_BM, BN, 0, 0);
+            constexpr uint32_t dhi = desc_hi_word(1024, 2);  // K-major SW128: SBO = 1024, layout 2
+            const uint32_t a_lo0 = desc_lo_word(smem_u32(smem), 16);
+            const uint32_t b_lo0 = desc_lo_word(smem_u32(smem) + TG_A_BYTES, 16);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t first = 1;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-                const int kind = p.taps[tap].kind;
-                const int nk = kind ? p.kchunks16 : p.kchunks32;
-                for (int kc = 0; kc < nk; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint32_t sb = sa + TG_A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte row (8 tf32 or 16 bf16)
-                        const uint64_t ad = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                        const uint64_t bd = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        const uint32_t acc = (first && k == 0) ? 0u : 1u;
-                        if (kind) umma_bf16(tmem_base, ad, bd, idesc16, acc);
-                        else umma_tf32(tmem_base, ad, bd, idesc32, acc);
-                    }
-                    first = 0;
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+            uint32_t slo = 0;  // (stage * STAGE_BYTES) >> 4, carried incrementally
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t tacc = tmem_base + buf * BN;
+                mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);  // epilogue drained this buffer
+                tc_fence_after();
+                uint32_t acc = 0;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const int kind = p.taps[tap].kind;
+                    const int nk = kind ? p.kchunks16 : p.kchunks32;
+                    for (int kc = 0; kc < nk; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t alo = a_lo0 + slo, blo = b_lo0 + slo;
+                        if (kind) {
+                            umma_bf16_lh(tacc, alo, dhi, blo, dhi, idesc16, acc);
+                            umma_bf16_lh(tacc, alo + 2, dhi, blo + 2, dhi, idesc16, 1);
+                            umma_bf16_lh(tacc, alo + 4, dhi, blo + 4, dhi, idesc16, 1);
+                            umma_bf16_lh(tacc, alo + 6, dhi, blo + 6, dhi, idesc16, 1);
+                        } else {
+                            umma_tf32_lh(tacc, alo, dhi, blo, dhi, idesc32, acc);
+                            umma_tf32_lh(tacc, alo + 2, dhi, blo + 2, dhi, idesc32, 1);
+                            umma_tf32_lh(tacc, alo + 4, dhi, blo + 4, dhi, idesc32, 1);
+                            umma_tf32_lh(tacc, alo + 6, dhi, blo + 6, dhi, idesc32, 1);
+                        }
+                        acc = 1;
+                        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                        slo += L::STAGE_BYTES >> 4;
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                            slo = 0;
+                        }
                     }
                 }
+                umma_commit(&tmem_full[buf]);
             }
-            umma_commit(accum_bar);
         }
     } else {
         // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
         const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int h = h0 + (row >> p.tw_log2);
-        const int w = w0 + (row & (TW - 1));
-        const bool valid = (h < p.gh) && (w < p.gw);
-        const long long obase = (long long)img * p.osn + (long long)h * p.osh + (long long)w * p.osw;
-        const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
-            const int c0 = n0 + j * 32;
-            if (c0 >= p.ncols) break;
-            float v[32];
-            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(j * 32), v);
-            tmem_ld_wait();
-            const int sub = c0 / p.sub_c;
-            const int cc = c0 - sub * p.sub_c;
-            if (p.scale != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= __ldg(p.scale + cc + i);
-            }
-            if (p.shift != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(p.shift + cc + i);
-            }
-            if (valid) {
-                const long long off =
-                    obase + (long long)(sub / p.sub_s) * p.sub_sh + (long long)(sub % p.sub_s) * p.sub_sw + cc;
-                if (p.accumulate) {
-                    const float4* o4 = reinterpret_cast<const float4*>(p.out.hi + off);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 prev = o4[i];
-                        v[4 * i] += prev.x;
-                        v[4 * i + 1] += prev.y;
-                        v[4 * i + 2] += prev.z;
-                        v[4 * i + 3] += prev.w;
-                    }
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    store_split4(p.out, off + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-            }
-            if (p.stats != nullptr) {  // warp-uniform
-                float sq[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = valid ? v[i] : 0.f;
-                    sq[i] = v[i] * v[i];
-                }
-                const float s1 = warp_transpose_sum(v, lane);
-                const float s2 = warp_transpose_sum(sq, lane);
-                sstat[(q * 2 + 0) * BN + j * 32 + lane] = s1;  // each (warp, column) written exactly once:
-                sstat[(q * 2 + 1) * BN + j * 32 + lane] = s2;  // fixed-order combine below => deterministic
-            }
-        }
-        if (p.stats != nullptr) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = et; i < BN; i += 128) {
-                const int col = n0 + i;
-                if (col < p.ncols) {
-                    const int ch = col % p.sub_c;
-                    const float t1 = (sstat[i] + sstat[2 * BN + i]) + (sstat[4 * BN + i] + sstat[6 * BN + i]);
-                    const float t2 = (sstat[BN + i] + sstat[3 * BN + i]) + (sstat[5 * BN + i] + sstat[7 * BN + i]);
-                    atomicAdd(&p.stats[ch], (double)t1);
-                    atomicAdd(&p.stats[p.stat_c + ch], (double)t2);
-                }
-            }
+        const int et = threadIdx.x - 64;
+        TgEpi e;
+        e.out = p.out; e.osn = p.osn; e.osh = p.osh; e.osw = p.osw; e.sub_c = p.sub_c; e.sub_s = p.sub_s;
+        e.sub_sh = p.sub_sh; e.sub_sw = p.sub_sw; e.ncols = p.ncols; e.scale = p.scale; e.shift = p.shift;
+        e.relu = p.relu; e.accumulate = p.accumulate; e.stats = p.stats; e.stat_c = p.stat_c; e.gh = p.gh; e.gw = p.gw;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            int t = tile % tiles_m;
+            const int n0 = (tile / tiles_m) * BN;
+            const int tw_i = t % p.tiles_w;
+            t /= p.tiles_w;
+            const int th_i = t % p.tiles_h;
+            const int img = t / p.tiles_h;
+            const int buf = it & 1;
+            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            tg_epilogue<BN>(e, tmem_base + buf * BN, q, lane, et, img, th_i * TH, tw_i * TW, p.tw_log2, n0, sstat);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
-        tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
-    }
+    if (warp == 1) tmem_dealloc<L::TMEM_COLS>(tmem_base);
 }
 
 }  // namespace a2x

@@ -150,41 +150,49 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgPa
         if (elect_one()) {
             constexpr uint32_t idesc32 = make_idesc_tf32(128, BN, 1, 1);
             constexpr uint32_t idesc16 = make_idesc_bf16(128, BN, 1, 1);
+            // loop-invariant descriptor words (MN-major): tf32 atoms use the 32-byte-atomicity swizzle (layout 1,
+            // SBO 512), bf16 atoms the plain 128B swizzle (layout 2, SBO 1024); LBO = atom size for both
+            const uint32_t hi32 = desc_hi_word(p.sbo_bytes, p.layout);
+            constexpr uint32_t hi16 = desc_hi_word(1024, 2);
+            const uint32_t lo0 = desc_lo_word(smem_u32(smem), p.lbo_bytes);
+            const uint32_t lo16 = desc_lo_word(smem_u32(smem), WG_ATOM_BYTES);
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t slo = 0;  // (stage * STAGE_BYTES) >> 4
+            uint32_t acc = 0;
             for (int it = 0; it < ntiles; ++it) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + stage * L::STAGE_BYTES);
 #pragma unroll
                 for (int k = 0; k < WG_PIX / 8; ++k) {  // tf32: K = 8 pixel rows per MMA (two 4-row swizzle groups)
-                    const uint64_t ad = make_smem_desc_sw128(st + k * 1024, p.lbo_bytes, p.sbo_bytes, p.layout);
+                    const uint32_t alo = lo0 + slo + k * (1024 >> 4);
 #pragma unroll
                     for (int tt = 0; tt < TPC; ++tt) {
-                        const uint64_t bd = make_smem_desc_sw128(st + L::OFF_B32 + tt * (BN / 32) * WG_ATOM_BYTES + k * 1024,
-                                                                 p.lbo_bytes, p.sbo_bytes, p.layout);
-                        umma_tf32(tmem_base + tt * BN, ad, bd, idesc32, (it | k) != 0);
+                        const uint32_t blo = lo0 + slo + ((L::OFF_B32 + tt * (BN / 32) * WG_ATOM_BYTES + k * 1024) >> 4);
+                        umma_tf32_lh(tmem_base + tt * BN, alo, hi32, blo, hi32, idesc32, k == 0 ? acc : 1u);
                     }
                 }
                 if (SPLIT) {
 #pragma unroll
                     for (int k = 0; k < WG_PIX / 16; ++k) {  // bf16: K = 16 pixel rows per MMA (two 8-row groups)
-                        const uint64_t ah = make_smem_desc_sw128(st + L::OFF_A16 + k * 2048, WG_ATOM_BYTES, 1024, 2);
-                        const uint64_t al = make_smem_desc_sw128(st + L::OFF_A16 + L::A16 + k * 2048, WG_ATOM_BYTES, 1024, 2);
+                        const uint32_t ah = lo16 + slo + ((L::OFF_A16 + k * 2048) >> 4);
+                        const uint32_t al = ah + (L::A16 >> 4);
 #pragma unroll
                         for (int tt = 0; tt < TPC; ++tt) {
-                            const uint32_t bo = L::OFF_B16 + tt * (BN / 64) * WG_ATOM_BYTES + k * 2048;
-                            const uint64_t bh = make_smem_desc_sw128(st + bo, WG_ATOM_BYTES, 1024, 2);
-                            const uint64_t bl = make_smem_desc_sw128(st + bo + L::B16, WG_ATOM_BYTES, 1024, 2);
-                            umma_bf16(tmem_base + tt * BN, al, bh, idesc16, 1);  // A_lo * B_hi
-                            umma_bf16(tmem_base + tt * BN, ah, bl, idesc16, 1);  // A_hi * B_lo
+                            const uint32_t bh = lo16 + slo + ((L::OFF_B16 + tt * (BN / 64) * WG_ATOM_BYTES + k * 2048) >> 4);
+                            const uint32_t bl = bh + (L::B16 >> 4);
+                            umma_bf16_lh(tmem_base + tt * BN, al, hi16, bh, hi16, idesc16, 1);  // A_lo * B_hi
+                            umma_bf16_lh(tmem_base + tt * BN, ah, hi16, bl, hi16, idesc16, 1);  // A_hi * B_lo
                         }
                     }
                 }
+                acc = 1;
                 umma_commit(&empty_bar[stage]);
+                slo += L::STAGE_BYTES >> 4;
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
+                    slo = 0;
                 }
             }
             umma_commit(accum_bar);

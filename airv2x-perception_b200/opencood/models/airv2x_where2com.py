@@ -157,7 +157,24 @@ class Airv2xWhere2com(nn.Module):
         return d
 
     def _layout(self, data_dict, device):
-        """Scene-major agent order (vehicles, RSUs, drones per scene): airv2x_base_model.py:179-248."""
+        """Scene-major agent order (vehicles, RSUs, drones per scene): airv2x_base_model.py:179-248.
+        Cached per (record_len, batch_idxs) signature so steady-state steps create no new device tensors."""
+        raw0 = data_dict.get("raw_points")
+        key = []
+        for t in AGENT_TYPES:
+            d = data_dict.get(t)
+            if d is None:
+                continue
+            r = d["record_len"]
+            key.append((t, tuple(int(v) for v in (r.tolist() if torch.is_tensor(r) else r)), tuple(d["batch_idxs"]),
+                        raw0 is not None or d.get("batch_merged_lidar_features_torch") is not None))
+        key = (tuple(key), str(device))
+        cache = self.__dict__.setdefault("_layout_cache", {})
+        if key not in cache:
+            cache[key] = self._build_layout(data_dict, device)
+        return cache[key]
+
+    def _build_layout(self, data_dict, device):
         rl, idxs = {}, {}
         raw = data_dict.get("raw_points")
         for t in AGENT_TYPES:
@@ -280,6 +297,63 @@ class Airv2xWhere2com(nn.Module):
         self.engine.backward(P, dheads, self._grad_buffers())
         self._last_layout = layout
         return loss3
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the fused step
+    def train_step_graphed(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0):
+        """train_step() captured once into a CUDA graph (raw-point input only): per step the host copies the clouds /
+        labels into static buffers (pinned -> device), draws the top-K sizes and replays ~360 kernel launches with one
+        cudaGraphLaunch. Falls back to capture again when the agent layout or the cloud capacity changes."""
+        assert self.training and data_dict.get("raw_points") is not None, "graphed step needs raw_points input"
+        import random as _random
+
+        dev = next(self.parameters()).device
+        raw = data_dict["raw_points"]
+        layout = self._layout(data_dict, dev)
+        P = int(raw["points"].shape[0])
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = (id(layout), float(cls_weight), float(reg_coe))
+        st = graphs.get(key)
+        if st is None or st["cap"] < P:
+            st = self._capture(data_dict, label_dict, cls_weight, reg_coe, layout, dev, max(P, int(P * 1.1)))
+            graphs[key] = st
+        st["points"][:P].copy_(raw["points"], non_blocking=True)
+        st["offsets"].copy_(raw["offsets"], non_blocking=True)
+        for k in ("targets", "pos_equal_one", "class_ids"):
+            st["labels"][k].copy_(label_dict[k].reshape(st["labels"][k].shape), non_blocking=True)
+        eng = self.engine
+        if not eng.fully:
+            hw = st["hw"]
+            eng.set_k([int(hw * _random.uniform(0, 1)) for _ in layout["record_len"]], layout["record_len"])
+        st["graph"].replay()
+        self._last_aux = st["aux"]
+        return st["loss3"]
+
+    def _capture(self, data_dict, label_dict, cw, rc, layout, dev, cap):
+        raw = data_dict["raw_points"]
+        P = int(raw["points"].shape[0])
+        pts = torch.zeros(cap, 4, device=dev)
+        pts[:P].copy_(raw["points"])
+        offs = raw["offsets"].to(device=dev, dtype=torch.int32).clone()
+        labels = {k: v.clone() for k, v in self.prepare_labels(label_dict, dev).items()}
+        dd = {k: v for k, v in data_dict.items() if k != "raw_points"}
+        dd["raw_points"] = dict(raw)
+        dd["raw_points"]["points"] = pts
+        dd["raw_points"]["offsets"] = offs
+        rng_state = random.getstate()  # warm-up / capture must not consume the caller's top-K random stream
+        for _ in range(2):  # eager warm-up: every buffer / stream / attribute exists before capture
+            self.train_step(dd, labels, cw, rc)
+        torch.cuda.synchronize()
+        from ... import _lib
+
+        lib = _lib.load()
+        g = torch.cuda.CUDAGraph()
+        l0 = lib.a2x_launch_count()
+        with torch.cuda.graph(g):
+            loss3 = self.train_step(dd, labels, cw, rc)
+        self.launches_per_step = int(lib.a2x_launch_count() - l0)  # kernels of this library inside one replay
+        random.setstate(rng_state)
+        return dict(graph=g, points=pts, offsets=offs, labels=labels, loss3=loss3, aux=self._last_aux, cap=cap,
+                    hw=self._last_aux["hw"])
 
     def _output_dict(self, heads, layout):
         A, K = self.args["anchor_number"], self.args["num_class"]

@@ -347,11 +347,7 @@ class W2CEngine:
                 # K per scene from Python's `random` exactly like the reference (where2comm_fuse.py:106)
                 if k_list is None:
                     k_list = [int(hw * random.uniform(0, 1)) for _ in range(B)]
-                k_host = self._pinned("k_host", (N,), torch.int32)
-                pos = 0
-                for b, n in enumerate(record_len):
-                    k_host[pos:pos + n] = k_list[b]
-                    pos += n
+                k_host = self.set_k(k_list, record_len)
                 k_dev = self._buf("k_dev", (N,), torch.int32)
                 k_dev.copy_(k_host, non_blocking=True)
                 ops.comm_smooth_mask(conf, gw, gb, ksz, N, h2, w2, thr, False, smooth, mask)
@@ -387,6 +383,15 @@ class W2CEngine:
                               heads=heads, layout=layout, canvas=canvas)
         aux = dict(comm_rate=nz, ones=ones, hw=hw)
         return heads, aux
+
+    def set_k(self, k_list, record_len):
+        """write the per-scene top-K sizes into the pinned staging buffer the (possibly graph-captured) H2D copy reads"""
+        k_host = self._pinned("k_host", (sum(record_len),), torch.int32)
+        pos = 0
+        for b, n in enumerate(record_len):
+            k_host[pos:pos + n] = int(k_list[b])
+            pos += n
+        return k_host
 
     def _pinned(self, name, shape, dtype):
         key = ("pinned", name, tuple(shape), dtype)

@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     cfg = load_config()
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +198,8 @@ def main():
     metric = "scenes/sec (fwd+bwd) Where2Comm 5-agent 60k-pt"
     config = {"workload": "airv2x_intermediate_where2com.yaml: 5 agents (2 veh, 2 rsu, 1 drone) x 60k pts, 200x704 BEV, "
                           "1 scene per GPU, train-mode fwd + PointPillarLossMultiClass + bwd",
-              "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+              "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
+              "launch": "eager" if "--no-graph" in sys.argv else "cuda-graph replay of the fused step"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -243,8 +245,10 @@ def main():
     # data-parallel over scenes (the reference's DDP, tools/train.py:161-163): average parameter gradients
     allreduce_grads = a2x_import.pkg("dist").GradAverager(model.parameters())
 
+    step_fn = model.train_step if args.no_graph else model.train_step_graphed
+
     def step(dd, lab):
-        loss3 = model.train_step(dd, lab, cw, rc)
+        loss3 = step_fn(dd, lab, cw, rc)
         allreduce_grads()
         return loss3
 
@@ -278,6 +282,8 @@ def main():
     with ClockSampler(local_rank) as clk:
         ms, loss3 = timed(dd_dev, lab_dev, args.steps, False)
     launches = lib.a2x_launch_count() - l0
+    if not args.no_graph:  # replays do not pass through the C launchers: count = kernels captured per step x steps
+        launches = model.launches_per_step * args.steps
     # end-to-end: host pinned clouds + labels -> H2D, loss -> D2H, every step
     if args.no_e2e:
         ms_e2e, loss_val = ms, float(loss3.sum().item())

@@ -110,6 +110,46 @@ def test_train_step_matches_reference_golden(small):
     assert max(errs.values()) < 0.15 and float(np.median(list(errs.values()))) < 0.03, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
 
 
+def test_graphed_step_matches_eager(small):
+    """CUDA-graph replay of the fused step == eager launches (same loss, same gradients), across changing inputs"""
+    import a2x_import
+
+    cfg, gold, _, sd, _ = small
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    rng = cfg["preprocess"]["cav_lidar_range"]
+    agents = [str(a) for a in gold["agents"]]
+
+    def scene(seed, npts):
+        clouds = [O.synth_points(seed * 100 + k, npts, rng, (10.0, 5.0)) for k in range(len(agents))]
+        offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+        raw = {"raw_points": {"points": torch.from_numpy(np.concatenate(clouds, 0)).cuda(),
+                              "offsets": torch.from_numpy(offs).cuda(), "preprocess": cfg["preprocess"], "filter": True}}
+        for t in O.AGENT_TYPES:
+            n = sum(1 for a in agents if a == t)
+            raw[t] = {"record_len": [n], "batch_idxs": [0] if n else []}
+        return raw
+
+    H, W = gold["train_psm"].shape[2:]
+    models = []
+    for _ in range(2):
+        m = M.Airv2xWhere2com(cfg["model_args"])
+        m.load_state_dict(sd)
+        models.append(m.cuda().train())
+    eager, graphed = models
+    for step, (seed, npts) in enumerate([(3, 6000), (4, 6000), (5, 5500)]):   # last: fewer points than the capacity
+        labels = O.make_labels(20 + step, 1, H, W, cfg["model_args"]["anchor_number"])
+        dd = scene(seed, npts)
+        random.seed(100 + step)
+        l_e = eager.train_step(dd, labels, 1.0, 2.0).clone()
+        random.seed(100 + step)
+        l_g = graphed.train_step_graphed(dd, labels, 1.0, 2.0).clone()
+        assert torch.allclose(l_e, l_g, rtol=1e-6, atol=1e-9), (step, l_e, l_g)
+        for (n, pe), (_, pg) in zip(eager.named_parameters(), graphed.named_parameters()):
+            if pe.grad is not None:
+                assert torch.allclose(pe.grad, pg.grad, rtol=1e-4, atol=1e-6 * float(pe.grad.abs().max()) + 1e-12), (step, n)
+    assert graphed.launches_per_step > 300
+
+
 def test_baseline_size_properties():
     """BASELINE config 1 (5 agents x 60k points, 200 x 704): determinism, invariance of the fused output to the order
     of the NON-ego agents of one type, and the documented output contract."""
