@@ -206,21 +206,26 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
            ((M >> 4) << 24);
 }
 
-// ---------------------------------------------------------------- 3-term operand split
-// v  ~=  hi + lo,  hi = tf32_rn(v) kept in fp32,  (h16, l16) = (bf16(hi), bf16(v - hi)).
-// A GEMM  sum a*b  is evaluated as  hi_a*hi_b [tf32]  +  l16_a*h16_b [bf16]  +  h16_a*l16_b [bf16]: the dropped
-// lo*lo term and the bf16 roundings of the two correction products are each <= 2^-20 relative.
+// ---------------------------------------------------------------- 3-term operand split (bf16 x 3)
+// v ~= h + l with (h16, l16) = (bf16(v), bf16(v - h16)); the fp32 plane keeps v itself for the consumers that are not
+// GEMMs (BN backward, ReLU masks, fusion). A GEMM  sum a*b  is evaluated as  h_a*h_b + l_a*h_b + h_a*l_b, three
+// kind::f16 (bf16) MMAs into one fp32 TMEM accumulator: every product is exact in fp32, the dropped l*l term and the
+// second-level residuals are each <= 2^-17 relative (eval logits within 1e-4 of the fp32 reference).
 struct SplitOut {
-    float* hi;            // fp32 plane (may be the only one)
+    float* hi;            // fp32 plane: the full value (may be the only plane)
     __nv_bfloat16* b16;   // null = single-plane mode; else plane 0 = h16, plane 1 = l16 (plane stride `ps` elements)
     long long ps;
 };
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
+    h = __float2bfloat16_rn(v);
+    l = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 __device__ __forceinline__ void store_split4(const SplitOut& o, long long off, float4 v) {
+    *reinterpret_cast<float4*>(o.hi + off) = v;
     if (o.b16 != nullptr) {
-        const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-        *reinterpret_cast<float4*>(o.hi + off) = h;
-        __nv_bfloat162 h01 = __floats2bfloat162_rn(h.x, h.y), h23 = __floats2bfloat162_rn(h.z, h.w);
-        __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - h.x, v.y - h.y), l23 = __floats2bfloat162_rn(v.z - h.z, v.w - h.w);
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
         uint2 hp, lp;
         hp.x = *reinterpret_cast<uint32_t*>(&h01);
         hp.y = *reinterpret_cast<uint32_t*>(&h23);
@@ -228,8 +233,6 @@ __device__ __forceinline__ void store_split4(const SplitOut& o, long long off, f
         lp.y = *reinterpret_cast<uint32_t*>(&l23);
         *reinterpret_cast<uint2*>(o.b16 + off) = hp;
         *reinterpret_cast<uint2*>(o.b16 + o.ps + off) = lp;
-    } else {
-        *reinterpret_cast<float4*>(o.hi + off) = v;
     }
 }
 

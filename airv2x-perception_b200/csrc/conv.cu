@@ -185,24 +185,31 @@ static int run_halo(const a2x_operand* a, int n, int h, int w, int k_ch, int nco
                     const a2x_output* y, const float* scale, const float* shift, int relu, int accumulate,
                     double* stats, cudaStream_t st) {
     ThParams p{};
-    if (int r = make_halo_map(&p.amap[0], a->hi, n, h, w, k_ch, a->cs, 0)) return r;
     const int bn = bn_for(ncols);
-    if (int r = make_w_map(&p.bmap, wts->w32, 9, ncols, k_ch, bn)) return r;
-    p.npass = 1;
     if (a->b16) {
+        // two A passes: h16 against the 18 weight taps (h16 then l16 planes), l16 against the 9 h16 taps
         const __nv_bfloat16* b = (const __nv_bfloat16*)a->b16;
+        if (int r = make_halo_map(&p.amap[0], b, n, h, w, k_ch, a->cs, 1)) return r;                // h16
         if (int r = make_halo_map(&p.amap[1], b + a->b16_plane, n, h, w, k_ch, a->cs, 1)) return r;  // l16
-        if (int r = make_halo_map(&p.amap[2], b, n, h, w, k_ch, a->cs, 1)) return r;                // h16
-        if (int r = make_w_map(&p.bmap16, wts->w16, 18, ncols, k_ch, bn, 1)) return r;
-        p.npass = 3;
+        if (int r = make_w_map(&p.bmap, wts->w16, 18, ncols, k_ch, bn, 1)) return r;
+        p.npass = 2;
+        p.pass_taps[0] = 18;
+        p.pass_taps[1] = 9;
+        p.kind = 1;
+        p.kchunks = k_ch / 64;
+    } else {
+        if (int r = make_halo_map(&p.amap[0], a->hi, n, h, w, k_ch, a->cs, 0)) return r;
+        if (int r = make_w_map(&p.bmap, wts->w32, 9, ncols, k_ch, bn)) return r;
+        p.npass = 1;
+        p.pass_taps[0] = 9;
+        p.kind = 0;
+        p.kchunks = k_ch / 32;
     }
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) {
             p.dh[r * 3 + c] = (int8_t)(sign * (r - 1));
             p.dw[r * 3 + c] = (int8_t)(sign * (c - 1));
         }
-    p.kchunks32 = k_ch / 32;
-    p.kchunks16 = k_ch / 64;
     p.n_img = n;
     p.gh = h;
     p.gw = w;
@@ -282,17 +289,16 @@ static int build_fwd_maps(const a2x_conv_shape* s, const a2x_operand* x, CUtenso
     return 0;
 }
 
-// split mode: D = A_hi*B_hi [tf32] + A_l16*B_h16 [bf16] + A_h16*B_l16 [bf16]. Base taps reference fp32 maps
-// [0, nmaps) and weight taps [0, ntaps_w); h16 views live at map + nmaps, l16 views at map + 2 nmaps; bf16 weights
-// carry the h16 taps first, then the l16 taps (+ ntaps_w).
+// split mode: D = A_h*B_h + A_l*B_h + A_h*B_l, all kind::f16 (bf16). Base taps reference fp32 maps [0, nmaps) and
+// weight taps [0, ntaps_w); h16 views live at map + nmaps, l16 views at map + 2 nmaps; the bf16 weight tensor carries
+// the h16 taps first, then the l16 taps (+ ntaps_w).
 static int expand_split_taps(TgTap* taps, int ntaps, int nmaps, int ntaps_w) {
     for (int i = ntaps - 1; i >= 0; --i) {
         const TgTap t = taps[i];
         TgTap a = t, b = t, c = t;
-        a.kind = 0;
-        b.kind = 1;
+        a.kind = b.kind = c.kind = 1;
+        a.map = (int16_t)(t.map + nmaps);      // A h16 x W h16
         b.map = (int16_t)(t.map + 2 * nmaps);  // A l16 x W h16
-        c.kind = 1;
         c.map = (int16_t)(t.map + nmaps);      // A h16 x W l16
         c.btap = t.btap + ntaps_w;
         taps[3 * i] = a;
@@ -327,21 +333,26 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream
     p.sbo_bytes = g_debug[3] > 0 ? (uint32_t)g_debug[3] : 512u;
     p.layout = g_debug[5] > 0 ? (uint32_t)g_debug[5] : 1u;
     const int bn = p.cb >= 128 ? 128 : (p.cb >= 64 ? 64 : 32);
-    const int tpc = (!split && p.ntaps % 3 == 0) ? 3 : 1;
+    const int tpc = (p.ntaps % 3 == 0 && bn <= 128) ? 3 : 1;
     p.n_tiles_b = (p.cb + bn - 1) / bn;
     const int tiles_a = (p.ca + 127) / 128;
     const int tap_groups = p.ntaps / tpc;
     const int total_tiles = n_img * p.tiles_h * p.tiles_w;
     const int sms = 148;
     const int blocks_mn = tiles_a * p.n_tiles_b * tap_groups;
-    int ksplit = (2 * sms + blocks_mn - 1) / blocks_mn;
+    int ksplit = (tpc * bn > 256) ? sms / blocks_mn : (2 * sms + blocks_mn - 1) / blocks_mn;  // 512 TMEM columns => 1 CTA / SM
     if (ksplit > total_tiles) ksplit = total_tiles;
     if (ksplit < 1) ksplit = 1;
     p.tiles_per_cta = (total_tiles + ksplit - 1) / ksplit;
     ksplit = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
     if (split) {
-        if (bn == 128) return launch_wg<128, 1, 3, true>(p, ksplit, tiles_a, tap_groups, st);
-        if (bn == 64) return launch_wg<64, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
+        if (tpc == 3) {
+            if (bn == 128) return launch_wg<128, 3, 3, true>(p, ksplit, tiles_a, tap_groups, st);
+            if (bn == 64) return launch_wg<64, 3, 4, true>(p, ksplit, tiles_a, tap_groups, st);
+        } else {
+            if (bn == 128) return launch_wg<128, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
+            if (bn == 64) return launch_wg<64, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
+        }
         set_error("split wgrad needs cb >= 64");
         return 1;
     }
@@ -355,14 +366,61 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream
     return launch_wg<32, 1, 4, false>(p, ksplit, tiles_a, tap_groups, st);
 }
 
+template <int BN, int STAGES>
+static int launch_wr(const WrParams& p, int ksplit, int blocks_mn, cudaStream_t st) {
+    using L = WrSmem<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(wgrad_row_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            L::TOTAL));
+        configured = true;
+    }
+    dim3 grid(ksplit, blocks_mn, 3);
+    wgrad_row_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// 3x3 stride-1 weight gradient in split mode through the row-halo kernel
+static int run_wr(const a2x_conv_shape* s, const a2x_operand* x, const a2x_operand* dy, float* dw_packed, cudaStream_t st) {
+    WrParams p{};
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x->b16;
+    const __nv_bfloat16* db = (const __nv_bfloat16*)dy->b16;
+    for (int pl = 0; pl < 2; ++pl) {
+        if (int r = make_act_map(&p.amap16[pl], db + pl * dy->b16_plane, s->n, s->h, s->w, s->cout, dy->cs, 1, 0, 0,
+                                 WG_PIX, 1, 0, 1))
+            return r;
+        if (int r = make_act_map(&p.bmap16[pl], xb + pl * x->b16_plane, s->n, s->h, s->w, s->cin, x->cs, 1, 0, 0,
+                                 WR_B_ROWS, 1, 0, 1))
+            return r;
+    }
+    p.ca = s->cout;
+    p.cb = s->cin;
+    p.n_img = s->n;
+    p.gh = s->h;
+    p.tiles_w = (s->w + WG_PIX - 1) / WG_PIX;
+    p.dw = dw_packed;
+    const int bn = p.cb >= 128 ? 128 : 64;
+    p.n_tiles_b = (p.cb + bn - 1) / bn;
+    const int tiles_a = (p.ca + 127) / 128;
+    const int blocks_mn = tiles_a * p.n_tiles_b;
+    const int total_tiles = p.n_img * p.gh * p.tiles_w;
+    // BN = 128 allocates all 512 TMEM columns (one CTA per SM): a single wave of <= 148 CTAs; BN = 64 fits two per SM
+    int ksplit = (bn == 128 ? 148 : 296) / (blocks_mn * 3);
+    if (g_debug[10] > 0) ksplit = g_debug[10];
+    if (ksplit > total_tiles) ksplit = total_tiles;
+    if (ksplit < 1) ksplit = 1;
+    p.tiles_per_cta = (total_tiles + ksplit - 1) / ksplit;
+    ksplit = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    if (bn == 128) return launch_wr<128, 5>(p, ksplit, blocks_mn, st);
+    return launch_wr<64, 4>(p, ksplit, blocks_mn, st);
+}
+
 // ------------------------------------------------------------------ small re-layout kernels
 __device__ __forceinline__ void put_w(float* w32, __nv_bfloat16* w16, long long plane, long long j, float v) {
-    const float hi = tf32_rn(v);
-    if (w32) w32[j] = hi;
-    if (w16) {
-        w16[j] = __float2bfloat16_rn(hi);
-        w16[plane + j] = __float2bfloat16_rn(v - hi);
-    }
+    if (w32) w32[j] = tf32_rn(v);  // single-plane (kind::tf32) operand: pre-rounded, the MMA would truncate
+    if (w16) split_bf16(v, w16[j], w16[plane + j]);
 }
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, int cout, int cin, int kk, int cout_pad,
                                    float* __restrict__ wf, __nv_bfloat16* __restrict__ wf16, float* __restrict__ wd,
@@ -589,6 +647,8 @@ int a2x_conv2d_wgrad(const a2x_conv_shape* s, const a2x_operand* x, const a2x_op
     A2X_REQUIRE(dw_packed, "conv2d_wgrad: null output");
     const bool split = x->b16 && dy->b16;
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
+    if (split && s->ksize == 3 && s->stride == 1 && g_debug[7] != 1)
+        return run_wr(s, x, dy, dw_packed, (cudaStream_t)stream);
     WgParams p{};
     p.tw_log2 = pick_tw_log2(ho, wo, WG_PIX, 2, 5);
     const int TW = 1 << p.tw_log2, TH = WG_PIX >> p.tw_log2;

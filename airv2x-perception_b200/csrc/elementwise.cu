@@ -1,6 +1,6 @@
 // HBM-bound elementwise / per-channel-reduction kernels around the tensor-core contractions:
 // BatchNorm (train-mode batch statistics, eval-mode affine), ReLU, their backward passes, mask multiply,
-// operand splitting for 3xTF32. All tensors are fp32 NHWC with an explicit pixel stride.
+// operand splitting for the 3-pass bf16 GEMMs. All tensors are fp32 NHWC with an explicit pixel stride.
 //
 // Reference semantics: nn.BatchNorm2d(eps=1e-3, momentum=0.01) + nn.ReLU in
 // opencood/models/common_modules/base_bev_backbone.py:52-66, :82-90; bias+ReLU in downsample_conv.py:18-32.
@@ -18,22 +18,10 @@ static __host__ SplitOut to_split(const a2x_output* o) {
     return r;
 }
 
-// ---------------------------------------------------------------------------------------------- split / combine
+// ---------------------------------------------------------------------------------------------- split
 __global__ void split_kernel(const float* __restrict__ x, long long n4, SplitOut o) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
         store_split4(o, 4 * i, reinterpret_cast<const float4*>(x)[i]);
-}
-
-__global__ void combine_kernel(const float* __restrict__ a, const __nv_bfloat16* __restrict__ l16, long long n4,
-                               float* __restrict__ o) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 x = reinterpret_cast<const float4*>(a)[i];
-        const uint2 u = reinterpret_cast<const uint2*>(l16)[i];
-        const __nv_bfloat162 l01 = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-        const __nv_bfloat162 l23 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-        const float2 f01 = __bfloat1622float2(l01), f23 = __bfloat1622float2(l23);
-        reinterpret_cast<float4*>(o)[i] = make_float4(x.x + f01.x, x.y + f01.y, x.z + f23.x, x.w + f23.y);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------- channel stats
@@ -324,14 +312,6 @@ extern "C" {
 int a2x_split(const float* x, long long n, const a2x_output* out, a2x_stream_t stream) {
     A2X_REQUIRE(x && out && out->hi && out->b16 && n % 4 == 0, "split: bad args (n must be a multiple of 4)");
     split_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, n / 4, to_split(out));
-    A2X_LAUNCHED();
-    A2X_CHECK_CUDA(cudaGetLastError());
-    return 0;
-}
-
-int a2x_combine(const float* hi, const void* l16, long long n, float* out, a2x_stream_t stream) {
-    A2X_REQUIRE(hi && l16 && out && n % 4 == 0, "combine: bad args (n must be a multiple of 4)");
-    combine_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(hi, (const __nv_bfloat16*)l16, n / 4, out);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

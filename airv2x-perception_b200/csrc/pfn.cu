@@ -231,19 +231,13 @@ __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restric
         }
         const long long cell = ((long long)agent_map[agent] * g.ny + cy) * g.nx + cx;
         float* o = canvas.hi + cell * NC;
+        o[lane] = out0;
+        o[lane + 32] = out1;
         if (canvas.b16 != nullptr) {
-            const float h0 = tf32_rn(out0), h1 = tf32_rn(out1);
-            o[lane] = h0;
-            o[lane + 32] = h1;
             __nv_bfloat16* hb = canvas.b16 + cell * NC;
             __nv_bfloat16* lb = hb + canvas.ps;
-            hb[lane] = __float2bfloat16_rn(h0);
-            hb[lane + 32] = __float2bfloat16_rn(h1);
-            lb[lane] = __float2bfloat16_rn(out0 - h0);
-            lb[lane + 32] = __float2bfloat16_rn(out1 - h1);
-        } else {
-            o[lane] = out0;
-            o[lane + 32] = out1;
+            split_bf16(out0, hb[lane], lb[lane]);
+            split_bf16(out1, hb[lane + 32], lb[lane + 32]);
         }
         if (pillar_out != nullptr) {
             pillar_out[pil * NC + lane] = out0;

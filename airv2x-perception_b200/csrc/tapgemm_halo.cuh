@@ -16,12 +16,13 @@ constexpr int TH_A_SLOT = 23 * 1024;                    // 1024-aligned slot
 constexpr int TH_NA = 2;                                // A slots
 
 struct ThParams {
-    CUtensorMap amap[3];  // hi (fp32), l16, h16 (bf16) halo-box views, in pass order
-    CUtensorMap bmap;     // fp32 weights [9][cols][k]
-    CUtensorMap bmap16;   // bf16 weights [18][cols][k]
-    int npass;            // 1 (single plane) or 3 (split)
+    CUtensorMap amap[2];  // halo-box views in pass order: split = {h16, l16} (bf16); single plane = {fp32}
+    CUtensorMap bmap;     // weights: split = bf16 [18][cols][k] (9 h16 taps, then 9 l16 taps); single = fp32 [9][cols][k]
+    int npass;            // 1 (single plane) or 2 (split: A_h16 x 18 weight taps, A_l16 x the 9 h16 taps)
+    int pass_taps[2];     // weight taps per pass (tap t uses window offset t % 9)
+    int kind;             // 0 = tf32 (32 channels per 128-byte row), 1 = bf16 (64 channels)
+    int kchunks;          // K / (32 | 64)
     int8_t dh[9], dw[9];  // window offsets per tap (forward: r-1, c-1; data gradient: 1-r, 1-c)
-    int kchunks32, kchunks16;
     int n_img, gh, gw, tiles_h, tiles_w;
     SplitOut out;
     long long osn, osh, osw;
@@ -99,13 +100,10 @@ __global__ void __launch_bounds__(192) tapgemm_halo_kernel(const __grid_constant
                 const int th_i = t % p.tiles_h;
                 const int img = t / p.tiles_h;
                 const int h0 = th_i * 16, w0 = tw_i * 8;
+                const int kw = p.kind ? 64 : 32;
                 for (int pass = 0; pass < p.npass; ++pass) {
-                    const int kind = pass > 0;
-                    const int nk = kind ? p.kchunks16 : p.kchunks32;
-                    const int kw = kind ? 64 : 32;
-                    const CUtensorMap* bm = kind ? &p.bmap16 : &p.bmap;
-                    const int bt0 = pass == 2 ? 9 : 0;  // pass 1: A l16 x W h16; pass 2: A h16 x W l16
-                    for (int kc = 0; kc < nk; ++kc) {
+                    const int nt = p.pass_taps[pass];
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&a_empty[sa], pa ^ 1);
                         mbar_arrive_expect_tx(&a_full[sa], TH_A_BYTES);
                         tma_load_5d(smem + sa * TH_A_SLOT, &p.amap[pass], &a_full[sa], kc * kw, w0 - 1, 0, h0 - 1, img);
@@ -113,10 +111,10 @@ __global__ void __launch_bounds__(192) tapgemm_halo_kernel(const __grid_constant
                             sa = 0;
                             pa ^= 1;
                         }
-                        for (int tap = 0; tap < 9; ++tap) {
+                        for (int tap = 0; tap < nt; ++tap) {
                             mbar_wait(&b_empty[sb], pb ^ 1);
                             mbar_arrive_expect_tx(&b_full[sb], L::B_BYTES);
-                            tma_load_3d(smem + L::OFF_B + sb * L::B_BYTES, bm, &b_full[sb], kc * kw, n0, bt0 + tap);
+                            tma_load_3d(smem + L::OFF_B + sb * L::B_BYTES, &p.bmap, &b_full[sb], kc * kw, n0, tap);
                             if (++sb == NB) {
                                 sb = 0;
                                 pb ^= 1;
@@ -148,39 +146,41 @@ __global__ void __launch_bounds__(192) tapgemm_halo_kernel(const __grid_constant
                 mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 uint32_t acc = 0;
+                const int kind = p.kind;
                 for (int pass = 0; pass < p.npass; ++pass) {
-                    const int kind = pass > 0;
-                    const int nk = kind ? p.kchunks16 : p.kchunks32;
-                    for (int kc = 0; kc < nk; ++kc) {
+                    const int ngroups = p.pass_taps[pass] / 9;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&a_full[sa], pa);
                         tc_fence_after();
                         const uint32_t aslot = a_lo0 + sa * (TH_A_SLOT >> 4);
+                        for (int g = 0; g < ngroups; ++g) {
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            mbar_wait(&b_full[sb], pb);
-                            tc_fence_after();
-                            const uint32_t alo = aslot + a_tap[tap], blo = b_lo0 + sblo;
-                            if (kind) {
-                                umma_bf16_lh(tacc, alo, ahi, blo, bhi, idesc16, acc);
-                                umma_bf16_lh(tacc, alo + 2, ahi, blo + 2, bhi, idesc16, 1);
-                                umma_bf16_lh(tacc, alo + 4, ahi, blo + 4, bhi, idesc16, 1);
-                                umma_bf16_lh(tacc, alo + 6, ahi, blo + 6, bhi, idesc16, 1);
-                            } else {
-                                umma_tf32_lh(tacc, alo, ahi, blo, bhi, idesc32, acc);
-                                umma_tf32_lh(tacc, alo + 2, ahi, blo + 2, bhi, idesc32, 1);
-                                umma_tf32_lh(tacc, alo + 4, ahi, blo + 4, bhi, idesc32, 1);
-                                umma_tf32_lh(tacc, alo + 6, ahi, blo + 6, bhi, idesc32, 1);
-                            }
-                            acc = 1;
-                            umma_commit(&b_empty[sb]);
-                            sblo += L::B_BYTES >> 4;
-                            if (++sb == NB) {
-                                sb = 0;
-                                pb ^= 1;
-                                sblo = 0;
+                            for (int tap = 0; tap < 9; ++tap) {
+                                mbar_wait(&b_full[sb], pb);
+                                tc_fence_after();
+                                const uint32_t alo = aslot + a_tap[tap], blo = b_lo0 + sblo;
+                                if (kind) {
+                                    umma_bf16_lh(tacc, alo, ahi, blo, bhi, idesc16, acc);
+                                    umma_bf16_lh(tacc, alo + 2, ahi, blo + 2, bhi, idesc16, 1);
+                                    umma_bf16_lh(tacc, alo + 4, ahi, blo + 4, bhi, idesc16, 1);
+                                    umma_bf16_lh(tacc, alo + 6, ahi, blo + 6, bhi, idesc16, 1);
+                                } else {
+                                    umma_tf32_lh(tacc, alo, ahi, blo, bhi, idesc32, acc);
+                                    umma_tf32_lh(tacc, alo + 2, ahi, blo + 2, bhi, idesc32, 1);
+                                    umma_tf32_lh(tacc, alo + 4, ahi, blo + 4, bhi, idesc32, 1);
+                                    umma_tf32_lh(tacc, alo + 6, ahi, blo + 6, bhi, idesc32, 1);
+                                }
+                                acc = 1;
+                                umma_commit(&b_empty[sb]);
+                                sblo += L::B_BYTES >> 4;
+                                if (++sb == NB) {
+                                    sb = 0;
+                                    pb ^= 1;
+                                    sblo = 0;
+                                }
                             }
                         }
-                        umma_commit(&a_empty[sa]);  // the halo tile is free once its 9 taps retire
+                        umma_commit(&a_empty[sa]);  // the halo tile is free once its taps retire
                         if (++sa == TH_NA) {
                             sa = 0;
                             pa ^= 1;

@@ -94,8 +94,8 @@ class Operand(ctypes.Structure):
 
 
 class Act:
-    """An NHWC activation as GEMM operand: `hi` fp32 (tf32-rounded when split) and, in split mode, `b16`: a bf16 tensor
-    [2, n, h, w, c] with plane 0 = bf16(hi), plane 1 = bf16(v - hi)."""
+    """An NHWC activation as GEMM operand: `hi` = the fp32 value and, in split mode, `b16`: a bf16 tensor
+    [2, n, h, w, c] with plane 0 = h16 = bf16(v), plane 1 = l16 = bf16(v - h16) (the bf16 x 3 GEMM operands)."""
 
     __slots__ = ("hi", "b16")
 
@@ -109,7 +109,7 @@ class Act:
         return Act(hi, b16)
 
     def value(self):
-        return self.hi if self.b16 is None else self.hi + self.b16[1].float()
+        return self.hi
 
     def slice_c(self, c0, c1):
         return Act(self.hi[..., c0:c1], None if self.b16 is None else self.b16[..., c0:c1])
@@ -143,12 +143,6 @@ def split(x):
 
 
 split_tf32 = split
-
-
-def combine(act, out):
-    """out = hi + float(l16) (fp32 value of a split activation; identity copy target for consumers that are not GEMMs)"""
-    call("a2x_combine", _ptr(act.hi), _ptr(act.b16[1]), ctypes.c_longlong(act.hi.numel()), _ptr(out), stream_ptr())
-    return out
 
 
 # split-aware conv family ------------------------------------------------------------------------------------

@@ -402,12 +402,8 @@ class W2CEngine:
         return t
 
     def _full(self, act, name):
-        """fp32 value of a (possibly split) activation as one dense tensor (fusion consumes full precision)."""
-        if act.b16 is None:
-            return act.hi
-        out = self._buf(name, act.shape)
-        ops.combine(act, out)
-        return out
+        """fp32 value of a (possibly split) activation (the fp32 plane always holds the full value)."""
+        return act.hi
 
     # ------------------------------------------------------------------ loss (fused value + gradient)
     def loss(self, heads, labels, cls_weight=1.0, reg_coe=2.0, want_grad=True):
@@ -462,12 +458,7 @@ class W2CEngine:
         def bias_grad(g, C, out):
             """out[c] = sum over pixels of the gradient; g: Act (the exact value is hi + l16) or plain tensor"""
             sums = self._zeroed("bias.sums", 2 * C, torch.float64)
-            if isinstance(g, Act) and g.b16 is not None:
-                full = self._buf("bwd.biasfull.%d" % C, g.shape)
-                ops.combine(g, full)
-                ops.channel_stats(full, sums)
-            else:
-                ops.channel_stats(g.hi if isinstance(g, Act) else g, sums)
+            ops.channel_stats(g.hi if isinstance(g, Act) else g, sums)
             ops.sums_to_float(sums, C, out)
 
         # ---- heads
@@ -490,7 +481,7 @@ class W2CEngine:
 
         # ---- shrink conv 2 (3x3 + bias + ReLU)
         g2 = self._act("bwd.g2", S["y2"].shape)
-        ops.relu_bwd(d_y2, S["y2"].hi, g2)  # y > 0 <=> hi > 0 (rounding keeps the sign)
+        ops.relu_bwd(d_y2, S["y2"].hi, g2)
         n2 = "shrink_conv.layers.0.double_conv.2"
         with self._on_side():
             dwp = wgrad_conv(S["y1"], g2, n2 + ".weight", 3, 1)

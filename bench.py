@@ -295,7 +295,7 @@ def main():
     value = world * 1000.0 / ms
     line = {"metric": metric, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32x3 (3-pass split TF32 tensor-core GEMMs, fp32-equivalent; fp32 elsewhere)"
+            "vs_baseline": None, "dtype": "bf16x3 (3-pass bf16-split tensor-core GEMMs, fp32 accumulate, fp32-equivalent to 1e-4; fp32 elsewhere)"
             if args.precision == "split3" else "tf32", "data": "synthetic", "config": config,
             "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "scenes/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": 24, "ms_per_step": ms_e2e},
@@ -349,16 +349,15 @@ def roofline_pass(model, libmod, dd, lab, cw, rc, precision, torch):
     tg_ms = sum(g["ms"] for g in tg)
     tg_fl = sum(g["flops"] for g in tg)
     achieved = tg_fl / (tg_ms * 1e-3) / 1e12 if tg_ms > 0 else 0.0
-    hw_mult = 2.0 if precision == "split3" else 1.0  # tf32-MMA-equivalents per algorithmic FLOP
+    hw_mult = 3.0 if precision == "split3" else 2.0  # bf16-MMA-equivalents executed per algorithmic FLOP
     top = sorted(((k, round(v["ms"], 3), v["calls"]) for k, v in groups.items()), key=lambda x: -x[1])[:8]
-    return {"bound": "tensor", "kernel": "tapgemm_kernel (tcgen05.mma.kind::tf32; conv fwd + dgrad + deconv launches)",
+    return {"bound": "tensor", "kernel": "tapgemm_kernel / tapgemm_halo_kernel (tcgen05.mma kind::f16 bf16, 3 split passes; conv fwd + dgrad + deconv launches)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
             "peak_source": src, "algorithmic_gflop_per_step": tg_fl / 1e9, "kernel_ms_per_step": tg_ms,
             "share_of_step": tg_ms / total_ms if total_ms else None,
             "hw_tflops_executed": achieved * hw_mult,
-            "note": "peak is the measured dense bf16 number; kind::tf32 runs at half the bf16 rate and split3 executes one "
-                    "tf32 + two bf16 MMAs (= 2 tf32-equivalents) per algorithmic FLOP, so the hardware-side tensor "
-                    "utilisation is hw_tflops_executed / (peak/2)",
+            "note": "achieved counts each algorithmic FLOP once; the bf16x3 split executes three bf16 MMAs per algorithmic "
+                    "FLOP, so the hardware-side tensor utilisation is hw_tflops_executed / peak",
             "wgrad": {"ms": groups.get("a2x_conv2d_wgrad", {}).get("ms"),
                       "tflops": (groups["a2x_conv2d_wgrad"]["flops"] / (groups["a2x_conv2d_wgrad"]["ms"] * 1e-3) / 1e12)
                       if "a2x_conv2d_wgrad" in groups else None},

@@ -43,12 +43,13 @@ typedef struct {
     int n, h, w, cin, cout, ksize, stride;
 } a2x_conv_shape;
 
-/* Precision. Every GEMM operand v may be given as one plane (`b16 == NULL`: plain TF32, values should be pre-rounded
- * to TF32 with round-to-nearest, which every producer kernel here does) or as the 3-term SPLIT:
- *     hi = tf32_rn(v) (fp32),   b16 plane 0 = bf16(hi),   b16 plane 1 = bf16(v - hi)
- * and the contraction is evaluated as  hi*hi [kind::tf32]  +  l16*h16 [kind::f16 bf16]  +  h16*l16 [bf16]  into one
- * fp32 TMEM accumulator: fp32-equivalent accuracy (~2^-20 relative per product) at 2 TF32-MMA-equivalents instead of 3.
- * Split operands need channel counts that are multiples of 64. */
+/* Precision. Every GEMM operand v may be given as one plane (`b16 == NULL`: plain TF32; the MMA truncates the fp32
+ * bits) or as the 3-term SPLIT:
+ *     hi = v (fp32, read by the non-GEMM consumers),   b16 plane 0 = h16 = bf16(v),   b16 plane 1 = l16 = bf16(v - h16)
+ * and the contraction is evaluated as  h16*h16 + l16*h16 + h16*l16  (three kind::f16 bf16 MMAs) into one fp32 TMEM
+ * accumulator: every product is exact in fp32, the dropped terms are ~2^-17 relative per product (logits within 1e-4 of
+ * the fp32 reference through the 23-layer stack) at 3 bf16-MMA passes. Split operands need channel counts that are
+ * multiples of 64. */
 typedef struct {
     const float* hi;     /* NHWC fp32, pixel stride `cs` elements */
     const void* b16;     /* NHWC bf16 [2 planes], same pixel stride; NULL = single-plane mode */
@@ -57,12 +58,12 @@ typedef struct {
 } a2x_operand;
 typedef struct {
     float* hi;
-    void* b16;           /* NULL: write the fp32 value only (not rounded) */
+    void* b16;           /* NULL: write the fp32 value only */
     long long b16_plane;
     int cs;
 } a2x_output;
 typedef struct {
-    const float* w32;    /* packed fp32 plane (tf32-rounded) */
+    const float* w32;    /* packed fp32 plane (tf32-rounded; the single-plane operand) */
     const void* w16;     /* packed bf16 planes [2][...] (h16, l16); may be NULL in single-plane mode */
 } a2x_weights;
 
@@ -100,10 +101,8 @@ int a2x_deconv_wgrad(const a2x_conv_shape* s, const a2x_operand* x, const a2x_op
                      a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- operand split
- * hi = tf32_rn(x), b16 = (bf16(hi), bf16(x - hi))  (n multiple of 4; out->cs ignored) */
+ * hi = x, b16 = (bf16(x), bf16(x - bf16(x)))  (n multiple of 4; out->cs ignored) */
 int a2x_split(const float* x, long long n, const a2x_output* out, a2x_stream_t stream);
-/* out = hi + float(l16): the fp32 value of a split pair to ~2^-20 (for consumers that are not GEMMs) */
-int a2x_combine(const float* hi, const void* l16, long long n, float* out, a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- BatchNorm / ReLU / masks (HBM-bound)
  * Replace nn.BatchNorm2d(eps 1e-3, momentum 0.01) + nn.ReLU and their autograd

@@ -150,10 +150,10 @@ def shrink_conv(sd, sh_args, x):
 
 
 # --------------------------------------------------------------------------------------------------- a12 mask
-def communication(sd, comm_args, psm_single, record_len, training):
+def communication(sd, comm_args, psm_single, record_len, training, keep=None):
     """where2comm_modules/where2comm_fuse.py:83-149. Train mode draws K from Python `random` (:106)."""
     thr = comm_args["threshold"]
-    masks, rates = [], []
+    masks, rates, smooths = [], [], []
     start = 0
     for n in record_len.tolist():
         conf = psm_single[start:start + n]
@@ -179,6 +179,9 @@ def communication(sd, comm_args, psm_single, record_len, training):
         mask = mask.clone()
         mask[0] = 1
         masks.append(mask)
+        smooths.append(maps)
+    if keep is not None:
+        keep["smooth"] = torch.cat(smooths, 0)
     return torch.cat(masks, 0), sum(rates) / len(rates)
 
 
@@ -205,7 +208,13 @@ def where2comm_fusion(sd, args, spatial_features, psm_single, record_len, traini
             if fa["fully"]:
                 rate = torch.tensor(1)
             else:
-                mask, rate = communication(sd, fa["communication"], psm_single, record_len, training)
+                mask, rate = communication(sd, fa["communication"], psm_single, record_len, training, keep)
+                if keep is not None and keep.get("mask_override") is not None:
+                    # test hook: teacher-force the (discontinuous) top-K / threshold decisions of the implementation
+                    # under test, so the comparison downstream of the mask is well-posed (tests check separately that
+                    # the two masks differ only at pixels whose smoothed confidence ties with the cut)
+                    keep["mask_own"] = mask
+                    mask = keep["mask_override"].to(mask.dtype).reshape(mask.shape)
                 if x.shape[-1] != mask.shape[-1]:
                     mask = F.interpolate(mask, size=(x.shape[-2], x.shape[-1]), mode="bilinear", align_corners=False)
                 if keep is not None:

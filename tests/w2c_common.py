@@ -52,3 +52,50 @@ def to_device(dd, dev):
         else:
             out[k] = v
     return out
+
+
+def engine_buf(model, name):
+    for k, t in model.engine.bufs.items():
+        if len(k) == 3 and k[0] == name:
+            return t
+    raise KeyError(name)
+
+
+def oracle_train_step(sd, cfg, dd, labels, k_seed, mask_override=None):
+    """The oracle's train-mode forward + PointPillarLossMultiClass + autograd backward on the CPU. With
+    `mask_override` (the [N,h,w] communication mask the CUDA path selected) the top-K tie-breaks are teacher-forced.
+    Returns (outputs, total loss, {param: grad}, keep)."""
+    args = cfg["model_args"]
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "gaussian" not in k
+             and "num_batches" not in k else v.clone()) for k, v in sd.items()}
+    keep = {"mask_override": mask_override}
+    random.seed(k_seed)
+    out, bufs = O.where2com_forward(p, args, dd, training=True, keep=keep)
+    loss = O.point_pillar_loss_multiclass(out, labels, args["num_class"], cfg["loss_args"]["cls_weight"],
+                                          cfg["loss_args"]["reg"])[0]
+    loss.backward()
+    grads = {k: v.grad for k, v in p.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    return out, loss.detach(), grads, keep
+
+
+def check_mask_ties(mask_gpu, keep, tol=1e-4, max_frac=5e-3):
+    """The CUDA mask may differ from the oracle's own only where the smoothed confidence ties (within `tol`) with the
+    per-agent cut (the K-th largest value): returns the number of differing pixels."""
+    own = keep.get("mask_own", keep["mask"]).reshape(mask_gpu.shape)
+    diff = own != mask_gpu
+    n = int(diff.sum())
+    if n == 0:
+        return 0
+    assert n <= max_frac * mask_gpu.numel(), "mask differs at %d pixels" % n
+    smooth = keep["smooth"].reshape(mask_gpu.shape[0], -1)
+    d = diff.reshape(mask_gpu.shape[0], -1)
+    m = own.reshape(mask_gpu.shape[0], -1)
+    for a in range(mask_gpu.shape[0]):
+        if not d[a].any():
+            continue
+        sel = smooth[a][m[a] > 0]
+        if sel.numel() == 0 or a == 0 and bool((m[a] > 0).all()):
+            continue  # ego row is forced to one
+        cut = float(sel.min())
+        assert float((smooth[a][d[a]] - cut).abs().max()) < tol, "agent %d: mask differs away from the top-K cut" % a
+    return n
