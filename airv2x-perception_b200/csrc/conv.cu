@@ -477,6 +477,75 @@ __global__ void unpack_deconv_dw_kernel(const float* __restrict__ dwp, int cin, 
     }
 }
 
+// ------------------------------------------------------------------ batched re-layout (one launch per step)
+// The per-layer pack / unpack kernels above move a few hundred KB each: launch latency, not bandwidth, is what they
+// cost inside the step. These two kernels walk a device-resident job table instead (<= 64 jobs, staged in smem).
+__global__ void __launch_bounds__(256) pack_batched_kernel(const a2x_pack_job* __restrict__ jobs, int njobs) {
+    __shared__ a2x_pack_job sj[64];
+    for (int i = threadIdx.x; i < njobs; i += blockDim.x) sj[i] = jobs[i];
+    __syncthreads();
+    const long long total = sj[njobs - 1].elem_begin + sj[njobs - 1].elems;
+    int j = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        while (i >= sj[j].elem_begin + sj[j].elems) ++j;  // i grows monotonically per thread
+        const a2x_pack_job& J = sj[j];
+        const long long e = i - J.elem_begin;
+        if (J.kind == 2) {  // plain vector copy (fused head bias)
+            J.f32[J.row0 + e] = J.src[e];
+            continue;
+        }
+        if (J.kind == 0) {  // conv OIHW [rows][cin][kk] -> [tap][row0 + co][ci] and [tap][ci][row0 + co]
+            const int cin = J.b, rows = J.a, kk = J.kk;
+            const int ci = (int)(e % cin);
+            const int co = (int)((e / cin) % rows);
+            const int tap = (int)(e / ((long long)cin * rows));
+            const float w = J.src[((long long)co * cin + ci) * kk + tap];
+            const long long plane = (long long)kk * J.cout_pad * cin;
+            put_w(J.f32, (__nv_bfloat16*)J.f16, plane, ((long long)tap * J.cout_pad + J.row0 + co) * cin + ci, w);
+            put_w(J.d32, (__nv_bfloat16*)J.d16, plane, ((long long)tap * cin + ci) * J.cout_pad + J.row0 + co, w);
+        } else {  // deconv [ci][co][i][j] -> [(ij, co)][ci] and [ij][ci][co]
+            const int cin = J.a, cout = J.b, ss = J.kk;
+            const int ij = (int)(e % ss);
+            const int co = (int)((e / ss) % cout);
+            const int ci = (int)(e / ((long long)ss * cout));
+            const float w = J.src[e];
+            const long long plane = (long long)cin * cout * ss;
+            put_w(J.f32, (__nv_bfloat16*)J.f16, plane, ((long long)ij * cout + co) * cin + ci, w);
+            put_w(J.d32, (__nv_bfloat16*)J.d16, plane, ((long long)ij * cin + ci) * cout + co, w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_batched_kernel(const a2x_unpack_job* __restrict__ jobs, int njobs) {
+    __shared__ a2x_unpack_job sj[64];
+    for (int i = threadIdx.x; i < njobs; i += blockDim.x) sj[i] = jobs[i];
+    __syncthreads();
+    const long long total = sj[njobs - 1].elem_begin + sj[njobs - 1].elems;
+    int j = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        while (i >= sj[j].elem_begin + sj[j].elems) ++j;
+        const a2x_unpack_job& J = sj[j];
+        const long long e = i - J.elem_begin;
+        if (J.kind == 2) {  // double sums -> float vector (bias gradients)
+            J.dst[e] = (float)reinterpret_cast<const double*>(J.src)[J.row0 + e];
+        } else if (J.kind == 0) {  // [tap][cout_pad][cin] rows [row0, row0 + rows) -> OIHW
+            const int cin = J.b, kk = J.kk;
+            const int tap = (int)(e % kk);
+            const int ci = (int)((e / kk) % cin);
+            const int co = (int)(e / ((long long)kk * cin));
+            J.dst[e] = reinterpret_cast<const float*>(J.src)[((long long)tap * J.cout_pad + J.row0 + co) * cin + ci];
+        } else {  // [ij][ci][co] -> [ci][co][i][j]
+            const int cin = J.a, cout = J.b, ss = J.kk;
+            const int ij = (int)(e % ss);
+            const int co = (int)((e / ss) % cout);
+            const int ci = (int)(e / ((long long)ss * cout));
+            J.dst[e] = reinterpret_cast<const float*>(J.src)[((long long)ij * cin + ci) * cout + co];
+        }
+    }
+}
+
 static int grid_for(long long total) {
     long long b = (total + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
@@ -527,6 +596,22 @@ int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, fl
     A2X_REQUIRE(dw_packed && dw_iohw && cin > 0 && cout > 0 && s > 0, "bad unpack args");
     unpack_deconv_dw_kernel<<<grid_for((long long)cin * cout * s * s), 256, 0, (cudaStream_t)stream>>>(
         dw_packed, cin, cout, s, dw_iohw, accumulate);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_pack_weights_batched(const a2x_pack_job* jobs_dev, int njobs, long long total_elems, a2x_stream_t stream) {
+    A2X_REQUIRE(jobs_dev && njobs > 0 && njobs <= 64 && total_elems > 0, "pack_weights_batched: bad args (<= 64 jobs)");
+    pack_batched_kernel<<<grid_for(total_elems), 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_unpack_wgrads_batched(const a2x_unpack_job* jobs_dev, int njobs, long long total_elems, a2x_stream_t stream) {
+    A2X_REQUIRE(jobs_dev && njobs > 0 && njobs <= 64 && total_elems > 0, "unpack_wgrads_batched: bad args (<= 64 jobs)");
+    unpack_batched_kernel<<<grid_for(total_elems), 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -210,6 +210,77 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------- BN (train) apply
+// bn_finalize fused into the apply pass: every block derives (scale, shift) of all C channels from the batch sums into
+// shared memory (C <= 1024: a few hundred double ops per block), block 0 also publishes scale / shift / mean / invstd
+// for the backward pass and performs the `n_updates` running-statistics updates. Then y = relu?(z*scale + shift).
+__global__ void __launch_bounds__(256) bn_train_act_kernel(const float* __restrict__ z, int z_cs,
+                                                           const double* __restrict__ sums, double count,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, float momentum,
+                                                           int n_updates, float* __restrict__ running_mean,
+                                                           float* __restrict__ running_var, float* __restrict__ scale_out,
+                                                           float* __restrict__ shift_out, float* __restrict__ mean_out,
+                                                           float* __restrict__ invstd_out, int relu, SplitOut y, int y_cs,
+                                                           long long npix, int C) {
+    extern __shared__ float tab[];  // [C] scale, [C] shift
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double m = sums[c] / count;
+        double var = sums[C + c] / count - m * m;
+        if (var < 0) var = 0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+        const float sc = g * invstd, sh = b - (float)m * g * invstd;
+        tab[c] = sc;
+        tab[C + c] = sh;
+        if (blockIdx.x == 0) {
+            scale_out[c] = sc;
+            shift_out[c] = sh;
+            if (mean_out) mean_out[c] = (float)m;
+            if (invstd_out) invstd_out[c] = invstd;
+            if (running_mean != nullptr && n_updates > 0) {
+                const float unbiased = (float)(count > 1 ? var * count / (count - 1) : var);
+                float rm = running_mean[c], rv = running_var[c];
+                for (int i = 0; i < n_updates; ++i) {
+                    rm = (1.f - momentum) * rm + momentum * (float)m;
+                    rv = (1.f - momentum) * rv + momentum * unbiased;
+                }
+                running_mean[c] = rm;
+                running_var[c] = rv;
+            }
+        }
+    }
+    __syncthreads();
+    const int q = C >> 2;
+    const long long total = npix * q;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    constexpr int U = 4;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+        float4 v[U];
+        long long p[U];
+        int c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            p[u] = i / q;
+            c[u] = (int)(i - p[u] * q) * 4;
+            if (i < total) v[u] = *reinterpret_cast<const float4*>(z + p[u] * z_cs + c[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride >= total) break;
+            float4 t = v[u];
+            const float4 s = *reinterpret_cast<const float4*>(tab + c[u]);
+            const float4 b = *reinterpret_cast<const float4*>(tab + C + c[u]);
+            t.x = t.x * s.x + b.x; t.y = t.y * s.y + b.y; t.z = t.z * s.z + b.z; t.w = t.w * s.w + b.w;
+            if (relu) {
+                t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+            store_split4(y, p[u] * y_cs + c[u], t);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- BN+ReLU backward
 // g = dy * (z*scale+shift > 0); dz = gamma*invstd * (g - sum_g/m - zhat * sum_gz/m)        (train mode)
 __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __restrict__ dy, int dy_cs,
@@ -219,7 +290,24 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
                                                                 const float* __restrict__ mean,
                                                                 const float* __restrict__ invstd,
                                                                 const double* __restrict__ sums, double count,
-                                                                SplitOut dz, int dz_cs, long long npix, int C) {
+                                                                SplitOut dz, int dz_cs, long long npix, int C,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                int accumulate) {
+    extern __shared__ float tab[];  // per channel: scale, shift, mean, invstd, mean(g), mean(g*zhat)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        tab[c] = scale[c];
+        tab[C + c] = shift[c];
+        tab[2 * C + c] = mean[c];
+        tab[3 * C + c] = invstd[c];
+        tab[4 * C + c] = (float)(sums[c] / count);
+        tab[5 * C + c] = (float)(sums[C + c] / count);
+        if (blockIdx.x == 0) {  // dgamma = sum g*zhat, dbeta = sum g  (bn_bwd_finalize fused)
+            const float dg = (float)sums[C + c], db = (float)sums[c];
+            if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+            if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
+        }
+    }
+    __syncthreads();
     const int q = C >> 2;
     const long long total = npix * q;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -247,11 +335,10 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int ch = c[u] + e;
-                const float sc = scale[ch], sh = shift[ch];
+                const float sc = tab[ch], sh = tab[C + ch];
                 const float g = (zz[e] * sc + sh > 0.f) ? d[e] : 0.f;
-                const float zh = (zz[e] - mean[ch]) * invstd[ch];
-                const float mg = (float)(sums[ch] / count), mgz = (float)(sums[C + ch] / count);
-                o[e] = sc * (g - mg - zh * mgz);  // scale = gamma * invstd
+                const float zh = (zz[e] - tab[2 * C + ch]) * tab[3 * C + ch];
+                o[e] = sc * (g - tab[4 * C + ch] - zh * tab[5 * C + ch]);  // scale = gamma * invstd
             }
             store_split4(dz, p[u] * dz_cs + c[u], make_float4(o[0], o[1], o[2], o[3]));
         }
@@ -299,6 +386,14 @@ __global__ void count_nonzero_kernel(const float* __restrict__ x, long long n4, 
 static int ew_grid(long long total) {
     long long b = (total + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// kernels that build a per-channel table in their prologue: fewer, fatter blocks
+static int ew_grid_tab(long long total) {
+    long long b = (total + 256 * 8 - 1) / (256 * 8);
+    if (b > 148 * 6) b = 148 * 6;
     if (b < 1) b = 1;
     return (int)b;
 }
@@ -393,16 +488,25 @@ int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, 
     if (int r = check_c(C)) return r;
     A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && dz && dz->hi && npix > 0,
                 "bn_relu_bwd_apply: bad args");
-    bn_relu_bwd_apply_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
-        dy, dy_cs, z, z_cs, scale, shift, mean, invstd, sums, count, to_split(dz), dz->cs, npix, C);
+    bn_relu_bwd_apply_kernel<<<ew_grid_tab(npix * (C / 4)), 256, 6 * C * sizeof(float), (cudaStream_t)stream>>>(
+        dy, dy_cs, z, z_cs, scale, shift, mean, invstd, sums, count, to_split(dz), dz->cs, npix, C, dgamma, dbeta,
+        accumulate_param_grads);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
-    if (dgamma || dbeta) {
-        bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta,
-                                                                                accumulate_param_grads);
+    return 0;
+}
+
+int a2x_bn_train_act(const float* z, int z_cs, const double* sums, double count, const float* gamma, const float* beta,
+                     float eps, float momentum, int n_updates, float* running_mean, float* running_var, float* scale,
+                     float* shift, float* mean_out, float* invstd_out, int relu, const a2x_output* y, long long npix,
+                     int C, a2x_stream_t stream) {
+    if (int r = check_c(C)) return r;
+    A2X_REQUIRE(z && sums && scale && shift && y && y->hi && npix > 0 && count > 0, "bn_train_act: bad args");
+    bn_train_act_kernel<<<ew_grid_tab(npix * (C / 4)), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+        z, z_cs, sums, count, gamma, beta, eps, momentum, n_updates, running_mean, running_var, scale, shift, mean_out,
+        invstd_out, relu, to_split(y), y->cs, npix, C);
     A2X_LAUNCHED();
-        A2X_CHECK_CUDA(cudaGetLastError());
-    }
+    A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 

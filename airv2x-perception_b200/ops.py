@@ -88,6 +88,77 @@ def unpack_deconv_wgrad(dwp, cin, cout, s, out=None, accumulate=False):
     return out
 
 
+# ----------------------------------------------------------------------------- batched pack / unpack (one launch)
+class PackJob(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p), ("f32", ctypes.c_void_p), ("f16", ctypes.c_void_p), ("d32", ctypes.c_void_p),
+                ("d16", ctypes.c_void_p), ("kind", c_int), ("a", c_int), ("b", c_int), ("kk", c_int),
+                ("cout_pad", c_int), ("row0", c_int), ("elem_begin", ctypes.c_longlong), ("elems", ctypes.c_longlong)]
+
+
+class UnpackJob(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("kind", c_int), ("a", c_int), ("b", c_int),
+                ("kk", c_int), ("cout_pad", c_int), ("row0", c_int), ("elem_begin", ctypes.c_longlong),
+                ("elems", ctypes.c_longlong)]
+
+
+def conv_pack_job(w, pk, row0=0):
+    """OIHW parameter `w` -> rows [row0, row0 + cout) of the PackedW `pk` (cout_pad = pk.f32.shape[1])"""
+    cout, cin, k, _ = w.shape
+    return PackJob(w.data_ptr(), pk.f32.data_ptr(), pk.f16.data_ptr(), pk.d32.data_ptr(), pk.d16.data_ptr(), 0, cout, cin,
+                   k * k, pk.f32.shape[1], row0, 0, k * k * cout * cin)
+
+
+def deconv_pack_job(w, pk):
+    cin, cout, s, _ = w.shape
+    return PackJob(w.data_ptr(), pk.f32.data_ptr(), pk.f16.data_ptr(), pk.d32.data_ptr(), pk.d16.data_ptr(), 1, cin, cout,
+                   s * s, 0, 0, 0, cin * cout * s * s)
+
+
+def copy_pack_job(src, dst, row0):
+    return PackJob(src.data_ptr(), dst.data_ptr(), None, None, None, 2, 0, 0, 0, 0, row0, 0, src.numel())
+
+
+def conv_unpack_job(dwp, dw, row0=0):
+    """packed [kk][cout_pad][cin] rows [row0, row0 + cout) -> OIHW gradient `dw`"""
+    cout, cin, k, _ = dw.shape
+    return UnpackJob(dwp.data_ptr(), dw.data_ptr(), 0, cout, cin, k * k, dwp.shape[1], row0, 0, dw.numel())
+
+
+def deconv_unpack_job(dwp, dw):
+    cin, cout, s, _ = dw.shape
+    return UnpackJob(dwp.data_ptr(), dw.data_ptr(), 1, cin, cout, s * s, 0, 0, 0, dw.numel())
+
+
+def sums_unpack_job(sums, out, row0=0):
+    """float out[i] = (float) double sums[row0 + i]"""
+    return UnpackJob(sums.data_ptr(), out.data_ptr(), 2, 0, 0, 0, 0, row0, 0, out.numel())
+
+
+class JobTable:
+    """A device-resident job table (uploaded once per distinct set of pointers)."""
+
+    def __init__(self, jobs, device):
+        assert 0 < len(jobs) <= 64, "at most 64 jobs per batched launch"
+        pos = 0
+        for j in jobs:
+            j.elem_begin = pos
+            pos += j.elems
+        self.total = pos
+        self.n = len(jobs)
+        arr = (type(jobs[0]) * len(jobs))(*jobs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.dev = host.to(device)
+        self.key = tuple((j.src, getattr(j, "dst", None) or getattr(j, "f32", None)) for j in jobs)
+
+
+def pack_weights_batched(table):
+    call("a2x_pack_weights_batched", _ptr(table.dev), c_int(table.n), c_ll(table.total), stream_ptr())
+
+
+def unpack_wgrads_batched(table):
+    call("a2x_unpack_wgrads_batched", _ptr(table.dev), c_int(table.n), c_ll(table.total), stream_ptr())
+
+
 # ============================================================================= split-plane activations
 class Operand(ctypes.Structure):
     _fields_ = [("hi", ctypes.c_void_p), ("b16", ctypes.c_void_p), ("b16_plane", ctypes.c_longlong), ("cs", c_int)]
@@ -223,6 +294,15 @@ def bn_finalize(sums, count, gamma, beta, n_updates, rm, rv, scale, shift, mean,
 def bn_eval_affine(gamma, beta, rm, rv, scale, shift, eps=1e-3):
     call("a2x_bn_eval_affine", _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), c_f(eps), c_int(scale.numel()), _ptr(scale),
          _ptr(shift), stream_ptr())
+
+
+def bn_train_act(z, sums, count, gamma, beta, n_updates, rm, rv, scale, shift, mean, invstd, relu, out, eps=1e-3,
+                 momentum=0.01):
+    """fused bn_finalize + affine_act (train mode): out = relu?(BN_batch(z)); scale/shift/mean/invstd are published"""
+    call("a2x_bn_train_act", _ptr(z), c_int(_cs(z)), _ptr(sums), c_d(float(count)), _ptr(gamma), _ptr(beta), c_f(eps),
+         c_f(momentum), c_int(n_updates), _ptr(rm), _ptr(rv), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+         c_int(int(relu)), _op(out), c_ll(_npix(z)), c_int(z.shape[3]), stream_ptr())
+    return out
 
 
 def affine_act(x, scale, shift, relu, out, mask=None):

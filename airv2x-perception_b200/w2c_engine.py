@@ -81,8 +81,11 @@ class W2CEngine:
         off = self._arena_off_map.setdefault(dtype, 0)
         need = off + nbytes_elems
         if arena is None or arena.numel() < need:
-            # first pass discovers the size; grow and re-zero
+            # first pass discovers the size; grow and re-zero. Slices already handed out this step (and raw pointers
+            # to them in job tables) must stay valid until the step ends: retire, do not free, the old arena.
             new = torch.zeros(max(need * 2, 1 << 16), device=self.device, dtype=dtype)
+            if arena is not None:
+                self._retired.append(arena)
             self.bufs[("arena", dtype)] = new
             arena = new
         self._arena_off_map[dtype] = need
@@ -90,6 +93,7 @@ class W2CEngine:
 
     def _begin_step(self):
         self._arena_off_map = {}
+        self._retired = []
         for dt in (torch.float64, torch.float32):
             a = self.bufs.get(("arena", dt))
             if a is not None:
@@ -106,38 +110,52 @@ class W2CEngine:
         return pk
 
     def _pack_weights(self, P):
-        W = {}
+        """Re-lay every conv / deconv weight for this step (OIHW -> tap-major forward and data-gradient operands, bf16
+        split planes) with ONE batched launch over a cached device job table; the three 1x1 heads share one fused
+        64-column GEMM operand (cls | reg | obj | zero pad)."""
+        W, jobs = {}, []
         for i, ln in enumerate(self.layer_nums):
             for k in range(ln + 1):
                 name = "backbone.blocks.%d.%d.weight" % (i, 1 + 3 * k)
                 w = P[name]
                 co, ci = w.shape[0], w.shape[1]
-                W[name] = ops.pack_conv_weight(w, out=self._packed(name, (9, co, ci), (9, ci, co)))
+                W[name] = self._packed(name, (9, co, ci), (9, ci, co))
+                jobs.append(ops.conv_pack_job(w, W[name]))
             name = "backbone.deblocks.%d.0.weight" % i
             w = P[name]
             s = self.up_strides[i]
             ci, co = w.shape[0], w.shape[1]
-            W[name] = ops.pack_deconv_weight(w, out=self._packed(name, (1, s * s * co, ci), (s * s, ci, co)))
+            W[name] = self._packed(name, (1, s * s * co, ci), (s * s, ci, co))
+            jobs.append(ops.deconv_pack_job(w, W[name]))
         for idx, k in ((0, 1), (2, 3)):
             name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
             w = P[name]
             co, ci = w.shape[0], w.shape[1]
-            W[name] = ops.pack_conv_weight(w, out=self._packed(name, (k * k, co, ci), (k * k, ci, co)))
-        hw = self._buf("heads.w", (HEAD_PAD, self.c_shrink, 1, 1))
-        hb = self._buf("heads.b", (HEAD_PAD,))
+            W[name] = self._packed(name, (k * k, co, ci), (k * k, ci, co))
+            jobs.append(ops.conv_pack_job(w, W[name]))
         nc, nr = self.A * self.K, 7 * self.A
-        hw.zero_()
-        hb.zero_()
-        hw[:nc].copy_(P["cls_head.weight"])
-        hw[nc:nc + nr].copy_(P["reg_head.weight"])
-        hw[nc + nr:self.n_head].copy_(P["obj_head.weight"])
-        hb[:nc].copy_(P["cls_head.bias"])
-        hb[nc:nc + nr].copy_(P["reg_head.bias"])
-        hb[nc + nr:self.n_head].copy_(P["obj_head.bias"])
-        W["heads"] = ops.pack_conv_weight(hw, out=self._packed("heads", (1, HEAD_PAD, self.c_shrink),
-                                                               (1, self.c_shrink, HEAD_PAD)))
+        fresh = ("packed", "heads") not in self.bufs
+        hp = self._packed("heads", (1, HEAD_PAD, self.c_shrink), (1, self.c_shrink, HEAD_PAD))
+        hb = self._buf("heads.b", (HEAD_PAD,))
+        if fresh:  # the pad rows / pad bias stay zero: no job ever writes them
+            for t in (hp.f32, hp.f16, hp.d32, hp.d16, hb):
+                t.zero_()
+        for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+            jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0))
+            jobs.append(ops.copy_pack_job(P[name + ".bias"], hb, row0))
+        W["heads"] = hp
         W["heads.bias"] = hb
+        ops.pack_weights_batched(self._job_table("pack", jobs))
         return W
+
+    def _job_table(self, name, jobs):
+        """device job table cached by the pointers it refers to (stable across steps: one upload)"""
+        key = tuple((j.src, j.dst if hasattr(j, "dst") else j.f32) for j in jobs)
+        ent = self.bufs.get(("jobs", name))
+        if ent is None or ent[0] != key:
+            ent = (key, ops.JobTable(jobs, self.device))
+            self.bufs[("jobs", name)] = ent
+        return ent[1]
 
     # ------------------------------------------------------------------ layers
     def _bn_params(self, P, bn, training, z, n_updates, tag, sums=None):
@@ -158,6 +176,16 @@ class W2CEngine:
                         P[bn + ".running_var"], scale, shift, mean, invstd)
         return scale, shift, mean, invstd
 
+    def _bn_train_act(self, P, bn, z, sums, n_updates, tag, out):
+        """train-mode BN (finalize fused into the apply pass) + ReLU + operand split; returns the saved statistics"""
+        C = z.shape[3]
+        scale, shift = self._buf(tag + ".scale", (C,)), self._buf(tag + ".shift", (C,))
+        mean, invstd = self._buf(tag + ".mean", (C,)), self._buf(tag + ".invstd", (C,))
+        count = z.shape[0] * z.shape[1] * z.shape[2]
+        ops.bn_train_act(z, sums, count, P[bn + ".weight"], P[bn + ".bias"], n_updates, P[bn + ".running_mean"],
+                         P[bn + ".running_var"], scale, shift, mean, invstd, True, out)
+        return scale, shift, mean, invstd
+
     def _conv_bn_relu(self, P, W, conv, bn, x, stride, training, n_updates, tag, record):
         n, h, w, _ = x.shape
         cout = P[conv].shape[0]
@@ -171,8 +199,7 @@ class W2CEngine:
         z = self._buf(tag + ".z", (n, ho, wo, cout))
         sums = self._zeroed(tag + ".sums", 2 * cout, torch.float64)
         ops.conv_fwd(x, wf, 3, stride, Act(z), stats=sums)  # BN batch statistics come out of the GEMM epilogue
-        scale, shift, mean, invstd = self._bn_params(P, bn, True, z, n_updates, tag, sums)
-        ops.affine_act(z, scale, shift, True, y)
+        scale, shift, mean, invstd = self._bn_train_act(P, bn, z, sums, n_updates, tag, y)
         if record is not None:
             record.append(dict(kind="conv", conv=conv, bn=bn, x=x, z=z, y=y, stride=stride, scale=scale, shift=shift,
                                mean=mean, invstd=invstd, tag=tag))
@@ -202,8 +229,7 @@ class W2CEngine:
         z = self._buf(tg + ".z", (n, h * s, w * s, cout))
         sums = self._zeroed(tg + ".sums", 2 * cout, torch.float64)
         ops.deconv_fwd(x, wf, cout, s, Act(z), stats=sums)
-        scale, shift, mean, invstd = self._bn_params(P, bn, True, z, n_updates, tg, sums)
-        ops.affine_act(z, scale, shift, True, out_slice)
+        scale, shift, mean, invstd = self._bn_train_act(P, bn, z, sums, n_updates, tg, out_slice)
         if record is not None:
             record.append(dict(kind="deconv", conv=conv, bn=bn, x=x, z=z, y=out_slice, stride=s, scale=scale,
                                shift=shift, mean=mean, invstd=invstd, tag=tg, level=i))
@@ -448,6 +474,8 @@ class W2CEngine:
         nc, nr = self.A * self.K, 7 * self.A
         B, h2, w2, _ = dheads.shape
 
+        unpack = []  # weight / bias gradient re-layouts, done by ONE batched launch at the end of the side stream
+
         def wgrad_conv(x, dy, name, k, stride):
             cout = dy.shape[3]
             cin = x.shape[3]
@@ -455,27 +483,22 @@ class W2CEngine:
             ops.conv_wgrad(x, dy, k, stride, dwp)
             return dwp
 
-        def bias_grad(g, C, out):
-            """out[c] = sum over pixels of the gradient; g: Act (the exact value is hi + l16) or plain tensor"""
+        def bias_grad(g, C, outs):
+            """out[c] = sum over pixels of the gradient; outs: [(tensor, first channel)] slices of the C channels"""
             sums = self._zeroed("bias.sums", 2 * C, torch.float64)
             ops.channel_stats(g.hi if isinstance(g, Act) else g, sums)
-            ops.sums_to_float(sums, C, out)
+            for out, c0 in outs:
+                unpack.append(ops.sums_unpack_job(sums, out, c0))
 
         # ---- heads
         dh = self._act("bwd.dheads", dheads.shape)
         ops.affine_act(dheads, None, None, False, dh)
         with self._on_side():
             dwp = wgrad_conv(S["y2"], dh, "heads", 1, 1)
-            hg = self._buf("heads.wgrad", (HEAD_PAD, self.c_shrink, 1, 1))
-            ops.unpack_conv_wgrad(dwp, HEAD_PAD, self.c_shrink, 1, out=hg)
-            grads["cls_head.weight"].copy_(hg[:nc])
-            grads["reg_head.weight"].copy_(hg[nc:nc + nr])
-            grads["obj_head.weight"].copy_(hg[nc + nr:self.n_head])
-            hbg = self._buf("heads.bgrad", (HEAD_PAD,))
-            bias_grad(dheads, HEAD_PAD, hbg)
-            grads["cls_head.bias"].copy_(hbg[:nc])
-            grads["reg_head.bias"].copy_(hbg[nc:nc + nr])
-            grads["obj_head.bias"].copy_(hbg[nc + nr:self.n_head])
+            for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+                unpack.append(ops.conv_unpack_job(dwp, grads[name + ".weight"], row0))
+            bias_grad(dheads, HEAD_PAD, [(grads["cls_head.bias"], 0), (grads["reg_head.bias"], nc),
+                                         (grads["obj_head.bias"], nc + nr)])
         d_y2 = self._buf("bwd.d_y2", S["y2"].shape)
         ops.conv_dgrad(dh, W["heads"], 1, 1, d_y2)
 
@@ -485,8 +508,8 @@ class W2CEngine:
         n2 = "shrink_conv.layers.0.double_conv.2"
         with self._on_side():
             dwp = wgrad_conv(S["y1"], g2, n2 + ".weight", 3, 1)
-            ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_shrink, 3, out=grads[n2 + ".weight"])
-            bias_grad(g2, self.c_shrink, grads[n2 + ".bias"])
+            unpack.append(ops.conv_unpack_job(dwp, grads[n2 + ".weight"]))
+            bias_grad(g2, self.c_shrink, [(grads[n2 + ".bias"], 0)])
         d_y1 = self._buf("bwd.d_y1", S["y1"].shape)
         ops.conv_dgrad(g2, W[n2 + ".weight"], 3, 1, d_y1)
 
@@ -496,8 +519,8 @@ class W2CEngine:
         n1 = "shrink_conv.layers.0.double_conv.0"
         with self._on_side():
             dwp = wgrad_conv(S["catB"], g1, n1 + ".weight", 1, 1)
-            ops.unpack_conv_wgrad(dwp, self.c_shrink, self.c_cat, 1, out=grads[n1 + ".weight"])
-            bias_grad(g1, self.c_shrink, grads[n1 + ".bias"])
+            unpack.append(ops.conv_unpack_job(dwp, grads[n1 + ".weight"]))
+            bias_grad(g1, self.c_shrink, [(grads[n1 + ".bias"], 0)])
         d_cat = self._buf("bwd.d_cat", (B, h2, w2, self.c_cat))
         ops.conv_dgrad(g1, W[n1 + ".weight"], 1, 1, d_cat)
 
@@ -519,7 +542,7 @@ class W2CEngine:
             dwp = self._zeroed(r["conv"] + ".dwp", s * s * cin * cout, torch.float32).view(s * s, cin, cout)
             with self._on_side():
                 ops.deconv_wgrad(r["x"], dz, s, dwp)
-                ops.unpack_deconv_wgrad(dwp, cin, cout, s, out=grads[r["conv"]])
+                unpack.append(ops.deconv_unpack_job(dwp, grads[r["conv"]]))
             d_fused = self._buf("bwd.d_fused%d" % i, lv["fused"].shape)
             ops.deconv_dgrad(dz, W[r["conv"]], s, d_fused)
             dx = self._buf("bwd.dx%d" % i, lv["x"].shape)
@@ -546,7 +569,7 @@ class W2CEngine:
                 dwp = self._zeroed(r["conv"] + ".dwp." + tag, 9 * cout * cin, torch.float32).view(9, cout, cin)
                 with self._on_side():
                     ops.conv_wgrad(r["x"], dz, 3, r["stride"], dwp)
-                    ops.unpack_conv_wgrad(dwp, cout, cin, 3, out=grads[r["conv"]])
+                    unpack.append(ops.conv_unpack_job(dwp, grads[r["conv"]]))
                 if k > 0:
                     dprev = self._buf("bwd.dprev.%s.b%d.%d" % (tag, i, k), r["x"].shape)
                     ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], dprev)
@@ -573,6 +596,8 @@ class W2CEngine:
                         r["mean"], r["invstd"], r["amap"], d_canvas, r["amax"], r["moments"], r["rows"], acc,
                         grads[pre + ".linear.weight"], grads[pre + ".norm.weight"], grads[pre + ".norm.bias"],
                         seg=r["seg"])
+        with self._on_side():  # ordered after every weight-gradient GEMM (and, through the fork, the main stream so far)
+            ops.unpack_wgrads_batched(self._job_table("unpack", unpack))
         if self.use_side_stream and self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
         return grads

@@ -81,6 +81,29 @@ int a2x_pack_deconv_weight(const float* w_iohw, int cin, int cout, int s, float*
 int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, float* dw_iohw, int accumulate,
                             a2x_stream_t stream);
 
+/* Batched forms (one launch per step instead of one per layer): device-resident job tables, <= 64 jobs, elem_begin =
+ * running sum of `elems`. kind 0 = conv (a = rows of this source, b = cin, kk = taps; the source's rows land at
+ * [row0, row0 + a) of the cout_pad-wide packed tensors, so several parameters can share one fused GEMM operand),
+ * kind 1 = deconv (a = cin, b = cout, kk = s*s), kind 2 = plain vector copy (pack: src -> f32 + row0; unpack: double
+ * sums[row0 + i] -> float dst[i]). */
+typedef struct {
+    const float* src;
+    float* f32;
+    void* f16;
+    float* d32;
+    void* d16;
+    int kind, a, b, kk, cout_pad, row0;
+    long long elem_begin, elems;
+} a2x_pack_job;
+typedef struct {
+    const void* src;
+    float* dst;
+    int kind, a, b, kk, cout_pad, row0;
+    long long elem_begin, elems;
+} a2x_unpack_job;
+int a2x_pack_weights_batched(const a2x_pack_job* jobs_dev, int njobs, long long total_elems, a2x_stream_t stream);
+int a2x_unpack_wgrads_batched(const a2x_unpack_job* jobs_dev, int njobs, long long total_elems, a2x_stream_t stream);
+
 /* y = act(scale[c] * conv(x, w) + shift[c]); scale/shift may be NULL.
  * stats != NULL (requires no scale/shift/relu): the epilogue also accumulates the BatchNorm batch statistics of the
  * raw output, stats[c] += sum, stats[cout + c] += sum of squares (doubles, caller zeroes) — no extra HBM pass. */
@@ -120,6 +143,12 @@ int a2x_bn_eval_affine(const float* gamma, const float* beta, const float* runni
 /* y = relu?(x*scale[c] + shift[c]) * mask[pixel]   (scale/shift/mask may be NULL; y->b16 != NULL -> split) */
 int a2x_affine_act(const float* x, int x_cs, const float* scale, const float* shift, int relu, const float* mask,
                    const a2x_output* y, long long npix, int C, a2x_stream_t stream);
+/* bn_finalize + affine_act in one pass (train mode): y = relu?(BN_batch(z)); publishes scale / shift / mean / invstd
+ * (read by the backward kernels) and applies `n_updates` running-statistics updates. sums = [sum, sum of squares]. */
+int a2x_bn_train_act(const float* z, int z_cs, const double* sums, double count, const float* gamma, const float* beta,
+                     float eps, float momentum, int n_updates, float* running_mean, float* running_var, float* scale,
+                     float* shift, float* mean_out, float* invstd_out, int relu, const a2x_output* y, long long npix,
+                     int C, a2x_stream_t stream);
 /* BN(train)+ReLU backward, pass 1: sums[c] += sum g, sums[C+c] += sum g*zhat with g = dy*(z*scale+shift > 0) */
 int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
                            const float* mean, const float* invstd, long long npix, int C, double* sums,

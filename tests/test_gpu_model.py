@@ -166,7 +166,7 @@ def test_graphed_step_matches_eager(small):
         for (n, pe), (_, pg) in zip(eager.named_parameters(), graphed.named_parameters()):
             if pe.grad is not None:
                 assert torch.allclose(pe.grad, pg.grad, rtol=1e-4, atol=1e-6 * float(pe.grad.abs().max()) + 1e-12), (step, n)
-    assert graphed.launches_per_step > 300
+    assert graphed.launches_per_step > 200
 
 
 def test_baseline_size_properties():
