@@ -1,0 +1,175 @@
+"""Host-side orchestration of the CoBEVT path (BASELINE config 4) on the C-ABI kernels:
+
+    voxels -> PillarVFE+scatter -> BEV backbone (once) -> shrink -> regroup (pad to L agents)
+           -> SwapFusionEncoder: depth x [LN -> window attention -> +res, LN -> FFN -> +res,
+                                          LN -> grid attention   -> +res, LN -> FFN -> +res]
+           -> mean over agents -> LN -> Linear -> detection heads
+
+Mirrors opencood/models/airv2x_cobevt.py:112-156 and cobevt_modules/swap_fusion_modules.py:130-280. The encoder half
+is shared with the Where2comm engine (same kernels); every nn.Linear is the 1x1 tcgen05 tap-GEMM (bf16x3 split, bias /
+GELU / residual add fused in the epilogue), LayerNorm and the window / grid attention are token kernels
+(csrc/transformer.cu). Forward only in this round (eval-mode parity); the backward of the transformer block is a
+"next" row.
+"""
+import torch
+
+from . import ops
+from .ops import Act
+from .w2c_engine import HEAD_PAD, W2CEngine
+
+
+class CoBEVTEngine(W2CEngine):
+    def __init__(self, args, device, precision="split3"):  # noqa: the Where2comm-specific checks do not apply
+        assert precision in ("split3", "tf32"), precision
+        self.args = args
+        self.device = torch.device(device)
+        self.split = precision == "split3"
+        self.precision = precision
+        bb = args["base_bev_backbone"]
+        self.layer_nums = list(bb["layer_nums"])
+        self.layer_strides = list(bb["layer_strides"])
+        self.num_filters = list(bb["num_filters"])
+        self.up_strides = list(bb["upsample_strides"])
+        self.up_filters = list(bb["num_upsample_filter"])
+        assert all(s == 2 for s in self.layer_strides), "backbone blocks must have stride 2"
+        sh = args["shrink_header"]
+        assert sh["use"] and list(sh["kernal_size"]) == [1] and list(sh["stride"]) == [1] and list(sh["padding"]) == [0], \
+            "only the airv2x shrink header (1x1 s1 + 3x3) is implemented"
+        assert not args.get("compression", 0), "NaiveCompressor (compression > 0) is not implemented"
+        self.c_cat = sum(self.up_filters)
+        self.c_shrink = sh["dim"][0]
+        self.A = args["anchor_number"]
+        self.K = args["num_class"]
+        assert args["obj_head"], "obj_head: false not implemented"
+        self.n_head = self.A * self.K + 7 * self.A + self.A
+        fa = args["fax_fusion"]
+        self.fa = fa
+        self.L = sum(args["max_cav"].values())
+        self.dim = fa["input_dim"]
+        assert self.dim == self.c_shrink and self.dim % fa["dim_head"] == 0
+        self.heads = self.dim // fa["dim_head"]
+        self.bufs = {}
+        self.saved = None
+        self.side = None
+        self.use_side_stream = False
+
+    # ------------------------------------------------------------------ weights (one batched pack per step)
+    def _linear_names(self):
+        names = []
+        for i in range(self.fa["depth"]):
+            p = "fusion_net.layers.%d" % i
+            for part in ("window", "grid"):
+                names += ["%s.%s_attention.fn.to_qkv.weight" % (p, part), "%s.%s_attention.fn.to_out.0.weight" % (p, part),
+                          "%s.%s_ffd.fn.net.0.weight" % (p, part), "%s.%s_ffd.fn.net.3.weight" % (p, part)]
+        return names + ["fusion_net.mlp_head.3.weight"]
+
+    def _pack_weights(self, P):
+        W, jobs = {}, []
+        for i, ln in enumerate(self.layer_nums):
+            for k in range(ln + 1):
+                name = "backbone.blocks.%d.%d.weight" % (i, 1 + 3 * k)
+                w = P[name]
+                co, ci = w.shape[0], w.shape[1]
+                W[name] = self._packed(name, (9, co, ci), (9, ci, co))
+                jobs.append(ops.conv_pack_job(w, W[name]))
+            name = "backbone.deblocks.%d.0.weight" % i
+            w = P[name]
+            s = self.up_strides[i]
+            ci, co = w.shape[0], w.shape[1]
+            W[name] = self._packed(name, (1, s * s * co, ci), (s * s, ci, co))
+            jobs.append(ops.deconv_pack_job(w, W[name]))
+        for idx, k in ((0, 1), (2, 3)):
+            name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
+            w = P[name]
+            co, ci = w.shape[0], w.shape[1]
+            W[name] = self._packed(name, (k * k, co, ci), (k * k, ci, co))
+            jobs.append(ops.conv_pack_job(w, W[name]))
+        for name in self._linear_names():  # nn.Linear [out, in] == 1x1 conv OIHW [out, in, 1, 1]
+            w = P[name]
+            co, ci = w.shape
+            W[name] = self._packed(name, (1, co, ci), (1, ci, co))
+            jobs.append(ops.conv_pack_job(w.view(co, ci, 1, 1), W[name]))
+        nc, nr = self.A * self.K, 7 * self.A
+        fresh = ("packed", "heads") not in self.bufs
+        hp = self._packed("heads", (1, HEAD_PAD, self.c_shrink), (1, self.c_shrink, HEAD_PAD))
+        hb = self._buf("heads.b", (HEAD_PAD,))
+        if fresh:
+            for t in (hp.f32, hp.f16, hp.d32, hp.d16, hb):
+                t.zero_()
+        for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+            jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0))
+            jobs.append(ops.copy_pack_job(P[name + ".bias"], hb, row0))
+        W["heads"] = hp
+        W["heads.bias"] = hb
+        ops.pack_weights_batched(self._job_table("pack", jobs))
+        return W
+
+    # ------------------------------------------------------------------ fusion network
+    def _attention(self, P, W, pre, X, key_mask, B, grid_mode, tag):
+        """x += to_out(attention(LN(x)))    (PreNormResidual(Attention), swap_fusion_modules.py:78-127)"""
+        n, h, w, d = X.shape
+        ln = self._act("fax.ln", X.shape)
+        ops.layernorm_fwd(X, P[pre + ".norm.weight"], P[pre + ".norm.bias"], ln)
+        qkv = self._buf("fax.qkv", (n, h, w, 3 * d))
+        ops.linear_fwd(ln, W[pre + ".fn.to_qkv.weight"], Act(qkv))
+        att = self._act("fax.att", X.shape)
+        ops.window_attention_fwd(qkv, P[pre + ".fn.relative_position_bias_table.weight"], key_mask, B, self.L, self.heads,
+                                 self.fa["dim_head"], self.fa["window_size"], grid_mode, att)
+        ops.linear_fwd(att, W[pre + ".fn.to_out.0.weight"], Act(X), accumulate=True)
+
+    def _ffn(self, P, W, pre, X):
+        """x += W2 gelu(W1 LN(x) + b1) + b2   (PreNormResidual(FeedForward), base_transformer.py:16-28)"""
+        ln = self._act("fax.ln", X.shape)
+        ops.layernorm_fwd(X, P[pre + ".norm.weight"], P[pre + ".norm.bias"], ln)
+        hid = self._act("fax.hid", X.shape[:3] + (self.fa["mlp_dim"],))
+        ops.linear_fwd(ln, W[pre + ".fn.net.0.weight"], hid, bias=P[pre + ".fn.net.0.bias"], act=2)
+        ops.linear_fwd(hid, W[pre + ".fn.net.3.weight"], Act(X), bias=P[pre + ".fn.net.3.bias"], accumulate=True)
+
+    def fusion(self, P, W, feat, layout):
+        """feat: dense [N, h, w, C] shrunk maps (scene-major). Returns Act [B, h, w, C]."""
+        B = len(layout["record_len"])
+        n, h, w, d = feat.shape
+        X = self._buf("fax.x", (B * self.L, h, w, d))
+        ops.regroup(feat, layout["scene_start"], layout["scene_len"], B, self.L, Act(X))
+        key_mask = layout["key_mask"] if self.fa.get("mask", False) else None
+        for i in range(self.fa["depth"]):
+            p = "fusion_net.layers.%d" % i
+            self._attention(P, W, p + ".window_attention", X, key_mask, B, False, "w%d" % i)
+            self._ffn(P, W, p + ".window_ffd", X)
+            self._attention(P, W, p + ".grid_attention", X, key_mask, B, True, "g%d" % i)
+            self._ffn(P, W, p + ".grid_ffd", X)
+        m = self._act("fax.mean", (B, h, w, d))
+        ops.agent_mean_layernorm(X, B, self.L, P["fusion_net.mlp_head.2.weight"], P["fusion_net.mlp_head.2.bias"], m)
+        fused = self._act("fax.fused", (B, h, w, d))
+        ops.linear_fwd(m, W["fusion_net.mlp_head.3.weight"], fused, bias=P["fusion_net.mlp_head.3.bias"])
+        return fused
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, P, lidar, layout, training, k_list=None):
+        if training:
+            raise NotImplementedError("CoBEVT on the B200 kernels is forward-only (eval mode) in this round: the "
+                                      "transformer-fusion backward and dropout are not implemented")
+        self._begin_step()
+        W = self._pack_weights(P)
+        N = layout["n_total"]
+        canvas = self._encode(P, lidar, layout, False, None)
+        x = canvas
+        h2 = w2 = None
+        cat = None
+        for i in range(len(self.layer_nums)):
+            x = self._block(P, W, i, x, False, 0, "E", None)
+            if cat is None:
+                h2, w2 = x.shape[1], x.shape[2]
+                cat = self._act("E.cat", (N, h2, w2, self.c_cat))
+            c0 = sum(self.up_filters[:i])
+            self._deblock(P, W, i, x, cat.slice_c(c0, c0 + self.up_filters[i]), False, 0, "E", None)
+        y1 = self._act("E.s1", (N, h2, w2, self.c_shrink))
+        y2 = self._act("E.s2", (N, h2, w2, self.c_shrink), split=False)
+        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,
+                     shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
+        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, y2,
+                     shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
+        fused = self.fusion(P, W, y2.hi, layout)
+        heads = self._buf("heads.out", (fused.shape[0], h2, w2, HEAD_PAD))
+        ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
+        return heads, {}

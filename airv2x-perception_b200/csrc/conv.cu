@@ -479,9 +479,9 @@ __global__ void unpack_deconv_dw_kernel(const float* __restrict__ dwp, int cin, 
 
 // ------------------------------------------------------------------ batched re-layout (one launch per step)
 // The per-layer pack / unpack kernels above move a few hundred KB each: launch latency, not bandwidth, is what they
-// cost inside the step. These two kernels walk a device-resident job table instead (<= 64 jobs, staged in smem).
+// cost inside the step. These two kernels walk a device-resident job table instead (<= 128 jobs, staged in smem).
 __global__ void __launch_bounds__(256) pack_batched_kernel(const a2x_pack_job* __restrict__ jobs, int njobs) {
-    __shared__ a2x_pack_job sj[64];
+    __shared__ a2x_pack_job sj[128];
     for (int i = threadIdx.x; i < njobs; i += blockDim.x) sj[i] = jobs[i];
     __syncthreads();
     const long long total = sj[njobs - 1].elem_begin + sj[njobs - 1].elems;
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const a2x_pack_job* _
 }
 
 __global__ void __launch_bounds__(256) unpack_batched_kernel(const a2x_unpack_job* __restrict__ jobs, int njobs) {
-    __shared__ a2x_unpack_job sj[64];
+    __shared__ a2x_unpack_job sj[128];
     for (int i = threadIdx.x; i < njobs; i += blockDim.x) sj[i] = jobs[i];
     __syncthreads();
     const long long total = sj[njobs - 1].elem_begin + sj[njobs - 1].elems;
@@ -602,7 +602,7 @@ int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, fl
 }
 
 int a2x_pack_weights_batched(const a2x_pack_job* jobs_dev, int njobs, long long total_elems, a2x_stream_t stream) {
-    A2X_REQUIRE(jobs_dev && njobs > 0 && njobs <= 64 && total_elems > 0, "pack_weights_batched: bad args (<= 64 jobs)");
+    A2X_REQUIRE(jobs_dev && njobs > 0 && njobs <= 128 && total_elems > 0, "pack_weights_batched: bad args (<= 128 jobs)");
     pack_batched_kernel<<<grid_for(total_elems), 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
@@ -610,7 +610,7 @@ int a2x_pack_weights_batched(const a2x_pack_job* jobs_dev, int njobs, long long 
 }
 
 int a2x_unpack_wgrads_batched(const a2x_unpack_job* jobs_dev, int njobs, long long total_elems, a2x_stream_t stream) {
-    A2X_REQUIRE(jobs_dev && njobs > 0 && njobs <= 64 && total_elems > 0, "unpack_wgrads_batched: bad args (<= 64 jobs)");
+    A2X_REQUIRE(jobs_dev && njobs > 0 && njobs <= 128 && total_elems > 0, "unpack_wgrads_batched: bad args (<= 128 jobs)");
     unpack_batched_kernel<<<grid_for(total_elems), 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
@@ -619,15 +619,23 @@ int a2x_unpack_wgrads_batched(const a2x_unpack_job* jobs_dev, int njobs, long lo
 
 int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
                    const float* scale, const float* shift, int relu, double* stats, a2x_stream_t stream) {
+    return a2x_conv2d_fwd_ex(s, x, w, y, scale, shift, relu, 0, stats, stream);
+}
+
+int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
+                      const float* scale, const float* shift, int relu, int accumulate, double* stats,
+                      a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
+    A2X_REQUIRE(relu >= 0 && relu <= 2, "conv2d_fwd: activation must be 0 (none), 1 (ReLU) or 2 (GELU)");
     if (int r = check_operand(x, s->cin, "conv2d_fwd x")) return r;
     A2X_REQUIRE(w && w->w32 && y && y->hi && y->cs >= s->cout && y->cs % 4 == 0, "conv2d_fwd: bad weights/output");
     A2X_REQUIRE(!x->b16 || w->w16, "conv2d_fwd: split input needs bf16 weight planes");
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
     const int kk = s->ksize * s->ksize;
-    A2X_REQUIRE(!stats || (!scale && !shift && !relu), "conv2d_fwd: fused statistics are of the raw conv output");
+    A2X_REQUIRE(!stats || (!scale && !shift && !relu && !accumulate),
+                "conv2d_fwd: fused statistics are of the raw conv output");
     if (s->ksize == 3 && s->stride == 1 && g_debug[7] != 1)
-        return run_halo(x, s->n, s->h, s->w, s->cin, s->cout, w, +1, y, scale, shift, relu, 0, stats,
+        return run_halo(x, s->n, s->h, s->w, s->cin, s->cout, w, +1, y, scale, shift, relu, accumulate, stats,
                         (cudaStream_t)stream);
     TgParams p{};
     p.tw_log2 = pick_tw_log2(ho, wo, TG_BM, 4, 7);
@@ -647,10 +655,9 @@ int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weig
     p.scale = scale;
     p.shift = shift;
     p.relu = relu;
-    p.accumulate = 0;
+    p.accumulate = accumulate;
     p.stats = stats;
     p.stat_c = s->cout;
-    A2X_REQUIRE(!stats || (!scale && !shift && !relu), "conv2d_fwd: fused statistics are of the raw conv output");
     return run_tg(p, ho, wo, s->n, s->cout, (cudaStream_t)stream);
 }
 

@@ -58,8 +58,8 @@ struct TgParams {
     // epilogue
     const float* scale;  // per output channel (index = col % sub_c), may be null
     const float* shift;  // may be null
-    int relu;
-    int accumulate;  // out += result (single-plane outputs only)
+    int relu;        // activation: 0 none, 1 ReLU, 2 GELU (erf)
+    int accumulate;  // out += result (residual add; the fp32 plane holds the previous value)
     // fused BatchNorm batch statistics of the raw result: stats[ch] += sum, stats[stat_c + ch] += sum of squares
     double* stats;
     int stat_c;
@@ -148,9 +148,12 @@ __device__ __forceinline__ void tg_epilogue(const TgEpi& e, uint32_t tacc, int q
                     v[4 * i + 3] += prev.w;
                 }
             }
-            if (e.relu) {
+            if (e.relu == 1) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (e.relu == 2) {  // exact (erf) GELU: nn.GELU() of the transformer feed-forward layers
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i)

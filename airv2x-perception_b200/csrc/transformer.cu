@@ -1,0 +1,355 @@
+// Token-wise kernels of the transformer fusion networks (CoBEVT SwapFusionEncoder, V2X-ViT encoder) around the
+// tcgen05 linears (which are the 1x1 tap-GEMM): LayerNorm, 3-D window / grid attention with relative-position bias
+// and agent key mask, agent mean + LayerNorm, and regroup (zero-pad every scene to L agents).
+// All token tensors are fp32 NHWC: [B*L][H][W][C], so "tokens" are pixels and a window is a strided gather.
+//
+// Reference semantics:
+//   opencood/models/cobevt_modules/base_transformer.py:6-13            PreNormResidual (nn.LayerNorm, eps 1e-5)
+//   opencood/models/cobevt_modules/swap_fusion_modules.py:78-127       Attention.forward
+//   opencood/models/cobevt_modules/swap_fusion_modules.py:155-195      window "(x w1) (y w2)" / grid "(w1 x) (w2 y)"
+//   opencood/models/cobevt_modules/swap_fusion_modules.py:268-275      mean over agents + LayerNorm (+ Linear = GEMM)
+//   opencood/models/cobevt_modules/fuse_utils.py:13-63                 regroup
+#include "../../include/airv2x_b200.h"
+#include "a2x_host.h"
+#include "a2x_ptx.cuh"
+
+namespace a2x {
+
+static __host__ SplitOut tr_split(const a2x_output* o) {
+    SplitOut r;
+    r.hi = o->hi;
+    r.b16 = (__nv_bfloat16*)o->b16;
+    r.ps = o->b16_plane;
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// One warp per row; C = 32 * 4 * V channels (V float4 per lane). Two-pass statistics in registers like
+// torch.nn.functional.layer_norm (mean, then biased variance of the centred values).
+template <int V>
+__device__ __forceinline__ void ln_row(float4 (&x)[V], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float eps, int lane, int C) {
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) s += (x[v].x + x[v].y) + (x[v].z + x[v].w);
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        x[v].x -= mean; x[v].y -= mean; x[v].z -= mean; x[v].w -= mean;
+        q += (x[v].x * x[v].x + x[v].y * x[v].y) + (x[v].z * x[v].z + x[v].w * x[v].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int c = (v * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+        const float4 b = *reinterpret_cast<const float4*>(beta + c);
+        x[v].x = x[v].x * rstd * g.x + b.x;
+        x[v].y = x[v].y * rstd * g.y + b.y;
+        x[v].z = x[v].z * rstd * g.z + b.z;
+        x[v].w = x[v].w * rstd * g.w + b.w;
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int x_cs,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, SplitOut y, int y_cs,
+                                                        long long rows) {
+    constexpr int C = V * 128;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < rows; r += nwarps) {
+        float4 v[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = *reinterpret_cast<const float4*>(x + r * x_cs + (i * 32 + lane) * 4);
+        ln_row<V>(v, gamma, beta, eps, lane, C);
+#pragma unroll
+        for (int i = 0; i < V; ++i) store_split4(y, r * y_cs + (i * 32 + lane) * 4, v[i]);
+    }
+}
+
+// mean over the L agents of every (scene, pixel) — padded agents included, swap_fusion_modules.py:269-271 — then LN
+template <int V>
+__global__ void __launch_bounds__(256) agent_mean_ln_kernel(const float* __restrict__ x, int L, long long pix,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, SplitOut y,
+                                                            long long rows /* B * pix */) {
+    constexpr int C = V * 128;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < rows; r += nwarps) {
+        const long long b = r / pix, p = r - b * pix;
+        float4 acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < L; ++l) {
+            const float* row = x + ((b * L + l) * pix + p) * C;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float4 t = *reinterpret_cast<const float4*>(row + (i * 32 + lane) * 4);
+                acc[i].x += t.x; acc[i].y += t.y; acc[i].z += t.z; acc[i].w += t.w;
+            }
+        }
+        const float inv = 1.f / (float)L;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            acc[i].x *= inv; acc[i].y *= inv; acc[i].z *= inv; acc[i].w *= inv;
+        }
+        ln_row<V>(acc, gamma, beta, eps, lane, C);
+#pragma unroll
+        for (int i = 0; i < V; ++i) store_split4(y, r * C + (i * 32 + lane) * 4, acc[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- regroup
+// dst[b][l] = src[start_b + l] for l < len_b, zeros otherwise; each image is `img` floats (multiple of 4)
+__global__ void regroup_kernel(const float* __restrict__ src, const int* __restrict__ scene_start,
+                               const int* __restrict__ scene_len, int L, long long img4, SplitOut dst,
+                               long long total4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long slot = i / img4, e = i - slot * img4;
+        const int b = (int)(slot / L), l = (int)(slot - (long long)b * L);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < scene_len[b]) v = reinterpret_cast<const float4*>(src)[((long long)scene_start[b] + l) * img4 + e];
+        store_split4(dst, 4 * i, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- window attention
+// One CTA per (window, head). Tokens of a window: t = l * w * w + w1 * w + w2  ("(l w1 w2)"), n = L * w * w.
+//   window mode: pixel (x*w + w1, y*w + w2);   grid mode: pixel (w1*X + x, w2*Y + y)      (X = H/w, Y = W/w)
+// K and V of the window's head live in shared memory; every thread owns QPT query rows (q and the running output in
+// registers) and streams over the keys with an online softmax. sim = (q*scale).k + bias[rel(i,j)][head], keys of
+// padded agents (key_mask[b][l] == 0) are skipped (= -inf). fp32 throughout.
+struct WinAttParams {
+    const float* qkv;      // [B*L][H][W][3*D]   (q | k | v, each "(head dim_head)")
+    const float* bias;     // [(2L-1)(2w-1)^2][heads]
+    const int* key_mask;   // [B][L] or null
+    SplitOut out;          // [B*L][H][W][D]
+    int B, L, H, W, heads, w, grid_mode;
+    float scale;
+};
+
+template <int DH, int QPT>
+__global__ void __launch_bounds__(64) window_attention_kernel(const WinAttParams p) {
+    extern __shared__ float sm[];
+    const int ww = p.w * p.w;
+    const int n = p.L * ww;
+    float* sK = sm;                 // [n][DH]
+    float* sV = sK + n * DH;        // [n][DH]
+    float* sB = sV + n * DH;        // [(2L-1)(2w-1)^2] bias of this head
+    int* sTok = reinterpret_cast<int*>(sB + (2 * p.L - 1) * (2 * p.w - 1) * (2 * p.w - 1));  // [n] pixel-row index
+    const int D = p.heads * DH;
+    const int X = p.H / p.w, Y = p.W / p.w;
+    const int head = blockIdx.x % p.heads;
+    int win = blockIdx.x / p.heads;
+    const int y = win % Y;
+    win /= Y;
+    const int x = win % X;
+    const int b = win / X;
+
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int l = t / ww, r = t - l * ww;
+        const int w1 = r / p.w, w2 = r - w1 * p.w;
+        const int ph = p.grid_mode ? w1 * X + x : x * p.w + w1;
+        const int pw = p.grid_mode ? w2 * Y + y : y * p.w + w2;
+        sTok[t] = ((b * p.L + l) * p.H + ph) * p.W + pw;
+    }
+    const int nb = (2 * p.L - 1) * (2 * p.w - 1) * (2 * p.w - 1);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) sB[i] = p.bias[i * p.heads + head];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * (DH / 4); i += blockDim.x) {
+        const int t = i / (DH / 4), c = (i - t * (DH / 4)) * 4;
+        const float* row = p.qkv + (long long)sTok[t] * (3 * D) + head * DH + c;
+        *reinterpret_cast<float4*>(sK + t * DH + c) = *reinterpret_cast<const float4*>(row + D);
+        *reinterpret_cast<float4*>(sV + t * DH + c) = *reinterpret_cast<const float4*>(row + 2 * D);
+    }
+    __syncthreads();
+
+    const int s2 = 2 * p.w - 1;
+    for (int q0 = threadIdx.x * QPT; q0 < n; q0 += blockDim.x * QPT) {
+        float q[QPT][DH], acc[QPT][DH], m[QPT], den[QPT];
+        int ql[QPT], q1[QPT], q2[QPT];
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            const int t = min(q0 + u, n - 1);
+            const float* row = p.qkv + (long long)sTok[t] * (3 * D) + head * DH;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(row + c);
+                q[u][c] = v.x * p.scale; q[u][c + 1] = v.y * p.scale; q[u][c + 2] = v.z * p.scale; q[u][c + 3] = v.w * p.scale;
+            }
+#pragma unroll
+            for (int c = 0; c < DH; ++c) acc[u][c] = 0.f;
+            m[u] = -INFINITY;
+            den[u] = 0.f;
+            ql[u] = t / ww;
+            const int r = t - ql[u] * ww;
+            q1[u] = r / p.w;
+            q2[u] = r - q1[u] * p.w;
+        }
+        for (int lj = 0; lj < p.L; ++lj) {
+            if (p.key_mask != nullptr && p.key_mask[b * p.L + lj] == 0) continue;  // uniform over the CTA
+            for (int r = 0; r < ww; ++r) {
+                const int j = lj * ww + r;
+                const int k1 = r / p.w, k2 = r - k1 * p.w;
+                float kk[DH];
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(sK + j * DH + c);
+                    kk[c] = v.x; kk[c + 1] = v.y; kk[c + 2] = v.z; kk[c + 3] = v.w;
+                }
+                float s[QPT];
+#pragma unroll
+                for (int u = 0; u < QPT; ++u) {
+                    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < DH; c += 2) {
+                        d0 = fmaf(q[u][c], kk[c], d0);
+                        d1 = fmaf(q[u][c + 1], kk[c + 1], d1);
+                    }
+                    const int bi = ((ql[u] - lj + p.L - 1) * s2 + (q1[u] - k1 + p.w - 1)) * s2 + (q2[u] - k2 + p.w - 1);
+                    s[u] = d0 + d1 + sB[bi];
+                }
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(sV + j * DH + c);
+                    kk[c] = v.x; kk[c + 1] = v.y; kk[c + 2] = v.z; kk[c + 3] = v.w;
+                }
+#pragma unroll
+                for (int u = 0; u < QPT; ++u) {
+                    const float mn = fmaxf(m[u], s[u]);
+                    const float corr = __expf(m[u] - mn);  // exp(-inf) = 0 on the first key
+                    const float e = __expf(s[u] - mn);
+                    den[u] = den[u] * corr + e;
+#pragma unroll
+                    for (int c = 0; c < DH; ++c) acc[u][c] = fmaf(acc[u][c], corr, e * kk[c]);
+                    m[u] = mn;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            if (q0 + u >= n) break;
+            const float inv = 1.f / den[u];
+            const long long off = (long long)sTok[q0 + u] * D + head * DH;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4)
+                store_split4(p.out, off + c,
+                             make_float4(acc[u][c] * inv, acc[u][c + 1] * inv, acc[u][c + 2] * inv, acc[u][c + 3] * inv));
+        }
+    }
+}
+
+static int row_grid(long long rows) {
+    long long b = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace a2x
+
+using namespace a2x;
+
+extern "C" {
+
+int a2x_layernorm_fwd(const float* x, int x_cs, long long rows, int C, const float* gamma, const float* beta, float eps,
+                      const a2x_output* y, a2x_stream_t stream) {
+    A2X_REQUIRE(x && gamma && beta && y && y->hi && rows > 0 && x_cs >= C && y->cs >= C, "layernorm_fwd: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = row_grid(rows);
+    if (C == 128) layernorm_kernel<1><<<g, 256, 0, st>>>(x, x_cs, gamma, beta, eps, tr_split(y), y->cs, rows);
+    else if (C == 256) layernorm_kernel<2><<<g, 256, 0, st>>>(x, x_cs, gamma, beta, eps, tr_split(y), y->cs, rows);
+    else if (C == 384) layernorm_kernel<3><<<g, 256, 0, st>>>(x, x_cs, gamma, beta, eps, tr_split(y), y->cs, rows);
+    else if (C == 512) layernorm_kernel<4><<<g, 256, 0, st>>>(x, x_cs, gamma, beta, eps, tr_split(y), y->cs, rows);
+    else {
+        set_error("layernorm_fwd: channel count %d not in {128, 256, 384, 512}", C);
+        return 1;
+    }
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_agent_mean_layernorm(const float* x, int B, int L, long long pix, int C, const float* gamma, const float* beta,
+                             float eps, const a2x_output* y, a2x_stream_t stream) {
+    A2X_REQUIRE(x && gamma && beta && y && y->hi && B > 0 && L > 0 && pix > 0 && y->cs == C,
+                "agent_mean_layernorm: bad args (dense output expected)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)B * pix;
+    const int g = row_grid(rows);
+    if (C == 128) agent_mean_ln_kernel<1><<<g, 256, 0, st>>>(x, L, pix, gamma, beta, eps, tr_split(y), rows);
+    else if (C == 256) agent_mean_ln_kernel<2><<<g, 256, 0, st>>>(x, L, pix, gamma, beta, eps, tr_split(y), rows);
+    else if (C == 384) agent_mean_ln_kernel<3><<<g, 256, 0, st>>>(x, L, pix, gamma, beta, eps, tr_split(y), rows);
+    else if (C == 512) agent_mean_ln_kernel<4><<<g, 256, 0, st>>>(x, L, pix, gamma, beta, eps, tr_split(y), rows);
+    else {
+        set_error("agent_mean_layernorm: channel count %d not in {128, 256, 384, 512}", C);
+        return 1;
+    }
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_regroup(const float* src, const int* scene_start, const int* scene_len, int B, int L, long long img_elems,
+                const a2x_output* dst, a2x_stream_t stream) {
+    A2X_REQUIRE(src && scene_start && scene_len && dst && dst->hi && B > 0 && L > 0 && img_elems > 0 && img_elems % 4 == 0,
+                "regroup: bad args (image size must be a multiple of 4 floats)");
+    const long long total4 = (long long)B * L * (img_elems / 4);
+    long long blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    regroup_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, scene_start, scene_len, L, img_elems / 4,
+                                                                 tr_split(dst), total4);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const int* key_mask, int B, int L, int H, int W,
+                             int heads, int dim_head, int window, int grid_mode, float scale, const a2x_output* out,
+                             a2x_stream_t stream) {
+    A2X_REQUIRE(qkv && bias_table && out && out->hi && B > 0 && L > 0 && heads > 0 && window > 0,
+                "window_attention_fwd: bad args");
+    A2X_REQUIRE(H % window == 0 && W % window == 0, "window_attention_fwd: H, W must be multiples of the window");
+    A2X_REQUIRE(out->cs == heads * dim_head, "window_attention_fwd: dense [.., heads*dim_head] output expected");
+    WinAttParams p;
+    p.qkv = qkv; p.bias = bias_table; p.key_mask = key_mask; p.out = tr_split(out);
+    p.B = B; p.L = L; p.H = H; p.W = W; p.heads = heads; p.w = window; p.grid_mode = grid_mode; p.scale = scale;
+    const int n = L * window * window;
+    const int nb = (2 * L - 1) * (2 * window - 1) * (2 * window - 1);
+    const size_t smem = (size_t)(2 * n * dim_head + nb + n) * sizeof(float);
+    A2X_REQUIRE(smem <= 200 * 1024, "window_attention_fwd: window of %d tokens does not fit shared memory", n);
+    const long long grid = (long long)B * (H / window) * (W / window) * heads;
+    cudaStream_t st = (cudaStream_t)stream;
+#define A2X_WA(DH, QPT)                                                                                         \
+    do {                                                                                                        \
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<DH, QPT>,                                   \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        window_attention_kernel<DH, QPT><<<(unsigned)grid, 64, smem, st>>>(p);                                  \
+    } while (0)
+    if (dim_head == 16) A2X_WA(16, 2);
+    else if (dim_head == 32) A2X_WA(32, 2);
+    else if (dim_head == 64) A2X_WA(64, 1);
+    else {
+        set_error("window_attention_fwd: dim_head %d not in {16, 32, 64}", dim_head);
+        return 1;
+    }
+#undef A2X_WA
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

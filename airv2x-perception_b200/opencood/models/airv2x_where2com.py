@@ -248,6 +248,8 @@ class Airv2xWhere2com(nn.Module):
     # ------------------------------------------------------------------ reference-facing API
     def forward(self, data_dict):
         dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("Airv2xWhere2com (B200) needs its parameters on a CUDA device; there is no CPU path")
         layout = self._layout(data_dict, dev)
         lidar = self._lidar(data_dict, dev, layout)
         B = len(layout["record_len"])

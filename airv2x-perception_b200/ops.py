@@ -138,7 +138,7 @@ class JobTable:
     """A device-resident job table (uploaded once per distinct set of pointers)."""
 
     def __init__(self, jobs, device):
-        assert 0 < len(jobs) <= 64, "at most 64 jobs per batched launch"
+        assert 0 < len(jobs) <= 128, "at most 128 jobs per batched launch"
         pos = 0
         for j in jobs:
             j.elem_begin = pos
@@ -217,14 +217,75 @@ split_tf32 = split
 
 
 # split-aware conv family ------------------------------------------------------------------------------------
-def conv_fwd(x, w, k, stride, out, scale=None, shift=None, relu=False, stats=None):
-    """x, out: Act; w: PackedW"""
+def conv_fwd(x, w, k, stride, out, scale=None, shift=None, relu=False, stats=None, accumulate=False):
+    """x, out: Act; w: PackedW. relu: False/0 none, True/1 ReLU, 2 GELU(erf). accumulate: out += result (residual)."""
     n, h, ww, cin = x.shape
     cout = w.f32.shape[1]
     sh = _shape(n, h, ww, cin, cout, k, stride)
-    call("a2x_conv2d_fwd", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _op(out), _ptr(scale), _ptr(shift),
-         c_int(int(relu)), _ptr(stats), stream_ptr())
+    call("a2x_conv2d_fwd_ex", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _op(out), _ptr(scale), _ptr(shift),
+         c_int(int(relu)), c_int(int(accumulate)), _ptr(stats), stream_ptr())
     return out
+
+
+def linear_fwd(x, w, out, bias=None, act=0, accumulate=False):
+    """token-wise nn.Linear on an NHWC token tensor = 1x1 tap-GEMM: out = act(x W^T + bias (+ out))"""
+    return conv_fwd(x, w, 1, 1, out, shift=bias, relu=act, accumulate=accumulate)
+
+
+# transformer fusion token kernels --------------------------------------------------------------------------------
+def _rows(t):
+    return t.shape[0] * t.shape[1] * t.shape[2]
+
+
+def layernorm_fwd(x, gamma, beta, out, eps=1e-5):
+    """x: NHWC tensor; out: Act"""
+    call("a2x_layernorm_fwd", _ptr(x), c_int(_cs(x)), c_ll(_rows(x)), c_int(x.shape[3]), _ptr(gamma), _ptr(beta), c_f(eps),
+         _op(out), stream_ptr())
+    return out
+
+
+def agent_mean_layernorm(x, B, L, gamma, beta, out, eps=1e-5):
+    """x: dense [B*L, H, W, C]; out: Act [B, H, W, C]"""
+    assert x.is_contiguous() and x.shape[0] == B * L
+    call("a2x_agent_mean_layernorm", _ptr(x), c_int(B), c_int(L), c_ll(x.shape[1] * x.shape[2]), c_int(x.shape[3]),
+         _ptr(gamma), _ptr(beta), c_f(eps), _op(out), stream_ptr())
+    return out
+
+
+def regroup(src, scene_start, scene_len, B, L, out):
+    """src: dense [N, H, W, C]; out: Act [B*L, H, W, C] (zero padded agents)"""
+    assert src.is_contiguous() and out.hi.is_contiguous()
+    call("a2x_regroup", _ptr(src), _ptr(scene_start), _ptr(scene_len), c_int(B), c_int(L),
+         c_ll(src.shape[1] * src.shape[2] * src.shape[3]), _op(out), stream_ptr())
+    return out
+
+
+def window_attention_fwd(qkv, bias_table, key_mask, B, L, heads, dim_head, window, grid_mode, out):
+    """qkv: dense [B*L, H, W, 3*heads*dim_head]; out: Act [B*L, H, W, heads*dim_head]"""
+    assert qkv.is_contiguous() and out.hi.is_contiguous()
+    _, H, W, _ = qkv.shape
+    call("a2x_window_attention_fwd", _ptr(qkv), _ptr(bias_table), _ptr(key_mask), c_int(B), c_int(L), c_int(H), c_int(W),
+         c_int(heads), c_int(dim_head), c_int(window), c_int(int(grid_mode)), c_f(dim_head ** -0.5), _op(out),
+         stream_ptr())
+    return out
+
+
+def warp_affine_fwd(src, theta, out, align_corners=False, nearest=False):
+    """src: NHWC [n, hi, wi, c]; theta: [n, 2, 3] f32; out: Act [n, ho, wo, c]"""
+    n, hi, wi, c = src.shape
+    _, ho, wo, _ = out.shape
+    call("a2x_warp_affine_fwd", _ptr(src), c_int(_cs(src)), _ptr(theta.contiguous()), c_int(n), c_int(hi), c_int(wi),
+         c_int(c), c_int(ho), c_int(wo), c_int(int(align_corners)), c_int(int(nearest)), _op(out), stream_ptr())
+    return out
+
+
+def warp_affine_bwd(dout, theta, dsrc, align_corners=False):
+    """dsrc (zeroed by the caller) += bilinear^T dout"""
+    n, hi, wi, c = dsrc.shape
+    _, ho, wo, _ = dout.shape
+    call("a2x_warp_affine_bwd", _ptr(dout), c_int(_cs(dout)), _ptr(theta.contiguous()), c_int(n), c_int(hi), c_int(wi),
+         c_int(c), c_int(ho), c_int(wo), c_int(int(align_corners)), _ptr(dsrc), c_int(_cs(dsrc)), stream_ptr())
+    return dsrc
 
 
 def conv_dgrad(dy, w, k, stride, dx, accumulate=False):

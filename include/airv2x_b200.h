@@ -81,7 +81,7 @@ int a2x_pack_deconv_weight(const float* w_iohw, int cin, int cout, int s, float*
 int a2x_unpack_deconv_wgrad(const float* dw_packed, int cin, int cout, int s, float* dw_iohw, int accumulate,
                             a2x_stream_t stream);
 
-/* Batched forms (one launch per step instead of one per layer): device-resident job tables, <= 64 jobs, elem_begin =
+/* Batched forms (one launch per step instead of one per layer): device-resident job tables, <= 128 jobs, elem_begin =
  * running sum of `elems`. kind 0 = conv (a = rows of this source, b = cin, kk = taps; the source's rows land at
  * [row0, row0 + a) of the cout_pad-wide packed tensors, so several parameters can share one fused GEMM operand),
  * kind 1 = deconv (a = cin, b = cout, kk = s*s), kind 2 = plain vector copy (pack: src -> f32 + row0; unpack: double
@@ -109,6 +109,12 @@ int a2x_unpack_wgrads_batched(const a2x_unpack_job* jobs_dev, int njobs, long lo
  * raw output, stats[c] += sum, stats[cout + c] += sum of squares (doubles, caller zeroes) — no extra HBM pass. */
 int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
                    const float* scale, const float* shift, int relu, double* stats, a2x_stream_t stream);
+/* Same with act in {0 none, 1 ReLU, 2 GELU(erf)} and accumulate != 0: y = act(scale*conv + shift + y_previous)
+ * (residual add in the epilogue). With ksize == 1 this is the token-wise nn.Linear of the transformer fusion
+ * networks (cobevt_modules/swap_fusion_modules.py:40-45, base_transformer.py:16-28): rows = n*h*w tokens. */
+int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
+                      const float* scale, const float* shift, int act, int accumulate, double* stats,
+                      a2x_stream_t stream);
 /* dx (+)= conv_transpose(dy, w)   (dx: fp32 NHWC, pixel stride dx_cs) */
 int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
                      int accumulate, a2x_stream_t stream);
@@ -126,6 +132,34 @@ int a2x_deconv_wgrad(const a2x_conv_shape* s, const a2x_operand* x, const a2x_op
 /* ---------------------------------------------------------------- operand split
  * hi = x, b16 = (bf16(x), bf16(x - bf16(x)))  (n multiple of 4; out->cs ignored) */
 int a2x_split(const float* x, long long n, const a2x_output* out, a2x_stream_t stream);
+
+/* ---------------------------------------------------------------- transformer fusion (CoBEVT / V2X-ViT) token kernels
+ * Token tensors are fp32 NHWC [B*L][H][W][C]. Replace nn.LayerNorm (cobevt_modules/base_transformer.py:6-13),
+ * Attention.forward (cobevt_modules/swap_fusion_modules.py:78-127) with its window "(x w1) (y w2)" / grid
+ * "(w1 x) (w2 y)" partitions (:155-195), the agent mean + LayerNorm of the mlp head (:268-275) and regroup
+ * (cobevt_modules/fuse_utils.py:13-63). */
+int a2x_layernorm_fwd(const float* x, int x_cs, long long rows, int C, const float* gamma, const float* beta, float eps,
+                      const a2x_output* y, a2x_stream_t stream);
+/* y[b][p][:] = LayerNorm(mean_l x[b][l][p][:])  — padded agents are part of the mean, as in the reference */
+int a2x_agent_mean_layernorm(const float* x, int B, int L, long long pix, int C, const float* gamma, const float* beta,
+                             float eps, const a2x_output* y, a2x_stream_t stream);
+/* dst[b][l] = src[scene_start[b] + l] (l < scene_len[b]) else zeros; images of img_elems floats */
+int a2x_regroup(const float* src, const int* scene_start, const int* scene_len, int B, int L, long long img_elems,
+                const a2x_output* dst, a2x_stream_t stream);
+/* qkv: [B*L][H][W][3*heads*dim_head] (q | k | v); bias_table: [(2L-1)(2w-1)^2][heads]; key_mask: int32 [B][L] or NULL;
+ * out: dense [B*L][H][W][heads*dim_head]. softmax(q*scale . k + bias) v per (window | grid cell, head). */
+int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const int* key_mask, int B, int L, int H, int W,
+                             int heads, int dim_head, int window, int grid_mode, float scale, const a2x_output* out,
+                             a2x_stream_t stream);
+
+/* ---------------------------------------------------------------- ego-warp (affine bilinear resampling, NHWC)
+ * warp_affine_simple = F.affine_grid + F.grid_sample(bilinear | nearest, zeros padding)
+ * (common_modules/torch_transformation_utils.py:327-334); theta: [n][2][3] normalised matrices. */
+int a2x_warp_affine_fwd(const float* src, int src_cs, const float* theta, int n, int hi, int wi, int c, int ho, int wo,
+                        int align_corners, int nearest, const a2x_output* dst, a2x_stream_t stream);
+/* dsrc += bilinear^T dout (caller zeroes dsrc) */
+int a2x_warp_affine_bwd(const float* dout, int dout_cs, const float* theta, int n, int hi, int wi, int c, int ho, int wo,
+                        int align_corners, float* dsrc, int dsrc_cs, a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- BatchNorm / ReLU / masks (HBM-bound)
  * Replace nn.BatchNorm2d(eps 1e-3, momentum 0.01) + nn.ReLU and their autograd

@@ -1,0 +1,133 @@
+"""TEST INFRASTRUCTURE ONLY: CPU restatement (torch fp32) of the reference's CoBEVT path, BASELINE config 4
+(`airv2x_intermediate_cobevt.yaml`). Only tests/, __graft_entry__.smoke() and scripts/ may import it; the product
+path never does. Pinned against the REAL reference by scripts/make_golden_cobevt.py (differences 0.0 in eval mode).
+
+Follows, function by function:
+  opencood/models/airv2x_cobevt.py:112-156                      model forward
+  opencood/models/cobevt_modules/fuse_utils.py:13-63            regroup (zero-pad every scene to L agents + mask)
+  opencood/models/cobevt_modules/swap_fusion_modules.py:14-127  Attention (3-D window attention, rel-pos bias, key mask)
+  opencood/models/cobevt_modules/swap_fusion_modules.py:130-195 SwapFusionBlockMask (window attn, FFN, grid attn, FFN)
+  opencood/models/cobevt_modules/swap_fusion_modules.py:233-280 SwapFusionEncoder (+ mean over agents, LN, Linear)
+  opencood/models/cobevt_modules/base_transformer.py:6-28       PreNormResidual, FeedForward (GELU)
+The encoder half (PillarVFE, scatter, backbone, shrink) is shared with oracle/w2c_oracle.py.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import w2c_oracle as O
+
+
+def regroup(x, record_len, L):
+    """fuse_utils.py:13-63: [sum n, C, H, W] -> [B, L, C, H, W] zero padded, mask [B, L]"""
+    outs, masks, pos = [], [], 0
+    for n in [int(v) for v in record_len]:
+        f = x[pos:pos + n]
+        pos += n
+        pad = torch.zeros(L - n, *f.shape[1:], dtype=f.dtype)
+        outs.append(torch.cat([f, pad], 0))
+        masks.append([1] * n + [0] * (L - n))
+    return torch.stack(outs), torch.tensor(masks)
+
+
+def relative_position_index(L, w):
+    """swap_fusion_modules.py:53-76"""
+    cd, ch, cw = torch.meshgrid(torch.arange(L), torch.arange(w), torch.arange(w), indexing="ij")
+    c = torch.stack([cd, ch, cw]).flatten(1)              # 3, n
+    rel = (c[:, :, None] - c[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[..., 0] += L - 1
+    rel[..., 1] += w - 1
+    rel[..., 2] += w - 1
+    rel[..., 0] *= (2 * w - 1) * (2 * w - 1)
+    rel[..., 1] *= 2 * w - 1
+    return rel.sum(-1)
+
+
+def window_attention(sd, pre, x, mask, dim_head):
+    """x: [b, L, X, Y, w1, w2, d] (already LayerNorm-ed); mask: [b, X, Y, w1, w2, 1, L]; :78-127"""
+    b, L, X, Y, w1, w2, d = x.shape
+    h = d // dim_head
+    t = x.permute(0, 2, 3, 1, 4, 5, 6).reshape(b * X * Y, L * w1 * w2, d)
+    q, k, v = F.linear(t, sd[pre + ".to_qkv.weight"]).chunk(3, -1)
+
+    def heads(z):
+        return z.reshape(z.shape[0], z.shape[1], h, dim_head).permute(0, 2, 1, 3)
+
+    q, k, v = heads(q) * dim_head ** -0.5, heads(k), heads(v)
+    sim = q @ k.transpose(-1, -2)
+    idx = sd.get(pre + ".relative_position_index")
+    if idx is None:
+        idx = relative_position_index(L, w1)
+    bias = F.embedding(idx, sd[pre + ".relative_position_bias_table.weight"])    # n, n, h
+    sim = sim + bias.permute(2, 0, 1)
+    if mask is not None:
+        m = mask.permute(0, 1, 2, 5, 6, 3, 4).reshape(b * X * Y, 1, 1, L * w1 * w2)   # (b x y) 1 1 (l w1 w2)
+        sim = sim.masked_fill(m == 0, -float("inf"))
+    out = sim.softmax(-1) @ v
+    out = out.permute(0, 2, 1, 3).reshape(b * X * Y, L, w1, w2, d)
+    out = F.linear(out, sd[pre + ".to_out.0.weight"])
+    return out.reshape(b, X, Y, L, w1, w2, d).permute(0, 3, 1, 2, 4, 5, 6)
+
+
+def feed_forward(sd, pre, x):
+    """base_transformer.py:16-28 (dropout is identity in eval / p handled by the caller in train)"""
+    x = F.gelu(F.linear(x, sd[pre + ".net.0.weight"], sd[pre + ".net.0.bias"]))
+    return F.linear(x, sd[pre + ".net.3.weight"], sd[pre + ".net.3.bias"])
+
+
+def _ln(sd, pre, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[pre + ".weight"], sd[pre + ".bias"], 1e-5)
+
+
+def swap_fusion_block(sd, pre, x, mask, w, dim_head):
+    """x: [b, L, d, H, W]; mask: [b, H, W, 1, L]; SwapFusionBlockMask.forward :155-195"""
+    b, L, d, H, W = x.shape
+    X, Y = H // w, W // w
+    # window partition: (x w1) (y w2)
+    xw = x.reshape(b, L, d, X, w, Y, w).permute(0, 1, 3, 5, 4, 6, 2)               # b L X Y w1 w2 d
+    mw = mask.reshape(b, X, w, Y, w, 1, L).permute(0, 1, 3, 2, 4, 5, 6) if mask is not None else None
+    xw = window_attention(sd, pre + ".window_attention.fn", _ln(sd, pre + ".window_attention.norm", xw), mw, dim_head) + xw
+    xw = feed_forward(sd, pre + ".window_ffd.fn", _ln(sd, pre + ".window_ffd.norm", xw)) + xw
+    x = xw.permute(0, 1, 6, 2, 4, 3, 5).reshape(b, L, d, H, W)
+    # grid partition: (w1 x) (w2 y)
+    xg = x.reshape(b, L, d, w, X, w, Y).permute(0, 1, 4, 6, 3, 5, 2)               # b L X Y w1 w2 d
+    mg = mask.reshape(b, w, X, w, Y, 1, L).permute(0, 2, 4, 1, 3, 5, 6) if mask is not None else None
+    xg = window_attention(sd, pre + ".grid_attention.fn", _ln(sd, pre + ".grid_attention.norm", xg), mg, dim_head) + xg
+    xg = feed_forward(sd, pre + ".grid_ffd.fn", _ln(sd, pre + ".grid_ffd.norm", xg)) + xg
+    return xg.permute(0, 1, 6, 4, 2, 5, 3).reshape(b, L, d, H, W)
+
+
+def swap_fusion_encoder(sd, fa, x, mask, pre="fusion_net", keep=None):
+    """SwapFusionEncoder.forward :277-280"""
+    for i in range(fa["depth"]):
+        x = swap_fusion_block(sd, "%s.layers.%d" % (pre, i), x, mask if fa.get("mask", False) else None,
+                              fa["window_size"], fa["dim_head"])
+        if keep is not None:
+            keep["block%d" % i] = x
+    x = x.mean(1).permute(0, 2, 3, 1)                                              # b h w d  (padded agents included)
+    x = _ln(sd, pre + ".mlp_head.2", x)
+    x = F.linear(x, sd[pre + ".mlp_head.3.weight"], sd[pre + ".mlp_head.3.bias"])
+    return x.permute(0, 3, 1, 2)
+
+
+def cobevt_forward(sd, args, data_dict, training=False, keep=None):
+    """models/airv2x_cobevt.py:112-156 (task == det; dropout = identity, i.e. eval mode or drop_out 0)."""
+    buffers = {}
+    sf, record_len = O.extract_features(sd, args, data_dict, training, buffers, keep)
+    feat = O.backbone_forward(sd, args["base_bev_backbone"], sf, training, buffers)
+    if args["shrink_header"]["use"]:
+        feat = O.shrink_conv(sd, args["shrink_header"], feat)
+    assert not args.get("compression", 0)
+    L = sum(args["max_cav"].values())
+    x, mask = regroup(feat, record_len.tolist(), L)
+    if keep is not None:
+        keep["regroup"] = x
+    H, W = x.shape[3], x.shape[4]
+    com_mask = mask[:, None, None, None, :].expand(-1, H, W, 1, -1)                 # b h w 1 l
+    fused = swap_fusion_encoder(sd, args["fax_fusion"], x, com_mask, keep=keep)
+    if keep is not None:
+        keep["fused_feature"] = fused
+    out = {"psm": F.conv2d(fused, sd["cls_head.weight"], sd["cls_head.bias"]),
+           "rm": F.conv2d(fused, sd["reg_head.weight"], sd["reg_head.bias"])}
+    if args["obj_head"]:
+        out["obj"] = F.conv2d(fused, sd["obj_head.weight"], sd["obj_head.bias"])
+    return out, buffers

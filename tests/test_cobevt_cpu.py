@@ -1,0 +1,66 @@
+"""CPU (-m "not gpu"): the CoBEVT oracle against the golden vectors recorded from the REAL reference, and the drop-in
+module's registry surface (class name, state_dict keys / shapes / parameter count)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+import cobevt_common as CC
+from oracle import cobevt_oracle as CO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model(args):
+    import a2x_import
+
+    M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+    return M.Airv2xCoBEVT(args)
+
+
+def test_oracle_matches_reference_golden():
+    cfg, gold = CC.load_small()
+    model = _model(cfg["model_args"])
+    sd = CC.golden_state_dict(model, gold)
+    dd = CC.golden_scene(cfg, gold)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        out, _ = CO.cobevt_forward(sd, cfg["model_args"], dd, training=False)
+    for k in ("psm", "rm", "obj"):
+        assert np.abs(out[k].numpy() - gold["eval_" + k]).max() < 1e-5, k
+    # fusion network alone, ragged agent mask (3 and 5 real agents of L = 7)
+    g = torch.Generator().manual_seed(int(gold["fusion_seed"]))
+    x = torch.randn(2, 7, 256, 8, 16, generator=g)
+    mask = torch.tensor([[1, 1, 1, 0, 0, 0, 0], [1, 1, 1, 1, 1, 0, 0]])
+    x = x * mask[:, :, None, None, None]
+    com = mask[:, None, None, None, :].expand(-1, 8, 16, 1, -1)
+    with torch.no_grad():
+        o = CO.swap_fusion_encoder(sd, cfg["model_args"]["fax_fusion"], x, com)
+    assert np.abs(o.numpy() - gold["fusion_out"]).max() < 1e-5
+
+
+def test_registry_surface_full_config():
+    """create_model's lookup rule (tools/train_utils.py:302-325) + the reference's parameter inventory"""
+    cfg = json.load(open(os.path.join(ROOT, "configs", "airv2x_intermediate_cobevt.json")))
+    import a2x_import
+
+    M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+    target = "airv2x_cobevt".replace("_", "")
+    cls = [v for k, v in vars(M).items() if k.lower() == target]
+    assert len(cls) == 1 and cls[0] is M.Airv2xCoBEVT
+    model = M.Airv2xCoBEVT(cfg["model_args"])
+    assert sum(p.numel() for p in model.parameters()) == 9741454
+    sd = model.state_dict()
+    assert sd["fusion_net.layers.0.window_attention.fn.to_qkv.weight"].shape == (768, 256)
+    assert sd["fusion_net.layers.2.grid_attention.fn.relative_position_bias_table.weight"].shape == (13 * 49, 8)
+    assert sd["fusion_net.layers.1.grid_ffd.fn.net.3.bias"].shape == (256,)
+    assert sd["fusion_net.mlp_head.3.weight"].shape == (256, 256)
+    assert torch.equal(sd["fusion_net.layers.0.window_attention.fn.relative_position_index"],
+                       CO.relative_position_index(7, 4))
+    try:
+        model(dict())
+    except Exception as e:  # no CPU path: must fail loudly, never fall back
+        assert "CUDA" in str(e) or "cuda" in str(e)
+    else:
+        raise AssertionError("forward on CPU parameters must raise")

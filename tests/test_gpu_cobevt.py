@@ -1,0 +1,188 @@
+"""GPU (-m gpu): the transformer-fusion token kernels and the drop-in Airv2xCoBEVT (BASELINE config 4) against the
+oracle (pinned bit-exact to the real reference) and the recorded golden vectors.
+Tolerance (north_star): logits max-abs <= 1e-3 (fp32 reference); per-kernel 1e-5 relative-to-max (fp32 kernels),
+5e-5 for the bf16x3 tensor-core linears."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cobevt_common as CC
+from oracle import cobevt_oracle as CO
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import a2x_import
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return a2x_import.pkg("ops")
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def test_layernorm_and_agent_mean(ops):
+    g = torch.Generator().manual_seed(0)
+    for C in (128, 256, 384):
+        x = (torch.randn(3, 5, 7, C, generator=g) * 3 + 1).cuda()
+        gam, bet = torch.rand(C, generator=g).cuda() + 0.5, torch.randn(C, generator=g).cuda()
+        out = ops.Act.empty(x.shape, "cuda", True)
+        ops.layernorm_fwd(x, gam, bet, out)
+        ref = F.layer_norm(x, (C,), gam, bet, 1e-5)
+        assert rel(out.hi, ref) < 1e-5
+        assert torch.equal(out.b16[0], out.hi.to(torch.bfloat16))
+    B, L, C = 2, 3, 256
+    x = torch.randn(B * L, 4, 6, C, generator=g).cuda()
+    gam, bet = torch.rand(C, generator=g).cuda() + 0.5, torch.randn(C, generator=g).cuda()
+    out = ops.Act.empty((B, 4, 6, C), "cuda", True)
+    ops.agent_mean_layernorm(x, B, L, gam, bet, out)
+    ref = F.layer_norm(x.view(B, L, 4, 6, C).mean(1), (C,), gam, bet, 1e-5)
+    assert rel(out.hi, ref) < 1e-5
+
+
+def test_regroup(ops):
+    g = torch.Generator().manual_seed(1)
+    src = torch.randn(5, 3, 4, 64, generator=g).cuda()
+    start = torch.tensor([0, 2], dtype=torch.int32).cuda()
+    length = torch.tensor([2, 3], dtype=torch.int32).cuda()
+    out = ops.Act(torch.full((2 * 4, 3, 4, 64), 7.0, device="cuda"))
+    ops.regroup(src, start, length, 2, 4, out)
+    want, mask = CO.regroup(src.cpu().permute(0, 3, 1, 2), [2, 3], 4)
+    assert torch.equal(out.hi.cpu().view(2, 4, 3, 4, 64), want.permute(0, 1, 3, 4, 2))
+    assert mask.tolist() == [[1, 1, 0, 0], [1, 1, 1, 0]]
+
+
+@pytest.mark.parametrize("case", [(2, 7, 8, 16, 8, 32, 4), (1, 3, 8, 8, 4, 64, 2), (1, 5, 4, 12, 16, 16, 4)])
+@pytest.mark.parametrize("grid_mode", [False, True])
+def test_window_attention(ops, case, grid_mode):
+    """softmax(q*scale k^T + rel-pos bias, masked keys) v per window / grid cell == Attention.forward without the
+    linears (cobevt_modules/swap_fusion_modules.py:78-127)"""
+    B, L, H, W, heads, dh, w = case
+    D = heads * dh
+    g = torch.Generator().manual_seed(2)
+    qkv = torch.randn(B * L, H, W, 3 * D, generator=g)
+    table = torch.randn((2 * L - 1) * (2 * w - 1) ** 2, heads, generator=g)
+    mask = torch.ones(B, L, dtype=torch.int32)
+    mask[0, L - 1] = 0
+    if B > 1:
+        mask[1, 1:] = 0
+    out = ops.Act.empty((B * L, H, W, D), "cuda", True)
+    ops.window_attention_fwd(qkv.cuda(), table.cuda(), mask.cuda(), B, L, heads, dh, w, grid_mode, out)
+    # reference: identity linears around the oracle's attention core
+    X, Y = H // w, W // w
+    t = qkv.view(B, L, H, W, 3 * D)
+    if grid_mode:
+        t = t.view(B, L, w, X, w, Y, 3 * D).permute(0, 1, 3, 5, 2, 4, 6)
+    else:
+        t = t.view(B, L, X, w, Y, w, 3 * D).permute(0, 1, 2, 4, 3, 5, 6)
+    tok = t.permute(0, 2, 3, 1, 4, 5, 6).reshape(B * X * Y, L * w * w, 3 * D)
+    q, k, v = tok.chunk(3, -1)
+    hs = lambda z: z.reshape(z.shape[0], z.shape[1], heads, dh).permute(0, 2, 1, 3)
+    sim = (hs(q) * dh ** -0.5) @ hs(k).transpose(-1, -2)
+    sim = sim + F.embedding(CO.relative_position_index(L, w), table).permute(2, 0, 1)
+    km = mask.view(B, 1, 1, L, 1, 1).expand(B, X, Y, L, w, w).reshape(B * X * Y, 1, 1, L * w * w)
+    sim = sim.masked_fill(km == 0, -float("inf"))
+    o = (sim.softmax(-1) @ hs(v)).permute(0, 2, 1, 3).reshape(B, X, Y, L, w, w, D)
+    if grid_mode:
+        ref = o.permute(0, 3, 4, 1, 5, 2, 6).reshape(B * L, H, W, D)
+    else:
+        ref = o.permute(0, 3, 1, 4, 2, 5, 6).reshape(B * L, H, W, D)
+    assert rel(out.hi.cpu(), ref) < 2e-5
+
+
+def test_linear_gelu_residual(ops):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 6, 10, 256, generator=g).cuda()
+    w1, b1 = (torch.randn(512, 256, generator=g) * 0.05).cuda(), torch.randn(512, generator=g).cuda() * 0.1
+    w2, b2 = (torch.randn(256, 512, generator=g) * 0.05).cuda(), torch.randn(256, generator=g).cuda() * 0.1
+    res = torch.randn(2, 6, 10, 256, generator=g).cuda()
+    hid = ops.Act.empty((2, 6, 10, 512), "cuda", True)
+    ops.linear_fwd(ops.split(x), ops.pack_conv_weight(w1.view(512, 256, 1, 1)), hid, bias=b1, act=2)
+    want_h = F.gelu(F.linear(x, w1, b1))
+    assert rel(hid.hi, want_h) < 5e-5
+    y = ops.Act(res.clone())
+    ops.linear_fwd(hid, ops.pack_conv_weight(w2.view(256, 512, 1, 1)), y, bias=b2, accumulate=True)
+    assert rel(y.hi, res + F.linear(want_h, w2, b2)) < 5e-5
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_warp_affine(ops, align):
+    """ego-warp == F.affine_grid + F.grid_sample (warp_affine_simple, torch_transformation_utils.py:327-334)"""
+    g = torch.Generator().manual_seed(4)
+    n, C, H, W = 3, 64, 20, 44
+    x = torch.randn(n, C, H, W, generator=g).cuda().requires_grad_(True)
+    ang = torch.tensor([0.0, 0.3, -2.1])
+    theta = torch.stack([torch.stack([torch.cos(ang), -torch.sin(ang) * H / W, torch.tensor([0.0, 0.2, -0.4])], -1),
+                         torch.stack([torch.sin(ang) * W / H, torch.cos(ang), torch.tensor([0.0, -0.1, 0.3])], -1)], 1).cuda()
+    grid = F.affine_grid(theta, [n, C, H, W], align_corners=align)
+    ref = F.grid_sample(x, grid, align_corners=align)
+    dout = torch.randn(n, C, H, W, generator=g).cuda()
+    ref.backward(dout)
+    xn = x.detach().permute(0, 2, 3, 1).contiguous()
+    out = ops.Act.empty((n, H, W, C), "cuda", True)
+    ops.warp_affine_fwd(xn, theta, out, align_corners=align)
+    assert rel(out.hi, ref.detach().permute(0, 2, 3, 1)) < 1e-5
+    dsrc = torch.zeros_like(xn)
+    ops.warp_affine_bwd(dout.permute(0, 2, 3, 1).contiguous(), theta, dsrc, align_corners=align)
+    assert rel(dsrc, x.grad.permute(0, 2, 3, 1)) < 1e-5
+    # identity transform (proj_first) is an exact copy
+    eye = torch.tensor([[1.0, 0, 0], [0, 1.0, 0]]).repeat(n, 1, 1).cuda()
+    ops.warp_affine_fwd(xn, eye, out, align_corners=align)
+    assert rel(out.hi, xn) < 1e-5                                          # coordinates carry fp32 rounding
+    nn_ref = F.grid_sample(x.detach(), grid, mode="nearest", align_corners=align)
+    ops.warp_affine_fwd(xn, theta, out, align_corners=align, nearest=True)
+    assert float((out.hi != nn_ref.permute(0, 2, 3, 1)).float().mean()) < 1e-3   # ties at .5 may round differently
+
+
+@pytest.fixture(scope="module")
+def small():
+    import a2x_import
+
+    M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+    cfg, gold = CC.load_small()
+    model = M.Airv2xCoBEVT(cfg["model_args"])
+    sd = CC.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().eval()
+    return cfg, gold, model, sd
+
+
+def test_fusion_net_matches_reference_golden(small):
+    """SwapFusionEncoder alone on the seeded ragged input recorded from the real reference"""
+    cfg, gold, model, sd = small
+    g = torch.Generator().manual_seed(int(gold["fusion_seed"]))
+    x = torch.randn(2, 7, 256, 8, 16, generator=g)
+    mask = torch.tensor([[1, 1, 1, 0, 0, 0, 0], [1, 1, 1, 1, 1, 0, 0]])
+    x = x * mask[:, :, None, None, None]
+    feat = torch.cat([x[0, :3], x[1, :5]]).permute(0, 2, 3, 1).contiguous().cuda()     # dense scene-major maps, NHWC
+    eng = model.engine
+    P = model._param_dict()
+    eng._begin_step()
+    W = eng._pack_weights(P)
+    layout = {"record_len": [3, 5], "scene_start": torch.tensor([0, 3], dtype=torch.int32).cuda(),
+              "scene_len": torch.tensor([3, 5], dtype=torch.int32).cuda(), "key_mask": mask.to(torch.int32).cuda()}
+    fused = eng.fusion(P, W, feat, layout)
+    got = fused.hi.permute(0, 3, 1, 2).cpu().numpy()
+    assert np.abs(got - gold["fusion_out"]).max() < TOL
+
+
+def test_eval_matches_reference_golden(small):
+    import w2c_common as C
+
+    cfg, gold, model, sd = small
+    dd = CC.golden_scene(cfg, gold)
+    with torch.no_grad():
+        out = model(C.to_device(dd, "cuda"))
+    for k in ("psm", "rm", "obj"):
+        assert out[k].shape == gold["eval_" + k].shape
+        assert np.abs(out[k].cpu().numpy() - gold["eval_" + k]).max() < TOL, k
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(C.to_device(dd, "cuda"))
+    model.eval()
