@@ -125,12 +125,17 @@ class CoBEVTEngine(W2CEngine):
         ops.linear_fwd(ln, W[pre + ".fn.net.0.weight"], hid, bias=P[pre + ".fn.net.0.bias"], act=2)
         ops.linear_fwd(hid, W[pre + ".fn.net.3.weight"], Act(X), bias=P[pre + ".fn.net.3.bias"], accumulate=True)
 
-    def fusion(self, P, W, feat, layout):
-        """feat: dense [N, h, w, C] shrunk maps (scene-major). Returns Act [B, h, w, C]."""
+    def fusion(self, P, W, feat, layout, peer_ptrs=None):
+        """feat: dense [N, h, w, C] shrunk maps (scene-major). Returns Act [B, h, w, C].
+        peer_ptrs (agent-parallel mode): int64 device table of per-agent map pointers in (peer) GPU memory; the maps
+        are then pulled over NVLink inside the regroup kernel and `feat` only supplies the shape."""
         B = len(layout["record_len"])
         n, h, w, d = feat.shape
         X = self._buf("fax.x", (B * self.L, h, w, d))
-        ops.regroup(feat, layout["scene_start"], layout["scene_len"], B, self.L, Act(X))
+        if peer_ptrs is not None:
+            ops.regroup_ptrs(peer_ptrs, (h, w, d), layout["scene_start"], layout["scene_len"], B, self.L, Act(X))
+        else:
+            ops.regroup(feat, layout["scene_start"], layout["scene_len"], B, self.L, Act(X))
         key_mask = layout["key_mask"] if self.fa.get("mask", False) else None
         for i in range(self.fa["depth"]):
             p = "fusion_net.layers.%d" % i
@@ -145,12 +150,9 @@ class CoBEVTEngine(W2CEngine):
         return fused
 
     # ------------------------------------------------------------------ forward
-    def forward(self, P, lidar, layout, training, k_list=None):
-        if training:
-            raise NotImplementedError("CoBEVT on the B200 kernels is forward-only (eval mode) in this round: the "
-                                      "transformer-fusion backward and dropout are not implemented")
-        self._begin_step()
-        W = self._pack_weights(P)
+    def encode(self, P, W, lidar, layout, out=None):
+        """per-agent half of the path: voxels -> PillarVFE+scatter -> backbone -> shrink. Returns the dense
+        [N, h/2, w/2, C] shrunk maps (written into `out` if given, e.g. a symmetric-memory buffer peers read)."""
         N = layout["n_total"]
         canvas = self._encode(P, lidar, layout, False, None)
         x = canvas
@@ -164,12 +166,25 @@ class CoBEVTEngine(W2CEngine):
             c0 = sum(self.up_filters[:i])
             self._deblock(P, W, i, x, cat.slice_c(c0, c0 + self.up_filters[i]), False, 0, "E", None)
         y1 = self._act("E.s1", (N, h2, w2, self.c_shrink))
-        y2 = self._act("E.s2", (N, h2, w2, self.c_shrink), split=False)
+        y2 = out if out is not None else self._buf("E.s2", (N, h2, w2, self.c_shrink))
+        assert tuple(y2.shape) == (N, h2, w2, self.c_shrink)
         ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,
                      shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
-        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, y2,
+        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, Act(y2),
                      shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
-        fused = self.fusion(P, W, y2.hi, layout)
-        heads = self._buf("heads.out", (fused.shape[0], h2, w2, HEAD_PAD))
+        return y2
+
+    def fuse_heads(self, P, W, feat, layout, peer_ptrs=None):
+        fused = self.fusion(P, W, feat, layout, peer_ptrs)
+        heads = self._buf("heads.out", (fused.shape[0], feat.shape[1], feat.shape[2], HEAD_PAD))
         ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
-        return heads, {}
+        return heads
+
+    def forward(self, P, lidar, layout, training, k_list=None):
+        if training:
+            raise NotImplementedError("CoBEVT on the B200 kernels is forward-only (eval mode) in this round: the "
+                                      "transformer-fusion backward and dropout are not implemented")
+        self._begin_step()
+        W = self._pack_weights(P)
+        feat = self.encode(P, W, lidar, layout)
+        return self.fuse_heads(P, W, feat, layout), {}

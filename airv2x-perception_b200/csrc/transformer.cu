@@ -126,6 +126,28 @@ __global__ void regroup_kernel(const float* __restrict__ src, const int* __restr
     }
 }
 
+// Agent-parallel form (one agent per GPU): the source images are addressed through a device table of pointers, one per
+// agent, which may point into PEER GPUs' memory (NVLink P2P / symmetric memory). The all-gather of the shrunk BEV maps
+// is thereby fused into the regroup: every rank pulls each peer's map exactly once, straight into its slot of the
+// padded [B*L] token tensor — no intermediate gathered buffer, no separate collective launch.
+__global__ void regroup_ptrs_kernel(const float* const* __restrict__ src_ptrs, const int* __restrict__ scene_start,
+                                    const int* __restrict__ scene_len, int L, long long img4, SplitOut dst,
+                                    long long total4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long slot = i / img4, e = i - slot * img4;
+        const int b = (int)(slot / L), l = (int)(slot - (long long)b * L);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < scene_len[b]) {
+            const float4* src = reinterpret_cast<const float4*>(src_ptrs[scene_start[b] + l]);
+            asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "l"(src + e));  // peer memory: system-scope load, never served from a stale L1 line
+        }
+        store_split4(dst, 4 * i, v);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- window attention
 // One CTA per (window, head). Tokens of a window: t = l * w * w + w1 * w + w2  ("(l w1 w2)"), n = L * w * w.
 //   window mode: pixel (x*w + w1, y*w + w2);   grid mode: pixel (w1*X + x, w2*Y + y)      (X = H/w, Y = W/w)
@@ -312,6 +334,21 @@ int a2x_regroup(const float* src, const int* scene_start, const int* scene_len, 
     if (blocks > 148 * 16) blocks = 148 * 16;
     regroup_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, scene_start, scene_len, L, img_elems / 4,
                                                                  tr_split(dst), total4);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_regroup_ptrs(const float* const* src_ptrs_dev, const int* scene_start, const int* scene_len, int B, int L,
+                     long long img_elems, const a2x_output* dst, a2x_stream_t stream) {
+    A2X_REQUIRE(src_ptrs_dev && scene_start && scene_len && dst && dst->hi && B > 0 && L > 0 && img_elems > 0 &&
+                    img_elems % 4 == 0,
+                "regroup_ptrs: bad args (image size must be a multiple of 4 floats)");
+    const long long total4 = (long long)B * L * (img_elems / 4);
+    long long blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    regroup_ptrs_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src_ptrs_dev, scene_start, scene_len, L,
+                                                                      img_elems / 4, tr_split(dst), total4);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

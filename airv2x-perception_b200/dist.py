@@ -23,3 +23,106 @@ class GradAverager:
         dist.all_reduce(self.flat)
         self.flat.div_(dist.get_world_size())
         torch._foreach_copy_([g.view(-1) for g in grads], views)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Agent-parallel inference (BASELINE config 4): one agent per GPU. Everything up to the fusion boundary
+# (voxelise, PillarVFE, scatter, backbone, shrink) is per-agent independent; the path's only exchange is the gather of
+# the shrunk BEV maps. Two transports:
+#   "nccl": one all_gather_into_tensor of the fp32 maps, then the ordinary regroup;
+#   "peer": the maps live in symmetric memory and every rank's regroup kernel pulls each peer's map over NVLink
+#           directly into its slot of the padded token tensor (collective fused into the first consumer).
+# Both are exact: the fused output equals the single-GPU output bit for bit (same kernels, same operands).
+def agent_rank_plan(agent_types):
+    """agent_types: the scene's agents in the reference's scene-major order (vehicles, RSUs, drones; ego first —
+    common_modules/airv2x_base_model.py:212-236). Rank r owns agent r. Returns per-rank local dict skeletons and the
+    global layout lists (record_len, per-type counts)."""
+    order = {"vehicle": 0, "rsu": 1, "drone": 2}
+    assert list(agent_types) == sorted(agent_types, key=lambda t: order[t]), \
+        "agents must be ordered vehicles, RSUs, drones (ego = agent 0)"
+    per_rank = []
+    for r, t in enumerate(agent_types):
+        per_rank.append({ty: {"record_len": [1 if ty == t else 0], "batch_idxs": [0] if ty == t else []}
+                         for ty in order})
+    return per_rank, {"record_len": [len(agent_types)],
+                      "counts": {ty: sum(1 for t in agent_types if t == ty) for ty in order}}
+
+
+def gather_agent_maps(local, group=None):
+    """all-gather of one [1, ...] map per rank into [world, ...] (rank order = agent order); gloo or nccl"""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    else:
+        dist.all_gather(list(out.split(1)), local.contiguous(), group=group)
+    return out
+
+
+class AgentParallelCoBEVT:
+    """Airv2xCoBEVT with the agents of ONE scene sharded one per rank. Every rank returns the fused output."""
+
+    def __init__(self, model, agent_types, transport="nccl", group=None):
+        assert transport in ("nccl", "peer")
+        self.model, self.group, self.transport = model, group, transport
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert len(agent_types) == self.world, "one agent per rank"
+        self.agent_types = list(agent_types)
+        self.per_rank, self.glob = agent_rank_plan(agent_types)
+        self._symm = None
+
+    def _layouts(self, dev):
+        m = self.model
+        skeleton = dict(self.per_rank[self.rank])
+        skeleton["raw_points"] = True  # layout key only
+        lay = dict(m._layout(skeleton, dev))
+        # only agent 0 of the scene is the ego (mask_ego_points applies to it alone)
+        lay["ego_flags"] = torch.tensor([1 if self.rank == 0 else 0], dtype=torch.uint8, device=dev)
+        L, n = m.max_cav_num, self.world
+        assert n <= L, "more agents than max_cav allows"
+        glob = {"record_len": [n], "n_total": n,
+                "scene_start": torch.zeros(1, dtype=torch.int32, device=dev),
+                "scene_len": torch.tensor([n], dtype=torch.int32, device=dev),
+                "key_mask": torch.tensor([[1] * n + [0] * (L - n)], dtype=torch.int32, device=dev)}
+        return lay, glob
+
+    def __call__(self, points, preprocess):
+        """points: [P, 4] f32 cloud of THIS rank's agent (host or device). Returns {"psm","rm","obj"}."""
+        m = self.model
+        assert not m.training, "agent-parallel mode is inference only"
+        dev = next(m.parameters()).device
+        if not hasattr(self, "_lay"):
+            self._lay = self._layouts(dev)
+        lay, glob = self._lay
+        dd = dict(self.per_rank[self.rank])
+        pts = points.to(device=dev, dtype=torch.float32)
+        dd["raw_points"] = {"points": pts, "offsets": torch.tensor([0, pts.shape[0]], dtype=torch.int32),
+                            "preprocess": preprocess, "filter": True}
+        lidar = m._lidar(dd, dev, lay)
+        lidar["raw"]["ego_flags"] = lay["ego_flags"]
+        eng, P = m.engine, m._param_dict()
+        eng._begin_step()
+        W = eng._pack_weights(P)
+        if self.transport == "nccl":
+            local = eng.encode(P, W, lidar, lay)
+            feat = gather_agent_maps(local, self.group)
+            heads = eng.fuse_heads(P, W, feat, glob)
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            if self._symm is None:
+                la = m.args[self.agent_types[self.rank]]["lidar"]["point_pillar_scatter"]["grid_size"]
+                shape = (1, int(la[1]) // 2, int(la[0]) // 2, eng.c_shrink)
+                buf = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                table = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+                self._symm = (buf, hdl, table)
+            buf, hdl, table = self._symm
+            eng.encode(P, W, lidar, lay, out=buf)
+            hdl.barrier(channel=0)   # every rank's map is complete before anyone pulls it
+            heads = eng.fuse_heads(P, W, buf, glob, peer_ptrs=table)
+            hdl.barrier(channel=1)   # nobody overwrites its map (next call) while a peer may still be reading
+        A, K = m.args["anchor_number"], m.args["num_class"]
+        nc, nr = A * K, 7 * A
+        nchw = heads.permute(0, 3, 1, 2)
+        return {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A]}

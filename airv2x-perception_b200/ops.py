@@ -260,6 +260,14 @@ def regroup(src, scene_start, scene_len, B, L, out):
     return out
 
 
+def regroup_ptrs(ptr_table, img_shape, scene_start, scene_len, B, L, out):
+    """ptr_table: int64 device tensor [N] of per-agent image pointers (possibly peer-GPU memory); img_shape: (H, W, C)"""
+    h, w, c = img_shape
+    call("a2x_regroup_ptrs", _ptr(ptr_table), _ptr(scene_start), _ptr(scene_len), c_int(B), c_int(L), c_ll(h * w * c),
+         _op(out), stream_ptr())
+    return out
+
+
 def window_attention_fwd(qkv, bias_table, key_mask, B, L, heads, dim_head, window, grid_mode, out):
     """qkv: dense [B*L, H, W, 3*heads*dim_head]; out: Act [B*L, H, W, heads*dim_head]"""
     assert qkv.is_contiguous() and out.hi.is_contiguous()

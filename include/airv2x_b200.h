@@ -146,6 +146,10 @@ int a2x_agent_mean_layernorm(const float* x, int B, int L, long long pix, int C,
 /* dst[b][l] = src[scene_start[b] + l] (l < scene_len[b]) else zeros; images of img_elems floats */
 int a2x_regroup(const float* src, const int* scene_start, const int* scene_len, int B, int L, long long img_elems,
                 const a2x_output* dst, a2x_stream_t stream);
+/* Same, the agents' images addressed through a DEVICE table of pointers (agent order), each of which may point into a
+ * peer GPU's memory (NVLink P2P): the agent all-gather fused into the regroup (agents one per GPU). */
+int a2x_regroup_ptrs(const float* const* src_ptrs_dev, const int* scene_start, const int* scene_len, int B, int L,
+                     long long img_elems, const a2x_output* dst, a2x_stream_t stream);
 /* qkv: [B*L][H][W][3*heads*dim_head] (q | k | v); bias_table: [(2L-1)(2w-1)^2][heads]; key_mask: int32 [B][L] or NULL;
  * out: dense [B*L][H][W][heads*dim_head]. softmax(q*scale . k + bias) v per (window | grid cell, head). */
 int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const int* key_mask, int B, int L, int H, int W,

@@ -42,3 +42,49 @@ def test_grad_averager_world2():
     for _, g0, g1 in res:
         assert torch.allclose(g0, torch.full((5, 3), 1.5))
         assert torch.allclose(g1, torch.arange(7, dtype=torch.float32) * 1.5)
+
+
+def _gather_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import a2x_import
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = a2x_import.pkg("dist")
+    local = torch.full((1, 2, 3, 4), float(rank + 1))
+    out = D.gather_agent_maps(local)
+    q.put((rank, out.clone()))
+    dist.destroy_process_group()
+
+
+def test_agent_parallel_plan_and_gather_world2():
+    """agents one per rank: the rank plan follows the reference's scene-major agent order and the gather
+    returns the maps in agent order on every rank"""
+    sys.path.insert(0, ROOT)
+    import a2x_import
+
+    D = a2x_import.pkg("dist")
+    per_rank, glob = D.agent_rank_plan(["vehicle", "vehicle", "rsu", "drone"])
+    assert glob["record_len"] == [4] and glob["counts"] == {"vehicle": 2, "rsu": 1, "drone": 1}
+    assert per_rank[0]["vehicle"] == {"record_len": [1], "batch_idxs": [0]} and per_rank[0]["rsu"]["batch_idxs"] == []
+    assert per_rank[2]["rsu"]["record_len"] == [1] and per_rank[3]["drone"]["batch_idxs"] == [0]
+    try:
+        D.agent_rank_plan(["rsu", "vehicle"])
+    except AssertionError:
+        pass
+    else:
+        raise AssertionError("out-of-order agents must be rejected (ego = first vehicle)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, out in res:
+        assert out.shape == (2, 2, 3, 4)
+        assert torch.equal(out[0], torch.full((2, 3, 4), 1.0)) and torch.equal(out[1], torch.full((2, 3, 4), 2.0))
