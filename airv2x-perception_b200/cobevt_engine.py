@@ -155,6 +155,7 @@ class CoBEVTEngine(W2CEngine):
         [N, h/2, w/2, C] shrunk maps (written into `out` if given, e.g. a symmetric-memory buffer peers read)."""
         N = layout["n_total"]
         canvas = self._encode(P, lidar, layout, False, None)
+        self._last_canvas = canvas
         x = canvas
         h2 = w2 = None
         cat = None

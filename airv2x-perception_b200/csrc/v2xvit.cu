@@ -1,0 +1,355 @@
+// V2X-ViT fusion kernels that are not plain linears / LayerNorm / window attention (those are shared with CoBEVT):
+// relative temporal encoding, heterogeneous multi-agent attention (HGT) with the relation tensors folded into the K / V
+// projections, and the split-attention fusion of the pyramid window branches.
+// Token tensors are fp32 NHWC [agents][H][W][C] of ONE padded-free scene batch (padded agents are never keys and only
+// agent 0 is returned, so they are skipped: exact).
+//
+// Reference semantics:
+//   opencood/models/v2xvit_modules/v2xvit_basic.py:41-80    RelTemporalEncoding / RTE
+//   opencood/models/v2xvit_modules/hmsa.py:37-158           HGTCavAttention (typed q/k/v/a linears, relation_att/msg)
+//   opencood/models/v2xvit_modules/split_attn.py:6-63       RadixSoftmax / SplitAttn
+#include "../../include/airv2x_b200.h"
+#include "a2x_host.h"
+#include "a2x_ptx.cuh"
+
+namespace a2x {
+
+// ---------------------------------------------------------------------------------------------- RTE
+// vec[a][c] = sum_k W[c][k] * emb[idx[a]][k] + b[c]           (one block per agent)
+__global__ void rte_vectors_kernel(const float* __restrict__ emb, const int* __restrict__ idx,
+                                   const float* __restrict__ W, const float* __restrict__ b, int C,
+                                   float* __restrict__ vec) {
+    extern __shared__ float se[];
+    const int a = blockIdx.x;
+    const float* e = emb + (long long)idx[a] * C;
+    for (int k = threadIdx.x; k < C; k += blockDim.x) se[k] = e[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < C; ++k) s = fmaf(W[(long long)c * C + k], se[k], s);
+        vec[(long long)a * C + c] = s + b[c];
+    }
+}
+
+// x[a][p][c] += vec[a][c]
+__global__ void agent_vec_add_kernel(float* __restrict__ x, const float* __restrict__ vec, long long pix, int C,
+                                     long long total4) {
+    const int q = C >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % q) * 4;
+        const long long a = i / (q * pix);
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        const float4 d = *reinterpret_cast<const float4*>(vec + a * C + c);
+        v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- HGT weight folding
+// For key-agent type tj the fused projection has 5*C output rows:
+//   [0,C)   q  = Wq[tj]
+//   [C,2C)  k' for query type 0 = A[0*T+tj] Wk[tj]      [2C,3C) k' for query type 1 = A[1*T+tj] Wk[tj]
+//   [3C,4C) v' for query type 0 = M[0*T+tj]^T Wv[tj]    [4C,5C) v' for query type 1 = M[1*T+tj]^T Wv[tj]
+// with A = relation_att, M = relation_msg ([relations][heads][dh][dh], block diagonal over heads), so that
+//   logit(i,j) = q_i . k'_{type_i}(j)   and   message(i,j) = v'_{type_i}(j)          (hmsa.py:136-151 re-associated).
+struct HgtFoldParams {
+    const float* qw[2]; const float* qb[2];
+    const float* kw[2]; const float* kb[2];
+    const float* vw[2]; const float* vb[2];
+    const float* rel_att; const float* rel_msg;
+    float* wf;  // [2][5C][C]
+    float* bf;  // [2][5C]
+    int C, heads, dh;
+};
+
+__global__ void hgt_fold_kernel(const HgtFoldParams p) {
+    const int C = p.C, dh = p.dh;
+    const long long per_type = (long long)5 * C * (C + 1);  // weights then one bias column
+    const long long total = 2 * per_type;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int tj = (int)(i / per_type);
+        long long r = i - tj * per_type;
+        const int col = (int)(r % (C + 1));  // col == C -> bias
+        const int row = (int)(r / (C + 1));
+        const int part = row / C, o = row - part * C;
+        float val;
+        if (part == 0) {
+            val = col < C ? p.qw[tj][(long long)o * C + col] : p.qb[tj][o];
+        } else {
+            const int ti = (part - 1) & 1;
+            const bool is_v = part >= 3;
+            const int h = o / dh, a = o - h * dh;
+            const float* R = (is_v ? p.rel_msg : p.rel_att) + ((long long)(ti * 2 + tj) * p.heads + h) * dh * dh;
+            const float* Wm = is_v ? p.vw[tj] : p.kw[tj];
+            const float* Bv = is_v ? p.vb[tj] : p.kb[tj];
+            float s = 0.f;
+            for (int t = 0; t < dh; ++t) {
+                const float rv = is_v ? R[t * dh + a] : R[a * dh + t];  // v' = M^T v ; k' = A k
+                const float src = col < C ? Wm[(long long)(h * dh + t) * C + col] : Bv[h * dh + t];
+                s = fmaf(rv, src, s);
+            }
+            val = s;
+        }
+        if (col < C) p.wf[((long long)tj * 5 * C + row) * C + col] = val;
+        else p.bf[(long long)tj * 5 * C + row] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- HGT attention
+// one thread per (pixel, query agent i, head m): softmax_j( scale * q_i . k'_{ti}(j) ) over the keys valid at this
+// pixel (mask[j][p] != 0), out_i = sum_j att * v'_{ti}(j).   qkv: [n][pix][5C] (layout above).
+template <int DH>
+__global__ void __launch_bounds__(256) hgt_attention_kernel(const float* __restrict__ qkv, const int* __restrict__ types,
+                                                            const float* __restrict__ mask, int n, long long pix,
+                                                            int heads, float scale, SplitOut out) {
+    const int C = heads * DH;
+    const long long total = pix * n * heads;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(t % heads);
+        const int i = (int)((t / heads) % n);
+        const long long p = t / ((long long)heads * n);
+        const int ti = types[i];
+        float q[DH], acc[DH];
+        const float* qrow = qkv + ((long long)i * pix + p) * 5 * C + m * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(qrow + c);
+            q[c] = v.x * scale; q[c + 1] = v.y * scale; q[c + 2] = v.z * scale; q[c + 3] = v.w * scale;
+        }
+#pragma unroll
+        for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+        float mx = -INFINITY, den = 0.f;
+        for (int j = 0; j < n; ++j) {
+            if (mask[(long long)j * pix + p] == 0.f) continue;
+            const float* krow = qkv + ((long long)j * pix + p) * 5 * C + (1 + ti) * C + m * DH;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(krow + c);
+                s0 = fmaf(q[c], v.x, s0); s1 = fmaf(q[c + 1], v.y, s1);
+                s0 = fmaf(q[c + 2], v.z, s0); s1 = fmaf(q[c + 3], v.w, s1);
+            }
+            const float s = s0 + s1;
+            const float mn = fmaxf(mx, s);
+            const float corr = __expf(mx - mn), e = __expf(s - mn);
+            den = den * corr + e;
+            const float* vrow = krow + 2 * C;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(vrow + c);
+                acc[c] = fmaf(acc[c], corr, e * v.x); acc[c + 1] = fmaf(acc[c + 1], corr, e * v.y);
+                acc[c + 2] = fmaf(acc[c + 2], corr, e * v.z); acc[c + 3] = fmaf(acc[c + 3], corr, e * v.w);
+            }
+            mx = mn;
+        }
+        const float inv = 1.f / den;  // no valid key -> NaN, like softmax over an all -inf row in the reference
+        const long long off = ((long long)i * pix + p) * C + m * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4)
+            store_split4(out, off + c, make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- split attention
+// sums[a][c] += sum_p (w0 + w1 + w2)[a][p][c]      (global average pool numerator)
+__global__ void __launch_bounds__(256) split_pool_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                                         const float* __restrict__ w2, long long pix, int C,
+                                                         int chunks, float* __restrict__ sums) {
+    // grid = (chunks, agents); blockDim = C/4 * rows
+    const int q = C >> 2;
+    const int cq = threadIdx.x % q, prow = threadIdx.x / q, ppb = blockDim.x / q;
+    const int a = blockIdx.y;
+    const long long per = (pix + chunks - 1) / chunks;
+    const long long p0 = (long long)blockIdx.x * per, p1 = min(pix, p0 + per);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (prow < ppb) {
+        for (long long p = p0 + prow; p < p1; p += ppb) {
+            const long long o = ((long long)a * pix + p) * C + cq * 4;
+            const float4 x = *reinterpret_cast<const float4*>(w0 + o);
+            const float4 y = *reinterpret_cast<const float4*>(w1 + o);
+            const float4 z = *reinterpret_cast<const float4*>(w2 + o);
+            s.x += (x.x + y.x) + z.x; s.y += (x.y + y.y) + z.y; s.z += (x.z + y.z) + z.z; s.w += (x.w + y.w) + z.w;
+        }
+    }
+    extern __shared__ float4 red4[];
+    red4[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < q) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < ppb; ++r) {
+            const float4 v = red4[r * q + threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        float* o = sums + (long long)a * C + threadIdx.x * 4;
+        atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+    }
+}
+
+// per agent: g = sums / pix; h = relu(LN(fc1 g)); a = fc2 h ([3C]); wts[r][c] = softmax_r a[r*C + c]
+__global__ void split_weights_kernel(const float* __restrict__ sums, float inv_pix, const float* __restrict__ fc1,
+                                     const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                     const float* __restrict__ fc2, int C, float* __restrict__ wts) {
+    extern __shared__ float sm[];
+    float* g = sm;          // [C]
+    float* h = sm + C;      // [C]
+    float* red = h + C;     // [2]
+    const int a = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) g[c] = sums[(long long)a * C + c] * inv_pix;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < C; ++k) s = fmaf(fc1[(long long)c * C + k], g[k], s);
+        h[c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // C <= 512: a serial two-pass LayerNorm is negligible
+        float m = 0.f;
+        for (int c = 0; c < C; ++c) m += h[c];
+        m /= C;
+        float v = 0.f;
+        for (int c = 0; c < C; ++c) v += (h[c] - m) * (h[c] - m);
+        red[0] = m;
+        red[1] = rsqrtf(v / C + 1e-5f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = (h[c] - red[0]) * red[1] * ln_g[c] + ln_b[c];
+        g[c] = fmaxf(v, 0.f);  // reuse g for the activated hidden vector (all reads of g finished above)
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float t = 0.f;
+            const float* w = fc2 + (long long)(r * C + c) * C;
+            for (int k = 0; k < C; ++k) t = fmaf(w[k], g[k], t);
+            s[r] = t;
+        }
+        const float mx = fmaxf(s[0], fmaxf(s[1], s[2]));
+        const float e0 = expf(s[0] - mx), e1 = expf(s[1] - mx), e2 = expf(s[2] - mx);
+        const float inv = 1.f / (e0 + e1 + e2);
+        float* o = wts + (long long)a * 3 * C;
+        o[c] = e0 * inv;
+        o[C + c] = e1 * inv;
+        o[2 * C + c] = e2 * inv;
+    }
+}
+
+// x[a][p][c] += w0*wts[a][0][c] + w1*wts[a][1][c] + w2*wts[a][2][c]      (PWA output + residual)
+__global__ void __launch_bounds__(256) split_combine_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                                            const float* __restrict__ w2, const float* __restrict__ wts,
+                                                            float* __restrict__ x, long long pix, int C,
+                                                            long long total4) {
+    const int q = C >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % q) * 4;
+        const long long a = i / (q * pix);
+        const float* wa = wts + a * 3 * C + c;
+        const float4 a0 = *reinterpret_cast<const float4*>(wa);
+        const float4 a1 = *reinterpret_cast<const float4*>(wa + C);
+        const float4 a2 = *reinterpret_cast<const float4*>(wa + 2 * C);
+        const float4 u = reinterpret_cast<const float4*>(w0)[i];
+        const float4 v = reinterpret_cast<const float4*>(w1)[i];
+        const float4 w = reinterpret_cast<const float4*>(w2)[i];
+        float4 r = reinterpret_cast<float4*>(x)[i];
+        r.x += u.x * a0.x + v.x * a1.x + w.x * a2.x;
+        r.y += u.y * a0.y + v.y * a1.y + w.y * a2.y;
+        r.z += u.z * a0.z + v.z * a1.z + w.z * a2.z;
+        r.w += u.w * a0.w + v.w * a1.w + w.w * a2.w;
+        reinterpret_cast<float4*>(x)[i] = r;
+    }
+}
+
+static int vx_grid(long long total) {
+    long long b = (total + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace a2x
+
+using namespace a2x;
+
+extern "C" {
+
+int a2x_rte_add(float* x, int n_agents, long long pix, int C, const float* emb_table, const int* emb_idx_dev,
+                const float* lin_w, const float* lin_b, float* vec_ws, a2x_stream_t stream) {
+    A2X_REQUIRE(x && emb_table && emb_idx_dev && lin_w && lin_b && vec_ws && n_agents > 0 && pix > 0 && C > 0 && C % 4 == 0,
+                "rte_add: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    rte_vectors_kernel<<<n_agents, 256, C * sizeof(float), st>>>(emb_table, emb_idx_dev, lin_w, lin_b, C, vec_ws);
+    A2X_LAUNCHED();
+    const long long total4 = (long long)n_agents * pix * (C / 4);
+    agent_vec_add_kernel<<<vx_grid(total4), 256, 0, st>>>(x, vec_ws, pix, C, total4);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_hgt_fold(const float* const* qw, const float* const* qb, const float* const* kw, const float* const* kb,
+                 const float* const* vw, const float* const* vb, const float* relation_att, const float* relation_msg,
+                 int C, int heads, float* w_fold, float* b_fold, a2x_stream_t stream) {
+    A2X_REQUIRE(qw && qb && kw && kb && vw && vb && relation_att && relation_msg && w_fold && b_fold && C > 0 &&
+                    heads > 0 && C % heads == 0,
+                "hgt_fold: bad args (two agent types expected)");
+    HgtFoldParams p;
+    for (int t = 0; t < 2; ++t) {
+        p.qw[t] = qw[t]; p.qb[t] = qb[t]; p.kw[t] = kw[t]; p.kb[t] = kb[t]; p.vw[t] = vw[t]; p.vb[t] = vb[t];
+    }
+    p.rel_att = relation_att; p.rel_msg = relation_msg; p.wf = w_fold; p.bf = b_fold;
+    p.C = C; p.heads = heads; p.dh = C / heads;
+    hgt_fold_kernel<<<vx_grid((long long)2 * 5 * C * (C + 1)), 256, 0, (cudaStream_t)stream>>>(p);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_hgt_attention_fwd(const float* qkv, const int* types_dev, const float* key_mask, int n_agents, long long pix,
+                          int heads, int dim_head, float scale, const a2x_output* out, a2x_stream_t stream) {
+    A2X_REQUIRE(qkv && types_dev && key_mask && out && out->hi && n_agents > 0 && pix > 0 && heads > 0,
+                "hgt_attention_fwd: bad args");
+    A2X_REQUIRE(out->cs == heads * dim_head, "hgt_attention_fwd: dense [.., heads*dim_head] output expected");
+    SplitOut o;
+    o.hi = out->hi; o.b16 = (__nv_bfloat16*)out->b16; o.ps = out->b16_plane;
+    const int g = vx_grid(pix * n_agents * heads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dim_head == 16) hgt_attention_kernel<16><<<g, 256, 0, st>>>(qkv, types_dev, key_mask, n_agents, pix, heads, scale, o);
+    else if (dim_head == 32) hgt_attention_kernel<32><<<g, 256, 0, st>>>(qkv, types_dev, key_mask, n_agents, pix, heads, scale, o);
+    else if (dim_head == 64) hgt_attention_kernel<64><<<g, 256, 0, st>>>(qkv, types_dev, key_mask, n_agents, pix, heads, scale, o);
+    else {
+        set_error("hgt_attention_fwd: dim_head %d not in {16, 32, 64}", dim_head);
+        return 1;
+    }
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_split_attn_fuse(const float* w0, const float* w1, const float* w2, int n_agents, long long pix, int C,
+                        const float* fc1, const float* ln_gamma, const float* ln_beta, const float* fc2,
+                        float* sums_ws, float* weights_ws, float* x_inout, a2x_stream_t stream) {
+    A2X_REQUIRE(w0 && w1 && w2 && fc1 && ln_gamma && ln_beta && fc2 && sums_ws && weights_ws && x_inout && n_agents > 0 &&
+                    pix > 0 && C > 0 && C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0,
+                "split_attn_fuse: bad args (C/4 must divide 256)");
+    cudaStream_t st = (cudaStream_t)stream;
+    A2X_CHECK_CUDA(cudaMemsetAsync(sums_ws, 0, (size_t)n_agents * C * sizeof(float), st));
+    const int chunks = 148 * 2 / n_agents > 0 ? 148 * 2 / n_agents : 1;
+    split_pool_kernel<<<dim3(chunks, n_agents), 256, 256 * sizeof(float4), st>>>(w0, w1, w2, pix, C, chunks, sums_ws);
+    A2X_LAUNCHED();
+    split_weights_kernel<<<n_agents, 256, (2 * C + 2) * sizeof(float), st>>>(sums_ws, 1.0f / (float)pix, fc1, ln_gamma,
+                                                                           ln_beta, fc2, C, weights_ws);
+    A2X_LAUNCHED();
+    const long long total4 = (long long)n_agents * pix * (C / 4);
+    split_combine_kernel<<<vx_grid(total4), 256, 0, st>>>(w0, w1, w2, weights_ws, x_inout, pix, C, total4);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -115,6 +115,24 @@ __global__ void __launch_bounds__(256) warp_affine_bwd_kernel(const float* __res
     }
 }
 
+// ROI mask = nearest-neighbour warp of an all-ones map (get_rotated_roi, torch_transformation_utils.py:81-113) times the
+// per-agent validity flag: out[a][p] = valid[a] && the source pixel of p falls inside the map
+__global__ void roi_mask_kernel(const float* __restrict__ theta, const int* __restrict__ valid, float* __restrict__ out,
+                                const WarpGeom g) {
+    const long long total = (long long)g.n * g.ho * g.wo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % g.wo);
+        const int oy = (int)((i / g.wo) % g.ho);
+        const int img = (int)(i / ((long long)g.wo * g.ho));
+        float ix, iy;
+        warp_coords(theta + img * 6, g, oy, ox, ix, iy);
+        const int x0 = (int)nearbyintf(ix), y0 = (int)nearbyintf(iy);
+        const bool in = x0 >= 0 && x0 < g.wi && y0 >= 0 && y0 < g.hi;
+        out[i] = (in && (valid == nullptr || valid[img] != 0)) ? 1.f : 0.f;
+    }
+}
+
 static int warp_grid(long long total) {
     long long b = (total + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
@@ -139,6 +157,16 @@ int a2x_warp_affine_fwd(const float* src, int src_cs, const float* theta, int n,
     o.b16 = (__nv_bfloat16*)dst->b16;
     o.ps = dst->b16_plane;
     warp_affine_fwd_kernel<<<warp_grid((long long)n * ho * wo * (c / 4)), 256, 0, (cudaStream_t)stream>>>(src, theta, o, g);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_roi_mask(const float* theta, const int* valid, int n, int h, int w, int align_corners, float* out,
+                 a2x_stream_t stream) {
+    A2X_REQUIRE(theta && out && n > 0 && h > 0 && w > 0, "roi_mask: bad args");
+    WarpGeom g{n, h, w, h, w, 4, 4, 4, align_corners, 1};
+    roi_mask_kernel<<<warp_grid((long long)n * h * w), 256, 0, (cudaStream_t)stream>>>(theta, valid, out, g);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

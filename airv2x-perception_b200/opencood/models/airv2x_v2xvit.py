@@ -1,0 +1,178 @@
+"""`opencood.models.airv2x_v2xvit.Airv2xV2XVit` on the B200 kernels (BASELINE config 3).
+
+Same registry name / class name / constructor (`cls(hypes["model"]["args"])`), same `hypes_yaml` keys
+(`modality_fusion.*`, `transformer.encoder.*`, `max_cav`), same `state_dict` key names and shapes (12 758 879 parameters
+for the shipped yaml, including the unused `prior_feed` and the frozen sinusoid table of the RTE embedding), same
+`forward(data_dict) -> {"psm","rm","obj","comm_rate"}` as opencood/models/airv2x_v2xvit.py:19-167 of the reference.
+The torch.nn layers below are parameter containers only; their forward is never called. Eval-mode forward only in
+this round; no CPU fallback.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from ...v2xvit_engine import V2XViTEngine
+from ...w2c_engine import AGENT_TYPES, TYPE_PREFIX
+from .airv2x_where2com import Airv2xWhere2com, _backbone_params, _PillarVFEParams, _shrink_params
+
+
+class _HGTParams(nn.Module):
+    """hmsa.py:6-35 (parameter order matters for state_dict order only)"""
+
+    def __init__(self, dim, heads, dim_head, num_types=2, num_relations=4):
+        super().__init__()
+        inner = heads * dim_head
+        self.k_linears, self.q_linears = nn.ModuleList(), nn.ModuleList()
+        self.v_linears, self.a_linears = nn.ModuleList(), nn.ModuleList()
+        for _ in range(num_types):
+            self.k_linears.append(nn.Linear(dim, inner))
+            self.q_linears.append(nn.Linear(dim, inner))
+            self.v_linears.append(nn.Linear(dim, inner))
+            self.a_linears.append(nn.Linear(inner, dim))
+        self.relation_att = nn.Parameter(torch.empty(num_relations, heads, dim_head, dim_head))
+        self.relation_msg = nn.Parameter(torch.empty(num_relations, heads, dim_head, dim_head))
+        nn.init.xavier_uniform_(self.relation_att)
+        nn.init.xavier_uniform_(self.relation_msg)
+
+
+class _WindowAttnParams(nn.Module):
+    def __init__(self, dim, heads, dim_head, ws):
+        super().__init__()
+        inner = heads * dim_head
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.pos_embedding = nn.Parameter(torch.randn(2 * ws - 1, 2 * ws - 1))
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Identity())
+
+
+class _SplitAttnParams(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, dim, bias=False)
+        self.bn1 = nn.LayerNorm(dim)
+        self.fc2 = nn.Linear(dim, dim * 3, bias=False)
+
+
+class _PyramidParams(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.pwmsa = nn.ModuleList([_WindowAttnParams(cfg["dim"], h, d, ws)
+                                    for h, d, ws in zip(cfg["heads"], cfg["dim_head"], cfg["window_size"])])
+        if cfg["fusion_method"] == "split_attn":
+            self.split_attn = _SplitAttnParams(256)
+
+
+class _PreNormParams(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+
+class _FeedForwardParams(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Identity(), nn.Linear(hidden, dim), nn.Identity())
+
+
+class _FusionBlockParams(nn.Module):
+    def __init__(self, num_blocks, ca, pw):
+        super().__init__()
+        self.layers = nn.ModuleList([nn.ModuleList([
+            _PreNormParams(ca["dim"], _HGTParams(ca["dim"], ca["heads"], ca["dim_head"])),
+            _PreNormParams(ca["dim"], _PyramidParams(pw))]) for _ in range(num_blocks)])
+
+
+class _RTEParams(nn.Module):
+    def __init__(self, dim, max_len=100):
+        super().__init__()
+        emb = nn.Module()
+        emb.emb = nn.Embedding(max_len, dim)
+        position = torch.arange(0.0, max_len).unsqueeze(1)
+        div = torch.exp(torch.arange(0, dim, 2) * -(math.log(10000.0) / dim))
+        emb.emb.weight.data[:, 0::2] = torch.sin(position * div) / math.sqrt(dim)
+        emb.emb.weight.data[:, 1::2] = torch.cos(position * div) / math.sqrt(dim)
+        emb.lin = nn.Linear(dim, dim)
+        self.emb = emb
+
+
+class _EncoderParams(nn.Module):
+    def __init__(self, enc):
+        super().__init__()
+        ca, pw = enc["cav_att_config"], enc["pwindow_att_config"]
+        self.prior_feed = nn.Linear(ca["dim"] + 3, ca["dim"])   # present in the reference, never used (v2xvit_basic.py:150)
+        self.layers = nn.ModuleList([])
+        if ca["use_RTE"]:
+            self.rte = _RTEParams(ca["dim"])
+        for _ in range(enc["depth"]):
+            self.layers.append(nn.ModuleList([_FusionBlockParams(enc["num_blocks"], ca, pw),
+                                              _PreNormParams(ca["dim"], _FeedForwardParams(ca["dim"], enc["feed_forward"]["mlp_dim"]))]))
+
+
+class _TransformerParams(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.encoder = _EncoderParams(args["encoder"])
+
+
+class Airv2xV2XVit(Airv2xWhere2com):
+    def __init__(self, args, precision="split3"):
+        nn.Module.__init__(self)
+        self.args = args
+        self.collaborators = args["collaborators"]
+        self.active_sensors = args["active_sensors"]
+        self.max_cav_num = sum(args["max_cav"].values())
+        self.veh_models, self.rsu_models, self.drone_models = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        for t in AGENT_TYPES:
+            if t not in self.collaborators:
+                continue
+            for m in args[t]["modalities"]:
+                if m != "lidar":
+                    raise NotImplementedError("modality %r is outside the B200 hot path (lidar only)" % m)
+                getattr(self, TYPE_PREFIX[t]).append(nn.Sequential(_PillarVFEParams(args[t]["lidar"]["pillar_vfe"]),
+                                                                   nn.Identity()))
+        mf = args["modality_fusion"]
+        self.backbone = _backbone_params(mf["base_bev_backbone"], 64)
+        self.shrink_flag = bool(mf.get("shrink_header", {}).get("use", False))
+        if self.shrink_flag:
+            self.shrink_conv = _shrink_params(mf["shrink_header"])
+        self.compression = mf["compression"] > 0
+        self.fusion_net = _TransformerParams(args["transformer"])
+        self.outC = args["outC"]
+        if args["task"] != "det":
+            raise NotImplementedError("task %r is outside the B200 hot path (det only)" % args["task"])
+        self.cls_head = nn.Conv2d(self.outC, args["anchor_number"] * args["num_class"], kernel_size=1)
+        self.reg_head = nn.Conv2d(self.outC, 7 * args["anchor_number"], kernel_size=1)
+        if args["obj_head"]:
+            self.obj_head = nn.Conv2d(self.outC, args["anchor_number"], kernel_size=1)
+        self.precision = precision
+        self._engine = None
+        self._last_aux = None
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("Airv2xV2XVit (B200) needs its parameters on a CUDA device; there is no CPU path")
+            self._engine = V2XViTEngine(self.args, dev, self.precision)
+        return self._engine
+
+    def forward(self, data_dict):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("Airv2xV2XVit (B200) needs its parameters on a CUDA device; there is no CPU path")
+        layout = self._layout(data_dict, dev)
+        lidar = self._lidar(data_dict, dev, layout)
+        heads, aux = self.engine.forward(self._param_dict(), lidar, layout, self.training,
+                                         prior=data_dict["prior_encoding"], scm=data_dict["spatial_correction_matrix"])
+        A, K = self.args["anchor_number"], self.args["num_class"]
+        nc, nr = A * K, 7 * A
+        nchw = heads.permute(0, 3, 1, 2)
+        return {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A],
+                "comm_rate": int(aux["comm_rate"].item())}
+
+    def train_step(self, *a, **k):
+        raise NotImplementedError("Airv2xV2XVit: the fused training step is not implemented in this round")
+
+    train_step_graphed = train_step

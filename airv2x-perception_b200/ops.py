@@ -514,3 +514,45 @@ def voxelize(points, offsets_dev, n_agents, lidar_range, voxel_size, max_points,
          c_int(max_points), c_int(max_voxels), c_int(cap), _ptr(ego_flags), c_int(int(strict_range)), _ptr(workspace),
          ctypes.c_size_t(workspace.numel()),
          _ptr(voxels), _ptr(coords), _ptr(num_points), _ptr(counts), stream_ptr())
+
+
+def roi_mask(theta, valid, n, h, w, out, align_corners=True):
+    call("a2x_roi_mask", _ptr(theta.contiguous()), _ptr(valid), c_int(n), c_int(h), c_int(w), c_int(int(align_corners)),
+         _ptr(out), stream_ptr())
+    return out
+
+
+# V2X-ViT fusion ---------------------------------------------------------------------------------------------------
+def rte_add(x, emb_table, emb_idx, lin_w, lin_b, vec_ws):
+    """x: dense [n, h, w, C] (+= per-agent vector Linear(emb[idx]))"""
+    n, h, w, c = x.shape
+    assert x.is_contiguous()
+    call("a2x_rte_add", _ptr(x), c_int(n), c_ll(h * w), c_int(c), _ptr(emb_table), _ptr(emb_idx), _ptr(lin_w), _ptr(lin_b),
+         _ptr(vec_ws), stream_ptr())
+
+
+def _ptr2(a, b):
+    return (ctypes.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+
+
+def hgt_fold(qw, qb, kw, kb, vw, vb, rel_att, rel_msg, heads, w_fold, b_fold):
+    """qw..vb: pairs of tensors (agent type 0, 1); w_fold: [2, 5C, C]; b_fold: [2, 5C]"""
+    C = qw[0].shape[1]
+    call("a2x_hgt_fold", _ptr2(*qw), _ptr2(*qb), _ptr2(*kw), _ptr2(*kb), _ptr2(*vw), _ptr2(*vb), _ptr(rel_att),
+         _ptr(rel_msg), c_int(C), c_int(heads), _ptr(w_fold), _ptr(b_fold), stream_ptr())
+
+
+def hgt_attention_fwd(qkv, types, key_mask, heads, dim_head, out):
+    """qkv: dense [n, h, w, 5C]; types: int32 [n]; key_mask: float [n, h, w]; out: Act [n, h, w, C]"""
+    n, h, w, _ = qkv.shape
+    assert qkv.is_contiguous() and key_mask.is_contiguous()
+    call("a2x_hgt_attention_fwd", _ptr(qkv), _ptr(types), _ptr(key_mask), c_int(n), c_ll(h * w), c_int(heads),
+         c_int(dim_head), c_f(dim_head ** -0.5), _op(out), stream_ptr())
+    return out
+
+
+def split_attn_fuse(w0, w1, w2, fc1, ln_g, ln_b, fc2, sums_ws, weights_ws, x):
+    """x (dense [n, h, w, C]) += split-attention mix of the three window branches"""
+    n, h, w, c = x.shape
+    call("a2x_split_attn_fuse", _ptr(w0), _ptr(w1), _ptr(w2), c_int(n), c_ll(h * w), c_int(c), _ptr(fc1), _ptr(ln_g),
+         _ptr(ln_b), _ptr(fc2), _ptr(sums_ws), _ptr(weights_ws), _ptr(x), stream_ptr())

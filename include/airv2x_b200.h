@@ -156,11 +156,35 @@ int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const in
                              int heads, int dim_head, int window, int grid_mode, float scale, const a2x_output* out,
                              a2x_stream_t stream);
 
+/* ---------------------------------------------------------------- V2X-ViT fusion (csrc/v2xvit.cu)
+ * x[a][p][:] += Linear(emb_table[emb_idx[a]])  — RTE, v2xvit_modules/v2xvit_basic.py:41-80. vec_ws: [n_agents][C]. */
+int a2x_rte_add(float* x, int n_agents, long long pix, int C, const float* emb_table, const int* emb_idx_dev,
+                const float* lin_w, const float* lin_b, float* vec_ws, a2x_stream_t stream);
+/* Fold relation_att / relation_msg ([4][heads][dh][dh]) into the typed K / V projections (hmsa.py:37-151): for key type
+ * tj the fused projection w_fold[tj] is [5C][C] = q | k' (query type 0) | k' (query type 1) | v' (0) | v' (1), with
+ * b_fold[tj] [5C]. qw..vb: HOST arrays of two device pointers (agent types 0 / 1). */
+int a2x_hgt_fold(const float* const* qw, const float* const* qb, const float* const* kw, const float* const* kb,
+                 const float* const* vw, const float* const* vb, const float* relation_att, const float* relation_msg,
+                 int C, int heads, float* w_fold, float* b_fold, a2x_stream_t stream);
+/* per pixel, per head: softmax over the agents j valid at that pixel (key_mask[j][p] != 0) of scale * q_i . k'_{type_i}(j),
+ * out_i = sum_j att v'_{type_i}(j). qkv: [n][pix][5C] from the folded projection; out: dense [n][pix][C]. */
+int a2x_hgt_attention_fwd(const float* qkv, const int* types_dev, const float* key_mask, int n_agents, long long pix,
+                          int heads, int dim_head, float scale, const a2x_output* out, a2x_stream_t stream);
+/* SplitAttn over the three pyramid-window branches + residual (split_attn.py:28-63):
+ * x += sum_r softmax_r(fc2 relu(LN(fc1 mean_p(w0+w1+w2))))[r] * w_r. sums_ws: [n][C], weights_ws: [n][3][C]. */
+int a2x_split_attn_fuse(const float* w0, const float* w1, const float* w2, int n_agents, long long pix, int C,
+                        const float* fc1, const float* ln_gamma, const float* ln_beta, const float* fc2,
+                        float* sums_ws, float* weights_ws, float* x_inout, a2x_stream_t stream);
+
 /* ---------------------------------------------------------------- ego-warp (affine bilinear resampling, NHWC)
  * warp_affine_simple = F.affine_grid + F.grid_sample(bilinear | nearest, zeros padding)
  * (common_modules/torch_transformation_utils.py:327-334); theta: [n][2][3] normalised matrices. */
 int a2x_warp_affine_fwd(const float* src, int src_cs, const float* theta, int n, int hi, int wi, int c, int ho, int wo,
                         int align_corners, int nearest, const a2x_output* dst, a2x_stream_t stream);
+/* out[a][p] = valid[a] (NULL = all valid) && nearest source pixel of p inside the map: the rotated ROI mask of
+ * get_roi_and_cav_mask (torch_transformation_utils.py:15-113) */
+int a2x_roi_mask(const float* theta, const int* valid, int n, int h, int w, int align_corners, float* out,
+                 a2x_stream_t stream);
 /* dsrc += bilinear^T dout (caller zeroes dsrc) */
 int a2x_warp_affine_bwd(const float* dout, int dout_cs, const float* theta, int n, int hi, int wi, int c, int ho, int wo,
                         int align_corners, float* dsrc, int dsrc_cs, a2x_stream_t stream);
