@@ -274,6 +274,85 @@ __global__ void __launch_bounds__(64) window_attention_kernel(const WinAttParams
     }
 }
 
+// Small-window variant (n = L*w*w tokens <= 128 and 128 % n == 0, e.g. the 2x2 / 4x4 single-agent windows of the
+// V2X-ViT pyramid, mswin.py:23-108): a 128-thread CTA packs G = 128 / n windows of one head, thread t = (window g,
+// query t % n); every thread stages the K / V rows of its own token, so global loads are one contiguous row each.
+template <int DH>
+__global__ void __launch_bounds__(128) window_attention_small_kernel(const WinAttParams p, int num_windows) {
+    extern __shared__ float sm[];
+    const int ww = p.w * p.w;
+    const int n = p.L * ww;
+    constexpr int RS = DH + 4;       // padded row stride (floats): spreads the groups over the banks
+    float* sK = sm;                  // [128][RS]
+    float* sV = sK + 128 * RS;       // [128][RS]
+    float* sB = sV + 128 * RS;
+    const int nb = (2 * p.L - 1) * (2 * p.w - 1) * (2 * p.w - 1);
+    const int D = p.heads * DH;
+    const int X = p.H / p.w, Y = p.W / p.w;
+    const int G = 128 / n;
+    const int head = blockIdx.x % p.heads;
+    const int g = threadIdx.x / n, tq = threadIdx.x - g * n;
+    int win = (blockIdx.x / p.heads) * G + g;
+    const bool valid = win < num_windows;
+    if (!valid) win = num_windows - 1;
+    const int y = win % Y;
+    const int x = (win / Y) % X;
+    const int b = win / (Y * X);
+    const int l = tq / ww, r = tq - l * ww;
+    const int w1 = r / p.w, w2 = r - w1 * p.w;
+    const int ph = p.grid_mode ? w1 * X + x : x * p.w + w1;
+    const int pw = p.grid_mode ? w2 * Y + y : y * p.w + w2;
+    const long long tok = ((long long)(b * p.L + l) * p.H + ph) * p.W + pw;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) sB[i] = p.bias[i * p.heads + head];
+    const float* row = p.qkv + tok * (3 * D) + head * DH;
+    float q[DH];
+#pragma unroll
+    for (int c = 0; c < DH; c += 4) {
+        const float4 qv = *reinterpret_cast<const float4*>(row + c);
+        q[c] = qv.x * p.scale; q[c + 1] = qv.y * p.scale; q[c + 2] = qv.z * p.scale; q[c + 3] = qv.w * p.scale;
+        *reinterpret_cast<float4*>(sK + threadIdx.x * RS + c) = *reinterpret_cast<const float4*>(row + D + c);
+        *reinterpret_cast<float4*>(sV + threadIdx.x * RS + c) = *reinterpret_cast<const float4*>(row + 2 * D + c);
+    }
+    __syncthreads();
+    float acc[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+    float mx = -INFINITY, den = 0.f;
+    const int s2 = 2 * p.w - 1;
+    for (int j = 0; j < n; ++j) {
+        const int lj = j / ww, rj = j - lj * ww;
+        if (p.key_mask != nullptr && p.key_mask[b * p.L + lj] == 0) continue;
+        const int k1 = rj / p.w, k2 = rj - k1 * p.w;
+        const float* kr = sK + (g * n + j) * RS;
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+            const float4 kv = *reinterpret_cast<const float4*>(kr + c);
+            d0 = fmaf(q[c], kv.x, d0); d1 = fmaf(q[c + 1], kv.y, d1);
+            d0 = fmaf(q[c + 2], kv.z, d0); d1 = fmaf(q[c + 3], kv.w, d1);
+        }
+        const float sc = d0 + d1 + sB[((l - lj + p.L - 1) * s2 + (w1 - k1 + p.w - 1)) * s2 + (w2 - k2 + p.w - 1)];
+        const float mn = fmaxf(mx, sc);
+        const float corr = __expf(mx - mn), e = __expf(sc - mn);
+        den = den * corr + e;
+        const float* vr = sV + (g * n + j) * RS;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+            const float4 vv = *reinterpret_cast<const float4*>(vr + c);
+            acc[c] = fmaf(acc[c], corr, e * vv.x); acc[c + 1] = fmaf(acc[c + 1], corr, e * vv.y);
+            acc[c + 2] = fmaf(acc[c + 2], corr, e * vv.z); acc[c + 3] = fmaf(acc[c + 3], corr, e * vv.w);
+        }
+        mx = mn;
+    }
+    if (valid) {
+        const float inv = 1.f / den;
+        const long long off = tok * D + head * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4)
+            store_split4(p.out, off + c, make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv));
+    }
+}
+
 static int row_grid(long long rows) {
     long long b = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
     if (b > 148 * 8) b = 148 * 8;
@@ -366,10 +445,33 @@ int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const in
     p.B = B; p.L = L; p.H = H; p.W = W; p.heads = heads; p.w = window; p.grid_mode = grid_mode; p.scale = scale;
     const int n = L * window * window;
     const int nb = (2 * L - 1) * (2 * window - 1) * (2 * window - 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 64 && 128 % n == 0) {  // small windows: pack 128 / n windows per CTA
+        const int num_windows = B * (H / window) * (W / window);
+        const int G = 128 / n;
+        const size_t sm_small = (size_t)(2 * 128 * (dim_head + 4) + nb) * sizeof(float);
+        const long long gsm = (long long)((num_windows + G - 1) / G) * heads;
+#define A2X_WAS(DH)                                                                                             \
+    do {                                                                                                        \
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(window_attention_small_kernel<DH>,                                  \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));       \
+        window_attention_small_kernel<DH><<<(unsigned)gsm, 128, sm_small, st>>>(p, num_windows);                \
+    } while (0)
+        if (dim_head == 16) A2X_WAS(16);
+        else if (dim_head == 32) A2X_WAS(32);
+        else if (dim_head == 64) A2X_WAS(64);
+        else {
+            set_error("window_attention_fwd: dim_head %d not in {16, 32, 64}", dim_head);
+            return 1;
+        }
+#undef A2X_WAS
+        A2X_LAUNCHED();
+        A2X_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = (size_t)(2 * n * dim_head + nb + n) * sizeof(float);
     A2X_REQUIRE(smem <= 200 * 1024, "window_attention_fwd: window of %d tokens does not fit shared memory", n);
     const long long grid = (long long)B * (H / window) * (W / window) * heads;
-    cudaStream_t st = (cudaStream_t)stream;
 #define A2X_WA(DH, QPT)                                                                                         \
     do {                                                                                                        \
         A2X_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<DH, QPT>,                                   \

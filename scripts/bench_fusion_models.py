@@ -1,5 +1,9 @@
-"""Eval-forward timing of the CoBEVT path (BASELINE config 4 geometry, N agents on one GPU) with a per-C-ABI-call
-breakdown (CUDA events). Prints one JSON line. Not the headline bench (bench.py measures config 2)."""
+"""Eval-forward timing of the transformer-fusion paths at full geometry on one GPU — BASELINE config 3 (V2X-ViT) and
+config 4 (CoBEVT), 5 agents x 60k points — with a per-C-ABI-call breakdown (CUDA events). One JSON line per model.
+Not the headline bench (bench.py measures config 2).
+
+    python scripts/bench_fusion_models.py [cobevt|v2xvit] [n_agents]
+"""
 import json
 import os
 import sys
@@ -14,15 +18,15 @@ import bench
 
 
 def main():
-    n_agents = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-    cfg = json.load(open(os.path.join(ROOT, "configs", "airv2x_intermediate_cobevt.json")))
-    M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+    which = sys.argv[1] if len(sys.argv) > 1 else "cobevt"
+    n_agents = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    cfg = json.load(open(os.path.join(ROOT, "configs", "airv2x_intermediate_%s.json" % which)))
+    M = a2x_import.pkg("opencood.models.airv2x_" + which)
     libmod = a2x_import.pkg("_lib")
     torch.manual_seed(0)
-    model = M.Airv2xCoBEVT(cfg["model_args"]).cuda().eval()
-    types = (["vehicle"] * 3 + ["rsu"] * 2 + ["drone"] * 2)
-    types = sorted(types[:2] + types[3:4] + types[5:6] + types[2:3] + types[4:5] + types[6:7][:0], key=lambda t: {"vehicle": 0, "rsu": 1, "drone": 2}[t])[:n_agents] \
-        if n_agents != 5 else ["vehicle", "vehicle", "rsu", "rsu", "drone"]
+    model = (M.Airv2xCoBEVT if which == "cobevt" else M.Airv2xV2XVit)(cfg["model_args"]).cuda().eval()
+    types = ["vehicle", "vehicle", "rsu", "rsu", "drone"][:n_agents] if n_agents <= 5 else \
+        ["vehicle"] * 3 + ["rsu"] * 2 + ["drone"] * (n_agents - 5)
     rng = cfg["preprocess"]["cav_lidar_range"]
     clouds = [bench.synth_cloud(k, bench.N_POINTS, rng) for k in range(len(types))]
     offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
@@ -31,6 +35,15 @@ def main():
     for t in ("vehicle", "rsu", "drone"):
         n = sum(1 for a in types if a == t)
         dd[t] = {"record_len": [n], "batch_idxs": [0] if n else []}
+    if which == "v2xvit":
+        L = sum(cfg["model_args"]["max_cav"].values())
+        prior = torch.zeros(1, L, 3)
+        scm = torch.eye(4, dtype=torch.float64).repeat(1, L, 1, 1)
+        for i, t in enumerate(types):
+            prior[0, i] = torch.tensor([0.1 * i, float(i % 2), 1.0 if t == "rsu" else 0.0])
+        scm[0, 1, 0, 3], scm[0, 1, 1, 3] = 6.0, -3.0
+        scm[0, 1, :2, :2] = torch.tensor([[0.9801, -0.1987], [0.1987, 0.9801]], dtype=torch.float64)
+        dd["prior_encoding"], dd["spatial_correction_matrix"] = prior, scm
     with torch.no_grad():
         for _ in range(3):
             model(dd)
@@ -52,7 +65,7 @@ def main():
         g[0] += a.elapsed_time(b)
         g[1] += 1
     top = sorted(((k, round(v[0], 3), v[1]) for k, v in groups.items()), key=lambda x: -x[1])[:10]
-    print(json.dumps({"metric": "scenes/sec (eval fwd) CoBEVT %d-agent 60k-pt, L=7" % len(types), "value": 1000.0 / ms,
+    print(json.dumps({"metric": "scenes/sec (eval fwd) %s %d-agent 60k-pt" % (which, len(types)), "value": 1000.0 / ms,
                       "ms_per_scene": ms, "agents": types, "top_calls_ms": top}))
 
 

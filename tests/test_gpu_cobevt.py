@@ -58,7 +58,10 @@ def test_regroup(ops):
     assert mask.tolist() == [[1, 1, 0, 0], [1, 1, 1, 0]]
 
 
-@pytest.mark.parametrize("case", [(2, 7, 8, 16, 8, 32, 4), (1, 3, 8, 8, 4, 64, 2), (1, 5, 4, 12, 16, 16, 4)])
+@pytest.mark.parametrize("case", [(2, 7, 8, 16, 8, 32, 4), (1, 3, 8, 8, 4, 64, 2), (1, 5, 4, 12, 16, 16, 4),
+                                  # small windows (128 / n windows per CTA): the V2X-ViT pyramid shapes, partial groups
+                                  (3, 1, 8, 12, 16, 16, 2), (2, 1, 8, 16, 8, 32, 4), (2, 1, 12, 8, 4, 64, 4),
+                                  (2, 2, 4, 8, 8, 32, 2), (1, 1, 4, 12, 8, 32, 4)])
 @pytest.mark.parametrize("grid_mode", [False, True])
 def test_window_attention(ops, case, grid_mode):
     """softmax(q*scale k^T + rel-pos bias, masked keys) v per window / grid cell == Attention.forward without the
@@ -69,9 +72,10 @@ def test_window_attention(ops, case, grid_mode):
     qkv = torch.randn(B * L, H, W, 3 * D, generator=g)
     table = torch.randn((2 * L - 1) * (2 * w - 1) ** 2, heads, generator=g)
     mask = torch.ones(B, L, dtype=torch.int32)
-    mask[0, L - 1] = 0
-    if B > 1:
-        mask[1, 1:] = 0
+    if L > 1:
+        mask[0, L - 1] = 0
+        if B > 1:
+            mask[1, 1:] = 0
     out = ops.Act.empty((B * L, H, W, D), "cuda", True)
     ops.window_attention_fwd(qkv.cuda(), table.cuda(), mask.cuda(), B, L, heads, dh, w, grid_mode, out)
     # reference: identity linears around the oracle's attention core
