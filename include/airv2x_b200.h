@@ -189,6 +189,24 @@ int a2x_roi_mask(const float* theta, const int* valid, int n, int h, int w, int 
 int a2x_warp_affine_bwd(const float* dout, int dout_cs, const float* theta, int n, int hi, int wi, int c, int ho, int wo,
                         int align_corners, float* dsrc, int dsrc_cs, a2x_stream_t stream);
 
+/* ---------------------------------------------------------------- detection decode + rotated NMS (batch 1 inference)
+ * Replaces VoxelPostprocessor.post_process_airv2x (data_utils/post_processor/voxel_postprocessor.py:666-840):
+ * objectness gate (sigmoid(obj) > obj_threshold), delta_to_boxes3d (:585-635), boxes_to_corners_3d order "hwl"
+ * (utils/box_utils.py:195-258), remove_large_pred_bbx / remove_bbx_abnormal_z (:981-1035), nms_rotated (:823-868:
+ * top-1000 by score, greedy, IoU of the first four corners' polygons > nms_threshold; shapely -> convex-quad clipping
+ * in double precision), range mask (:399-430). heads: NHWC [H][W][heads_cs] = cls (class-major, A*num_class) | reg
+ * (7A) | obj (A); anchors: [H][W][A][7] (x, y, z, h, w, l, yaw). Outputs (device, score-descending): corners
+ * [max_out][8][3], scores, labels, boxes [max_out][7], anchor index; *n_out_dev = count. *status_dev != 0 reports an
+ * internal capacity overflow (bit 0: candidates, bit 1: score ties at the top-1000 cut). No host sync. */
+size_t a2x_postprocess_workspace_bytes(int n_anchors);
+int a2x_postprocess_det(const float* heads, int heads_cs, int H, int W, int A, int num_class, const float* anchors,
+                        float obj_threshold, float nms_threshold, const float* lidar_range6, void* workspace,
+                        size_t workspace_bytes, float* out_corners, float* out_scores, int* out_labels, float* out_boxes,
+                        int* out_anchor_index, int max_out, int* n_out_dev, int* status_dev, a2x_stream_t stream);
+/* out[i][j] = IoU of the xy polygons (first four corners) of boxes_a[i] and boxes_b[j], each [n][8][3]: the matching
+ * step of caluclate_tp_fp (utils/eval_utils_opv2v.py:41-95) */
+int a2x_rotated_iou_matrix(const float* boxes_a, int na, const float* boxes_b, int nb, float* out, a2x_stream_t stream);
+
 /* ---------------------------------------------------------------- BatchNorm / ReLU / masks (HBM-bound)
  * Replace nn.BatchNorm2d(eps 1e-3, momentum 0.01) + nn.ReLU and their autograd
  * (opencood/models/common_modules/base_bev_backbone.py:52-66, :82-90) and the bias+ReLU of
