@@ -155,6 +155,77 @@ __global__ void mask_rate_ego_kernel(float* __restrict__ mask, int HW, const int
     if ((threadIdx.x & 31) == 0 && cnt != 0.f) atomicAdd(&ones[b], cnt);
 }
 
+// ---------------------------------------------------------------------------------------------- sparse feature select
+// Where2comm transmits only the BEV cells its communication mask selected (where2comm_fuse.py:83-149, :237). Sender:
+// warp-ballot compaction of the selected cells of one agent's level-0 map into (count, cell index, feature row)
+// records. Receiver: the records of every agent are pulled through a pointer table (local memory after an all-gather,
+// or PEER GPU memory over NVLink: system-scope loads) and scattered into the dense, zero-filled per-agent maps the
+// fusion kernels read. Bytes on the wire = mask rate x dense size; no host round trip for the counts.
+__global__ void __launch_bounds__(256) mask_compact_kernel(const float* __restrict__ x, int x_cs,
+                                                           const float* __restrict__ mask, int force_all, int hw,
+                                                           int C, int* __restrict__ hdr, int* __restrict__ idx,
+                                                           float* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int q = C >> 2;
+    for (int p0 = warp * 32; p0 < hw; p0 += nwarps * 32) {
+        const int p = p0 + lane;
+        const bool nz = p < hw && mask[p] != 0.f;
+        const bool sel = p < hw && (force_all || nz);
+        const unsigned ms = __ballot_sync(0xffffffffu, sel), mz = __ballot_sync(0xffffffffu, nz);
+        int base = 0;
+        if (lane == 0) {
+            if (ms) base = atomicAdd(&hdr[0], __popc(ms));
+            if (mz) atomicAdd(&hdr[1], __popc(mz));  // cells selected by the mask itself (the communication rate)
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (sel) idx[base + __popc(ms & ((1u << lane) - 1))] = p;
+        unsigned rem = ms;
+        int r = 0;
+        while (rem) {  // the warp copies the selected rows one by one (C/4 float4 per row)
+            const int b = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const float4* src = reinterpret_cast<const float4*>(x + (long long)(p0 + b) * x_cs);
+            float4* dst = reinterpret_cast<float4*>(vals + (long long)(base + r) * C);
+            for (int c = lane; c < q; c += 32) dst[c] = src[c];
+            ++r;
+        }
+    }
+}
+
+__device__ __forceinline__ float4 ld_sys_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_sys_i32(const int* p) {
+    int v;
+    asm volatile("ld.global.relaxed.sys.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// dst[a][idx][:] = vals[a][r][:] for r < count[a]; dst is zero-filled by the caller. blockIdx.y = agent.
+__global__ void __launch_bounds__(256) mask_decompact_ptrs_kernel(const char* const* __restrict__ bufs, long long off_idx,
+                                                                  long long off_vals, int C, int hw,
+                                                                  float* __restrict__ dst) {
+    const int a = blockIdx.y;
+    const char* base = bufs[a];
+    const int count = min(ld_sys_i32(reinterpret_cast<const int*>(base)), hw);
+    const int* idx = reinterpret_cast<const int*>(base + off_idx);
+    const float* vals = reinterpret_cast<const float*>(base + off_vals);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int q = C >> 2;
+    for (int r = warp; r < count; r += nwarps) {
+        const int p = ld_sys_i32(idx + r);
+        const float4* src = reinterpret_cast<const float4*>(vals + (long long)r * C);
+        float4* out = reinterpret_cast<float4*>(dst + ((long long)a * hw + p) * C);
+        for (int c = lane; c < q; c += 32) out[c] = ld_sys_f4(src + c);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- attention fusion
 // One thread group of G = min(32, C/4) lanes per pixel, V = C/(4G) float4 per lane.
 template <int G, int V>
@@ -318,6 +389,33 @@ int a2x_comm_smooth_mask(const float* conf, const float* gauss_w, const float* g
 int a2x_comm_topk_mask(const float* smooth, int n, int hw, const int* k_per_agent, float* mask, a2x_stream_t stream) {
     A2X_REQUIRE(smooth && k_per_agent && mask && n > 0 && hw > 0, "comm_topk_mask: bad args");
     topk_mask_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(smooth, hw, k_per_agent, mask);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_mask_compact(const float* x, int x_cs, const float* mask, int force_all, int hw, int C, int* hdr, int* idx,
+                     float* vals, a2x_stream_t stream) {
+    A2X_REQUIRE(x && mask && hdr && idx && vals && hw > 0 && C > 0 && C % 4 == 0 && x_cs >= C, "mask_compact: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    A2X_CHECK_CUDA(cudaMemsetAsync(hdr, 0, 2 * sizeof(int), st));
+    int blocks = (hw + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    mask_compact_kernel<<<blocks, 256, 0, st>>>(x, x_cs, mask, force_all, hw, C, hdr, idx, vals);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_mask_decompact_ptrs(const void* const* bufs_dev, long long off_idx_bytes, long long off_vals_bytes, int n_agents,
+                            int hw, int C, float* dst, a2x_stream_t stream) {
+    A2X_REQUIRE(bufs_dev && dst && n_agents > 0 && hw > 0 && C > 0 && C % 4 == 0 && off_idx_bytes % 4 == 0 &&
+                    off_vals_bytes % 16 == 0,
+                "mask_decompact_ptrs: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    A2X_CHECK_CUDA(cudaMemsetAsync(dst, 0, (size_t)n_agents * hw * C * sizeof(float), st));
+    mask_decompact_ptrs_kernel<<<dim3(148, n_agents), 256, 0, st>>>((const char* const*)bufs_dev, off_idx_bytes,
+                                                                   off_vals_bytes, C, hw, dst);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

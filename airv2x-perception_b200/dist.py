@@ -126,3 +126,72 @@ class AgentParallelCoBEVT:
         nc, nr = A * K, 7 * A
         nchw = heads.permute(0, 3, 1, 2)
         return {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A]}
+
+
+class AgentParallelWhere2comm:
+    """Airv2xWhere2com inference with the agents of ONE scene sharded one per rank (rank 0 = ego). Each rank publishes
+    the level-0 cells its communication mask selected (warp-ballot compaction, `a2x_mask_compact`) and its dense deeper
+    levels in ONE buffer; transports: "nccl" (one all_gather_into_tensor of the buffers) or "peer" (symmetric memory:
+    the receivers' decompaction / copy kernels pull the records over NVLink, bytes on the wire ~ mask rate)."""
+
+    def __init__(self, model, agent_types, transport="nccl", group=None):
+        assert transport in ("nccl", "peer")
+        self.model, self.group, self.transport = model, group, transport
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert len(agent_types) == self.world, "one agent per rank"
+        self.agent_types = list(agent_types)
+        self.per_rank, _ = agent_rank_plan(agent_types)
+        self._state = None
+
+    def _setup(self, dev):
+        m = self.model
+        skeleton = dict(self.per_rank[self.rank])
+        skeleton["raw_points"] = True
+        lay = dict(m._layout(skeleton, dev))
+        lay["ego_flags"] = torch.tensor([1 if self.rank == 0 else 0], dtype=torch.uint8, device=dev)
+        h2, w2 = lay["ny"] // 2, lay["nx"] // 2
+        total = m.engine.ap_regions(h2, w2)["total"]
+        if self.transport == "peer":
+            import torch.distributed._symmetric_memory as symm_mem
+
+            buf = symm_mem.empty(total, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            table = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+
+            def exchange():
+                hdl.barrier(channel=0)
+                return table
+
+            def done():
+                hdl.barrier(channel=1)
+        else:
+            buf = torch.empty(total, dtype=torch.float32, device=dev)
+            gathered = torch.empty(self.world, total, dtype=torch.float32, device=dev)
+            table = torch.tensor([gathered.data_ptr() + r * total * 4 for r in range(self.world)], dtype=torch.int64,
+                                 device=dev)
+
+            def exchange():
+                dist.all_gather_into_tensor(gathered, buf, group=self.group)
+                return table
+
+            def done():
+                pass
+        self._state = (lay, buf, exchange, done)
+
+    def __call__(self, points, preprocess):
+        """points: [P, 4] f32 cloud of THIS rank's agent. Returns the reference's output dict (same on every rank)."""
+        m = self.model
+        assert not m.training, "agent-parallel mode is inference only"
+        dev = next(m.parameters()).device
+        if self._state is None:
+            self._setup(dev)
+        lay, buf, exchange, done = self._state
+        dd = dict(self.per_rank[self.rank])
+        pts = points.to(device=dev, dtype=torch.float32)
+        dd["raw_points"] = {"points": pts, "offsets": torch.tensor([0, pts.shape[0]], dtype=torch.int32),
+                            "preprocess": preprocess, "filter": True}
+        lidar = m._lidar(dd, dev, lay)
+        lidar["raw"]["ego_flags"] = lay["ego_flags"]
+        heads, aux = m.engine.forward_agent_parallel(m._param_dict(), lidar, lay, self.rank, self.world, buf, exchange, done)
+        m._last_aux = aux
+        return m._output_dict(heads, {"record_len": [self.world]})

@@ -480,6 +480,22 @@ def comm_rate_ego(mask, hw, n_scenes, scene_start, scene_len, ones):
          stream_ptr())
 
 
+def mask_compact(x, mask, force_all, hdr, idx, vals):
+    """x: NHWC [1, h, w, C]; mask: [h, w] float; hdr: int32 [>=2]; idx: int32 [hw]; vals: float [hw, C]"""
+    _, h, w, c = x.shape
+    call("a2x_mask_compact", _ptr(x), c_int(_cs(x)), _ptr(mask), c_int(int(force_all)), c_int(h * w), c_int(c), _ptr(hdr),
+         _ptr(idx), _ptr(vals), stream_ptr())
+
+
+def mask_decompact_ptrs(ptr_table, off_idx_bytes, off_vals_bytes, n_agents, dst):
+    """ptr_table: int64 device tensor [n] of record-buffer base pointers; dst: dense [n, h, w, C] (zero-filled here)"""
+    n, h, w, c = dst.shape
+    assert n == n_agents and dst.is_contiguous()
+    call("a2x_mask_decompact_ptrs", _ptr(ptr_table), c_ll(off_idx_bytes), c_ll(off_vals_bytes), c_int(n), c_int(h * w),
+         c_int(c), _ptr(dst), stream_ptr())
+    return dst
+
+
 def att_fuse_fwd(x, out):
     """x: dense NHWC tensor [n_agents,h,w,c] of one scene; out: Act [1,h,w,c] (or [h,w,c])"""
     n, h, w, c = x.shape

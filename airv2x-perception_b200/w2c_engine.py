@@ -410,6 +410,103 @@ class W2CEngine:
         aux = dict(comm_rate=nz, ones=ones, hw=hw)
         return heads, aux
 
+    # ------------------------------------------------------------------ agent-parallel inference (one agent per GPU)
+    def ap_regions(self, h2, w2):
+        """float offsets of one rank's exchange buffer: header | cell indices | selected level-0 rows | dense levels 1.."""
+        hw = h2 * w2
+        reg, pos = {}, 0
+        for name, n in (("hdr", 64), ("idx", (hw + 3) // 4 * 4), ("vals", hw * self.num_filters[0])):
+            reg[name] = (pos, n)
+            pos += n
+        hh, ww = h2, w2
+        for i in range(1, len(self.layer_nums)):
+            hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+            reg["lvl%d" % i] = (pos, hh * ww * self.num_filters[i], (hh, ww, self.num_filters[i]))
+            pos += hh * ww * self.num_filters[i]
+        reg["total"] = pos
+        return reg
+
+    def forward_agent_parallel(self, P, lidar, layout, rank, n_agents, xbuf, exchange, done):
+        """Eval-mode Where2comm with the scene's agents sharded one per rank. Every rank runs the
+        per-agent half (encoder, un-masked pass for its own confidence map, mask, masked blocks), publishes ONE buffer —
+        the warp-ballot-compacted level-0 cells its mask selected plus its dense level-1.. maps — and pulls the peers'
+        buffers (`exchange()` -> device table of per-rank buffer pointers: local copies after an all-gather or peer
+        memory) straight into the dense per-agent tensors the fusion kernels read. `xbuf`: this rank's flat fp32 buffer
+        of ap_regions()["total"] elements. Returns (heads, aux) like forward(); identical on every rank."""
+        self._begin_step()
+        W = self._pack_weights(P)
+        canvas = self._encode(P, lidar, layout, False, None)
+        x0 = self._block(P, W, 0, canvas, False, 0, "A", None)
+        _, h2, w2, c0 = x0.shape
+        hw = h2 * w2
+        reg = self.ap_regions(h2, w2)
+        assert xbuf.numel() >= reg["total"] and xbuf.dtype == torch.float32
+        hdr = xbuf[reg["hdr"][0]:reg["hdr"][0] + 64].view(torch.int32)
+        idx = xbuf[reg["idx"][0]:reg["idx"][0] + reg["idx"][1]].view(torch.int32)
+        vals = xbuf[reg["vals"][0]:reg["vals"][0] + reg["vals"][1]]
+        ops.count_nonzero(canvas.hi, hdr[2:4].view(torch.int64))
+        # pass A on the own map -> confidence -> mask (where2comm_fuse.py:83-149, eval branch)
+        catA = self._act("A.cat", (1, h2, w2, self.c_cat))
+        xa = x0
+        for i in range(len(self.layer_nums)):
+            if i > 0:
+                xa = self._block(P, W, i, xa, False, 0, "A", None)
+            c_lo = sum(self.up_filters[:i])
+            self._deblock(P, W, i, xa, catA.slice_c(c_lo, c_lo + self.up_filters[i]), False, 0, "A", None)
+        _, _, headsA = self._shrink_heads(P, W, catA, "A")
+        mask = self._buf("mask", (1, h2, w2))
+        thr = float(self.comm["threshold"])
+        if self.fully or not thr:
+            mask.fill_(1.0)
+        else:
+            conf, smooth = self._buf("conf", (1, h2, w2)), self._buf("smooth", (1, h2, w2))
+            ops.comm_confidence(headsA, self.A * self.K, conf)
+            gs = self.comm.get("gaussian_smooth")
+            ops.comm_smooth_mask(conf, P.get("fusion_net.naive_communication.gaussian_filter.weight"),
+                                 P.get("fusion_net.naive_communication.gaussian_filter.bias"), gs["k_size"] if gs else 0,
+                                 1, h2, w2, thr, True, smooth, mask)
+        # sparse feature select: what this agent transmits (the ego keeps every cell, where2comm_fuse.py:137-143)
+        ego = rank == 0
+        ops.mask_compact(x0.hi, mask[0], ego or self.fully, hdr, idx, vals)
+        if ego:
+            mask.fill_(1.0)
+        x0m = self._act("B.x0m", x0.shape)
+        ops.affine_act(x0.hi, None, None, False, x0m, mask=mask)
+        xb = x0m
+        for i in range(1, len(self.layer_nums)):
+            xb = self._block(P, W, i, xb, False, 0, "B", None)
+            o, n, _ = reg["lvl%d" % i]
+            xbuf[o:o + n].copy_(xb.hi.reshape(-1))
+        # ---- the path's one exchange
+        table = exchange()
+        xfull0 = self._buf("ap.x0", (n_agents, h2, w2, c0))
+        ops.mask_decompact_ptrs(table, reg["idx"][0] * 4, reg["vals"][0] * 4, n_agents, xfull0)
+        start = self._buf("ap.start", (1,), torch.int32)
+        length = self._buf("ap.len", (1,), torch.int32)
+        start.zero_()
+        length.fill_(n_agents)
+        hdrs = self._buf("ap.hdrs", (n_agents, 1, 1, 64))
+        ops.regroup_ptrs(table, (1, 1, 64), start, length, 1, n_agents, Act(hdrs))
+        levels = [xfull0]
+        for i in range(1, len(self.layer_nums)):
+            o, n, shp = reg["lvl%d" % i]
+            xf = self._buf("ap.x%d" % i, (n_agents,) + shp)
+            ops.regroup_ptrs(table + o * 4, shp, start, length, 1, n_agents, Act(xf))
+            levels.append(xf)
+        done()
+        # ---- fusion (where2comm_fuse.py:214-262), replicated on every rank
+        catB = self._act("B.cat", (1, h2, w2, self.c_cat))
+        for i, xf in enumerate(levels):
+            fused = self._act("B.fuse%d" % i, (1,) + tuple(xf.shape[1:]))
+            ops.att_fuse_fwd(xf, fused)
+            c_lo = sum(self.up_filters[:i])
+            self._deblock(P, W, i, fused, catB.slice_c(c_lo, c_lo + self.up_filters[i]), False, 0, "B", None)
+        _, _, heads = self._shrink_heads(P, W, catB, "B")
+        hi = hdrs.view(n_agents, 64).view(torch.int32)
+        aux = dict(comm_rate=hi[:, 2:4].contiguous().view(torch.int64).sum(), hw=hw,
+                   ones=hi[:, 1].sum().to(torch.float32).reshape(1))
+        return heads, aux
+
     def set_k(self, k_list, record_len):
         """write the per-scene top-K sizes into the pinned staging buffer the (possibly graph-captured) H2D copy reads"""
         k_host = self._pinned("k_host", (sum(record_len),), torch.int32)

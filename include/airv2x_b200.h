@@ -313,6 +313,16 @@ int a2x_comm_smooth_mask(const float* conf, const float* gauss_w, const float* g
                          float threshold, int write_mask, float* smooth, float* mask, a2x_stream_t stream);
 /* train mode: mask[a] = 1 on the k_per_agent[a] largest smooth values of agent a (device array) */
 int a2x_comm_topk_mask(const float* smooth, int n, int hw, const int* k_per_agent, float* mask, a2x_stream_t stream);
+/* Sparse feature select (the payload an agent transmits, where2comm_fuse.py:237): warp-ballot compaction of the cells
+ * of one agent's level-0 map [hw][C] selected by its mask (all cells if force_all, the ego). hdr[0] = records written,
+ * hdr[1] = cells the mask itself selected (communication-rate numerator); idx[r] = cell, vals[r][:] = feature row. */
+int a2x_mask_compact(const float* x, int x_cs, const float* mask, int force_all, int hw, int C, int* hdr, int* idx,
+                     float* vals, a2x_stream_t stream);
+/* Receiver: dst [n_agents][hw][C] is zero-filled, then for every agent a the records at bufs_dev[a] (+0: count,
+ * +off_idx_bytes: idx, +off_vals_bytes: vals) are scattered into dst[a]. bufs_dev: DEVICE table of per-agent base
+ * pointers, local (after an all-gather) or peer-GPU memory (NVLink P2P: the gather fused into the decompaction). */
+int a2x_mask_decompact_ptrs(const void* const* bufs_dev, long long off_idx_bytes, long long off_vals_bytes, int n_agents,
+                            int hw, int C, float* dst, a2x_stream_t stream);
 /* ones[b] = sum of the scene's mask (before ego override); then mask[ego of scene b] = 1 */
 int a2x_comm_rate_ego(float* mask, int hw, int n_scenes, const int* scene_start, const int* scene_len, float* ones,
                       a2x_stream_t stream);

@@ -303,3 +303,27 @@ def test_deconv_epilogue_batch_statistics(ops):
     ops.deconv_fwd(ops.split(nhwc(x)), pw, cout, s, y, stats=stats)
     ref = torch.cat([y.hi.double().sum((0, 1, 2)), (y.hi.double() ** 2).sum((0, 1, 2))])
     assert float((stats - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_mask_compact_decompact_roundtrip(ops):
+    """sparse feature select (warp-ballot compaction) followed by the pointer-table scatter == x * mask, per agent"""
+    g = _g(11)
+    n, H, W, C = 3, 13, 21, 64
+    hw = H * W
+    x = rnd(g, n, H, W, C)
+    mask = (torch.rand(n, H, W, generator=g) > 0.7).float().cuda()
+    total = 64 + (hw + 3) // 4 * 4 + hw * C
+    bufs = torch.zeros(n, total, device="cuda")
+    for a in range(n):
+        hdr = bufs[a, :64].view(torch.int32)
+        idx = bufs[a, 64:64 + (hw + 3) // 4 * 4].view(torch.int32)
+        vals = bufs[a, 64 + (hw + 3) // 4 * 4:]
+        ops.mask_compact(x[a:a + 1], mask[a], a == 0, hdr, idx, vals)
+        assert int(hdr[1]) == int(mask[a].sum())                          # communication-rate numerator
+        assert int(hdr[0]) == (hw if a == 0 else int(mask[a].sum()))      # the ego sends every cell
+    table = torch.tensor([bufs[a].data_ptr() for a in range(n)], dtype=torch.int64, device="cuda")
+    dst = torch.full((n, H, W, C), 5.0, device="cuda")
+    ops.mask_decompact_ptrs(table, 64 * 4, (64 + (hw + 3) // 4 * 4) * 4, n, dst)
+    want = x * mask[..., None]
+    want[0] = x[0]
+    assert torch.equal(dst, want)

@@ -60,3 +60,22 @@ def test_config_json_matches_yaml_keys():
     assert a["modality_fusion"]["base_bev_backbone"]["layer_nums"] == [3, 5, 8]
     assert a["where2com_fusion"]["communication"]["threshold"] == 0.01
     assert cfg["preprocess"]["args"]["max_voxel_train"] == 32000
+
+
+def test_agent_parallel_exchange_regions():
+    """layout of the one buffer an agent publishes (header | cell indices | selected level-0 rows | dense deeper levels)"""
+    import json
+    import os
+
+    import a2x_import
+
+    E = a2x_import.pkg("w2c_engine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = json.load(open(os.path.join(root, "configs", "airv2x_intermediate_where2com.json")))
+    eng = E.W2CEngine(cfg["model_args"], "cpu")
+    reg = eng.ap_regions(100, 352)
+    assert reg["hdr"] == (0, 64) and reg["idx"] == (64, 35200) and reg["vals"] == (64 + 35200, 35200 * 64)
+    assert reg["lvl1"][2] == (50, 176, 128) and reg["lvl2"][2] == (25, 88, 256)
+    assert reg["total"] == 64 + 35200 + 35200 * 64 + 50 * 176 * 128 + 25 * 88 * 256
+    for k in ("idx", "vals", "lvl1", "lvl2"):
+        assert reg[k][0] % 4 == 0          # 16-byte aligned regions (float4 / int4 access)
