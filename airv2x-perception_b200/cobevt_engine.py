@@ -35,9 +35,11 @@ class CoBEVTEngine(W2CEngine):
         sh = args["shrink_header"]
         assert sh["use"] and list(sh["kernal_size"]) == [1] and list(sh["stride"]) == [1] and list(sh["padding"]) == [0], \
             "only the airv2x shrink header (1x1 s1 + 3x3) is implemented"
-        assert not args.get("compression", 0), "NaiveCompressor (compression > 0) is not implemented"
+        self.compression = int(args.get("compression", 0) or 0)
         self.c_cat = sum(self.up_filters)
         self.c_shrink = sh["dim"][0]
+        assert self.compression == 0 or (256 % self.compression == 0 and (256 // self.compression) % 64 == 0), \
+            "NaiveCompressor: 256 / compression must be a multiple of 64 channels (compression in {1, 2, 4})"
         self.A = args["anchor_number"]
         self.K = args["num_class"]
         assert args["obj_head"], "obj_head: false not implemented"
@@ -63,6 +65,29 @@ class CoBEVTEngine(W2CEngine):
                           "%s.%s_ffd.fn.net.0.weight" % (p, part), "%s.%s_ffd.fn.net.3.weight" % (p, part)]
         return names + ["fusion_net.mlp_head.3.weight"]
 
+    @staticmethod
+    def _compressor_convs():
+        """(conv, its BatchNorm) of NaiveCompressor: encoder conv, two decoder convs (naive_compress.py:10-36)"""
+        return {"naive_compressor.encoder.0": "naive_compressor.encoder.1",
+                "naive_compressor.decoder.0": "naive_compressor.decoder.1",
+                "naive_compressor.decoder.3": "naive_compressor.decoder.4"}
+
+    def _compress(self, P, W, x):
+        """NaiveCompressor.forward (eval): 3 x [conv3x3 + bias -> BatchNorm (running stats) -> ReLU]; the conv bias is
+        folded into the BN shift, so each layer is one tap-GEMM with an affine + ReLU epilogue."""
+        convs = self._compressor_convs()
+        for li, (conv, bn) in enumerate(convs.items()):
+            co = P[conv + ".weight"].shape[0]
+            scale, shift = self._buf("cmp.scale%d" % li, (co,)), self._buf("cmp.shift%d" % li, (co,))
+            ops.bn_eval_affine(P[bn + ".weight"], P[bn + ".bias"], P[bn + ".running_mean"], P[bn + ".running_var"],
+                               scale, shift)
+            shift.addcmul_(scale, P[conv + ".bias"])
+            last = li == len(convs) - 1
+            y = self._act("cmp.y%d" % li, x.shape[:3] + (co,), split=(False if last else None))
+            ops.conv_fwd(x, W[conv], 3, 1, y, scale=scale, shift=shift, relu=True)
+            x = y
+        return x.hi
+
     def _pack_weights(self, P):
         W, jobs = {}, []
         for i, ln in enumerate(self.layer_nums):
@@ -84,6 +109,12 @@ class CoBEVTEngine(W2CEngine):
             co, ci = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (k * k, co, ci), (k * k, ci, co))
             jobs.append(ops.conv_pack_job(w, W[name]))
+        if self.compression:
+            for name in self._compressor_convs():
+                w = P[name + ".weight"]
+                co, ci = w.shape[0], w.shape[1]
+                W[name] = self._packed(name, (9, co, ci), (9, ci, co))
+                jobs.append(ops.conv_pack_job(w, W[name]))
         for name in self._linear_names():  # nn.Linear [out, in] == 1x1 conv OIHW [out, in, 1, 1]
             w = P[name]
             co, ci = w.shape
@@ -167,12 +198,21 @@ class CoBEVTEngine(W2CEngine):
             c0 = sum(self.up_filters[:i])
             self._deblock(P, W, i, x, cat.slice_c(c0, c0 + self.up_filters[i]), False, 0, "E", None)
         y1 = self._act("E.s1", (N, h2, w2, self.c_shrink))
-        y2 = out if out is not None else self._buf("E.s2", (N, h2, w2, self.c_shrink))
-        assert tuple(y2.shape) == (N, h2, w2, self.c_shrink)
+        if self.compression:
+            y2a = self._act("E.s2c", (N, h2, w2, self.c_shrink))
+        else:
+            y2 = out if out is not None else self._buf("E.s2", (N, h2, w2, self.c_shrink))
+            assert tuple(y2.shape) == (N, h2, w2, self.c_shrink)
+            y2a = Act(y2)
         ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,
                      shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
-        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, Act(y2),
+        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, y2a,
                      shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
+        if self.compression:  # airv2x_cobevt.py:121-123
+            y2 = self._compress(P, W, y2a)
+            if out is not None:
+                out.copy_(y2)
+                y2 = out
         return y2
 
     def fuse_heads(self, P, W, feat, layout, peer_ptrs=None):

@@ -183,7 +183,7 @@ static int make_halo_map(CUtensorMap* m, const void* base, int n, int h, int w, 
 // 3x3 stride-1 window GEMM through the halo kernel. sign = +1: forward taps (r-1, c-1); -1: data-gradient (1-r, 1-c).
 static int run_halo(const a2x_operand* a, int n, int h, int w, int k_ch, int ncols, const a2x_weights* wts, int sign,
                     const a2x_output* y, const float* scale, const float* shift, int relu, int accumulate,
-                    double* stats, cudaStream_t st) {
+                    double* stats, cudaStream_t st, const a2x_bn_bwd_stats* bst = nullptr) {
     ThParams p{};
     const int bn = bn_for(ncols);
     if (a->b16) {
@@ -228,6 +228,14 @@ static int run_halo(const a2x_operand* a, int n, int h, int w, int k_ch, int nco
     p.accumulate = accumulate;
     p.stats = stats;
     p.stat_c = ncols;
+    if (bst != nullptr) {  // fused BN+ReLU backward reduction of the consumer layer (data-gradient epilogue)
+        if (!bst->z || !bst->scale || !bst->shift || !bst->mean || !bst->invstd || !bst->sums || bst->z_cs != y->cs) {
+            set_error("conv2d_dgrad: bad bn_bwd_stats (z must share the output's pixel stride)");
+            return 1;
+        }
+        p.stats = bst->sums;
+        p.bz = bst->z; p.bscale = bst->scale; p.bshift = bst->shift; p.bmean = bst->mean; p.binvstd = bst->invstd;
+    }
     p.base_offset_mode = g_debug[6];
     if (g_debug[9]) p.relu = 77;
     const int tiles_n = (ncols + bn - 1) / bn;
@@ -663,7 +671,14 @@ int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_w
 
 int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
                      int accumulate, a2x_stream_t stream) {
+    return a2x_conv2d_dgrad_ex(s, dy, w, dx, dx_cs, accumulate, nullptr, stream);
+}
+
+int a2x_conv2d_dgrad_ex(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
+                        int accumulate, const a2x_bn_bwd_stats* bn_stats, a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
+    A2X_REQUIRE(!bn_stats || (s->ksize == 3 && s->stride == 1),
+                "conv2d_dgrad: the fused BN backward reduction is implemented for 3x3 stride-1 windows");
     if (int r = check_operand(dy, s->cout, "conv2d_dgrad dy")) return r;
     A2X_REQUIRE(w && w->w32 && dx && dx_cs >= s->cin && dx_cs % 4 == 0, "conv2d_dgrad: bad weights/output");
     A2X_REQUIRE(!dy->b16 || w->w16, "conv2d_dgrad: split input needs bf16 weight planes");
@@ -673,7 +688,8 @@ int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_w
     a2x_output out{dx, nullptr, 0, dx_cs};
     if (s->ksize == 3 && s->stride == 1 && g_debug[7] != 1)
         return run_halo(dy, s->n, s->h, s->w, s->cout, s->cin, w, -1, &out, nullptr, nullptr, 0, accumulate, nullptr,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, bn_stats);
+    A2X_REQUIRE(!bn_stats, "conv2d_dgrad: fused BN backward reduction needs the halo path");
     for (int cls = 0; cls < n_class; ++cls) {
         const int hp = cls >> 1, wp = cls & 1;
         const int step = s->stride;

@@ -105,6 +105,14 @@ struct TgEpi {
     double* stats;
     int stat_c;
     int gh, gw;
+    // BN(train)+ReLU backward reduction fused into a data-gradient epilogue: when bz != null the statistics of
+    // g = v * [bz*bscale+bshift > 0] and g * zhat (zhat = (bz - bmean) * binvstd) replace the plain sum / sum of squares,
+    // i.e. stats[c] += sum g, stats[stat_c + c] += sum g*zhat: pass 1 of the consumer's bn_relu_bwd for free.
+    const float* bz;        // the consumer layer's pre-BN activation, same pixel grid / strides as the output
+    const float* bscale;
+    const float* bshift;
+    const float* bmean;
+    const float* binvstd;
 };
 
 // Drain one 128 x BN accumulator (TMEM buffer at `tacc`) for the tile at (img, h0, w0), column offset n0.
@@ -161,10 +169,28 @@ __device__ __forceinline__ void tg_epilogue(const TgEpi& e, uint32_t tacc, int q
         }
         if (e.stats != nullptr) {  // warp-uniform
             float sq[32];
+            if (e.bz != nullptr) {
+                const long long off = obase + cc;  // plain (non-scattered) output addressing
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                v[i] = valid ? v[i] : 0.f;
-                sq[i] = v[i] * v[i];
+                for (int i = 0; i < 8; ++i) {
+                    float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) z4 = *reinterpret_cast<const float4*>(e.bz + off + 4 * i);
+                    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int ch = cc + 4 * i + k;
+                        const float z = zz[k];
+                        const float g = (valid && z * __ldg(e.bscale + ch) + __ldg(e.bshift + ch) > 0.f) ? v[4 * i + k] : 0.f;
+                        v[4 * i + k] = g;
+                        sq[4 * i + k] = g * (z - __ldg(e.bmean + ch)) * __ldg(e.binvstd + ch);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = valid ? v[i] : 0.f;
+                    sq[i] = v[i] * v[i];
+                }
             }
             const float s1 = warp_transpose_sum(v, lane);
             const float s2 = warp_transpose_sum(sq, lane);
@@ -318,6 +344,7 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
         e.out = p.out; e.osn = p.osn; e.osh = p.osh; e.osw = p.osw; e.sub_c = p.sub_c; e.sub_s = p.sub_s;
         e.sub_sh = p.sub_sh; e.sub_sw = p.sub_sw; e.ncols = p.ncols; e.scale = p.scale; e.shift = p.shift;
         e.relu = p.relu; e.accumulate = p.accumulate; e.stats = p.stats; e.stat_c = p.stat_c; e.gh = p.gh; e.gw = p.gw;
+        e.bz = nullptr; e.bscale = e.bshift = e.bmean = e.binvstd = nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             int t = tile % tiles_m;

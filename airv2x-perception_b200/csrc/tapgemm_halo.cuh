@@ -32,6 +32,11 @@ struct ThParams {
     int relu, accumulate;
     double* stats;
     int stat_c;
+    const float* bz;  // fused BN+ReLU backward reduction (see TgEpi); null = plain statistics
+    const float* bscale;
+    const float* bshift;
+    const float* bmean;
+    const float* binvstd;
     int base_offset_mode;  // debug: 0 = descriptor base_offset 0, 1 = (start >> 7) & 7
 };
 
@@ -197,6 +202,7 @@ __global__ void __launch_bounds__(192) tapgemm_halo_kernel(const __grid_constant
         e.out = p.out; e.osn = p.osn; e.osh = p.osh; e.osw = p.osw; e.sub_c = 1 << 30; e.sub_s = 1;
         e.sub_sh = 0; e.sub_sw = 0; e.ncols = p.ncols; e.scale = p.scale; e.shift = p.shift;
         e.relu = p.relu; e.accumulate = p.accumulate; e.stats = p.stats; e.stat_c = p.stat_c; e.gh = p.gh; e.gw = p.gw;
+        e.bz = p.bz; e.bscale = p.bscale; e.bshift = p.bshift; e.bmean = p.bmean; e.binvstd = p.binvstd;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             int t = tile % tiles_m;

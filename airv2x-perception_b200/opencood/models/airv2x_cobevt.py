@@ -90,6 +90,14 @@ class Airv2xCoBEVT(Airv2xWhere2com):
         if self.shrink_flag:
             self.shrink_conv = _shrink_params(args["shrink_header"])
         self.compression = args["compression"] > 0
+        if self.compression:  # NaiveCompressor(256, ratio), naive_compress.py:5-42 (parameter containers only)
+            c, r = 256, args["compression"]
+            bn = lambda ch: nn.BatchNorm2d(ch, eps=1e-3, momentum=0.01)
+            nc = nn.Module()
+            nc.encoder = nn.Sequential(nn.Conv2d(c, c // r, 3, padding=1), bn(c // r), nn.ReLU())
+            nc.decoder = nn.Sequential(nn.Conv2d(c // r, c, 3, padding=1), bn(c), nn.ReLU(), nn.Conv2d(c, c, 3, padding=1),
+                                       bn(c), nn.ReLU())
+            self.naive_compressor = nc
         args["fax_fusion"]["agent_size"] = self.max_cav_num  # airv2x_cobevt.py:49
         self.fusion_net = _SwapFusionEncoderParams(args["fax_fusion"])
         self.outC = args["outC"]

@@ -296,13 +296,24 @@ def warp_affine_bwd(dout, theta, dsrc, align_corners=False):
     return dsrc
 
 
-def conv_dgrad(dy, w, k, stride, dx, accumulate=False):
-    """dy: Act; dx: plain NHWC tensor [n,h,w,cin]"""
+class BnBwdStats(ctypes.Structure):
+    _fields_ = [("z", ctypes.c_void_p), ("z_cs", c_int), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
+                ("mean", ctypes.c_void_p), ("invstd", ctypes.c_void_p), ("sums", ctypes.c_void_p)]
+
+
+def conv_dgrad(dy, w, k, stride, dx, accumulate=False, bn_stats=None):
+    """dy: Act; dx: plain NHWC tensor [n,h,w,cin]. bn_stats = (z, scale, shift, mean, invstd, sums) of the layer that
+    consumes dx as its dy: pass 1 of its BN+ReLU backward is accumulated in the epilogue (3x3 stride 1)."""
     n, h, ww, cin = dx.shape
     cout = dy.shape[3]
     sh = _shape(n, h, ww, cin, cout, k, stride)
-    call("a2x_conv2d_dgrad", ctypes.byref(sh), _op(dy), ctypes.byref(w.dgrad), _ptr(dx), c_int(_cs(dx)),
-         c_int(int(accumulate)), stream_ptr())
+    st = None
+    if bn_stats is not None:
+        z, scale, shift, mean, invstd, sums = bn_stats
+        st = ctypes.byref(BnBwdStats(z.data_ptr(), _cs(z), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                     invstd.data_ptr(), sums.data_ptr()))
+    call("a2x_conv2d_dgrad_ex", ctypes.byref(sh), _op(dy), ctypes.byref(w.dgrad), _ptr(dx), c_int(_cs(dx)),
+         c_int(int(accumulate)), st, stream_ptr())
     return dx
 
 
@@ -381,11 +392,12 @@ def affine_act(x, scale, shift, relu, out, mask=None):
     return out
 
 
-def bn_relu_bwd(dy, z, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, accumulate=False):
-    """dy, z: NHWC tensors; dz: Act; sums: zeroed [2C] double"""
+def bn_relu_bwd(dy, z, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, accumulate=False, sums_ready=False):
+    """dy, z: NHWC tensors; dz: Act; sums: zeroed [2C] double (already filled by a fused dgrad epilogue if sums_ready)"""
     npix, C = _npix(dy), dy.shape[3]
-    call("a2x_bn_relu_bwd_reduce", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift), _ptr(mean),
-         _ptr(invstd), c_ll(npix), c_int(C), _ptr(sums), stream_ptr())
+    if not sums_ready:
+        call("a2x_bn_relu_bwd_reduce", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift),
+             _ptr(mean), _ptr(invstd), c_ll(npix), c_int(C), _ptr(sums), stream_ptr())
     call("a2x_bn_relu_bwd_apply", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift), _ptr(mean),
          _ptr(invstd), _ptr(sums), c_d(float(npix)), _op(dz), c_ll(npix), c_int(C),
          _ptr(dgamma), _ptr(dbeta), c_int(int(accumulate)), stream_ptr())

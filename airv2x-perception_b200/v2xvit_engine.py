@@ -37,6 +37,7 @@ class V2XViTEngine(CoBEVTEngine):
         assert sh["use"] and list(sh["kernal_size"]) == [1] and list(sh["stride"]) == [1] and list(sh["padding"]) == [0], \
             "only the airv2x shrink header (1x1 s1 + 3x3) is implemented"
         assert not mf.get("compression", 0), "NaiveCompressor (compression > 0) is not implemented"
+        self.compression = 0
         self.c_cat = sum(self.up_filters)
         self.c_shrink = sh["dim"][0]
         self.A = args["anchor_number"]

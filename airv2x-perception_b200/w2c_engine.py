@@ -60,6 +60,9 @@ class W2CEngine:
         self._arena_off = 0
         self.side = None  # second stream: weight gradients run beside the data-gradient chain (fills idle SMs)
         self.use_side_stream = True
+        # BN backward pass 1 inside the producing data-gradient epilogue: correct (tests) but measured SLOWER on B200
+        # (8.79 vs 8.24 ms per step: the dgrad epilogue is on the critical path, the separate pass overlaps) -> off
+        self.fuse_bn_bwd_reduce = False
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name, shape, dtype=torch.float32):
@@ -656,20 +659,31 @@ class W2CEngine:
         def block_bwd(tag, i, dy, dx_first, accumulate_first, mask=None):
             """dy: gradient w.r.t. the block output; returns nothing, writes the input gradient into dx_first."""
             nl = self.layer_nums[i]
+            sums_ready = False
             for k in range(nl, -1, -1):
                 r = by_tag["%s.b%d.%d" % (tag, i, k)]
                 dz = self._act("bwd.dz." + r["tag"], r["z"].shape)
-                sums = self._zeroed(r["tag"] + ".bsums", 2 * r["z"].shape[3], torch.float64)
+                if not sums_ready:
+                    sums = self._zeroed(r["tag"] + ".bsums", 2 * r["z"].shape[3], torch.float64)
                 ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
-                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
+                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"], sums_ready=sums_ready)
                 cout, cin = r["z"].shape[3], r["x"].shape[3]
                 dwp = self._zeroed(r["conv"] + ".dwp." + tag, 9 * cout * cin, torch.float32).view(9, cout, cin)
                 with self._on_side():
                     ops.conv_wgrad(r["x"], dz, 3, r["stride"], dwp)
                     unpack.append(ops.conv_unpack_job(dwp, grads[r["conv"]]))
+                sums_ready = False
                 if k > 0:
                     dprev = self._buf("bwd.dprev.%s.b%d.%d" % (tag, i, k), r["x"].shape)
-                    ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], dprev)
+                    bn_stats = None
+                    if r["stride"] == 1 and self.fuse_bn_bwd_reduce:
+                        # the data gradient of this conv is the dy of layer k-1: accumulate that layer's BN+ReLU backward
+                        # reduction (sum g, sum g*zhat) in this GEMM's epilogue instead of a separate pass over dy and z
+                        rp = by_tag["%s.b%d.%d" % (tag, i, k - 1)]
+                        sums = self._zeroed(rp["tag"] + ".bsums", 2 * rp["z"].shape[3], torch.float64)
+                        bn_stats = (rp["z"], rp["scale"], rp["shift"], rp["mean"], rp["invstd"], sums)
+                        sums_ready = True
+                    ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], dprev, bn_stats=bn_stats)
                     dy = dprev
                 else:
                     ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], dx_first, accumulate=accumulate_first)

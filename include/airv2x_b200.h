@@ -118,6 +118,20 @@ int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_w
 /* dx (+)= conv_transpose(dy, w)   (dx: fp32 NHWC, pixel stride dx_cs) */
 int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
                      int accumulate, a2x_stream_t stream);
+/* Same, with pass 1 of the CONSUMER layer's BatchNorm(train)+ReLU backward fused into the epilogue (3x3 stride 1 only):
+ * dx is that layer's dy, so sums[c] += sum g and sums[C + c] += sum g*zhat with g = dx * [z*scale+shift > 0],
+ * zhat = (z - mean)*invstd are accumulated while dx is written (a2x_bn_relu_bwd_reduce becomes unnecessary). */
+typedef struct {
+    const float* z;      /* the consumer layer's pre-BN activation [n][h][w][cin], pixel stride z_cs == dx_cs */
+    int z_cs;
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* invstd;
+    double* sums;        /* [2*cin], zeroed by the caller */
+} a2x_bn_bwd_stats;
+int a2x_conv2d_dgrad_ex(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
+                        int accumulate, const a2x_bn_bwd_stats* bn_stats, a2x_stream_t stream);
 /* dw_packed[tap][cout][cin] += sum_pixels dy (x) x   (caller zeroes dw_packed) */
 int a2x_conv2d_wgrad(const a2x_conv_shape* s, const a2x_operand* x, const a2x_operand* dy, float* dw_packed,
                      a2x_stream_t stream);

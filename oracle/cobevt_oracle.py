@@ -109,6 +109,14 @@ def swap_fusion_encoder(sd, fa, x, mask, pre="fusion_net", keep=None):
     return x.permute(0, 3, 1, 2)
 
 
+def naive_compressor(sd, x, training, buffers, pre="naive_compressor"):
+    """common_modules/naive_compress.py:38-42: encoder (conv3x3+BN+ReLU) then decoder (2 x conv3x3+BN+ReLU)"""
+    for conv, bn in (("encoder.0", "encoder.1"), ("decoder.0", "decoder.1"), ("decoder.3", "decoder.4")):
+        x = F.conv2d(x, sd["%s.%s.weight" % (pre, conv)], sd["%s.%s.bias" % (pre, conv)], padding=1)
+        x = F.relu(O._bn(x, sd, "%s.%s" % (pre, bn), training, buffers))
+    return x
+
+
 def cobevt_forward(sd, args, data_dict, training=False, keep=None):
     """models/airv2x_cobevt.py:112-156 (task == det; dropout = identity, i.e. eval mode or drop_out 0)."""
     buffers = {}
@@ -116,7 +124,8 @@ def cobevt_forward(sd, args, data_dict, training=False, keep=None):
     feat = O.backbone_forward(sd, args["base_bev_backbone"], sf, training, buffers)
     if args["shrink_header"]["use"]:
         feat = O.shrink_conv(sd, args["shrink_header"], feat)
-    assert not args.get("compression", 0)
+    if args.get("compression", 0):
+        feat = naive_compressor(sd, feat, training, buffers)
     L = sum(args["max_cav"].values())
     x, mask = regroup(feat, record_len.tolist(), L)
     if keep is not None:

@@ -52,6 +52,28 @@ def main():
         out["eval_" + k] = ref_out[k].numpy()
     for k in ("regroup", "block0", "block1", "block2", "fused_feature"):
         out["eval_keep_" + k] = MG.sample(keep[k])
+    # NaiveCompressor (a10): same scene with `compression: 2`, the compressor's parameters seeded separately
+    import copy
+    hy2 = copy.deepcopy(hypes)
+    hy2["model"]["args"]["compression"] = 2
+    model2 = ref_import.create_model(hy2)
+    sh2 = {k: tuple(v.shape) for k, v in model2.state_dict().items() if k.startswith("naive_compressor")}
+    sd2 = dict(sd)
+    sd2.update(O.det_init_state_dict(sh2, seed=97))
+    full2 = model2.state_dict()
+    full2.update(sd2)
+    model2.load_state_dict(full2)
+    sd2 = {k: v.clone() for k, v in model2.state_dict().items()}
+    model2.eval()
+    with torch.no_grad():
+        r2 = model2(dd)
+        o2, _ = CO.cobevt_forward(sd2, hy2["model"]["args"], dd, training=False)
+    for k in ("psm", "rm", "obj"):
+        err = float((r2[k] - o2[k]).abs().max())
+        print("compression=2 eval %s: ref-vs-oracle max abs err %.3e" % (k, err))
+        assert err < 1e-5, k
+        out["cmp2_eval_" + k] = r2[k].numpy()
+    out["cmp_param_seed"] = 97
     # the fusion network alone on a seeded random input with a ragged mask (2 scenes: 3 and 5 agents of L = 7)
     fa = dict(args["fax_fusion"])
     g = torch.Generator().manual_seed(3)

@@ -28,3 +28,15 @@ def golden_scene(cfg, gold):
     agents = [str(a) for a in gold["agents"]]
     return O.make_scene(cfg["preprocess"], agents, int(gold["n_points"]), int(gold["scene_seed"]),
                         cfg["preprocess"]["args"]["max_voxel_train"])
+
+
+def golden_state_dict_compressed(model, gold):
+    """parameters of the `compression: 2` golden run: the base model's seeded parameters + separately seeded compressor"""
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()
+              if "relative_position_index" not in k and not k.startswith("naive_compressor")}
+    sd = O.det_init_state_dict(shapes, seed=int(gold["param_seed"]))
+    sh2 = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("naive_compressor")}
+    sd.update(O.det_init_state_dict(sh2, seed=int(gold["cmp_param_seed"])))
+    full = {k: v.clone() for k, v in model.state_dict().items()}
+    full.update(sd)
+    return full

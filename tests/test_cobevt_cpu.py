@@ -40,6 +40,22 @@ def test_oracle_matches_reference_golden():
     assert np.abs(o.numpy() - gold["fusion_out"]).max() < 1e-5
 
 
+def test_oracle_naive_compressor_matches_reference_golden():
+    """a10: `compression: 2` inserts NaiveCompressor after the shrink header (airv2x_cobevt.py:121-123)"""
+    cfg, gold = CC.load_small()
+    args = json.loads(json.dumps(cfg["model_args"]))
+    args["compression"] = 2
+    model = _model(args)
+    assert model.state_dict()["naive_compressor.encoder.0.weight"].shape == (128, 256, 3, 3)
+    assert model.state_dict()["naive_compressor.decoder.3.weight"].shape == (256, 256, 3, 3)
+    sd = CC.golden_state_dict_compressed(model, gold)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        out, _ = CO.cobevt_forward(sd, args, CC.golden_scene(cfg, gold), training=False)
+    for k in ("psm", "rm", "obj"):
+        assert np.abs(out[k].numpy() - gold["cmp2_eval_" + k]).max() < 1e-5, k
+
+
 def test_registry_surface_full_config():
     """create_model's lookup rule (tools/train_utils.py:302-325) + the reference's parameter inventory"""
     cfg = json.load(open(os.path.join(ROOT, "configs", "airv2x_intermediate_cobevt.json")))

@@ -190,3 +190,23 @@ def test_eval_matches_reference_golden(small):
     with pytest.raises(NotImplementedError):
         model(C.to_device(dd, "cuda"))
     model.eval()
+
+
+def test_naive_compressor_eval_matches_reference_golden():
+    """a10: NaiveCompressor (3 x conv3x3 + BN + ReLU, bias folded into the BN shift) between shrink and fusion"""
+    import json
+
+    import a2x_import
+    import w2c_common as C
+
+    M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+    cfg, gold = CC.load_small()
+    args = json.loads(json.dumps(cfg["model_args"]))
+    args["compression"] = 2
+    model = M.Airv2xCoBEVT(args)
+    model.load_state_dict(CC.golden_state_dict_compressed(model, gold))
+    model.cuda().eval()
+    with torch.no_grad():
+        out = model(C.to_device(CC.golden_scene(cfg, gold), "cuda"))
+    for k in ("psm", "rm", "obj"):
+        assert np.abs(out[k].cpu().numpy() - gold["cmp2_eval_" + k]).max() < TOL, k

@@ -327,3 +327,25 @@ def test_mask_compact_decompact_roundtrip(ops):
     want = x * mask[..., None]
     want[0] = x[0]
     assert torch.equal(dst, want)
+
+
+def test_dgrad_fused_bn_bwd_reduction(ops):
+    """the BN+ReLU backward reduction accumulated in the data-gradient epilogue == the separate reduce pass over (dx, z)"""
+    g = _g(12)
+    n, h, w, cin, cout = 2, 19, 37, 128, 256
+    dy = rnd(g, n, cout, h, w)
+    wt = rnd(g, cout, cin, 3, 3) * 0.1
+    z = rnd(g, n, h, w, cin)
+    scale, shift = torch.rand(cin, generator=g).cuda() + 0.5, torch.randn(cin, generator=g).cuda() * 0.3
+    mean, invstd = torch.randn(cin, generator=g).cuda() * 0.2, torch.rand(cin, generator=g).cuda() + 0.5
+    pw = ops.pack_conv_weight(wt)
+    dys = ops.split(nhwc(dy))
+    dx_ref, dx = torch.empty(n, h, w, cin, device="cuda"), torch.empty(n, h, w, cin, device="cuda")
+    ops.conv_dgrad(dys, pw, 3, 1, dx_ref)
+    sums = torch.zeros(2 * cin, dtype=torch.float64, device="cuda")
+    ops.conv_dgrad(dys, pw, 3, 1, dx, bn_stats=(z, scale, shift, mean, invstd, sums))
+    assert torch.equal(dx, dx_ref)
+    gate = (z * scale + shift > 0).double()
+    gg = dx_ref.double() * gate
+    want = torch.cat([gg.sum((0, 1, 2)), (gg * ((z - mean) * invstd).double()).sum((0, 1, 2))])
+    assert float((sums - want).abs().max() / want.abs().max()) < 1e-5
