@@ -155,6 +155,28 @@ __global__ void mask_rate_ego_kernel(float* __restrict__ mask, int HW, const int
     if ((threadIdx.x & 31) == 0 && cnt != 0.f) atomicAdd(&ones[b], cnt);
 }
 
+// ---------------------------------------------------------------------------------------------- mask resize
+// F.interpolate(mask, size, mode="bilinear", align_corners=False) of the communication mask when the level-0 features
+// are finer than the confidence map (legacy stride-2 shrink header, where2comm_fuse.py:230-236)
+__global__ void resize_bilinear_kernel(const float* __restrict__ src, int h, int w, float* __restrict__ dst, int H, int W,
+                                       long long total) {
+    const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % W);
+        const int Y = (int)((i / W) % H);
+        const long long n = i / ((long long)W * H);
+        float fy = sh * (Y + 0.5f) - 0.5f, fx = sw * (X + 0.5f) - 0.5f;
+        fy = fy < 0.f ? 0.f : fy;
+        fx = fx < 0.f ? 0.f : fx;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+        const float* s = src + n * h * w;
+        dst[i] = hy * (hx * s[y0 * w + x0] + lx * s[y0 * w + x1]) + ly * (hx * s[y1 * w + x0] + lx * s[y1 * w + x1]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- sparse feature select
 // Where2comm transmits only the BEV cells its communication mask selected (where2comm_fuse.py:83-149, :237). Sender:
 // warp-ballot compaction of the selected cells of one agent's level-0 map into (count, cell index, feature row)
@@ -389,6 +411,17 @@ int a2x_comm_smooth_mask(const float* conf, const float* gauss_w, const float* g
 int a2x_comm_topk_mask(const float* smooth, int n, int hw, const int* k_per_agent, float* mask, a2x_stream_t stream) {
     A2X_REQUIRE(smooth && k_per_agent && mask && n > 0 && hw > 0, "comm_topk_mask: bad args");
     topk_mask_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(smooth, hw, k_per_agent, mask);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_resize_bilinear(const float* src, int n, int h, int w, float* dst, int H, int W, a2x_stream_t stream) {
+    A2X_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && H > 0 && W > 0, "resize_bilinear: bad args");
+    const long long total = (long long)n * H * W;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    resize_bilinear_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, h, w, dst, H, W, total);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -1,0 +1,101 @@
+"""`opencood.models.point_pillar_where2comm.PointPillarWhere2comm` on the B200 kernels (BASELINE config 1).
+
+Same registry name / class name / constructor, same `hypes_yaml` keys (`pillar_vfe`, `point_pillar_scatter`,
+`base_bev_backbone`, `shrink_header`, `where2comm_fusion`, `head_dim`, `anchor_number`, `compression`), same
+`state_dict` keys and shapes (8 057 386 parameters for V2XR_where2comm.yaml), same
+`forward(data_dict) -> {"psm","rm","com","mask","each_mask","comm_rate"}` as opencood/models/point_pillar_where2comm.py
+of the reference (input: `data_dict["processed_lidar"]`, `record_len`, `pairwise_t_matrix`). Parameter containers only;
+eval-mode forward in this round; no CPU fallback.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ...ppw2c_engine import LegacyW2CEngine
+from .airv2x_where2com import _backbone_params, _comm_params, _PillarVFEParams
+
+
+def _legacy_shrink_params(cfg):
+    m = nn.Module()
+    m.layers = nn.ModuleList()
+    cin = cfg["input_dim"]
+    for k, d, s, p in zip(cfg["kernal_size"], cfg["dim"], cfg["stride"], cfg["padding"]):
+        dc = nn.Module()
+        dc.double_conv = nn.Sequential(nn.Conv2d(cin, d, k, stride=s, padding=p), nn.ReLU(inplace=True),
+                                       nn.Conv2d(d, d, 3, padding=1), nn.ReLU(inplace=True))
+        m.layers.append(dc)
+        cin = d
+    return m
+
+
+class PointPillarWhere2comm(nn.Module):
+    def __init__(self, args, precision="split3"):
+        super().__init__()
+        self.args = args
+        self.modality = args.get("use_modality", "processed_lidar")
+        self.max_cav = args["max_cav"]
+        self.pillar_vfe = _PillarVFEParams(args["pillar_vfe"])
+        self.backbone = _backbone_params(args["base_bev_backbone"], 64)
+        self.shrink_flag = "shrink_header" in args
+        if not self.shrink_flag:
+            raise NotImplementedError("point_pillar_where2comm without a shrink header is not implemented")
+        self.shrink_conv = _legacy_shrink_params(args["shrink_header"])
+        if args["compression"]:
+            raise NotImplementedError("NaiveCompressor (compression > 0) is not implemented for this model")
+        self.compression = False
+        self.fusion_net = _comm_params(args["where2comm_fusion"])
+        self.multi_scale = args["where2comm_fusion"]["multi_scale"]
+        self.cls_head = nn.Conv2d(args["head_dim"], args["anchor_number"], kernel_size=1)
+        self.reg_head = nn.Conv2d(args["head_dim"], 7 * args["anchor_number"], kernel_size=1)
+        self.precision = precision
+        self._engine = None
+        if args.get("backbone_fix", False):
+            for n, p in self.named_parameters():
+                if not n.startswith("fusion_net"):
+                    p.requires_grad = False
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("PointPillarWhere2comm (B200) needs its parameters on a CUDA device; there is no CPU path")
+            self._engine = LegacyW2CEngine(self.args, dev, self.precision)
+        return self._engine
+
+    def _param_dict(self):
+        d = {n: p.data for n, p in self.named_parameters()}
+        d.update({n: b for n, b in self.named_buffers()})
+        return d
+
+    def forward(self, data_dict):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PointPillarWhere2comm (B200) needs its parameters on a CUDA device; there is no CPU path")
+        lid = data_dict[self.modality]
+        r = data_dict["record_len"]
+        record_len = [int(v) for v in (r.tolist() if torch.is_tensor(r) else r)]
+        key = tuple(record_len)
+        cache = self.__dict__.setdefault("_layout_cache", {})
+        if key not in cache:
+            nx, ny, _ = [int(v) for v in self.args["point_pillar_scatter"]["grid_size"]]
+            n = sum(record_len)
+            start = np.concatenate([[0], np.cumsum(record_len)[:-1]]).astype(np.int32)
+            cache[key] = dict(n_total=n, nx=nx, ny=ny, record_len=record_len,
+                              identity_map=torch.arange(n, dtype=torch.int32, device=dev),
+                              scene_start=torch.tensor(start, dtype=torch.int32, device=dev),
+                              scene_len=torch.tensor(record_len, dtype=torch.int32, device=dev))
+        layout = cache[key]
+        lidar = {"voxel_features": lid["voxel_features"].to(device=dev, dtype=torch.float32).contiguous(),
+                 "voxel_num_points": lid["voxel_num_points"].to(device=dev, dtype=torch.int32).contiguous(),
+                 "voxel_coords": lid["voxel_coords"].to(device=dev, dtype=torch.int32).contiguous()}
+        heads, aux = self.engine.forward(self._param_dict(), lidar, layout, self.training)
+        A = self.args["anchor_number"]
+        nchw = heads.permute(0, 3, 1, 2)
+        rl = torch.tensor(record_len, dtype=torch.float32, device=dev)
+        if self.engine.fully:
+            com = torch.tensor(1, device=dev)
+        else:
+            com = (aux["ones"] / (rl * aux["hw"])).sum() / len(record_len)
+        return {"psm": nchw[:, :A], "rm": nchw[:, A:8 * A], "com": com, "mask": 0, "each_mask": 0,
+                "comm_rate": int(aux["comm_rate"].item())}

@@ -492,6 +492,13 @@ def comm_rate_ego(mask, hw, n_scenes, scene_start, scene_len, ones):
          stream_ptr())
 
 
+def resize_bilinear(src, dst):
+    """src: [n, h, w] float; dst: [n, H, W] (F.interpolate bilinear, align_corners=False)"""
+    call("a2x_resize_bilinear", _ptr(src), c_int(src.shape[0]), c_int(src.shape[1]), c_int(src.shape[2]), _ptr(dst),
+         c_int(dst.shape[1]), c_int(dst.shape[2]), stream_ptr())
+    return dst
+
+
 def mask_compact(x, mask, force_all, hdr, idx, vals):
     """x: NHWC [1, h, w, C]; mask: [h, w] float; hdr: int32 [>=2]; idx: int32 [hw]; vals: float [hw, C]"""
     _, h, w, c = x.shape

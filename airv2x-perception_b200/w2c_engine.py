@@ -348,11 +348,15 @@ class W2CEngine:
         h2, w2 = x0.shape[1], x0.shape[2]
         catA = self._act("A.cat", (N, h2, w2, self.c_cat))
         xa = x0
+        # deblock i only feeds the concat buffer, so it runs on the side stream beside block i+1 (the deep blocks have
+        # fewer 128-pixel tiles than the GPU has SMs: the HBM-bound 1x1 deblock GEMMs fill the idle ones)
         for i in range(len(self.layer_nums)):
             if i > 0:
                 xa = self._block(P, W, i, xa, training, 2, "A", None)
             c0 = sum(self.up_filters[:i])
-            self._deblock(P, W, i, xa, catA.slice_c(c0, c0 + self.up_filters[i]), training, 2, "A", None)
+            with self._on_side():
+                self._deblock(P, W, i, xa, catA.slice_c(c0, c0 + self.up_filters[i]), training, 2, "A", None)
+        self._join_side()
         _, _, headsA = self._shrink_heads(P, W, catA, "A")
 
         # ---- communication mask (where2comm_fuse.py:83-149)
@@ -405,7 +409,9 @@ class W2CEngine:
                 pos += n
             levels.append(dict(x=xb, xfull=xfull, fused=fused))
             c0 = sum(self.up_filters[:i])
-            self._deblock(P, W, i, fused, catB.slice_c(c0, c0 + self.up_filters[i]), training, 1, "B", rec)
+            with self._on_side():
+                self._deblock(P, W, i, fused, catB.slice_c(c0, c0 + self.up_filters[i]), training, 1, "B", rec)
+        self._join_side()
         y1, y2, heads = self._shrink_heads(P, W, catB, "B")
         if training:
             self.saved = dict(rec=rec, W=W, levels=levels, mask=mask, x0=x0, x0m=x0m, catB=catB, y1=y1, y2=y2,
@@ -565,6 +571,10 @@ class W2CEngine:
 
     def _on_side(self):
         return W2CEngine._Side(self)
+
+    def _join_side(self):
+        if self.use_side_stream and self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
 
     def backward(self, P, dheads, grads):
         """dheads: [B,h,w,32] gradient w.r.t. the head logits. grads: dict name -> fp32 tensor (written)."""

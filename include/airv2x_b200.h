@@ -327,6 +327,9 @@ int a2x_comm_smooth_mask(const float* conf, const float* gauss_w, const float* g
                          float threshold, int write_mask, float* smooth, float* mask, a2x_stream_t stream);
 /* train mode: mask[a] = 1 on the k_per_agent[a] largest smooth values of agent a (device array) */
 int a2x_comm_topk_mask(const float* smooth, int n, int hw, const int* k_per_agent, float* mask, a2x_stream_t stream);
+/* dst [n][H][W] = F.interpolate(src [n][h][w], bilinear, align_corners=False): the mask resize of
+ * where2comm_fuse.py:230-236 (legacy stride-2 shrink header) */
+int a2x_resize_bilinear(const float* src, int n, int h, int w, float* dst, int H, int W, a2x_stream_t stream);
 /* Sparse feature select (the payload an agent transmits, where2comm_fuse.py:237): warp-ballot compaction of the cells
  * of one agent's level-0 map [hw][C] selected by its mask (all cells if force_all, the ego). hdr[0] = records written,
  * hdr[1] = cells the mask itself selected (communication-rate numerator); idx[r] = cell, vals[r][:] = feature row. */

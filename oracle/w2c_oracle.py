@@ -311,6 +311,50 @@ def point_pillar_loss_multiclass(output, target, num_class, cls_weight=1.0, reg_
     return reg_loss + conf_loss + obj_loss, reg_loss, conf_loss, obj_loss
 
 
+# --------------------------------------------------------------------------------------------------- legacy model
+def pp_where2comm_forward(sd, args, data_dict, training=False, keep=None):
+    """models/point_pillar_where2comm.py:99-151 (`point_pillar_where2comm`, BASELINE config 1; multi_scale branch):
+    one PillarVFE for all agents, the backbone evaluated once, a stride-2 shrink header (so the communication mask
+    lives at half the resolution of the level-0 features and is bilinearly resized, where2comm_fuse.py:230-236),
+    1-class heads without objectness."""
+    buffers = {}
+    lid = data_dict[args.get("use_modality", "processed_lidar")]
+    record_len = data_dict["record_len"]
+    pf, _ = pillar_vfe(sd, "pillar_vfe", lid["voxel_features"], lid["voxel_num_points"], lid["voxel_coords"],
+                       args["voxel_size"], args["lidar_range"], training, buffers)
+    nx, ny, _ = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
+    sf = scatter(pf, lid["voxel_coords"], nx, ny, int(record_len.sum()))
+    comm_rates = int(sf.count_nonzero().item())
+    feat2d = backbone_forward(sd, args["base_bev_backbone"], sf, training, buffers)
+    if "shrink_header" in args:
+        feat2d = shrink_conv(sd, args["shrink_header"], feat2d)
+    psm_single = F.conv2d(feat2d, sd["cls_head.weight"], sd["cls_head.bias"])
+    assert not args["compression"] and args["where2comm_fusion"]["multi_scale"]
+    pseudo = {"where2com_fusion": args["where2comm_fusion"], "modality_fusion": {"base_bev_backbone": args["base_bev_backbone"]}}
+    fused, rate = where2comm_fusion(sd, pseudo, sf, psm_single, record_len, training, buffers, keep)
+    if "shrink_header" in args:
+        fused = shrink_conv(sd, args["shrink_header"], fused)
+    out = {"psm": F.conv2d(fused, sd["cls_head.weight"], sd["cls_head.bias"]),
+           "rm": F.conv2d(fused, sd["reg_head.weight"], sd["reg_head.bias"])}
+    out.update({"com": rate, "mask": 0, "each_mask": 0, "comm_rate": comm_rates})
+    return out, buffers
+
+
+def make_scene_legacy(preprocess, n_agents, n_points, seed, max_voxels, sigma_xy=(8.0, 8.0)):
+    """`processed_lidar` dict of the legacy datasets: all agents of the scene collated into one voxel batch"""
+    rng = preprocess["cav_lidar_range"]
+    per = []
+    for k in range(n_agents):
+        pts = synth_points(seed * 100 + k, n_points, rng, sigma_xy=sigma_xy)
+        pts = _V.mask_points(pts, rng, ego_box=(k == 0))
+        per.append(_V.voxelize(pts, rng, preprocess["args"]["voxel_size"], preprocess["args"]["max_points_per_voxel"], max_voxels))
+    col = _V.collate(per)
+    L = 5
+    return {"processed_lidar": {k: torch.from_numpy(v) for k, v in col.items()},
+            "record_len": torch.tensor([n_agents], dtype=torch.int32),
+            "pairwise_t_matrix": torch.eye(4).view(1, 1, 1, 4, 4).repeat(1, L, L, 1, 1)}
+
+
 # --------------------------------------------------------------------------------------------------- synthetic data
 def synth_points(seed, n_points, lidar_range, sigma_xy=(35.0, 15.0)):
     """SURVEY §8d synthetic cloud: x~N(0,sx), y~N(0,sy) clipped to the range, z~U(zlo,zhi), intensity~U(0,1)."""
