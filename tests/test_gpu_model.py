@@ -199,3 +199,25 @@ def test_baseline_size_properties():
     for k in ("psm", "rm", "obj"):
         assert float((a[k] - c[k]).abs().max()) < 1e-4, k
     assert a["comm_rate"] == c["comm_rate"]
+
+
+def test_ragged_multi_scene_batch_matches_oracle(small):
+    """B = 3 ragged scenes (4, 2 and 3 agents; one scene without RSUs, one without drones): the reference's per-type
+    collate + scene-major regrouping (airv2x_base_model.py:179-248), per-scene masks / rates and per-scene fusion"""
+    cfg, gold, model, sd, _ = small
+    model.load_state_dict(sd)
+    model.eval()
+    scenes = [["vehicle", "vehicle", "rsu", "drone"], ["vehicle", "drone"], ["vehicle", "rsu", "rsu"]]
+    pre = dict(cfg["preprocess"])
+    pre["args"] = dict(pre["args"])
+    pre["args"]["max_voxel_test"] = pre["args"]["max_voxel_train"]
+    dd, raw = C.make_batch(pre, scenes, 4000, 31, pre["args"]["max_voxel_train"])
+    with torch.no_grad():
+        ora, _ = O.where2com_forward(sd, cfg["model_args"], dd, training=False)
+        out = model(C.to_device(dd, "cuda"))
+        out_raw = model(raw)
+    assert out["psm"].shape[0] == 3
+    for k in ("psm", "rm", "obj"):
+        assert float((out[k].cpu() - ora[k]).abs().max()) < TOL, k
+        assert torch.equal(out[k], out_raw[k]), k                      # raw-point boundary == voxel-dict boundary
+    assert abs(float(out["com"]) - float(ora["com"])) < 1e-6 and out["comm_rate"] == ora["comm_rate"]

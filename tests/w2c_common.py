@@ -99,3 +99,48 @@ def check_mask_ties(mask_gpu, keep, tol=1e-4, max_frac=5e-3):
         cut = float(sel.min())
         assert float((smooth[a][d[a]] - cut).abs().max()) < tol, "agent %d: mask differs away from the top-K cut" % a
     return n
+
+
+def make_batch(preprocess, scenes, n_points, seed, max_voxels, sigma_xy=(10.0, 5.0)):
+    """B ragged scenes in the reference's collate layout (intermediate_fusion_dataset.py:833-868): per agent type one
+    merged voxel batch over all scenes (agent index = position within the type, scene-major), `record_len` per scene,
+    `batch_idxs` = the scenes that contain the type. scenes: list of agent-type lists (vehicles, RSUs, drones order).
+    Also returns the raw clouds (scene-major agent order) for the raw-point boundary."""
+    from oracle import voxelize as V
+
+    rng = preprocess["cav_lidar_range"]
+    per_type = {t: [] for t in O.AGENT_TYPES}
+    rl = {t: [] for t in O.AGENT_TYPES}
+    clouds, k = [], 0
+    for b, agents in enumerate(scenes):
+        first = True
+        for t in O.AGENT_TYPES:
+            n_t = sum(1 for a in agents if a == t)
+            rl[t].append(n_t)
+            for _ in range(n_t):
+                pts = O.synth_points(seed * 100 + k, n_points, rng, sigma_xy=sigma_xy)
+                clouds.append(pts)
+                p = V.mask_points(pts, rng, ego_box=first)
+                first = False
+                per_type[t].append(V.voxelize(p, rng, preprocess["args"]["voxel_size"],
+                                              preprocess["args"]["max_points_per_voxel"], max_voxels))
+                k += 1
+    dd = {}
+    for t in O.AGENT_TYPES:
+        idxs = [b for b, n in enumerate(rl[t]) if n > 0]
+        if per_type[t]:
+            col = V.collate(per_type[t])
+            feats = {k2: torch.from_numpy(v) for k2, v in col.items()}
+        else:
+            feats = None
+        dd[t] = {"batch_merged_lidar_features_torch": feats, "record_len": torch.tensor(rl[t], dtype=torch.int32),
+                 "batch_idxs": idxs}
+    B = len(scenes)
+    dd["img_pairwise_t_matrix_collab"] = torch.eye(4).view(1, 1, 1, 4, 4).repeat(B, 15, 15, 1, 1)
+    dd["record_len"] = torch.tensor([len(a) for a in scenes], dtype=torch.int32)
+    offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    raw = {"raw_points": {"points": torch.from_numpy(np.concatenate(clouds, 0)), "offsets": torch.from_numpy(offs),
+                          "preprocess": preprocess, "filter": True}}
+    for t in O.AGENT_TYPES:
+        raw[t] = {"record_len": rl[t], "batch_idxs": dd[t]["batch_idxs"]}
+    return dd, raw
