@@ -325,10 +325,93 @@ class Airv2xWhere2com(nn.Module):
         eng = self.engine
         if not eng.fully:
             hw = st["hw"]
-            eng.set_k([int(hw * _random.uniform(0, 1)) for _ in layout["record_len"]], layout["record_len"])
+            k_host = eng.set_k([int(hw * _random.uniform(0, 1)) for _ in layout["record_len"]], layout["record_len"])
+            eng._buf("k_dev", (k_host.numel(),), torch.int32).copy_(k_host, non_blocking=True)
         st["graph"].replay()
         self._last_aux = st["aux"]
         return st["loss3"]
+
+    # ------------------------------------------------------------------ pipelined input staging (overlap H2D / D2H)
+    def stage_inputs(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0):
+        """Start the host->device copies of the NEXT step's inputs (pinned host tensors) on a copy stream, so they
+        overlap the step that is currently running. Follow with `train_step_staged()`. The top-K sizes of the
+        communication mask are drawn here from Python's `random`, in call order, exactly like the reference."""
+        import random as _random
+
+        assert self.training and data_dict.get("raw_points") is not None
+        dev = next(self.parameters()).device
+        raw = data_dict["raw_points"]
+        layout = self._layout(data_dict, dev)
+        P = int(raw["points"].shape[0])
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = (id(layout), float(cls_weight), float(reg_coe))
+        st = graphs.get(key)
+        if st is None or st["cap"] < P:
+            st = self._capture(data_dict, label_dict, cls_weight, reg_coe, layout, dev, max(P, int(P * 1.1)))
+            graphs[key] = st
+        if "stage" not in st:
+            n_agents = layout["n_total"]
+            st["stage"] = dict(points=torch.empty_like(st["points"]), offsets=torch.empty_like(st["offsets"]),
+                               labels={k: torch.empty_like(v) for k, v in st["labels"].items()},
+                               k=torch.zeros(n_agents, dtype=torch.int32, device=dev),
+                               k_host=[torch.zeros(n_agents, dtype=torch.int32).pin_memory() for _ in range(2)], flip=0,
+                               stream=torch.cuda.Stream(device=dev), ready=torch.cuda.Event(), consumed=torch.cuda.Event(),
+                               loss_host=[torch.zeros(3, dtype=torch.float64).pin_memory() for _ in range(2)],
+                               loss_evt=[torch.cuda.Event(), torch.cuda.Event()])
+            st["stage"]["consumed"].record()
+        sg = st["stage"]
+        eng = self.engine
+        if not eng.fully:
+            kh = sg["k_host"][sg["flip"]]
+            pos = 0
+            for b, n in enumerate(layout["record_len"]):
+                kh[pos:pos + n] = int(st["hw"] * _random.uniform(0, 1))
+                pos += n
+        with torch.cuda.stream(sg["stream"]):
+            sg["stream"].wait_event(sg["consumed"])      # the previous staged batch has been moved to the static buffers
+            sg["points"][:P].copy_(raw["points"], non_blocking=True)
+            sg["offsets"].copy_(raw["offsets"], non_blocking=True)
+            for k in ("targets", "pos_equal_one", "class_ids"):
+                sg["labels"][k].copy_(label_dict[k].reshape(sg["labels"][k].shape), non_blocking=True)
+            if not eng.fully:
+                sg["k"].copy_(sg["k_host"][sg["flip"]], non_blocking=True)
+            sg["ready"].record()
+        sg["P"] = P
+        self._staged = st
+        return st
+
+    def train_step_staged(self):
+        """Run the step whose inputs `stage_inputs()` copied: device-to-device hand-over into the graph's static buffers,
+        one graph replay, and an asynchronous device->host copy of the [reg, cls, obj] loss. Returns a handle whose
+        `.result()` waits for that copy only (by then usually complete: call it after launching the next step)."""
+        st = self._staged
+        sg = st["stage"]
+        eng = self.engine
+        cur = torch.cuda.current_stream()
+        cur.wait_event(sg["ready"])
+        st["points"][:sg["P"]].copy_(sg["points"][:sg["P"]], non_blocking=True)
+        st["offsets"].copy_(sg["offsets"], non_blocking=True)
+        for k in ("targets", "pos_equal_one", "class_ids"):
+            st["labels"][k].copy_(sg["labels"][k], non_blocking=True)
+        if not eng.fully:
+            eng._buf("k_dev", (sg["k"].numel(),), torch.int32).copy_(sg["k"], non_blocking=True)
+        sg["consumed"].record()
+        if not st.get("k_free_graph", False):
+            raise RuntimeError("stage_inputs() must capture the graph (call it before train_step_graphed on this layout)")
+        st["graph"].replay()
+        i = sg["flip"]
+        sg["flip"] ^= 1
+        sg["loss_host"][i].copy_(st["loss3"], non_blocking=True)
+        sg["loss_evt"][i].record()
+        self._last_aux = st["aux"]
+        host, evt = sg["loss_host"][i], sg["loss_evt"][i]
+
+        class _Handle:
+            def result(self_inner):
+                evt.synchronize()
+                return host.clone()
+
+        return _Handle()
 
     def _capture(self, data_dict, label_dict, cw, rc, layout, dev, cap):
         raw = data_dict["raw_points"]
@@ -350,12 +433,18 @@ class Airv2xWhere2com(nn.Module):
         lib = _lib.load()
         g = torch.cuda.CUDAGraph()
         l0 = lib.a2x_launch_count()
-        with torch.cuda.graph(g):
-            loss3 = self.train_step(dd, labels, cw, rc)
+        # the top-K sizes reach `k_dev` by an explicit copy issued before every replay (from the pinned `k_host`, or from
+        # the staged device copy in pipelined mode), not from inside the graph
+        self.engine.k_on_device = True
+        try:
+            with torch.cuda.graph(g):
+                loss3 = self.train_step(dd, labels, cw, rc)
+        finally:
+            self.engine.k_on_device = False
         self.launches_per_step = int(lib.a2x_launch_count() - l0)  # kernels of this library inside one replay
         random.setstate(rng_state)
         return dict(graph=g, points=pts, offsets=offs, labels=labels, loss3=loss3, aux=self._last_aux, cap=cap,
-                    hw=self._last_aux["hw"])
+                    hw=self._last_aux["hw"], k_free_graph=True)
 
     def _output_dict(self, heads, layout):
         A, K = self.args["anchor_number"], self.args["num_class"]

@@ -63,6 +63,7 @@ class W2CEngine:
         # BN backward pass 1 inside the producing data-gradient epilogue: correct (tests) but measured SLOWER on B200
         # (8.79 vs 8.24 ms per step: the dgrad epilogue is on the critical path, the separate pass overlaps) -> off
         self.fuse_bn_bwd_reduce = False
+        self.k_on_device = False
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name, shape, dtype=torch.float32):
@@ -382,7 +383,8 @@ class W2CEngine:
                     k_list = [int(hw * random.uniform(0, 1)) for _ in range(B)]
                 k_host = self.set_k(k_list, record_len)
                 k_dev = self._buf("k_dev", (N,), torch.int32)
-                k_dev.copy_(k_host, non_blocking=True)
+                if not self.k_on_device:  # pipelined mode stages K with the other inputs (no H2D inside the graph)
+                    k_dev.copy_(k_host, non_blocking=True)
                 ops.comm_smooth_mask(conf, gw, gb, ksz, N, h2, w2, thr, False, smooth, mask)
                 ops.comm_topk_mask(smooth, N, hw, k_dev, mask)
             elif thr:
@@ -517,8 +519,10 @@ class W2CEngine:
         return heads, aux
 
     def set_k(self, k_list, record_len):
-        """write the per-scene top-K sizes into the pinned staging buffer the (possibly graph-captured) H2D copy reads"""
-        k_host = self._pinned("k_host", (sum(record_len),), torch.int32)
+        """write the per-scene top-K sizes into a pinned staging buffer for the asynchronous H2D copy that follows. A ring
+        of 64 buffers: the host may run many steps ahead of the device without overwriting values not yet copied."""
+        self._k_ring = (getattr(self, "_k_ring", -1) + 1) % 64
+        k_host = self._pinned("k_host.%d" % self._k_ring, (sum(record_len),), torch.int32)
         pos = 0
         for b, n in enumerate(record_len):
             k_host[pos:pos + n] = int(k_list[b])

@@ -221,3 +221,53 @@ def test_ragged_multi_scene_batch_matches_oracle(small):
         assert float((out[k].cpu() - ora[k]).abs().max()) < TOL, k
         assert torch.equal(out[k], out_raw[k]), k                      # raw-point boundary == voxel-dict boundary
     assert abs(float(out["com"]) - float(ora["com"])) < 1e-6 and out["comm_rate"] == ora["comm_rate"]
+
+
+def test_staged_pipeline_matches_graphed_step(small):
+    """stage_inputs() + train_step_staged() (H2D overlapped with the previous step, loss read one step late) gives the
+    same losses and gradients as train_step_graphed() fed the same host batches and the same top-K random stream"""
+    import a2x_import
+
+    cfg, gold, _, sd, _ = small
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    rng = cfg["preprocess"]["cav_lidar_range"]
+    agents = [str(a) for a in gold["agents"]]
+    H, W = gold["train_psm"].shape[2:]
+
+    def batch(seed):
+        clouds = [O.synth_points(seed * 100 + k, 6000, rng, (10.0, 5.0)) for k in range(len(agents))]
+        offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+        raw = {"raw_points": {"points": torch.from_numpy(np.concatenate(clouds, 0)).pin_memory(),
+                              "offsets": torch.from_numpy(offs).pin_memory(), "preprocess": cfg["preprocess"], "filter": True}}
+        for t in O.AGENT_TYPES:
+            n = sum(1 for a in agents if a == t)
+            raw[t] = {"record_len": [n], "batch_idxs": [0] if n else []}
+        lab = O.make_labels(40 + seed, 1, H, W, cfg["model_args"]["anchor_number"])
+        return raw, {k: v.float().pin_memory() if v.is_floating_point() else v.int().pin_memory() for k, v in lab.items()}
+
+    batches = [batch(s) for s in (1, 2, 3)]
+    ref_m, pipe_m = [M.Airv2xWhere2com(cfg["model_args"]) for _ in range(2)]
+    for m in (ref_m, pipe_m):
+        m.load_state_dict(sd)
+        m.cuda().train()
+    random.seed(77)
+    want = []
+    for dd, lab in batches:
+        want.append(ref_m.train_step_graphed(dd, lab, 1.0, 2.0).clone().cpu())
+    g_ref = {n: p.grad.clone() for n, p in ref_m.named_parameters() if p.grad is not None}
+    random.seed(77)
+    pipe_m.stage_inputs(*batches[0], 1.0, 2.0)
+    got, prev = [], None
+    for i in range(len(batches)):
+        h = pipe_m.train_step_staged()
+        if i + 1 < len(batches):
+            pipe_m.stage_inputs(*batches[i + 1], 1.0, 2.0)
+        if prev is not None:
+            got.append(prev.result())
+        prev = h
+    got.append(prev.result())
+    for a, b in zip(got, want):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-9), (a, b)
+    for n, p in pipe_m.named_parameters():
+        if p.grad is not None:
+            assert torch.allclose(p.grad, g_ref[n], rtol=1e-4, atol=1e-6 * float(g_ref[n].abs().max()) + 1e-12), n
