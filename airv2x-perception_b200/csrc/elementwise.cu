@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const float* __rest
                                                              const float* __restrict__ shift,
                                                              const float* __restrict__ mean,
                                                              const float* __restrict__ invstd, long long npix, int C,
-                                                             double* __restrict__ sums) {
+                                                             double* __restrict__ sums, int replicas) {
     extern __shared__ float red[];  // [2][256][4]
     const int q = C >> 2;                  // float4 groups per pixel
     const int cq = threadIdx.x % q;        // my channel quad
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const float* __rest
         }
     }
     if (prow < ppb) {
-        constexpr int U = 4;  // pixels in flight per thread
+        constexpr int U = MODE == 1 ? 4 : 8;  // pixels in flight per thread (MODE 1 loads two tensors)
         const long long pstride = (long long)gridDim.x * ppb;
         for (long long p0 = (long long)blockIdx.x * ppb + prow; p0 < npix; p0 += pstride * U) {
             float4 xv[U], zv[U];
@@ -104,10 +104,32 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const float* __rest
                 d1[e] += r1[(r * q + threadIdx.x) * 4 + e];
             }
         }
+        // `replicas` copies of the accumulators ([replica][2C]) spread the same-address atomics of the many blocks; the
+        // consumer adds the copies up
+        double* dst = sums + (long long)(blockIdx.x % replicas) * 2 * C;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            atomicAdd(&sums[threadIdx.x * 4 + e], d0[e]);
-            atomicAdd(&sums[C + threadIdx.x * 4 + e], d1[e]);
+            atomicAdd(&dst[threadIdx.x * 4 + e], d0[e]);
+            atomicAdd(&dst[C + threadIdx.x * 4 + e], d1[e]);
+        }
+    }
+    if (replicas > 1) {
+        // the last block to finish folds the copies into copy 0 (ticket counter behind the copies, zeroed with them)
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + (long long)replicas * 2 * C);
+            last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+                double t = 0.0;
+                for (int r = 0; r < replicas; ++r) t += __ldcg(&sums[(long long)r * 2 * C + i]);
+                sums[i] = t;
+            }
         }
     }
 }
@@ -223,19 +245,25 @@ __global__ void __launch_bounds__(256) bn_train_act_kernel(const float* __restri
                                                            float* __restrict__ shift_out, float* __restrict__ mean_out,
                                                            float* __restrict__ invstd_out, int relu, SplitOut y, int y_cs,
                                                            long long npix, int C) {
-    extern __shared__ float tab[];  // [C] scale, [C] shift
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // every thread owns one channel quad (cq) and walks pixels with a constant stride: no index division in the loop,
+    // the four (scale, shift) pairs live in registers
+    const int q = C >> 2;
+    const int cq = threadIdx.x % q, prow = threadIdx.x / q, ppb = blockDim.x / q;
+    if (prow >= ppb) return;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = cq * 4 + e;
         const double m = sums[c] / count;
         double var = sums[C + c] / count - m * m;
         if (var < 0) var = 0;
         const float invstd = (float)(1.0 / sqrt(var + (double)eps));
         const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-        const float sc = g * invstd, sh = b - (float)m * g * invstd;
-        tab[c] = sc;
-        tab[C + c] = sh;
-        if (blockIdx.x == 0) {
-            scale_out[c] = sc;
-            shift_out[c] = sh;
+        sc[e] = g * invstd;
+        sh[e] = b - (float)m * g * invstd;
+        if (blockIdx.x == 0 && prow == 0) {
+            scale_out[c] = sc[e];
+            shift_out[c] = sh[e];
             if (mean_out) mean_out[c] = (float)m;
             if (invstd_out) invstd_out[c] = invstd;
             if (running_mean != nullptr && n_updates > 0) {
@@ -250,33 +278,25 @@ __global__ void __launch_bounds__(256) bn_train_act_kernel(const float* __restri
             }
         }
     }
-    __syncthreads();
-    const int q = C >> 2;
-    const long long total = npix * q;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    constexpr int U = 4;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    constexpr int U = 8;
+    const long long pstride = (long long)gridDim.x * ppb;
+    for (long long p0 = (long long)blockIdx.x * ppb + prow; p0 < npix; p0 += pstride * U) {
         float4 v[U];
-        long long p[U];
-        int c[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            p[u] = i / q;
-            c[u] = (int)(i - p[u] * q) * 4;
-            if (i < total) v[u] = *reinterpret_cast<const float4*>(z + p[u] * z_cs + c[u]);
+            const long long p = p0 + u * pstride;
+            if (p < npix) v[u] = *reinterpret_cast<const float4*>(z + p * z_cs + cq * 4);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (i0 + u * stride >= total) break;
+            const long long p = p0 + u * pstride;
+            if (p >= npix) break;
             float4 t = v[u];
-            const float4 s = *reinterpret_cast<const float4*>(tab + c[u]);
-            const float4 b = *reinterpret_cast<const float4*>(tab + C + c[u]);
-            t.x = t.x * s.x + b.x; t.y = t.y * s.y + b.y; t.z = t.z * s.z + b.z; t.w = t.w * s.w + b.w;
+            t.x = t.x * sc[0] + sh[0]; t.y = t.y * sc[1] + sh[1]; t.z = t.z * sc[2] + sh[2]; t.w = t.w * sc[3] + sh[3];
             if (relu) {
                 t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
             }
-            store_split4(y, p[u] * y_cs + c[u], t);
+            store_split4(y, p * y_cs + cq * 4, t);
         }
     }
 }
@@ -293,54 +313,49 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __r
                                                                 SplitOut dz, int dz_cs, long long npix, int C,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                 int accumulate) {
-    extern __shared__ float tab[];  // per channel: scale, shift, mean, invstd, mean(g), mean(g*zhat)
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        tab[c] = scale[c];
-        tab[C + c] = shift[c];
-        tab[2 * C + c] = mean[c];
-        tab[3 * C + c] = invstd[c];
-        tab[4 * C + c] = (float)(sums[c] / count);
-        tab[5 * C + c] = (float)(sums[C + c] / count);
-        if (blockIdx.x == 0) {  // dgamma = sum g*zhat, dbeta = sum g  (bn_bwd_finalize fused)
-            const float dg = (float)sums[C + c], db = (float)sums[c];
+    const int q = C >> 2;
+    const int cq = threadIdx.x % q, prow = threadIdx.x / q, ppb = blockDim.x / q;
+    if (prow >= ppb) return;
+    float sc[4], sh[4], mu[4], is[4], mg[4], mgz[4];  // per-channel coefficients of my quad, in registers
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = cq * 4 + e;
+        sc[e] = scale[c]; sh[e] = shift[c]; mu[e] = mean[c]; is[e] = invstd[c];
+        const double sg = sums[c], sgz = sums[C + c];  // copy 0 holds the folded totals
+        mg[e] = (float)(sg / count);
+        mgz[e] = (float)(sgz / count);
+        if (blockIdx.x == 0 && prow == 0) {  // dgamma = sum g*zhat, dbeta = sum g  (bn_bwd_finalize fused)
+            const float dg = (float)sgz, db = (float)sg;
             if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
             if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
         }
     }
-    __syncthreads();
-    const int q = C >> 2;
-    const long long total = npix * q;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    constexpr int U = 2;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    constexpr int U = 4;
+    const long long pstride = (long long)gridDim.x * ppb;
+    for (long long p0 = (long long)blockIdx.x * ppb + prow; p0 < npix; p0 += pstride * U) {
         float4 d4[U], z4[U];
-        long long p[U];
-        int c[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            p[u] = i / q;
-            c[u] = (int)(i - p[u] * q) * 4;
-            if (i < total) {
-                d4[u] = *reinterpret_cast<const float4*>(dy + p[u] * dy_cs + c[u]);
-                z4[u] = *reinterpret_cast<const float4*>(z + p[u] * z_cs + c[u]);
+            const long long p = p0 + u * pstride;
+            if (p < npix) {
+                d4[u] = *reinterpret_cast<const float4*>(dy + p * dy_cs + cq * 4);
+                z4[u] = *reinterpret_cast<const float4*>(z + p * z_cs + cq * 4);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (i0 + u * stride >= total) break;
+            const long long p = p0 + u * pstride;
+            if (p >= npix) break;
             const float d[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
             const float zz[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w};
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int ch = c[u] + e;
-                const float sc = tab[ch], sh = tab[C + ch];
-                const float g = (zz[e] * sc + sh > 0.f) ? d[e] : 0.f;
-                const float zh = (zz[e] - tab[2 * C + ch]) * tab[3 * C + ch];
-                o[e] = sc * (g - tab[4 * C + ch] - zh * tab[5 * C + ch]);  // scale = gamma * invstd
+                const float g = (zz[e] * sc[e] + sh[e] > 0.f) ? d[e] : 0.f;
+                const float zh = (zz[e] - mu[e]) * is[e];
+                o[e] = sc[e] * (g - mg[e] - zh * mgz[e]);  // scale = gamma * invstd
             }
-            store_split4(dz, p[u] * dz_cs + c[u], make_float4(o[0], o[1], o[2], o[3]));
+            store_split4(dz, p * dz_cs + cq * 4, make_float4(o[0], o[1], o[2], o[3]));
         }
     }
 }
@@ -390,12 +405,16 @@ static int ew_grid(long long total) {
     return (int)b;
 }
 
-// kernels that build a per-channel table in their prologue: fewer, fatter blocks
-static int ew_grid_tab(long long total) {
-    long long b = (total + 256 * 8 - 1) / (256 * 8);
-    if (b > 148 * 6) b = 148 * 6;
+// column-owner kernels: blockDim = q * (256 / q) threads (q = C/4 channel quads), each block iteration covers
+// 256 / q pixels; grid sized so that every thread sees ~16 pixels, capped at 8 blocks per SM
+static void col_launch_dims(long long npix, int C, int* threads, int* blocks) {
+    const int q = C / 4;
+    const int ppb = 256 / q > 0 ? 256 / q : 1;
+    *threads = q * ppb;
+    long long b = (npix + (long long)ppb * 16 - 1) / ((long long)ppb * 16);
+    if (b > 148 * 8) b = 148 * 8;
     if (b < 1) b = 1;
-    return (int)b;
+    *blocks = (int)b;
 }
 
 }  // namespace a2x
@@ -427,7 +446,7 @@ int a2x_channel_stats(const float* x, int x_cs, long long npix, int C, double* s
     long long blocks = (npix + ppb - 1) / ppb;
     if (blocks > 148 * 2) blocks = 148 * 2;  // few blocks: the tail is 2C same-address double atomics per block
     channel_reduce_kernel<0><<<(int)blocks, 256, 2 * 256 * 4 * sizeof(float), (cudaStream_t)stream>>>(
-        x, x_cs, nullptr, 0, nullptr, nullptr, nullptr, nullptr, npix, C, sums);
+        x, x_cs, nullptr, 0, nullptr, nullptr, nullptr, nullptr, npix, C, sums, 1);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -472,10 +491,11 @@ int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs,
     if (int r = check_c(C)) return r;
     A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && npix > 0, "bn_relu_bwd_reduce: bad args");
     const int ppb = 256 / (C / 4);
-    long long blocks = (npix + ppb - 1) / ppb;
-    if (blocks > 148 * 2) blocks = 148 * 2;  // few blocks: the tail is 2C same-address double atomics per block
+    long long blocks = (npix + (long long)ppb * 8 - 1) / ((long long)ppb * 8);
+    if (blocks > 148 * 6) blocks = 148 * 6;  // the 2C double atomics per block land on A2X_BN_BWD_REPLICAS copies of `sums`
+    if (blocks < 1) blocks = 1;
     channel_reduce_kernel<1><<<(int)blocks, 256, 2 * 256 * 4 * sizeof(float), (cudaStream_t)stream>>>(
-        dy, dy_cs, z, z_cs, scale, shift, mean, invstd, npix, C, sums);
+        dy, dy_cs, z, z_cs, scale, shift, mean, invstd, npix, C, sums, A2X_BN_BWD_REPLICAS);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -488,7 +508,9 @@ int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, 
     if (int r = check_c(C)) return r;
     A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && dz && dz->hi && npix > 0,
                 "bn_relu_bwd_apply: bad args");
-    bn_relu_bwd_apply_kernel<<<ew_grid_tab(npix * (C / 4)), 256, 6 * C * sizeof(float), (cudaStream_t)stream>>>(
+    int threads, blocks;
+    col_launch_dims(npix, C, &threads, &blocks);
+    bn_relu_bwd_apply_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
         dy, dy_cs, z, z_cs, scale, shift, mean, invstd, sums, count, to_split(dz), dz->cs, npix, C, dgamma, dbeta,
         accumulate_param_grads);
     A2X_LAUNCHED();
@@ -502,7 +524,9 @@ int a2x_bn_train_act(const float* z, int z_cs, const double* sums, double count,
                      int C, a2x_stream_t stream) {
     if (int r = check_c(C)) return r;
     A2X_REQUIRE(z && sums && scale && shift && y && y->hi && npix > 0 && count > 0, "bn_train_act: bad args");
-    bn_train_act_kernel<<<ew_grid_tab(npix * (C / 4)), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+    int threads, blocks;
+    col_launch_dims(npix, C, &threads, &blocks);
+    bn_train_act_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
         z, z_cs, sums, count, gamma, beta, eps, momentum, n_updates, running_mean, running_var, scale, shift, mean_out,
         invstd_out, relu, to_split(y), y->cs, npix, C);
     A2X_LAUNCHED();

@@ -387,7 +387,7 @@ int a2x_pfn_moments(const float* voxels, const int* num_points, const int* coord
     const PfnSeg sg = make_seg(seg, &m);
     A2X_REQUIRE(voxels && num_points && coords && geom && moments65 && m > 0, "pfn_moments: bad args");
     A2X_CHECK_CUDA(cudaMemsetAsync(moments65, 0, sizeof(double) * (NF + NS2), (cudaStream_t)stream));
-    pfn_moments_kernel<<<warp_grid(m), 256, 0, (cudaStream_t)stream>>>(voxels, num_points, coords, make_geom(geom), m,
+    pfn_moments_kernel<<<warp_grid(m, 148 * 2), 256, 0, (cudaStream_t)stream>>>(voxels, num_points, coords, make_geom(geom), m,
                                                                      sg, moments65);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());

@@ -296,6 +296,14 @@ def warp_affine_bwd(dout, theta, dsrc, align_corners=False):
     return dsrc
 
 
+BN_BWD_REPLICAS = 8  # A2X_BN_BWD_REPLICAS: copies of the [2C] BN-backward accumulators
+
+
+def bn_bwd_sums_len(C):
+    """A2X_BN_BWD_SUMS(C): doubles to allocate (and zero) for the BN-backward accumulators"""
+    return 2 * C * BN_BWD_REPLICAS + 1
+
+
 class BnBwdStats(ctypes.Structure):
     _fields_ = [("z", ctypes.c_void_p), ("z_cs", c_int), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
                 ("mean", ctypes.c_void_p), ("invstd", ctypes.c_void_p), ("sums", ctypes.c_void_p)]

@@ -648,7 +648,7 @@ class W2CEngine:
             c0 = sum(self.up_filters[:i])
             dy = d_cat[..., c0:c0 + self.up_filters[i]]
             dz = self._act("bwd.dz.d%d" % i, r["z"].shape)
-            sums = self._zeroed(r["tag"] + ".bsums", 2 * r["z"].shape[3], torch.float64)
+            sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
             ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
                             grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
             s = r["stride"]
@@ -678,7 +678,7 @@ class W2CEngine:
                 r = by_tag["%s.b%d.%d" % (tag, i, k)]
                 dz = self._act("bwd.dz." + r["tag"], r["z"].shape)
                 if not sums_ready:
-                    sums = self._zeroed(r["tag"] + ".bsums", 2 * r["z"].shape[3], torch.float64)
+                    sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
                 ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
                                 grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"], sums_ready=sums_ready)
                 cout, cin = r["z"].shape[3], r["x"].shape[3]
@@ -694,7 +694,7 @@ class W2CEngine:
                         # the data gradient of this conv is the dy of layer k-1: accumulate that layer's BN+ReLU backward
                         # reduction (sum g, sum g*zhat) in this GEMM's epilogue instead of a separate pass over dy and z
                         rp = by_tag["%s.b%d.%d" % (tag, i, k - 1)]
-                        sums = self._zeroed(rp["tag"] + ".bsums", 2 * rp["z"].shape[3], torch.float64)
+                        sums = self._zeroed(rp["tag"] + ".bsums", ops.bn_bwd_sums_len(rp["z"].shape[3]), torch.float64)
                         bn_stats = (rp["z"], rp["scale"], rp["shift"], rp["mean"], rp["invstd"], sums)
                         sums_ready = True
                     ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], dprev, bn_stats=bn_stats)

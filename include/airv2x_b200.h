@@ -128,7 +128,7 @@ typedef struct {
     const float* shift;
     const float* mean;
     const float* invstd;
-    double* sums;        /* [2*cin], zeroed by the caller */
+    double* sums;        /* [A2X_BN_BWD_REPLICAS][2*cin], zeroed by the caller (copy 0 is written) */
 } a2x_bn_bwd_stats;
 int a2x_conv2d_dgrad_ex(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
                         int accumulate, const a2x_bn_bwd_stats* bn_stats, a2x_stream_t stream);
@@ -243,7 +243,12 @@ int a2x_bn_train_act(const float* z, int z_cs, const double* sums, double count,
                      float eps, float momentum, int n_updates, float* running_mean, float* running_var, float* scale,
                      float* shift, float* mean_out, float* invstd_out, int relu, const a2x_output* y, long long npix,
                      int C, a2x_stream_t stream);
-/* BN(train)+ReLU backward, pass 1: sums[c] += sum g, sums[C+c] += sum g*zhat with g = dy*(z*scale+shift > 0) */
+/* BN(train)+ReLU backward, pass 1: sum g and sum g*zhat with g = dy*(z*scale+shift > 0), accumulated into
+ * A2X_BN_BWD_REPLICAS copies of [2C] doubles (`sums` = [replicas][2C] + one ticket word, all zeroed by the caller; block b
+ * adds into copy b % replicas, which spreads the same-address atomics, and the last block folds the copies into copy 0,
+ * which is what pass 2 reads). Allocate A2X_BN_BWD_SUMS(C) doubles. */
+#define A2X_BN_BWD_SUMS(C) (2 * (C) * A2X_BN_BWD_REPLICAS + 1)
+#define A2X_BN_BWD_REPLICAS 8
 int a2x_bn_relu_bwd_reduce(const float* dy, int dy_cs, const float* z, int z_cs, const float* scale, const float* shift,
                            const float* mean, const float* invstd, long long npix, int C, double* sums,
                            a2x_stream_t stream);

@@ -142,7 +142,7 @@ def test_batchnorm_relu_train(ops, case):
     ops.bn_finalize(sums, N * H * W, gam.detach(), bet.detach(), 3, rm, rv, scale, shift, mean, invstd)
     yo = ops.Act.empty((N, H, W, C), "cuda", True)
     ops.affine_act(z.detach(), scale, shift, True, yo)
-    bs = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    bs = torch.zeros(ops.bn_bwd_sums_len(C), dtype=torch.float64, device="cuda")
     dz = ops.Act(torch.empty(N, H, W, C, device="cuda"))
     dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     ops.bn_relu_bwd(dy, z.detach(), scale, shift, mean, invstd, bs, dz, dg, db)
@@ -342,8 +342,9 @@ def test_dgrad_fused_bn_bwd_reduction(ops):
     dys = ops.split(nhwc(dy))
     dx_ref, dx = torch.empty(n, h, w, cin, device="cuda"), torch.empty(n, h, w, cin, device="cuda")
     ops.conv_dgrad(dys, pw, 3, 1, dx_ref)
-    sums = torch.zeros(2 * cin, dtype=torch.float64, device="cuda")
+    sums = torch.zeros(ops.bn_bwd_sums_len(cin), dtype=torch.float64, device="cuda")
     ops.conv_dgrad(dys, pw, 3, 1, dx, bn_stats=(z, scale, shift, mean, invstd, sums))
+    sums = sums[:2 * cin]
     assert torch.equal(dx, dx_ref)
     gate = (z * scale + shift > 0).double()
     gg = dx_ref.double() * gate
