@@ -197,38 +197,57 @@ __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restric
         float f[NF];
         int num, agent, cy, cx;
         pillar_features(voxels, num_points, coords, g, pil, lane, f, num, agent, cy, cx);
-        float out0 = 0.f, out1 = 0.f;
-        unsigned int am0 = 0, am1 = 0;
-#pragma unroll 4
-        for (int c = 0; c < NC; ++c) {
-            const float4 w0 = *reinterpret_cast<const float4*>(&sW[c * 12]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&sW[c * 12 + 4]);
-            const float2 w2 = *reinterpret_cast<const float2*>(&sW[c * 12 + 8]);
-            float y = f[0] * w0.x;
-            y = fmaf(f[1], w0.y, y);
-            y = fmaf(f[2], w0.z, y);
-            y = fmaf(f[3], w0.w, y);
-            y = fmaf(f[4], w1.x, y);
-            y = fmaf(f[5], w1.y, y);
-            y = fmaf(f[6], w1.z, y);
-            y = fmaf(f[7], w1.w, y);
-            y = fmaf(f[8], w2.x, y);
-            y = fmaf(f[9], w2.y, y);
-            y = fmaf(y, sS[c], sB[c]);
-            y = y > 0.f ? y : 0.f;  // +0 for every non-positive value: uint order == float order below
-            const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
-            if ((c & 31) == lane) {
-                if (c < 32) out0 = __uint_as_float(mx);
-                else out1 = __uint_as_float(mx);
+        // y[c] for 32 channels at a time in registers (lane = point slot), then a butterfly transpose-reduce: lane L ends
+        // with max over the 32 slots of channel c0 + L (31 shuffles per 32 channels instead of 32 warp reductions + 32
+        // per-lane selects). Values are >= +0 after the ReLU, so unsigned order == float order.
+        float outv[2];
+        unsigned int amv[2] = {0, 0};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            unsigned int yv[32], keep[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = half * 32 + j;
+                const float4 w0 = *reinterpret_cast<const float4*>(&sW[c * 12]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&sW[c * 12 + 4]);
+                const float2 w2 = *reinterpret_cast<const float2*>(&sW[c * 12 + 8]);
+                float y = f[0] * w0.x;
+                y = fmaf(f[1], w0.y, y);
+                y = fmaf(f[2], w0.z, y);
+                y = fmaf(f[3], w0.w, y);
+                y = fmaf(f[4], w1.x, y);
+                y = fmaf(f[5], w1.y, y);
+                y = fmaf(f[6], w1.z, y);
+                y = fmaf(f[7], w1.w, y);
+                y = fmaf(f[8], w2.x, y);
+                y = fmaf(f[9], w2.y, y);
+                y = fmaf(y, sS[c], sB[c]);
+                y = y > 0.f ? y : 0.f;  // +0 for every non-positive value
+                yv[j] = __float_as_uint(y);
+                keep[j] = yv[j];
             }
-            if (amax != nullptr) {
-                const unsigned int who = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(y) == mx)) - 1;
-                if ((c & 31) == lane) {
-                    if (c < 32) am0 = who;
-                    else am1 = who;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const bool up = (lane & s) != 0;
+#pragma unroll
+                for (int i = 0; i < s; ++i) {
+                    const unsigned int send = up ? yv[i] : yv[i + s];
+                    const unsigned int mine = up ? yv[i + s] : yv[i];
+                    yv[i] = max(mine, __shfl_xor_sync(0xffffffffu, send, s));
+                }
+            }
+            outv[half] = __uint_as_float(yv[0]);
+            if (amax != nullptr) {  // arg-max slot (lowest slot among ties) of channel c0 + lane, for the backward
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const unsigned int mj = __shfl_sync(0xffffffffu, yv[0], j);
+                    const unsigned int who = __ffs(__ballot_sync(0xffffffffu, keep[j] == mj)) - 1;
+                    if (lane == j) amv[half] = who;
                 }
             }
         }
+        const float out0 = outv[0], out1 = outv[1];
+        const unsigned int am0 = amv[0], am1 = amv[1];
         const long long cell = ((long long)agent_map[agent] * g.ny + cy) * g.nx + cx;
         float* o = canvas.hi + cell * NC;
         o[lane] = out0;
