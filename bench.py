@@ -397,8 +397,8 @@ def roofline_pass(model, libmod, dd, lab, cw, rc, precision, torch):
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (tapgemm_halo_kernel) from the
-    committed `ncu --set full` capture (profiles/r1_ncu_full_v5_summary.json); None if the summary is absent."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_v5_summary.json")
+    committed `ncu --set full` capture (profiles/r1_ncu_full_v7_summary.json); None if the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_v7_summary.json")
     if not os.path.exists(path):
         return None, None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -412,7 +412,7 @@ def ncu_traffic():
         return None, None
     tot = [b(r["dram__bytes_read.sum"]) + b(r["dram__bytes_write.sum"]) for r in rows]
     return sum(tot) / len(tot), ("mean over the %d tapgemm_halo_kernel launches captured with ncu --set full "
-                                 "(profiles/r1_ncu_full_v5_summary.json); algorithmic operand bytes of those launches "
+                                 "(profiles/r1_ncu_full_v7_summary.json); algorithmic operand bytes of those launches "
                                  "are 22.5 / 22.5 / 11.3 MB — outputs stay in the 126 MB L2 inside the kernel" % len(tot))
 
 
