@@ -492,3 +492,342 @@ int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const in
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Backward kernels of the transformer fusion (training step of the CoBEVT path): LayerNorm, GELU, window attention.
+// Autograd of nn.LayerNorm / nn.GELU / Attention.forward (cobevt_modules/base_transformer.py:6-28,
+// swap_fusion_modules.py:78-127); everything is recomputed from the saved inputs, nothing but x / qkv is stored.
+namespace a2x {
+
+// dx_accum[r][:] += LN'(x[r]) applied to dy[r];  dgamma[c] += sum_r dy*xhat, dbeta[c] += sum_r dy  (double accumulators)
+template <int V>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, int x_cs,
+                                                            const float* __restrict__ dy, int dy_cs,
+                                                            const float* __restrict__ gamma, float eps,
+                                                            float* __restrict__ dx_accum, int dx_cs, long long rows,
+                                                            double* __restrict__ dgamma, double* __restrict__ dbeta) {
+    constexpr int C = V * 128;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float4 gq[V], ag[V], ab[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        gq[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+        ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long r = warp0; r < rows; r += nwarps) {
+        float4 xv[V], dv[V];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            xv[i] = *reinterpret_cast<const float4*>(x + r * x_cs + (i * 32 + lane) * 4);
+            dv[i] = *reinterpret_cast<const float4*>(dy + r * dy_cs + (i * 32 + lane) * 4);
+            s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+            q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
+            ag[i].x += dv[i].x * xv[i].x; ag[i].y += dv[i].y * xv[i].y; ag[i].z += dv[i].z * xv[i].z; ag[i].w += dv[i].w * xv[i].w;
+            ab[i].x += dv[i].x; ab[i].y += dv[i].y; ab[i].z += dv[i].z; ab[i].w += dv[i].w;
+            dv[i].x *= gq[i].x; dv[i].y *= gq[i].y; dv[i].z *= gq[i].z; dv[i].w *= gq[i].w;  // g = dy * gamma
+            sg += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
+            sgx += (dv[i].x * xv[i].x + dv[i].y * xv[i].y) + (dv[i].z * xv[i].z + dv[i].w * xv[i].w);
+        }
+        const float mg = warp_sum(sg) / (float)C, mgx = warp_sum(sgx) / (float)C;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float4* o = reinterpret_cast<float4*>(dx_accum + r * dx_cs + (i * 32 + lane) * 4);
+            float4 t = *o;
+            t.x += rstd * (dv[i].x - mg - xv[i].x * mgx);
+            t.y += rstd * (dv[i].y - mg - xv[i].y * mgx);
+            t.z += rstd * (dv[i].z - mg - xv[i].z * mgx);
+            t.w += rstd * (dv[i].w - mg - xv[i].w * mgx);
+            *o = t;
+        }
+    }
+    // block combine of the per-warp column sums, then one double atomic per column per block
+    __shared__ float red[8][2][V * 128];
+    const int wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        *reinterpret_cast<float4*>(&red[wid][0][(i * 32 + lane) * 4]) = ag[i];
+        *reinterpret_cast<float4*>(&red[wid][1][(i * 32 + lane) * 4]) = ab[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float tg = 0.f, tb = 0.f;
+        for (int w = 0; w < 8; ++w) {
+            tg += red[w][0][c];
+            tb += red[w][1][c];
+        }
+        atomicAdd(&dgamma[c], (double)tg);
+        atomicAdd(&dbeta[c], (double)tb);
+    }
+}
+
+// y = gelu(x) (erf form) as a split operand;  dx = dy * gelu'(x) as a split operand
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ x, long long n4, SplitOut y) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        v.x = 0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752f));
+        v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752f));
+        v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752f));
+        v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752f));
+        store_split4(y, 4 * i, v);
+    }
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+    return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                       long long n4, SplitOut dx) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 d = reinterpret_cast<const float4*>(dy)[i];
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        store_split4(dx, 4 * i, make_float4(d.x * gelu_grad(v.x), d.y * gelu_grad(v.y), d.z * gelu_grad(v.z), d.w * gelu_grad(v.w)));
+    }
+}
+
+// ---- window attention backward. One CTA per (window, head), 128 threads, Q (pre-scaled) / K / V / dO in shared memory.
+// phase 1 (thread = query i): softmax statistics m_i, l_i, D_i = sum_j P_ij dP_ij, and dQ_i;
+// phase 2 (thread = key j):   dK_j, dV_j, and the relative-position-bias gradient (shared-memory table, flushed by atomics).
+struct WinAttBwdParams {
+    const float* qkv;      // [B*L][H][W][3*D]
+    const float* dout;     // [B*L][H][W][D]   gradient w.r.t. the attention output (before to_out)
+    const float* bias;     // [(2L-1)(2w-1)^2][heads]
+    const int* key_mask;   // [B][L] or null
+    float* dqkv;           // [B*L][H][W][3*D]  (written: every token belongs to exactly one window per call)
+    float* dbias;          // [(2L-1)(2w-1)^2][heads], accumulated with atomics
+    int B, L, H, W, heads, w, grid_mode;
+    float scale;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(128) window_attention_bwd_kernel(const WinAttBwdParams p) {
+    extern __shared__ float sm[];
+    const int ww = p.w * p.w;
+    const int n = p.L * ww;
+    constexpr int RS = DH + 1;      // row stride: conflict-free column walks
+    float* sQ = sm;                 // [n][RS]  q * scale
+    float* sK = sQ + n * RS;
+    float* sV = sK + n * RS;
+    float* sO = sV + n * RS;        // dO
+    float* sM = sO + n * RS;        // [n] row max
+    float* sL = sM + n;             // [n] 1 / row sum
+    float* sD = sL + n;             // [n] D_i
+    const int nb = (2 * p.L - 1) * (2 * p.w - 1) * (2 * p.w - 1);
+    float* sB = sD + n;             // [nb] bias of this head
+    float* sdB = sB + nb;           // [nb] bias gradient of this CTA
+    int* sTok = reinterpret_cast<int*>(sdB + nb);
+    const int D = p.heads * DH;
+    const int X = p.H / p.w, Y = p.W / p.w;
+    const int head = blockIdx.x % p.heads;
+    int win = blockIdx.x / p.heads;
+    const int y = win % Y;
+    win /= Y;
+    const int x = win % X;
+    const int b = win / X;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int l = t / ww, r = t - l * ww;
+        const int w1 = r / p.w, w2 = r - w1 * p.w;
+        const int ph = p.grid_mode ? w1 * X + x : x * p.w + w1;
+        const int pw = p.grid_mode ? w2 * Y + y : y * p.w + w2;
+        sTok[t] = ((b * p.L + l) * p.H + ph) * p.W + pw;
+    }
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        sB[i] = p.bias[i * p.heads + head];
+        sdB[i] = 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * DH; i += blockDim.x) {
+        const int t = i / DH, c = i - t * DH;
+        const float* row = p.qkv + (long long)sTok[t] * (3 * D) + head * DH + c;
+        sQ[t * RS + c] = row[0] * p.scale;
+        sK[t * RS + c] = row[D];
+        sV[t * RS + c] = row[2 * D];
+        sO[t * RS + c] = p.dout[(long long)sTok[t] * D + head * DH + c];
+    }
+    __syncthreads();
+    const int s2 = 2 * p.w - 1;
+    auto valid_key = [&](int lj) { return p.key_mask == nullptr || p.key_mask[b * p.L + lj] != 0; };
+    auto bias_idx = [&](int ti, int tj) {
+        const int li = ti / ww, ri = ti - li * ww, lj = tj / ww, rj = tj - lj * ww;
+        return ((li - lj + p.L - 1) * s2 + (ri / p.w - rj / p.w + p.w - 1)) * s2 + (ri % p.w - rj % p.w + p.w - 1);
+    };
+    // ---- phase 1
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float q[DH], o[DH], dq[DH];
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+            q[c] = sQ[i * RS + c];
+            o[c] = sO[i * RS + c];
+            dq[c] = 0.f;
+        }
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < n; ++j) {
+            if (!valid_key(j / ww)) continue;
+            float s = sB[bias_idx(i, j)];
+#pragma unroll
+            for (int c = 0; c < DH; ++c) s = fmaf(q[c], sK[j * RS + c], s);
+            const float mn = fmaxf(m, s);
+            l = l * expf(m - mn) + expf(s - mn);
+            m = mn;
+        }
+        const float inv = 1.f / l;
+        float Dv = 0.f;
+        for (int j = 0; j < n; ++j) {
+            if (!valid_key(j / ww)) continue;
+            float s = sB[bias_idx(i, j)], dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) {
+                s = fmaf(q[c], sK[j * RS + c], s);
+                dp = fmaf(o[c], sV[j * RS + c], dp);
+            }
+            Dv = fmaf(expf(s - m) * inv, dp, Dv);
+        }
+        for (int j = 0; j < n; ++j) {
+            if (!valid_key(j / ww)) continue;
+            float s = sB[bias_idx(i, j)], dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) {
+                s = fmaf(q[c], sK[j * RS + c], s);
+                dp = fmaf(o[c], sV[j * RS + c], dp);
+            }
+            const float ds = expf(s - m) * inv * (dp - Dv);
+#pragma unroll
+            for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, sK[j * RS + c], dq[c]);
+        }
+        sM[i] = m;
+        sL[i] = inv;
+        sD[i] = Dv;
+        float* out = p.dqkv + (long long)sTok[i] * (3 * D) + head * DH;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) out[c] = dq[c] * p.scale;  // s = (q * scale) . k
+    }
+    __syncthreads();
+    // ---- phase 2
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float k[DH], v[DH], dk[DH], dv[DH];
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+            k[c] = sK[j * RS + c];
+            v[c] = sV[j * RS + c];
+            dk[c] = 0.f;
+            dv[c] = 0.f;
+        }
+        const bool ok = valid_key(j / ww);
+        if (ok) {
+            for (int i = 0; i < n; ++i) {
+                const int bi = bias_idx(i, j);
+                float s = sB[bi], dp = 0.f;
+#pragma unroll
+                for (int c = 0; c < DH; ++c) {
+                    s = fmaf(sQ[i * RS + c], k[c], s);
+                    dp = fmaf(sO[i * RS + c], v[c], dp);
+                }
+                const float pij = expf(s - sM[i]) * sL[i];
+                const float ds = pij * (dp - sD[i]);
+                atomicAdd(&sdB[bi], ds);
+#pragma unroll
+                for (int c = 0; c < DH; ++c) {
+                    dv[c] = fmaf(pij, sO[i * RS + c], dv[c]);
+                    dk[c] = fmaf(ds, sQ[i * RS + c], dk[c]);  // sQ already carries the scale
+                }
+            }
+        }
+        float* out = p.dqkv + (long long)sTok[j] * (3 * D) + head * DH;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+            out[D + c] = dk[c];
+            out[2 * D + c] = dv[c];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sdB[i]);
+}
+
+}  // namespace a2x
+
+extern "C" {
+
+int a2x_layernorm_bwd(const float* x, int x_cs, const float* dy, int dy_cs, long long rows, int C, const float* gamma,
+                      float eps, float* dx_accum, int dx_cs, double* dgamma, double* dbeta, a2x_stream_t stream) {
+    A2X_REQUIRE(x && dy && gamma && dx_accum && dgamma && dbeta && rows > 0, "layernorm_bwd: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long b = (rows + 63) / 64;
+    if (b > 148 * 4) b = 148 * 4;
+    const int g = (int)(b < 1 ? 1 : b);
+    if (C == 128) a2x::layernorm_bwd_kernel<1><<<g, 256, 0, st>>>(x, x_cs, dy, dy_cs, gamma, eps, dx_accum, dx_cs, rows, dgamma, dbeta);
+    else if (C == 256) a2x::layernorm_bwd_kernel<2><<<g, 256, 0, st>>>(x, x_cs, dy, dy_cs, gamma, eps, dx_accum, dx_cs, rows, dgamma, dbeta);
+    else {
+        a2x::set_error("layernorm_bwd: channel count %d not in {128, 256}", C);
+        return 1;
+    }
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_gelu_fwd(const float* x, long long n, const a2x_output* y, a2x_stream_t stream) {
+    A2X_REQUIRE(x && y && y->hi && n > 0 && n % 4 == 0, "gelu_fwd: bad args");
+    long long b = (n / 4 + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    a2x::gelu_fwd_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, n / 4, a2x::tr_split(y));
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_gelu_bwd(const float* dy, const float* x, long long n, const a2x_output* dx, a2x_stream_t stream) {
+    A2X_REQUIRE(dy && x && dx && dx->hi && n > 0 && n % 4 == 0, "gelu_bwd: bad args");
+    long long b = (n / 4 + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    a2x::gelu_bwd_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(dy, x, n / 4, a2x::tr_split(dx));
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* bias_table, const int* key_mask, int B,
+                             int L, int H, int W, int heads, int dim_head, int window, int grid_mode, float scale,
+                             float* dqkv, float* dbias_table, a2x_stream_t stream) {
+    A2X_REQUIRE(qkv && dout && bias_table && dqkv && dbias_table && B > 0 && L > 0 && heads > 0 && window > 0,
+                "window_attention_bwd: bad args");
+    A2X_REQUIRE(H % window == 0 && W % window == 0, "window_attention_bwd: H, W must be multiples of the window");
+    a2x::WinAttBwdParams p;
+    p.qkv = qkv; p.dout = dout; p.bias = bias_table; p.key_mask = key_mask; p.dqkv = dqkv; p.dbias = dbias_table;
+    p.B = B; p.L = L; p.H = H; p.W = W; p.heads = heads; p.w = window; p.grid_mode = grid_mode; p.scale = scale;
+    const int n = L * window * window;
+    const int nb = (2 * L - 1) * (2 * window - 1) * (2 * window - 1);
+    const size_t smem = (size_t)(4 * n * (dim_head + 1) + 3 * n + 2 * nb + n) * sizeof(float);
+    A2X_REQUIRE(smem <= 200 * 1024, "window_attention_bwd: window of %d tokens does not fit shared memory", n);
+    const long long grid = (long long)B * (H / window) * (W / window) * heads;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dim_head == 32) {
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a2x::window_attention_bwd_kernel<32><<<(unsigned)grid, 128, smem, st>>>(p);
+    } else if (dim_head == 16) {
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a2x::window_attention_bwd_kernel<16><<<(unsigned)grid, 128, smem, st>>>(p);
+    } else {
+        a2x::set_error("window_attention_bwd: dim_head %d not in {16, 32}", dim_head);
+        return 1;
+    }
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

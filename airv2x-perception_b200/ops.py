@@ -599,3 +599,28 @@ def split_attn_fuse(w0, w1, w2, fc1, ln_g, ln_b, fc2, sums_ws, weights_ws, x):
     n, h, w, c = x.shape
     call("a2x_split_attn_fuse", _ptr(w0), _ptr(w1), _ptr(w2), c_int(n), c_ll(h * w), c_int(c), _ptr(fc1), _ptr(ln_g),
          _ptr(ln_b), _ptr(fc2), _ptr(sums_ws), _ptr(weights_ws), _ptr(x), stream_ptr())
+
+
+# transformer fusion backward ----------------------------------------------------------------------------------------
+def layernorm_bwd(x, dy, gamma, dx_accum, dgamma, dbeta, eps=1e-5):
+    """x, dy, dx_accum: NHWC tensors (dx_accum += LN backward); dgamma/dbeta: zeroed float64 [C]"""
+    call("a2x_layernorm_bwd", _ptr(x), c_int(_cs(x)), _ptr(dy), c_int(_cs(dy)), c_ll(_rows(x)), c_int(x.shape[3]),
+         _ptr(gamma), c_f(eps), _ptr(dx_accum), c_int(_cs(dx_accum)), _ptr(dgamma), _ptr(dbeta), stream_ptr())
+
+
+def gelu_fwd(x, out):
+    call("a2x_gelu_fwd", _ptr(x), c_ll(x.numel()), _op(out), stream_ptr())
+    return out
+
+
+def gelu_bwd(dy, x, out):
+    call("a2x_gelu_bwd", _ptr(dy), _ptr(x), c_ll(x.numel()), _op(out), stream_ptr())
+    return out
+
+
+def window_attention_bwd(qkv, dout, bias_table, key_mask, B, L, heads, dim_head, window, grid_mode, dqkv, dbias):
+    assert qkv.is_contiguous() and dout.is_contiguous() and dqkv.is_contiguous()
+    _, H, W, _ = qkv.shape
+    call("a2x_window_attention_bwd", _ptr(qkv), _ptr(dout), _ptr(bias_table), _ptr(key_mask), c_int(B), c_int(L), c_int(H),
+         c_int(W), c_int(heads), c_int(dim_head), c_int(window), c_int(int(grid_mode)), c_f(dim_head ** -0.5), _ptr(dqkv),
+         _ptr(dbias), stream_ptr())

@@ -170,6 +170,19 @@ int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const in
                              int heads, int dim_head, int window, int grid_mode, float scale, const a2x_output* out,
                              a2x_stream_t stream);
 
+/* Backward of the token kernels (training step of the transformer fusion; autograd of nn.LayerNorm / nn.GELU /
+ * Attention.forward). layernorm_bwd: dx_accum += dLN(dy) (the residual stream's gradient), dgamma/dbeta double [C]
+ * accumulators (caller zeroes). gelu_fwd / gelu_bwd: erf GELU of a pre-activation kept in fp32. window_attention_bwd:
+ * dqkv [B*L][H][W][3*heads*dim_head] from dout (gradient of the attention output), everything recomputed from qkv;
+ * dbias_table accumulated with atomics (caller zeroes). */
+int a2x_layernorm_bwd(const float* x, int x_cs, const float* dy, int dy_cs, long long rows, int C, const float* gamma,
+                      float eps, float* dx_accum, int dx_cs, double* dgamma, double* dbeta, a2x_stream_t stream);
+int a2x_gelu_fwd(const float* x, long long n, const a2x_output* y, a2x_stream_t stream);
+int a2x_gelu_bwd(const float* dy, const float* x, long long n, const a2x_output* dx, a2x_stream_t stream);
+int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* bias_table, const int* key_mask, int B,
+                             int L, int H, int W, int heads, int dim_head, int window, int grid_mode, float scale,
+                             float* dqkv, float* dbias_table, a2x_stream_t stream);
+
 /* ---------------------------------------------------------------- V2X-ViT fusion (csrc/v2xvit.cu)
  * x[a][p][:] += Linear(emb_table[emb_idx[a]])  — RTE, v2xvit_modules/v2xvit_basic.py:41-80. vec_ws: [n_agents][C]. */
 int a2x_rte_add(float* x, int n_agents, long long pix, int C, const float* emb_table, const int* emb_idx_dev,

@@ -210,3 +210,55 @@ def test_naive_compressor_eval_matches_reference_golden():
         out = model(C.to_device(CC.golden_scene(cfg, gold), "cuda"))
     for k in ("psm", "rm", "obj"):
         assert np.abs(out[k].cpu().numpy() - gold["cmp2_eval_" + k]).max() < TOL, k
+
+
+def test_layernorm_gelu_backward(ops):
+    g = torch.Generator().manual_seed(20)
+    x = (torch.randn(2, 5, 7, 256, generator=g) * 2 + 0.5).cuda().requires_grad_(True)
+    gam = (torch.rand(256, generator=g) + 0.5).cuda().requires_grad_(True)
+    bet = torch.randn(256, generator=g).cuda().requires_grad_(True)
+    dy = torch.randn(2, 5, 7, 256, generator=g).cuda()
+    F.layer_norm(x, (256,), gam, bet, 1e-5).backward(dy)
+    acc = torch.randn(2, 5, 7, 256, generator=g).cuda()
+    dx = acc.clone()
+    dg, db = torch.zeros(256, dtype=torch.float64, device="cuda"), torch.zeros(256, dtype=torch.float64, device="cuda")
+    ops.layernorm_bwd(x.detach(), dy, gam.detach(), dx, dg, db)
+    assert rel(dx - acc, x.grad) < 1e-5 and rel(dg.float(), gam.grad) < 1e-5 and rel(db.float(), bet.grad) < 1e-5
+    h = torch.randn(2, 5, 7, 256, generator=g).cuda().requires_grad_(True)
+    F.gelu(h).backward(dy)
+    y = ops.Act.empty(h.shape, "cuda", True)
+    ops.gelu_fwd(h.detach(), y)
+    d = ops.Act.empty(h.shape, "cuda", True)
+    ops.gelu_bwd(dy, h.detach(), d)
+    assert rel(y.hi, F.gelu(h.detach())) < 1e-6 and rel(d.hi, h.grad) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(2, 7, 8, 8, 8, 32, 4), (1, 3, 4, 8, 4, 16, 2)])
+@pytest.mark.parametrize("grid_mode", [False, True])
+def test_window_attention_backward(ops, case, grid_mode):
+    """dq, dk, dv and the relative-position-bias gradient == torch autograd of the attention core"""
+    B, L, H, W, heads, dh, w = case
+    D = heads * dh
+    g = torch.Generator().manual_seed(21)
+    qkv = torch.randn(B * L, H, W, 3 * D, generator=g, dtype=torch.float64).requires_grad_(True)
+    table = torch.randn((2 * L - 1) * (2 * w - 1) ** 2, heads, generator=g, dtype=torch.float64).requires_grad_(True)
+    mask = torch.ones(B, L, dtype=torch.int32)
+    mask[0, L - 1] = 0
+    dout = torch.randn(B * L, H, W, D, generator=g, dtype=torch.float64)
+    X, Y = H // w, W // w
+    t = qkv.view(B, L, H, W, 3 * D)
+    t = t.view(B, L, w, X, w, Y, 3 * D).permute(0, 1, 3, 5, 2, 4, 6) if grid_mode else t.view(B, L, X, w, Y, w, 3 * D).permute(0, 1, 2, 4, 3, 5, 6)
+    tok = t.permute(0, 2, 3, 1, 4, 5, 6).reshape(B * X * Y, L * w * w, 3 * D)
+    q, k, v = tok.chunk(3, -1)
+    hs = lambda z: z.reshape(z.shape[0], z.shape[1], heads, dh).permute(0, 2, 1, 3)
+    sim = (hs(q) * dh ** -0.5) @ hs(k).transpose(-1, -2) + F.embedding(CO.relative_position_index(L, w), table).permute(2, 0, 1)
+    km = mask.view(B, 1, 1, L, 1, 1).expand(B, X, Y, L, w, w).reshape(B * X * Y, 1, 1, L * w * w)
+    o = (sim.masked_fill(km == 0, -float("inf")).softmax(-1) @ hs(v)).permute(0, 2, 1, 3).reshape(B, X, Y, L, w, w, D)
+    ref = o.permute(0, 3, 4, 1, 5, 2, 6).reshape(B * L, H, W, D) if grid_mode else o.permute(0, 3, 1, 4, 2, 5, 6).reshape(B * L, H, W, D)
+    ref.backward(dout)
+    dqkv = torch.full((B * L, H, W, 3 * D), 9.0, device="cuda")
+    dbias = torch.zeros(table.shape, device="cuda")
+    ops.window_attention_bwd(qkv.detach().float().cuda(), dout.float().cuda(), table.detach().float().cuda(), mask.cuda(), B, L,
+                             heads, dh, w, grid_mode, dqkv, dbias)
+    assert rel(dqkv.cpu().double(), qkv.grad) < 2e-5
+    assert rel(dbias.cpu().double(), table.grad) < 2e-5
