@@ -221,10 +221,251 @@ class CoBEVTEngine(W2CEngine):
         ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
         return heads
 
+    # ------------------------------------------------------------------ training step (dropout disabled)
+    def _sub(self, i, part, kind):
+        return "fusion_net.layers.%d.%s_%s" % (i, part, kind)
+
+    def forward_train(self, P, lidar, layout):
+        """Train-mode forward (batch-statistic BatchNorm in the encoder, dropout = identity) that keeps what the
+        backward needs: per sublayer the residual input, the LayerNorm output (GEMM operand of the weight gradients), the
+        qkv tensor / the attention output, the FFN pre-activation and hidden activation."""
+        self._begin_step()
+        rec = []
+        W = self._pack_weights(P)
+        N = layout["n_total"]
+        canvas = self._encode(P, lidar, layout, True, rec)
+        self._last_canvas_shape = tuple(canvas.shape)
+        x = canvas
+        cat = None
+        for i in range(len(self.layer_nums)):
+            x = self._block(P, W, i, x, True, 1, "E", rec)
+            if cat is None:
+                h2, w2 = x.shape[1], x.shape[2]
+                cat = self._act("E.cat", (N, h2, w2, self.c_cat))
+            c0 = sum(self.up_filters[:i])
+            with self._on_side():
+                self._deblock(P, W, i, x, cat.slice_c(c0, c0 + self.up_filters[i]), True, 1, "E", rec)
+        self._join_side()
+        assert not self.compression, "NaiveCompressor training is not implemented"
+        y1 = self._act("E.s1", (N, h2, w2, self.c_shrink))
+        y2 = self._buf("E.s2", (N, h2, w2, self.c_shrink))
+        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,
+                     shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
+        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, Act(y2),
+                     shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
+        B = len(layout["record_len"])
+        d = self.dim
+        X = self._buf("fax.x", (B * self.L, h2, w2, d))
+        ops.regroup(y2, layout["scene_start"], layout["scene_len"], B, self.L, Act(X))
+        key_mask = layout["key_mask"] if self.fa.get("mask", False) else None
+        subs = []
+        for i in range(self.fa["depth"]):
+            for part, grid_mode in (("window", False), ("grid", True)):
+                pa, pf = self._sub(i, part, "attention"), self._sub(i, part, "ffd")
+                tag = "%d%s" % (i, part[0])
+                # attention sublayer
+                xin = self._buf("sv.xin.a" + tag, X.shape)
+                xin.copy_(X)
+                ln = self._act("sv.ln.a" + tag, X.shape)
+                ops.layernorm_fwd(X, P[pa + ".norm.weight"], P[pa + ".norm.bias"], ln)
+                qkv = self._buf("sv.qkv." + tag, X.shape[:3] + (3 * d,))
+                ops.linear_fwd(ln, W[pa + ".fn.to_qkv.weight"], Act(qkv))
+                att = self._act("sv.att." + tag, X.shape)
+                ops.window_attention_fwd(qkv, P[pa + ".fn.relative_position_bias_table.weight"], key_mask, B, self.L,
+                                         self.heads, self.fa["dim_head"], self.fa["window_size"], grid_mode, att)
+                ops.linear_fwd(att, W[pa + ".fn.to_out.0.weight"], Act(X), accumulate=True)
+                subs.append(dict(kind="att", pre=pa, xin=xin, ln=ln, qkv=qkv, att=att, grid=grid_mode))
+                # feed-forward sublayer (pre-activation kept in fp32: GELU' needs it)
+                xin = self._buf("sv.xin.f" + tag, X.shape)
+                xin.copy_(X)
+                ln = self._act("sv.ln.f" + tag, X.shape)
+                ops.layernorm_fwd(X, P[pf + ".norm.weight"], P[pf + ".norm.bias"], ln)
+                pre = self._buf("sv.pre." + tag, X.shape[:3] + (self.fa["mlp_dim"],))
+                ops.linear_fwd(ln, W[pf + ".fn.net.0.weight"], Act(pre), bias=P[pf + ".fn.net.0.bias"])
+                hid = self._act("sv.hid." + tag, pre.shape)
+                ops.gelu_fwd(pre, hid)
+                ops.linear_fwd(hid, W[pf + ".fn.net.3.weight"], Act(X), bias=P[pf + ".fn.net.3.bias"], accumulate=True)
+                subs.append(dict(kind="ffn", pre=pf, xin=xin, ln=ln, hpre=pre, hid=hid))
+        m = self._act("fax.mean", (B, h2, w2, d))
+        ops.agent_mean_layernorm(X, B, self.L, P["fusion_net.mlp_head.2.weight"], P["fusion_net.mlp_head.2.bias"], m)
+        fused = self._act("fax.fused", (B, h2, w2, d))
+        ops.linear_fwd(m, W["fusion_net.mlp_head.3.weight"], fused, bias=P["fusion_net.mlp_head.3.bias"])
+        heads = self._buf("heads.out", (B, h2, w2, HEAD_PAD))
+        ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
+        self.saved = dict(rec=rec, W=W, subs=subs, X=X, m=m, fused=fused, y1=y1, y2=y2, cat=cat, layout=layout,
+                          key_mask=key_mask, B=B)
+        return heads
+
+    def backward_train(self, P, dheads, grads):
+        """dheads: [B,h,w,HEAD_PAD] gradient w.r.t. the head logits; grads: name -> fp32 tensor (written)."""
+        S = self.saved
+        W, rec, layout, B = S["W"], S["rec"], S["layout"], S["B"]
+        nc, nr = self.A * self.K, 7 * self.A
+        d = self.dim
+        unpack = []
+
+        def zero_f32(name, n):
+            return self._zeroed(name, n, torch.float32)
+
+        def lin_wgrad(x_act, dy_act, wname):
+            """grad of nn.Linear weight [out, in] = 1x1 conv wgrad"""
+            co, ci = dy_act.shape[3], x_act.shape[3]
+            dwp = zero_f32(wname + ".dwp", co * ci).view(1, co, ci)
+            ops.conv_wgrad(x_act, dy_act, 1, 1, dwp)
+            g = grads[wname]
+            unpack.append(ops.conv_unpack_job(dwp, g.view(co, ci, 1, 1)))
+
+        def col_sums(t, C, outs):
+            sums = self._zeroed("bias.sums", 2 * C, torch.float64)
+            ops.channel_stats(t, sums)
+            for out, c0 in outs:
+                unpack.append(ops.sums_unpack_job(sums, out, c0))
+
+        def split_of(t, name):
+            a = self._act(name, t.shape)
+            ops.affine_act(t, None, None, False, a)
+            return a
+
+        def ln_bwd(xin, d_ln, pre_norm, dX):
+            acc = self._zeroed(pre_norm + ".lnacc", 2 * d, torch.float64)
+            ops.layernorm_bwd(xin, d_ln, P[pre_norm + ".weight"], dX, acc[:d], acc[d:])
+            unpack.append(ops.sums_unpack_job(acc, grads[pre_norm + ".weight"], 0))
+            unpack.append(ops.sums_unpack_job(acc, grads[pre_norm + ".bias"], d))
+
+        # ---- heads, mlp_head
+        dh = split_of(dheads, "bwd.dheads")
+        dwp = zero_f32("heads.dwp", HEAD_PAD * self.c_shrink).view(1, HEAD_PAD, self.c_shrink)
+        ops.conv_wgrad(S["fused"], dh, 1, 1, dwp)
+        for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+            unpack.append(ops.conv_unpack_job(dwp, grads[name + ".weight"], row0))
+        col_sums(dheads, HEAD_PAD, [(grads["cls_head.bias"], 0), (grads["reg_head.bias"], nc), (grads["obj_head.bias"], nc + nr)])
+        d_fused = self._buf("bwd.d_fused", S["fused"].shape)
+        ops.conv_dgrad(dh, W["heads"], 1, 1, d_fused)
+        dfs = split_of(d_fused, "bwd.dfs")
+        lin_wgrad(S["m"], dfs, "fusion_net.mlp_head.3.weight")
+        col_sums(d_fused, d, [(grads["fusion_net.mlp_head.3.bias"], 0)])
+        d_m = self._buf("bwd.d_m", S["m"].shape)
+        ops.conv_dgrad(dfs, W["fusion_net.mlp_head.3.weight"], 1, 1, d_m)
+        # mean over agents + LayerNorm (swap_fusion_modules.py:269-273)
+        X = S["X"]
+        xbar = self._buf("bwd.xbar", S["m"].shape)
+        ops.agent_mean(X, B, self.L, xbar)
+        d_xbar = self._buf("bwd.d_xbar", S["m"].shape)
+        d_xbar.zero_()
+        ln_bwd(xbar, d_m, "fusion_net.mlp_head.2", d_xbar)
+        dX = self._buf("bwd.dX", X.shape)
+        ops.agent_broadcast(d_xbar, B, self.L, 1.0 / self.L, dX)
+        # ---- sublayers in reverse
+        for sl in reversed(S["subs"]):
+            pre = sl["pre"]
+            dXs = split_of(dX, "bwd.dXs")
+            if sl["kind"] == "ffn":
+                lin_wgrad(sl["hid"], dXs, pre + ".fn.net.3.weight")
+                col_sums(dX, d, [(grads[pre + ".fn.net.3.bias"], 0)])
+                d_hid = self._buf("bwd.d_hid", sl["hid"].shape)
+                ops.conv_dgrad(dXs, W[pre + ".fn.net.3.weight"], 1, 1, d_hid)
+                d_pre = self._act("bwd.d_pre", sl["hid"].shape)
+                ops.gelu_bwd(d_hid, sl["hpre"], d_pre)
+                lin_wgrad(sl["ln"], d_pre, pre + ".fn.net.0.weight")
+                col_sums(d_pre.hi, d_pre.shape[3], [(grads[pre + ".fn.net.0.bias"], 0)])
+                d_ln = self._buf("bwd.d_ln", X.shape)
+                ops.conv_dgrad(d_pre, W[pre + ".fn.net.0.weight"], 1, 1, d_ln)
+            else:
+                lin_wgrad(sl["att"], dXs, pre + ".fn.to_out.0.weight")
+                d_att = self._buf("bwd.d_att", X.shape)
+                ops.conv_dgrad(dXs, W[pre + ".fn.to_out.0.weight"], 1, 1, d_att)
+                dqkv = self._buf("bwd.dqkv", sl["qkv"].shape)
+                tname = pre + ".fn.relative_position_bias_table.weight"
+                grads[tname].zero_()
+                ops.window_attention_bwd(sl["qkv"], d_att, P[tname], S["key_mask"], B, self.L, self.heads,
+                                         self.fa["dim_head"], self.fa["window_size"], sl["grid"], dqkv, grads[tname])
+                dqs = split_of(dqkv, "bwd.dqs")
+                lin_wgrad(sl["ln"], dqs, pre + ".fn.to_qkv.weight")
+                d_ln = self._buf("bwd.d_ln", X.shape)
+                ops.conv_dgrad(dqs, W[pre + ".fn.to_qkv.weight"], 1, 1, d_ln)
+            ln_bwd(sl["xin"], d_ln, pre + ".norm", dX)
+        # ---- regroup^T: gradients of the valid agents' shrunk maps (padded slots are dropped)
+        y2, y1, cat = S["y2"], S["y1"], S["cat"]
+        d_y2 = self._buf("bwd.d_y2", y2.shape)
+        pos = 0
+        for b, n in enumerate(layout["record_len"]):
+            d_y2[pos:pos + n].copy_(dX[b * self.L:b * self.L + n])
+            pos += n
+        # ---- shrink header
+        g2 = self._act("bwd.g2", y2.shape)
+        ops.relu_bwd(d_y2, y2, g2)  # y2 is a plain fp32 tensor here
+        n2, n1 = "shrink_conv.layers.0.double_conv.2", "shrink_conv.layers.0.double_conv.0"
+        dwp = zero_f32(n2 + ".dwp", 9 * self.c_shrink * self.c_shrink).view(9, self.c_shrink, self.c_shrink)
+        ops.conv_wgrad(y1, g2, 3, 1, dwp)
+        unpack.append(ops.conv_unpack_job(dwp, grads[n2 + ".weight"]))
+        col_sums(g2.hi, self.c_shrink, [(grads[n2 + ".bias"], 0)])
+        d_y1 = self._buf("bwd.d_y1", y1.shape)
+        ops.conv_dgrad(g2, W[n2 + ".weight"], 3, 1, d_y1)
+        g1 = self._act("bwd.g1", y1.shape)
+        ops.relu_bwd(d_y1, y1.hi, g1)
+        dwp = zero_f32(n1 + ".dwp", self.c_shrink * self.c_cat).view(1, self.c_shrink, self.c_cat)
+        ops.conv_wgrad(cat, g1, 1, 1, dwp)
+        unpack.append(ops.conv_unpack_job(dwp, grads[n1 + ".weight"]))
+        col_sums(g1.hi, self.c_shrink, [(grads[n1 + ".bias"], 0)])
+        d_cat = self._buf("bwd.d_cat", cat.shape)
+        ops.conv_dgrad(g1, W[n1 + ".weight"], 1, 1, d_cat)
+        # ---- backbone: deblocks, then blocks deep -> shallow
+        by_tag = {r["tag"]: r for r in rec if r["kind"] == "conv"}
+        deconvs = {r["level"]: r for r in rec if r["kind"] == "deconv"}
+        nlev = len(self.layer_nums)
+        d_x = [None] * nlev
+        for i in range(nlev):
+            r = deconvs[i]
+            c0 = sum(self.up_filters[:i])
+            dy = d_cat[..., c0:c0 + self.up_filters[i]]
+            dz = self._act("bwd.dz.d%d" % i, r["z"].shape)
+            sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
+            ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
+                            grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
+            s = r["stride"]
+            cin, cout = r["x"].shape[3], r["z"].shape[3]
+            dwp = zero_f32(r["conv"] + ".dwp", s * s * cin * cout).view(s * s, cin, cout)
+            ops.deconv_wgrad(r["x"], dz, s, dwp)
+            unpack.append(ops.deconv_unpack_job(dwp, grads[r["conv"]]))
+            d_x[i] = self._buf("bwd.dx%d" % i, r["x"].shape)
+            ops.deconv_dgrad(dz, W[r["conv"]], s, d_x[i])
+        d_canvas = self._buf("bwd.d_canvas", self._last_canvas_shape)
+        for i in range(nlev - 1, -1, -1):
+            dy = d_x[i]
+            for k in range(self.layer_nums[i], -1, -1):
+                r = by_tag["E.b%d.%d" % (i, k)]
+                dz = self._act("bwd.dz." + r["tag"], r["z"].shape)
+                sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
+                ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
+                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
+                cout, cin = r["z"].shape[3], r["x"].shape[3]
+                dwp = zero_f32(r["conv"] + ".dwp", 9 * cout * cin).view(9, cout, cin)
+                ops.conv_wgrad(r["x"], dz, 3, r["stride"], dwp)
+                unpack.append(ops.conv_unpack_job(dwp, grads[r["conv"]]))
+                if k > 0:
+                    dprev = self._buf("bwd.dprev.b%d.%d" % (i, k), r["x"].shape)
+                    ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], dprev)
+                    dy = dprev
+                elif i > 0:
+                    ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], d_x[i - 1], accumulate=True)
+                else:
+                    ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], d_canvas)
+        for r in rec:
+            if r["kind"] != "pfn":
+                continue
+            pre = r["pre"]
+            acc = self._buf("pfn.%s.acc" % r["type"], (64 * 12,), torch.float64)
+            ops.pfn_bwd(r["vox"], r["num"], r["coords"], r["geom"], P[pre + ".linear.weight"], r["scale"], r["shift"],
+                        r["mean"], r["invstd"], r["amap"], d_canvas, r["amax"], r["moments"], r["rows"], acc,
+                        grads[pre + ".linear.weight"], grads[pre + ".norm.weight"], grads[pre + ".norm.bias"], seg=r["seg"])
+        for lo in range(0, len(unpack), 128):
+            ops.unpack_wgrads_batched(self._job_table("unpack%d" % lo, unpack[lo:lo + 128]))
+        return grads
+
     def forward(self, P, lidar, layout, training, k_list=None):
         if training:
-            raise NotImplementedError("CoBEVT on the B200 kernels is forward-only (eval mode) in this round: the "
-                                      "transformer-fusion backward and dropout are not implemented")
+            raise NotImplementedError("Airv2xCoBEVT: train-mode forward(data_dict) is not wired to autograd; use "
+                                      "train_step(data_dict, label_dict) (forward + loss + backward, dropout disabled)")
         self._begin_step()
         W = self._pack_weights(P)
         feat = self.encode(P, W, lidar, layout)

@@ -831,3 +831,53 @@ int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* b
 }
 
 }  // extern "C"
+
+namespace a2x {
+// out[b][p][:] = mean_l x[b][l][p][:]   and its adjoint   dst[b][l][p][:] = scale * src[b][p][:]
+__global__ void agent_mean_kernel(const float* __restrict__ x, int L, long long img4, float* __restrict__ out,
+                                  long long total4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / img4, e = i - b * img4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < L; ++l) {
+            const float4 t = reinterpret_cast<const float4*>(x)[(b * L + l) * img4 + e];
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        const float inv = 1.f / (float)L;
+        reinterpret_cast<float4*>(out)[i] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+    }
+}
+__global__ void agent_broadcast_kernel(const float* __restrict__ src, int L, long long img4, float scale,
+                                       float* __restrict__ dst, long long total4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long slot = i / img4, e = i - slot * img4;
+        const float4 t = reinterpret_cast<const float4*>(src)[(slot / L) * img4 + e];
+        reinterpret_cast<float4*>(dst)[i] = make_float4(t.x * scale, t.y * scale, t.z * scale, t.w * scale);
+    }
+}
+}  // namespace a2x
+
+extern "C" {
+int a2x_agent_mean(const float* x, int B, int L, long long img_elems, float* out, a2x_stream_t stream) {
+    A2X_REQUIRE(x && out && B > 0 && L > 0 && img_elems > 0 && img_elems % 4 == 0, "agent_mean: bad args");
+    const long long total4 = (long long)B * (img_elems / 4);
+    long long b = (total4 + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    a2x::agent_mean_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, L, img_elems / 4, out, total4);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int a2x_agent_broadcast(const float* src, int B, int L, long long img_elems, float scale, float* dst, a2x_stream_t stream) {
+    A2X_REQUIRE(src && dst && B > 0 && L > 0 && img_elems > 0 && img_elems % 4 == 0, "agent_broadcast: bad args");
+    const long long total4 = (long long)B * L * (img_elems / 4);
+    long long b = (total4 + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    a2x::agent_broadcast_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(src, L, img_elems / 4, scale, dst, total4);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+}  // extern "C"

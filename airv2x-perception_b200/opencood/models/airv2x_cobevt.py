@@ -137,7 +137,38 @@ class Airv2xCoBEVT(Airv2xWhere2com):
         nchw = heads.permute(0, 3, 1, 2)
         return {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A]}
 
-    def train_step(self, *a, **k):
-        raise NotImplementedError("Airv2xCoBEVT: the fused training step is not implemented in this round")
+    def _grad_buffers(self):
+        g = {}
+        for n, p in self.named_parameters():
+            if not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            g[n] = p.grad
+        return g
 
-    train_step_graphed = train_step
+    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, dropout="error"):
+        """forward (train-mode BatchNorm) + PointPillarLossMultiClass + backward of the whole CoBEVT path on the CUDA
+        kernels; parameter gradients land in p.grad, returns the device tensor [reg, cls, obj] (float64).
+        The reference applies nn.Dropout(fax_fusion.drop_out) in train mode (non-deterministic, no parity possible): the
+        kernels implement dropout = identity, so a yaml with drop_out > 0 needs the explicit dropout="off"."""
+        assert self.training, "train_step() needs model.train()"
+        if float(self.args["fax_fusion"].get("drop_out", 0.0)) > 0 and dropout != "off":
+            raise NotImplementedError("fax_fusion.drop_out > 0: pass dropout=\"off\" to train with dropout disabled")
+        dev = next(self.parameters()).device
+        layout = self._layout(data_dict, dev)
+        if "key_mask" not in layout:
+            L = self.max_cav_num
+            layout["key_mask"] = torch.tensor([[1] * n + [0] * (L - n) for n in layout["record_len"]], dtype=torch.int32,
+                                              device=dev)
+        lidar = self._lidar(data_dict, dev, layout)
+        labels = self.prepare_labels(label_dict, dev)
+        P = self._param_dict()
+        eng = self.engine
+        heads = eng.forward_train(P, lidar, layout)
+        loss3, dheads = eng.loss(heads, labels, cls_weight, reg_coe)
+        eng.backward_train(P, dheads, self._grad_buffers())
+        return loss3
+
+    def train_step_graphed(self, *a, **k):
+        raise NotImplementedError("Airv2xCoBEVT: CUDA-graph replay of the training step is not implemented")

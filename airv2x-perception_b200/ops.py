@@ -624,3 +624,16 @@ def window_attention_bwd(qkv, dout, bias_table, key_mask, B, L, heads, dim_head,
     call("a2x_window_attention_bwd", _ptr(qkv), _ptr(dout), _ptr(bias_table), _ptr(key_mask), c_int(B), c_int(L), c_int(H),
          c_int(W), c_int(heads), c_int(dim_head), c_int(window), c_int(int(grid_mode)), c_f(dim_head ** -0.5), _ptr(dqkv),
          _ptr(dbias), stream_ptr())
+
+
+def agent_mean(x, B, L, out):
+    """x: dense [B*L, H, W, C] -> out dense [B, H, W, C]"""
+    call("a2x_agent_mean", _ptr(x), c_int(B), c_int(L), c_ll(x.shape[1] * x.shape[2] * x.shape[3]), _ptr(out), stream_ptr())
+    return out
+
+
+def agent_broadcast(src, B, L, scale, dst):
+    """dst [B*L, H, W, C] = scale * src [B, H, W, C] repeated over the L agents"""
+    call("a2x_agent_broadcast", _ptr(src), c_int(B), c_int(L), c_ll(src.shape[1] * src.shape[2] * src.shape[3]), c_f(scale),
+         _ptr(dst), stream_ptr())
+    return dst

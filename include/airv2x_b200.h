@@ -175,6 +175,9 @@ int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const in
  * accumulators (caller zeroes). gelu_fwd / gelu_bwd: erf GELU of a pre-activation kept in fp32. window_attention_bwd:
  * dqkv [B*L][H][W][3*heads*dim_head] from dout (gradient of the attention output), everything recomputed from qkv;
  * dbias_table accumulated with atomics (caller zeroes). */
+/* out[b][p] = mean over the L agents of x[b][l][p] (images of img_elems floats) and its adjoint dst[b][l] = scale*src[b] */
+int a2x_agent_mean(const float* x, int B, int L, long long img_elems, float* out, a2x_stream_t stream);
+int a2x_agent_broadcast(const float* src, int B, int L, long long img_elems, float scale, float* dst, a2x_stream_t stream);
 int a2x_layernorm_bwd(const float* x, int x_cs, const float* dy, int dy_cs, long long rows, int C, const float* gamma,
                       float eps, float* dx_accum, int dx_cs, double* dgamma, double* dbeta, a2x_stream_t stream);
 int a2x_gelu_fwd(const float* x, long long n, const a2x_output* y, a2x_stream_t stream);

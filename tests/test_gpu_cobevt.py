@@ -262,3 +262,45 @@ def test_window_attention_backward(ops, case, grid_mode):
                              heads, dh, w, grid_mode, dqkv, dbias)
     assert rel(dqkv.cpu().double(), qkv.grad) < 2e-5
     assert rel(dbias.cpu().double(), table.grad) < 2e-5
+
+
+def test_train_step_matches_oracle_autograd():
+    """CoBEVT training step (train-mode BatchNorm, dropout off): loss and every parameter gradient against torch autograd
+    through the oracle (itself pinned bit-exact to the real reference in eval mode). Gradients of the fusion network and
+    heads are tight; encoder gradients pass ReLU / max gates (see tests/test_gpu_model.py) -> norm-wise bounds."""
+    import json
+
+    import a2x_import
+    import w2c_common as C
+    from oracle import w2c_oracle as O
+
+    M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+    cfg, gold = CC.load_small()
+    args = json.loads(json.dumps(cfg["model_args"]))
+    args["fax_fusion"]["drop_out"] = 0.0
+    model = M.Airv2xCoBEVT(args)
+    sd = CC.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    dd = CC.golden_scene(cfg, gold)
+    H, W = gold["eval_psm"].shape[2:]
+    labels = O.make_labels(5, 1, H, W, args["anchor_number"])
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])
+    # oracle: train-mode forward + the reference's loss + autograd on the CPU
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    torch.set_num_threads(8)
+    out, _ = CO.cobevt_forward(p, args, dd, training=True)
+    loss = O.point_pillar_loss_multiclass(out, labels, args["num_class"], cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])[0]
+    loss.backward()
+    assert abs(float(loss3.sum()) - float(loss)) < 1e-3 * abs(float(loss))
+    errs = {}
+    for n, q in model.named_parameters():
+        ref = p[n].grad
+        if ref is None:
+            continue
+        errs[n] = float((q.grad.cpu() - ref).norm() / (ref.norm() + 1e-30))
+    fusion = {n: e for n, e in errs.items() if n.startswith("fusion_net") or "head" in n}
+    assert len(fusion) > 60 and max(fusion.values()) < 2e-2, sorted(fusion.items(), key=lambda kv: -kv[1])[:5]
+    assert float(np.median(list(fusion.values()))) < 2e-3
+    assert max(errs.values()) < 0.15 and float(np.median(list(errs.values()))) < 0.05, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
