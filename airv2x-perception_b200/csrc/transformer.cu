@@ -615,19 +615,23 @@ struct WinAttBwdParams {
 
 template <int DH>
 __global__ void __launch_bounds__(128) window_attention_bwd_kernel(const WinAttBwdParams p) {
+    // The n x n probability matrix of the (window, head) lives in shared memory (n <= 128: 64 KB), so every score is
+    // computed once:   P = softmax(S)            (thread = query i, one sweep over the keys)
+    //                  dV_j = sum_i P_ij dO_i    (thread = key j)
+    //                  O_i = sum_j P_ij V_j, D_i = dO_i . O_i,  dS_ij = P_ij (dO_i . V_j - D_i) overwrites P_ij, dQ_i
+    //                  dK_j = sum_i dS_ij Q_i, bias gradient      (thread = key j)
     extern __shared__ float sm[];
     const int ww = p.w * p.w;
     const int n = p.L * ww;
-    constexpr int RS = DH + 1;      // row stride: conflict-free column walks
+    constexpr int RS = DH + 4;      // float4-aligned rows, staggered banks
     float* sQ = sm;                 // [n][RS]  q * scale
     float* sK = sQ + n * RS;
     float* sV = sK + n * RS;
     float* sO = sV + n * RS;        // dO
-    float* sM = sO + n * RS;        // [n] row max
-    float* sL = sM + n;             // [n] 1 / row sum
-    float* sD = sL + n;             // [n] D_i
+    float* sP = sO + n * RS;        // [n][n + 1]
+    const int PS = n + 1;
     const int nb = (2 * p.L - 1) * (2 * p.w - 1) * (2 * p.w - 1);
-    float* sB = sD + n;             // [nb] bias of this head
+    float* sB = sP + n * PS;        // [nb] bias of this head
     float* sdB = sB + nb;           // [nb] bias gradient of this CTA
     int* sTok = reinterpret_cast<int*>(sdB + nb);
     const int D = p.heads * DH;
@@ -650,108 +654,141 @@ __global__ void __launch_bounds__(128) window_attention_bwd_kernel(const WinAttB
         sdB[i] = 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n * DH; i += blockDim.x) {
-        const int t = i / DH, c = i - t * DH;
+    for (int i = threadIdx.x; i < n * (DH / 4); i += blockDim.x) {
+        const int t = i / (DH / 4), c = (i - t * (DH / 4)) * 4;
         const float* row = p.qkv + (long long)sTok[t] * (3 * D) + head * DH + c;
-        sQ[t * RS + c] = row[0] * p.scale;
-        sK[t * RS + c] = row[D];
-        sV[t * RS + c] = row[2 * D];
-        sO[t * RS + c] = p.dout[(long long)sTok[t] * D + head * DH + c];
+        float4 q4 = *reinterpret_cast<const float4*>(row);
+        q4.x *= p.scale; q4.y *= p.scale; q4.z *= p.scale; q4.w *= p.scale;
+        *reinterpret_cast<float4*>(sQ + t * RS + c) = q4;
+        *reinterpret_cast<float4*>(sK + t * RS + c) = *reinterpret_cast<const float4*>(row + D);
+        *reinterpret_cast<float4*>(sV + t * RS + c) = *reinterpret_cast<const float4*>(row + 2 * D);
+        *reinterpret_cast<float4*>(sO + t * RS + c) =
+            *reinterpret_cast<const float4*>(p.dout + (long long)sTok[t] * D + head * DH + c);
     }
     __syncthreads();
     const int s2 = 2 * p.w - 1;
     auto valid_key = [&](int lj) { return p.key_mask == nullptr || p.key_mask[b * p.L + lj] != 0; };
-    auto bias_idx = [&](int ti, int tj) {
-        const int li = ti / ww, ri = ti - li * ww, lj = tj / ww, rj = tj - lj * ww;
-        return ((li - lj + p.L - 1) * s2 + (ri / p.w - rj / p.w + p.w - 1)) * s2 + (ri % p.w - rj % p.w + p.w - 1);
-    };
-    // ---- phase 1
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        float q[DH], o[DH], dq[DH];
+    auto ld = [&](const float* base, int row, float (&v)[DH]) {
 #pragma unroll
-        for (int c = 0; c < DH; ++c) {
-            q[c] = sQ[i * RS + c];
-            o[c] = sO[i * RS + c];
-            dq[c] = 0.f;
+        for (int c = 0; c < DH; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(base + row * RS + c);
+            v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
         }
-        float m = -INFINITY, l = 0.f;
-        for (int j = 0; j < n; ++j) {
-            if (!valid_key(j / ww)) continue;
-            float s = sB[bias_idx(i, j)];
+    };
+    // ---- P = softmax(S), row i per thread
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float q[DH];
+        ld(sQ, i, q);
+        const int li = i / ww, ri = i - li * ww, i1 = ri / p.w, i2 = ri - i1 * p.w;
+        float m = -INFINITY;
+        for (int lj = 0; lj < p.L; ++lj) {
+            const bool ok = valid_key(lj);
+            for (int r = 0; r < ww; ++r) {
+                const int j = lj * ww + r;
+                float sc = -INFINITY;
+                if (ok) {
+                    const int k1 = r / p.w, k2 = r - k1 * p.w;
+                    float kk[DH];
+                    ld(sK, j, kk);
+                    float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < DH; ++c) s = fmaf(q[c], sK[j * RS + c], s);
-            const float mn = fmaxf(m, s);
-            l = l * expf(m - mn) + expf(s - mn);
-            m = mn;
+                    for (int c = 0; c < DH; c += 2) {
+                        d0 = fmaf(q[c], kk[c], d0);
+                        d1 = fmaf(q[c + 1], kk[c + 1], d1);
+                    }
+                    sc = d0 + d1 + sB[((li - lj + p.L - 1) * s2 + (i1 - k1 + p.w - 1)) * s2 + (i2 - k2 + p.w - 1)];
+                    m = fmaxf(m, sc);
+                }
+                sP[i * PS + j] = sc;
+            }
+        }
+        float l = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const float e = expf(sP[i * PS + j] - m);  // exp(-inf) = 0 for masked keys
+            sP[i * PS + j] = e;
+            l += e;
         }
         const float inv = 1.f / l;
-        float Dv = 0.f;
-        for (int j = 0; j < n; ++j) {
-            if (!valid_key(j / ww)) continue;
-            float s = sB[bias_idx(i, j)], dp = 0.f;
-#pragma unroll
-            for (int c = 0; c < DH; ++c) {
-                s = fmaf(q[c], sK[j * RS + c], s);
-                dp = fmaf(o[c], sV[j * RS + c], dp);
-            }
-            Dv = fmaf(expf(s - m) * inv, dp, Dv);
-        }
-        for (int j = 0; j < n; ++j) {
-            if (!valid_key(j / ww)) continue;
-            float s = sB[bias_idx(i, j)], dp = 0.f;
-#pragma unroll
-            for (int c = 0; c < DH; ++c) {
-                s = fmaf(q[c], sK[j * RS + c], s);
-                dp = fmaf(o[c], sV[j * RS + c], dp);
-            }
-            const float ds = expf(s - m) * inv * (dp - Dv);
-#pragma unroll
-            for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, sK[j * RS + c], dq[c]);
-        }
-        sM[i] = m;
-        sL[i] = inv;
-        sD[i] = Dv;
-        float* out = p.dqkv + (long long)sTok[i] * (3 * D) + head * DH;
-#pragma unroll
-        for (int c = 0; c < DH; ++c) out[c] = dq[c] * p.scale;  // s = (q * scale) . k
+        for (int j = 0; j < n; ++j) sP[i * PS + j] *= inv;
     }
     __syncthreads();
-    // ---- phase 2
+    // ---- dV_j = sum_i P_ij dO_i, column j per thread
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        float k[DH], v[DH], dk[DH], dv[DH];
+        float dv[DH];
 #pragma unroll
-        for (int c = 0; c < DH; ++c) {
-            k[c] = sK[j * RS + c];
-            v[c] = sV[j * RS + c];
-            dk[c] = 0.f;
-            dv[c] = 0.f;
+        for (int c = 0; c < DH; ++c) dv[c] = 0.f;
+        for (int i = 0; i < n; ++i) {
+            const float pij = sP[i * PS + j];
+            float o[DH];
+            ld(sO, i, o);
+#pragma unroll
+            for (int c = 0; c < DH; ++c) dv[c] = fmaf(pij, o[c], dv[c]);
         }
-        const bool ok = valid_key(j / ww);
-        if (ok) {
-            for (int i = 0; i < n; ++i) {
-                const int bi = bias_idx(i, j);
-                float s = sB[bi], dp = 0.f;
+        float* out = p.dqkv + (long long)sTok[j] * (3 * D) + 2 * D + head * DH;
 #pragma unroll
-                for (int c = 0; c < DH; ++c) {
-                    s = fmaf(sQ[i * RS + c], k[c], s);
-                    dp = fmaf(sO[i * RS + c], v[c], dp);
-                }
-                const float pij = expf(s - sM[i]) * sL[i];
-                const float ds = pij * (dp - sD[i]);
-                atomicAdd(&sdB[bi], ds);
+        for (int c = 0; c < DH; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
+    }
+    __syncthreads();
+    // ---- D_i = dO_i . O_i ; dS_ij = P_ij (dO_i . V_j - D_i) -> sP ; dQ_i
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float o[DH], acc[DH];
+        ld(sO, i, o);
 #pragma unroll
-                for (int c = 0; c < DH; ++c) {
-                    dv[c] = fmaf(pij, sO[i * RS + c], dv[c]);
-                    dk[c] = fmaf(ds, sQ[i * RS + c], dk[c]);  // sQ already carries the scale
-                }
+        for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const float pij = sP[i * PS + j];
+            float v[DH];
+            ld(sV, j, v);
+#pragma unroll
+            for (int c = 0; c < DH; ++c) acc[c] = fmaf(pij, v[c], acc[c]);
+        }
+        float Dv = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) Dv = fmaf(o[c], acc[c], Dv);
+#pragma unroll
+        for (int c = 0; c < DH; ++c) acc[c] = 0.f;  // now dQ
+        for (int j = 0; j < n; ++j) {
+            float v[DH];
+            ld(sV, j, v);
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; c += 2) {
+                d0 = fmaf(o[c], v[c], d0);
+                d1 = fmaf(o[c + 1], v[c + 1], d1);
+            }
+            const float ds = sP[i * PS + j] * (d0 + d1 - Dv);
+            sP[i * PS + j] = ds;
+            ld(sK, j, v);
+#pragma unroll
+            for (int c = 0; c < DH; ++c) acc[c] = fmaf(ds, v[c], acc[c]);
+        }
+        float* out = p.dqkv + (long long)sTok[i] * (3 * D) + head * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4)
+            *reinterpret_cast<float4*>(out + c) =
+                make_float4(acc[c] * p.scale, acc[c + 1] * p.scale, acc[c + 2] * p.scale, acc[c + 3] * p.scale);
+    }
+    __syncthreads();
+    // ---- dK_j = sum_i dS_ij Q_i (sQ carries the scale) ; bias gradient
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float dk[DH];
+#pragma unroll
+        for (int c = 0; c < DH; ++c) dk[c] = 0.f;
+        const int lj = j / ww, rj = j - lj * ww, k1 = rj / p.w, k2 = rj - k1 * p.w;
+        for (int i = 0; i < n; ++i) {
+            const float ds = sP[i * PS + j];
+            float q[DH];
+            ld(sQ, i, q);
+#pragma unroll
+            for (int c = 0; c < DH; ++c) dk[c] = fmaf(ds, q[c], dk[c]);
+            if (ds != 0.f) {
+                const int li = i / ww, ri = i - li * ww;
+                atomicAdd(&sdB[((li - lj + p.L - 1) * s2 + (ri / p.w - k1 + p.w - 1)) * s2 + (ri % p.w - k2 + p.w - 1)], ds);
             }
         }
-        float* out = p.dqkv + (long long)sTok[j] * (3 * D) + head * DH;
+        float* out = p.dqkv + (long long)sTok[j] * (3 * D) + D + head * DH;
 #pragma unroll
-        for (int c = 0; c < DH; ++c) {
-            out[D + c] = dk[c];
-            out[2 * D + c] = dv[c];
-        }
+        for (int c = 0; c < DH; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nb; i += blockDim.x)
@@ -811,7 +848,7 @@ int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* b
     p.B = B; p.L = L; p.H = H; p.W = W; p.heads = heads; p.w = window; p.grid_mode = grid_mode; p.scale = scale;
     const int n = L * window * window;
     const int nb = (2 * L - 1) * (2 * window - 1) * (2 * window - 1);
-    const size_t smem = (size_t)(4 * n * (dim_head + 1) + 3 * n + 2 * nb + n) * sizeof(float);
+    const size_t smem = (size_t)(4 * n * (dim_head + 4) + n * (n + 1) + 2 * nb + n) * sizeof(float);
     A2X_REQUIRE(smem <= 200 * 1024, "window_attention_bwd: window of %d tokens does not fit shared memory", n);
     const long long grid = (long long)B * (H / window) * (W / window) * heads;
     cudaStream_t st = (cudaStream_t)stream;

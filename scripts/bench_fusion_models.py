@@ -59,6 +59,25 @@ def main():
         model(dd)
         torch.cuda.synchronize()
         prof, libmod.PROFILE = libmod.PROFILE, None
+    train = None
+    if which == "cobevt" and "--train" in sys.argv:
+        lab_np = bench.synth_labels(3, 100, 352, cfg["model_args"]["anchor_number"])
+        lab = {k: torch.from_numpy(v).cuda() for k, v in lab_np.items()}
+        model.train()
+        for _ in range(2):
+            model.train_step(dd, lab, 1.0, 2.0, dropout="off")
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            loss3 = model.train_step(dd, lab, 1.0, 2.0, dropout="off")
+        e1.record()
+        torch.cuda.synchronize()
+        train = {"ms_per_step": e0.elapsed_time(e1) / 5, "loss": float(loss3.sum()),
+                 "note": "fwd (train-mode BN) + PointPillarLossMultiClass + bwd, dropout off, eager launches"}
+        libmod.PROFILE = []
+        model.train_step(dd, lab, 1.0, 2.0, dropout="off")
+        torch.cuda.synchronize()
+        prof, libmod.PROFILE = libmod.PROFILE, None
     groups = {}
     for name, _, a, b in prof:
         g = groups.setdefault(name, [0.0, 0])
@@ -66,7 +85,7 @@ def main():
         g[1] += 1
     top = sorted(((k, round(v[0], 3), v[1]) for k, v in groups.items()), key=lambda x: -x[1])[:10]
     print(json.dumps({"metric": "scenes/sec (eval fwd) %s %d-agent 60k-pt" % (which, len(types)), "value": 1000.0 / ms,
-                      "ms_per_scene": ms, "agents": types, "top_calls_ms": top}))
+                      "ms_per_scene": ms, "agents": types, "train_step": train, "top_calls_ms": top}))
 
 
 if __name__ == "__main__":
