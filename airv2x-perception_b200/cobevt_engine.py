@@ -385,12 +385,33 @@ class CoBEVTEngine(W2CEngine):
                 ops.conv_dgrad(dqs, W[pre + ".fn.to_qkv.weight"], 1, 1, d_ln)
             ln_bwd(sl["xin"], d_ln, pre + ".norm", dX)
         # ---- regroup^T: gradients of the valid agents' shrunk maps (padded slots are dropped)
-        y2, y1, cat = S["y2"], S["y1"], S["cat"]
-        d_y2 = self._buf("bwd.d_y2", y2.shape)
+        d_y2 = self._buf("bwd.d_y2", S["y2"].shape)
         pos = 0
         for b, n in enumerate(layout["record_len"]):
             d_y2[pos:pos + n].copy_(dX[b * self.L:b * self.L + n])
             pos += n
+        self._encoder_backward(P, S, d_y2, grads, unpack)
+        for lo in range(0, len(unpack), 128):
+            ops.unpack_wgrads_batched(self._job_table("unpack%d" % lo, unpack[lo:lo + 128]))
+        return grads
+
+
+    # ------------------------------------------------------------------ shared encoder backward
+    def _encoder_backward(self, P, S, d_y2, grads, unpack):
+        """d_y2: gradient w.r.t. the shrunk maps [N, h, w, C] -> shrink header, deblocks, blocks, PillarVFE. Appends the
+        weight-gradient re-layout jobs to `unpack` (flushed by the caller)."""
+        W, rec = S["W"], S["rec"]
+        y2, y1, cat = S["y2"], S["y1"], S["cat"]
+
+        def zero_f32(name, n):
+            return self._zeroed(name, n, torch.float32)
+
+        def col_sums(t, C, outs):
+            sums = self._zeroed("bias.sums", 2 * C, torch.float64)
+            ops.channel_stats(t, sums)
+            for out, c0 in outs:
+                unpack.append(ops.sums_unpack_job(sums, out, c0))
+
         # ---- shrink header
         g2 = self._act("bwd.g2", y2.shape)
         ops.relu_bwd(d_y2, y2, g2)  # y2 is a plain fp32 tensor here
@@ -458,9 +479,6 @@ class CoBEVTEngine(W2CEngine):
             ops.pfn_bwd(r["vox"], r["num"], r["coords"], r["geom"], P[pre + ".linear.weight"], r["scale"], r["shift"],
                         r["mean"], r["invstd"], r["amap"], d_canvas, r["amax"], r["moments"], r["rows"], acc,
                         grads[pre + ".linear.weight"], grads[pre + ".norm.weight"], grads[pre + ".norm.bias"], seg=r["seg"])
-        for lo in range(0, len(unpack), 128):
-            ops.unpack_wgrads_batched(self._job_table("unpack%d" % lo, unpack[lo:lo + 128]))
-        return grads
 
     def forward(self, P, lidar, layout, training, k_list=None):
         if training:

@@ -795,6 +795,120 @@ __global__ void __launch_bounds__(128) window_attention_bwd_kernel(const WinAttB
         if (sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sdB[i]);
 }
 
+// Small-window backward (n = L*w*w <= 16 tokens, 128 % n == 0): thread = (window g, query), like the forward small kernel.
+// The query's probability row lives in registers; dK / dV of the window's keys accumulate in shared memory.
+template <int DH>
+__global__ void __launch_bounds__(128) window_attention_small_bwd_kernel(const WinAttBwdParams p, int num_windows) {
+    extern __shared__ float sm[];
+    const int ww = p.w * p.w;
+    const int n = p.L * ww;
+    constexpr int RS = DH + 4;
+    float* sK = sm;                   // [128][RS]
+    float* sV = sK + 128 * RS;
+    float* sdK = sV + 128 * RS;
+    float* sdV = sdK + 128 * RS;
+    const int nb = (2 * p.L - 1) * (2 * p.w - 1) * (2 * p.w - 1);
+    float* sB = sdV + 128 * RS;
+    float* sdB = sB + nb;
+    const int D = p.heads * DH;
+    const int X = p.H / p.w, Y = p.W / p.w;
+    const int G = 128 / n;
+    const int head = blockIdx.x % p.heads;
+    const int g = threadIdx.x / n, tq = threadIdx.x - g * n;
+    int win = (blockIdx.x / p.heads) * G + g;
+    const bool valid = win < num_windows;
+    if (!valid) win = num_windows - 1;
+    const int y = win % Y;
+    const int x = (win / Y) % X;
+    const int b = win / (Y * X);
+    const int l = tq / ww, r = tq - l * ww;
+    const int w1 = r / p.w, w2 = r - w1 * p.w;
+    const int ph = p.grid_mode ? w1 * X + x : x * p.w + w1;
+    const int pw = p.grid_mode ? w2 * Y + y : y * p.w + w2;
+    const long long tok = ((long long)(b * p.L + l) * p.H + ph) * p.W + pw;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        sB[i] = p.bias[i * p.heads + head];
+        sdB[i] = 0.f;
+    }
+    const float* row = p.qkv + tok * (3 * D) + head * DH;
+    float q[DH], go[DH];
+#pragma unroll
+    for (int c = 0; c < DH; c += 4) {
+        const float4 qv = *reinterpret_cast<const float4*>(row + c);
+        q[c] = qv.x * p.scale; q[c + 1] = qv.y * p.scale; q[c + 2] = qv.z * p.scale; q[c + 3] = qv.w * p.scale;
+        *reinterpret_cast<float4*>(sK + threadIdx.x * RS + c) = *reinterpret_cast<const float4*>(row + D + c);
+        *reinterpret_cast<float4*>(sV + threadIdx.x * RS + c) = *reinterpret_cast<const float4*>(row + 2 * D + c);
+        const float4 gv = *reinterpret_cast<const float4*>(p.dout + tok * D + head * DH + c);
+        go[c] = gv.x; go[c + 1] = gv.y; go[c + 2] = gv.z; go[c + 3] = gv.w;
+        *reinterpret_cast<float4*>(sdK + threadIdx.x * RS + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sdV + threadIdx.x * RS + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int s2 = 2 * p.w - 1;
+    float pr[16], dp[16];
+    float mx = -INFINITY;
+    for (int j = 0; j < n; ++j) {
+        pr[j] = -INFINITY;
+        dp[j] = 0.f;
+        const int lj = j / ww, rj = j - lj * ww;
+        if (p.key_mask != nullptr && p.key_mask[b * p.L + lj] == 0) continue;
+        const float* kr = sK + (g * n + j) * RS;
+        const float* vr = sV + (g * n + j) * RS;
+        float a = sB[((l - lj + p.L - 1) * s2 + (w1 - rj / p.w + p.w - 1)) * s2 + (w2 - rj % p.w + p.w - 1)], d2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+            a = fmaf(q[c], kr[c], a);
+            d2 = fmaf(go[c], vr[c], d2);
+        }
+        pr[j] = a;
+        dp[j] = d2;
+        mx = fmaxf(mx, a);
+    }
+    float lsum = 0.f;
+    for (int j = 0; j < n; ++j) {
+        pr[j] = expf(pr[j] - mx);
+        lsum += pr[j];
+    }
+    const float inv = 1.f / lsum;
+    float Dv = 0.f;
+    for (int j = 0; j < n; ++j) {
+        pr[j] *= inv;
+        Dv = fmaf(pr[j], dp[j], Dv);
+    }
+    float dq[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) dq[c] = 0.f;
+    if (valid) {
+        for (int j = 0; j < n; ++j) {
+            if (pr[j] == 0.f) continue;
+            const float ds = pr[j] * (dp[j] - Dv);
+            const int lj = j / ww, rj = j - lj * ww;
+            atomicAdd(&sdB[((l - lj + p.L - 1) * s2 + (w1 - rj / p.w + p.w - 1)) * s2 + (w2 - rj % p.w + p.w - 1)], ds);
+            const float* kr = sK + (g * n + j) * RS;
+            float* dk = sdK + (g * n + j) * RS;
+            float* dv = sdV + (g * n + j) * RS;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) {
+                dq[c] = fmaf(ds, kr[c], dq[c]);
+                atomicAdd(&dk[c], ds * q[c]);
+                atomicAdd(&dv[c], pr[j] * go[c]);
+            }
+        }
+    }
+    __syncthreads();
+    if (valid) {
+        float* out = p.dqkv + tok * (3 * D) + head * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+            *reinterpret_cast<float4*>(out + c) = make_float4(dq[c] * p.scale, dq[c + 1] * p.scale, dq[c + 2] * p.scale, dq[c + 3] * p.scale);
+            *reinterpret_cast<float4*>(out + D + c) = *reinterpret_cast<const float4*>(sdK + threadIdx.x * RS + c);
+            *reinterpret_cast<float4*>(out + 2 * D + c) = *reinterpret_cast<const float4*>(sdV + threadIdx.x * RS + c);
+        }
+    }
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sdB[i]);
+}
+
 }  // namespace a2x
 
 extern "C" {
@@ -848,6 +962,30 @@ int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* b
     p.B = B; p.L = L; p.H = H; p.W = W; p.heads = heads; p.w = window; p.grid_mode = grid_mode; p.scale = scale;
     const int n = L * window * window;
     const int nb = (2 * L - 1) * (2 * window - 1) * (2 * window - 1);
+    cudaStream_t st0 = (cudaStream_t)stream;
+    if (n <= 16 && 128 % n == 0) {  // small windows: 128 / n windows per CTA
+        const int num_windows = B * (H / window) * (W / window);
+        const int G = 128 / n;
+        const size_t sms = (size_t)(4 * 128 * (dim_head + 4) + 2 * nb) * sizeof(float);
+        const long long gs = (long long)((num_windows + G - 1) / G) * heads;
+#define A2X_WASB(DH)                                                                                            \
+    do {                                                                                                        \
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_small_bwd_kernel<DH>,                         \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));            \
+        a2x::window_attention_small_bwd_kernel<DH><<<(unsigned)gs, 128, sms, st0>>>(p, num_windows);            \
+    } while (0)
+        if (dim_head == 16) A2X_WASB(16);
+        else if (dim_head == 32) A2X_WASB(32);
+        else if (dim_head == 64) A2X_WASB(64);
+        else {
+            a2x::set_error("window_attention_bwd: dim_head %d not in {16, 32, 64}", dim_head);
+            return 1;
+        }
+#undef A2X_WASB
+        A2X_LAUNCHED();
+        A2X_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = (size_t)(4 * n * (dim_head + 4) + n * (n + 1) + 2 * nb + n) * sizeof(float);
     A2X_REQUIRE(smem <= 200 * 1024, "window_attention_bwd: window of %d tokens does not fit shared memory", n);
     const long long grid = (long long)B * (H / window) * (W / window) * heads;

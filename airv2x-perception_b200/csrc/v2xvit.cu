@@ -353,3 +353,390 @@ int a2x_split_attn_fuse(const float* w0, const float* w1, const float* w2, int n
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Backward kernels of the V2X-ViT fusion (training step): autograd of HGTCavAttention (through the folded projections),
+// SplitAttn and RTE. Same re-association as the forward; everything is recomputed from the saved projections.
+namespace a2x {
+
+constexpr int HGT_MAX_AGENTS = 16;
+
+// one thread per (pixel, head). dqkv (zero-filled by the caller) has the layout of qkv: q | k'(0) | k'(1) | v'(0) | v'(1);
+// the thread owns its (pixel, head) slices of every agent, so the k' / v' gradients accumulate with plain read-modify-write.
+template <int DH>
+__global__ void __launch_bounds__(128) hgt_attention_bwd_kernel(const float* __restrict__ qkv, const int* __restrict__ types,
+                                                                const float* __restrict__ mask,
+                                                                const float* __restrict__ dout, int n, long long pix,
+                                                                int heads, float scale, float* __restrict__ dqkv) {
+    const int C = heads * DH;
+    const long long total = pix * heads;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(t % heads);
+        const long long p = t / heads;
+        for (int i = 0; i < n; ++i) {
+            const int ti = types[i];
+            float q[DH], go[DH], dq[DH];
+            const float* qrow = qkv + ((long long)i * pix + p) * 5 * C + m * DH;
+            const float* grow = dout + ((long long)i * pix + p) * C + m * DH;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) {
+                q[c] = qrow[c] * scale;
+                go[c] = grow[c];
+                dq[c] = 0.f;
+            }
+            float s[HGT_MAX_AGENTS], dp[HGT_MAX_AGENTS];
+            float mx = -INFINITY;
+            for (int j = 0; j < n; ++j) {
+                s[j] = -INFINITY;
+                dp[j] = 0.f;
+                if (mask[(long long)j * pix + p] == 0.f) continue;
+                const float* krow = qkv + ((long long)j * pix + p) * 5 * C + (1 + ti) * C + m * DH;
+                const float* vrow = krow + 2 * C;
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int c = 0; c < DH; ++c) {
+                    a = fmaf(q[c], krow[c], a);
+                    b = fmaf(go[c], vrow[c], b);
+                }
+                s[j] = a;
+                dp[j] = b;
+                mx = fmaxf(mx, a);
+            }
+            float l = 0.f;
+            for (int j = 0; j < n; ++j) {
+                s[j] = expf(s[j] - mx);
+                l += s[j];
+            }
+            const float inv = 1.f / l;
+            float Dv = 0.f;
+            for (int j = 0; j < n; ++j) {
+                s[j] *= inv;  // P_ij
+                Dv = fmaf(s[j], dp[j], Dv);
+            }
+            for (int j = 0; j < n; ++j) {
+                if (s[j] == 0.f) continue;
+                const float ds = s[j] * (dp[j] - Dv);
+                const long long base = ((long long)j * pix + p) * 5 * C + (1 + ti) * C + m * DH;
+                const float* krow = qkv + base;
+                float* dk = dqkv + base;
+                float* dv = dk + 2 * C;
+#pragma unroll
+                for (int c = 0; c < DH; ++c) {
+                    dq[c] = fmaf(ds, krow[c], dq[c]);
+                    dk[c] += ds * q[c];          // q carries the scale: s = (q * scale) . k'
+                    dv[c] += s[j] * go[c];
+                }
+            }
+            float* dqo = dqkv + ((long long)i * pix + p) * 5 * C + m * DH;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) dqo[c] = dq[c] * scale;
+        }
+    }
+}
+
+// Backward of hgt_fold: gradients of the fused projection (dwf [2][5C][C], dbf [2][5C]) -> typed q/k/v linears and the
+// relation tensors. Weights and biases are handled as one [C][C+1] extended matrix (last column = bias).
+struct HgtFoldBwdParams {
+    const float* dwf; const float* dbf;
+    const float* kw[2]; const float* kb[2]; const float* vw[2]; const float* vb[2];
+    const float* rel_att; const float* rel_msg;
+    float* dqw[2]; float* dqb[2]; float* dkw[2]; float* dkb[2]; float* dvw[2]; float* dvb[2];
+    float* drel_att; float* drel_msg;
+    int C, heads, dh;
+};
+
+__global__ void hgt_fold_bwd_kernel(const HgtFoldBwdParams p) {
+    const int C = p.C, dh = p.dh, E = C + 1;
+    auto dWf = [&](int tj, int row, int col) { return col < C ? p.dwf[((long long)tj * 5 * C + row) * C + col] : p.dbf[tj * 5 * C + row]; };
+    const long long n1 = (long long)2 * 3 * C * E;                 // typed linear gradients
+    const long long n2 = (long long)2 * 4 * p.heads * dh * dh;     // relation tensor gradients (att, msg)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n1 + n2; i += (long long)gridDim.x * blockDim.x) {
+        if (i < n1) {
+            const int col = (int)(i % E);
+            const int o = (int)((i / E) % C);
+            const int which = (int)((i / ((long long)E * C)) % 3);  // 0 q, 1 k, 2 v
+            const int tj = (int)(i / ((long long)E * C * 3));
+            const int h = o / dh, t = o - h * dh;
+            float val = 0.f;
+            if (which == 0) {
+                val = dWf(tj, o, col);
+            } else {
+                for (int ti = 0; ti < 2; ++ti) {
+                    const float* R = (which == 1 ? p.rel_att : p.rel_msg) + ((long long)(ti * 2 + tj) * p.heads + h) * dh * dh;
+                    const int row0 = (which == 1 ? 1 : 3) * C + ti * C + h * dh;
+                    for (int a = 0; a < dh; ++a) {
+                        const float r = which == 1 ? R[a * dh + t] : R[t * dh + a];  // k' = A k ; v' = M^T v
+                        val = fmaf(r, dWf(tj, row0 + a, col), val);
+                    }
+                }
+            }
+            float* W = which == 0 ? p.dqw[tj] : which == 1 ? p.dkw[tj] : p.dvw[tj];
+            float* Bv = which == 0 ? p.dqb[tj] : which == 1 ? p.dkb[tj] : p.dvb[tj];
+            if (col < C) W[(long long)o * C + col] = val;
+            else Bv[o] = val;
+        } else {
+            long long r = i - n1;
+            const int y = (int)(r % dh);
+            const int x = (int)((r / dh) % dh);
+            const int h = (int)((r / (dh * dh)) % p.heads);
+            const int e = (int)((r / ((long long)dh * dh * p.heads)) % 4);
+            const int is_msg = (int)(r / ((long long)dh * dh * p.heads * 4));
+            const int ti = e >> 1, tj = e & 1;
+            // att: dA[x][y] = sum_col dk'[(h,x)][col] * Wk_ext[(h,y)][col] ; msg: dM[x][y] = sum_col Wv_ext[(h,x)][col] * dv'[(h,y)][col]
+            const int grow = (is_msg ? 3 : 1) * C + ti * C + h * dh + (is_msg ? y : x);
+            const int wrow = h * dh + (is_msg ? x : y);
+            const float* Wm = is_msg ? p.vw[tj] : p.kw[tj];
+            const float* Bv = is_msg ? p.vb[tj] : p.kb[tj];
+            float s = 0.f;
+            for (int col = 0; col < C; ++col) s = fmaf(dWf(tj, grow, col), Wm[(long long)wrow * C + col], s);
+            s = fmaf(dWf(tj, grow, C), Bv[wrow], s);
+            (is_msg ? p.drel_msg : p.drel_att)[((long long)e * p.heads + h) * dh * dh + x * dh + y] = s;
+        }
+    }
+}
+
+// ---- split attention backward
+// dw[a][r][c] = sum_p dx[a][p][c] * w_r[a][p][c]
+__global__ void __launch_bounds__(256) split_bwd_reduce_kernel(const float* __restrict__ dx, const float* __restrict__ w0,
+                                                               const float* __restrict__ w1, const float* __restrict__ w2,
+                                                               long long pix, int C, int chunks, float* __restrict__ dw) {
+    const int q = C >> 2;
+    const int cq = threadIdx.x % q, prow = threadIdx.x / q, ppb = blockDim.x / q;
+    const int a = blockIdx.y;
+    const long long per = (pix + chunks - 1) / chunks;
+    const long long p0 = (long long)blockIdx.x * per, p1 = min(pix, p0 + per);
+    float4 s[3];
+    for (int r = 0; r < 3; ++r) s[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (prow < ppb) {
+        for (long long p = p0 + prow; p < p1; p += ppb) {
+            const long long o = ((long long)a * pix + p) * C + cq * 4;
+            const float4 d = *reinterpret_cast<const float4*>(dx + o);
+            const float4 x0 = *reinterpret_cast<const float4*>(w0 + o), x1 = *reinterpret_cast<const float4*>(w1 + o),
+                         x2 = *reinterpret_cast<const float4*>(w2 + o);
+            s[0].x += d.x * x0.x; s[0].y += d.y * x0.y; s[0].z += d.z * x0.z; s[0].w += d.w * x0.w;
+            s[1].x += d.x * x1.x; s[1].y += d.y * x1.y; s[1].z += d.z * x1.z; s[1].w += d.w * x1.w;
+            s[2].x += d.x * x2.x; s[2].y += d.y * x2.y; s[2].z += d.z * x2.z; s[2].w += d.w * x2.w;
+        }
+        for (int r = 0; r < 3; ++r) {
+            float* o = dw + ((long long)a * 3 + r) * C + cq * 4;
+            atomicAdd(o, s[r].x); atomicAdd(o + 1, s[r].y); atomicAdd(o + 2, s[r].z); atomicAdd(o + 3, s[r].w);
+        }
+    }
+}
+
+// per agent (one block): recompute the tiny MLP, back-propagate dw -> d_gap[a][:] (already divided by pix), and the
+// gradients of fc1 / bn1 / fc2 (atomics across agents; caller zeroes them)
+__global__ void split_bwd_mlp_kernel(const float* __restrict__ sums, float inv_pix, const float* __restrict__ fc1,
+                                     const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                     const float* __restrict__ fc2, const float* __restrict__ dw, int C,
+                                     float* __restrict__ d_gap, float* __restrict__ dfc1, float* __restrict__ dln_g,
+                                     float* __restrict__ dln_b, float* __restrict__ dfc2) {
+    extern __shared__ float sm[];
+    float* g = sm;            // [C]   gap
+    float* h1 = g + C;        // [C]   fc1 g
+    float* xh = h1 + C;       // [C]   xhat
+    float* act = xh + C;      // [C]   relu(LN)
+    float* da = act + C;      // [3C]  gradient w.r.t. fc2 output
+    float* dact = da + 3 * C; // [C]
+    float* dh1 = dact + C;    // [C]
+    float* red = dh1 + C;     // [4]
+    const int a = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) g[c] = sums[(long long)a * C + c] * inv_pix;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < C; ++k) s = fmaf(fc1[(long long)c * C + k], g[k], s);
+        h1[c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int c = 0; c < C; ++c) m += h1[c];
+        m /= C;
+        float v = 0.f;
+        for (int c = 0; c < C; ++c) v += (h1[c] - m) * (h1[c] - m);
+        red[0] = m;
+        red[1] = rsqrtf(v / C + 1e-5f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        xh[c] = (h1[c] - red[0]) * red[1];
+        act[c] = fmaxf(xh[c] * ln_g[c] + ln_b[c], 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s[3];
+        for (int r = 0; r < 3; ++r) {
+            float t = 0.f;
+            const float* w = fc2 + (long long)(r * C + c) * C;
+            for (int k = 0; k < C; ++k) t = fmaf(w[k], act[k], t);
+            s[r] = t;
+        }
+        const float mx = fmaxf(s[0], fmaxf(s[1], s[2]));
+        float e[3] = {expf(s[0] - mx), expf(s[1] - mx), expf(s[2] - mx)};
+        const float inv = 1.f / (e[0] + e[1] + e[2]);
+        float dot = 0.f;
+        for (int r = 0; r < 3; ++r) {
+            e[r] *= inv;
+            dot = fmaf(e[r], dw[((long long)a * 3 + r) * C + c], dot);
+        }
+        for (int r = 0; r < 3; ++r) da[r * C + c] = e[r] * (dw[((long long)a * 3 + r) * C + c] - dot);  // softmax over the radix
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+        float s = 0.f;
+        for (int rc = 0; rc < 3 * C; ++rc) s = fmaf(fc2[(long long)rc * C + k], da[rc], s);
+        dact[k] = (xh[k] * ln_g[k] + ln_b[k] > 0.f) ? s : 0.f;  // ReLU gate
+    }
+    __syncthreads();
+    for (long long i = threadIdx.x; i < (long long)3 * C * C; i += blockDim.x)
+        atomicAdd(&dfc2[i], da[i / C] * act[i % C]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&dln_g[c], dact[c] * xh[c]);
+        atomicAdd(&dln_b[c], dact[c]);
+    }
+    if (threadIdx.x == 0) {
+        float mg = 0.f, mgx = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float gg = dact[c] * ln_g[c];
+            mg += gg;
+            mgx += gg * xh[c];
+        }
+        red[2] = mg / C;
+        red[3] = mgx / C;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) dh1[c] = red[1] * (dact[c] * ln_g[c] - red[2] - xh[c] * red[3]);
+    __syncthreads();
+    for (long long i = threadIdx.x; i < (long long)C * C; i += blockDim.x) atomicAdd(&dfc1[i], dh1[i / C] * g[i % C]);
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(fc1[(long long)c * C + k], dh1[c], s);
+        d_gap[(long long)a * C + k] = s * inv_pix;
+    }
+}
+
+// d_win_r[a][p][c] = dx[a][p][c] * wts[a][r][c] + d_gap[a][c]   -> three split operands
+__global__ void __launch_bounds__(256) split_bwd_apply_kernel(const float* __restrict__ dx, const float* __restrict__ wts,
+                                                              const float* __restrict__ d_gap, long long pix, int C,
+                                                              SplitOut o0, SplitOut o1, SplitOut o2, long long total4) {
+    const int q = C >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % q) * 4;
+        const long long a = i / (q * pix);
+        const float4 d = reinterpret_cast<const float4*>(dx)[i];
+        const float4 gg = *reinterpret_cast<const float4*>(d_gap + a * C + c);
+        const float* wa = wts + a * 3 * C + c;
+        const float4 a0 = *reinterpret_cast<const float4*>(wa), a1 = *reinterpret_cast<const float4*>(wa + C),
+                     a2 = *reinterpret_cast<const float4*>(wa + 2 * C);
+        store_split4(o0, 4 * i, make_float4(d.x * a0.x + gg.x, d.y * a0.y + gg.y, d.z * a0.z + gg.z, d.w * a0.w + gg.w));
+        store_split4(o1, 4 * i, make_float4(d.x * a1.x + gg.x, d.y * a1.y + gg.y, d.z * a1.z + gg.z, d.w * a1.w + gg.w));
+        store_split4(o2, 4 * i, make_float4(d.x * a2.x + gg.x, d.y * a2.y + gg.y, d.z * a2.z + gg.z, d.w * a2.w + gg.w));
+    }
+}
+
+// ---- RTE backward: dvec[a][c] = sum_p dx[a][p][c] (computed by the caller with a2x_channel_stats per agent), then
+// dlin_w[c][k] += dvec[a][c] * emb[idx[a]][k], dlin_b[c] += dvec[a][c], demb[idx[a]][k] += sum_c W[c][k] dvec[a][c]
+__global__ void rte_bwd_kernel(const double* __restrict__ dvec_sums /* [n][2C], first C used */, const float* __restrict__ emb,
+                               const int* __restrict__ idx, const float* __restrict__ W, int C, float* __restrict__ dW,
+                               float* __restrict__ db, float* __restrict__ demb) {
+    const int a = blockIdx.x;
+    const double* dv = dvec_sums + (long long)a * 2 * C;
+    const float* e = emb + (long long)idx[a] * C;
+    for (long long i = threadIdx.x; i < (long long)C * C; i += blockDim.x) atomicAdd(&dW[i], (float)dv[i / C] * e[i % C]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&db[c], (float)dv[c]);
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(W[(long long)c * C + k], (float)dv[c], s);
+        atomicAdd(&demb[(long long)idx[a] * C + k], s);
+    }
+}
+
+}  // namespace a2x
+
+extern "C" {
+
+int a2x_hgt_attention_bwd(const float* qkv, const int* types_dev, const float* key_mask, const float* dout, int n_agents,
+                          long long pix, int heads, int dim_head, float scale, float* dqkv, a2x_stream_t stream) {
+    A2X_REQUIRE(qkv && types_dev && key_mask && dout && dqkv && n_agents > 0 && n_agents <= a2x::HGT_MAX_AGENTS && pix > 0,
+                "hgt_attention_bwd: bad args (at most 16 agents)");
+    cudaStream_t st = (cudaStream_t)stream;
+    A2X_CHECK_CUDA(cudaMemsetAsync(dqkv, 0, (size_t)n_agents * pix * 5 * heads * dim_head * sizeof(float), st));
+    long long b = (pix * heads + 127) / 128;
+    if (b > 148 * 16) b = 148 * 16;
+    if (dim_head == 32) a2x::hgt_attention_bwd_kernel<32><<<(int)b, 128, 0, st>>>(qkv, types_dev, key_mask, dout, n_agents, pix, heads, scale, dqkv);
+    else if (dim_head == 16) a2x::hgt_attention_bwd_kernel<16><<<(int)b, 128, 0, st>>>(qkv, types_dev, key_mask, dout, n_agents, pix, heads, scale, dqkv);
+    else {
+        a2x::set_error("hgt_attention_bwd: dim_head %d not in {16, 32}", dim_head);
+        return 1;
+    }
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_hgt_fold_bwd(const float* dw_fold, const float* db_fold, const float* const* kw, const float* const* kb,
+                     const float* const* vw, const float* const* vb, const float* relation_att, const float* relation_msg,
+                     int C, int heads, float* const* dqw, float* const* dqb, float* const* dkw, float* const* dkb,
+                     float* const* dvw, float* const* dvb, float* drelation_att, float* drelation_msg, a2x_stream_t stream) {
+    A2X_REQUIRE(dw_fold && db_fold && kw && kb && vw && vb && relation_att && relation_msg && dqw && dqb && dkw && dkb && dvw &&
+                    dvb && drelation_att && drelation_msg && C > 0 && heads > 0 && C % heads == 0,
+                "hgt_fold_bwd: bad args");
+    a2x::HgtFoldBwdParams p;
+    p.dwf = dw_fold; p.dbf = db_fold; p.rel_att = relation_att; p.rel_msg = relation_msg;
+    for (int t = 0; t < 2; ++t) {
+        p.kw[t] = kw[t]; p.kb[t] = kb[t]; p.vw[t] = vw[t]; p.vb[t] = vb[t];
+        p.dqw[t] = dqw[t]; p.dqb[t] = dqb[t]; p.dkw[t] = dkw[t]; p.dkb[t] = dkb[t]; p.dvw[t] = dvw[t]; p.dvb[t] = dvb[t];
+    }
+    p.drel_att = drelation_att; p.drel_msg = drelation_msg;
+    p.C = C; p.heads = heads; p.dh = C / heads;
+    const long long total = (long long)2 * 3 * C * (C + 1) + (long long)2 * 4 * heads * p.dh * p.dh;
+    a2x::hgt_fold_bwd_kernel<<<a2x::vx_grid(total), 256, 0, (cudaStream_t)stream>>>(p);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_split_attn_bwd(const float* dx, const float* w0, const float* w1, const float* w2, int n_agents, long long pix, int C,
+                       const float* fc1, const float* ln_gamma, const float* ln_beta, const float* fc2, const float* sums_saved,
+                       const float* weights_saved, float* dw_ws, float* dgap_ws, const a2x_output* d0, const a2x_output* d1,
+                       const a2x_output* d2, float* dfc1, float* dln_gamma, float* dln_beta, float* dfc2,
+                       a2x_stream_t stream) {
+    A2X_REQUIRE(dx && w0 && w1 && w2 && fc1 && ln_gamma && ln_beta && fc2 && sums_saved && weights_saved && dw_ws && dgap_ws &&
+                    d0 && d1 && d2 && dfc1 && dln_gamma && dln_beta && dfc2 && n_agents > 0 && pix > 0 && C % 4 == 0 &&
+                    256 % (C / 4) == 0,
+                "split_attn_bwd: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    A2X_CHECK_CUDA(cudaMemsetAsync(dw_ws, 0, (size_t)n_agents * 3 * C * sizeof(float), st));
+    const int chunks = 148 * 2 / n_agents > 0 ? 148 * 2 / n_agents : 1;
+    a2x::split_bwd_reduce_kernel<<<dim3(chunks, n_agents), 256, 0, st>>>(dx, w0, w1, w2, pix, C, chunks, dw_ws);
+    A2X_LAUNCHED();
+    a2x::split_bwd_mlp_kernel<<<n_agents, 256, (10 * C + 4) * sizeof(float), st>>>(sums_saved, 1.0f / (float)pix, fc1, ln_gamma,
+                                                                                 ln_beta, fc2, dw_ws, C, dgap_ws, dfc1,
+                                                                                 dln_gamma, dln_beta, dfc2);
+    A2X_LAUNCHED();
+    auto so = [](const a2x_output* o) {
+        a2x::SplitOut r;
+        r.hi = o->hi; r.b16 = (__nv_bfloat16*)o->b16; r.ps = o->b16_plane;
+        return r;
+    };
+    const long long total4 = (long long)n_agents * pix * (C / 4);
+    a2x::split_bwd_apply_kernel<<<a2x::vx_grid(total4), 256, 0, st>>>(dx, weights_saved, dgap_ws, pix, C, so(d0), so(d1), so(d2),
+                                                                     total4);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int a2x_rte_bwd(const double* dvec_sums, int n_agents, int C, const float* emb_table, const int* emb_idx_dev, const float* lin_w,
+                float* dlin_w, float* dlin_b, float* demb_table, a2x_stream_t stream) {
+    A2X_REQUIRE(dvec_sums && emb_table && emb_idx_dev && lin_w && dlin_w && dlin_b && demb_table && n_agents > 0 && C > 0,
+                "rte_bwd: bad args");
+    a2x::rte_bwd_kernel<<<n_agents, 256, 0, (cudaStream_t)stream>>>(dvec_sums, emb_table, emb_idx_dev, lin_w, C, dlin_w, dlin_b,
+                                                                   demb_table);
+    A2X_LAUNCHED();
+    A2X_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -637,3 +637,34 @@ def agent_broadcast(src, B, L, scale, dst):
     call("a2x_agent_broadcast", _ptr(src), c_int(B), c_int(L), c_ll(src.shape[1] * src.shape[2] * src.shape[3]), c_f(scale),
          _ptr(dst), stream_ptr())
     return dst
+
+
+# V2X-ViT fusion backward ----------------------------------------------------------------------------------------------
+def hgt_attention_bwd(qkv, types, key_mask, dout, heads, dim_head, dqkv):
+    n, h, w, _ = qkv.shape
+    assert qkv.is_contiguous() and dout.is_contiguous() and dqkv.is_contiguous() and key_mask.is_contiguous()
+    call("a2x_hgt_attention_bwd", _ptr(qkv), _ptr(types), _ptr(key_mask), _ptr(dout), c_int(n), c_ll(h * w), c_int(heads),
+         c_int(dim_head), c_f(dim_head ** -0.5), _ptr(dqkv), stream_ptr())
+    return dqkv
+
+
+def hgt_fold_bwd(dw_fold, db_fold, kw, kb, vw, vb, rel_att, rel_msg, heads, dqw, dqb, dkw, dkb, dvw, dvb, drel_att, drel_msg):
+    """dw_fold: [2, 5C, C]; db_fold: [2, 5C]; kw..vb and dqw..dvb: pairs of tensors (agent type 0, 1)"""
+    C = kw[0].shape[1]
+    call("a2x_hgt_fold_bwd", _ptr(dw_fold), _ptr(db_fold), _ptr2(*kw), _ptr2(*kb), _ptr2(*vw), _ptr2(*vb), _ptr(rel_att),
+         _ptr(rel_msg), c_int(C), c_int(heads), _ptr2(*dqw), _ptr2(*dqb), _ptr2(*dkw), _ptr2(*dkb), _ptr2(*dvw), _ptr2(*dvb),
+         _ptr(drel_att), _ptr(drel_msg), stream_ptr())
+
+
+def split_attn_bwd(dx, w0, w1, w2, fc1, ln_g, ln_b, fc2, sums_saved, weights_saved, dw_ws, dgap_ws, d0, d1, d2, dfc1, dln_g,
+                   dln_b, dfc2):
+    n, h, w, c = dx.shape
+    call("a2x_split_attn_bwd", _ptr(dx), _ptr(w0), _ptr(w1), _ptr(w2), c_int(n), c_ll(h * w), c_int(c), _ptr(fc1), _ptr(ln_g),
+         _ptr(ln_b), _ptr(fc2), _ptr(sums_saved), _ptr(weights_saved), _ptr(dw_ws), _ptr(dgap_ws), _op(d0), _op(d1), _op(d2),
+         _ptr(dfc1), _ptr(dln_g), _ptr(dln_b), _ptr(dfc2), stream_ptr())
+
+
+def rte_bwd(dvec_sums, emb_table, emb_idx, lin_w, dlin_w, dlin_b, demb):
+    n = emb_idx.numel()
+    call("a2x_rte_bwd", _ptr(dvec_sums), c_int(n), c_int(lin_w.shape[0]), _ptr(emb_table), _ptr(emb_idx), _ptr(lin_w),
+         _ptr(dlin_w), _ptr(dlin_b), _ptr(demb), stream_ptr())

@@ -206,6 +206,26 @@ int a2x_split_attn_fuse(const float* w0, const float* w1, const float* w2, int n
                         const float* fc1, const float* ln_gamma, const float* ln_beta, const float* fc2,
                         float* sums_ws, float* weights_ws, float* x_inout, a2x_stream_t stream);
 
+/* Backward of the V2X-ViT kernels. hgt_attention_bwd: dqkv [n][pix][5C] (zero-filled here) from dout [n][pix][C].
+ * hgt_fold_bwd: gradients of the fused projection (dw_fold [2][5C][C], db_fold [2][5C]) -> typed q/k/v linears (written)
+ * and relation_att / relation_msg (written). split_attn_bwd: d(win_r) as three split operands, gradients of fc1 / bn1 /
+ * fc2 accumulated with atomics (caller zeroes); sums_saved / weights_saved are the forward's [n][C] pooled sums and
+ * [n][3][C] mixing weights. rte_bwd: dvec_sums = per-agent column sums of dx ([n][2C] doubles from a2x_channel_stats);
+ * dlin_w / dlin_b / demb_table accumulated with atomics (caller zeroes). */
+int a2x_hgt_attention_bwd(const float* qkv, const int* types_dev, const float* key_mask, const float* dout, int n_agents,
+                          long long pix, int heads, int dim_head, float scale, float* dqkv, a2x_stream_t stream);
+int a2x_hgt_fold_bwd(const float* dw_fold, const float* db_fold, const float* const* kw, const float* const* kb,
+                     const float* const* vw, const float* const* vb, const float* relation_att, const float* relation_msg,
+                     int C, int heads, float* const* dqw, float* const* dqb, float* const* dkw, float* const* dkb,
+                     float* const* dvw, float* const* dvb, float* drelation_att, float* drelation_msg, a2x_stream_t stream);
+int a2x_split_attn_bwd(const float* dx, const float* w0, const float* w1, const float* w2, int n_agents, long long pix, int C,
+                       const float* fc1, const float* ln_gamma, const float* ln_beta, const float* fc2, const float* sums_saved,
+                       const float* weights_saved, float* dw_ws, float* dgap_ws, const a2x_output* d0, const a2x_output* d1,
+                       const a2x_output* d2, float* dfc1, float* dln_gamma, float* dln_beta, float* dfc2,
+                       a2x_stream_t stream);
+int a2x_rte_bwd(const double* dvec_sums, int n_agents, int C, const float* emb_table, const int* emb_idx_dev, const float* lin_w,
+                float* dlin_w, float* dlin_b, float* demb_table, a2x_stream_t stream);
+
 /* ---------------------------------------------------------------- ego-warp (affine bilinear resampling, NHWC)
  * warp_affine_simple = F.affine_grid + F.grid_sample(bilinear | nearest, zeros padding)
  * (common_modules/torch_transformation_utils.py:327-334); theta: [n][2][3] normalised matrices. */

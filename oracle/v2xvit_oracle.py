@@ -101,7 +101,7 @@ def hgt_attention(sd, pre, x, mask, prior, heads, dim_head, num_types=2):
     types = prior[:, :, 0, 0, 2].to(torch.int)
 
     def typed(name, t):
-        out = torch.empty(B, L, H, W, sd["%s.%s.0.weight" % (pre, name)].shape[0])
+        out = torch.empty(B, L, H, W, sd["%s.%s.0.weight" % (pre, name)].shape[0], dtype=t.dtype)
         for b in range(B):
             for i in range(L):
                 ty = int(types[b, i])

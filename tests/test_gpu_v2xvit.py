@@ -131,3 +131,103 @@ def test_eval_matches_reference_golden(small):
         assert out[k].shape == gold["eval_" + k].shape
         assert np.abs(out[k].cpu().numpy() - gold["eval_" + k]).max() < TOL, k
     assert out["comm_rate"] == int(gold["eval_comm_rate"])
+
+
+def test_hgt_backward_through_fold(ops):
+    """d(typed q/k/v linears, relation tensors, input) of HGTCavAttention (identity output projection) == torch autograd
+    on the oracle: hgt_attention_bwd -> fp32 dgrad/wgrad of the folded projection (torch) -> hgt_fold_bwd"""
+    g = torch.Generator().manual_seed(7)
+    n, H, W, C, heads, dh = 4, 4, 5, 256, 8, 32
+    pre = "f"
+    sd = {}
+    for name in ("q_linears", "k_linears", "v_linears"):
+        for t in range(2):
+            sd["%s.%s.%d.weight" % (pre, name, t)] = (torch.randn(C, C, generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
+            sd["%s.%s.%d.bias" % (pre, name, t)] = (torch.randn(C, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    for t in range(2):
+        sd["%s.a_linears.%d.weight" % (pre, t)] = torch.eye(C, dtype=torch.float64)
+        sd["%s.a_linears.%d.bias" % (pre, t)] = torch.zeros(C, dtype=torch.float64)
+    sd[pre + ".relation_att"] = (torch.randn(4, heads, dh, dh, generator=g, dtype=torch.float64) * 0.2).requires_grad_(True)
+    sd[pre + ".relation_msg"] = (torch.randn(4, heads, dh, dh, generator=g, dtype=torch.float64) * 0.2).requires_grad_(True)
+    x = torch.randn(1, n, H, W, C, generator=g, dtype=torch.float64).requires_grad_(True)
+    types = [0, 1, 1, 0]
+    prior = torch.zeros(1, n, H, W, 3, dtype=torch.float64)
+    prior[0, :, :, :, 2] = torch.tensor(types, dtype=torch.float64)[:, None, None]
+    mask = (torch.rand(1, H, W, 1, n, generator=g) > 0.3).double()
+    mask[..., 0] = 1.0
+    dout = torch.randn(n, H, W, C, generator=g, dtype=torch.float64)
+    VO.hgt_attention(sd, pre, x, mask, prior, heads, dh)[0].backward(dout)
+    # CUDA path
+    f32 = lambda t: t.detach().float().cuda()
+    pair = lambda nme, s: (f32(sd["%s.%s.0.%s" % (pre, nme, s)]), f32(sd["%s.%s.1.%s" % (pre, nme, s)]))
+    wf, bf = torch.empty(2, 5 * C, C, device="cuda"), torch.empty(2, 5 * C, device="cuda")
+    ops.hgt_fold(pair("q_linears", "weight"), pair("q_linears", "bias"), pair("k_linears", "weight"), pair("k_linears", "bias"),
+                 pair("v_linears", "weight"), pair("v_linears", "bias"), f32(sd[pre + ".relation_att"]), f32(sd[pre + ".relation_msg"]),
+                 heads, wf, bf)
+    xc = f32(x)[0]
+    qkv = torch.stack([F.linear(xc[a], wf[types[a]], bf[types[a]]) for a in range(n)])
+    km = mask[0, :, :, 0, :].permute(2, 0, 1).contiguous().float().cuda()
+    tdev = torch.tensor(types, dtype=torch.int32).cuda()
+    dqkv = torch.empty_like(qkv)
+    ops.hgt_attention_bwd(qkv, tdev, km, dout.float().cuda(), heads, dh, dqkv)
+    dwf, dbf, dx = torch.zeros_like(wf), torch.zeros_like(bf), torch.zeros(n, H, W, C, device="cuda")
+    for a in range(n):                                     # the projection's own backward: plain fp32 torch here
+        g2 = dqkv[a].reshape(-1, 5 * C)
+        dwf[types[a]] += g2.t() @ xc[a].reshape(-1, C)
+        dbf[types[a]] += g2.sum(0)
+        dx[a] = (g2 @ wf[types[a]]).reshape(H, W, C)
+    outs = {k: [torch.empty(C, C, device="cuda") for _ in range(2)] for k in ("q", "k", "v")}
+    outb = {k: [torch.empty(C, device="cuda") for _ in range(2)] for k in ("q", "k", "v")}
+    dA, dM = torch.empty(4, heads, dh, dh, device="cuda"), torch.empty(4, heads, dh, dh, device="cuda")
+    ops.hgt_fold_bwd(dwf, dbf, pair("k_linears", "weight"), pair("k_linears", "bias"), pair("v_linears", "weight"),
+                     pair("v_linears", "bias"), f32(sd[pre + ".relation_att"]), f32(sd[pre + ".relation_msg"]), heads,
+                     outs["q"], outb["q"], outs["k"], outb["k"], outs["v"], outb["v"], dA, dM)
+    assert rel(dx.cpu().double(), x.grad[0]) < 5e-5
+    assert rel(dA.cpu().double(), sd[pre + ".relation_att"].grad) < 5e-5
+    assert rel(dM.cpu().double(), sd[pre + ".relation_msg"].grad) < 5e-5
+    for k, nme in (("q", "q_linears"), ("k", "k_linears"), ("v", "v_linears")):
+        for t in range(2):
+            assert rel(outs[k][t].cpu().double(), sd["%s.%s.%d.weight" % (pre, nme, t)].grad) < 5e-5, (k, t)
+            assert rel(outb[k][t].cpu().double(), sd["%s.%s.%d.bias" % (pre, nme, t)].grad) < 5e-5, (k, t)
+
+
+def test_split_attn_and_rte_backward(ops):
+    g = torch.Generator().manual_seed(8)
+    n, H, W, C = 3, 6, 8, 256
+    wins = [torch.randn(1, n, H, W, C, generator=g, dtype=torch.float64).requires_grad_(True) for _ in range(3)]
+    sd = {"s.fc1.weight": (torch.randn(C, C, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True),
+          "s.bn1.weight": (torch.rand(C, generator=g, dtype=torch.float64) + 0.5).requires_grad_(True),
+          "s.bn1.bias": (torch.randn(C, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True),
+          "s.fc2.weight": (torch.randn(3 * C, C, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)}
+    dx = torch.randn(n, H, W, C, generator=g, dtype=torch.float64)
+    VO.split_attn(sd, "s", wins)[0].backward(dx)
+    f32 = lambda t: t.detach().float().cuda().contiguous()
+    w = [f32(t[0]) for t in wins]
+    x = torch.zeros(n, H, W, C, device="cuda")
+    sums, wts = torch.empty(n, C, device="cuda"), torch.empty(n, 3, C, device="cuda")
+    ops.split_attn_fuse(w[0], w[1], w[2], f32(sd["s.fc1.weight"]), f32(sd["s.bn1.weight"]), f32(sd["s.bn1.bias"]),
+                        f32(sd["s.fc2.weight"]), sums, wts, x)              # forward leaves the pooled sums / weights
+    d = [ops.Act.empty((n, H, W, C), "cuda", True) for _ in range(3)]
+    dfc1, dg, db, dfc2 = (torch.zeros(C, C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"),
+                          torch.zeros(3 * C, C, device="cuda"))
+    ops.split_attn_bwd(dx.float().cuda(), w[0], w[1], w[2], f32(sd["s.fc1.weight"]), f32(sd["s.bn1.weight"]), f32(sd["s.bn1.bias"]),
+                       f32(sd["s.fc2.weight"]), sums, wts, torch.empty(n, 3, C, device="cuda"), torch.empty(n, C, device="cuda"),
+                       d[0], d[1], d[2], dfc1, dg, db, dfc2)
+    for r in range(3):
+        assert rel(d[r].hi.cpu().double(), wins[r].grad[0]) < 5e-5, r
+    assert rel(dfc1.cpu().double(), sd["s.fc1.weight"].grad) < 1e-4 and rel(dfc2.cpu().double(), sd["s.fc2.weight"].grad) < 1e-4
+    assert rel(dg.cpu().double(), sd["s.bn1.weight"].grad) < 1e-4 and rel(db.cpu().double(), sd["s.bn1.bias"].grad) < 1e-4
+    # RTE
+    emb = torch.randn(100, C, generator=g, dtype=torch.float64).requires_grad_(True)
+    lw = (torch.randn(C, C, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    lb = torch.randn(C, generator=g, dtype=torch.float64).requires_grad_(True)
+    idx = torch.tensor([0, 4, 4])
+    xx = torch.randn(n, H, W, C, generator=g, dtype=torch.float64)
+    (xx + F.linear(emb[idx], lw, lb)[:, None, None, :]).backward(dx)
+    sums2 = torch.zeros(n, 2 * C, dtype=torch.float64, device="cuda")
+    dxc = dx.float().cuda()
+    for a in range(n):
+        ops.channel_stats(dxc[a:a + 1], sums2[a])
+    dW, dB, dE = torch.zeros(C, C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(100, C, device="cuda")
+    ops.rte_bwd(sums2, emb.detach().float().cuda(), idx.int().cuda(), lw.detach().float().cuda(), dW, dB, dE)
+    assert rel(dW.cpu().double(), lw.grad) < 5e-5 and rel(dB.cpu().double(), lb.grad) < 5e-5 and rel(dE.cpu().double(), emb.grad) < 5e-5
