@@ -225,13 +225,9 @@ class CoBEVTEngine(W2CEngine):
     def _sub(self, i, part, kind):
         return "fusion_net.layers.%d.%s_%s" % (i, part, kind)
 
-    def forward_train(self, P, lidar, layout):
-        """Train-mode forward (batch-statistic BatchNorm in the encoder, dropout = identity) that keeps what the
-        backward needs: per sublayer the residual input, the LayerNorm output (GEMM operand of the weight gradients), the
-        qkv tensor / the attention output, the FFN pre-activation and hidden activation."""
-        self._begin_step()
-        rec = []
-        W = self._pack_weights(P)
+    def _encode_train(self, P, W, lidar, layout, rec):
+        """train-mode encoder (batch-statistic BatchNorm, everything the backward needs recorded in `rec`):
+        voxels -> PillarVFE+scatter -> backbone -> shrink. Returns (y1 Act, y2 fp32 [N,h,w,C], cat Act)."""
         N = layout["n_total"]
         canvas = self._encode(P, lidar, layout, True, rec)
         self._last_canvas_shape = tuple(canvas.shape)
@@ -253,6 +249,17 @@ class CoBEVTEngine(W2CEngine):
                      shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
         ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, Act(y2),
                      shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
+        return y1, y2, cat
+
+    def forward_train(self, P, lidar, layout):
+        """Train-mode forward (batch-statistic BatchNorm in the encoder, dropout = identity) that keeps what the
+        backward needs: per sublayer the residual input, the LayerNorm output (GEMM operand of the weight gradients), the
+        qkv tensor / the attention output, the FFN pre-activation and hidden activation."""
+        self._begin_step()
+        rec = []
+        W = self._pack_weights(P)
+        y1, y2, cat = self._encode_train(P, W, lidar, layout, rec)
+        h2, w2 = y2.shape[1], y2.shape[2]
         B = len(layout["record_len"])
         d = self.dim
         X = self._buf("fax.x", (B * self.L, h2, w2, d))

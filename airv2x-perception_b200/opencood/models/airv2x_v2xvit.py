@@ -4,8 +4,8 @@ Same registry name / class name / constructor (`cls(hypes["model"]["args"])`), s
 (`modality_fusion.*`, `transformer.encoder.*`, `max_cav`), same `state_dict` key names and shapes (12 758 879 parameters
 for the shipped yaml, including the unused `prior_feed` and the frozen sinusoid table of the RTE embedding), same
 `forward(data_dict) -> {"psm","rm","obj","comm_rate"}` as opencood/models/airv2x_v2xvit.py:19-167 of the reference.
-The torch.nn layers below are parameter containers only; their forward is never called. Eval-mode forward only in
-this round; no CPU fallback.
+The torch.nn layers below are parameter containers only; their forward is never called. forward() is the eval path,
+train_step() the fused training step (dropout disabled); no CPU fallback.
 """
 import math
 
@@ -172,7 +172,43 @@ class Airv2xV2XVit(Airv2xWhere2com):
         return {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A],
                 "comm_rate": int(aux["comm_rate"].item())}
 
-    def train_step(self, *a, **k):
-        raise NotImplementedError("Airv2xV2XVit: the fused training step is not implemented in this round")
+    def _grad_buffers(self):
+        g = {}
+        for n, p in self.named_parameters():
+            if not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            g[n] = p.grad
+        return g
 
-    train_step_graphed = train_step
+    def _dropouts(self):
+        enc = self.args["transformer"]["encoder"]
+        return [float(enc["cav_att_config"].get("dropout", 0.0)), float(enc["pwindow_att_config"].get("dropout", 0.0)),
+                float(enc["feed_forward"].get("dropout", 0.0))]
+
+    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, dropout="error"):
+        """forward (train-mode BatchNorm) + PointPillarLossMultiClass + backward of the whole V2X-ViT path on the CUDA
+        kernels; parameter gradients land in p.grad, returns the device tensor [reg, cls, obj] (float64).
+        The reference applies nn.Dropout (cav_att / pwindow_att / feed_forward `dropout`) in train mode, which is
+        non-deterministic and has no parity target: the kernels implement dropout = identity, so a yaml with a dropout
+        > 0 needs the explicit dropout="off". The RTE embedding table receives a gradient as it does in the reference
+        (`emb.requires_grad = False` at v2xvit_basic.py:53 sets a module attribute, the weight stays trainable)."""
+        assert self.training, "train_step() needs model.train()"
+        if max(self._dropouts()) > 0 and dropout != "off":
+            raise NotImplementedError("transformer.encoder dropout > 0: pass dropout=\"off\" to train with dropout disabled")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("Airv2xV2XVit (B200) needs its parameters on a CUDA device; there is no CPU path")
+        layout = self._layout(data_dict, dev)
+        lidar = self._lidar(data_dict, dev, layout)
+        labels = self.prepare_labels(label_dict, dev)
+        P = self._param_dict()
+        eng = self.engine
+        heads = eng.forward_train(P, lidar, layout, data_dict["prior_encoding"], data_dict["spatial_correction_matrix"])
+        loss3, dheads = eng.loss(heads, labels, cls_weight, reg_coe)
+        eng.backward_train(P, dheads, self._grad_buffers())
+        return loss3
+
+    def train_step_graphed(self, *a, **k):
+        raise NotImplementedError("Airv2xV2XVit: CUDA-graph replay of the training step is not implemented")

@@ -8,7 +8,8 @@
 Mirrors opencood/models/airv2x_v2xvit.py:108-167 and v2xvit_modules/v2xvit_basic.py:135-213. Padded agents are never
 attention keys and only agent 0 is returned, so the kernels run on the valid agents only (exact; the reference spends
 2/3 of its 4.6 TFLOP on padding). Every nn.Linear is the 1x1 tcgen05 tap-GEMM (bf16x3 split); the HGT relation tensors
-are folded into the K / V projections once per step. Forward only in this round (eval-mode parity).
+are folded into the K / V projections once per step. forward() is the eval path; forward_train() / backward_train()
+are the training step (dropout = identity).
 """
 import torch
 
@@ -223,10 +224,285 @@ class V2XViTEngine(CoBEVTEngine):
         ops.regroup(X, layout["scene_start"], ones, B, 1, fused)
         return fused
 
+    # ------------------------------------------------------------------ training step
+    def forward_train(self, P, lidar, layout, prior, scm):
+        """Train-mode forward (batch-statistic BatchNorm in the encoder, dropout = identity) keeping what the backward
+        needs: per sublayer the residual input, the LayerNorm output, the projected q|k|v tensors, the attention outputs,
+        the three window branches with the split-attention statistics, the FFN pre-activation and hidden activation."""
+        self._begin_step()
+        rec = []
+        W = self._pack_weights(P)
+        y1, y2, cat = self._encode_train(P, W, lidar, layout, rec)
+        enc = self.enc
+        ca, pw = enc["cav_att_config"], enc["pwindow_att_config"]
+        record_len = layout["record_len"]
+        B, (N, h, w, C) = len(record_len), y2.shape
+        dev = self.device
+        prior = prior.detach().cpu().float()
+        starts = [sum(record_len[:b]) for b in range(B)]
+        valid = [(b, l) for b in range(B) for l in range(record_len[b])]
+        types = [int(prior[b, l, 2]) for b, l in valid]
+        assert all(t in (0, 1) for t in types), "prior_encoding[..., 2] (agent type) must be 0 or 1 (hmsa.py:8)"
+        types_dev = torch.tensor(types, dtype=torch.int32, device=dev)
+        X = self._buf("vit.x", (N, h, w, C))
+        X.copy_(y2)
+        rte_idx = None
+        if ca["use_RTE"]:
+            rte_idx = torch.tensor([int(prior[b, l, 1]) * ca["RTE_ratio"] for b, l in valid], dtype=torch.int32, device=dev)
+            rp = "fusion_net.encoder.rte.emb"
+            ops.rte_add(X, P[rp + ".emb.weight"], rte_idx, P[rp + ".lin.weight"], P[rp + ".lin.bias"], self._buf("vit.rte", (N, C)))
+        dr, ds = enc["sttf"]["voxel_size"][0], enc["sttf"]["downsample_rate"]
+        theta_all = warp.sttf_theta(scm, dr, ds, h, w)
+        theta = torch.stack([theta_all[b, l] for b, l in valid]).to(dev)
+        Xw = self._buf("vit.xw", (N, h, w, C))
+        ops.warp_affine_fwd(X, theta, Act(Xw), align_corners=True)
+        for s in starts:
+            Xw[s].copy_(X[s])
+        X = Xw
+        kmask = self._buf("vit.kmask", (N, h, w))
+        if enc["use_roi_mask"]:
+            ops.roi_mask(theta, None, N, h, w, kmask, align_corners=True)
+        else:
+            kmask.fill_(1.0)
+        runs = self._runs(types)
+        layers = []
+        for d in range(enc["depth"]):
+            lp, bp, hg, pwp = self._names(d)
+            f = hg + ".fn"
+            tag = "sv%d." % d
+            sv = {}
+            # HGT multi-agent attention
+            sv["xin_h"] = self._buf(tag + "xin_h", X.shape)
+            sv["xin_h"].copy_(X)
+            ln = sv["ln_h"] = self._act(tag + "ln_h", X.shape)
+            ops.layernorm_fwd(X, P[hg + ".norm.weight"], P[hg + ".norm.bias"], ln)
+            qkv = sv["hqkv"] = self._buf(tag + "hqkv", (N, h, w, 5 * C))
+            for s, e, t in runs:
+                ops.linear_fwd(ln.narrow_n(s, e - s), W["%s.fold.%d" % (f, t)], Act(qkv[s:e]),
+                               bias=W["%s.fold.%d.bias" % (f, t)])
+            att = sv["hatt"] = self._act(tag + "hatt", X.shape)
+            for b in range(B):
+                s, e = starts[b], starts[b] + record_len[b]
+                ops.hgt_attention_fwd(qkv[s:e], types_dev[s:e], kmask[s:e], ca["heads"], ca["dim_head"], att.narrow_n(s, e - s))
+            for s, e, t in runs:
+                ops.linear_fwd(att.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], Act(X[s:e]),
+                               bias=P["%s.a_linears.%d.bias" % (f, t)], accumulate=True)
+            # pyramid window attention + split attention
+            sv["xin_p"] = self._buf(tag + "xin_p", X.shape)
+            sv["xin_p"].copy_(X)
+            ln = sv["ln_p"] = self._act(tag + "ln_p", X.shape)
+            ops.layernorm_fwd(X, P[pwp + ".norm.weight"], P[pwp + ".norm.bias"], ln)
+            sv["wqkv"], sv["watt"], sv["win"], sv["table"] = [], [], [], []
+            for lv, (hh, dh, ws) in enumerate(zip(pw["heads"], pw["dim_head"], pw["window_size"])):
+                bp_l = "%s.fn.pwmsa.%d" % (pwp, lv)
+                wqkv = self._buf(tag + "wqkv%d" % lv, (N, h, w, 3 * C))
+                ops.linear_fwd(ln, W[bp_l + ".to_qkv.weight"], Act(wqkv))
+                table = P[bp_l + ".pos_embedding"].flip(0, 1).reshape(-1, 1).expand(-1, hh).contiguous()
+                watt = self._act(tag + "watt%d" % lv, X.shape)
+                ops.window_attention_fwd(wqkv, table, None, N, 1, hh, dh, ws, False, watt)
+                win = self._buf(tag + "win%d" % lv, (N, h, w, C))
+                ops.linear_fwd(watt, W[bp_l + ".to_out.0.weight"], Act(win), bias=P[bp_l + ".to_out.0.bias"])
+                sv["wqkv"].append(wqkv)
+                sv["watt"].append(watt)
+                sv["win"].append(win)
+                sv["table"].append(table)
+            sp = pwp + ".fn.split_attn"
+            sv["sa_sums"], sv["sa_w"] = self._buf(tag + "sa_sums", (N, C)), self._buf(tag + "sa_w", (N, 3, C))
+            ops.split_attn_fuse(sv["win"][0], sv["win"][1], sv["win"][2], P[sp + ".fc1.weight"], P[sp + ".bn1.weight"],
+                                P[sp + ".bn1.bias"], P[sp + ".fc2.weight"], sv["sa_sums"], sv["sa_w"], X)
+            # feed forward (pre-activation kept in fp32: GELU' needs it)
+            sv["xin_f"] = self._buf(tag + "xin_f", X.shape)
+            sv["xin_f"].copy_(X)
+            ln = sv["ln_f"] = self._act(tag + "ln_f", X.shape)
+            ops.layernorm_fwd(X, P[lp + ".1.norm.weight"], P[lp + ".1.norm.bias"], ln)
+            pre = sv["hpre"] = self._buf(tag + "hpre", (N, h, w, enc["feed_forward"]["mlp_dim"]))
+            ops.linear_fwd(ln, W[lp + ".1.fn.net.0.weight"], Act(pre), bias=P[lp + ".1.fn.net.0.bias"])
+            hid = sv["hid"] = self._act(tag + "hid", pre.shape)
+            ops.gelu_fwd(pre, hid)
+            ops.linear_fwd(hid, W[lp + ".1.fn.net.3.weight"], Act(X), bias=P[lp + ".1.fn.net.3.bias"], accumulate=True)
+            layers.append(sv)
+        fused = self._act("vit.fused", (B, h, w, C))
+        ones = self._buf("vit.ones", (B,), torch.int32)
+        ones.fill_(1)
+        ops.regroup(X, layout["scene_start"], ones, B, 1, fused)
+        heads = self._buf("heads.out", (B, h, w, HEAD_PAD))
+        ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
+        self.saved = dict(rec=rec, W=W, layers=layers, fused=fused, y1=y1, y2=y2, cat=cat, layout=layout, B=B, runs=runs,
+                          starts=starts, types_dev=types_dev, kmask=kmask, theta=theta, rte_idx=rte_idx)
+        return heads
+
+    def backward_train(self, P, dheads, grads):
+        """dheads: [B,h,w,HEAD_PAD] gradient w.r.t. the head logits; grads: name -> fp32 tensor (written; the unused
+        `prior_feed` stays zero, as autograd leaves it in the reference)."""
+        S = self.saved
+        W, layout, B, runs, starts = S["W"], S["layout"], S["B"], S["runs"], S["starts"]
+        enc = self.enc
+        ca, pw = enc["cav_att_config"], enc["pwindow_att_config"]
+        record_len = layout["record_len"]
+        nc, nr = self.A * self.K, 7 * self.A
+        C = self.dim
+        N, h, w, _ = S["y2"].shape
+        unpack = []
+        dwps = {}
+
+        def zero_f32(n):
+            return self._zeroed("z", n, torch.float32)
+
+        def dwp_for(wname, co, ci):
+            if wname not in dwps:
+                dwps[wname] = zero_f32(co * ci).view(1, co, ci)
+                unpack.append(ops.conv_unpack_job(dwps[wname], grads[wname].view(co, ci, 1, 1)))
+            return dwps[wname]
+
+        def lin_wgrad(x_act, dy_act, wname):
+            """grad of nn.Linear weight [out, in] = 1x1 conv wgrad; repeated calls for one weight accumulate"""
+            ops.conv_wgrad(x_act, dy_act, 1, 1, dwp_for(wname, dy_act.shape[3], x_act.shape[3]))
+
+        def col_sums(t, Cc, outs):
+            sums = self._zeroed("bias.sums", 2 * Cc, torch.float64)
+            ops.channel_stats(t, sums)
+            for out, c0 in outs:
+                unpack.append(ops.sums_unpack_job(sums, out, c0))
+
+        def split_of(t, name):
+            a = self._act(name, t.shape)
+            n_, h_, w_, c_ = t.shape
+            if c_ > 1024:  # elementwise: present wide rows to the kernel as C-wide ones
+                k = c_ // C
+                ops.affine_act(t.view(n_, h_, w_ * k, C), None, None, False,
+                               Act(a.hi.view(n_, h_, w_ * k, C), None if a.b16 is None else a.b16.view(2, n_, h_, w_ * k, C)))
+            else:
+                ops.affine_act(t, None, None, False, a)
+            return a
+
+        def ln_bwd(xin, d_ln, pre_norm, dX):
+            acc = self._zeroed(pre_norm + ".lnacc", 2 * C, torch.float64)
+            ops.layernorm_bwd(xin, d_ln, P[pre_norm + ".weight"], dX, acc[:C], acc[C:])
+            unpack.append(ops.sums_unpack_job(acc, grads[pre_norm + ".weight"], 0))
+            unpack.append(ops.sums_unpack_job(acc, grads[pre_norm + ".bias"], C))
+
+        # ---- heads; only the ego rows of the encoder output are used (V2XTransformer returns output[:, 0])
+        dh = split_of(dheads, "bwd.dheads")
+        dwp = zero_f32(HEAD_PAD * self.c_shrink).view(1, HEAD_PAD, self.c_shrink)
+        ops.conv_wgrad(S["fused"], dh, 1, 1, dwp)
+        for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+            unpack.append(ops.conv_unpack_job(dwp, grads[name + ".weight"], row0))
+        col_sums(dheads, HEAD_PAD, [(grads["cls_head.bias"], 0), (grads["reg_head.bias"], nc), (grads["obj_head.bias"], nc + nr)])
+        d_fused = self._buf("bwd.d_fused", S["fused"].shape)
+        ops.conv_dgrad(dh, W["heads"], 1, 1, d_fused)
+        dX = self._buf("bwd.dX", (N, h, w, C))
+        dX.zero_()
+        for b, s in enumerate(starts):
+            dX[s].copy_(d_fused[b])
+        d_ln = self._buf("bwd.d_ln", (N, h, w, C))
+        for d in range(enc["depth"] - 1, -1, -1):
+            lp, bp, hg, pwp = self._names(d)
+            f = hg + ".fn"
+            sv = S["layers"][d]
+            # ---- feed forward
+            pre = lp + ".1"
+            dXs = split_of(dX, "bwd.dXs")
+            lin_wgrad(sv["hid"], dXs, pre + ".fn.net.3.weight")
+            col_sums(dX, C, [(grads[pre + ".fn.net.3.bias"], 0)])
+            d_hid = self._buf("bwd.d_hid", sv["hid"].shape)
+            ops.conv_dgrad(dXs, W[pre + ".fn.net.3.weight"], 1, 1, d_hid)
+            d_pre = self._act("bwd.d_pre", sv["hid"].shape)
+            ops.gelu_bwd(d_hid, sv["hpre"], d_pre)
+            lin_wgrad(sv["ln_f"], d_pre, pre + ".fn.net.0.weight")
+            col_sums(d_pre.hi, d_pre.shape[3], [(grads[pre + ".fn.net.0.bias"], 0)])
+            ops.conv_dgrad(d_pre, W[pre + ".fn.net.0.weight"], 1, 1, d_ln)
+            ln_bwd(sv["xin_f"], d_ln, pre + ".norm", dX)
+            # ---- pyramid window attention + split attention
+            sp = pwp + ".fn.split_attn"
+            dwin = [self._act("bwd.dwin%d" % lv, (N, h, w, C)) for lv in range(3)]
+            for n in (".fc1.weight", ".bn1.weight", ".bn1.bias", ".fc2.weight"):
+                grads[sp + n].zero_()
+            ops.split_attn_bwd(dX, sv["win"][0], sv["win"][1], sv["win"][2], P[sp + ".fc1.weight"], P[sp + ".bn1.weight"],
+                               P[sp + ".bn1.bias"], P[sp + ".fc2.weight"], sv["sa_sums"], sv["sa_w"],
+                               self._buf("bwd.sa_dw", (N, 3, C)), self._buf("bwd.sa_dgap", (N, C)), dwin[0], dwin[1], dwin[2],
+                               grads[sp + ".fc1.weight"], grads[sp + ".bn1.weight"], grads[sp + ".bn1.bias"],
+                               grads[sp + ".fc2.weight"])
+            for lv, (hh, dhd, ws) in enumerate(zip(pw["heads"], pw["dim_head"], pw["window_size"])):
+                bp_l = "%s.fn.pwmsa.%d" % (pwp, lv)
+                lin_wgrad(sv["watt"][lv], dwin[lv], bp_l + ".to_out.0.weight")
+                col_sums(dwin[lv].hi, C, [(grads[bp_l + ".to_out.0.bias"], 0)])
+                d_att = self._buf("bwd.d_att", (N, h, w, C))
+                ops.conv_dgrad(dwin[lv], W[bp_l + ".to_out.0.weight"], 1, 1, d_att)
+                dqkv = self._buf("bwd.dwqkv", (N, h, w, 3 * C))
+                dbias = self._buf("bwd.dbias%d" % lv, sv["table"][lv].shape)
+                dbias.zero_()
+                ops.window_attention_bwd(sv["wqkv"][lv], d_att, sv["table"][lv], None, N, 1, hh, dhd, ws, False, dqkv, dbias)
+                # the table is the flipped pos_embedding broadcast over heads (mswin.py:15-20)
+                grads[bp_l + ".pos_embedding"].copy_(dbias.sum(1).view(2 * ws - 1, 2 * ws - 1).flip(0, 1))
+                dqs = split_of(dqkv, "bwd.dwqs")
+                lin_wgrad(sv["ln_p"], dqs, bp_l + ".to_qkv.weight")
+                ops.conv_dgrad(dqs, W[bp_l + ".to_qkv.weight"], 1, 1, d_ln, accumulate=lv > 0)
+            ln_bwd(sv["xin_p"], d_ln, pwp + ".norm", dX)
+            # ---- HGT multi-agent attention
+            dXs = split_of(dX, "bwd.dXs")
+            d_att = self._buf("bwd.d_att", (N, h, w, C))
+            asums = self._zeroed("hgt.asums", 2 * 2 * C, torch.float64).view(2, 2 * C)
+            for t in range(2):  # an agent type absent from the batch gets a zero gradient
+                dwp_for("%s.a_linears.%d.weight" % (f, t), C, C)
+            for s, e, t in runs:
+                lin_wgrad(sv["hatt"].narrow_n(s, e - s), dXs.narrow_n(s, e - s), "%s.a_linears.%d.weight" % (f, t))
+                ops.channel_stats(dX[s:e], asums[t])
+                ops.conv_dgrad(dXs.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], 1, 1, d_att[s:e])
+            for t in range(2):
+                unpack.append(ops.sums_unpack_job(asums[t], grads["%s.a_linears.%d.bias" % (f, t)], 0))
+            dhq = self._buf("bwd.dhqkv", (N, h, w, 5 * C))
+            for b in range(B):
+                s, e = starts[b], starts[b] + record_len[b]
+                ops.hgt_attention_bwd(sv["hqkv"][s:e], S["types_dev"][s:e], S["kmask"][s:e], d_att[s:e], ca["heads"],
+                                      ca["dim_head"], dhq[s:e])
+            dhs = split_of(dhq, "bwd.dhqs")
+            dwf = zero_f32(2 * 5 * C * C).view(2, 5 * C, C)
+            fsums = self._zeroed("hgt.fsums", 2 * 5 * 2 * C, torch.float64).view(2, 5, 2 * C)
+            for s, e, t in runs:
+                ops.conv_wgrad(sv["ln_h"].narrow_n(s, e - s), dhs.narrow_n(s, e - s), 1, 1, dwf[t].view(1, 5 * C, C))
+                for j in range(5):
+                    ops.channel_stats(dhq[s:e, :, :, j * C:(j + 1) * C], fsums[t, j])
+                ops.conv_dgrad(dhs.narrow_n(s, e - s), W["%s.fold.%d" % (f, t)], 1, 1, d_ln[s:e])
+            dbf = self._buf("bwd.dbf", (2, 5 * C))
+            for t in range(2):
+                for j in range(5):
+                    ops.sums_to_float(fsums[t, j], C, dbf[t, j * C:(j + 1) * C])
+            pair = lambda n, s_: (P["%s.%s.0.%s" % (f, n, s_)], P["%s.%s.1.%s" % (f, n, s_)])
+            gpair = lambda n, s_: (grads["%s.%s.0.%s" % (f, n, s_)], grads["%s.%s.1.%s" % (f, n, s_)])
+            ops.hgt_fold_bwd(dwf, dbf, pair("k_linears", "weight"), pair("k_linears", "bias"), pair("v_linears", "weight"),
+                             pair("v_linears", "bias"), P[f + ".relation_att"], P[f + ".relation_msg"], ca["heads"],
+                             gpair("q_linears", "weight"), gpair("q_linears", "bias"), gpair("k_linears", "weight"),
+                             gpair("k_linears", "bias"), gpair("v_linears", "weight"), gpair("v_linears", "bias"),
+                             grads[f + ".relation_att"], grads[f + ".relation_msg"])
+            ln_bwd(sv["xin_h"], d_ln, hg + ".norm", dX)
+        # ---- STTF^T: non-ego gradients go back through the bilinear resampling, the ego map was copied
+        d_pre_warp = self._buf("bwd.d_prewarp", (N, h, w, C))
+        d_pre_warp.zero_()
+        ops.warp_affine_bwd(dX, S["theta"], d_pre_warp, align_corners=True)
+        for s in starts:
+            d_pre_warp[s].copy_(dX[s])
+        # ---- RTE^T: the per-agent vector's gradient is the column sum of its map's gradient
+        if S["rte_idx"] is not None:
+            rp = "fusion_net.encoder.rte.emb"
+            rsums = self._zeroed("rte.sums", N * 2 * C, torch.float64).view(N, 2 * C)
+            for a in range(N):
+                ops.channel_stats(d_pre_warp[a:a + 1], rsums[a])
+            for n in (".lin.weight", ".lin.bias", ".emb.weight"):
+                grads[rp + n].zero_()
+            ops.rte_bwd(rsums, P[rp + ".emb.weight"], S["rte_idx"], P[rp + ".lin.weight"], grads[rp + ".lin.weight"],
+                        grads[rp + ".lin.bias"], grads[rp + ".emb.weight"])
+        for n in ("fusion_net.encoder.prior_feed.weight", "fusion_net.encoder.prior_feed.bias"):
+            if n in grads:
+                grads[n].zero_()
+        self._encoder_backward(P, S, d_pre_warp, grads, unpack)
+        for lo in range(0, len(unpack), 128):
+            ops.unpack_wgrads_batched(self._job_table("unpack%d" % lo, unpack[lo:lo + 128]))
+        return grads
+
     def forward(self, P, lidar, layout, training, prior=None, scm=None):
         if training:
-            raise NotImplementedError("V2X-ViT on the B200 kernels is forward-only (eval mode) in this round: the "
-                                      "transformer-fusion backward and dropout are not implemented")
+            raise NotImplementedError("Airv2xV2XVit: train-mode forward(data_dict) is not wired to autograd; use "
+                                      "train_step(data_dict, label_dict) (forward + loss + backward, dropout disabled)")
         self._begin_step()
         W = self._pack_weights(P)
         canvas_nz = self._buf("comm_rate", (1,), torch.int64)

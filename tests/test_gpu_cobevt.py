@@ -296,7 +296,7 @@ def test_train_step_matches_oracle_autograd():
     out, _ = CO.cobevt_forward(p, args, dd, training=True)
     loss = O.point_pillar_loss_multiclass(out, labels, args["num_class"], cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])[0]
     loss.backward()
-    assert abs(float(loss3.sum()) - float(loss)) < 1e-3 * abs(float(loss))
+    assert abs(float(loss3.sum()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
     errs = {}
     for n, q in model.named_parameters():
         ref = p[n].grad

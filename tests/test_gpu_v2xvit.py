@@ -231,3 +231,56 @@ def test_split_attn_and_rte_backward(ops):
     dW, dB, dE = torch.zeros(C, C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(100, C, device="cuda")
     ops.rte_bwd(sums2, emb.detach().float().cuda(), idx.int().cuda(), lw.detach().float().cuda(), dW, dB, dE)
     assert rel(dW.cpu().double(), lw.grad) < 5e-5 and rel(dB.cpu().double(), lb.grad) < 5e-5 and rel(dE.cpu().double(), emb.grad) < 5e-5
+
+
+def test_train_step_matches_oracle_autograd():
+    """V2X-ViT training step (train-mode BatchNorm, dropout off): loss and every parameter gradient against torch autograd
+    through the oracle (pinned to the real reference in eval mode). Fusion-network / head gradients are tight; encoder
+    gradients pass ReLU / max gates (see tests/test_gpu_model.py) -> norm-wise bounds. `prior_feed` is unused: zero grads."""
+    import json
+
+    import a2x_import
+    import w2c_common as C
+    from oracle import w2c_oracle as O
+
+    M = a2x_import.pkg("opencood.models.airv2x_v2xvit")
+    cfg, gold = VC.load_small()
+    args = json.loads(json.dumps(cfg["model_args"]))
+    model = M.Airv2xV2XVit(args)
+    sd = VC.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    dd = VC.golden_scene(cfg, gold)
+    H, W = gold["eval_psm"].shape[2:]
+    labels = O.make_labels(5, 1, H, W, args["anchor_number"])
+    if max(model._dropouts()) > 0:
+        with pytest.raises(NotImplementedError):
+            model.train_step(C.to_device(dd, "cuda"), labels)
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"],
+                             dropout="off")
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    torch.set_num_threads(8)
+    out, _ = VO.v2xvit_forward(p, args, dd, training=True)
+    loss = O.point_pillar_loss_multiclass(out, labels, args["num_class"], cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])[0]
+    loss.backward()
+    assert abs(float(loss3.sum()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
+    errs = {}
+    for n, q in model.named_parameters():
+        ref = p[n].grad
+        if ref is None:
+            assert float(q.grad.abs().max()) == 0.0, n
+            continue
+        errs[n] = float((q.grad.cpu() - ref).norm() / (ref.norm() + 1e-30))
+    print(sorted(errs.items(), key=lambda kv: -kv[1])[:12])
+    fusion = {n: e for n, e in errs.items() if n.startswith("fusion_net") or "head" in n}
+    assert len(fusion) > 100 and max(fusion.values()) < 2e-2, sorted(fusion.items(), key=lambda kv: -kv[1])[:5]
+    assert float(np.median(list(fusion.values()))) < 2e-3
+    assert max(errs.values()) < 0.15 and float(np.median(list(errs.values()))) < 0.05, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    # a second step reuses every buffer (stale-state check): same loss, same gradients
+    g1 = {n: q.grad.clone() for n, q in model.named_parameters()}
+    loss3b = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"],
+                              dropout="off")
+    assert torch.allclose(loss3b, loss3, rtol=1e-6)
+    worst = max(float((q.grad - g1[n]).norm() / (g1[n].norm() + 1e-30)) for n, q in model.named_parameters())
+    assert worst < 1e-3, worst
