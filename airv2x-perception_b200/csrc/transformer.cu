@@ -795,27 +795,29 @@ __global__ void __launch_bounds__(128) window_attention_bwd_kernel(const WinAttB
         if (sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sdB[i]);
 }
 
-// Small-window backward (n = L*w*w <= 16 tokens, 128 % n == 0): thread = (window g, query), like the forward small kernel.
-// The query's probability row lives in registers; dK / dV of the window's keys accumulate in shared memory.
-template <int DH>
+// Small-window backward (NT = L*w*w in {4, 16} tokens): 128 / NT windows per CTA, no atomics on the data path.
+// Phase 1, thread = (window g, query i): probability row and dS row in registers -> dQ; both rows go to shared memory.
+// Phase 2, the same thread as key j of its window: dK_j = sum_i dS_ij Q_i, dV_j = sum_i P_ij dO_i from the shared rows.
+// The relative-position-bias gradient is gathered per table entry (one thread per entry), one global atomic per entry and CTA.
+template <int DH, int NT>
 __global__ void __launch_bounds__(128) window_attention_small_bwd_kernel(const WinAttBwdParams p, int num_windows) {
     extern __shared__ float sm[];
     const int ww = p.w * p.w;
-    const int n = p.L * ww;
-    constexpr int RS = DH + 4;
+    constexpr int RS = DH + 4, PS = NT + 1, G = 128 / NT;
     float* sK = sm;                   // [128][RS]
     float* sV = sK + 128 * RS;
-    float* sdK = sV + 128 * RS;
-    float* sdV = sdK + 128 * RS;
+    float* sQ = sV + 128 * RS;        // scaled q
+    float* sG = sQ + 128 * RS;        // dO
+    float* sP = sG + 128 * RS;        // [128][PS]
+    float* sS = sP + 128 * PS;
     const int nb = (2 * p.L - 1) * (2 * p.w - 1) * (2 * p.w - 1);
-    float* sB = sdV + 128 * RS;
-    float* sdB = sB + nb;
+    float* sB = sS + 128 * PS;
     const int D = p.heads * DH;
     const int X = p.H / p.w, Y = p.W / p.w;
-    const int G = 128 / n;
     const int head = blockIdx.x % p.heads;
-    const int g = threadIdx.x / n, tq = threadIdx.x - g * n;
-    int win = (blockIdx.x / p.heads) * G + g;
+    const int g = threadIdx.x / NT, tq = threadIdx.x - g * NT;
+    const int win0 = (blockIdx.x / p.heads) * G;
+    int win = win0 + g;
     const bool valid = win < num_windows;
     if (!valid) win = num_windows - 1;
     const int y = win % Y;
@@ -826,87 +828,141 @@ __global__ void __launch_bounds__(128) window_attention_small_bwd_kernel(const W
     const int ph = p.grid_mode ? w1 * X + x : x * p.w + w1;
     const int pw = p.grid_mode ? w2 * Y + y : y * p.w + w2;
     const long long tok = ((long long)(b * p.L + l) * p.H + ph) * p.W + pw;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-        sB[i] = p.bias[i * p.heads + head];
-        sdB[i] = 0.f;
-    }
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) sB[i] = p.bias[i * p.heads + head];
     const float* row = p.qkv + tok * (3 * D) + head * DH;
-    float q[DH], go[DH];
-#pragma unroll
-    for (int c = 0; c < DH; c += 4) {
-        const float4 qv = *reinterpret_cast<const float4*>(row + c);
-        q[c] = qv.x * p.scale; q[c + 1] = qv.y * p.scale; q[c + 2] = qv.z * p.scale; q[c + 3] = qv.w * p.scale;
-        *reinterpret_cast<float4*>(sK + threadIdx.x * RS + c) = *reinterpret_cast<const float4*>(row + D + c);
-        *reinterpret_cast<float4*>(sV + threadIdx.x * RS + c) = *reinterpret_cast<const float4*>(row + 2 * D + c);
-        const float4 gv = *reinterpret_cast<const float4*>(p.dout + tok * D + head * DH + c);
-        go[c] = gv.x; go[c + 1] = gv.y; go[c + 2] = gv.z; go[c + 3] = gv.w;
-        *reinterpret_cast<float4*>(sdK + threadIdx.x * RS + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(sdV + threadIdx.x * RS + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
     const int s2 = 2 * p.w - 1;
-    float pr[16], dp[16];
+    float pr[NT], ds[NT];
     float mx = -INFINITY;
-    for (int j = 0; j < n; ++j) {
-        pr[j] = -INFINITY;
-        dp[j] = 0.f;
-        const int lj = j / ww, rj = j - lj * ww;
-        if (p.key_mask != nullptr && p.key_mask[b * p.L + lj] == 0) continue;
-        const float* kr = sK + (g * n + j) * RS;
-        const float* vr = sV + (g * n + j) * RS;
-        float a = sB[((l - lj + p.L - 1) * s2 + (w1 - rj / p.w + p.w - 1)) * s2 + (w2 - rj % p.w + p.w - 1)], d2 = 0.f;
+    {
+        float q[DH], go[DH];
 #pragma unroll
-        for (int c = 0; c < DH; ++c) {
-            a = fmaf(q[c], kr[c], a);
-            d2 = fmaf(go[c], vr[c], d2);
+        for (int c = 0; c < DH; c += 4) {
+            float4 qv = *reinterpret_cast<const float4*>(row + c);
+            qv.x *= p.scale; qv.y *= p.scale; qv.z *= p.scale; qv.w *= p.scale;
+            q[c] = qv.x; q[c + 1] = qv.y; q[c + 2] = qv.z; q[c + 3] = qv.w;
+            *reinterpret_cast<float4*>(sQ + threadIdx.x * RS + c) = qv;
+            *reinterpret_cast<float4*>(sK + threadIdx.x * RS + c) = *reinterpret_cast<const float4*>(row + D + c);
+            *reinterpret_cast<float4*>(sV + threadIdx.x * RS + c) = *reinterpret_cast<const float4*>(row + 2 * D + c);
+            const float4 gv = *reinterpret_cast<const float4*>(p.dout + tok * D + head * DH + c);
+            go[c] = gv.x; go[c + 1] = gv.y; go[c + 2] = gv.z; go[c + 3] = gv.w;
+            *reinterpret_cast<float4*>(sG + threadIdx.x * RS + c) = gv;
         }
-        pr[j] = a;
-        dp[j] = d2;
-        mx = fmaxf(mx, a);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            pr[j] = -INFINITY;
+            ds[j] = 0.f;
+            const int lj = j / ww, rj = j - lj * ww;
+            if (p.key_mask != nullptr && p.key_mask[b * p.L + lj] == 0) continue;
+            const float* kr = sK + (g * NT + j) * RS;
+            const float* vr = sV + (g * NT + j) * RS;
+            float a0 = sB[((l - lj + p.L - 1) * s2 + (w1 - rj / p.w + p.w - 1)) * s2 + (w2 - rj % p.w + p.w - 1)], a1 = 0.f;
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4) {
+                const float4 k4 = *reinterpret_cast<const float4*>(kr + c);
+                const float4 v4 = *reinterpret_cast<const float4*>(vr + c);
+                a0 = fmaf(q[c], k4.x, a0); a1 = fmaf(q[c + 1], k4.y, a1);
+                a0 = fmaf(q[c + 2], k4.z, a0); a1 = fmaf(q[c + 3], k4.w, a1);
+                d0 = fmaf(go[c], v4.x, d0); d1 = fmaf(go[c + 1], v4.y, d1);
+                d0 = fmaf(go[c + 2], v4.z, d0); d1 = fmaf(go[c + 3], v4.w, d1);
+            }
+            pr[j] = a0 + a1;
+            ds[j] = d0 + d1;
+            mx = fmaxf(mx, pr[j]);
+        }
     }
     float lsum = 0.f;
-    for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
         pr[j] = expf(pr[j] - mx);
         lsum += pr[j];
     }
-    const float inv = 1.f / lsum;
+    const float inv = valid ? 1.f / lsum : 0.f;  // a clamped (out-of-range) window contributes nothing
     float Dv = 0.f;
-    for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
         pr[j] *= inv;
-        Dv = fmaf(pr[j], dp[j], Dv);
+        Dv = fmaf(pr[j], ds[j], Dv);
     }
-    float dq[DH];
 #pragma unroll
-    for (int c = 0; c < DH; ++c) dq[c] = 0.f;
-    if (valid) {
-        for (int j = 0; j < n; ++j) {
-            if (pr[j] == 0.f) continue;
-            const float ds = pr[j] * (dp[j] - Dv);
-            const int lj = j / ww, rj = j - lj * ww;
-            atomicAdd(&sdB[((l - lj + p.L - 1) * s2 + (w1 - rj / p.w + p.w - 1)) * s2 + (w2 - rj % p.w + p.w - 1)], ds);
-            const float* kr = sK + (g * n + j) * RS;
-            float* dk = sdK + (g * n + j) * RS;
-            float* dv = sdV + (g * n + j) * RS;
-#pragma unroll
-            for (int c = 0; c < DH; ++c) {
-                dq[c] = fmaf(ds, kr[c], dq[c]);
-                atomicAdd(&dk[c], ds * q[c]);
-                atomicAdd(&dv[c], pr[j] * go[c]);
-            }
-        }
+    for (int j = 0; j < NT; ++j) {
+        ds[j] = pr[j] * (ds[j] - Dv);
+        sP[threadIdx.x * PS + j] = pr[j];
+        sS[threadIdx.x * PS + j] = ds[j];
     }
-    __syncthreads();
     if (valid) {
         float* out = p.dqkv + tok * (3 * D) + head * DH;
 #pragma unroll
-        for (int c = 0; c < DH; c += 4) {
-            *reinterpret_cast<float4*>(out + c) = make_float4(dq[c] * p.scale, dq[c + 1] * p.scale, dq[c + 2] * p.scale, dq[c + 3] * p.scale);
-            *reinterpret_cast<float4*>(out + D + c) = *reinterpret_cast<const float4*>(sdK + threadIdx.x * RS + c);
-            *reinterpret_cast<float4*>(out + 2 * D + c) = *reinterpret_cast<const float4*>(sdV + threadIdx.x * RS + c);
+        for (int c0 = 0; c0 < DH; c0 += 16) {
+            float acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const float* kr = sK + (g * NT + j) * RS + c0;
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(kr + c);
+                    acc[c] = fmaf(ds[j], k4.x, acc[c]); acc[c + 1] = fmaf(ds[j], k4.y, acc[c + 1]);
+                    acc[c + 2] = fmaf(ds[j], k4.z, acc[c + 2]); acc[c + 3] = fmaf(ds[j], k4.w, acc[c + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c += 4)
+                *reinterpret_cast<float4*>(out + c0 + c) =
+                    make_float4(acc[c] * p.scale, acc[c + 1] * p.scale, acc[c + 2] * p.scale, acc[c + 3] * p.scale);
         }
     }
-    for (int i = threadIdx.x; i < nb; i += blockDim.x)
-        if (sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sdB[i]);
+    __syncthreads();
+    // ---- phase 2: this thread as key tq of window g
+    if (valid) {
+        float* out = p.dqkv + tok * (3 * D) + head * DH;
+        float sj[NT], pj[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            sj[i] = sS[(g * NT + i) * PS + tq];
+            pj[i] = sP[(g * NT + i) * PS + tq];
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 16) {
+            float dk[16], dv[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) dk[c] = dv[c] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                const float* qr = sQ + (g * NT + i) * RS + c0;
+                const float* gr = sG + (g * NT + i) * RS + c0;
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    const float4 q4 = *reinterpret_cast<const float4*>(qr + c);
+                    const float4 g4 = *reinterpret_cast<const float4*>(gr + c);
+                    dk[c] = fmaf(sj[i], q4.x, dk[c]); dk[c + 1] = fmaf(sj[i], q4.y, dk[c + 1]);
+                    dk[c + 2] = fmaf(sj[i], q4.z, dk[c + 2]); dk[c + 3] = fmaf(sj[i], q4.w, dk[c + 3]);
+                    dv[c] = fmaf(pj[i], g4.x, dv[c]); dv[c + 1] = fmaf(pj[i], g4.y, dv[c + 1]);
+                    dv[c + 2] = fmaf(pj[i], g4.z, dv[c + 2]); dv[c + 3] = fmaf(pj[i], g4.w, dv[c + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+                *reinterpret_cast<float4*>(out + D + c0 + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
+                *reinterpret_cast<float4*>(out + 2 * D + c0 + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
+            }
+        }
+    }
+    // ---- bias gradient: one thread per table entry gathers dS over the CTA's windows
+    for (int e = threadIdx.x; e < nb; e += blockDim.x) {
+        const int e2 = e % s2 - (p.w - 1), e1 = (e / s2) % s2 - (p.w - 1), el = e / (s2 * s2) - (p.L - 1);
+        float acc = 0.f;
+        for (int i = 0; i < NT; ++i) {
+            const int li = i / ww, ri = i - li * ww, i1 = ri / p.w, i2 = ri - i1 * p.w;
+            const int lj = li - el, k1 = i1 - e1, k2 = i2 - e2;
+            if (lj < 0 || lj >= p.L || k1 < 0 || k1 >= p.w || k2 < 0 || k2 >= p.w) continue;
+            const int j = lj * ww + k1 * p.w + k2;
+            for (int gg = 0; gg < G; ++gg) acc += sS[(gg * NT + i) * PS + j];
+        }
+        if (acc != 0.f) atomicAdd(&p.dbias[e * p.heads + head], acc);
+    }
 }
 
 }  // namespace a2x
@@ -963,20 +1019,23 @@ int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* b
     const int n = L * window * window;
     const int nb = (2 * L - 1) * (2 * window - 1) * (2 * window - 1);
     cudaStream_t st0 = (cudaStream_t)stream;
-    if (n <= 16 && 128 % n == 0) {  // small windows: 128 / n windows per CTA
+    if (n == 4 || n == 16) {  // small windows: 128 / n windows per CTA
         const int num_windows = B * (H / window) * (W / window);
         const int G = 128 / n;
-        const size_t sms = (size_t)(4 * 128 * (dim_head + 4) + 2 * nb) * sizeof(float);
+        const size_t sms = (size_t)(4 * 128 * (dim_head + 4) + 2 * 128 * (n + 1) + nb) * sizeof(float);
         const long long gs = (long long)((num_windows + G - 1) / G) * heads;
-#define A2X_WASB(DH)                                                                                            \
+#define A2X_WASB(DH, NT)                                                                                        \
     do {                                                                                                        \
-        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_small_bwd_kernel<DH>,                         \
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_small_bwd_kernel<DH, NT>,                     \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));            \
-        a2x::window_attention_small_bwd_kernel<DH><<<(unsigned)gs, 128, sms, st0>>>(p, num_windows);            \
+        a2x::window_attention_small_bwd_kernel<DH, NT><<<(unsigned)gs, 128, sms, st0>>>(p, num_windows);        \
     } while (0)
-        if (dim_head == 16) A2X_WASB(16);
-        else if (dim_head == 32) A2X_WASB(32);
-        else if (dim_head == 64) A2X_WASB(64);
+        if (dim_head == 16 && n == 4) A2X_WASB(16, 4);
+        else if (dim_head == 32 && n == 4) A2X_WASB(32, 4);
+        else if (dim_head == 64 && n == 4) A2X_WASB(64, 4);
+        else if (dim_head == 16) A2X_WASB(16, 16);
+        else if (dim_head == 32) A2X_WASB(32, 16);
+        else if (dim_head == 64) A2X_WASB(64, 16);
         else {
             a2x::set_error("window_attention_bwd: dim_head %d not in {16, 32, 64}", dim_head);
             return 1;

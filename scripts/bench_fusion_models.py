@@ -60,7 +60,7 @@ def main():
         torch.cuda.synchronize()
         prof, libmod.PROFILE = libmod.PROFILE, None
     train = None
-    if which == "cobevt" and "--train" in sys.argv:
+    if "--train" in sys.argv:
         lab_np = bench.synth_labels(3, 100, 352, cfg["model_args"]["anchor_number"])
         lab = {k: torch.from_numpy(v).cuda() for k, v in lab_np.items()}
         model.train()
