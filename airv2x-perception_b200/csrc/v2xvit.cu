@@ -359,77 +359,124 @@ int a2x_split_attn_fuse(const float* w0, const float* w1, const float* w2, int n
 // SplitAttn and RTE. Same re-association as the forward; everything is recomputed from the saved projections.
 namespace a2x {
 
-constexpr int HGT_MAX_AGENTS = 16;
+constexpr int HGT_MAX_AGENTS = 12;  // backward: 2 n^2 floats of shared memory per thread
 
-// one thread per (pixel, head). dqkv (zero-filled by the caller) has the layout of qkv: q | k'(0) | k'(1) | v'(0) | v'(1);
-// the thread owns its (pixel, head) slices of every agent, so the k' / v' gradients accumulate with plain read-modify-write.
+// one thread per (pixel, head); dqkv has the layout of qkv: q | k'(0) | k'(1) | v'(0) | v'(1), every slot written here.
+// Phase A, per query agent i: probability row P_i. and dS_i. -> the thread's shared-memory slab, dq_i from registers.
+// Phase B, per key agent j and query type ty: dk'_ty(j) = sum_{i of type ty} dS_ij q_i, dv'_ty(j) = sum P_ij dO_i,
+// accumulated in registers and stored once (no read-modify-write of global memory).
 template <int DH>
 __global__ void __launch_bounds__(128) hgt_attention_bwd_kernel(const float* __restrict__ qkv, const int* __restrict__ types,
                                                                 const float* __restrict__ mask,
                                                                 const float* __restrict__ dout, int n, long long pix,
                                                                 int heads, float scale, float* __restrict__ dqkv) {
+    extern __shared__ float hsm[];           // [2][n][n][128]: P, dS (thread-interleaved: conflict free)
     const int C = heads * DH;
     const long long total = pix * heads;
+    float* sP = hsm + threadIdx.x;
+    float* sS = sP + n * n * 128;
+    auto ld = [&](const float* src, float (&v)[DH], float mul) {
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(src + c);
+            v[c] = t.x * mul; v[c + 1] = t.y * mul; v[c + 2] = t.z * mul; v[c + 3] = t.w * mul;
+        }
+    };
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int m = (int)(t % heads);
         const long long p = t / heads;
         for (int i = 0; i < n; ++i) {
             const int ti = types[i];
-            float q[DH], go[DH], dq[DH];
-            const float* qrow = qkv + ((long long)i * pix + p) * 5 * C + m * DH;
-            const float* grow = dout + ((long long)i * pix + p) * C + m * DH;
-#pragma unroll
-            for (int c = 0; c < DH; ++c) {
-                q[c] = qrow[c] * scale;
-                go[c] = grow[c];
-                dq[c] = 0.f;
-            }
-            float s[HGT_MAX_AGENTS], dp[HGT_MAX_AGENTS];
+            float q[DH], go[DH];
+            ld(qkv + ((long long)i * pix + p) * 5 * C + m * DH, q, scale);
+            ld(dout + ((long long)i * pix + p) * C + m * DH, go, 1.f);
             float mx = -INFINITY;
             for (int j = 0; j < n; ++j) {
-                s[j] = -INFINITY;
-                dp[j] = 0.f;
-                if (mask[(long long)j * pix + p] == 0.f) continue;
-                const float* krow = qkv + ((long long)j * pix + p) * 5 * C + (1 + ti) * C + m * DH;
-                const float* vrow = krow + 2 * C;
-                float a = 0.f, b = 0.f;
+                float a = -INFINITY, bsum = 0.f;
+                if (mask[(long long)j * pix + p] != 0.f) {
+                    const float* krow = qkv + ((long long)j * pix + p) * 5 * C + (1 + ti) * C + m * DH;
+                    const float* vrow = krow + 2 * C;
+                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-                for (int c = 0; c < DH; ++c) {
-                    a = fmaf(q[c], krow[c], a);
-                    b = fmaf(go[c], vrow[c], b);
+                    for (int c = 0; c < DH; c += 4) {
+                        const float4 k4 = *reinterpret_cast<const float4*>(krow + c);
+                        const float4 v4 = *reinterpret_cast<const float4*>(vrow + c);
+                        a0 = fmaf(q[c], k4.x, a0); a1 = fmaf(q[c + 1], k4.y, a1);
+                        a0 = fmaf(q[c + 2], k4.z, a0); a1 = fmaf(q[c + 3], k4.w, a1);
+                        b0 = fmaf(go[c], v4.x, b0); b1 = fmaf(go[c + 1], v4.y, b1);
+                        b0 = fmaf(go[c + 2], v4.z, b0); b1 = fmaf(go[c + 3], v4.w, b1);
+                    }
+                    a = a0 + a1;
+                    bsum = b0 + b1;
+                    mx = fmaxf(mx, a);
                 }
-                s[j] = a;
-                dp[j] = b;
-                mx = fmaxf(mx, a);
+                sP[(i * n + j) * 128] = a;
+                sS[(i * n + j) * 128] = bsum;
             }
             float l = 0.f;
             for (int j = 0; j < n; ++j) {
-                s[j] = expf(s[j] - mx);
-                l += s[j];
+                const float e = expf(sP[(i * n + j) * 128] - mx);
+                sP[(i * n + j) * 128] = e;
+                l += e;
             }
             const float inv = 1.f / l;
             float Dv = 0.f;
             for (int j = 0; j < n; ++j) {
-                s[j] *= inv;  // P_ij
-                Dv = fmaf(s[j], dp[j], Dv);
+                const float pj = sP[(i * n + j) * 128] * inv;
+                sP[(i * n + j) * 128] = pj;
+                Dv = fmaf(pj, sS[(i * n + j) * 128], Dv);
             }
-            for (int j = 0; j < n; ++j) {
-                if (s[j] == 0.f) continue;
-                const float ds = s[j] * (dp[j] - Dv);
-                const long long base = ((long long)j * pix + p) * 5 * C + (1 + ti) * C + m * DH;
-                const float* krow = qkv + base;
-                float* dk = dqkv + base;
-                float* dv = dk + 2 * C;
+            float dq[DH];
 #pragma unroll
-                for (int c = 0; c < DH; ++c) {
-                    dq[c] = fmaf(ds, krow[c], dq[c]);
-                    dk[c] += ds * q[c];          // q carries the scale: s = (q * scale) . k'
-                    dv[c] += s[j] * go[c];
+            for (int c = 0; c < DH; ++c) dq[c] = 0.f;
+            for (int j = 0; j < n; ++j) {
+                const float pj = sP[(i * n + j) * 128];
+                const float ds = pj * (sS[(i * n + j) * 128] - Dv);
+                sS[(i * n + j) * 128] = ds;
+                if (pj == 0.f) continue;
+                const float* krow = qkv + ((long long)j * pix + p) * 5 * C + (1 + ti) * C + m * DH;
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(krow + c);
+                    dq[c] = fmaf(ds, k4.x, dq[c]); dq[c + 1] = fmaf(ds, k4.y, dq[c + 1]);
+                    dq[c + 2] = fmaf(ds, k4.z, dq[c + 2]); dq[c + 3] = fmaf(ds, k4.w, dq[c + 3]);
                 }
             }
             float* dqo = dqkv + ((long long)i * pix + p) * 5 * C + m * DH;
 #pragma unroll
-            for (int c = 0; c < DH; ++c) dqo[c] = dq[c] * scale;
+            for (int c = 0; c < DH; c += 4)
+                *reinterpret_cast<float4*>(dqo + c) = make_float4(dq[c] * scale, dq[c + 1] * scale, dq[c + 2] * scale, dq[c + 3] * scale);
+        }
+        for (int j = 0; j < n; ++j) {
+            for (int ty = 0; ty < 2; ++ty) {
+                float dk[DH], dv[DH];
+#pragma unroll
+                for (int c = 0; c < DH; ++c) dk[c] = dv[c] = 0.f;
+                for (int i = 0; i < n; ++i) {
+                    if (types[i] != ty) continue;
+                    const float pj = sP[(i * n + j) * 128];
+                    if (pj == 0.f) continue;
+                    const float ds = sS[(i * n + j) * 128] * scale;   // s = (q * scale) . k'
+                    const float* qrow = qkv + ((long long)i * pix + p) * 5 * C + m * DH;
+                    const float* grow = dout + ((long long)i * pix + p) * C + m * DH;
+#pragma unroll
+                    for (int c = 0; c < DH; c += 4) {
+                        const float4 q4 = *reinterpret_cast<const float4*>(qrow + c);
+                        const float4 g4 = *reinterpret_cast<const float4*>(grow + c);
+                        dk[c] = fmaf(ds, q4.x, dk[c]); dk[c + 1] = fmaf(ds, q4.y, dk[c + 1]);
+                        dk[c + 2] = fmaf(ds, q4.z, dk[c + 2]); dk[c + 3] = fmaf(ds, q4.w, dk[c + 3]);
+                        dv[c] = fmaf(pj, g4.x, dv[c]); dv[c + 1] = fmaf(pj, g4.y, dv[c + 1]);
+                        dv[c + 2] = fmaf(pj, g4.z, dv[c + 2]); dv[c + 3] = fmaf(pj, g4.w, dv[c + 3]);
+                    }
+                }
+                float* dko = dqkv + ((long long)j * pix + p) * 5 * C + (1 + ty) * C + m * DH;
+                float* dvo = dko + 2 * C;
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    *reinterpret_cast<float4*>(dko + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
+                    *reinterpret_cast<float4*>(dvo + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
+                }
+            }
         }
     }
 }
@@ -659,13 +706,19 @@ extern "C" {
 int a2x_hgt_attention_bwd(const float* qkv, const int* types_dev, const float* key_mask, const float* dout, int n_agents,
                           long long pix, int heads, int dim_head, float scale, float* dqkv, a2x_stream_t stream) {
     A2X_REQUIRE(qkv && types_dev && key_mask && dout && dqkv && n_agents > 0 && n_agents <= a2x::HGT_MAX_AGENTS && pix > 0,
-                "hgt_attention_bwd: bad args (at most 16 agents)");
+                "hgt_attention_bwd: bad args (at most 12 agents)");
     cudaStream_t st = (cudaStream_t)stream;
-    A2X_CHECK_CUDA(cudaMemsetAsync(dqkv, 0, (size_t)n_agents * pix * 5 * heads * dim_head * sizeof(float), st));
     long long b = (pix * heads + 127) / 128;
     if (b > 148 * 16) b = 148 * 16;
-    if (dim_head == 32) a2x::hgt_attention_bwd_kernel<32><<<(int)b, 128, 0, st>>>(qkv, types_dev, key_mask, dout, n_agents, pix, heads, scale, dqkv);
-    else if (dim_head == 16) a2x::hgt_attention_bwd_kernel<16><<<(int)b, 128, 0, st>>>(qkv, types_dev, key_mask, dout, n_agents, pix, heads, scale, dqkv);
+    const size_t smem = (size_t)2 * n_agents * n_agents * 128 * sizeof(float);
+    A2X_REQUIRE(smem <= 200 * 1024, "hgt_attention_bwd: %d agents do not fit shared memory", n_agents);
+    if (dim_head == 32) {
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::hgt_attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a2x::hgt_attention_bwd_kernel<32><<<(int)b, 128, smem, st>>>(qkv, types_dev, key_mask, dout, n_agents, pix, heads, scale, dqkv);
+    } else if (dim_head == 16) {
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::hgt_attention_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a2x::hgt_attention_bwd_kernel<16><<<(int)b, 128, smem, st>>>(qkv, types_dev, key_mask, dout, n_agents, pix, heads, scale, dqkv);
+    }
     else {
         a2x::set_error("hgt_attention_bwd: dim_head %d not in {16, 32}", dim_head);
         return 1;

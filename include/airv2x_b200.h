@@ -206,7 +206,7 @@ int a2x_split_attn_fuse(const float* w0, const float* w1, const float* w2, int n
                         const float* fc1, const float* ln_gamma, const float* ln_beta, const float* fc2,
                         float* sums_ws, float* weights_ws, float* x_inout, a2x_stream_t stream);
 
-/* Backward of the V2X-ViT kernels. hgt_attention_bwd: dqkv [n][pix][5C] (zero-filled here) from dout [n][pix][C].
+/* Backward of the V2X-ViT kernels. hgt_attention_bwd: dqkv [n][pix][5C] (every slot written) from dout [n][pix][C].
  * hgt_fold_bwd: gradients of the fused projection (dw_fold [2][5C][C], db_fold [2][5C]) -> typed q/k/v linears (written)
  * and relation_att / relation_msg (written). split_attn_bwd: d(win_r) as three split operands, gradients of fc1 / bn1 /
  * fc2 accumulated with atomics (caller zeroes); sums_saved / weights_saved are the forward's [n][C] pooled sums and
