@@ -231,6 +231,7 @@ class CoBEVTEngine(W2CEngine):
         N = layout["n_total"]
         canvas = self._encode(P, lidar, layout, True, rec)
         self._last_canvas_shape = tuple(canvas.shape)
+        self._last_canvas = canvas
         x = canvas
         cat = None
         for i in range(len(self.layer_nums)):
@@ -489,8 +490,8 @@ class CoBEVTEngine(W2CEngine):
 
     def forward(self, P, lidar, layout, training, k_list=None):
         if training:
-            raise NotImplementedError("Airv2xCoBEVT: train-mode forward(data_dict) is not wired to autograd; use "
-                                      "train_step(data_dict, label_dict) (forward + loss + backward, dropout disabled)")
+            raise NotImplementedError("Airv2xCoBEVT: train-mode forward under torch.no_grad() is not implemented (model.eval() "
+                                      "for inference; model(batch) with grad enabled or train_step() for training)")
         self._begin_step()
         W = self._pack_weights(P)
         feat = self.encode(P, W, lidar, layout)

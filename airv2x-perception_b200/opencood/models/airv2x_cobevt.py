@@ -69,6 +69,24 @@ class _SwapFusionEncoderParams(nn.Module):
                                       nn.Linear(fa["input_dim"], fa["input_dim"]), nn.Identity())
 
 
+class _FusionStep(torch.autograd.Function):
+    """Autograd boundary of the transformer-fusion models: inputs are the trainable parameters, the output is the NHWC
+    head-logit tensor; backward runs the engine's backward_train and hands one gradient per parameter to autograd."""
+
+    @staticmethod
+    def forward(ctx, model, run_forward, names, *params):
+        ctx.model, ctx.names = model, names
+        return run_forward()
+
+    @staticmethod
+    def backward(ctx, dheads):
+        model = ctx.model
+        P = model._param_dict()
+        grads = {n: torch.zeros_like(P[n]) for n in ctx.names}
+        model.engine.backward_train(P, dheads.contiguous(), grads)
+        return (None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
 class Airv2xCoBEVT(Airv2xWhere2com):
     def __init__(self, args, precision="split3"):
         nn.Module.__init__(self)
@@ -108,6 +126,7 @@ class Airv2xCoBEVT(Airv2xWhere2com):
         if args["obj_head"]:
             self.obj_head = nn.Conv2d(self.outC, args["anchor_number"], kernel_size=1)
         self.precision = precision
+        self.dropout = "error"   # "off": train with nn.Dropout disabled (the kernels implement dropout = identity)
         self._engine = None
         self._last_aux = None
 
@@ -131,7 +150,16 @@ class Airv2xCoBEVT(Airv2xWhere2com):
             layout["key_mask"] = torch.tensor([[1] * n + [0] * (L - n) for n in layout["record_len"]], dtype=torch.int32,
                                               device=dev)
         lidar = self._lidar(data_dict, dev, layout)
-        heads, _ = self.engine.forward(self._param_dict(), lidar, layout, self.training)
+        if self.training and torch.is_grad_enabled():
+            # reference training loop (tools/train.py:216-221): model(batch) -> criterion -> loss.backward()
+            if float(self.args["fax_fusion"].get("drop_out", 0.0)) > 0 and self.dropout != "off":
+                raise NotImplementedError("fax_fusion.drop_out > 0: set model.dropout = \"off\" to train with dropout disabled")
+            names = [n for n, p in self.named_parameters() if p.requires_grad]
+            params = [p for n, p in self.named_parameters() if p.requires_grad]
+            eng = self.engine
+            heads = _FusionStep.apply(self, lambda: eng.forward_train(self._param_dict(), lidar, layout), names, *params)
+        else:
+            heads, _ = self.engine.forward(self._param_dict(), lidar, layout, self.training)
         A, K = self.args["anchor_number"], self.args["num_class"]
         nc, nr = A * K, 7 * A
         nchw = heads.permute(0, 3, 1, 2)

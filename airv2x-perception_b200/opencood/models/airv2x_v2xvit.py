@@ -14,6 +14,7 @@ import torch.nn as nn
 
 from ...v2xvit_engine import V2XViTEngine
 from ...w2c_engine import AGENT_TYPES, TYPE_PREFIX
+from .airv2x_cobevt import _FusionStep
 from .airv2x_where2com import Airv2xWhere2com, _backbone_params, _PillarVFEParams, _shrink_params
 
 
@@ -146,6 +147,7 @@ class Airv2xV2XVit(Airv2xWhere2com):
         if args["obj_head"]:
             self.obj_head = nn.Conv2d(self.outC, args["anchor_number"], kernel_size=1)
         self.precision = precision
+        self.dropout = "error"   # "off": train with nn.Dropout disabled (the kernels implement dropout = identity)
         self._engine = None
         self._last_aux = None
 
@@ -164,8 +166,20 @@ class Airv2xV2XVit(Airv2xWhere2com):
             raise RuntimeError("Airv2xV2XVit (B200) needs its parameters on a CUDA device; there is no CPU path")
         layout = self._layout(data_dict, dev)
         lidar = self._lidar(data_dict, dev, layout)
-        heads, aux = self.engine.forward(self._param_dict(), lidar, layout, self.training,
-                                         prior=data_dict["prior_encoding"], scm=data_dict["spatial_correction_matrix"])
+        prior, scm = data_dict["prior_encoding"], data_dict["spatial_correction_matrix"]
+        eng = self.engine
+        if self.training and torch.is_grad_enabled():
+            # reference training loop (tools/train.py:216-221): model(batch) -> criterion -> loss.backward()
+            if max(self._dropouts()) > 0 and self.dropout != "off":
+                raise NotImplementedError("transformer.encoder dropout > 0: set model.dropout = \"off\" to train with "
+                                          "dropout disabled")
+            names = [n for n, p in self.named_parameters() if p.requires_grad]
+            params = [p for n, p in self.named_parameters() if p.requires_grad]
+            heads = _FusionStep.apply(self, lambda: eng.forward_train(self._param_dict(), lidar, layout, prior, scm),
+                                      names, *params)
+            aux = eng.last_aux
+        else:
+            heads, aux = eng.forward(self._param_dict(), lidar, layout, self.training, prior=prior, scm=scm)
         A, K = self.args["anchor_number"], self.args["num_class"]
         nc, nr = A * K, 7 * A
         nchw = heads.permute(0, 3, 1, 2)

@@ -233,6 +233,9 @@ class V2XViTEngine(CoBEVTEngine):
         rec = []
         W = self._pack_weights(P)
         y1, y2, cat = self._encode_train(P, W, lidar, layout, rec)
+        canvas_nz = self._buf("comm_rate", (1,), torch.int64)
+        ops.count_nonzero(self._last_canvas.hi, canvas_nz)
+        self.last_aux = {"comm_rate": canvas_nz}
         enc = self.enc
         ca, pw = enc["cav_att_config"], enc["pwindow_att_config"]
         record_len = layout["record_len"]
@@ -501,8 +504,8 @@ class V2XViTEngine(CoBEVTEngine):
 
     def forward(self, P, lidar, layout, training, prior=None, scm=None):
         if training:
-            raise NotImplementedError("Airv2xV2XVit: train-mode forward(data_dict) is not wired to autograd; use "
-                                      "train_step(data_dict, label_dict) (forward + loss + backward, dropout disabled)")
+            raise NotImplementedError("Airv2xV2XVit: train-mode forward under torch.no_grad() is not implemented (model.eval() "
+                                      "for inference; model(batch) with grad enabled or train_step() for training)")
         self._begin_step()
         W = self._pack_weights(P)
         canvas_nz = self._buf("comm_rate", (1,), torch.int64)

@@ -277,6 +277,20 @@ def test_train_step_matches_oracle_autograd():
     assert len(fusion) > 100 and max(fusion.values()) < 2e-2, sorted(fusion.items(), key=lambda kv: -kv[1])[:5]
     assert float(np.median(list(fusion.values()))) < 2e-3
     assert max(errs.values()) < 0.15 and float(np.median(list(errs.values()))) < 0.05, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    # reference-style use (tools/train.py:216-221): model(batch) -> the reference's loss (torch ops) -> loss.backward()
+    g_step = {n: q.grad.clone() for n, q in model.named_parameters()}
+    model.zero_grad()
+    with pytest.raises(NotImplementedError):   # yaml dropout > 0 needs the explicit opt-out
+        model(C.to_device(dd, "cuda"))
+    model.dropout = "off"
+    out2 = model(C.to_device(dd, "cuda"))
+    cpu_out = {k: out2[k].cpu() for k in ("psm", "rm", "obj")}
+    loss2 = O.point_pillar_loss_multiclass(cpu_out, labels, args["num_class"], cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])[0]
+    assert abs(float(loss2.detach()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
+    loss2.backward()
+    for n, q in model.named_parameters():
+        assert q.grad is not None, n
+        assert float((q.grad - g_step[n]).abs().max()) <= 2e-3 * float(g_step[n].abs().max()) + 1e-7, n
     # a second step reuses every buffer (stale-state check): same loss, same gradients
     g1 = {n: q.grad.clone() for n, q in model.named_parameters()}
     loss3b = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"],
