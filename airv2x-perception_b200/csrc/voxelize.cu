@@ -28,16 +28,27 @@ struct VoxGeom {
     int grid[3];  // nx, ny, nz
 };
 
+// project_points_by_matrix_torch (utils/box_utils.py:1038-1066): [x y z 1] . T^T in fp32. torch's CPU sgemm evaluates the
+// K = 4 dot product as x*T0, then fused multiply-adds in k order (pinned bit-exact in tests/test_gpu_voxelize.py).
+__device__ __forceinline__ float4 vox_project(float4 p, const float* __restrict__ T) {
+    float4 o = p;
+    o.x = __fadd_rn(__fmaf_rn(p.z, T[2], __fmaf_rn(p.y, T[1], __fmul_rn(p.x, T[0]))), T[3]);
+    o.y = __fadd_rn(__fmaf_rn(p.z, T[6], __fmaf_rn(p.y, T[5], __fmul_rn(p.x, T[4]))), T[7]);
+    o.z = __fadd_rn(__fmaf_rn(p.z, T[10], __fmaf_rn(p.y, T[9], __fmul_rn(p.x, T[8]))), T[11]);
+    return o;
+}
+
 __global__ void __launch_bounds__(256) vox_key_kernel(const float* __restrict__ pts, const int* __restrict__ offsets,
-                                                      VoxGeom g, int cells,
+                                                      const float* __restrict__ xf, VoxGeom g, int cells,
                                                       const unsigned char* __restrict__ ego_flags, int strict_range,
                                                       int* __restrict__ keys, int* __restrict__ first,
                                                       int* __restrict__ cnt) {
     const int a = blockIdx.y;
     const int p0 = offsets[a], np = offsets[a + 1] - p0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
-        const float4 p = reinterpret_cast<const float4*>(pts)[p0 + i];
-        const float v[3] = {p.x, p.y, p.z};
+        const float4 p = reinterpret_cast<const float4*>(pts)[p0 + i];   // sensor frame: the ego-box test below uses it
+        const float4 pe = xf != nullptr ? vox_project(p, xf + a * 16) : p;
+        const float v[3] = {pe.x, pe.y, pe.z};
         int c[3];
         bool ok = true;
 #pragma unroll
@@ -311,6 +322,7 @@ __device__ __forceinline__ int bitonic_merge32(int v, int lane) {  // input bito
 }
 
 __global__ void __launch_bounds__(256) vox_gather_kernel(const float* __restrict__ pts, const int* __restrict__ offsets,
+                                                         const float* __restrict__ xf,
                                                          const int* __restrict__ counts, int cap,
                                                          const int* __restrict__ pcount, const int* __restrict__ poff,
                                                          const int* __restrict__ plist, float* __restrict__ voxels,
@@ -334,7 +346,10 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float* __restrict
             best = bitonic_merge32(best, lane);
         }
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (best != INT_MAX) p = reinterpret_cast<const float4*>(pts)[p0 + best];
+        if (best != INT_MAX) {
+            p = reinterpret_cast<const float4*>(pts)[p0 + best];
+            if (xf != nullptr) p = vox_project(p, xf + a * 16);
+        }
         reinterpret_cast<float4*>(voxels)[vi * 32 + lane] = p;
         if (lane == 0) num_points[vi] = min(n, 32);
     }
@@ -360,6 +375,14 @@ int a2x_voxelize(const float* points, const int* offsets_dev, int n_agents, long
                  const float* vsize3, int max_points, int max_voxels, int cap, const unsigned char* ego_flags,
                  int strict_range, void* workspace, size_t workspace_bytes, float* voxels, int* coords, int* num_points,
                  int* counts, a2x_stream_t stream) {
+    return a2x_voxelize_ex(points, offsets_dev, nullptr, n_agents, total_points, range6, vsize3, max_points, max_voxels, cap,
+                           ego_flags, strict_range, workspace, workspace_bytes, voxels, coords, num_points, counts, stream);
+}
+
+int a2x_voxelize_ex(const float* points, const int* offsets_dev, const float* transforms_dev, int n_agents,
+                    long long total_points, const float* range6, const float* vsize3, int max_points, int max_voxels,
+                    int cap, const unsigned char* ego_flags, int strict_range, void* workspace, size_t workspace_bytes,
+                    float* voxels, int* coords, int* num_points, int* counts, a2x_stream_t stream) {
     A2X_REQUIRE(points && offsets_dev && range6 && vsize3 && workspace && voxels && coords && num_points && counts,
                 "voxelize: null argument");
     A2X_REQUIRE(max_points == 32, "voxelize: max_points_per_voxel must be 32 (one warp per pillar)");
@@ -389,7 +412,7 @@ int a2x_voxelize(const float* points, const int* offsets_dev, int n_agents, long
     A2X_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_agents * cells * 4, st));
     A2X_CHECK_CUDA(cudaMemsetAsync(fill, 0, (size_t)n_agents * cap * 4, st));
     dim3 gk(64, n_agents);
-    vox_key_kernel<<<gk, 256, 0, st>>>(points, offsets_dev, g, (int)cells, ego_flags, strict_range, keys, first, cnt);
+    vox_key_kernel<<<gk, 256, 0, st>>>(points, offsets_dev, transforms_dev, g, (int)cells, ego_flags, strict_range, keys, first, cnt);
     A2X_LAUNCHED();
     if (g_debug[11] == 1) {  // reference single-CTA ranking (kept for A/B checks)
         vox_rank_kernel<<<n_agents, 1024, 0, st>>>(offsets_dev, keys, first, cnt, g, (int)cells, cap, max_voxels, cell_vid,
@@ -410,7 +433,7 @@ int a2x_voxelize(const float* points, const int* offsets_dev, int n_agents, long
     vox_fill_kernel<<<gk, 256, 0, st>>>(offsets_dev, keys, cell_vid, (int)cells, cap, poff, fill, plist);
     A2X_LAUNCHED();
     dim3 gg(128, n_agents);
-    vox_gather_kernel<<<gg, 256, 0, st>>>(points, offsets_dev, counts, cap, pcount, poff, plist, voxels, num_points);
+    vox_gather_kernel<<<gg, 256, 0, st>>>(points, offsets_dev, transforms_dev, counts, cap, pcount, poff, plist, voxels, num_points);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -223,7 +223,11 @@ class Airv2xWhere2com(nn.Module):
             # B200 extension of the boundary: raw per-agent clouds instead of CPU-voxelised pillars.
             # raw_points = {"points": [sum P, 4] f32 (all agents, scene-major order), "offsets": int32 [N+1],
             #               optional "preprocess": hypes["preprocess"], optional "filter": True -> apply the dataset's
-            #               mask_ego_points (first agent of every scene) + mask_points_by_range on the GPU}
+            #               mask_ego_points + mask_points_by_range on the GPU, optional "transforms": [N,4,4] agent -> ego
+            #               poses (the dataset's `transformation_matrix`, intermediate_fusion_dataset.py:592-600)}
+            # With "transforms" the clouds are in each agent's SENSOR frame, as the dataset holds them: every agent's own
+            # body box is removed, then the points are projected, then range-filtered (the reference's order). Without,
+            # the clouds are already in the ego frame and only the ego agent's body box (first agent of a scene) is.
             pre = raw.get("preprocess")
             first = next(iter(layout["agent_map"]))
             la = self.args[first]["lidar"]
@@ -232,11 +236,17 @@ class Airv2xWhere2com(nn.Module):
             mp = pre["args"]["max_points_per_voxel"] if pre else 32
             mv = (pre["args"]["max_voxel_train" if self.training else "max_voxel_test"] if pre
                   else (32000 if self.training else 70000))
+            xf = raw.get("transforms")
+            if xf is not None:  # float64 numpy / torch poses -> fp32, like check_numpy_to_torch(...).float()
+                xf = torch.as_tensor(xf).to(device=device, dtype=torch.float32).contiguous()
+                assert xf.shape == (layout["n_total"], 4, 4), "raw_points['transforms'] must be [N, 4, 4]"
             return {"raw": {"points": raw["points"].to(device=device, dtype=torch.float32, non_blocking=True).contiguous(),
                             "offsets": raw["offsets"].to(device=device, dtype=torch.int32, non_blocking=True).contiguous(),
                             "types": layout["types"], "voxel_size": vs, "lidar_range": rng, "max_points": mp,
                             "max_voxels": mv, "filter": bool(raw.get("filter", False)),
-                            "ego_flags": layout["ego_flags"] if raw.get("filter", False) else None}}
+                            "transforms": xf,
+                            "ego_flags": (None if not raw.get("filter", False) else
+                                          torch.ones_like(layout["ego_flags"]) if xf is not None else layout["ego_flags"])}}
         out = {}
         for t in layout["agent_map"]:
             d = data_dict[t]["batch_merged_lidar_features_torch"]
@@ -310,6 +320,8 @@ class Airv2xWhere2com(nn.Module):
 
         dev = next(self.parameters()).device
         raw = data_dict["raw_points"]
+        if raw.get("transforms") is not None:
+            raise NotImplementedError("CUDA-graph replay takes ego-frame clouds; use train_step() with raw_points['transforms']")
         layout = self._layout(data_dict, dev)
         P = int(raw["points"].shape[0])
         graphs = self.__dict__.setdefault("_graphs", {})
@@ -341,6 +353,8 @@ class Airv2xWhere2com(nn.Module):
         assert self.training and data_dict.get("raw_points") is not None
         dev = next(self.parameters()).device
         raw = data_dict["raw_points"]
+        if raw.get("transforms") is not None:
+            raise NotImplementedError("CUDA-graph replay takes ego-frame clouds; use train_step() with raw_points['transforms']")
         layout = self._layout(data_dict, dev)
         P = int(raw["points"].shape[0])
         graphs = self.__dict__.setdefault("_graphs", {})

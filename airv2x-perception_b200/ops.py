@@ -549,11 +549,14 @@ def voxelize_workspace_bytes(n_agents, total_points, nx, ny, nz, cap):
 
 
 def voxelize(points, offsets_dev, n_agents, lidar_range, voxel_size, max_points, max_voxels, cap, workspace, voxels,
-             coords, num_points, counts, ego_flags=None, strict_range=False):
-    """points: [total,4] f32 device; offsets_dev: int32 [n_agents+1] device. Slab outputs (see include/airv2x_b200.h)."""
+             coords, num_points, counts, ego_flags=None, strict_range=False, transforms=None):
+    """points: [total,4] f32 device; offsets_dev: int32 [n_agents+1] device; transforms: optional [n_agents,4,4] f32 device
+    (agent -> ego projection applied before the range test). Slab outputs (see include/airv2x_b200.h)."""
     rng = (c_f * 6)(*[float(v) for v in lidar_range])
     vs = (c_f * 3)(*[float(v) for v in voxel_size])
-    call("a2x_voxelize", _ptr(points), _ptr(offsets_dev), c_int(n_agents), c_ll(points.shape[0]), rng, vs,
+    if transforms is not None:
+        assert transforms.shape == (n_agents, 4, 4) and transforms.dtype == torch.float32 and transforms.is_contiguous()
+    call("a2x_voxelize_ex", _ptr(points), _ptr(offsets_dev), _ptr(transforms), c_int(n_agents), c_ll(points.shape[0]), rng, vs,
          c_int(max_points), c_int(max_voxels), c_int(cap), _ptr(ego_flags), c_int(int(strict_range)), _ptr(workspace),
          ctypes.c_size_t(workspace.numel()),
          _ptr(voxels), _ptr(coords), _ptr(num_points), _ptr(counts), stream_ptr())

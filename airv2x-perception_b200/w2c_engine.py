@@ -268,7 +268,7 @@ class W2CEngine:
         counts = self._buf("vox.counts", (N,), torch.int32)
         ops.voxelize(pts, raw["offsets"], N, raw["lidar_range"], raw["voxel_size"], int(raw["max_points"]), cap, cap, ws,
                      vox, coords, num, counts, ego_flags=raw.get("ego_flags"),
-                     strict_range=bool(raw.get("filter", False)))
+                     strict_range=bool(raw.get("filter", False)), transforms=raw.get("transforms"))
         ident = layout.get("identity_map")
         out = {}
         for t in AGENT_TYPES:

@@ -316,6 +316,16 @@ int a2x_voxelize(const float* points, const int* offsets_dev, int n_agents, long
                  const float* vsize3, int max_points, int max_voxels, int cap, const unsigned char* ego_flags,
                  int strict_range, void* workspace, size_t workspace_bytes, float* voxels, int* coords, int* num_points,
                  int* counts, a2x_stream_t stream);
+/* Same, with the dataset's agent -> ego projection folded in (project_points_by_matrix_torch, utils/box_utils.py:1038-1066,
+ * called between mask_ego_points and mask_points_by_range at
+ * data_utils/datasets/airv2x/intermediate_fusion_dataset.py:592-600): transforms_dev [n_agents][4][4] f32 row-major
+ * (device, may be NULL = identity, no arithmetic). Points arrive in each agent's sensor frame; the ego-box test uses the
+ * sensor-frame coordinates, the range test / voxel index / stored pillar points the projected ones, bit-exact with
+ * torch's fp32 evaluation of the reference's einsum. */
+int a2x_voxelize_ex(const float* points, const int* offsets_dev, const float* transforms_dev, int n_agents,
+                    long long total_points, const float* range6, const float* vsize3, int max_points, int max_voxels,
+                    int cap, const unsigned char* ego_flags, int strict_range, void* workspace, size_t workspace_bytes,
+                    float* voxels, int* coords, int* num_points, int* counts, a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- PillarVFE + PointPillarScatter
  * Replace PillarVFE.forward / PFNLayer.forward / PointPillarScatter.forward

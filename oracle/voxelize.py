@@ -117,3 +117,33 @@ def mask_points(points, lidar_range, ego_box=True):
     r = lidar_range
     keep = (p[:, 0] > r[0]) & (p[:, 0] < r[3]) & (p[:, 1] > r[1]) & (p[:, 1] < r[4]) & (p[:, 2] > r[2]) & (p[:, 2] < r[5])
     return p[keep]
+
+
+def project_points(points, transformation_matrix):
+    """utils/box_utils.py:1038-1066 (project_points_by_matrix_torch) as the dataset calls it on `lidar_np[:, :3]`
+    (data_utils/datasets/airv2x/intermediate_fusion_dataset.py:592-600): numpy inputs go through
+    `torch.from_numpy(x).float()` (common_utils.py:36-39), the points are padded with a homogeneous 1 and contracted
+    with the 4x4 matrix by torch.einsum in fp32. Restated with the same torch calls, so the fp32 evaluation order is
+    torch's own (x*T0 then fused multiply-adds in k order for clouds of >= 100 points on this image's CPU sgemm).
+    points: [P, 4] (x, y, z, intensity) -> [P, 4] fp32 with xyz projected."""
+    import torch
+    import torch.nn.functional as F
+
+    p = np.asarray(points, dtype=np.float32).copy()
+    if p.shape[0] == 0:
+        return p
+    xyz = torch.from_numpy(p[:, :3].copy()).float()
+    T = torch.from_numpy(np.asarray(transformation_matrix)).float()
+    hom = F.pad(xyz, (0, 1), mode="constant", value=1)
+    p[:, :3] = torch.einsum("ik, jk->ij", hom, T)[:, :3].numpy()
+    return p
+
+
+def dataset_points(points, transformation_matrix, lidar_range):
+    """get_item_single_car's cloud pipeline (intermediate_fusion_dataset.py:590-600) without the random shuffle:
+    mask_ego_points (sensor frame) -> project to the ego frame -> mask_points_by_range."""
+    p = np.asarray(points, dtype=np.float32)
+    keep = ~((p[:, 0] >= -1.95) & (p[:, 0] <= 2.95) & (p[:, 1] >= -1.1) & (p[:, 1] <= 1.1))
+    p = project_points(p[keep], transformation_matrix)
+    return mask_points(p, lidar_range, ego_box=False)
+

@@ -66,6 +66,56 @@ def test_raw_point_path_equals_voxel_dict_path(small):
     assert a["comm_rate"] == b["comm_rate"]
 
 
+def test_sensor_frame_clouds_with_poses_equal_the_dataset_pipeline(small):
+    """raw_points with "transforms": the dataset's whole per-agent cloud pipeline (own-body box, agent -> ego projection,
+    range filter, voxelisation, collate) on the GPU == the same pipeline on the CPU (oracle) fed as the reference dict."""
+    import math
+
+    from oracle import voxelize as V
+
+    cfg, gold, model, sd, dd = small
+    model.load_state_dict(sd)
+    model.eval()
+    pre = cfg["preprocess"]
+    rng = pre["cav_lidar_range"]
+    agents = [str(a) for a in gold["agents"]]
+    g = np.random.default_rng(11)
+    clouds, poses = [], []
+    for k in range(len(agents)):
+        c = O.synth_points(900 + k, int(gold["n_points"]), rng, (10.0, 5.0))
+        yaw = 0.0 if k == 0 else g.uniform(-math.pi, math.pi)
+        T = np.eye(4)
+        T[:2, :2] = [[math.cos(yaw), -math.sin(yaw)], [math.sin(yaw), math.cos(yaw)]]
+        if k:
+            T[:3, 3] = [g.uniform(-6, 6), g.uniform(-3, 3), g.uniform(-0.2, 0.2)]
+        clouds.append(c)
+        poses.append(T)
+    mv = pre["args"]["max_voxel_test"]
+    ref_dd, k = {}, 0
+    for t in O.AGENT_TYPES:
+        ids = [i for i, a in enumerate(agents) if a == t]
+        if not ids:
+            ref_dd[t] = {"batch_merged_lidar_features_torch": None, "record_len": torch.tensor([0], dtype=torch.int32), "batch_idxs": []}
+            continue
+        per = [V.voxelize(V.dataset_points(clouds[i], poses[i], rng), rng, pre["args"]["voxel_size"],
+                          pre["args"]["max_points_per_voxel"], mv) for i in ids]
+        ref_dd[t] = {"batch_merged_lidar_features_torch": {k2: torch.from_numpy(v) for k2, v in V.collate(per).items()},
+                     "record_len": torch.tensor([len(ids)], dtype=torch.int32), "batch_idxs": [0]}
+    ref_dd["record_len"] = torch.tensor([len(agents)], dtype=torch.int32)
+    offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    raw = {"raw_points": {"points": torch.from_numpy(np.concatenate(clouds, 0)), "offsets": torch.from_numpy(offs),
+                          "preprocess": pre, "filter": True, "transforms": np.stack(poses)}}
+    for t in O.AGENT_TYPES:
+        n = sum(1 for a in agents if a == t)
+        raw[t] = {"record_len": [n], "batch_idxs": [0] if n else []}
+    with torch.no_grad():
+        a = model(raw)
+        b = model(C.to_device(ref_dd, "cuda"))
+    for key in ("psm", "rm", "obj"):
+        assert torch.equal(a[key], b[key]), key
+    assert a["comm_rate"] == b["comm_rate"] and a["comm_rate"] > 0
+
+
 def test_train_step_matches_reference_golden(small):
     """Train-mode forward / loss / gradients against the reference. The train-mode communication mask is a top-K over
     a map whose neighbouring values differ by ~1e-6 (where2comm_fuse.py:104-121), so a perturbation far below the 1e-3

@@ -81,3 +81,53 @@ def test_baseline_size(ops):
     clouds = [bench.synth_cloud(k, 60000, rng) for k in range(5)]
     check(ops, clouds, rng, vs, 32000, True)                   # train cap is hit with 60k points
     check(ops, clouds[:2], rng, vs, 70000, False)
+
+
+def test_sensor_frame_clouds_with_agent_to_ego_projection(ops):
+    """a1 complete: every agent's body box removed in its sensor frame, projection by the dataset's 4x4 pose (fp32, the
+    evaluation order of torch's einsum), strict range filter, voxelisation — bit-exact against the oracle pipeline."""
+    import math
+
+    import bench
+    from oracle import voxelize as V
+
+    cfg = bench.load_config()
+    rng, vs = cfg["preprocess"]["cav_lidar_range"], cfg["preprocess"]["args"]["voxel_size"]
+    g = np.random.default_rng(5)
+    n, P = 4, 40000
+    clouds, poses = [], []
+    for a in range(n):
+        c = np.stack([g.normal(0, 30, P), g.normal(0, 14, P), g.uniform(-3.5, 1.5, P), g.uniform(0, 1, P)], 1).astype(np.float32)
+        c[:200, :2] = g.uniform(-1.0, 1.0, (200, 2)).astype(np.float32)       # returns from the carrier's own body
+        yaw, pitch = g.uniform(-math.pi, math.pi), g.uniform(-0.03, 0.03)
+        T = np.eye(4)
+        cy, sy, cp, sp = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch)
+        T[:3, :3] = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]]) @ np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+        T[:3, 3] = [g.uniform(-40, 40), g.uniform(-15, 15), g.uniform(-0.5, 0.5)]
+        if a == 0:
+            T = np.eye(4)                                                       # the ego agent
+        clouds.append(c)
+        poses.append(T)
+    offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    grid = [int(round((rng[3 + j] - rng[j]) / vs[j])) for j in range(3)]
+    cap = 32000
+    ws = torch.empty(ops.voxelize_workspace_bytes(n, int(offs[-1]), grid[0], grid[1], grid[2], cap), dtype=torch.uint8, device="cuda")
+    vox = torch.full((n * cap, 32, 4), 7.0, device="cuda")
+    coords = torch.full((n * cap, 4), -9, dtype=torch.int32, device="cuda")
+    num = torch.full((n * cap,), -9, dtype=torch.int32, device="cuda")
+    counts = torch.full((n,), -9, dtype=torch.int32, device="cuda")
+    xf = torch.from_numpy(np.stack(poses)).float().cuda().contiguous()
+    ops.voxelize(torch.from_numpy(np.concatenate(clouds, 0)).cuda(), torch.from_numpy(offs).cuda(), n, rng, vs, 32, cap, cap, ws,
+                 vox, coords, num, counts, ego_flags=torch.ones(n, dtype=torch.uint8, device="cuda"), strict_range=True,
+                 transforms=xf)
+    torch.cuda.synchronize()
+    vox, coords = vox.cpu().numpy().reshape(n, cap, 32, 4), coords.cpu().numpy().reshape(n, cap, 4)
+    num, counts = num.cpu().numpy().reshape(n, cap), counts.cpu().numpy()
+    for a in range(n):
+        o = V.voxelize(V.dataset_points(clouds[a], poses[a], rng), rng, vs, 32, cap)
+        m = o["voxel_features"].shape[0]
+        assert m > 1000 and counts[a] == m, (a, counts[a], m)
+        assert np.array_equal(coords[a, :m, 1:], o["voxel_coords"])
+        assert np.array_equal(num[a, :m], o["voxel_num_points"])
+        assert np.array_equal(vox[a, :m].view(np.uint32), o["voxel_features"].view(np.uint32))
+
