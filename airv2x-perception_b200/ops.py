@@ -671,3 +671,14 @@ def rte_bwd(dvec_sums, emb_table, emb_idx, lin_w, dlin_w, dlin_b, demb):
     n = emb_idx.numel()
     call("a2x_rte_bwd", _ptr(dvec_sums), c_int(n), c_int(lin_w.shape[0]), _ptr(emb_table), _ptr(emb_idx), _ptr(lin_w),
          _ptr(dlin_w), _ptr(dlin_b), _ptr(demb), stream_ptr())
+
+
+# label generation -------------------------------------------------------------------------------------------------------
+def assign_targets(anchor_standup, anchors, gt_standup, gt_boxes, gt_class, gt_offsets, B, pos_threshold, neg_threshold,
+                   code_ws, best_ws, targets, pos, neg, class_ids):
+    """see include/airv2x_b200.h: a2x_assign_targets"""
+    call("a2x_assign_targets", _ptr(anchor_standup), _ptr(anchors), c_int(anchors.shape[0]), _ptr(gt_standup), _ptr(gt_boxes),
+         _ptr(gt_class), _ptr(gt_offsets), c_int(0 if gt_boxes is None else gt_boxes.shape[0]), c_int(B),
+         c_f(float(pos_threshold)), c_f(float(neg_threshold)), _ptr(code_ws), _ptr(best_ws), _ptr(targets), _ptr(pos),
+         _ptr(neg), _ptr(class_ids), stream_ptr())
+

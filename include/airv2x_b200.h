@@ -301,6 +301,20 @@ int a2x_sums_to_float(const double* sums, int C, float* out, int accumulate, a2x
 /* torch.count_nonzero (airv2x_where2com.py:122) */
 int a2x_count_nonzero(const float* x, long long n, unsigned long long* out, a2x_stream_t stream);
 
+/* ---------------------------------------------------------------- anchor-target assignment (label generation)
+ * Replaces VoxelPostprocessor.generate_label_airv2x + collate_batch_airv2x
+ * (opencood/data_utils/post_processor/voxel_postprocessor.py:217-354, :392-430) and bbox_overlaps
+ * (opencood/utils/box_overlaps.pyx:17-56) for a batch of B samples. anchor_standup [N][4] f32 / gt_standup [total_gt][4]
+ * f32: axis-aligned (xmin, ymin, xmax, ymax) footprints of the rotated boxes (host: labels.py, the reference's fp32
+ * corner arithmetic); anchors [N][7] f64 (x,y,z,h,w,l,yaw), N = H*W*A in (h, w, a) order; gt_boxes [total_gt][7] f64 and
+ * gt_class [total_gt]: the valid boxes of every sample back to back, gt_offsets_dev [B+1]. Outputs in the layout
+ * a2x_det_loss reads: targets [B][N][7] f32, pos_equal_one / neg_equal_one [B][N] f32, class_ids [B][N] i32.
+ * Workspaces: code_ws [B][N] i32, best_ws [max(total_gt,1)] u64. */
+int a2x_assign_targets(const float* anchor_standup, const double* anchors, int n_anchors, const float* gt_standup,
+                       const double* gt_boxes, const int* gt_class, const int* gt_offsets_dev, int total_gt, int B,
+                       float pos_threshold, float neg_threshold, int* code_ws, unsigned long long* best_ws, float* targets,
+                       float* pos_equal_one, float* neg_equal_one, int* class_ids, a2x_stream_t stream);
+
 /* ---------------------------------------------------------------- voxelisation
  * Replaces SpVoxelPreprocessor.preprocess -> spconv Point2VoxelCPU3d.point_to_voxel + collate_batch
  * (opencood/data_utils/pre_processor/sp_voxel_preprocessor.py:59-72, :96-116, :142-175), bit-exact with the
