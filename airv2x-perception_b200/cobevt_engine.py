@@ -55,6 +55,14 @@ class CoBEVTEngine(W2CEngine):
         self.side = None
         self.use_side_stream = False
 
+    # shrink header geometry / head rows: overridden by the legacy (`point_pillar_*`) engines
+    shrink_k0 = 1        # kernel of shrink_conv.layers.0.double_conv.0 (airv2x yaml: 1x1 s1; legacy yamls: 3x3 s2)
+    shrink_stride = 1
+
+    def _head_rows(self):
+        nc, nr = self.A * self.K, 7 * self.A
+        return (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr))
+
     # ------------------------------------------------------------------ weights (one batched pack per step)
     def _linear_names(self):
         names = []
@@ -103,7 +111,7 @@ class CoBEVTEngine(W2CEngine):
             ci, co = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (1, s * s * co, ci), (s * s, ci, co))
             jobs.append(ops.deconv_pack_job(w, W[name]))
-        for idx, k in ((0, 1), (2, 3)):
+        for idx, k in ((0, self.shrink_k0), (2, 3)):
             name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
             w = P[name]
             co, ci = w.shape[0], w.shape[1]
@@ -120,14 +128,13 @@ class CoBEVTEngine(W2CEngine):
             co, ci = w.shape
             W[name] = self._packed(name, (1, co, ci), (1, ci, co))
             jobs.append(ops.conv_pack_job(w.view(co, ci, 1, 1), W[name]))
-        nc, nr = self.A * self.K, 7 * self.A
         fresh = ("packed", "heads") not in self.bufs
         hp = self._packed("heads", (1, HEAD_PAD, self.c_shrink), (1, self.c_shrink, HEAD_PAD))
         hb = self._buf("heads.b", (HEAD_PAD,))
         if fresh:
             for t in (hp.f32, hp.f16, hp.d32, hp.d16, hb):
                 t.zero_()
-        for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+        for name, row0 in self._head_rows():
             jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0))
             jobs.append(ops.copy_pack_job(P[name + ".bias"], hb, row0))
         W["heads"] = hp
@@ -197,6 +204,8 @@ class CoBEVTEngine(W2CEngine):
                 cat = self._act("E.cat", (N, h2, w2, self.c_cat))
             c0 = sum(self.up_filters[:i])
             self._deblock(P, W, i, x, cat.slice_c(c0, c0 + self.up_filters[i]), False, 0, "E", None)
+        s = self.shrink_stride
+        h2, w2 = (h2 - 1) // s + 1, (w2 - 1) // s + 1
         y1 = self._act("E.s1", (N, h2, w2, self.c_shrink))
         if self.compression:
             y2a = self._act("E.s2c", (N, h2, w2, self.c_shrink))
@@ -204,7 +213,7 @@ class CoBEVTEngine(W2CEngine):
             y2 = out if out is not None else self._buf("E.s2", (N, h2, w2, self.c_shrink))
             assert tuple(y2.shape) == (N, h2, w2, self.c_shrink)
             y2a = Act(y2)
-        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,
+        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], self.shrink_k0, s, y1,
                      shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
         ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, y2a,
                      shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
@@ -244,6 +253,7 @@ class CoBEVTEngine(W2CEngine):
                 self._deblock(P, W, i, x, cat.slice_c(c0, c0 + self.up_filters[i]), True, 1, "E", rec)
         self._join_side()
         assert not self.compression, "NaiveCompressor training is not implemented"
+        assert self.shrink_k0 == 1 and self.shrink_stride == 1, "training of the legacy shrink header is not implemented"
         y1 = self._act("E.s1", (N, h2, w2, self.c_shrink))
         y2 = self._buf("E.s2", (N, h2, w2, self.c_shrink))
         ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,

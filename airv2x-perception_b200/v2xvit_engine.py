@@ -84,7 +84,7 @@ class V2XViTEngine(CoBEVTEngine):
             ci, co = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (1, s * s * co, ci), (s * s, ci, co))
             jobs.append(ops.deconv_pack_job(w, W[name]))
-        for idx, k in ((0, 1), (2, 3)):
+        for idx, k in ((0, self.shrink_k0), (2, 3)):
             name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
             w = P[name]
             co, ci = w.shape[0], w.shape[1]
@@ -115,14 +115,19 @@ class V2XViTEngine(CoBEVTEngine):
                 lin("%s.fn.pwmsa.%d.to_out.0.weight" % (pwp, lv), P["%s.fn.pwmsa.%d.to_out.0.weight" % (pwp, lv)])
             lin(lp + ".1.fn.net.0.weight", P[lp + ".1.fn.net.0.weight"])
             lin(lp + ".1.fn.net.3.weight", P[lp + ".1.fn.net.3.weight"])
-        nc, nr = self.A * self.K, 7 * self.A
+        if self.compression:
+            for name in self._compressor_convs():
+                w = P[name + ".weight"]
+                co, ci = w.shape[0], w.shape[1]
+                W[name] = self._packed(name, (9, co, ci), (9, ci, co))
+                jobs.append(ops.conv_pack_job(w, W[name]))
         fresh = ("packed", "heads") not in self.bufs
         hp = self._packed("heads", (1, HEAD_PAD, self.c_shrink), (1, self.c_shrink, HEAD_PAD))
         hb = self._buf("heads.b", (HEAD_PAD,))
         if fresh:
             for t in (hp.f32, hp.f16, hp.d32, hp.d16, hb):
                 t.zero_()
-        for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+        for name, row0 in self._head_rows():
             jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0))
             jobs.append(ops.copy_pack_job(P[name + ".bias"], hb, row0))
         W["heads"] = hp

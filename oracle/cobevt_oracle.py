@@ -140,3 +140,34 @@ def cobevt_forward(sd, args, data_dict, training=False, keep=None):
     if args["obj_head"]:
         out["obj"] = F.conv2d(fused, sd["obj_head.weight"], sd["obj_head.bias"])
     return out, buffers
+
+
+def _legacy_encoder(sd, args, data_dict, training, buffers):
+    """the shared front of the legacy `point_pillar_*` models (point_pillar_cobevt.py:76-106): one PillarVFE, scatter,
+    backbone, 3x3 stride-2 shrink header, optional NaiveCompressor. Returns (features [N,256,h,w], comm_rate)."""
+    lid = data_dict[args.get("use_modality", "processed_lidar")]
+    record_len = data_dict["record_len"]
+    pf, _ = O.pillar_vfe(sd, "pillar_vfe", lid["voxel_features"], lid["voxel_num_points"], lid["voxel_coords"],
+                         args["voxel_size"], args["lidar_range"], training, buffers)
+    nx, ny, _ = [int(v) for v in args["point_pillar_scatter"]["grid_size"]]
+    sf = O.scatter(pf, lid["voxel_coords"], nx, ny, int(record_len.sum()))
+    comm_rate = int(sf.count_nonzero().item())
+    feat = O.backbone_forward(sd, args["base_bev_backbone"], sf, training, buffers)
+    if "shrink_header" in args:
+        feat = O.shrink_conv(sd, args["shrink_header"], feat)
+    if args["compression"] > 0:
+        feat = naive_compressor(sd, feat, training, buffers)
+    return feat, comm_rate, (ny, nx)
+
+
+def pp_cobevt_forward(sd, args, data_dict, training=False, keep=None):
+    """models/point_pillar_cobevt.py:76-128 (`point_pillar_cobevt`; dropout = identity)"""
+    buffers = {}
+    feat, comm_rate, _ = _legacy_encoder(sd, args, data_dict, training, buffers)
+    x, mask = regroup(feat, data_dict["record_len"].tolist(), args["max_cav"])
+    H, W = x.shape[3], x.shape[4]
+    com_mask = mask[:, None, None, None, :].expand(-1, H, W, 1, -1)
+    fused = swap_fusion_encoder(sd, args["fax_fusion"], x, com_mask, keep=keep)
+    return {"psm": F.conv2d(fused, sd["cls_head.weight"], sd["cls_head.bias"]),
+            "rm": F.conv2d(fused, sd["reg_head.weight"], sd["reg_head.bias"]),
+            "mask": 0, "each_mask": 0, "comm_rate": comm_rate}, buffers

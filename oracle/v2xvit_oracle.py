@@ -212,3 +212,34 @@ def v2xvit_forward(sd, args, data_dict, training=False, keep=None):
         out["obj"] = F.conv2d(fused, sd["obj_head.weight"], sd["obj_head.bias"])
     out["comm_rate"] = comm_rate
     return out, buffers
+
+
+def pp_v2xvit_forward(sd, args, data_dict, training=False, keep=None):
+    """models/point_pillar_v2xvit.py:82-185 (`point_pillar_v2xvit`; dropout = identity): legacy encoder, regroup, zero
+    prior encoding, every agent's map resampled into the ego frame by pairwise_t_matrix[b, 0] (warp_affine_simple:
+    F.affine_grid / F.grid_sample, align_corners False, torch_transformation_utils.py:327-334; normalisation with the
+    pillar canvas' H, W and downsample_rate 1, :140-156), V2XTransformer with an identity spatial correction."""
+    buffers = {}
+    feat, comm_rate, (H, W) = CO._legacy_encoder(sd, args, data_dict, training, buffers)
+    L = args["max_cav"]
+    x, mask = CO.regroup(feat, data_dict["record_len"].tolist(), L)                     # (B,L,C,h,w)
+    B, _, C, h, w = x.shape
+    x = torch.cat([x, torch.zeros(B, L, 3, h, w)], 2)
+    t = data_dict["pairwise_t_matrix"][:, :, :, [0, 1], :][:, :, :, :, [0, 1, 3]].clone().float()
+    dr = args["voxel_size"][0]
+    t[..., 0, 1] = t[..., 0, 1] * H / W
+    t[..., 1, 0] = t[..., 1, 0] * W / H
+    t[..., 0, 2] = t[..., 0, 2] / (1 * dr * W) * 2
+    t[..., 1, 2] = t[..., 1, 2] / (1 * dr * H) * 2
+    out = []
+    for b in range(B):
+        grid = F.affine_grid(t[b, 0], [L, C + 3, h, w], align_corners=False)
+        out.append(F.grid_sample(x[b], grid, align_corners=False))
+    x = torch.stack(out).permute(0, 1, 3, 4, 2)
+    if keep is not None:
+        keep["warped"] = x
+    scm = torch.eye(4).expand(B, L, 4, 4)
+    fused = v2x_encoder(sd, args["transformer"]["encoder"], x, mask, scm, keep=keep).permute(0, 3, 1, 2)
+    return {"psm": F.conv2d(fused, sd["cls_head.weight"], sd["cls_head.bias"]),
+            "rm": F.conv2d(fused, sd["reg_head.weight"], sd["reg_head.bias"]),
+            "mask": 0, "each_mask": 0, "comm_rate": comm_rate}, buffers
