@@ -364,6 +364,8 @@ def roofline_pass(model, libmod, dd, lab, cw, rc, precision, torch):
     for name, cargs, e0, e1 in prof:
         ms = e0.elapsed_time(e1)
         total_ms += ms
+        if name.endswith("_ex"):     # a2x_conv2d_fwd_ex / a2x_conv2d_dgrad_ex: same kernels, extended epilogue arguments
+            name = name[:-3]
         g = groups.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0})
         g["ms"] += ms
         g["calls"] += 1
