@@ -52,7 +52,7 @@ def pillar_vfe(sd, prefix, voxel_features, voxel_num_points, coords, voxel_size,
     f_center[:, :, 2] = vf[:, :, 2] - (coords[:, 1].to(vf.dtype).unsqueeze(1) * vz + z_off)
     feats = torch.cat([vf, f_cluster, f_center], dim=-1)  # use_absolute_xyz, no distance
     t = vf.shape[1]
-    mask = (voxel_num_points.int().unsqueeze(1) > torch.arange(t, dtype=torch.int32).view(1, -1)).unsqueeze(-1)
+    mask = (voxel_num_points.int().unsqueeze(1) > torch.arange(t, dtype=torch.int32, device=vf.device).view(1, -1)).unsqueeze(-1)
     feats = feats * mask.type_as(vf)
     x = F.linear(feats, sd[prefix + ".pfn_layers.0.linear.weight"])          # [M,32,64]
     x = _bn(x.permute(0, 2, 1), sd, prefix + ".pfn_layers.0.norm", training, buffers).permute(0, 2, 1)
@@ -66,7 +66,7 @@ def scatter(pillar_features, coords, nx, ny, n_agents):
     c = pillar_features.shape[1]
     out = []
     for b in range(n_agents):
-        canvas = torch.zeros(c, nx * ny, dtype=pillar_features.dtype)
+        canvas = torch.zeros(c, nx * ny, dtype=pillar_features.dtype, device=pillar_features.device)
         m = coords[:, 0] == b
         tc = coords[m]
         idx = (tc[:, 1] + tc[:, 2] * nx + tc[:, 3]).long()
@@ -170,7 +170,7 @@ def communication(sd, comm_args, psm_single, record_len, training, keep=None):
             K = int(H * W * random.uniform(0, 1))
             flat = maps.reshape(L, H * W)
             _, idx = torch.topk(flat, k=K, sorted=False)
-            mask = torch.zeros_like(flat).scatter(-1, idx, torch.ones(L, K)).reshape(L, 1, H, W)
+            mask = torch.zeros_like(flat).scatter(-1, idx, torch.ones(L, K, device=flat.device)).reshape(L, 1, H, W)
         elif thr:
             mask = (maps > thr).to(maps.dtype)
         else:
@@ -280,7 +280,7 @@ def point_pillar_loss_multiclass(output, target, num_class, cls_weight=1.0, reg_
     reg_weights = reg_weights / torch.clamp(pos_norm, min=1.0)
     cls_weights = cls_weights / torch.clamp(pos_norm, min=1.0)
     cls_targets = target["class_ids"]
-    one_hot = torch.zeros(*cls_targets.shape, num_class, dtype=cls_preds.dtype)
+    one_hot = torch.zeros(*cls_targets.shape, num_class, dtype=cls_preds.dtype, device=cls_preds.device)
     one_hot.scatter_(-1, cls_targets.unsqueeze(-1).long(), 1.0)
     _, H, W, AC = cls_preds.shape
     A = AC // num_class
