@@ -8,8 +8,9 @@
 Mirrors opencood/models/airv2x_cobevt.py:112-156 and cobevt_modules/swap_fusion_modules.py:130-280. The encoder half
 is shared with the Where2comm engine (same kernels); every nn.Linear is the 1x1 tcgen05 tap-GEMM (bf16x3 split, bias /
 GELU / residual add fused in the epilogue), LayerNorm and the window / grid attention are token kernels
-(csrc/transformer.cu). Forward only in this round (eval-mode parity); the backward of the transformer block is a
-"next" row.
+(csrc/transformer.cu). forward() is the eval path; forward_train() / backward_train() are the training step (dropout =
+identity): saved activations per sublayer, 1x1 tap-GEMM dgrad / wgrad, LayerNorm / GELU / window-attention backward
+kernels, then the shared encoder backward (_encoder_backward, also used by the V2X-ViT engine).
 """
 import torch
 

@@ -4,7 +4,9 @@ Same registry name / class name / constructor (`cls(hypes["model"]["args"])`), s
 (`base_bev_backbone`, `shrink_header`, `compression`, `fax_fusion.*`, `max_cav`), same `state_dict` key names and shapes
 (9 741 454 parameters for the shipped yaml), same `forward(data_dict) -> {"psm","rm","obj"}` as
 opencood/models/airv2x_cobevt.py:15-156 of the reference. The torch.nn layers below are parameter containers only
-(names + default init); their forward is never called. Eval-mode forward only in this round; no CPU fallback.
+(names + default init); their forward is never called. forward() in eval mode is the inference path; in train mode
+(grad enabled) it is wired to autograd through the fused forward_train / backward_train of the engine, and train_step()
+is the fused fast path (dropout disabled, explicitly); no CPU fallback.
 """
 import torch
 import torch.nn as nn
