@@ -245,7 +245,7 @@ class CoBEVTEngine(W2CEngine):
         x = canvas
         cat = None
         for i in range(len(self.layer_nums)):
-            x = self._block(P, W, i, x, True, 1, "E", rec)
+            x = self._block(P, W, i, x, True, 1, "E", rec, need_hi=False)  # feeds the next block and the deblock only
             if cat is None:
                 h2, w2 = x.shape[1], x.shape[2]
                 cat = self._act("E.cat", (N, h2, w2, self.c_cat))
@@ -461,7 +461,7 @@ class CoBEVTEngine(W2CEngine):
             dz = self._act("bwd.dz.d%d" % i, r["z"].shape)
             sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
             ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
-                            grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
+                            grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"], write_hi=False)
             s = r["stride"]
             cin, cout = r["x"].shape[3], r["z"].shape[3]
             dwp = zero_f32(r["conv"] + ".dwp", s * s * cin * cout).view(s * s, cin, cout)
@@ -477,7 +477,7 @@ class CoBEVTEngine(W2CEngine):
                 dz = self._act("bwd.dz." + r["tag"], r["z"].shape)
                 sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
                 ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
-                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
+                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"], write_hi=False)
                 cout, cin = r["z"].shape[3], r["x"].shape[3]
                 dwp = zero_f32(r["conv"] + ".dwp", 9 * cout * cin).view(9, cout, cin)
                 ops.conv_wgrad(r["x"], dz, 3, r["stride"], dwp)

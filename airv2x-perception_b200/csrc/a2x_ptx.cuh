@@ -212,7 +212,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
 // kind::f16 (bf16) MMAs into one fp32 TMEM accumulator: every product is exact in fp32, the dropped l*l term and the
 // second-level residuals are each <= 2^-17 relative (eval logits within 1e-4 of the fp32 reference).
 struct SplitOut {
-    float* hi;            // fp32 plane: the full value (may be the only plane)
+    float* hi;            // fp32 plane: the full value (may be the only plane; null = split planes only, see store_split4)
     __nv_bfloat16* b16;   // null = single-plane mode; else plane 0 = h16, plane 1 = l16 (plane stride `ps` elements)
     long long ps;
 };
@@ -221,7 +221,8 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloa
     l = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 __device__ __forceinline__ void store_split4(const SplitOut& o, long long off, float4 v) {
-    *reinterpret_cast<float4*>(o.hi + off) = v;
+    // hi == null: the consumer is a split GEMM (reads only the bf16 planes), so the fp32 plane's 4 B / element stay unwritten
+    if (o.hi != nullptr) *reinterpret_cast<float4*>(o.hi + off) = v;
     if (o.b16 != nullptr) {
         __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
         const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);

@@ -506,7 +506,7 @@ int a2x_bn_relu_bwd_apply(const float* dy, int dy_cs, const float* z, int z_cs, 
                           const a2x_output* dz, long long npix, int C, float* dgamma, float* dbeta,
                           int accumulate_param_grads, a2x_stream_t stream) {
     if (int r = check_c(C)) return r;
-    A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && dz && dz->hi && npix > 0,
+    A2X_REQUIRE(dy && z && scale && shift && mean && invstd && sums && dz && (dz->hi || dz->b16) && npix > 0,
                 "bn_relu_bwd_apply: bad args");
     int threads, blocks;
     col_launch_dims(npix, C, &threads, &blocks);
@@ -523,7 +523,7 @@ int a2x_bn_train_act(const float* z, int z_cs, const double* sums, double count,
                      float* shift, float* mean_out, float* invstd_out, int relu, const a2x_output* y, long long npix,
                      int C, a2x_stream_t stream) {
     if (int r = check_c(C)) return r;
-    A2X_REQUIRE(z && sums && scale && shift && y && y->hi && npix > 0 && count > 0, "bn_train_act: bad args");
+    A2X_REQUIRE(z && sums && scale && shift && y && (y->hi || y->b16) && npix > 0 && count > 0, "bn_train_act: bad args");
     int threads, blocks;
     col_launch_dims(npix, C, &threads, &blocks);
     bn_train_act_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(

@@ -3,6 +3,7 @@
 All activations are fp32 NHWC tensors; channel slices of wider NHWC buffers are passed as (view, pixel stride).
 """
 import ctypes
+import os
 
 import torch
 
@@ -204,6 +205,19 @@ def _op(a):
     return ctypes.byref(a.operand())
 
 
+POISON_SKIPPED_HI = bool(int(os.environ.get("A2X_POISON_HI", "0")))   # debug: NaN-fill fp32 planes that are not written
+
+
+def _op_planes(a, write_hi):
+    """output operand; write_hi False (split mode only): the kernel leaves the fp32 plane unwritten (hi pointer null)"""
+    o = a.operand()
+    if not write_hi and a.b16 is not None:
+        if POISON_SKIPPED_HI:
+            a.hi.fill_(float("nan"))
+        o.hi = None
+    return ctypes.byref(o)
+
+
 def split(x):
     """fp32 NHWC tensor -> split Act"""
     x = x.contiguous()
@@ -385,11 +399,12 @@ def bn_eval_affine(gamma, beta, rm, rv, scale, shift, eps=1e-3):
 
 
 def bn_train_act(z, sums, count, gamma, beta, n_updates, rm, rv, scale, shift, mean, invstd, relu, out, eps=1e-3,
-                 momentum=0.01):
-    """fused bn_finalize + affine_act (train mode): out = relu?(BN_batch(z)); scale/shift/mean/invstd are published"""
+                 momentum=0.01, write_hi=True):
+    """fused bn_finalize + affine_act (train mode): out = relu?(BN_batch(z)); scale/shift/mean/invstd are published.
+    write_hi False: only the bf16 split planes of `out` are written (its consumers are split GEMMs)."""
     call("a2x_bn_train_act", _ptr(z), c_int(_cs(z)), _ptr(sums), c_d(float(count)), _ptr(gamma), _ptr(beta), c_f(eps),
          c_f(momentum), c_int(n_updates), _ptr(rm), _ptr(rv), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
-         c_int(int(relu)), _op(out), c_ll(_npix(z)), c_int(z.shape[3]), stream_ptr())
+         c_int(int(relu)), _op_planes(out, write_hi), c_ll(_npix(z)), c_int(z.shape[3]), stream_ptr())
     return out
 
 
@@ -400,14 +415,15 @@ def affine_act(x, scale, shift, relu, out, mask=None):
     return out
 
 
-def bn_relu_bwd(dy, z, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, accumulate=False, sums_ready=False):
+def bn_relu_bwd(dy, z, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, accumulate=False, sums_ready=False,
+                write_hi=True):
     """dy, z: NHWC tensors; dz: Act; sums: zeroed [2C] double (already filled by a fused dgrad epilogue if sums_ready)"""
     npix, C = _npix(dy), dy.shape[3]
     if not sums_ready:
         call("a2x_bn_relu_bwd_reduce", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift),
              _ptr(mean), _ptr(invstd), c_ll(npix), c_int(C), _ptr(sums), stream_ptr())
     call("a2x_bn_relu_bwd_apply", _ptr(dy), c_int(_cs(dy)), _ptr(z), c_int(_cs(z)), _ptr(scale), _ptr(shift), _ptr(mean),
-         _ptr(invstd), _ptr(sums), c_d(float(npix)), _op(dz), c_ll(npix), c_int(C),
+         _ptr(invstd), _ptr(sums), c_d(float(npix)), _op_planes(dz, write_hi), c_ll(npix), c_int(C),
          _ptr(dgamma), _ptr(dbeta), c_int(int(accumulate)), stream_ptr())
     return dz
 

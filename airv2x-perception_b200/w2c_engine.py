@@ -180,17 +180,18 @@ class W2CEngine:
                         P[bn + ".running_var"], scale, shift, mean, invstd)
         return scale, shift, mean, invstd
 
-    def _bn_train_act(self, P, bn, z, sums, n_updates, tag, out):
-        """train-mode BN (finalize fused into the apply pass) + ReLU + operand split; returns the saved statistics"""
+    def _bn_train_act(self, P, bn, z, sums, n_updates, tag, out, need_hi=True):
+        """train-mode BN (finalize fused into the apply pass) + ReLU + operand split; returns the saved statistics.
+        need_hi False: every consumer of `out` is a split GEMM, so its fp32 plane is not written (4 of 12 B / element)"""
         C = z.shape[3]
         scale, shift = self._buf(tag + ".scale", (C,)), self._buf(tag + ".shift", (C,))
         mean, invstd = self._buf(tag + ".mean", (C,)), self._buf(tag + ".invstd", (C,))
         count = z.shape[0] * z.shape[1] * z.shape[2]
         ops.bn_train_act(z, sums, count, P[bn + ".weight"], P[bn + ".bias"], n_updates, P[bn + ".running_mean"],
-                         P[bn + ".running_var"], scale, shift, mean, invstd, True, out)
+                         P[bn + ".running_var"], scale, shift, mean, invstd, True, out, write_hi=need_hi)
         return scale, shift, mean, invstd
 
-    def _conv_bn_relu(self, P, W, conv, bn, x, stride, training, n_updates, tag, record):
+    def _conv_bn_relu(self, P, W, conv, bn, x, stride, training, n_updates, tag, record, need_hi=True):
         n, h, w, _ = x.shape
         cout = P[conv].shape[0]
         ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
@@ -203,18 +204,22 @@ class W2CEngine:
         z = self._buf(tag + ".z", (n, ho, wo, cout))
         sums = self._zeroed(tag + ".sums", 2 * cout, torch.float64)
         ops.conv_fwd(x, wf, 3, stride, Act(z), stats=sums)  # BN batch statistics come out of the GEMM epilogue
-        scale, shift, mean, invstd = self._bn_train_act(P, bn, z, sums, n_updates, tag, y)
+        scale, shift, mean, invstd = self._bn_train_act(P, bn, z, sums, n_updates, tag, y, need_hi)
         if record is not None:
             record.append(dict(kind="conv", conv=conv, bn=bn, x=x, z=z, y=y, stride=stride, scale=scale, shift=shift,
                                mean=mean, invstd=invstd, tag=tag))
         return y
 
-    def _block(self, P, W, i, x, training, n_updates, tag, record):
+    def _block(self, P, W, i, x, training, n_updates, tag, record, need_hi=True):
+        """need_hi: whether anything reads the fp32 value of the block's OUTPUT (mask multiply, attention fusion); the
+        layers inside a block only feed the next conv, so their fp32 planes are never written in train mode"""
         p = "backbone.blocks.%d" % i
-        x = self._conv_bn_relu(P, W, p + ".1.weight", p + ".2", x, 2, training, n_updates, "%s.b%d.0" % (tag, i), record)
-        for k in range(self.layer_nums[i]):
+        last = self.layer_nums[i]
+        x = self._conv_bn_relu(P, W, p + ".1.weight", p + ".2", x, 2, training, n_updates, "%s.b%d.0" % (tag, i), record,
+                               need_hi and last == 0)
+        for k in range(last):
             x = self._conv_bn_relu(P, W, "%s.%d.weight" % (p, 4 + 3 * k), "%s.%d" % (p, 5 + 3 * k), x, 1, training,
-                                   n_updates, "%s.b%d.%d" % (tag, i, k + 1), record)
+                                   n_updates, "%s.b%d.%d" % (tag, i, k + 1), record, need_hi and k == last - 1)
         return x
 
     def _deblock(self, P, W, i, x, out_slice, training, n_updates, tag, record):
@@ -233,7 +238,7 @@ class W2CEngine:
         z = self._buf(tg + ".z", (n, h * s, w * s, cout))
         sums = self._zeroed(tg + ".sums", 2 * cout, torch.float64)
         ops.deconv_fwd(x, wf, cout, s, Act(z), stats=sums)
-        scale, shift, mean, invstd = self._bn_train_act(P, bn, z, sums, n_updates, tg, out_slice)
+        scale, shift, mean, invstd = self._bn_train_act(P, bn, z, sums, n_updates, tg, out_slice, False)  # feeds the shrink conv
         if record is not None:
             record.append(dict(kind="deconv", conv=conv, bn=bn, x=x, z=z, y=out_slice, stride=s, scale=scale,
                                shift=shift, mean=mean, invstd=invstd, tag=tg, level=i))
@@ -353,7 +358,7 @@ class W2CEngine:
         # fewer 128-pixel tiles than the GPU has SMs: the HBM-bound 1x1 deblock GEMMs fill the idle ones)
         for i in range(len(self.layer_nums)):
             if i > 0:
-                xa = self._block(P, W, i, xa, training, 2, "A", None)
+                xa = self._block(P, W, i, xa, training, 2, "A", None, need_hi=False)
             c0 = sum(self.up_filters[:i])
             with self._on_side():
                 self._deblock(P, W, i, xa, catA.slice_c(c0, c0 + self.up_filters[i]), training, 2, "A", None)
@@ -650,7 +655,7 @@ class W2CEngine:
             dz = self._act("bwd.dz.d%d" % i, r["z"].shape)
             sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
             ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
-                            grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"])
+                            grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"], write_hi=False)
             s = r["stride"]
             cin, cout = r["x"].shape[3], r["z"].shape[3]
             dwp = self._zeroed(r["conv"] + ".dwp", s * s * cin * cout, torch.float32).view(s * s, cin, cout)
@@ -680,7 +685,8 @@ class W2CEngine:
                 if not sums_ready:
                     sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
                 ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
-                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"], sums_ready=sums_ready)
+                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"], sums_ready=sums_ready,
+                                write_hi=False)
                 cout, cin = r["z"].shape[3], r["x"].shape[3]
                 dwp = self._zeroed(r["conv"] + ".dwp." + tag, 9 * cout * cin, torch.float32).view(9, cout, cin)
                 with self._on_side():
