@@ -199,7 +199,7 @@ class CoBEVTEngine(W2CEngine):
         h2 = w2 = None
         cat = None
         for i in range(len(self.layer_nums)):
-            x = self._block(P, W, i, x, False, 0, "E", None)
+            x = self._block(P, W, i, x, False, 0, "E", None, need_hi=False)
             if cat is None:
                 h2, w2 = x.shape[1], x.shape[2]
                 cat = self._act("E.cat", (N, h2, w2, self.c_cat))

@@ -105,7 +105,7 @@ static int run_tg(TgParams& p, int gh, int gw, int n_img, int ncols, cudaStream_
 
 static void set_plain_out(TgParams& p, const a2x_output* y, int h, int w, int step, int h_off, int w_off) {
     const long long o = ((long long)h_off * w + w_off) * y->cs;
-    p.out.hi = y->hi + o;
+    p.out.hi = y->hi ? y->hi + o : nullptr;   // null fp32 plane: only the split planes are stored (store_split4)
     p.out.b16 = y->b16 ? (__nv_bfloat16*)y->b16 + o : nullptr;
     p.out.ps = y->b16_plane;
     p.osn = (long long)h * w * y->cs;
@@ -636,7 +636,8 @@ int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_w
     if (int r = check_shape(s, false)) return r;
     A2X_REQUIRE(relu >= 0 && relu <= 2, "conv2d_fwd: activation must be 0 (none), 1 (ReLU) or 2 (GELU)");
     if (int r = check_operand(x, s->cin, "conv2d_fwd x")) return r;
-    A2X_REQUIRE(w && w->w32 && y && y->hi && y->cs >= s->cout && y->cs % 4 == 0, "conv2d_fwd: bad weights/output");
+    A2X_REQUIRE(w && w->w32 && y && (y->hi || y->b16) && (y->hi || !accumulate) && y->cs >= s->cout && y->cs % 4 == 0,
+                "conv2d_fwd: bad weights/output");
     A2X_REQUIRE(!x->b16 || w->w16, "conv2d_fwd: split input needs bf16 weight planes");
     const int ho = (s->h - 1) / s->stride + 1, wo = (s->w - 1) / s->stride + 1;
     const int kk = s->ksize * s->ksize;
@@ -775,7 +776,7 @@ int a2x_deconv_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weig
                    const float* scale, const float* shift, int relu, double* stats, a2x_stream_t stream) {
     if (int r = check_shape(s, true)) return r;
     if (int r = check_operand(x, s->cin, "deconv_fwd x")) return r;
-    A2X_REQUIRE(w && w->w32 && y && y->hi && y->cs >= s->cout && y->cs % 4 == 0, "deconv_fwd: bad weights/output");
+    A2X_REQUIRE(w && w->w32 && y && (y->hi || y->b16) && y->cs >= s->cout && y->cs % 4 == 0, "deconv_fwd: bad weights/output");
     A2X_REQUIRE(!x->b16 || w->w16, "deconv_fwd: split input needs bf16 weight planes");
     const int st = s->stride;
     TgParams p{};

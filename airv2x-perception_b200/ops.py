@@ -231,13 +231,14 @@ split_tf32 = split
 
 
 # split-aware conv family ------------------------------------------------------------------------------------
-def conv_fwd(x, w, k, stride, out, scale=None, shift=None, relu=False, stats=None, accumulate=False):
-    """x, out: Act; w: PackedW. relu: False/0 none, True/1 ReLU, 2 GELU(erf). accumulate: out += result (residual)."""
+def conv_fwd(x, w, k, stride, out, scale=None, shift=None, relu=False, stats=None, accumulate=False, write_hi=True):
+    """x, out: Act; w: PackedW. relu: False/0 none, True/1 ReLU, 2 GELU(erf). accumulate: out += result (residual).
+    write_hi False: only the split planes of `out` are stored (every consumer is a split GEMM)."""
     n, h, ww, cin = x.shape
     cout = w.f32.shape[1]
     sh = _shape(n, h, ww, cin, cout, k, stride)
-    call("a2x_conv2d_fwd_ex", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _op(out), _ptr(scale), _ptr(shift),
-         c_int(int(relu)), c_int(int(accumulate)), _ptr(stats), stream_ptr())
+    call("a2x_conv2d_fwd_ex", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _op_planes(out, write_hi or accumulate),
+         _ptr(scale), _ptr(shift), c_int(int(relu)), c_int(int(accumulate)), _ptr(stats), stream_ptr())
     return out
 
 
@@ -348,10 +349,10 @@ def conv_wgrad(x, dy, k, stride, dwp):
     return dwp
 
 
-def deconv_fwd(x, w, cout, s, out, scale=None, shift=None, relu=False, stats=None):
+def deconv_fwd(x, w, cout, s, out, scale=None, shift=None, relu=False, stats=None, write_hi=True):
     n, h, ww, cin = x.shape
     sh = _shape(n, h, ww, cin, cout, s, s)
-    call("a2x_deconv_fwd", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _op(out), _ptr(scale), _ptr(shift),
+    call("a2x_deconv_fwd", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _op_planes(out, write_hi), _ptr(scale), _ptr(shift),
          c_int(int(relu)), _ptr(stats), stream_ptr())
     return out
 

@@ -199,7 +199,7 @@ class W2CEngine:
         wf = W[conv]
         if not training:
             scale, shift, _, _ = self._bn_params(P, bn, False, y.hi, 0, tag)
-            ops.conv_fwd(x, wf, 3, stride, y, scale=scale, shift=shift, relu=True)
+            ops.conv_fwd(x, wf, 3, stride, y, scale=scale, shift=shift, relu=True, write_hi=need_hi)
             return y
         z = self._buf(tag + ".z", (n, ho, wo, cout))
         sums = self._zeroed(tag + ".sums", 2 * cout, torch.float64)
@@ -233,7 +233,7 @@ class W2CEngine:
         tg = "%s.d%d" % (tag, i)
         if not training:
             scale, shift, _, _ = self._bn_params(P, bn, False, out_slice.hi, 0, tg)
-            ops.deconv_fwd(x, wf, cout, s, out_slice, scale=scale, shift=shift, relu=True)
+            ops.deconv_fwd(x, wf, cout, s, out_slice, scale=scale, shift=shift, relu=True, write_hi=False)
             return
         z = self._buf(tg + ".z", (n, h * s, w * s, cout))
         sums = self._zeroed(tg + ".sums", 2 * cout, torch.float64)
