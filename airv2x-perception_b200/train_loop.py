@@ -1,0 +1,140 @@
+"""The caller side of the training step: what `opencood/tools/train.py:191-260` and
+`opencood/tools/train_utils.py:35-118, :371-465` do around `model(batch)`, arranged for the B200 path.
+
+  * labels are assigned on the GPU from the padded ground-truth boxes (`labels.TargetAssigner`) instead of arriving as
+    fp64 maps from a DataLoader worker;
+  * forward + loss + backward is the model's fused `train_step` (or the CUDA-graph replay when the batch carries raw
+    point clouds), the optimizer / scheduler are the reference's (`setup_optimizer`, `setup_lr_schedular`: same yaml keys);
+  * checkpoints keep the reference's file name and dict layout (`net_epoch%d.pth` with `epoch`, `model_state_dict`,
+    `optimizer_state_dict`, `scheduler_state_dict`, train.py:243-253) and RESUME WORKS: the reference's
+    `load_saved_model` reads that dict as if it were a flat state_dict (every key is dropped, nothing is loaded,
+    train_utils.py:88-116) and its `findLastCheckpoint` returns an undefined name when checkpoints exist (:54-63).
+
+Host logic only; every number-crunching step is a kernel behind the model / assigner. No CPU fallback.
+"""
+import glob
+import os
+import re
+
+import torch
+
+from .labels import TargetAssigner
+
+
+def setup_optimizer(hypes, model):
+    """train_utils.py:371-390: `getattr(torch.optim, core_method)(model.parameters(), lr=..., **args)`; on CUDA the
+    fused (single multi-tensor kernel) implementation of the same optimizer is selected when torch offers it."""
+    cfg = hypes["optimizer"]
+    cls = getattr(torch.optim, cfg["core_method"], None)
+    if cls is None:
+        raise ValueError("{} is not supported".format(cfg["core_method"]))
+    params = [p for p in model.parameters() if p.requires_grad]
+    kw = dict(cfg.get("args", {}))
+    if cfg["core_method"] in ("Adam", "AdamW", "SGD") and all(p.is_cuda for p in params):
+        kw.setdefault("fused", True)
+    return cls(params, lr=cfg["lr"], **kw)
+
+
+def setup_lr_scheduler(hypes, optimizer, init_epoch=None):
+    """train_utils.py:393-452 (step / multistep / exponential; the timm cosine schedule is outside the path)"""
+    cfg = hypes["lr_scheduler"]
+    m = cfg["core_method"]
+    if m == "step":
+        sch = torch.optim.lr_scheduler.StepLR(optimizer, step_size=cfg["step_size"], gamma=cfg["gamma"])
+    elif m == "multistep":
+        sch = torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=cfg["step_size"], gamma=cfg["gamma"])
+    elif m == "exponential":
+        sch = torch.optim.lr_scheduler.ExponentialLR(optimizer, cfg["gamma"])
+    else:
+        raise NotImplementedError("lr scheduler %r is not implemented" % m)
+    for _ in range(init_epoch or 0):
+        sch.step()
+    return sch
+
+
+def find_last_checkpoint(save_dir):
+    """highest N among `*epochN.pth` files, 0 if there is none (what train_utils.py:54-63 means to do)"""
+    epochs = []
+    for f in glob.glob(os.path.join(save_dir, "*epoch*.pth")):
+        m = re.findall(r".*epoch(\d+)\.pth$", f)
+        if m:
+            epochs.append(int(m[0]))
+    return max(epochs) if epochs else 0
+
+
+def load_saved_model(saved_path, model, epoch=None, optimizer=None, scheduler=None):
+    """Same call as train_utils.load_saved_model (`initial_epoch, model = load_saved_model(path, model)`), accepting
+    both checkpoint layouts: the dict train.py writes and a flat state_dict (the published checkpoints). `module.`
+    prefixes of DataParallel / DDP are stripped and shape mismatches skipped like the reference (:88-116)."""
+    assert os.path.exists(saved_path), "{} not found".format(saved_path)
+    initial_epoch = find_last_checkpoint(saved_path) if epoch is None else int(epoch)
+    if initial_epoch == 0:
+        return 0, model
+    ckpt = torch.load(os.path.join(saved_path, "net_epoch%d.pth" % initial_epoch), map_location="cpu")
+    flat = ckpt["model_state_dict"] if isinstance(ckpt, dict) and "model_state_dict" in ckpt else ckpt
+    own = model.state_dict()
+    state = {}
+    for k, v in flat.items():
+        if k.startswith("module") and not k.startswith("module_list"):
+            k = k[7:]
+        if k in own and tuple(own[k].shape) == tuple(v.shape):
+            state[k] = v
+    model.load_state_dict(state, strict=False)
+    if isinstance(ckpt, dict) and "model_state_dict" in ckpt:
+        if optimizer is not None and "optimizer_state_dict" in ckpt:
+            optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        if scheduler is not None and "scheduler_state_dict" in ckpt:
+            scheduler.load_state_dict(ckpt["scheduler_state_dict"])
+    return initial_epoch, model
+
+
+class Trainer:
+    """`Trainer(model, hypes)`; `loss3 = trainer.step(batch)` with batch = the model's data_dict plus the padded boxes
+    `object_bbx_center [B,max_num,7]`, `object_bbx_mask [B,max_num]`, `object_class_ids [B,max_num]` (the tensors the
+    dataset hands to `generate_label_airv2x`) — or a ready `label_dict`. Returns the device tensor [reg, cls, obj]."""
+
+    def __init__(self, model, hypes, graph=True):
+        self.model, self.hypes = model, hypes
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("Trainer (B200) needs the model on a CUDA device; there is no CPU path")
+        self.assigner = TargetAssigner(hypes["postprocess"], dev)
+        self.optimizer = setup_optimizer(hypes, model)
+        self.scheduler = setup_lr_scheduler(hypes, self.optimizer)
+        la = hypes["loss"]["args"]
+        self.cls_weight, self.reg_coe = float(la["cls_weight"]), float(la["reg"])
+        self.graph = graph
+        self.epoch = 0
+
+    def labels(self, batch):
+        if "label_dict" in batch:
+            return batch["label_dict"]
+        return self.assigner(batch["object_bbx_center"], batch["object_bbx_mask"], batch["object_class_ids"])
+
+    def step(self, batch, **kw):
+        model = self.model
+        model.train()
+        labels = self.labels(batch)
+        data = {k: v for k, v in batch.items() if k not in ("label_dict", "object_bbx_center", "object_bbx_mask", "object_class_ids")}
+        graphed = self.graph and data.get("raw_points") is not None and data["raw_points"].get("transforms") is None \
+            and hasattr(model, "train_step_graphed") and type(model).__name__ == "Airv2xWhere2com"
+        if graphed:
+            loss3 = model.train_step_graphed(data, labels, self.cls_weight, self.reg_coe)
+        else:
+            loss3 = model.train_step(data, labels, self.cls_weight, self.reg_coe, **kw)
+        self.optimizer.step()                       # gradients were written into p.grad by the fused step
+        return loss3
+
+    def end_epoch(self, saved_path=None):
+        self.scheduler.step()
+        self.epoch += 1
+        if saved_path is not None:
+            os.makedirs(saved_path, exist_ok=True)
+            torch.save({"epoch": self.epoch - 1, "model_state_dict": self.model.state_dict(),
+                        "optimizer_state_dict": self.optimizer.state_dict(),
+                        "scheduler_state_dict": self.scheduler.state_dict()},
+                       os.path.join(saved_path, "net_epoch%d.pth" % self.epoch))
+
+    def resume(self, saved_path):
+        self.epoch, _ = load_saved_model(saved_path, self.model, None, self.optimizer, self.scheduler)
+        return self.epoch

@@ -79,3 +79,44 @@ def test_agent_parallel_exchange_regions():
     assert reg["total"] == 64 + 35200 + 35200 * 64 + 50 * 176 * 128 + 25 * 88 * 256
     for k in ("idx", "vals", "lvl1", "lvl2"):
         assert reg[k][0] % 4 == 0          # 16-byte aligned regions (float4 / int4 access)
+
+
+def test_checkpoint_resume_helpers(tmp_path):
+    """train_loop.find_last_checkpoint / load_saved_model: the latest `net_epochN.pth` is found (the reference's
+    findLastCheckpoint returns an undefined name, train_utils.py:54-63) and BOTH layouts load — the dict train.py writes
+    (which the reference's loader silently drops key by key, :88-116) and a flat / DataParallel-prefixed state_dict."""
+    import torch
+    import torch.nn as nn
+
+    import a2x_import
+
+    TL = a2x_import.pkg("train_loop")
+    d = str(tmp_path)
+    assert TL.find_last_checkpoint(d) == 0
+    net = nn.Sequential(nn.Linear(4, 3), nn.BatchNorm1d(3))
+    opt = torch.optim.Adam(net.parameters(), lr=0.002, eps=1e-10, weight_decay=1e-4)
+    sch = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1, 3], gamma=0.1)
+    net(torch.randn(5, 4)).sum().backward()
+    opt.step()
+    sch.step()
+    torch.save({"epoch": 2, "model_state_dict": net.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                "scheduler_state_dict": sch.state_dict()}, d + "/net_epoch3.pth")
+    torch.save({"module." + k: v for k, v in net.state_dict().items()}, d + "/net_epoch12.pth")
+    torch.save({"x": 1}, d + "/net_epoch_bestval_at7.pth")                      # not an epoch checkpoint
+    assert TL.find_last_checkpoint(d) == 12
+    fresh = nn.Sequential(nn.Linear(4, 3), nn.BatchNorm1d(3))
+    ep, _ = TL.load_saved_model(d, fresh)                                        # flat, `module.`-prefixed layout
+    assert ep == 12 and all(torch.equal(a, b) for a, b in zip(fresh.state_dict().values(), net.state_dict().values()))
+    fresh = nn.Sequential(nn.Linear(4, 3), nn.BatchNorm1d(3))
+    opt2 = torch.optim.Adam(fresh.parameters(), lr=0.5)
+    sch2 = torch.optim.lr_scheduler.MultiStepLR(opt2, milestones=[1, 3], gamma=0.1)
+    ep, _ = TL.load_saved_model(d, fresh, epoch=3, optimizer=opt2, scheduler=sch2)  # the dict layout of train.py
+    assert ep == 3 and all(torch.equal(a, b) for a, b in zip(fresh.state_dict().values(), net.state_dict().values()))
+    assert opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"] and sch2.last_epoch == sch.last_epoch
+    assert len(opt2.state) == len(opt.state)
+    hypes = {"optimizer": {"core_method": "Adam", "lr": 0.002, "args": {"eps": 1e-10, "weight_decay": 1e-4}},
+             "lr_scheduler": {"core_method": "multistep", "gamma": 0.1, "step_size": [10, 25, 40]}}
+    o = TL.setup_optimizer(hypes, net)
+    assert type(o).__name__ == "Adam" and o.defaults["eps"] == 1e-10 and o.defaults["weight_decay"] == 1e-4
+    s = TL.setup_lr_scheduler(hypes, o, init_epoch=11)
+    assert abs(o.param_groups[0]["lr"] - 0.0002) < 1e-12 and s.last_epoch == 11
