@@ -393,12 +393,12 @@ class CoBEVTEngine(W2CEngine):
                 lin_wgrad(sl["att"], dXs, pre + ".fn.to_out.0.weight")
                 d_att = self._buf("bwd.d_att", X.shape)
                 ops.conv_dgrad(dXs, W[pre + ".fn.to_out.0.weight"], 1, 1, d_att)
-                dqkv = self._buf("bwd.dqkv", sl["qkv"].shape)
+                dqs = self._act("bwd.dqs", sl["qkv"].shape)   # written as a GEMM operand: no fp32 plane, no conversion pass
                 tname = pre + ".fn.relative_position_bias_table.weight"
                 grads[tname].zero_()
                 ops.window_attention_bwd(sl["qkv"], d_att, P[tname], S["key_mask"], B, self.L, self.heads,
-                                         self.fa["dim_head"], self.fa["window_size"], sl["grid"], dqkv, grads[tname])
-                dqs = split_of(dqkv, "bwd.dqs")
+                                         self.fa["dim_head"], self.fa["window_size"], sl["grid"], dqs, grads[tname],
+                                         write_hi=False)
                 lin_wgrad(sl["ln"], dqs, pre + ".fn.to_qkv.weight")
                 d_ln = self._buf("bwd.d_ln", X.shape)
                 ops.conv_dgrad(dqs, W[pre + ".fn.to_qkv.weight"], 1, 1, d_ln)

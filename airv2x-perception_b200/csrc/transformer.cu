@@ -607,7 +607,7 @@ struct WinAttBwdParams {
     const float* dout;     // [B*L][H][W][D]   gradient w.r.t. the attention output (before to_out)
     const float* bias;     // [(2L-1)(2w-1)^2][heads]
     const int* key_mask;   // [B][L] or null
-    float* dqkv;           // [B*L][H][W][3*D]  (written: every token belongs to exactly one window per call)
+    SplitOut dqkv;         // [B*L][H][W][3*D]  (written: every token belongs to exactly one window per call); fp32 and / or split planes
     float* dbias;          // [(2L-1)(2w-1)^2][heads], accumulated with atomics
     int B, L, H, W, heads, w, grid_mode;
     float scale;
@@ -724,9 +724,9 @@ __global__ void __launch_bounds__(128) window_attention_bwd_kernel(const WinAttB
 #pragma unroll
             for (int c = 0; c < DH; ++c) dv[c] = fmaf(pij, o[c], dv[c]);
         }
-        float* out = p.dqkv + (long long)sTok[j] * (3 * D) + 2 * D + head * DH;
+        const long long out = (long long)sTok[j] * (3 * D) + 2 * D + head * DH;
 #pragma unroll
-        for (int c = 0; c < DH; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
+        for (int c = 0; c < DH; c += 4) store_split4(p.dqkv, out + c, make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]));
     }
     __syncthreads();
     // ---- D_i = dO_i . O_i ; dS_ij = P_ij (dO_i . V_j - D_i) -> sP ; dQ_i
@@ -762,11 +762,11 @@ __global__ void __launch_bounds__(128) window_attention_bwd_kernel(const WinAttB
 #pragma unroll
             for (int c = 0; c < DH; ++c) acc[c] = fmaf(ds, v[c], acc[c]);
         }
-        float* out = p.dqkv + (long long)sTok[i] * (3 * D) + head * DH;
+        const long long out = (long long)sTok[i] * (3 * D) + head * DH;
 #pragma unroll
         for (int c = 0; c < DH; c += 4)
-            *reinterpret_cast<float4*>(out + c) =
-                make_float4(acc[c] * p.scale, acc[c + 1] * p.scale, acc[c + 2] * p.scale, acc[c + 3] * p.scale);
+            store_split4(p.dqkv, out + c,
+                         make_float4(acc[c] * p.scale, acc[c + 1] * p.scale, acc[c + 2] * p.scale, acc[c + 3] * p.scale));
     }
     __syncthreads();
     // ---- dK_j = sum_i dS_ij Q_i (sQ carries the scale) ; bias gradient
@@ -786,9 +786,9 @@ __global__ void __launch_bounds__(128) window_attention_bwd_kernel(const WinAttB
                 atomicAdd(&sdB[((li - lj + p.L - 1) * s2 + (ri / p.w - k1 + p.w - 1)) * s2 + (ri % p.w - k2 + p.w - 1)], ds);
             }
         }
-        float* out = p.dqkv + (long long)sTok[j] * (3 * D) + D + head * DH;
+        const long long out = (long long)sTok[j] * (3 * D) + D + head * DH;
 #pragma unroll
-        for (int c = 0; c < DH; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
+        for (int c = 0; c < DH; c += 4) store_split4(p.dqkv, out + c, make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nb; i += blockDim.x)
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(128) window_attention_small_bwd_kernel(const W
         sS[threadIdx.x * PS + j] = ds[j];
     }
     if (valid) {
-        float* out = p.dqkv + tok * (3 * D) + head * DH;
+        const long long out = tok * (3 * D) + head * DH;
 #pragma unroll
         for (int c0 = 0; c0 < DH; c0 += 16) {
             float acc[16];
@@ -910,14 +910,14 @@ __global__ void __launch_bounds__(128) window_attention_small_bwd_kernel(const W
             }
 #pragma unroll
             for (int c = 0; c < 16; c += 4)
-                *reinterpret_cast<float4*>(out + c0 + c) =
-                    make_float4(acc[c] * p.scale, acc[c + 1] * p.scale, acc[c + 2] * p.scale, acc[c + 3] * p.scale);
+                store_split4(p.dqkv, out + c0 + c,
+                             make_float4(acc[c] * p.scale, acc[c + 1] * p.scale, acc[c + 2] * p.scale, acc[c + 3] * p.scale));
         }
     }
     __syncthreads();
     // ---- phase 2: this thread as key tq of window g
     if (valid) {
-        float* out = p.dqkv + tok * (3 * D) + head * DH;
+        const long long out = tok * (3 * D) + head * DH;
         float sj[NT], pj[NT];
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
@@ -945,8 +945,8 @@ __global__ void __launch_bounds__(128) window_attention_small_bwd_kernel(const W
             }
 #pragma unroll
             for (int c = 0; c < 16; c += 4) {
-                *reinterpret_cast<float4*>(out + D + c0 + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
-                *reinterpret_cast<float4*>(out + 2 * D + c0 + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
+                store_split4(p.dqkv, out + D + c0 + c, make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]));
+                store_split4(p.dqkv, out + 2 * D + c0 + c, make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]));
             }
         }
     }
@@ -1010,11 +1010,24 @@ int a2x_gelu_bwd(const float* dy, const float* x, long long n, const a2x_output*
 int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* bias_table, const int* key_mask, int B,
                              int L, int H, int W, int heads, int dim_head, int window, int grid_mode, float scale,
                              float* dqkv, float* dbias_table, a2x_stream_t stream) {
-    A2X_REQUIRE(qkv && dout && bias_table && dqkv && dbias_table && B > 0 && L > 0 && heads > 0 && window > 0,
+    A2X_REQUIRE(dqkv, "window_attention_bwd: bad args");
+    a2x_output o;
+    o.hi = dqkv; o.b16 = nullptr; o.b16_plane = 0; o.cs = 3 * heads * dim_head;
+    return a2x_window_attention_bwd_split(qkv, dout, bias_table, key_mask, B, L, H, W, heads, dim_head, window, grid_mode, scale,
+                                          &o, dbias_table, stream);
+}
+
+int a2x_window_attention_bwd_split(const float* qkv, const float* dout, const float* bias_table, const int* key_mask, int B,
+                                   int L, int H, int W, int heads, int dim_head, int window, int grid_mode, float scale,
+                                   const a2x_output* dqkv, float* dbias_table, a2x_stream_t stream) {
+    A2X_REQUIRE(qkv && dout && bias_table && dqkv && (dqkv->hi || dqkv->b16) && dbias_table && B > 0 && L > 0 && heads > 0 &&
+                    window > 0,
                 "window_attention_bwd: bad args");
+    A2X_REQUIRE(dqkv->cs == 3 * heads * dim_head, "window_attention_bwd: dense [.., 3*heads*dim_head] gradient expected");
     A2X_REQUIRE(H % window == 0 && W % window == 0, "window_attention_bwd: H, W must be multiples of the window");
     a2x::WinAttBwdParams p;
-    p.qkv = qkv; p.dout = dout; p.bias = bias_table; p.key_mask = key_mask; p.dqkv = dqkv; p.dbias = dbias_table;
+    p.qkv = qkv; p.dout = dout; p.bias = bias_table; p.key_mask = key_mask; p.dbias = dbias_table;
+    p.dqkv.hi = dqkv->hi; p.dqkv.b16 = (__nv_bfloat16*)dqkv->b16; p.dqkv.ps = dqkv->b16_plane;
     p.B = B; p.L = L; p.H = H; p.W = W; p.heads = heads; p.w = window; p.grid_mode = grid_mode; p.scale = scale;
     const int n = L * window * window;
     const int nb = (2 * L - 1) * (2 * window - 1) * (2 * window - 1);

@@ -638,9 +638,18 @@ def gelu_bwd(dy, x, out):
     return out
 
 
-def window_attention_bwd(qkv, dout, bias_table, key_mask, B, L, heads, dim_head, window, grid_mode, dqkv, dbias):
-    assert qkv.is_contiguous() and dout.is_contiguous() and dqkv.is_contiguous()
+def window_attention_bwd(qkv, dout, bias_table, key_mask, B, L, heads, dim_head, window, grid_mode, dqkv, dbias,
+                         write_hi=True):
+    """dqkv: fp32 tensor [B*L, H, W, 3D], or an Act (split planes written directly; write_hi False skips its fp32 plane)"""
+    assert qkv.is_contiguous() and dout.is_contiguous()
     _, H, W, _ = qkv.shape
+    if isinstance(dqkv, Act):
+        assert dqkv.hi.is_contiguous()
+        call("a2x_window_attention_bwd_split", _ptr(qkv), _ptr(dout), _ptr(bias_table), _ptr(key_mask), c_int(B), c_int(L),
+             c_int(H), c_int(W), c_int(heads), c_int(dim_head), c_int(window), c_int(int(grid_mode)), c_f(dim_head ** -0.5),
+             _op_planes(dqkv, write_hi), _ptr(dbias), stream_ptr())
+        return
+    assert dqkv.is_contiguous()
     call("a2x_window_attention_bwd", _ptr(qkv), _ptr(dout), _ptr(bias_table), _ptr(key_mask), c_int(B), c_int(L), c_int(H),
          c_int(W), c_int(heads), c_int(dim_head), c_int(window), c_int(int(grid_mode)), c_f(dim_head ** -0.5), _ptr(dqkv),
          _ptr(dbias), stream_ptr())

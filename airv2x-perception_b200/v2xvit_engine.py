@@ -436,13 +436,13 @@ class V2XViTEngine(CoBEVTEngine):
                 col_sums(dwin[lv].hi, C, [(grads[bp_l + ".to_out.0.bias"], 0)])
                 d_att = self._buf("bwd.d_att", (N, h, w, C))
                 ops.conv_dgrad(dwin[lv], W[bp_l + ".to_out.0.weight"], 1, 1, d_att)
-                dqkv = self._buf("bwd.dwqkv", (N, h, w, 3 * C))
+                dqs = self._act("bwd.dwqs", (N, h, w, 3 * C))  # written as a GEMM operand: no fp32 plane, no conversion pass
                 dbias = self._buf("bwd.dbias%d" % lv, sv["table"][lv].shape)
                 dbias.zero_()
-                ops.window_attention_bwd(sv["wqkv"][lv], d_att, sv["table"][lv], None, N, 1, hh, dhd, ws, False, dqkv, dbias)
+                ops.window_attention_bwd(sv["wqkv"][lv], d_att, sv["table"][lv], None, N, 1, hh, dhd, ws, False, dqs, dbias,
+                                         write_hi=False)
                 # the table is the flipped pos_embedding broadcast over heads (mswin.py:15-20)
                 grads[bp_l + ".pos_embedding"].copy_(dbias.sum(1).view(2 * ws - 1, 2 * ws - 1).flip(0, 1))
-                dqs = split_of(dqkv, "bwd.dwqs")
                 lin_wgrad(sv["ln_p"], dqs, bp_l + ".to_qkv.weight")
                 ops.conv_dgrad(dqs, W[bp_l + ".to_qkv.weight"], 1, 1, d_ln, accumulate=lv > 0)
             ln_bwd(sv["xin_p"], d_ln, pwp + ".norm", dX)

@@ -185,6 +185,11 @@ int a2x_gelu_bwd(const float* dy, const float* x, long long n, const a2x_output*
 int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* bias_table, const int* key_mask, int B,
                              int L, int H, int W, int heads, int dim_head, int window, int grid_mode, float scale,
                              float* dqkv, float* dbias_table, a2x_stream_t stream);
+/* Same, with the gradient written as a GEMM operand: dqkv->hi (fp32, may be NULL) and / or the bf16 split planes — its
+ * consumers are the to_qkv weight / data gradient GEMMs, so no separate conversion pass over the [.., 3*D] tensor. */
+int a2x_window_attention_bwd_split(const float* qkv, const float* dout, const float* bias_table, const int* key_mask, int B,
+                                   int L, int H, int W, int heads, int dim_head, int window, int grid_mode, float scale,
+                                   const a2x_output* dqkv, float* dbias_table, a2x_stream_t stream);
 
 /* ---------------------------------------------------------------- V2X-ViT fusion (csrc/v2xvit.cu)
  * x[a][p][:] += Linear(emb_table[emb_idx[a]])  — RTE, v2xvit_modules/v2xvit_basic.py:41-80. vec_ws: [n_agents][C]. */
