@@ -342,7 +342,7 @@ class CoBEVTEngine(W2CEngine):
 
         def split_of(t, name):
             a = self._act(name, t.shape)
-            ops.affine_act(t, None, None, False, a)
+            ops.affine_act(t, None, None, False, a, write_hi=False)  # GEMM operand only
             return a
 
         def ln_bwd(xin, d_ln, pre_norm, dX):

@@ -477,7 +477,7 @@ int a2x_bn_eval_affine(const float* gamma, const float* beta, const float* runni
 int a2x_affine_act(const float* x, int x_cs, const float* scale, const float* shift, int relu, const float* mask,
                    const a2x_output* y, long long npix, int C, a2x_stream_t stream) {
     if (int r = check_c(C)) return r;
-    A2X_REQUIRE(x && y && y->hi && npix > 0, "affine_act: bad args");
+    A2X_REQUIRE(x && y && (y->hi || y->b16) && npix > 0, "affine_act: bad args");
     affine_act_kernel<<<ew_grid(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_cs, scale, shift, relu, mask,
                                                                                to_split(y), y->cs, npix, C);
     A2X_LAUNCHED();

@@ -409,9 +409,10 @@ def bn_train_act(z, sums, count, gamma, beta, n_updates, rm, rv, scale, shift, m
     return out
 
 
-def affine_act(x, scale, shift, relu, out, mask=None):
-    """x: NHWC tensor; out: Act"""
-    call("a2x_affine_act", _ptr(x), c_int(_cs(x)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(mask), _op(out),
+def affine_act(x, scale, shift, relu, out, mask=None, write_hi=True):
+    """x: NHWC tensor; out: Act (write_hi False: split planes only)"""
+    call("a2x_affine_act", _ptr(x), c_int(_cs(x)), _ptr(scale), _ptr(shift), c_int(int(relu)), _ptr(mask),
+         _op_planes(out, write_hi),
          c_ll(_npix(x)), c_int(x.shape[3]), stream_ptr())
     return out
 

@@ -378,9 +378,10 @@ class V2XViTEngine(CoBEVTEngine):
             if c_ > 1024:  # elementwise: present wide rows to the kernel as C-wide ones
                 k = c_ // C
                 ops.affine_act(t.view(n_, h_, w_ * k, C), None, None, False,
-                               Act(a.hi.view(n_, h_, w_ * k, C), None if a.b16 is None else a.b16.view(2, n_, h_, w_ * k, C)))
+                               Act(a.hi.view(n_, h_, w_ * k, C), None if a.b16 is None else a.b16.view(2, n_, h_, w_ * k, C)),
+                               write_hi=False)
             else:
-                ops.affine_act(t, None, None, False, a)
+                ops.affine_act(t, None, None, False, a, write_hi=False)  # GEMM operand only
             return a
 
         def ln_bwd(xin, d_ln, pre_norm, dX):
