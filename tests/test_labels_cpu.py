@@ -51,3 +51,23 @@ def test_assignment_rules_on_a_hand_case():
     assert lab["pos_equal_one"][iy, ix, ia] == 1 and lab["neg_equal_one"][iy, ix, ia] == 0
     empty = LO.generate_label(box, np.zeros(8, int), cls, anchors, 0.6, 0.45)
     assert empty["pos_equal_one"].sum() == 0 and empty["neg_equal_one"].sum() == H * W * A and np.all(empty["targets"] == 0)
+
+
+def test_host_footprints_match_the_oracle():
+    """labels._standup (the host half of TargetAssigner: fp32 corner arithmetic of boxes_to_corners_3d) == the oracle's
+    standup boxes bit for bit, for the anchors and for rotated ground-truth boxes; a CPU device is refused loudly"""
+    import pytest
+    import torch
+
+    import a2x_import
+
+    L = a2x_import.pkg("labels")
+    params, _ = load()
+    anchors = PO.generate_anchor_box(params["anchor_args"], params["order"]).reshape(-1, 7)
+    assert np.array_equal(L._standup(anchors).numpy().view(np.uint32), LO.standup_boxes(anchors).view(np.uint32))
+    box, mask, _ = LO.synth_gt(params, 201)
+    valid = box[mask == 1]
+    assert np.array_equal(L._standup(valid).numpy().view(np.uint32), LO.standup_boxes(valid).view(np.uint32))
+    assert L._standup(valid[:0]).shape == (0, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        L.TargetAssigner(params, "cpu")
