@@ -709,3 +709,23 @@ def assign_targets(anchor_standup, anchors, gt_standup, gt_boxes, gt_class, gt_o
          c_f(float(pos_threshold)), c_f(float(neg_threshold)), _ptr(code_ws), _ptr(best_ws), _ptr(targets), _ptr(pos),
          _ptr(neg), _ptr(class_ids), stream_ptr())
 
+
+
+# Lift-Splat camera branch -------------------------------------------------------------------------------------------------
+def lift_splat_fwd(depth, feat, geom, B, N, origin3, dx3, nx3, bev, cells_ws):
+    """depth [B*N,D,fH,fW], feat [B*N,C,fH,fW], geom [B,N,D,fH,fW,3] -> bev NHWC [B,ny,nx,nz*C] (see airv2x_b200.h)"""
+    _, D, fH, fW = depth.shape
+    C = feat.shape[1]
+    assert depth.is_contiguous() and feat.is_contiguous() and geom.is_contiguous() and bev.is_contiguous()
+    call("a2x_lift_splat_fwd", _ptr(depth), _ptr(feat), _ptr(geom), c_int(B), c_int(N), c_int(D), c_int(fH), c_int(fW), c_int(C),
+         (c_f * 3)(*[float(v) for v in origin3]), (c_f * 3)(*[float(v) for v in dx3]), (c_int * 3)(*[int(v) for v in nx3]),
+         _ptr(bev), _ptr(cells_ws), stream_ptr())
+    return bev
+
+
+def lift_splat_bwd(depth, feat, cells_ws, dbev, B, N, ddepth, dfeat):
+    _, D, fH, fW = depth.shape
+    C = feat.shape[1]
+    assert dbev.is_contiguous() and ddepth.is_contiguous() and dfeat.is_contiguous()
+    call("a2x_lift_splat_bwd", _ptr(depth), _ptr(feat), _ptr(cells_ws), _ptr(dbev), c_int(B), c_int(N), c_int(D), c_int(fH),
+         c_int(fW), c_int(C), _ptr(ddepth), _ptr(dfeat), stream_ptr())

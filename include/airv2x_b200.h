@@ -306,6 +306,19 @@ int a2x_sums_to_float(const double* sums, int C, float* out, int accumulate, a2x
 /* torch.count_nonzero (airv2x_where2com.py:122) */
 int a2x_count_nonzero(const float* x, long long n, unsigned long long* out, a2x_stream_t stream);
 
+/* ---------------------------------------------------------------- Lift-Splat camera branch (lift + voxel pooling)
+ * Replace the lift `depth.unsqueeze(1) * x_img.unsqueeze(2)` of CamEncode.forward
+ * (opencood/models/sub_modules/lss_submodule.py:170-186) together with LiftSplatShootEncoder.voxel_pooling
+ * (opencood/models/common_modules/airv2x_encoder.py:208-275) without materialising the [B,N,D,fH,fW,C] product.
+ * depth [B*N][D][fH][fW] (softmax over D), feat [B*N][C][fH][fW], geom [B][N][D][fH][fW][3] (get_geometry, :133-168);
+ * origin3 = bx - dx / 2, dx3, nx3 = gen_dx_bx (utils/camera_utils.py:238-244). bev: NHWC [B][ny][nx][nz*C] (channel
+ * z*C + c = the reference's [B, C*nz, ny, nx] after its unbind/cat), zero-filled here. cells_ws [B*N*D*fH*fW] i32 keeps
+ * every frustum point's cell (-1 = outside) for the backward: ddepth / dfeat in the layouts of depth / feat. */
+int a2x_lift_splat_fwd(const float* depth, const float* feat, const float* geom, int B, int N, int D, int fH, int fW, int C,
+                       const float* origin3, const float* dx3, const int* nx3, float* bev, int* cells_ws, a2x_stream_t stream);
+int a2x_lift_splat_bwd(const float* depth, const float* feat, const int* cells_ws, const float* dbev, int B, int N, int D,
+                       int fH, int fW, int C, float* ddepth, float* dfeat, a2x_stream_t stream);
+
 /* ---------------------------------------------------------------- anchor-target assignment (label generation)
  * Replaces VoxelPostprocessor.generate_label_airv2x + collate_batch_airv2x
  * (opencood/data_utils/post_processor/voxel_postprocessor.py:217-354, :392-430) and bbox_overlaps
