@@ -25,6 +25,10 @@ typedef void* a2x_stream_t; /* cudaStream_t */
 /* ---------------------------------------------------------------- library */
 const char* a2x_last_error(void);
 int a2x_version(void);
+/* Bring-up / A-B switches (all 0 = production behaviour; used by tests and profiling scripts only):
+ *   1 tile width override of the tap-GEMM (N per CTA)      7 = 1: disable the halo (3x3 stride-1 A-tile reuse) variants
+ *   8 cap on persistent CTAs (default 148 = one per SM)    10 K-split override of the weight-gradient kernel
+ *   11 = 1: single-CTA reference ranking in the voxeliser   2, 3, 5, 6, 9: UMMA descriptor / epilogue experiments */
 void a2x_debug_set(int key, int value);
 int a2x_device_info(int* sm_count, int* cc_major, int* cc_minor);
 unsigned long long a2x_launch_count(void); /* kernels launched by this library since load */
