@@ -51,3 +51,21 @@ def test_module_refuses_cpu(pkg):
     m = M.Airv2xWhere2com(cfg["model_args"])
     with pytest.raises(RuntimeError, match="no CPU path"):
         _ = m.engine
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md names every C entry point the header declares (brace groups like a2x_conv2d_{fwd,dgrad} expanded),
+    so the reference-side binding table cannot silently go stale."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "airv2x_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(a2x_[a-z0-9_]+)\s*\(", hdr)))
+    known = set(re.findall(r"a2x_[a-z0-9_]+", doc))
+    for m in re.finditer(r"(a2x_[a-z0-9_]*)\{([^}]+)\}", doc):
+        known.update(m.group(1) + part.strip() for part in m.group(2).split(","))
+    prefixes = [m.group(1) for m in re.finditer(r"(a2x_[a-z0-9_]+_)\*", doc)]
+    missing = [n for n in names if n not in known and not any(n.startswith(p) for p in prefixes)]
+    assert len(names) > 70 and not missing, missing
