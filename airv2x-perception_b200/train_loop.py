@@ -18,6 +18,7 @@ import re
 
 import torch
 
+from .dist import GradAverager
 from .labels import TargetAssigner
 
 
@@ -105,6 +106,9 @@ class Trainer:
         self.cls_weight, self.reg_coe = float(la["cls_weight"]), float(la["reg"])
         self.graph = graph
         self.epoch = 0
+        # scene-parallel training (one process per GPU, tools/train.py:161-163 wraps the model in DDP): one flat all-reduce
+        # of the gradients per step; a no-op unless torch.distributed is initialised with world_size > 1
+        self.average_grads = GradAverager(model.parameters())
 
     def labels(self, batch):
         if "label_dict" in batch:
@@ -122,7 +126,8 @@ class Trainer:
             loss3 = model.train_step_graphed(data, labels, self.cls_weight, self.reg_coe)
         else:
             loss3 = model.train_step(data, labels, self.cls_weight, self.reg_coe, **kw)
-        self.optimizer.step()                       # gradients were written into p.grad by the fused step
+        self.average_grads()                        # gradients were written into p.grad by the fused step
+        self.optimizer.step()
         return loss3
 
     def end_epoch(self, saved_path=None):
