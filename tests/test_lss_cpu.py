@@ -56,3 +56,53 @@ def test_host_half_matches_oracle():
     assert np.array_equal(L.depth_bins(*grid["ddiscr"], "LID"), LO.depth_discretization(*grid["ddiscr"], "LID"))
     with pytest.raises(RuntimeError, match="CUDA"):
         L.LiftSplat(grid, final_dim, down, "cpu")
+
+
+def test_bevencode_oracle_matches_reference_golden():
+    """the BEV encoder that consumes the pooled camera features (groundwork for its kernels): oracle == the recorded
+    outputs of the real reference BevEncode, eval and train mode"""
+    from oracle import bevencode_oracle as BO, w2c_oracle as O
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bevencode_small.npz"))
+    in_c, out_c, H, W, seed = int(g["in_c"]), int(g["out_c"]), int(g["h"]), int(g["w"]), int(g["seed"])
+    import torchvision  # noqa: F401  (state_dict key layout = torchvision resnet18 layer1-3)
+
+    shapes = {"conv1.weight": (64, in_c, 7, 7)}
+    for n in ("bn1",):
+        shapes.update({n + ".weight": (64,), n + ".bias": (64,), n + ".running_mean": (64,), n + ".running_var": (64,),
+                       n + ".num_batches_tracked": ()})
+
+    def bn(n, c):
+        return {n + ".weight": (c,), n + ".bias": (c,), n + ".running_mean": (c,), n + ".running_var": (c,),
+                n + ".num_batches_tracked": ()}
+
+    cin = 64
+    for li, c in ((1, 64), (2, 128), (3, 256)):
+        for b in range(2):
+            p = "layer%d.%d" % (li, b)
+            shapes[p + ".conv1.weight"] = (c, cin if b == 0 else c, 3, 3)
+            shapes.update(bn(p + ".bn1", c))
+            shapes[p + ".conv2.weight"] = (c, c, 3, 3)
+            shapes.update(bn(p + ".bn2", c))
+            if b == 0 and li > 1:
+                shapes[p + ".downsample.0.weight"] = (c, cin, 1, 1)
+                shapes.update(bn(p + ".downsample.1", c))
+        cin = c
+    shapes["up1.conv.0.weight"] = (256, 320, 3, 3)
+    shapes.update(bn("up1.conv.1", 256))
+    shapes["up1.conv.3.weight"] = (256, 256, 3, 3)
+    shapes.update(bn("up1.conv.4", 256))
+    shapes["up2.1.weight"] = (128, 256, 3, 3)
+    shapes.update(bn("up2.2", 128))
+    shapes["up2.4.weight"] = (out_c, 128, 1, 1)
+    shapes["up2.4.bias"] = (out_c,)
+    assert len(shapes) == 110
+    sd = O.det_init_state_dict(shapes, seed=seed)
+    x = torch.randn(2, in_c, H, W, generator=torch.Generator().manual_seed(seed + 1))
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ev = BO.bev_encode(sd, x, training=False)
+        tr = BO.bev_encode(sd, x, training=True, buffers={})
+    assert ev.shape == (2, out_c, H, W)
+    assert np.abs(ev[:, ::8, ::4, ::4].numpy() - g["eval_out"]).max() < 1e-5
+    assert np.abs(tr[:, ::8, ::4, ::4].numpy() - g["train_out"]).max() < 1e-4
