@@ -311,6 +311,46 @@ def point_pillar_loss_multiclass(output, target, num_class, cls_weight=1.0, reg_
     return reg_loss + conf_loss + obj_loss, reg_loss, conf_loss, obj_loss
 
 
+def point_pillar_loss(output, target, cls_weight=1.0, reg_coe=2.0):
+    """loss/point_pillar_loss.py:77-166, :168-215 — the 1-class loss of the legacy `point_pillar_*` models: sigmoid focal
+    loss on `psm` (alpha .25, gamma 2; one logit per anchor, normalised by the positives of each sample, summed and
+    divided by B once — the multi-class variant divides twice), smooth-L1 (beta 1/9, sin-difference on yaw) on `rm`,
+    no objectness term. Returns (total, reg, conf)."""
+    rm, psm = output["rm"], output["psm"]
+    B = psm.shape[0]
+    cls_preds = psm.permute(0, 2, 3, 1).contiguous()
+    labels = target["pos_equal_one"].view(B, -1).contiguous()
+    positives = labels > 0
+    negatives = labels == 0
+    cls_weights = (negatives * 1.0 + 1.0 * positives).float()
+    reg_weights = positives.float()
+    pos_norm = positives.sum(1, keepdim=True).float()
+    reg_weights = reg_weights / torch.clamp(pos_norm, min=1.0)
+    cls_weights = cls_weights / torch.clamp(pos_norm, min=1.0)
+    one_hot = torch.zeros(*labels.shape, 2, dtype=cls_preds.dtype, device=labels.device)
+    one_hot.scatter_(-1, labels.unsqueeze(-1).long(), 1.0)
+    inp = cls_preds.view(B, -1, 1)
+    tgt = one_hot[..., 1:]
+    ps = torch.sigmoid(inp)
+    alpha_w = tgt * 0.25 + (1 - tgt) * 0.75
+    pt = tgt * (1.0 - ps) + (1.0 - tgt) * ps
+    focal = alpha_w * torch.pow(pt, 2.0)
+    bce = torch.clamp(inp, min=0) - inp * tgt + torch.log1p(torch.exp(-torch.abs(inp)))
+    conf_loss = (focal * bce * cls_weights.unsqueeze(-1)).sum() / B * cls_weight
+    rmv = rm.permute(0, 2, 3, 1).contiguous().view(B, -1, 7)
+    tg = target["targets"].view(B, -1, 7)
+    p_sin = torch.sin(rmv[..., 6:7]) * torch.cos(tg[..., 6:7])
+    t_sin = torch.cos(rmv[..., 6:7]) * torch.sin(tg[..., 6:7])
+    b1 = torch.cat([rmv[..., :6], p_sin], -1)
+    b2 = torch.cat([tg[..., :6], t_sin], -1)
+    b2 = torch.where(torch.isnan(b2), b1, b2)
+    n = torch.abs(b1 - b2)
+    beta = 1.0 / 9.0
+    sl1 = torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta) * reg_weights.unsqueeze(-1)
+    reg_loss = sl1.sum() / B * reg_coe
+    return reg_loss + conf_loss, reg_loss, conf_loss
+
+
 # --------------------------------------------------------------------------------------------------- legacy model
 def pp_where2comm_forward(sd, args, data_dict, training=False, keep=None):
     """models/point_pillar_where2comm.py:99-151 (`point_pillar_where2comm`, BASELINE config 1; multi_scale branch):

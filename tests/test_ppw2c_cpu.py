@@ -56,3 +56,22 @@ def test_oracle_and_registry_surface():
         assert "CUDA" in str(e)
     else:
         raise AssertionError("forward on CPU parameters must raise")
+
+
+def test_legacy_loss_oracle_matches_reference_golden():
+    """O.point_pillar_loss (the 1-class loss of the legacy models) == the recorded value / gradients of the real
+    reference PointPillarLoss (scripts/make_golden_legacy_loss.py) — groundwork for the legacy training step"""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import make_golden_legacy_loss as G
+
+    gold = np.load(os.path.join(GOLD, "pploss.npz"))
+    psm, rm, lab = G.inputs()
+    a, b = psm.clone().requires_grad_(True), rm.clone().requires_grad_(True)
+    tot, reg, conf = O.point_pillar_loss({"psm": a, "rm": b}, lab, 1.0, 2.0)
+    tot.backward()
+    assert abs(float(tot) - float(gold["total"])) < 1e-9 * float(gold["total"])
+    assert abs(float(reg) - float(gold["reg"])) < 1e-6 and abs(float(conf) - float(gold["conf"])) < 1e-4
+    assert np.abs(a.grad.numpy() - gold["dpsm"]).max() < 1e-7
+    assert np.abs(b.grad[:, :, ::4, ::4].numpy() - gold["drm_sample"]).max() < 1e-7
