@@ -75,3 +75,42 @@ def test_legacy_loss_oracle_matches_reference_golden():
     assert abs(float(reg) - float(gold["reg"])) < 1e-6 and abs(float(conf) - float(gold["conf"])) < 1e-4
     assert np.abs(a.grad.numpy() - gold["dpsm"]).max() < 1e-7
     assert np.abs(b.grad[:, :, ::4, ::4].numpy() - gold["drm_sample"]).max() < 1e-7
+
+
+def test_legacy_train_mode_oracle_matches_reference_golden():
+    """train-mode forward (batch-statistic BN, top-K mask with the reference's `random` draws) + PointPillarLoss + autograd
+    of the oracle == the recorded run of the real reference `point_pillar_where2comm` (scripts/make_golden_legacy_train.py):
+    groundwork for the legacy training step on the kernels"""
+    import random
+    import sys
+
+    import a2x_import
+
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import make_golden_legacy_train as G
+
+    M = a2x_import.pkg("opencood.models.point_pillar_where2comm")
+    cfg, gold = load()
+    tg = np.load(os.path.join(GOLD, "ppw2c_train_small.npz"))
+    model = M.PointPillarWhere2comm(cfg["model_args"])
+    sd = golden_state_dict(model, gold)
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "gaussian" not in k else v.clone())
+         for k, v in sd.items()}
+    torch.set_num_threads(8)
+    random.seed(int(tg["k_seed"]))
+    out, _ = O.pp_where2comm_forward(p, cfg["model_args"], golden_scene(cfg, gold), training=True)
+    lab = G.labels(out["psm"].shape[2], out["psm"].shape[3], cfg["model_args"]["anchor_number"])
+    loss = O.point_pillar_loss(out, lab, 1.0, 2.0)[0]
+    loss.backward()
+    for k in ("psm", "rm"):
+        assert np.abs(out[k].detach().numpy() - tg["train_" + k]).max() < 1e-5, k
+    assert abs(float(loss.detach()) - float(tg["loss"])) < 1e-6 * float(tg["loss"])
+    assert abs(float(out["com"]) - float(tg["train_com"])) < 1e-7
+    n = 0
+    for name in [k[5:] for k in tg.files if k.startswith("grad_")]:
+        g = p[name].grad
+        got = g.flatten()[:: max(1, g.numel() // 256)][:256].numpy()
+        ref = tg["grad_" + name]
+        assert np.abs(got - ref).max() <= 1e-4 * (np.abs(ref).max() + 1e-30) + 1e-9, name
+        n += 1
+    assert n == 77
