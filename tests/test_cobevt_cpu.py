@@ -80,3 +80,37 @@ def test_registry_surface_full_config():
         assert "CUDA" in str(e) or "cuda" in str(e)
     else:
         raise AssertionError("forward on CPU parameters must raise")
+
+
+def test_compressor_train_mode_oracle_matches_reference_golden():
+    """NaiveCompressor in train mode (batch-statistic BN, backward): oracle == the recorded run of the real reference
+    module (scripts/make_golden_compressor_train.py) — groundwork for training with compression > 0"""
+    import os
+    import sys
+
+    import numpy as np
+    import torch
+
+    from oracle import cobevt_oracle as CO, w2c_oracle as O
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import make_golden_compressor_train as G
+
+    g = np.load(os.path.join(root, "tests", "golden", "compressor_train.npz"))
+    c, r = int(g["c"]), int(g["r"])
+    shapes = {}
+    for conv, bn, ci, co in (("encoder.0", "encoder.1", c, c // r), ("decoder.0", "decoder.1", c // r, c), ("decoder.3", "decoder.4", c, c)):
+        shapes[conv + ".weight"], shapes[conv + ".bias"] = (co, ci, 3, 3), (co,)
+        for k, shp in (("weight", (co,)), ("bias", (co,)), ("running_mean", (co,)), ("running_var", (co,)), ("num_batches_tracked", ())):
+            shapes["%s.%s" % (bn, k)] = shp
+    sd = {"naive_compressor." + k: v for k, v in O.det_init_state_dict(shapes, seed=int(g["seed"])).items()}
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    x, w = G.inputs()
+    x = x.requires_grad_(True)
+    y = CO.naive_compressor(p, x, True, {})
+    (y * w).sum().backward()
+    assert np.abs(y.detach()[:, ::16, ::2, ::2].numpy() - g["y"]).max() < 1e-5
+    assert np.abs(x.grad[:, ::16, ::2, ::2].numpy() - g["dx"]).max() < 1e-5
+    ref = g["dw_enc"]
+    assert np.abs(p["naive_compressor.encoder.0.weight"].grad[::8, ::16].numpy() - ref).max() < 1e-4 * np.abs(ref).max()
