@@ -47,7 +47,11 @@ def build(force=False, verbose=False):
         return OUT
     if not os.path.exists(NVCC):
         if os.path.exists(OUT):
-            return OUT  # GPU box without a toolchain change: use the shipped binary
+            # a box without nvcc: use the shipped binary, but say so when it was built from different sources
+            if not (os.path.exists(stamp) and open(stamp).read() == dig):
+                sys.stderr.write("WARNING: libairv2x_b200.so is older than csrc/ (source digest mismatch) and nvcc is "
+                                 "missing: running the stale binary\n")
+            return OUT
         raise RuntimeError("nvcc not found and no prebuilt libairv2x_b200.so")
 
     def compile_one(src):

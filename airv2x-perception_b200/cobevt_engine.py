@@ -16,7 +16,7 @@ import torch
 
 from . import ops
 from .ops import Act
-from .w2c_engine import HEAD_PAD, W2CEngine
+from .w2c_engine import AGENT_TYPES, HEAD_PAD, TYPE_PREFIX, W2CEngine
 
 
 class CoBEVTEngine(W2CEngine):
@@ -490,6 +490,17 @@ class CoBEVTEngine(W2CEngine):
                     ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], d_x[i - 1], accumulate=True)
                 else:
                     ops.conv_dgrad(dz, W[r["conv"]], 3, r["stride"], d_canvas)
+        # agent types absent from this batch get a ZERO gradient (the persistent .grad buffers are overwritten, never
+        # accumulated: without this a type's previous-step gradient would be applied again; the reference's zero_grad()
+        # leaves those grads None and the optimizer skips them)
+        present = {r["type"] for r in rec if r["kind"] == "pfn"}
+        for t in AGENT_TYPES:
+            if t in present:
+                continue
+            for suffix in (".linear.weight", ".norm.weight", ".norm.bias"):
+                g = grads.get(TYPE_PREFIX[t] + ".0.0.pfn_layers.0" + suffix)
+                if g is not None:
+                    g.zero_()
         for r in rec:
             if r["kind"] != "pfn":
                 continue

@@ -131,14 +131,26 @@ class Trainer:
         return loss3
 
     def end_epoch(self, saved_path=None):
+        """scheduler step + checkpoint. Scene-parallel runs: the BatchNorm running statistics (the only buffers; every
+        rank sees different scenes) are broadcast from rank 0 first, like DDP's buffer broadcast (tools/train.py:161-163),
+        rank 0 alone writes the file and every rank waits for it."""
         self.scheduler.step()
         self.epoch += 1
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if multi:
+            for b in self.model.buffers():
+                if b.is_floating_point():
+                    dist.broadcast(b, 0)
         if saved_path is not None:
-            os.makedirs(saved_path, exist_ok=True)
-            torch.save({"epoch": self.epoch - 1, "model_state_dict": self.model.state_dict(),
-                        "optimizer_state_dict": self.optimizer.state_dict(),
-                        "scheduler_state_dict": self.scheduler.state_dict()},
-                       os.path.join(saved_path, "net_epoch%d.pth" % self.epoch))
+            if not multi or dist.get_rank() == 0:
+                os.makedirs(saved_path, exist_ok=True)
+                torch.save({"epoch": self.epoch - 1, "model_state_dict": self.model.state_dict(),
+                            "optimizer_state_dict": self.optimizer.state_dict(),
+                            "scheduler_state_dict": self.scheduler.state_dict()},
+                           os.path.join(saved_path, "net_epoch%d.pth" % self.epoch))
+            if multi:
+                dist.barrier()
 
     def resume(self, saved_path):
         self.epoch, _ = load_saved_model(saved_path, self.model, None, self.optimizer, self.scheduler)

@@ -718,6 +718,17 @@ class W2CEngine:
         block_bwd("A", 0, d_x0, d_canvas, False)
 
         # ---- PillarVFE
+        # agent types absent from this batch get a ZERO gradient (the persistent .grad buffers are overwritten, never
+        # accumulated: without this a type's previous-step gradient would be applied again; the reference's zero_grad()
+        # leaves those grads None and the optimizer skips them)
+        present = {r["type"] for r in rec if r["kind"] == "pfn"}
+        for t in AGENT_TYPES:
+            if t in present:
+                continue
+            for suffix in (".linear.weight", ".norm.weight", ".norm.bias"):
+                g = grads.get(TYPE_PREFIX[t] + ".0.0.pfn_layers.0" + suffix)
+                if g is not None:
+                    g.zero_()
         for r in rec:
             if r["kind"] != "pfn":
                 continue

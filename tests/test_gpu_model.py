@@ -321,3 +321,23 @@ def test_staged_pipeline_matches_graphed_step(small):
     for n, p in pipe_m.named_parameters():
         if p.grad is not None:
             assert torch.allclose(p.grad, g_ref[n], rtol=1e-4, atol=1e-6 * float(g_ref[n].abs().max()) + 1e-12), n
+
+
+def test_absent_agent_type_gets_zero_gradient(small):
+    """the fused step overwrites persistent .grad buffers; a batch WITHOUT an agent type must leave that
+    type's PillarVFE gradients at zero (the reference's zero_grad() leaves them None), not at the previous step's value."""
+    cfg, gold, model, sd, _ = small
+    model.load_state_dict(sd)
+    model.train()
+    pre = cfg["preprocess"]
+    H, W = gold["train_psm"].shape[2:]
+    labels = O.make_labels(3, 1, H, W, cfg["model_args"]["anchor_number"])
+    dd1, _ = C.make_batch(pre, [["vehicle", "rsu", "drone"]], 3000, 5, pre["args"]["max_voxel_train"])
+    dd2, _ = C.make_batch(pre, [["vehicle", "rsu"]], 3000, 6, pre["args"]["max_voxel_train"])
+    random.seed(1)
+    model.train_step(C.to_device(dd1, "cuda"), labels, 1.0, 2.0)
+    drone = [p for n, p in model.named_parameters() if n.startswith("drone_models")]
+    assert all(float(p.grad.abs().max()) > 0 for p in drone)
+    model.train_step(C.to_device(dd2, "cuda"), labels, 1.0, 2.0)
+    assert all(float(p.grad.abs().max()) == 0.0 for p in drone)
+    assert all(float(p.grad.abs().max()) > 0 for n, p in model.named_parameters() if n.startswith("rsu_models"))
