@@ -12,6 +12,7 @@
 #include "../../include/airv2x_b200.h"
 #include "a2x_host.h"
 #include "a2x_ptx.cuh"
+#include "window_attn_tc.cuh"
 
 namespace a2x {
 
@@ -353,6 +354,24 @@ __global__ void __launch_bounds__(128) window_attention_small_kernel(const WinAt
     }
 }
 
+// tcgen05 window attention (window_attn_tc.cuh) applies to 4x4 windows, 32-wide heads, 32..128 tokens in multiples of 16,
+// at most 8 agents (key-mask bits); A2X_ATTN_SIMT=1 forces the fp32 CUDA-core kernels (A/B debugging)
+static bool wt_eligible(int window, int dim_head, int n, int L) {
+    static int simt = -1;
+    if (simt < 0) {
+        const char* e = getenv("A2X_ATTN_SIMT");
+        simt = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return !simt && window == WT_W && dim_head == WT_DH && n % 16 == 0 && n >= 32 && n <= 128 && L <= 8;
+}
+// persistent grid: a multiple of `heads` CTAs (a CTA keeps one head), ctas_per_sm per SM, never more than the work
+static int wt_grid(int num_windows, int heads, int ctas_per_sm) {
+    int groups = (148 * ctas_per_sm) / heads;
+    if (groups > num_windows) groups = num_windows;
+    if (groups < 1) groups = 1;
+    return groups * heads;
+}
+
 static int row_grid(long long rows) {
     long long b = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
     if (b > 148 * 8) b = 148 * 8;
@@ -465,6 +484,21 @@ int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const in
             return 1;
         }
 #undef A2X_WAS
+        A2X_LAUNCHED();
+        A2X_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (wt_eligible(window, dim_head, n, L)) {  // tcgen05 path: S = QK^T and O = PV as bf16x3 UMMA tiles, softmax on the TMEM row
+        WinTcParams q;
+        q.qkv = qkv; q.dout = nullptr; q.bias = bias_table; q.key_mask = key_mask; q.out = tr_split(out); q.dbias = nullptr;
+        q.B = B; q.L = L; q.H = H; q.W = W; q.heads = heads; q.grid_mode = grid_mode; q.scale = scale;
+        const int num_windows = B * (H / window) * (W / window);
+        static int once = 0;
+        if (!once) {
+            A2X_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTF_SMEM));
+            once = 1;
+        }
+        window_attention_tc_fwd_kernel<<<wt_grid(num_windows, heads, 2), 128, WTF_SMEM, st>>>(q, num_windows);
         A2X_LAUNCHED();
         A2X_CHECK_CUDA(cudaGetLastError());
         return 0;
@@ -1054,6 +1088,22 @@ int a2x_window_attention_bwd_split(const float* qkv, const float* dout, const fl
             return 1;
         }
 #undef A2X_WASB
+        A2X_LAUNCHED();
+        A2X_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (a2x::wt_eligible(window, dim_head, n, L)) {
+        a2x::WinTcParams q;
+        q.qkv = qkv; q.dout = dout; q.bias = bias_table; q.key_mask = key_mask; q.out = p.dqkv; q.dbias = dbias_table;
+        q.B = B; q.L = L; q.H = H; q.W = W; q.heads = heads; q.grid_mode = grid_mode; q.scale = scale;
+        const int num_windows = B * (H / window) * (W / window);
+        static int once = 0;
+        if (!once) {
+            A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                a2x::WTB_SMEM));
+            once = 1;
+        }
+        a2x::window_attention_tc_bwd_kernel<<<a2x::wt_grid(num_windows, heads, 1), 128, a2x::WTB_SMEM, st0>>>(q, num_windows);
         A2X_LAUNCHED();
         A2X_CHECK_CUDA(cudaGetLastError());
         return 0;

@@ -58,7 +58,15 @@ def test_regroup(ops):
     assert mask.tolist() == [[1, 1, 0, 0], [1, 1, 1, 0]]
 
 
+def _tc(case):
+    """shapes the tcgen05 attention kernels take (csrc/window_attn_tc.cuh); bf16x3 operands -> 5e-5 instead of 2e-5"""
+    B, L, H, W, heads, dh, w = case
+    return w == 4 and dh == 32 and 32 <= L * 16 <= 128
+
+
 @pytest.mark.parametrize("case", [(2, 7, 8, 16, 8, 32, 4), (1, 3, 8, 8, 4, 64, 2), (1, 5, 4, 12, 16, 16, 4),
+                                  # tcgen05 path: 128 / 32 / 80-token windows (8, 2, 5 agents), more windows than CTAs
+                                  (1, 8, 8, 8, 8, 32, 4), (2, 2, 8, 8, 4, 32, 4), (1, 5, 4, 12, 8, 32, 4), (1, 7, 100, 352, 8, 32, 4),
                                   # small windows (128 / n windows per CTA): the V2X-ViT pyramid shapes, partial groups
                                   (3, 1, 8, 12, 16, 16, 2), (2, 1, 8, 16, 8, 32, 4), (2, 1, 12, 8, 4, 64, 4),
                                   (2, 2, 4, 8, 8, 32, 2), (1, 1, 4, 12, 8, 32, 4)])
@@ -97,7 +105,8 @@ def test_window_attention(ops, case, grid_mode):
         ref = o.permute(0, 3, 4, 1, 5, 2, 6).reshape(B * L, H, W, D)
     else:
         ref = o.permute(0, 3, 1, 4, 2, 5, 6).reshape(B * L, H, W, D)
-    assert rel(out.hi.cpu(), ref) < 2e-5
+    assert rel(out.hi.cpu(), ref) < (5e-5 if _tc(case) else 2e-5)
+    assert torch.equal(out.b16[0], out.hi.to(torch.bfloat16))
 
 
 def test_linear_gelu_residual(ops):
@@ -234,6 +243,7 @@ def test_layernorm_gelu_backward(ops):
 
 
 @pytest.mark.parametrize("case", [(2, 7, 8, 8, 8, 32, 4), (1, 3, 4, 8, 4, 16, 2),
+                                  (1, 8, 8, 8, 8, 32, 4), (2, 2, 8, 8, 4, 32, 4), (1, 5, 4, 12, 8, 32, 4), (1, 7, 48, 64, 8, 32, 4),
                                   # small windows (V2X-ViT pyramid): 128 / n windows per CTA
                                   (3, 1, 8, 12, 16, 16, 2), (2, 1, 8, 16, 8, 32, 4), (2, 1, 12, 8, 4, 64, 4), (1, 1, 4, 12, 8, 32, 4)])
 @pytest.mark.parametrize("grid_mode", [False, True])
@@ -263,8 +273,9 @@ def test_window_attention_backward(ops, case, grid_mode):
     dbias = torch.zeros(table.shape, device="cuda")
     ops.window_attention_bwd(qkv.detach().float().cuda(), dout.float().cuda(), table.detach().float().cuda(), mask.cuda(), B, L,
                              heads, dh, w, grid_mode, dqkv, dbias)
-    assert rel(dqkv.cpu().double(), qkv.grad) < 2e-5
-    assert rel(dbias.cpu().double(), table.grad) < 2e-5
+    tol = 5e-5 if _tc(case) else 2e-5
+    assert rel(dqkv.cpu().double(), qkv.grad) < tol
+    assert rel(dbias.cpu().double(), table.grad) < tol
 
 
 def test_train_step_matches_oracle_autograd():

@@ -82,7 +82,10 @@ def _w2c_eval(cfg, model, sd, gold, cache):
     _full_diff(out, ora)                                            # every cell, against the oracle
     for k in ("psm", "rm", "obj"):
         assert torch.equal(out[k], raw[k]), k                       # GPU voxeliser == CPU voxeliser at 60k points
-    assert out["comm_rate"] == int(gold["eval_comm_rate"]) == ora["comm_rate"] == raw["comm_rate"]
+    # comm_rate = count_nonzero(BEV canvas) (airv2x_where2com.py:122): of the 8.2 M positive PillarVFE outputs a handful sit
+    # within an fp32 ulp of the ReLU's zero, so the count may differ from the reference's by a few units (1e-6 relative)
+    assert ora["comm_rate"] == int(gold["eval_comm_rate"]) and out["comm_rate"] == raw["comm_rate"]
+    assert abs(out["comm_rate"] - ora["comm_rate"]) <= max(2, int(1e-6 * ora["comm_rate"])), (out["comm_rate"], ora["comm_rate"])
     assert abs(float(out["com"]) - float(gold["eval_com"])) < 1e-6
     cache["eval"] = (out, ora)
 
@@ -256,7 +259,7 @@ def test_config3_v2xvit_eval_full_size():
     with torch.no_grad():
         out = model(C.to_device(dd, "cuda"))
     FC.compare_with_golden(out, gold, "eval_", TOL)                    # the reference ran L = 15 padded
-    assert out["comm_rate"] == int(gold["eval_comm_rate"])
+    assert abs(out["comm_rate"] - int(gold["eval_comm_rate"])) <= max(2, int(1e-6 * int(gold["eval_comm_rate"])))
     # every cell, against the oracle on the valid agents only (exact: padded agents are masked keys)
     n = len(FC.AGENTS)
     a5 = copy.deepcopy(args)
