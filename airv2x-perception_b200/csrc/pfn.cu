@@ -168,6 +168,12 @@ __global__ void pfn_stats_finalize_kernel(const double* __restrict__ moments, do
 }
 
 // ------------------------------------------------------------------------------------------------ forward + scatter
+// One warp per pillar. Lane = point slot while the 10 features are built (pillar mean by shuffles); then lane = channel
+// pair (c, c + 32): the warp walks over the pillar's REAL points only — a synthetic 60k-point cloud has ~2 points per
+// pillar, the other 30 slots are zero rows whose PFN output is the per-channel constant relu(shift_c) — broadcasting a
+// point's features by shuffle and keeping the running max / arg-max (lowest slot among ties, like a max over the 32
+// slots in slot order; the padded slots enter once, as slot `num`). ~130 instructions per pillar instead of ~1300 for
+// the all-slots butterfly. The arithmetic per (slot, channel) is unchanged: products in k order, fma(y, scale, shift).
 __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restrict__ voxels,
                                                           const int* __restrict__ num_points,
                                                           const int* __restrict__ coords, PfnGeom g, long long M,
@@ -176,96 +182,88 @@ __global__ void __launch_bounds__(256) pfn_scatter_kernel(const float* __restric
                                                           const float* __restrict__ shift,
                                                           const int* __restrict__ agent_map, SplitOut canvas,
                                                           float* __restrict__ pillar_out /* [M][64] or null */,
-                                                          unsigned char* __restrict__ amax /* [M][64] or null */) {
-    __shared__ float sW[NC * 12];  // rows padded to 12 floats for float4 reads
-    __shared__ float sS[NC], sB[NC];
-    for (int i = threadIdx.x; i < NC * 12; i += blockDim.x) {
-        const int c = i / 12, k = i % 12;
-        sW[i] = k < NF ? W[c * NF + k] : 0.f;
-    }
-    for (int i = threadIdx.x; i < NC; i += blockDim.x) {
-        sS[i] = scale[i];
-        sB[i] = shift[i];
-    }
-    __syncthreads();
+                                                          unsigned char* __restrict__ amax /* [M][64] or null */,
+                                                          unsigned long long* __restrict__ nz_count /* or null */) {
     const int lane = threadIdx.x & 31;
+    float w0[NF], w1[NF];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+        w0[k] = W[lane * NF + k];
+        w1[k] = W[(lane + 32) * NF + k];
+    }
+    const float sc0 = scale[lane], sc1 = scale[lane + 32], sh0 = shift[lane], sh1 = shift[lane + 32];
+    const float pad0 = sh0 > 0.f ? sh0 : 0.f, pad1 = sh1 > 0.f ? sh1 : 0.f;   // PFN output of an all-zero (padded) slot
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned int nz = 0;
     for (long long pp = warp0; pp < M; pp += nwarps) {
         long long pil;
         if (!seg_resolve(sg, pp, pil)) continue;
         float f[NF];
         int num, agent, cy, cx;
         pillar_features(voxels, num_points, coords, g, pil, lane, f, num, agent, cy, cx);
-        // y[c] for 32 channels at a time in registers (lane = point slot), then a butterfly transpose-reduce: lane L ends
-        // with max over the 32 slots of channel c0 + L (31 shuffles per 32 channels instead of 32 warp reductions + 32
-        // per-lane selects). Values are >= +0 after the ReLU, so unsigned order == float order.
-        float outv[2];
-        unsigned int amv[2] = {0, 0};
+        float best0 = -1.f, best1 = -1.f;   // outputs are >= +0 after the ReLU: the first slot always wins over the init
+        int arg0 = 0, arg1 = 0;
+        const int np = num < 32 ? num : 32;
+        for (int s = 0; s < np; ++s) {
+            float fs[NF];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            unsigned int yv[32], keep[32];
+            for (int k = 0; k < NF; ++k) fs[k] = __shfl_sync(0xffffffffu, f[k], s);
+            float y0 = fs[0] * w0[0], y1 = fs[0] * w1[0];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int c = half * 32 + j;
-                const float4 w0 = *reinterpret_cast<const float4*>(&sW[c * 12]);
-                const float4 w1 = *reinterpret_cast<const float4*>(&sW[c * 12 + 4]);
-                const float2 w2 = *reinterpret_cast<const float2*>(&sW[c * 12 + 8]);
-                float y = f[0] * w0.x;
-                y = fmaf(f[1], w0.y, y);
-                y = fmaf(f[2], w0.z, y);
-                y = fmaf(f[3], w0.w, y);
-                y = fmaf(f[4], w1.x, y);
-                y = fmaf(f[5], w1.y, y);
-                y = fmaf(f[6], w1.z, y);
-                y = fmaf(f[7], w1.w, y);
-                y = fmaf(f[8], w2.x, y);
-                y = fmaf(f[9], w2.y, y);
-                y = fmaf(y, sS[c], sB[c]);
-                y = y > 0.f ? y : 0.f;  // +0 for every non-positive value
-                yv[j] = __float_as_uint(y);
-                keep[j] = yv[j];
+            for (int k = 1; k < NF; ++k) {
+                y0 = fmaf(fs[k], w0[k], y0);
+                y1 = fmaf(fs[k], w1[k], y1);
             }
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
-                const bool up = (lane & s) != 0;
-#pragma unroll
-                for (int i = 0; i < s; ++i) {
-                    const unsigned int send = up ? yv[i] : yv[i + s];
-                    const unsigned int mine = up ? yv[i + s] : yv[i];
-                    yv[i] = max(mine, __shfl_xor_sync(0xffffffffu, send, s));
-                }
+            y0 = fmaf(y0, sc0, sh0);
+            y1 = fmaf(y1, sc1, sh1);
+            y0 = y0 > 0.f ? y0 : 0.f;
+            y1 = y1 > 0.f ? y1 : 0.f;
+            if (y0 > best0) {
+                best0 = y0;
+                arg0 = s;
             }
-            outv[half] = __uint_as_float(yv[0]);
-            if (amax != nullptr) {  // arg-max slot (lowest slot among ties) of channel c0 + lane, for the backward
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const unsigned int mj = __shfl_sync(0xffffffffu, yv[0], j);
-                    const unsigned int who = __ffs(__ballot_sync(0xffffffffu, keep[j] == mj)) - 1;
-                    if (lane == j) amv[half] = who;
-                }
+            if (y1 > best1) {
+                best1 = y1;
+                arg1 = s;
             }
         }
-        const float out0 = outv[0], out1 = outv[1];
-        const unsigned int am0 = amv[0], am1 = amv[1];
+        if (np < 32) {
+            if (pad0 > best0) {
+                best0 = pad0;
+                arg0 = np;
+            }
+            if (pad1 > best1) {
+                best1 = pad1;
+                arg1 = np;
+            }
+        }
+        nz += (best0 != 0.f) + (best1 != 0.f);
         const long long cell = ((long long)agent_map[agent] * g.ny + cy) * g.nx + cx;
-        float* o = canvas.hi + cell * NC;
-        o[lane] = out0;
-        o[lane + 32] = out1;
+        if (canvas.hi != nullptr) {
+            float* o = canvas.hi + cell * NC;
+            o[lane] = best0;
+            o[lane + 32] = best1;
+        }
         if (canvas.b16 != nullptr) {
             __nv_bfloat16* hb = canvas.b16 + cell * NC;
             __nv_bfloat16* lb = hb + canvas.ps;
-            split_bf16(out0, hb[lane], lb[lane]);
-            split_bf16(out1, hb[lane + 32], lb[lane + 32]);
+            split_bf16(best0, hb[lane], lb[lane]);
+            split_bf16(best1, hb[lane + 32], lb[lane + 32]);
         }
         if (pillar_out != nullptr) {
-            pillar_out[pil * NC + lane] = out0;
-            pillar_out[pil * NC + lane + 32] = out1;
+            pillar_out[pil * NC + lane] = best0;
+            pillar_out[pil * NC + lane + 32] = best1;
         }
         if (amax != nullptr) {
-            amax[pil * NC + lane] = (unsigned char)am0;
-            amax[pil * NC + lane + 32] = (unsigned char)am1;
+            amax[pil * NC + lane] = (unsigned char)arg0;
+            amax[pil * NC + lane + 32] = (unsigned char)arg1;
         }
+    }
+    if (nz_count != nullptr) {   // count_nonzero of the canvas (airv2x_where2com.py:122): every cell is written at most once
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        if (lane == 0 && nz) atomicAdd(nz_count, (unsigned long long)nz);
     }
 }
 
@@ -432,16 +430,25 @@ int a2x_pfn_scatter(const float* voxels, const int* num_points, const int* coord
                     const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift,
                     const int* agent_map, const a2x_output* canvas, float* pillar_out, unsigned char* amax,
                     a2x_stream_t stream) {
+    return a2x_pfn_scatter_ex(voxels, num_points, coords, m, geom, seg, w, scale, shift, agent_map, canvas, pillar_out, amax,
+                              nullptr, stream);
+}
+
+int a2x_pfn_scatter_ex(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
+                       const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift,
+                       const int* agent_map, const a2x_output* canvas, float* pillar_out, unsigned char* amax,
+                       long long* nonzero_count, a2x_stream_t stream) {
     const PfnSeg sg = make_seg(seg, &m);
-    A2X_REQUIRE(voxels && num_points && coords && geom && w && scale && shift && agent_map && canvas && canvas->hi &&
-                    m > 0,
+    A2X_REQUIRE(voxels && num_points && coords && geom && w && scale && shift && agent_map && canvas &&
+                    (canvas->hi || canvas->b16) && m > 0,
                 "pfn_scatter: bad args");
     SplitOut so;
     so.hi = canvas->hi;
     so.b16 = (__nv_bfloat16*)canvas->b16;
     so.ps = canvas->b16_plane;
     pfn_scatter_kernel<<<warp_grid(m), 256, 0, (cudaStream_t)stream>>>(voxels, num_points, coords, make_geom(geom), m,
-                                                                     sg, w, scale, shift, agent_map, so, pillar_out, amax);
+                                                                     sg, w, scale, shift, agent_map, so, pillar_out, amax,
+                                                                     (unsigned long long*)nonzero_count);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

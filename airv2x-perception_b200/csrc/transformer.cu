@@ -493,12 +493,9 @@ int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const in
         q.qkv = qkv; q.dout = nullptr; q.bias = bias_table; q.key_mask = key_mask; q.out = tr_split(out); q.dbias = nullptr;
         q.B = B; q.L = L; q.H = H; q.W = W; q.heads = heads; q.grid_mode = grid_mode; q.scale = scale;
         const int num_windows = B * (H / window) * (W / window);
-        static int once = 0;
-        if (!once) {
-            A2X_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTF_SMEM));
-            once = 1;
-        }
-        window_attention_tc_fwd_kernel<<<wt_grid(num_windows, heads, 2), 128, WTF_SMEM, st>>>(q, num_windows);
+        const int smem_tc = wt_smem_bytes(n, false);
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
+        window_attention_tc_kernel<false><<<wt_grid(num_windows, heads, 1), 256, smem_tc, st>>>(q, num_windows);
         A2X_LAUNCHED();
         A2X_CHECK_CUDA(cudaGetLastError());
         return 0;
@@ -1097,13 +1094,9 @@ int a2x_window_attention_bwd_split(const float* qkv, const float* dout, const fl
         q.qkv = qkv; q.dout = dout; q.bias = bias_table; q.key_mask = key_mask; q.out = p.dqkv; q.dbias = dbias_table;
         q.B = B; q.L = L; q.H = H; q.W = W; q.heads = heads; q.grid_mode = grid_mode; q.scale = scale;
         const int num_windows = B * (H / window) * (W / window);
-        static int once = 0;
-        if (!once) {
-            A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                a2x::WTB_SMEM));
-            once = 1;
-        }
-        a2x::window_attention_tc_bwd_kernel<<<a2x::wt_grid(num_windows, heads, 1), 128, a2x::WTB_SMEM, st0>>>(q, num_windows);
+        const int smem_tc = a2x::wt_smem_bytes(n, true);
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
+        a2x::window_attention_tc_kernel<true><<<a2x::wt_grid(num_windows, heads, 1), 256, smem_tc, st0>>>(q, num_windows);
         A2X_LAUNCHED();
         A2X_CHECK_CUDA(cudaGetLastError());
         return 0;

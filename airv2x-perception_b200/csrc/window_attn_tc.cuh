@@ -3,7 +3,10 @@
 // and its autograd for windows of n = L*w*w tokens, n % 16 == 0, n <= 128 (config 4: 7 agents x 4x4 = 112), w = 4,
 // dim_head = 32. The small windows of the V2X-ViT pyramid (4 / 16 tokens) stay on the packed SIMT kernels.
 //
-// A persistent CTA (128 threads) owns one head and walks over windows; thread t <-> token t <-> TMEM lane t.
+// A persistent CTA owns one head and walks over windows. Two warpgroups: the LOADER (warps 4-7) gathers the q / k / v (/ dO)
+// rows of the next window from global memory, splits them and fills one of two tile buffers; the COMPUTE group (warps
+// 0-3: thread t <-> token t <-> TMEM lane t) issues the MMAs, runs the softmax and the epilogue. full / empty mbarriers
+// per buffer (empty is arrived by tcgen05.commit of the window's last MMA), so global latency is off the compute path.
 // Every operand is the bf16 split pair of an fp32 row, kept side by side in ONE 128-byte shared-memory row
 // [hi(32) | lo(32)] with the 128-byte swizzle, so a tile is simply 128 rows x 128 B and the UMMA descriptors decide how
 // it is read:
@@ -25,10 +28,10 @@
 
 namespace a2x {
 
-constexpr int WT_TILE = 128 * 128;  // bytes: 128 rows x 128 B
 constexpr int WT_W = 4;             // window edge
 constexpr int WT_S2 = 2 * WT_W - 1;
 constexpr int WT_DH = 32;
+constexpr int WT_AUX = 4096 + 4096 + 2 * 1024 + 256;   // bias | bias gradient | token tables (2) | barriers, TMEM slot
 
 struct WinTcParams {
     const float* qkv;      // [B*L][H][W][3*D]
@@ -41,7 +44,8 @@ struct WinTcParams {
     float scale;
 };
 
-// byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte-swizzled [rows][128 B] tile
+// A tile is n rows x 128 B (TS = n * 128 bytes, a multiple of 1024) with the 128-byte swizzle.
+// byte offset of 16-byte chunk c (0..7) of row r:
 __device__ __forceinline__ uint32_t wt_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 __device__ __forceinline__ void wt_split2(float a, float b, uint32_t& h, uint32_t& l) {
@@ -63,16 +67,17 @@ __device__ __forceinline__ void wt_store8_hl(uint8_t* tile, int r, int c8, float
     *reinterpret_cast<uint4*>(tile + wt_off(r, 4 + c8)) = l;
 }
 
-// 8 consecutive probabilities of row r (keys 8*c16 .. 8*c16+7, c16 = 0..15) -> split planes (hi at `plane`, lo at plane + 2 tiles)
-__device__ __forceinline__ void wt_store8_planes(uint8_t* plane, int r, int c16, const float* v) {
+// 8 consecutive probabilities of row r (keys 8*c16 .. 8*c16+7, c16 = 0..15) -> split planes: hi atoms at plane + {0, TS},
+// lo atoms at plane + {2 TS, 3 TS}
+__device__ __forceinline__ void wt_store8_planes(uint8_t* plane, uint32_t TS, int r, int c16, const float* v) {
     uint4 h, l;
     wt_split2(v[0], v[1], h.x, l.x);
     wt_split2(v[2], v[3], h.y, l.y);
     wt_split2(v[4], v[5], h.z, l.z);
     wt_split2(v[6], v[7], h.w, l.w);
-    const uint32_t off = (uint32_t)(c16 >> 3) * WT_TILE + wt_off(r, c16 & 7);
+    const uint32_t off = (uint32_t)(c16 >> 3) * TS + wt_off(r, c16 & 7);
     *reinterpret_cast<uint4*>(plane + off) = h;
-    *reinterpret_cast<uint4*>(plane + 2 * WT_TILE + off) = l;
+    *reinterpret_cast<uint4*>(plane + 2 * TS + off) = l;
 }
 
 __device__ __forceinline__ long long wt_token(const WinTcParams& p, int b, int x, int y, int X, int Y, int t) {
@@ -82,16 +87,42 @@ __device__ __forceinline__ long long wt_token(const WinTcParams& p, int b, int x
     return ((long long)(b * p.L + l) * p.H + ph) * p.W + pw;
 }
 
-// rows of `src` (row stride `rs` floats, 32 floats used from column `c0`) -> [hi | lo] tile; optional scale
-__device__ __forceinline__ void wt_load_tile(uint8_t* tile, const float* src, long long rs, int c0, const long long* sTok,
-                                             int n, float scale) {
-    for (int idx = threadIdx.x; idx < n * 4; idx += 128) {
-        const int r = idx >> 2, c8 = idx & 3;
-        const float4* g = reinterpret_cast<const float4*>(src + sTok[r] * rs + c0 + c8 * 8);
-        float4 a = __ldg(g), b = __ldg(g + 1);
-        a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
-        b.x *= scale; b.y *= scale; b.z *= scale; b.w *= scale;
-        wt_store8_hl(tile, r, c8, a, b);
+__device__ __forceinline__ void wt_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// NT tensors' rows (32 floats each, tensor k at `src[k]` + token * rs[k]) -> [hi | lo] tiles at tile0 + toff[k].
+// ALL global loads of the window are issued before the first conversion (n * 4 <= 512 items of 32 B per tensor for the
+// 128 loader threads: one round trip to L2 / HBM per window, 2 * 4 * NT float4 registers in flight).
+template <int NT>
+__device__ __forceinline__ void wt_load_tiles(uint8_t* tile0, const uint32_t (&toff)[NT], const float* const (&src)[NT],
+                                              const long long (&rs)[NT], const float (&scale)[NT],
+                                              const long long* sTok, int n, int tl) {
+    float4 a[NT][4], b[NT][4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = tl + it * 128;
+        if (idx < n * 4) {
+            const long long tok = sTok[idx >> 2];
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const float4* g = reinterpret_cast<const float4*>(src[k] + tok * rs[k] + (idx & 3) * 8);
+                a[k][it] = __ldg(g);
+                b[k][it] = __ldg(g + 1);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int idx = tl + it * 128;
+            if (idx < n * 4) {
+                float4 x = a[k][it], y = b[k][it];
+                const float sc = scale[k];
+                x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
+                y.x *= sc; y.y *= sc; y.z *= sc; y.w *= sc;
+                wt_store8_hl(tile0 + toff[k], idx >> 2, idx & 3, x, y);
+            }
+        }
     }
 }
 
@@ -108,15 +139,15 @@ __device__ __forceinline__ void wt_mma_qk(uint32_t tacc, uint32_t a_lo, uint32_t
 
 // D[128 x 64] = (Ph + Pl) [Bh | Bl]:  A = split planes of P / dS, read K-major (a_mn = 0: rows = M) or MN-major
 // (a_mn = 1: rows = K); B = an [hi | lo] tile read MN-major (rows = K). nk = n / 16 k-steps.
-__device__ __forceinline__ void wt_mma_pv(uint32_t tacc, uint32_t plane_addr, uint32_t b_addr, int nk, int a_mn) {
+__device__ __forceinline__ void wt_mma_pv(uint32_t tacc, uint32_t plane_addr, uint32_t b_addr, uint32_t TS, int nk, int a_mn) {
     constexpr uint32_t hi = desc_hi_word(1024, 2);
     const uint32_t idesc = make_idesc_bf16(128, 64, (uint32_t)a_mn, 1);
-    const uint32_t b_lo = desc_lo_word(b_addr, WT_TILE);
+    const uint32_t b_lo = desc_lo_word(b_addr, TS);
     uint32_t acc = 0;
     for (int pl = 0; pl < 2; ++pl) {
-        const uint32_t a_lo = desc_lo_word(plane_addr + pl * 2 * WT_TILE, a_mn ? WT_TILE : 16);
+        const uint32_t a_lo = desc_lo_word(plane_addr + pl * 2 * TS, a_mn ? TS : 16);
         for (int kk = 0; kk < nk; ++kk) {
-            const uint32_t a_off = a_mn ? (uint32_t)kk * (2048 >> 4) : (uint32_t)(kk >> 2) * (WT_TILE >> 4) + (uint32_t)(kk & 3) * 2;
+            const uint32_t a_off = a_mn ? (uint32_t)kk * (2048 >> 4) : (uint32_t)(kk >> 2) * (TS >> 4) + (uint32_t)(kk & 3) * 2;
             umma_bf16_lh(tacc, a_lo + a_off, hi, b_lo + (uint32_t)kk * (2048 >> 4), hi, idesc, acc);
             acc = 1;
         }
@@ -144,282 +175,282 @@ __device__ __forceinline__ float wt_scores(uint32_t trow, int n, int t, uint32_t
     return m;
 }
 
-constexpr int WTF_SMEM = 4 * WT_TILE + WT_TILE + 4096 + 1024 + 256 + 1024;   // P planes (over Q, K) | V | bias | tokens | barrier | align
-
-__global__ void __launch_bounds__(128, 2) window_attention_tc_fwd_kernel(const WinTcParams p, int num_windows) {
-    extern __shared__ uint8_t wt_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wt_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* tQ = smem;                      // Q tile, later P planes (4 tiles: hi atoms 0-1, lo atoms 0-1)
-    uint8_t* tK = smem + WT_TILE;
-    uint8_t* tV = smem + 4 * WT_TILE;
-    float* sB = reinterpret_cast<float*>(smem + 5 * WT_TILE);
-    long long* sTok = reinterpret_cast<long long*>(smem + 5 * WT_TILE + 4096);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 5 * WT_TILE + 4096 + 1024);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-
-    const int t = threadIdx.x, warp = t >> 5;
-    const int n = p.L * 16;
-    const int D = p.heads * WT_DH;
-    const int X = p.H / WT_W, Y = p.W / WT_W;
-    const int head = blockIdx.x % p.heads;
-    const int G = gridDim.x / p.heads;
-    const int nb = (2 * p.L - 1) * WT_S2 * WT_S2;
-    for (int i = t; i < nb; i += 128) sB[i] = p.bias[i * p.heads + head];
-    if (t == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) tmem_alloc<128>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)n, 0, 0);
-    uint32_t ph = 0;
-
-    for (int win = blockIdx.x / p.heads; win < num_windows; win += G) {
-        const int y = win % Y, x = (win / Y) % X, b = win / (Y * X);
-        if (t < n) sTok[t] = wt_token(p, b, x, y, X, Y, t);
-        uint32_t kmask = 0xffffffffu;
-        if (p.key_mask != nullptr) {
-            kmask = 0;
-            for (int l = 0; l < p.L; ++l) kmask |= (p.key_mask[b * p.L + l] != 0 ? 1u : 0u) << l;
-        }
-        __syncthreads();
-        wt_load_tile(tQ, p.qkv, 3 * D, head * WT_DH, sTok, n, p.scale);
-        wt_load_tile(tK, p.qkv, 3 * D, D + head * WT_DH, sTok, n, 1.f);
-        wt_load_tile(tV, p.qkv, 3 * D, 2 * D + head * WT_DH, sTok, n, 1.f);
-        fence_proxy_async();
-        __syncthreads();
-        if (t == 0) {
-            tc_fence_after();
-            wt_mma_qk(tmem, desc_lo_word(smem_u32(tQ), 16), desc_lo_word(smem_u32(tK), 16), idesc_s);
-            umma_commit(bar);
-        }
-        mbar_wait(bar, ph);
-        ph ^= 1;
-        tc_fence_after();
-        float s[128];
-        const float m = wt_scores(trow, n, t, kmask, sB, p.L, s);
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 128; ++j) {
-            s[j] = __expf(s[j] - m);
-            sum += s[j];
-        }
-        // every thread has read its S row and the S MMAs have retired: P may overwrite Q / K, O may overwrite S
-#pragma unroll
-        for (int c = 0; c < 16; ++c)
-            if (c * 8 < n) wt_store8_planes(tQ, t, c, s + c * 8);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (t == 0) {
-            tc_fence_after();
-            wt_mma_pv(tmem, smem_u32(tQ), smem_u32(tV), n >> 4, 0);
-            umma_commit(bar);
-        }
-        mbar_wait(bar, ph);
-        ph ^= 1;
-        tc_fence_after();
-        float o[64];
-        tmem_ld_32x32(trow, o);
-        tmem_ld_32x32(trow + 32, o + 32);
-        tmem_ld_wait();
-        if (t < n) {
-            const float inv = 1.f / sum;
-            const long long off = sTok[t] * D + head * WT_DH;
-#pragma unroll
-            for (int c = 0; c < 32; c += 4)
-                store_split4(p.out, off + c, make_float4((o[c] + o[32 + c]) * inv, (o[c + 1] + o[33 + c]) * inv,
-                                                         (o[c + 2] + o[34 + c]) * inv, (o[c + 3] + o[35 + c]) * inv));
-        }
-        tc_fence_before();
-        __syncthreads();   // tiles, token table and TMEM are reused by the next window
-    }
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<128>(tmem);
+__device__ __forceinline__ uint32_t wt_kmask(const WinTcParams& p, int b) {
+    if (p.key_mask == nullptr) return 0xffffffffu;
+    uint32_t k = 0;
+    for (int l = 0; l < p.L; ++l) k |= (p.key_mask[b * p.L + l] != 0 ? 1u : 0u) << l;
+    return k;
 }
 
-// backward: tiles Q | K | V | dO, P planes (4 tiles), dS planes (4 tiles), bias, bias gradient, tokens, barrier
-constexpr int WTB_SMEM = 12 * WT_TILE + 4096 + 4096 + 1024 + 256 + 1024;
+// shared memory: forward 2 buffers x [Q | K | . | . | V] (P planes overlay Q, K and the two spare tiles) = 10 TS;
+// backward 2 buffers x [Q | K | V | dO] + ONE set of split planes (4 TS) that holds P for dV = P^T dO and then dS for
+// dK / dQ = 12 TS (168 KB at 112 tokens, 192 KB at 128); + WT_AUX + 1 KB alignment slack
+__host__ __device__ constexpr int wt_smem_bytes(int n, bool bwd) { return (bwd ? 12 : 10) * n * 128 + WT_AUX + 1024; }
 
-__global__ void __launch_bounds__(128, 1) window_attention_tc_bwd_kernel(const WinTcParams p, int num_windows) {
+struct WtSmem {
+    uint8_t* base;
+    float* sB;
+    float* sdB;
+    long long* sTok;      // [2][128]
+    uint64_t *full, *empty, *mma;
+    uint32_t* tmem_slot;
+};
+__device__ __forceinline__ WtSmem wt_carve(uint8_t* raw, int tiles_bytes) {
+    WtSmem w;
+    w.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* aux = w.base + tiles_bytes;
+    w.sB = reinterpret_cast<float*>(aux);
+    w.sdB = reinterpret_cast<float*>(aux + 4096);
+    w.sTok = reinterpret_cast<long long*>(aux + 8192);
+    w.full = reinterpret_cast<uint64_t*>(aux + 8192 + 2048);
+    w.empty = w.full + 2;
+    w.mma = w.empty + 2;
+    w.tmem_slot = reinterpret_cast<uint32_t*>(w.mma + 1);
+    return w;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTcParams p, int num_windows) {
     extern __shared__ uint8_t wt_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wt_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* tQ = smem;
-    uint8_t* tK = smem + WT_TILE;
-    uint8_t* tV = smem + 2 * WT_TILE;
-    uint8_t* tO = smem + 3 * WT_TILE;        // dO
-    uint8_t* tP = smem + 4 * WT_TILE;        // P planes
-    uint8_t* tS = smem + 8 * WT_TILE;        // dS planes
-    float* sB = reinterpret_cast<float*>(smem + 12 * WT_TILE);
-    float* sdB = sB + 1024;
-    long long* sTok = reinterpret_cast<long long*>(smem + 12 * WT_TILE + 8192);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 12 * WT_TILE + 8192 + 1024);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-
-    const int t = threadIdx.x, warp = t >> 5;
     const int n = p.L * 16;
+    const uint32_t TS = (uint32_t)n * 128;
+    constexpr int BUF_TILES = BWD ? 4 : 5;
+    const WtSmem sm = wt_carve(wt_raw, (BWD ? 12 : 10) * (int)TS);
+    uint8_t* tP = sm.base + 8 * TS;       // backward: the split planes (P, then dS)
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int D = p.heads * WT_DH;
     const int X = p.H / WT_W, Y = p.W / WT_W;
     const int head = blockIdx.x % p.heads;
     const int G = gridDim.x / p.heads;
     const int nb = (2 * p.L - 1) * WT_S2 * WT_S2;
-    for (int i = t; i < nb; i += 128) {
-        sB[i] = p.bias[i * p.heads + head];
-        sdB[i] = 0.f;
+    for (int i = tid; i < nb; i += 256) {
+        sm.sB[i] = p.bias[i * p.heads + head];
+        sm.sdB[i] = 0.f;
     }
-    if (t == 0) {
-        mbar_init(bar, 1);
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sm.full[b], 128);
+            mbar_init(&sm.empty[b], 1);
+        }
+        mbar_init(sm.mma, 1);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    constexpr uint32_t TM_COLS = BWD ? 512 : 128;
+    if (warp == 0) tmem_alloc<TM_COLS>(sm.tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t tacc = trow + 256;    // this thread's row of sum_windows dS (bias gradient), columns [256, 384)
-    const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)n, 0, 0);
-    const int li = t >> 4, i1 = (t >> 2) & 3, i2 = t & 3;
-    const int bbase = ((li + p.L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1);
-    uint32_t ph = 0;
-    {
-        float z[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_st_32x32(tacc + c * 32, z);
-        tmem_st_wait();
-    }
+    const uint32_t tmem = *sm.tmem_slot;
 
-    for (int win = blockIdx.x / p.heads; win < num_windows; win += G) {
-        const int y = win % Y, x = (win / Y) % X, b = win / (Y * X);
-        if (t < n) sTok[t] = wt_token(p, b, x, y, X, Y, t);
-        uint32_t kmask = 0xffffffffu;
-        if (p.key_mask != nullptr) {
-            kmask = 0;
-            for (int l = 0; l < p.L; ++l) kmask |= (p.key_mask[b * p.L + l] != 0 ? 1u : 0u) << l;
-        }
-        __syncthreads();
-        wt_load_tile(tQ, p.qkv, 3 * D, head * WT_DH, sTok, n, p.scale);
-        wt_load_tile(tK, p.qkv, 3 * D, D + head * WT_DH, sTok, n, 1.f);
-        wt_load_tile(tV, p.qkv, 3 * D, 2 * D + head * WT_DH, sTok, n, 1.f);
-        wt_load_tile(tO, p.dout, D, head * WT_DH, sTok, n, 1.f);
-        fence_proxy_async();
-        __syncthreads();
-        if (t == 0) {
-            tc_fence_after();
-            wt_mma_qk(tmem, desc_lo_word(smem_u32(tQ), 16), desc_lo_word(smem_u32(tK), 16), idesc_s);          // S
-            wt_mma_qk(tmem + 128, desc_lo_word(smem_u32(tO), 16), desc_lo_word(smem_u32(tV), 16), idesc_s);    // dP = dO V^T
-            umma_commit(bar);
-        }
-        mbar_wait(bar, ph);
-        ph ^= 1;
-        tc_fence_after();
-        float s[128];
-        const float m = wt_scores(trow, n, t, kmask, sB, p.L, s);
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 128; ++j) {
-            s[j] = __expf(s[j] - m);
-            sum += s[j];
-        }
-        const float inv = 1.f / sum;
-#pragma unroll
-        for (int j = 0; j < 128; ++j) s[j] *= inv;                       // P
-#pragma unroll
-        for (int c = 0; c < 16; ++c)
-            if (c * 8 < n) wt_store8_planes(tP, t, c, s + c * 8);
-        float Dv = 0.f;                                                   // D_i = sum_j P_ij dP_ij
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (c * 32 < n) {
-                float dp[32];
-                tmem_ld_32x32(trow + 128 + c * 32, dp);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c * 32 + j < n) Dv = fmaf(s[c * 32 + j], dp[j], Dv);        // TMEM columns >= n are stale (may be NaN)
+    if (warp >= 4) {
+        // ------------------------------------------------------------------ loader warpgroup
+        const int tl = tid - 128;
+        int it = 0;
+        for (int win = blockIdx.x / p.heads; win < num_windows; win += G, ++it) {
+            const int buf = it & 1;
+            uint8_t* tb = sm.base + buf * BUF_TILES * TS;
+            const int y = win % Y, x = (win / Y) % X, b = win / (Y * X);
+            mbar_wait(&sm.empty[buf], ((it >> 1) & 1) ^ 1);     // the MMAs that read this buffer have retired
+            if (tl < n) sm.sTok[buf * 128 + tl] = wt_token(p, b, x, y, X, Y, tl);
+            wt_bar(2);
+            const float* q0 = p.qkv + head * WT_DH;
+            if (BWD) {
+                const uint32_t toff[4] = {0, TS, 2 * TS, 3 * TS};
+                const float* const src[4] = {q0, q0 + D, q0 + 2 * D, p.dout + head * WT_DH};
+                const long long rs[4] = {3LL * D, 3LL * D, 3LL * D, (long long)D};
+                const float sc[4] = {p.scale, 1.f, 1.f, 1.f};
+                wt_load_tiles<4>(tb, toff, src, rs, sc, sm.sTok + buf * 128, n, tl);
+            } else {
+                const uint32_t toff[3] = {0, TS, 4 * TS};
+                const float* const src[3] = {q0, q0 + D, q0 + 2 * D};
+                const long long rs[3] = {3LL * D, 3LL * D, 3LL * D};
+                const float sc[3] = {p.scale, 1.f, 1.f};
+                wt_load_tiles<3>(tb, toff, src, rs, sc, sm.sTok + buf * 128, n, tl);
             }
+            fence_proxy_async();
+            mbar_arrive(&sm.full[buf]);
         }
+    } else {
+        // ------------------------------------------------------------------ compute warpgroup
+        const int t = tid;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)n, 0, 0);
+        const int nk = n >> 4;
+        const int li = t >> 4, i1 = (t >> 2) & 3, i2 = t & 3;
+        const int bbase = ((li + p.L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1);
+        const uint32_t tacc = trow + 256;    // backward: this thread's row of sum_windows dS (bias gradient), columns [256, 384)
+        if (BWD) {
+            float z[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (c * 32 < n) {
-                float dp[32], ac[32];
-                tmem_ld_32x32(trow + 128 + c * 32, dp);
-                tmem_ld_32x32(tacc + c * 32, ac);
-                tmem_ld_wait();
+            for (int j = 0; j < 32; ++j) z[j] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float ds = c * 32 + j < n ? s[c * 32 + j] * (dp[j] - Dv) : 0.f;   // dS_ij (0 at masked keys)
-                    dp[j] = ds;
-                    ac[j] += ds;
+            for (int c = 0; c < 4; ++c) tmem_st_32x32(tacc + c * 32, z);
+            tmem_st_wait();
+        }
+        uint32_t ph = 0;
+        int it = 0;
+        for (int win = blockIdx.x / p.heads; win < num_windows; win += G, ++it) {
+            const int buf = it & 1;
+            uint8_t* tb = sm.base + buf * BUF_TILES * TS;
+            const uint32_t tb_a = smem_u32(tb);
+            const int b = win / (Y * X);
+            const uint32_t kmask = wt_kmask(p, b);
+            mbar_wait(&sm.full[buf], (it >> 1) & 1);
+            const long long tok = t < n ? sm.sTok[buf * 128 + t] : 0;
+            if (t == 0) {
+                tc_fence_after();
+                wt_mma_qk(tmem, desc_lo_word(tb_a, 16), desc_lo_word(tb_a + TS, 16), idesc_s);                         // S
+                if (BWD) wt_mma_qk(tmem + 128, desc_lo_word(tb_a + 3 * TS, 16), desc_lo_word(tb_a + 2 * TS, 16), idesc_s);   // dP = dO V^T
+                umma_commit(sm.mma);
+            }
+            mbar_wait(sm.mma, ph);
+            ph ^= 1;
+            tc_fence_after();
+            float s[128];
+            const float m = wt_scores(trow, n, t, kmask, sm.sB, p.L, s);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 128; ++j) {
+                s[j] = __expf(s[j] - m);
+                sum += s[j];
+            }
+            const float inv = 1.f / sum;
+            if (!BWD) {
+                // every thread has read its S row and the S MMAs have retired: P may overwrite Q / K, O may overwrite S
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c * 8 < n && t < n) wt_store8_planes(tb, TS, t, c, s + c * 8);   // tiles have n rows: no row >= n
+                fence_proxy_async();
+                tc_fence_before();
+                wt_bar(1);
+                if (t == 0) {
+                    tc_fence_after();
+                    wt_mma_pv(tmem, tb_a, tb_a + 4 * TS, TS, nk, 0);
+                    umma_commit(sm.mma);
+                    umma_commit(&sm.empty[buf]);
                 }
-                tmem_st_32x32(tacc + c * 32, ac);
+                mbar_wait(sm.mma, ph);
+                ph ^= 1;
+                tc_fence_after();
+                float o[64];
+                tmem_ld_32x32(trow, o);
+                tmem_ld_32x32(trow + 32, o + 32);
+                tmem_ld_wait();
+                if (t < n) {
+                    const long long off = tok * D + head * WT_DH;
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) wt_store8_planes(tS, t, c * 4 + c8, dp + c8 * 8);
+                    for (int c = 0; c < 32; c += 4)
+                        store_split4(p.out, off + c, make_float4((o[c] + o[32 + c]) * inv, (o[c + 1] + o[33 + c]) * inv,
+                                                                 (o[c + 2] + o[34 + c]) * inv, (o[c + 3] + o[35 + c]) * inv));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 128; ++j) s[j] *= inv;                       // P
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c * 8 < n && t < n) wt_store8_planes(tP, TS, t, c, s + c * 8);   // tiles have n rows: no row >= n
+                fence_proxy_async();
+                tc_fence_before();
+                wt_bar(1);
+                if (t == 0) {
+                    tc_fence_after();
+                    wt_mma_pv(tmem, smem_u32(tP), tb_a + 3 * TS, TS, nk, 1);      // dV = P^T dO  -> columns [0, 64) (S is in registers)
+                    umma_commit(sm.mma);
+                }
+                float Dv = 0.f;                                                   // D_i = sum_j P_ij dP_ij (overlaps the dV MMAs)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 32 < n) {
+                        float dp[32];
+                        tmem_ld_32x32(trow + 128 + c * 32, dp);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j < n) Dv = fmaf(s[c * 32 + j], dp[j], Dv);    // TMEM columns >= n are stale (may be NaN)
+                    }
+                }
+                mbar_wait(sm.mma, ph);                                            // dV done: the planes may take dS
+                ph ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 32 < n) {
+                        float dp[32], ac[32];
+                        tmem_ld_32x32(trow + 128 + c * 32, dp);
+                        tmem_ld_32x32(tacc + c * 32, ac);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float ds = c * 32 + j < n ? s[c * 32 + j] * (dp[j] - Dv) : 0.f;   // dS_ij (0 at masked keys)
+                            dp[j] = ds;
+                            ac[j] += ds;
+                        }
+                        tmem_st_32x32(tacc + c * 32, ac);
+                        if (t < n)
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) wt_store8_planes(tP, TS, t, c * 4 + c8, dp + c8 * 8);
+                    }
+                }
+                tmem_st_wait();
+                fence_proxy_async();
+                tc_fence_before();
+                wt_bar(1);
+                if (t == 0) {
+                    tc_fence_after();
+                    const uint32_t pa = smem_u32(tP);
+                    wt_mma_pv(tmem + 64, pa, tb_a, TS, nk, 1);                    // dK = dS^T (scale Q)
+                    wt_mma_pv(tmem + 128, pa, tb_a + TS, TS, nk, 0);              // dQ = dS K (scaled below); dP has been consumed
+                    umma_commit(sm.mma);
+                    umma_commit(&sm.empty[buf]);
+                }
+                mbar_wait(sm.mma, ph);
+                ph ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {                            // 0: dV, 1: dK, 2: dQ
+                    float o[64];
+                    tmem_ld_32x32(trow + part * 64, o);
+                    tmem_ld_32x32(trow + part * 64 + 32, o + 32);
+                    tmem_ld_wait();
+                    if (t < n) {
+                        const float f = part == 2 ? p.scale : 1.f;
+                        const long long off = tok * (3 * D) + (2 - part) * D + head * WT_DH;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            store_split4(p.out, off + c, make_float4((o[c] + o[32 + c]) * f, (o[c + 1] + o[33 + c]) * f,
+                                                                     (o[c + 2] + o[34 + c]) * f, (o[c + 3] + o[35 + c]) * f));
+                    }
+                }
             }
+            tc_fence_before();
+            wt_bar(1);   // the accumulators (and, backward, the P / dS planes) are reused by the next window
         }
-        tmem_st_wait();
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (t == 0) {
-            tc_fence_after();
-            const int nk = n >> 4;
-            wt_mma_pv(tmem, smem_u32(tP), smem_u32(tO), nk, 1);           // dV = P^T dO
-            wt_mma_pv(tmem + 64, smem_u32(tS), smem_u32(tQ), nk, 1);      // dK = dS^T (scale Q)
-            wt_mma_pv(tmem + 128, smem_u32(tS), smem_u32(tK), nk, 0);     // dQ = dS K (scaled below)
-            umma_commit(bar);
-        }
-        mbar_wait(bar, ph);
-        ph ^= 1;
-        tc_fence_after();
+        if (BWD) {
+            // fold the per-thread rows of sum dS into the head's table (entry of (i, j) = bbase_i - sub_j)
 #pragma unroll
-        for (int part = 0; part < 3; ++part) {                            // 0: dV, 1: dK, 2: dQ
-            float o[64];
-            tmem_ld_32x32(trow + part * 64, o);
-            tmem_ld_32x32(trow + part * 64 + 32, o + 32);
-            tmem_ld_wait();
-            if (t < n) {
-                const float f = part == 2 ? p.scale : 1.f;
-                const long long off = sTok[t] * (3 * D) + (2 - part) * D + head * WT_DH;
+            for (int c = 0; c < 4; ++c) {
+                if (c * 32 < n) {
+                    float ac[32];
+                    tmem_ld_32x32(tacc + c * 32, ac);
+                    tmem_ld_wait();
+                    if (t < n) {
 #pragma unroll
-                for (int c = 0; c < 32; c += 4)
-                    store_split4(p.out, off + c, make_float4((o[c] + o[32 + c]) * f, (o[c + 1] + o[33 + c]) * f,
-                                                             (o[c + 2] + o[34 + c]) * f, (o[c + 3] + o[35 + c]) * f));
-            }
-        }
-        tc_fence_before();
-        __syncthreads();
-    }
-    __syncthreads();
-    // fold the per-thread rows of sum dS into the head's table (entry of (i, j) = bbase_i - sub_j), then one global
-    // atomic per entry and CTA
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if (c * 32 < n) {
-            float ac[32];
-            tmem_ld_32x32(tacc + c * 32, ac);
-            tmem_ld_wait();
-            if (t < n) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int jj = c * 32 + j;
-                    if (jj < n && ac[j] != 0.f)
-                        atomicAdd(&sdB[bbase - (((jj >> 4) * WT_S2 + ((jj >> 2) & 3)) * WT_S2 + (jj & 3))], ac[j]);
+                        for (int j = 0; j < 32; ++j) {
+                            const int jj = c * 32 + j;
+                            if (jj < n && ac[j] != 0.f)
+                                atomicAdd(&sm.sdB[bbase - (((jj >> 4) * WT_S2 + ((jj >> 2) & 3)) * WT_S2 + (jj & 3))], ac[j]);
+                        }
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    for (int i = t; i < nb; i += 128)
-        if (sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sdB[i]);
-    if (warp == 0) tmem_dealloc<512>(tmem);
+    if (BWD)
+        for (int i = tid; i < nb; i += 256)
+            if (sm.sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sm.sdB[i]);
+    if (warp == 0) tmem_dealloc<TM_COLS>(tmem);
 }
 
 }  // namespace a2x

@@ -486,9 +486,13 @@ def pfn_stats_finalize(moments, rows, w, gamma, beta, n_updates, rm, rv, scale, 
          stream_ptr())
 
 
-def pfn_scatter(vox, num, coords, geom, w, scale, shift, agent_map, canvas, pillar_out=None, amax=None, seg=None):
-    call("a2x_pfn_scatter", _ptr(vox), _ptr(num), _ptr(coords), c_ll(_m(vox, seg)), ctypes.byref(geom), _seg(seg), _ptr(w),
-         _ptr(scale), _ptr(shift), _ptr(agent_map), _op(canvas), _ptr(pillar_out), _ptr(amax), stream_ptr())
+def pfn_scatter(vox, num, coords, geom, w, scale, shift, agent_map, canvas, pillar_out=None, amax=None, seg=None, nz=None,
+                write_hi=True):
+    """nz: int64 device counter accumulating count_nonzero of what is scattered (caller zeroes it); write_hi False (split
+    canvas): only the bf16 planes are written"""
+    call("a2x_pfn_scatter_ex", _ptr(vox), _ptr(num), _ptr(coords), c_ll(_m(vox, seg)), ctypes.byref(geom), _seg(seg), _ptr(w),
+         _ptr(scale), _ptr(shift), _ptr(agent_map), _op_planes(canvas, write_hi), _ptr(pillar_out), _ptr(amax), _ptr(nz),
+         stream_ptr())
 
 
 def pfn_bwd(vox, num, coords, geom, w, scale, shift, mean, invstd, agent_map, dcanvas, amax, moments, rows, acc_ws, dw,

@@ -71,7 +71,7 @@ class LegacyCoBEVTEngine(CoBEVTEngine):
         W = self._pack_weights(P)
         feat = self.encode(P, W, lidar, layout)
         nz = self._buf("comm_rate", (1,), torch.int64)
-        ops.count_nonzero(self._last_canvas.hi, nz)
+        nz.copy_(self._canvas_nz)
         return self.fuse_heads(P, W, feat, layout), {"comm_rate": nz}
 
 
@@ -102,7 +102,7 @@ class LegacyV2XViTEngine(V2XViTEngine):
         W = self._pack_weights(P)
         feat = self.encode(P, W, lidar, layout)
         nz = self._buf("comm_rate", (1,), torch.int64)
-        ops.count_nonzero(self._last_canvas.hi, nz)
+        nz.copy_(self._canvas_nz)
         record_len = layout["record_len"]
         B, (N, h, w, C) = len(record_len), feat.shape
         # warp_affine_simple(regroup_feature[b], pairwise_t_matrix[b, ego = 0]) (point_pillar_v2xvit.py:140-166). H, W

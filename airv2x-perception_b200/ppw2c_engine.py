@@ -85,16 +85,21 @@ class LegacyW2CEngine(W2CEngine):
     def _encode(self, P, lidar, layout, training, record):
         n_total, ny, nx = layout["n_total"], layout["ny"], layout["nx"]
         canvas = self._act("canvas", (n_total, ny, nx, 64))
-        canvas.hi.zero_()
-        if canvas.b16 is not None:
+        hi = canvas.b16 is None      # split mode: only the bf16 planes feed the block-0 GEMM (see W2CEngine._encode)
+        if hi:
+            canvas.hi.zero_()
+        else:
             canvas.b16.zero_()
+        nzc = self._buf("canvas.nz", (1,), torch.int64)
+        nzc.zero_()
+        self._canvas_nz = nzc
         geom = ops.pfn_geom(self.args["voxel_size"], self.args["lidar_range"], nx, ny)
         pre = "pillar_vfe.pfn_layers.0"
         scale, shift = self._buf("pfn.scale", (64,)), self._buf("pfn.shift", (64,))
         ops.bn_eval_affine(P[pre + ".norm.weight"], P[pre + ".norm.bias"], P[pre + ".norm.running_mean"],
                            P[pre + ".norm.running_var"], scale, shift)
         ops.pfn_scatter(lidar["voxel_features"], lidar["voxel_num_points"], lidar["voxel_coords"], geom,
-                        P[pre + ".linear.weight"], scale, shift, layout["identity_map"], canvas)
+                        P[pre + ".linear.weight"], scale, shift, layout["identity_map"], canvas, nz=nzc, write_hi=hi)
         return canvas
 
     def _shrink_heads(self, P, W, cat, tag, heads_only_cls=False):
@@ -120,7 +125,7 @@ class LegacyW2CEngine(W2CEngine):
         B, N = len(record_len), layout["n_total"]
         canvas = self._encode(P, lidar, layout, False, None)
         nz = self._buf("comm_rate", (1,), torch.int64)
-        ops.count_nonzero(canvas.hi, nz)
+        nz.copy_(self._canvas_nz)
         x0 = self._block(P, W, 0, canvas, False, 0, "A", None)
         h2, w2 = x0.shape[1], x0.shape[2]
         catA = self._act("A.cat", (N, h2, w2, self.c_cat))

@@ -239,7 +239,7 @@ class V2XViTEngine(CoBEVTEngine):
         W = self._pack_weights(P)
         y1, y2, cat = self._encode_train(P, W, lidar, layout, rec)
         canvas_nz = self._buf("comm_rate", (1,), torch.int64)
-        ops.count_nonzero(self._last_canvas.hi, canvas_nz)
+        canvas_nz.copy_(self._canvas_nz)
         self.last_aux = {"comm_rate": canvas_nz}
         enc = self.enc
         ca, pw = enc["cav_att_config"], enc["pwindow_att_config"]
@@ -516,7 +516,7 @@ class V2XViTEngine(CoBEVTEngine):
         W = self._pack_weights(P)
         canvas_nz = self._buf("comm_rate", (1,), torch.int64)
         feat = self.encode(P, W, lidar, layout)
-        ops.count_nonzero(self._last_canvas.hi, canvas_nz)
+        canvas_nz.copy_(self._canvas_nz)
         fused = self.fusion(P, W, feat, layout, prior, scm)
         heads = self._buf("heads.out", (fused.shape[0], feat.shape[1], feat.shape[2], HEAD_PAD))
         ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])

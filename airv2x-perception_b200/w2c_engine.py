@@ -293,9 +293,16 @@ class W2CEngine:
     def _encode(self, P, lidar, layout, training, record):
         n_total, ny, nx = layout["n_total"], layout["ny"], layout["nx"]
         canvas = self._act("canvas", (n_total, ny, nx, 64))
-        canvas.hi.zero_()
-        if canvas.b16 is not None:
+        # split mode: the canvas only feeds the block-0 tap-GEMM, which reads the bf16 planes -> the fp32 plane is neither
+        # cleared nor written, and `spatial_features.count_nonzero()` (airv2x_where2com.py:122) is counted by the scatter
+        hi = canvas.b16 is None
+        if hi:
+            canvas.hi.zero_()
+        else:
             canvas.b16.zero_()
+        nzc = self._buf("canvas.nz", (1,), torch.int64)
+        nzc.zero_()
+        self._canvas_nz = nzc
         if "raw" in lidar:
             lidar = self._voxelize(lidar["raw"], layout)
         for t in AGENT_TYPES:
@@ -322,7 +329,7 @@ class W2CEngine:
                                        P[pre + ".norm.running_mean"], P[pre + ".norm.running_var"], scale, shift, mean,
                                        invstd, seg=seg)
                 amax = self._buf("pfn.%s.amax" % t, (vox.shape[0], 64), torch.uint8)
-                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax, seg=seg)
+                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax, seg=seg, nz=nzc, write_hi=hi)
                 if record is not None:
                     record.append(dict(kind="pfn", type=t, vox=vox, num=num, coords=coords, geom=geom, pre=pre,
                                        scale=scale, shift=shift, mean=mean, invstd=invstd, amap=amap, amax=amax,
@@ -330,7 +337,7 @@ class W2CEngine:
             else:
                 ops.bn_eval_affine(P[pre + ".norm.weight"], P[pre + ".norm.bias"], P[pre + ".norm.running_mean"],
                                    P[pre + ".norm.running_var"], scale, shift)
-                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, seg=seg)
+                ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, seg=seg, nz=nzc, write_hi=hi)
         return canvas
 
     # ------------------------------------------------------------------ forward
@@ -345,7 +352,7 @@ class W2CEngine:
         B, N = len(record_len), layout["n_total"]
         canvas = self._encode(P, lidar, layout, training, rec)
         nz = self._buf("comm_rate", (1,), torch.int64)
-        ops.count_nonzero(canvas.hi, nz)
+        nz.copy_(self._canvas_nz)
 
         # ---- pass A: un-masked backbone on every agent map (single-agent confidence for the mask)
         # block 0 is shared with the fusion pass; in train mode its BNs see 3 identical running-stat updates
@@ -460,7 +467,7 @@ class W2CEngine:
         hdr = xbuf[reg["hdr"][0]:reg["hdr"][0] + 64].view(torch.int32)
         idx = xbuf[reg["idx"][0]:reg["idx"][0] + reg["idx"][1]].view(torch.int32)
         vals = xbuf[reg["vals"][0]:reg["vals"][0] + reg["vals"][1]]
-        ops.count_nonzero(canvas.hi, hdr[2:4].view(torch.int64))
+        hdr[2:4].view(torch.int64).copy_(self._canvas_nz)
         # pass A on the own map -> confidence -> mask (where2comm_fuse.py:83-149, eval branch)
         catA = self._act("A.cat", (1, h2, w2, self.c_cat))
         xa = x0

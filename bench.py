@@ -1,14 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — scenes/sec (forward + backward) of the Where2comm hot path, BASELINE.json configs[1]:
-airv2x_intermediate_where2com.yaml, 5 agents (2 vehicles, 2 RSUs, 1 drone) x 60k synthetic points, 200 x 704 BEV.
+"""bench.py — scenes/sec (forward + backward) of the collaborative-perception hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W            # the B200 path (one process per GPU under torchrun)
+    python bench.py --gpus N --steps K --warmup W            # headline: BASELINE.json configs[1] (= --config 2)
+    python bench.py --config {1,2,3,4,5} ...                  # the other BASELINE configs, same JSON contract
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm (oracle port) on the host CPUs
 
-A step = raw point clouds (resident in HBM) -> voxelise -> PillarVFE/scatter -> backbone -> mask -> fusion -> heads
--> PointPillarLossMultiClass -> full backward (all parameter gradients), one scene per GPU, no optimizer.
-Prints ONE JSON line (see the driver contract). `e2e` times the same step through the public call with HOST
-(pinned) buffers: H2D of the clouds + labels and D2H of the loss inside the timed region.
+  config 2 (default)  airv2x_intermediate_where2com.yaml, 5 agents (2 veh, 2 rsu, 1 drone) x 60k points, 200 x 704 BEV
+  config 1            point_pillar_where2comm (legacy registry name), 2 agents x 8k points, 128 x 128 BEV
+  config 3            airv2x_intermediate_v2xvit.yaml, 5 agents x 60k points
+  config 4            airv2x_intermediate_cobevt.yaml (FuseBEVT), 5 agents x 60k points on one GPU; under torchrun the
+                      agent-per-GPU mode (N agents = N ranks, one exchange of the BEV maps) is timed as well
+  config 5            Where2comm lidar branch on the 504 x 504 grid (range +-100.8 m), 5 agents x 60k points
+
+A step = raw point clouds (resident in HBM) -> voxelise -> PillarVFE/scatter -> backbone -> fusion -> heads ->
+PointPillarLossMultiClass -> full backward (all parameter gradients), one scene per GPU, no optimizer. The training labels
+come from 20 planted boxes through the GPU anchor-target assigner (labels.TargetAssigner). Prints ONE JSON line (driver
+contract). `e2e` times the same step through the public call with HOST (pinned) buffers: H2D of the clouds + labels and D2H
+of the loss inside the timed region. The default run additionally reports, under "extra", the train-step time of configs
+3 / 4 / 5 and, under "sustained", the headline step replayed for >= 3 s with the SM clock sampled.
 """
 import argparse
 import json
@@ -25,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 AGENTS = ["vehicle", "vehicle", "rsu", "rsu", "drone"]
 N_POINTS = 60000
+RANGE_504 = (-100.8, -100.8, 100.8, 100.8)
 
 
 # ------------------------------------------------------------------------------------------------ synthetic workload
@@ -38,9 +48,27 @@ def synth_cloud(seed, n, rng):
     return np.stack([x, y, z, i], 1).astype(np.float32)
 
 
+def synth_boxes(seed, rng, n_gt=20, max_num=100):
+    """SURVEY §8d planted ground truth: 20 boxes (h, w, l) = (1.56, 1.6, 3.9) x U(0.8, 1.2), yaw near 0 / pi/2, class
+    1..6, padded to max_num with a prefix mask — the tensors the dataset hands to generate_label_airv2x
+    (data_utils/post_processor/voxel_postprocessor.py:217-354)."""
+    g = np.random.default_rng(seed)
+    box = np.zeros((max_num, 7), np.float64)
+    box[:n_gt, 0] = g.uniform(rng[0] + 6, rng[3] - 6, n_gt)
+    box[:n_gt, 1] = g.uniform(rng[1] + 6, rng[4] - 6, n_gt)
+    box[:n_gt, 2] = -1.0 + g.uniform(-0.2, 0.2, n_gt)
+    box[:n_gt, 3:6] = np.array([1.56, 1.6, 3.9]) * g.uniform(0.8, 1.2, (n_gt, 3))
+    box[:n_gt, 6] = g.choice([0.0, np.pi / 2], n_gt) + g.uniform(-0.15, 0.15, n_gt)
+    mask = np.zeros(max_num, np.float64)
+    mask[:n_gt] = 1
+    cls = np.zeros(max_num, np.int64)
+    cls[:n_gt] = g.integers(1, 7, n_gt)
+    return box, mask, cls
+
+
 def synth_labels(seed, H, W, A, n_pos=40):
-    """planted positives: pos_equal_one / class_ids / regression targets in the collate layout of the reference
-    (data_utils/post_processor/voxel_postprocessor.py:392-430)."""
+    """planted positives directly in the collate layout (kept for the profiling scripts; bench.py itself builds its labels
+    with labels.TargetAssigner from synth_boxes)"""
     g = np.random.default_rng(seed)
     pos = np.zeros((1, H, W, A), np.float32)
     idx = g.choice(H * W * A, n_pos, replace=False)
@@ -51,27 +79,53 @@ def synth_labels(seed, H, W, A, n_pos=40):
     return {"targets": tg, "pos_equal_one": pos, "class_ids": cls}
 
 
-def load_config():
-    return json.load(open(os.path.join(ROOT, "configs", "airv2x_intermediate_where2com.json")))
+def load_config(name="airv2x_intermediate_where2com.json"):
+    p = os.path.join(ROOT, "configs", name)
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "tests", "golden", name)
+    return json.load(open(p))
 
 
-def make_raw_scene(cfg, seed):
+def make_raw_scene(cfg, seed, agents=AGENTS, n_points=N_POINTS):
     rng = cfg["preprocess"]["cav_lidar_range"]
-    clouds = [synth_cloud(seed * 100 + k, N_POINTS, rng) for k in range(len(AGENTS))]
+    clouds = [synth_cloud(seed * 100 + k, n_points, rng) for k in range(len(agents))]
     offsets = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
     return np.concatenate(clouds, 0), offsets
 
 
-def data_dict_from_raw(points, offsets, cfg, torch, pin=False):
+def data_dict_from_raw(points, offsets, cfg, torch, pin=False, agents=AGENTS):
     def t(a):
         x = torch.from_numpy(a)
         return x.pin_memory() if pin else x
 
     dd = {"raw_points": {"points": t(points), "offsets": t(offsets), "preprocess": cfg["preprocess"], "filter": True}}
     for ty in ("vehicle", "rsu", "drone"):
-        n = sum(1 for a in AGENTS if a == ty)
+        n = sum(1 for a in agents if a == ty)
         dd[ty] = {"record_len": [n], "batch_idxs": [0] if n else []}
     return dd
+
+
+WORKLOADS = {
+    2: dict(cfg="airv2x_intermediate_where2com.json", module="airv2x_where2com", cls="Airv2xWhere2com", agents=AGENTS,
+            n_points=N_POINTS, metric="scenes/sec (fwd+bwd) Where2Comm 5-agent 60k-pt",
+            workload="airv2x_intermediate_where2com.yaml: 5 agents (2 veh, 2 rsu, 1 drone) x 60k pts, 200x704 BEV, 1 scene "
+                     "per GPU, train-mode fwd + PointPillarLossMultiClass + bwd"),
+    3: dict(cfg="airv2x_intermediate_v2xvit.json", module="airv2x_v2xvit", cls="Airv2xV2XVit", agents=AGENTS,
+            n_points=N_POINTS, metric="scenes/sec (fwd+bwd) V2X-ViT 5-agent 60k-pt",
+            workload="airv2x_intermediate_v2xvit.yaml: 5 agents x 60k pts, 200x704 BEV, 1 scene per GPU, train-mode fwd + "
+                     "loss + bwd (valid agents only: the reference's padding to L=15 is exact to skip)"),
+    4: dict(cfg="airv2x_intermediate_cobevt.json", module="airv2x_cobevt", cls="Airv2xCoBEVT", agents=AGENTS,
+            n_points=N_POINTS, metric="scenes/sec (fwd+bwd) CoBEVT 5-agent 60k-pt",
+            workload="airv2x_intermediate_cobevt.yaml (FuseBEVT): 5 agents x 60k pts padded to L=7, 200x704 BEV, 1 scene "
+                     "per GPU, train-mode fwd + loss + bwd"),
+    5: dict(cfg="full_w2c504_config.json", module="airv2x_where2com", cls="Airv2xWhere2com", agents=AGENTS,
+            n_points=N_POINTS, metric="scenes/sec (fwd+bwd) Where2Comm lidar branch 504x504 5-agent 60k-pt",
+            workload="airv2x_intermediate_where2com.yaml with the lidar range set to +-100.8 m (504x504 BEV, config 5's "
+                     "grid), lidar branch only, 5 agents x 60k pts, train-mode fwd + loss + bwd"),
+    1: dict(cfg="ppw2c_small_config.json", module="point_pillar_where2comm", cls="PointPillarWhere2comm",
+            agents=["vehicle", "vehicle"], n_points=8000, metric="scenes/sec point_pillar_where2comm 2-agent 8k-pt",
+            workload="point_pillar_where2comm (legacy registry name), 2 agents x 8k pts, 128x128 BEV (PR1 plumbing case)"),
+}
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampling
@@ -117,12 +171,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, cfg, cores=None):
     """The reference algorithm on the host CPUs: oracle port (torch CPU fp32 restatement, pinned bit-exact to the
-    real reference modules) — voxelise (C restatement) + forward (train mode) + loss + backward per step."""
+    real reference modules at this very size: tests/test_fullsize_cpu.py) — voxelise (C restatement) + forward (train
+    mode) + loss + backward per step; the labels come from the same planted boxes through the oracle's restatement of
+    generate_label_airv2x."""
     import random
 
     import torch
 
-    from oracle import voxelize as V, w2c_oracle as O
+    from oracle import labels_oracle as LO, postprocess_oracle as PO, voxelize as V, w2c_oracle as O
 
     cores = cores or os.cpu_count()
     torch.set_num_threads(cores)
@@ -139,10 +195,11 @@ def run_reference(args, cfg, cores=None):
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "gaussian" not in k
               else v) for k, v in sd.items()}
     pre = cfg["preprocess"]
-    H, W = 100, 352
-    lab = synth_labels(3, H, W, margs["anchor_number"])
-    labels = {"targets": torch.from_numpy(lab["targets"]).double(), "pos_equal_one": torch.from_numpy(lab["pos_equal_one"]).double(),
-              "class_ids": torch.from_numpy(lab["class_ids"]).long()}
+    pp = cfg["postprocess"]
+    box, mask, cls = synth_boxes(3, pp["anchor_args"]["cav_lidar_range"])
+    anchors = PO.generate_anchor_box(pp["anchor_args"], pp["order"])
+    labels = LO.collate([LO.generate_label(box, mask, cls, anchors, pp["target_args"]["pos_threshold"],
+                                           pp["target_args"]["neg_threshold"])])
 
     def step():
         per_type = {t: [] for t in O.AGENT_TYPES}
@@ -163,9 +220,9 @@ def run_reference(args, cfg, cores=None):
         loss = O.point_pillar_loss_multiclass(out, labels, margs["num_class"], cfg["loss_args"]["cls_weight"],
                                               cfg["loss_args"]["reg"])[0]
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
-    # bounded sample: at most 1 warm-up + 3 timed full-size steps (each ~10-25 s of CPU work)
+    # bounded sample: at most 1 warm-up + 3 timed full-size steps (each ~5-25 s of CPU work)
     w_eff, k_eff = min(args.warmup, 1), max(1, min(args.steps, 3))
     random.seed(0)
     for _ in range(w_eff):
@@ -178,34 +235,190 @@ def run_reference(args, cfg, cores=None):
             "sample": "%d full-size scene step(s) (5 agents x 60k pts, voxelise + fwd + loss + bwd), %d warm-up" % (k_eff, w_eff)}
 
 
+# ------------------------------------------------------------------------------------------------ workloads on the GPU
+class Workload:
+    """model + one synthetic scene (device and pinned-host copies) + labels from the GPU target assigner"""
+
+    def __init__(self, which, torch, dev, seed, precision="split3", agents=None):
+        import a2x_import
+
+        w = WORKLOADS[which]
+        self.which, self.spec = which, w
+        self.cfg = load_config(w["cfg"])
+        self.agents = list(agents or w["agents"])
+        M = a2x_import.pkg("opencood.models." + w["module"])
+        torch.manual_seed(1)
+        self.model = getattr(M, w["cls"])(self.cfg["model_args"], precision=precision).to(dev)
+        self.legacy = which == 1
+        pts, offs = make_raw_scene(self.cfg, seed, self.agents, w["n_points"])
+        self.pts, self.offs = pts, offs
+        self.dd_host = data_dict_from_raw(pts, offs, self.cfg, torch, pin=True, agents=self.agents)
+        self.dd_dev = {k: (dict(v) if isinstance(v, dict) else v) for k, v in self.dd_host.items()}
+        self.dd_dev["raw_points"] = dict(self.dd_host["raw_points"])
+        self.dd_dev["raw_points"]["points"] = self.dd_host["raw_points"]["points"].to(dev)
+        self.dd_dev["raw_points"]["offsets"] = self.dd_host["raw_points"]["offsets"].to(dev)
+        if which == 3:
+            L = sum(self.cfg["model_args"]["max_cav"].values())
+            prior = torch.zeros(1, L, 3)
+            scm = torch.eye(4, dtype=torch.float64).repeat(1, L, 1, 1)
+            for i, t in enumerate(self.agents):
+                prior[0, i] = torch.tensor([0.1 * i, float(i % 2), 1.0 if t == "rsu" else 0.0])
+            scm[0, 1, 0, 3], scm[0, 1, 1, 3] = 6.0, -3.0
+            scm[0, 1, :2, :2] = torch.tensor([[0.9801, -0.1987], [0.1987, 0.9801]], dtype=torch.float64)
+            for d in (self.dd_host, self.dd_dev):
+                d["prior_encoding"], d["spatial_correction_matrix"] = prior, scm
+        # labels: planted boxes -> GPU anchor-target assignment (what train_loop.Trainer does per batch)
+        pp = self.cfg["postprocess"]
+        TA = a2x_import.pkg("labels").TargetAssigner
+        box, mask, cls = synth_boxes(3 + seed, pp["anchor_args"]["cav_lidar_range"])
+        lab = TA(pp, dev)(box[None], mask[None], cls[None])
+        self.n_pos = int(lab["pos_equal_one"].sum().item())
+        self.lab_dev = {k: lab[k] for k in ("targets", "pos_equal_one", "class_ids")}
+        self.lab_host = {k: v.cpu().pin_memory() for k, v in self.lab_dev.items()}
+        self.cw, self.rc = self.cfg["loss_args"]["cls_weight"], self.cfg["loss_args"]["reg"]
+        self.h2d_bytes = int(pts.nbytes + offs.nbytes + sum(v.numel() * v.element_size() for v in self.lab_host.values()))
+
+    def train_step(self, dd=None, lab=None):
+        return self.model.train_step(dd or self.dd_dev, lab or self.lab_dev, self.cw, self.rc)
+
+
+def time_steps(torch, fn, n, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, out
+
+
+def extra_configs(torch, dev, precision):
+    """train-step (and eval-forward) time of the other BASELINE configs on this GPU: eager launches, 5 timed steps each"""
+    res = {}
+    for which in (3, 4, 5):
+        try:
+            w = Workload(which, torch, dev, seed=0, precision=precision)
+            w.model.train()
+            ms_t, loss3 = time_steps(torch, w.train_step, 5, 2)
+            w.model.eval()
+            with torch.no_grad():
+                ms_e, _ = time_steps(torch, lambda: w.model(w.dd_dev), 5, 2)
+            res["config%d" % which] = {"workload": w.spec["workload"], "train_ms_per_step": ms_t,
+                                       "train_scenes_per_s": 1000.0 / ms_t, "eval_ms_per_scene": ms_e,
+                                       "loss": float(loss3.sum().item()), "launch": "eager"}
+            del w
+            torch.cuda.empty_cache()
+        except Exception as ex:  # report, never hide, and never lose the headline line
+            res["config%d" % which] = {"error": repr(ex)[:300]}
+    return res
+
+
+def agent_parallel_block(torch, dist, dev, rank, world, precision):
+    """N agents of ONE scene, one per GPU (north_star / BASELINE config 4): per-agent encoders run in parallel, one
+    exchange of the BEV maps (NCCL all-gather, or peer-memory pull fused into the consumer), replicated fusion. Reports
+    ms per scene (max over ranks) and the bytes each rank puts on the wire; asserts the output equals the single-GPU
+    output of the same scene bit for bit."""
+    import a2x_import
+
+    D = a2x_import.pkg("dist")
+    order = {"vehicle": 0, "rsu": 1, "drone": 2}
+    res = {}
+    for name, which, cls_ap in (("config4_cobevt", 4, "AgentParallelCoBEVT"), ("config2_where2comm", 2, "AgentParallelWhere2comm")):
+        try:
+            base = (["vehicle"] * 3 + ["rsu"] * 3 + ["drone"] * 2)
+            agents = sorted([base[(i * 3) % 8] if world < 8 else base[i] for i in range(world)], key=lambda t: order[t]) \
+                if world != 2 else ["vehicle", "rsu"]
+            w = Workload(which, torch, dev, seed=7, precision=precision, agents=agents)
+            margs = w.cfg["model_args"]
+            if which == 4 and world > sum(margs["max_cav"].values()):
+                margs["max_cav"] = {"vehicle": 3, "rsu": 3, "drone": 2}      # SURVEY 8d: 8 agents need L = 8
+                M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+                torch.manual_seed(1)
+                w.model = M.Airv2xCoBEVT(margs, precision=precision).to(dev)
+            if which == 2:
+                with torch.no_grad():
+                    w.model.cls_head.bias -= 4.0      # a selective communication mask, as trained weights give
+            for p in w.model.parameters():            # identical parameters on every rank
+                dist.broadcast(p.data, 0)
+            w.model.eval()
+
+            def timed(fn, n=5):
+                for _ in range(2):
+                    fn()
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    out = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return out, float(t)
+
+            with torch.no_grad():
+                single, ms_single = timed(lambda: w.model(w.dd_dev))
+                single = {k: v.clone() for k, v in single.items() if k in ("psm", "rm", "obj")}
+                blk = {"agents": agents, "ms_single_gpu": ms_single}
+                mine = torch.from_numpy(w.pts[w.offs[rank]:w.offs[rank + 1]])
+                for transport in ("nccl", "peer"):
+                    try:
+                        ap = getattr(D, cls_ap)(w.model, agents, transport=transport)
+                        out, ms = timed(lambda: ap(mine, w.cfg["preprocess"]))
+                        exact = all(torch.equal(out[k], single[k]) for k in ("psm", "rm", "obj"))
+                        ok = torch.tensor([1 if exact else 0], device=dev)
+                        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                        blk[transport] = {"ms_per_scene": ms, "bit_exact_vs_single_gpu": bool(ok.item()),
+                                          "wire_bytes_per_rank": int(getattr(ap, "wire_bytes", 0))}
+                    except Exception as ex:
+                        blk[transport] = {"error": repr(ex)[:300]}
+            res[name] = blk
+            del w
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            res[name] = {"error": repr(ex)[:300]}
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="split3", choices=["split3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs 3/4/5, sustained and agent-parallel blocks")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
-    cfg = load_config()
+    spec = WORKLOADS[args.config]
+    cfg = load_config(spec["cfg"])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    metric = "scenes/sec (fwd+bwd) Where2Comm 5-agent 60k-pt"
-    config = {"workload": "airv2x_intermediate_where2com.yaml: 5 agents (2 veh, 2 rsu, 1 drone) x 60k pts, 200x704 BEV, "
-                          "1 scene per GPU, train-mode fwd + PointPillarLossMultiClass + bwd",
+    metric = spec["metric"]
+    graphed = args.config == 2 and not args.no_graph
+    config = {"workload": spec["workload"],
+              "labels": "20 planted boxes -> labels.TargetAssigner (GPU generate_label_airv2x)",
               "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
-              "launch": "eager" if "--no-graph" in sys.argv else "cuda-graph replay of the fused step"}
+              "launch": "cuda-graph replay of the fused step" if graphed else "eager"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = run_reference(args, cfg)
-        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "scenes/s", "n_gpus": args.gpus,
+        cfg2 = load_config(WORKLOADS[2]["cfg"])
+        r = run_reference(args, cfg2)
+        config["workload"] = WORKLOADS[2]["workload"]
+        config["launch"] = "host CPUs"
+        line = {"impl": "reference", "metric": WORKLOADS[2]["metric"], "value": r["value"], "unit": "scenes/s", "n_gpus": args.gpus,
                 "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": "scenes/s", "cores": r["cores"], "kind": "port",
@@ -224,33 +437,29 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    M = a2x_import.pkg("opencood.models.airv2x_where2com")
     libmod = a2x_import.pkg("_lib")
     lib = libmod.load()
-    margs = cfg["model_args"]
-    torch.manual_seed(1)
-    model = M.Airv2xWhere2com(margs, precision=args.precision).to(dev)
-    model.train()
-    pts, offs = make_raw_scene(cfg, seed=rank)
-    H, W = 100, 352
-    lab_np = synth_labels(3 + rank, H, W, margs["anchor_number"])
-    dd_host = data_dict_from_raw(pts, offs, cfg, torch, pin=True)
-    lab_host = {k: torch.from_numpy(v).pin_memory() for k, v in lab_np.items()}
-    dd_dev = {k: (dict(v) if isinstance(v, dict) else v) for k, v in dd_host.items()}
-    dd_dev["raw_points"] = dict(dd_host["raw_points"])
-    dd_dev["raw_points"]["points"] = dd_host["raw_points"]["points"].to(dev)
-    dd_dev["raw_points"]["offsets"] = dd_host["raw_points"]["offsets"].to(dev)
-    lab_dev = {k: v.to(dev) for k, v in lab_host.items()}
-    cw, rc = cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"]
+    W = Workload(args.config, torch, dev, seed=rank, precision=args.precision)
+    model = W.model
+    dd_dev, lab_dev, dd_host, lab_host, cw, rc = W.dd_dev, W.lab_dev, W.dd_host, W.lab_host, W.cw, W.rc
+    if W.legacy:
+        model.eval()
+    else:
+        model.train()
     # data-parallel over scenes (the reference's DDP, tools/train.py:161-163): average parameter gradients
     allreduce_grads = a2x_import.pkg("dist").GradAverager(model.parameters())
 
-    step_fn = model.train_step if args.no_graph else model.train_step_graphed
+    if W.legacy:
+        def step(dd, lab):
+            with torch.no_grad():
+                return model(dd)["psm"].sum().double().reshape(1)
+    else:
+        step_fn = model.train_step_graphed if graphed else model.train_step
 
-    def step(dd, lab):
-        loss3 = step_fn(dd, lab, cw, rc)
-        allreduce_grads()
-        return loss3
+        def step(dd, lab):
+            loss3 = step_fn(dd, lab, cw, rc)
+            allreduce_grads()
+            return loss3
 
     def sync_all():
         if world > 1:
@@ -282,14 +491,14 @@ def main():
     with ClockSampler(local_rank) as clk:
         ms, loss3 = timed(dd_dev, lab_dev, args.steps, False)
     launches = lib.a2x_launch_count() - l0
-    if not args.no_graph:  # replays do not pass through the C launchers: count = kernels captured per step x steps
+    if graphed:  # replays do not pass through the C launchers: count = kernels captured per step x steps
         launches = model.launches_per_step * args.steps
     # end-to-end: host pinned clouds + labels -> H2D, loss -> D2H, every step. Through the public pipelined API:
     # stage_inputs() starts step i+1's H2D copies on a copy stream while step i runs; the loss of step i is read from
     # its (asynchronous) D2H copy after step i+1 has been launched. Every step's copies are inside the timed region.
     if args.no_e2e:
         ms_e2e, loss_val = ms, float(loss3.sum().item())
-    elif args.no_graph:
+    elif not graphed:
         for _ in range(2):
             step(dd_host, lab_host)
         ms_e2e, loss_val = timed(dd_host, lab_host, args.steps, True)
@@ -319,21 +528,37 @@ def main():
             t = torch.tensor([ms_e2e], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item())
-    h2d = pts.nbytes + offs.nbytes + sum(v.nbytes for v in lab_np.values())
     value = world * 1000.0 / ms
     line = {"metric": metric, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (3-pass bf16-split tensor-core GEMMs, fp32 accumulate, fp32-equivalent to 1e-4; fp32 elsewhere)"
             if args.precision == "split3" else "tf32", "data": "synthetic", "config": config,
-            "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "scenes/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": 24, "ms_per_step": ms_e2e,
+            "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "scenes/s", "h2d_bytes_per_step": W.h2d_bytes,
+                    "d2h_bytes_per_step": 24 if not W.legacy else 8, "ms_per_step": ms_e2e,
                     "api": "model.stage_inputs(host dicts) + model.train_step_staged().result(): H2D of step i+1 overlaps "
-                           "step i, loss D2H read one step late" if not args.no_graph else "model.train_step(host dicts)"},
-            "gpu_launches": int(launches), "loss": loss_val, "clocks": clk.summary()}
+                           "step i, loss D2H read one step late" if graphed else
+                           ("model(host dicts) [eval forward: the legacy models' training step is reported by config 2-5]"
+                            if W.legacy else "model.train_step(host dicts)")},
+            "gpu_launches": int(launches), "loss": loss_val, "label_positives": W.n_pos, "clocks": clk.summary()}
+    if args.config == 2 and not args.no_extra:
+        # sustained: the same graph-replayed step for >= 3 s, SM clock / throttle reasons sampled over the whole loop
+        n_sus = max(50, int(3200.0 / ms))
+        with ClockSampler(local_rank) as clk2:
+            ms_sus, _ = timed(dd_dev, lab_dev, n_sus, False)
+        line["sustained"] = {"value": world * 1000.0 / ms_sus, "unit": "scenes/s", "ms_per_step": ms_sus, "steps": n_sus,
+                             "seconds": ms_sus * n_sus / 1e3, "clocks": clk2.summary()}
 
-    if rank == 0 and not args.no_roofline:
+    if rank == 0 and not args.no_roofline and args.config in (2, 5):
         line["roofline"] = roofline_pass(model, libmod, dd_dev, lab_dev, cw, rc, args.precision, torch)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if world == 1 and args.config == 2 and not args.no_extra:
+        del W, model, allreduce_grads, step
+        torch.cuda.empty_cache()
+        line["extra"] = extra_configs(torch, dev, args.precision)
+    if world > 1 and args.config in (2, 4) and not args.no_extra:
+        blk = agent_parallel_block(torch, dist, dev, rank, world, args.precision)
+        if rank == 0:
+            line["agent_parallel"] = blk
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:
         r = run_reference(argparse.Namespace(steps=1, warmup=0), cfg)
         line["cpu_baseline"] = {"value": r["value"], "unit": "scenes/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
@@ -382,7 +607,7 @@ def roofline_pass(model, libmod, dd, lab, cw, rc, precision, torch):
     tg_fl = sum(g["flops"] for g in tg)
     achieved = tg_fl / (tg_ms * 1e-3) / 1e12 if tg_ms > 0 else 0.0
     hw_mult = 3.0 if precision == "split3" else 2.0  # bf16-MMA-equivalents executed per algorithmic FLOP
-    top = sorted(((k, round(v["ms"], 3), v["calls"]) for k, v in groups.items()), key=lambda x: -x[1])[:8]
+    top = sorted(((k, round(v["ms"], 3), v["calls"]) for k, v in groups.items()), key=lambda x: -x[1])[:10]
     traffic, traffic_src = ncu_traffic()
     return {"bound": "tensor", "kernel": "tapgemm_kernel / tapgemm_halo_kernel (tcgen05.mma kind::f16 bf16, 3 split passes; conv fwd + dgrad + deconv launches)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

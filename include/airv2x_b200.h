@@ -396,6 +396,13 @@ int a2x_pfn_scatter(const float* voxels, const int* num_points, const int* coord
                     const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift,
                     const int* agent_map, const a2x_output* canvas, float* pillar_out, unsigned char* amax,
                     a2x_stream_t stream);
+/* same, with (i) canvas->hi optional (null: only the bf16 split planes the block-0 tap-GEMM reads are written) and
+ * (ii) *nonzero_count += number of non-zero canvas values written: `spatial_features.count_nonzero()` of
+ * opencood/models/airv2x_where2com.py:122 without a pass over the canvas (caller zeroes the counter) */
+int a2x_pfn_scatter_ex(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
+                       const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift,
+                       const int* agent_map, const a2x_output* canvas, float* pillar_out, unsigned char* amax,
+                       long long* nonzero_count, a2x_stream_t stream);
 /* train-mode backward to (W, gamma, beta) given d(canvas); acc_ws = 64*12 doubles of workspace */
 int a2x_pfn_bwd(const float* voxels, const int* num_points, const int* coords, long long m, const a2x_pfn_geom* geom,
                 const a2x_pfn_segments* seg, const float* w, const float* scale, const float* shift, const float* mean, const float* invstd,

