@@ -263,10 +263,13 @@ class CoBEVTEngine(W2CEngine):
                      shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
         return y1, y2, cat
 
-    def forward_train(self, P, lidar, layout):
-        """Train-mode forward (batch-statistic BatchNorm in the encoder, dropout = identity) that keeps what the
-        backward needs: per sublayer the residual input, the LayerNorm output (GEMM operand of the weight gradients), the
-        qkv tensor / the attention output, the FFN pre-activation and hidden activation."""
+    def forward_train(self, P, lidar, layout, drop=None):
+        """Train-mode forward (batch-statistic BatchNorm in the encoder) that keeps what the backward needs: per sublayer
+        the residual input, the LayerNorm output (GEMM operand of the weight gradients), the qkv tensor / the attention
+        output, the FFN pre-activation and hidden activation. drop: ops.Dropout (rate fax_fusion.drop_out, this step's
+        seed) or None = nn.Dropout disabled. Sites, in call order per sublayer: Attention.to_out's Dropout
+        (swap_fusion_modules.py:43), FeedForward's two Dropouts (base_transformer.py:32,34); masks are regenerated from
+        (seed, site) by the backward, never stored."""
         self._begin_step()
         rec = []
         W = self._pack_weights(P)
@@ -292,8 +295,15 @@ class CoBEVTEngine(W2CEngine):
                 att = self._act("sv.att." + tag, X.shape)
                 ops.window_attention_fwd(qkv, P[pa + ".fn.relative_position_bias_table.weight"], key_mask, B, self.L,
                                          self.heads, self.fa["dim_head"], self.fa["window_size"], grid_mode, att)
-                ops.linear_fwd(att, W[pa + ".fn.to_out.0.weight"], Act(X), accumulate=True)
-                subs.append(dict(kind="att", pre=pa, xin=xin, ln=ln, qkv=qkv, att=att, grid=grid_mode))
+                site_o = None
+                if drop is None:
+                    ops.linear_fwd(att, W[pa + ".fn.to_out.0.weight"], Act(X), accumulate=True)
+                else:   # x += dropout(to_out(att))
+                    tmp = self._buf("fax.tmp", X.shape)
+                    ops.linear_fwd(att, W[pa + ".fn.to_out.0.weight"], Act(tmp))
+                    site_o = drop.site()
+                    ops.dropout_apply(tmp, drop, site_o, Act(X), residual=X)
+                subs.append(dict(kind="att", pre=pa, xin=xin, ln=ln, qkv=qkv, att=att, grid=grid_mode, site_o=site_o))
                 # feed-forward sublayer (pre-activation kept in fp32: GELU' needs it)
                 xin = self._buf("sv.xin.f" + tag, X.shape)
                 xin.copy_(X)
@@ -302,9 +312,18 @@ class CoBEVTEngine(W2CEngine):
                 pre = self._buf("sv.pre." + tag, X.shape[:3] + (self.fa["mlp_dim"],))
                 ops.linear_fwd(ln, W[pf + ".fn.net.0.weight"], Act(pre), bias=P[pf + ".fn.net.0.bias"])
                 hid = self._act("sv.hid." + tag, pre.shape)
-                ops.gelu_fwd(pre, hid)
-                ops.linear_fwd(hid, W[pf + ".fn.net.3.weight"], Act(X), bias=P[pf + ".fn.net.3.bias"], accumulate=True)
-                subs.append(dict(kind="ffn", pre=pf, xin=xin, ln=ln, hpre=pre, hid=hid))
+                site_h = site_o = None
+                if drop is None:
+                    ops.gelu_fwd(pre, hid)
+                    ops.linear_fwd(hid, W[pf + ".fn.net.3.weight"], Act(X), bias=P[pf + ".fn.net.3.bias"], accumulate=True)
+                else:   # x += dropout(W2 dropout(gelu(pre)) + b2)
+                    site_h = drop.site()
+                    ops.gelu_dropout_fwd(pre, drop, site_h, hid)
+                    tmp = self._buf("fax.tmp", X.shape)
+                    ops.linear_fwd(hid, W[pf + ".fn.net.3.weight"], Act(tmp), bias=P[pf + ".fn.net.3.bias"])
+                    site_o = drop.site()
+                    ops.dropout_apply(tmp, drop, site_o, Act(X), residual=X)
+                subs.append(dict(kind="ffn", pre=pf, xin=xin, ln=ln, hpre=pre, hid=hid, site_h=site_h, site_o=site_o))
         m = self._act("fax.mean", (B, h2, w2, d))
         ops.agent_mean_layernorm(X, B, self.L, P["fusion_net.mlp_head.2.weight"], P["fusion_net.mlp_head.2.bias"], m)
         fused = self._act("fax.fused", (B, h2, w2, d))
@@ -312,7 +331,7 @@ class CoBEVTEngine(W2CEngine):
         heads = self._buf("heads.out", (B, h2, w2, HEAD_PAD))
         ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
         self.saved = dict(rec=rec, W=W, subs=subs, X=X, m=m, fused=fused, y1=y1, y2=y2, cat=cat, layout=layout,
-                          key_mask=key_mask, B=B)
+                          key_mask=key_mask, B=B, drop=drop)
         return heads
 
     def backward_train(self, P, dheads, grads):
@@ -375,16 +394,25 @@ class CoBEVTEngine(W2CEngine):
         dX = self._buf("bwd.dX", X.shape)
         ops.agent_broadcast(d_xbar, B, self.L, 1.0 / self.L, dX)
         # ---- sublayers in reverse
+        drop = S["drop"]
         for sl in reversed(S["subs"]):
             pre = sl["pre"]
-            dXs = split_of(dX, "bwd.dXs")
+            if drop is None:
+                dXs, g_out = split_of(dX, "bwd.dXs"), dX
+            else:   # gradient w.r.t. the sublayer's last linear = stream gradient through that site's dropout mask
+                dXs = self._act("bwd.dXs", dX.shape)
+                ops.dropout_apply(dX, drop, sl["site_o"], dXs)
+                g_out = dXs.hi
             if sl["kind"] == "ffn":
                 lin_wgrad(sl["hid"], dXs, pre + ".fn.net.3.weight")
-                col_sums(dX, d, [(grads[pre + ".fn.net.3.bias"], 0)])
+                col_sums(g_out, d, [(grads[pre + ".fn.net.3.bias"], 0)])
                 d_hid = self._buf("bwd.d_hid", sl["hid"].shape)
                 ops.conv_dgrad(dXs, W[pre + ".fn.net.3.weight"], 1, 1, d_hid)
                 d_pre = self._act("bwd.d_pre", sl["hid"].shape)
-                ops.gelu_bwd(d_hid, sl["hpre"], d_pre)
+                if drop is None:
+                    ops.gelu_bwd(d_hid, sl["hpre"], d_pre)
+                else:
+                    ops.gelu_dropout_bwd(d_hid, sl["hpre"], drop, sl["site_h"], d_pre)
                 lin_wgrad(sl["ln"], d_pre, pre + ".fn.net.0.weight")
                 col_sums(d_pre.hi, d_pre.shape[3], [(grads[pre + ".fn.net.0.bias"], 0)])
                 d_ln = self._buf("bwd.d_ln", X.shape)

@@ -5,7 +5,8 @@
 //
 // A persistent CTA owns one head and walks over windows. Two warpgroups: the LOADER (warps 4-7) gathers the q / k / v (/ dO)
 // rows of the next window from global memory, splits them and fills one of two tile buffers; the COMPUTE group (warps
-// 0-3: thread t <-> token t <-> TMEM lane t) issues the MMAs, runs the softmax and the epilogue. full / empty mbarriers
+// 0-7: threads r and r + 128 share token r = TMEM lane r and take 64 score columns / 16 output features each, exchanging
+// the row max / sum / D through shared memory) issues the MMAs, runs the softmax and the epilogue. full / empty mbarriers
 // per buffer (empty is arrived by tcgen05.commit of the window's last MMA), so global latency is off the compute path.
 // Every operand is the bf16 split pair of an fp32 row, kept side by side in ONE 128-byte shared-memory row
 // [hi(32) | lo(32)] with the 128-byte swizzle, so a tile is simply 128 rows x 128 B and the UMMA descriptors decide how
@@ -31,7 +32,7 @@ namespace a2x {
 constexpr int WT_W = 4;             // window edge
 constexpr int WT_S2 = 2 * WT_W - 1;
 constexpr int WT_DH = 32;
-constexpr int WT_AUX = 4096 + 4096 + 2 * 1024 + 256;   // bias | bias gradient | token tables (2) | barriers, TMEM slot
+constexpr int WT_AUX = 4096 + 4096 + 2 * 1024 + 256 + 3072;   // bias | bias gradient | token tables (2) | barriers, TMEM slot | row max / sum / D exchange
 
 struct WinTcParams {
     const float* qkv;      // [B*L][H][W][3*D]
@@ -87,7 +88,8 @@ __device__ __forceinline__ long long wt_token(const WinTcParams& p, int b, int x
     return ((long long)(b * p.L + l) * p.H + ph) * p.W + pw;
 }
 
-__device__ __forceinline__ void wt_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void wt_bar_load() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void wt_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // NT tensors' rows (32 floats each, tensor k at `src[k]` + token * rs[k]) -> [hi | lo] tiles at tile0 + toff[k].
 // ALL global loads of the window are issued before the first conversion (n * 4 <= 512 items of 32 B per tensor for the
@@ -154,22 +156,22 @@ __device__ __forceinline__ void wt_mma_pv(uint32_t tacc, uint32_t plane_addr, ui
     }
 }
 
-// the thread's score row from TMEM (+ relative-position bias, key mask) -> s[128]; returns the row maximum
-__device__ __forceinline__ float wt_scores(uint32_t trow, int n, int t, uint32_t kmask, const float* sB, int L, float* s) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-        if (c * 32 < n) tmem_ld_32x32(trow + c * 32, s + c * 32);
+// this thread's half (columns 64 h .. 64 h + 63) of score row r from TMEM (+ relative-position bias, key mask) -> s[64];
+// returns the maximum over the half
+__device__ __forceinline__ float wt_scores(uint32_t trow, int n, int r, int h, uint32_t kmask, const float* sB, int L, float* s) {
+    const int j0 = 64 * h;
+    if (j0 < n) tmem_ld_32x32(trow + j0, s);
+    if (j0 + 32 < n) tmem_ld_32x32(trow + j0 + 32, s + 32);
     tmem_ld_wait();
-    const int li = t >> 4, i1 = (t >> 2) & 3, i2 = t & 3;
-    const int base = ((li + L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1);
+    const int li = r >> 4, i1 = (r >> 2) & 3, i2 = r & 3;
+    const int base = ((li + L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - 4 * h * WT_S2 * WT_S2;
     float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 128; ++j) {
-        const int lj = j >> 4;
-        const int sub = (lj * WT_S2 + ((j >> 2) & 3)) * WT_S2 + (j & 3);
-        const bool ok = j < n && ((kmask >> lj) & 1u);
-        const float v = ok ? s[j] + sB[base - sub] : -INFINITY;
-        s[j] = v;
+    for (int jj = 0; jj < 64; ++jj) {
+        const int sub = ((jj >> 4) * WT_S2 + ((jj >> 2) & 3)) * WT_S2 + (jj & 3);
+        const bool ok = j0 + jj < n && ((kmask >> (4 * h + (jj >> 4))) & 1u);
+        const float v = ok ? s[jj] + sB[base - sub] : -INFINITY;
+        s[jj] = v;
         m = fmaxf(m, v);
     }
     return m;
@@ -194,6 +196,7 @@ struct WtSmem {
     long long* sTok;      // [2][128]
     uint64_t *full, *empty, *mma;
     uint32_t* tmem_slot;
+    float* sEx;           // [3][2][128]: row max | row sum | D, one value per (half, row)
 };
 __device__ __forceinline__ WtSmem wt_carve(uint8_t* raw, int tiles_bytes) {
     WtSmem w;
@@ -206,11 +209,12 @@ __device__ __forceinline__ WtSmem wt_carve(uint8_t* raw, int tiles_bytes) {
     w.empty = w.full + 2;
     w.mma = w.empty + 2;
     w.tmem_slot = reinterpret_cast<uint32_t*>(w.mma + 1);
+    w.sEx = reinterpret_cast<float*>(aux + 8192 + 2048 + 256);
     return w;
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTcParams p, int num_windows) {
+__global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTcParams p, int num_windows) {
     extern __shared__ uint8_t wt_raw[];
     const int n = p.L * 16;
     const uint32_t TS = (uint32_t)n * 128;
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTc
     const int head = blockIdx.x % p.heads;
     const int G = gridDim.x / p.heads;
     const int nb = (2 * p.L - 1) * WT_S2 * WT_S2;
-    for (int i = tid; i < nb; i += 256) {
+    for (int i = tid; i < nb; i += 384) {
         sm.sB[i] = p.bias[i * p.heads + head];
         sm.sdB[i] = 0.f;
     }
@@ -242,9 +246,9 @@ __global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTc
     tc_fence_after();
     const uint32_t tmem = *sm.tmem_slot;
 
-    if (warp >= 4) {
+    if (warp >= 8) {
         // ------------------------------------------------------------------ loader warpgroup
-        const int tl = tid - 128;
+        const int tl = tid - 256;
         int it = 0;
         for (int win = blockIdx.x / p.heads; win < num_windows; win += G, ++it) {
             const int buf = it & 1;
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTc
             const int y = win % Y, x = (win / Y) % X, b = win / (Y * X);
             mbar_wait(&sm.empty[buf], ((it >> 1) & 1) ^ 1);     // the MMAs that read this buffer have retired
             if (tl < n) sm.sTok[buf * 128 + tl] = wt_token(p, b, x, y, X, Y, tl);
-            wt_bar(2);
+            wt_bar_load();
             const float* q0 = p.qkv + head * WT_DH;
             if (BWD) {
                 const uint32_t toff[4] = {0, TS, 2 * TS, 3 * TS};
@@ -271,20 +275,24 @@ __global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTc
             mbar_arrive(&sm.full[buf]);
         }
     } else {
-        // ------------------------------------------------------------------ compute warpgroup
-        const int t = tid;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        // ------------------------------------------------------------------ compute warpgroups (two threads per row)
+        const int r = tid & 127, h = tid >> 7;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)n, 0, 0);
         const int nk = n >> 4;
-        const int li = t >> 4, i1 = (t >> 2) & 3, i2 = t & 3;
-        const int bbase = ((li + p.L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1);
-        const uint32_t tacc = trow + 256;    // backward: this thread's row of sum_windows dS (bias gradient), columns [256, 384)
+        const int li = r >> 4, i1 = (r >> 2) & 3, i2 = r & 3;
+        const int bbase = ((li + p.L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - 4 * h * WT_S2 * WT_S2;
+        const uint32_t tacc = trow + 256 + 64 * h;   // backward: this thread's 64 columns of sum_windows dS (bias gradient)
+        float* exM = sm.sEx;            // [2][128] row max
+        float* exS = sm.sEx + 256;      // row sum
+        float* exD = sm.sEx + 512;      // D
+        const bool live = 64 * h < n;   // this half holds keys (n <= 64: the second half idles through the barriers)
         if (BWD) {
             float z[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) z[j] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_st_32x32(tacc + c * 32, z);
+            tmem_st_32x32(tacc, z);
+            tmem_st_32x32(tacc + 32, z);
             tmem_st_wait();
         }
         uint32_t ph = 0;
@@ -296,8 +304,8 @@ __global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTc
             const int b = win / (Y * X);
             const uint32_t kmask = wt_kmask(p, b);
             mbar_wait(&sm.full[buf], (it >> 1) & 1);
-            const long long tok = t < n ? sm.sTok[buf * 128 + t] : 0;
-            if (t == 0) {
+            const long long tok = r < n ? sm.sTok[buf * 128 + r] : 0;
+            if (tid == 0) {
                 tc_fence_after();
                 wt_mma_qk(tmem, desc_lo_word(tb_a, 16), desc_lo_word(tb_a + TS, 16), idesc_s);                         // S
                 if (BWD) wt_mma_qk(tmem + 128, desc_lo_word(tb_a + 3 * TS, 16), desc_lo_word(tb_a + 2 * TS, 16), idesc_s);   // dP = dO V^T
@@ -306,96 +314,107 @@ __global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTc
             mbar_wait(sm.mma, ph);
             ph ^= 1;
             tc_fence_after();
-            float s[128];
-            const float m = wt_scores(trow, n, t, kmask, sm.sB, p.L, s);
+            float s[64];
+            exM[h * 128 + r] = wt_scores(trow, n, r, h, kmask, sm.sB, p.L, s);
+            wt_bar();
+            const float m = fmaxf(exM[r], exM[128 + r]);
             float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 128; ++j) {
+            for (int j = 0; j < 64; ++j) {
                 s[j] = __expf(s[j] - m);
                 sum += s[j];
             }
-            const float inv = 1.f / sum;
+            exS[h * 128 + r] = sum;
             if (!BWD) {
-                // every thread has read its S row and the S MMAs have retired: P may overwrite Q / K, O may overwrite S
+                // every thread has read its S columns and the S MMAs have retired: P may overwrite Q / K, O may overwrite S
+                if (r < n && live) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c)
-                    if (c * 8 < n && t < n) wt_store8_planes(tb, TS, t, c, s + c * 8);   // tiles have n rows: no row >= n
+                    for (int c = 0; c < 8; ++c)
+                        if (64 * h + c * 8 < n) wt_store8_planes(tb, TS, r, 8 * h + c, s + c * 8);   // tiles have n rows: no row >= n
+                }
                 fence_proxy_async();
                 tc_fence_before();
-                wt_bar(1);
-                if (t == 0) {
+                wt_bar();
+                if (tid == 0) {
                     tc_fence_after();
                     wt_mma_pv(tmem, tb_a, tb_a + 4 * TS, TS, nk, 0);
                     umma_commit(sm.mma);
                     umma_commit(&sm.empty[buf]);
                 }
+                const float inv = 1.f / (exS[r] + exS[128 + r]);
                 mbar_wait(sm.mma, ph);
                 ph ^= 1;
                 tc_fence_after();
-                float o[64];
-                tmem_ld_32x32(trow, o);
-                tmem_ld_32x32(trow + 32, o + 32);
+                float oh[16], ol[16];          // features 16 h .. 16 h + 15: (P Vh) and (P Vl) halves of the accumulator
+                tmem_ld_32x16(trow + 16 * h, oh);
+                tmem_ld_32x16(trow + 32 + 16 * h, ol);
                 tmem_ld_wait();
-                if (t < n) {
-                    const long long off = tok * D + head * WT_DH;
+                if (r < n) {
+                    const long long off = tok * D + head * WT_DH + 16 * h;
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4)
-                        store_split4(p.out, off + c, make_float4((o[c] + o[32 + c]) * inv, (o[c + 1] + o[33 + c]) * inv,
-                                                                 (o[c + 2] + o[34 + c]) * inv, (o[c + 3] + o[35 + c]) * inv));
+                    for (int c = 0; c < 16; c += 4)
+                        store_split4(p.out, off + c, make_float4((oh[c] + ol[c]) * inv, (oh[c + 1] + ol[c + 1]) * inv,
+                                                                 (oh[c + 2] + ol[c + 2]) * inv, (oh[c + 3] + ol[c + 3]) * inv));
                 }
             } else {
+                wt_bar();
+                const float inv = 1.f / (exS[r] + exS[128 + r]);
 #pragma unroll
-                for (int j = 0; j < 128; ++j) s[j] *= inv;                       // P
+                for (int j = 0; j < 64; ++j) s[j] *= inv;                        // P
+                if (r < n && live) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c)
-                    if (c * 8 < n && t < n) wt_store8_planes(tP, TS, t, c, s + c * 8);   // tiles have n rows: no row >= n
+                    for (int c = 0; c < 8; ++c)
+                        if (64 * h + c * 8 < n) wt_store8_planes(tP, TS, r, 8 * h + c, s + c * 8);
+                }
+                float Dv = 0.f;                                                   // this half of D_i = sum_j P_ij dP_ij
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (64 * h + c * 32 < n) {
+                        float dp[32];
+                        tmem_ld_32x32(trow + 128 + 64 * h + c * 32, dp);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (64 * h + c * 32 + j < n) Dv = fmaf(s[c * 32 + j], dp[j], Dv);   // TMEM columns >= n are stale (may be NaN)
+                    }
+                }
+                exD[h * 128 + r] = Dv;
                 fence_proxy_async();
                 tc_fence_before();
-                wt_bar(1);
-                if (t == 0) {
+                wt_bar();
+                if (tid == 0) {
                     tc_fence_after();
                     wt_mma_pv(tmem, smem_u32(tP), tb_a + 3 * TS, TS, nk, 1);      // dV = P^T dO  -> columns [0, 64) (S is in registers)
                     umma_commit(sm.mma);
                 }
-                float Dv = 0.f;                                                   // D_i = sum_j P_ij dP_ij (overlaps the dV MMAs)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c * 32 < n) {
-                        float dp[32];
-                        tmem_ld_32x32(trow + 128 + c * 32, dp);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < n) Dv = fmaf(s[c * 32 + j], dp[j], Dv);    // TMEM columns >= n are stale (may be NaN)
-                    }
-                }
+                Dv = exD[r] + exD[128 + r];
                 mbar_wait(sm.mma, ph);                                            // dV done: the planes may take dS
                 ph ^= 1;
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c * 32 < n) {
+                for (int c = 0; c < 2; ++c) {
+                    if (64 * h + c * 32 < n) {
                         float dp[32], ac[32];
-                        tmem_ld_32x32(trow + 128 + c * 32, dp);
+                        tmem_ld_32x32(trow + 128 + 64 * h + c * 32, dp);
                         tmem_ld_32x32(tacc + c * 32, ac);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float ds = c * 32 + j < n ? s[c * 32 + j] * (dp[j] - Dv) : 0.f;   // dS_ij (0 at masked keys)
+                            const float ds = 64 * h + c * 32 + j < n ? s[c * 32 + j] * (dp[j] - Dv) : 0.f;   // dS_ij (0 at masked keys)
                             dp[j] = ds;
                             ac[j] += ds;
                         }
                         tmem_st_32x32(tacc + c * 32, ac);
-                        if (t < n)
+                        if (r < n)
 #pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) wt_store8_planes(tP, TS, t, c * 4 + c8, dp + c8 * 8);
+                            for (int c8 = 0; c8 < 4; ++c8) wt_store8_planes(tP, TS, r, 8 * h + c * 4 + c8, dp + c8 * 8);
                     }
                 }
                 tmem_st_wait();
                 fence_proxy_async();
                 tc_fence_before();
-                wt_bar(1);
-                if (t == 0) {
+                wt_bar();
+                if (tid == 0) {
                     tc_fence_after();
                     const uint32_t pa = smem_u32(tP);
                     wt_mma_pv(tmem + 64, pa, tb_a, TS, nk, 1);                    // dK = dS^T (scale Q)
@@ -408,36 +427,36 @@ __global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTc
                 tc_fence_after();
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {                            // 0: dV, 1: dK, 2: dQ
-                    float o[64];
-                    tmem_ld_32x32(trow + part * 64, o);
-                    tmem_ld_32x32(trow + part * 64 + 32, o + 32);
+                    float oh[16], ol[16];
+                    tmem_ld_32x16(trow + part * 64 + 16 * h, oh);
+                    tmem_ld_32x16(trow + part * 64 + 32 + 16 * h, ol);
                     tmem_ld_wait();
-                    if (t < n) {
+                    if (r < n) {
                         const float f = part == 2 ? p.scale : 1.f;
-                        const long long off = tok * (3 * D) + (2 - part) * D + head * WT_DH;
+                        const long long off = tok * (3 * D) + (2 - part) * D + head * WT_DH + 16 * h;
 #pragma unroll
-                        for (int c = 0; c < 32; c += 4)
-                            store_split4(p.out, off + c, make_float4((o[c] + o[32 + c]) * f, (o[c + 1] + o[33 + c]) * f,
-                                                                     (o[c + 2] + o[34 + c]) * f, (o[c + 3] + o[35 + c]) * f));
+                        for (int c = 0; c < 16; c += 4)
+                            store_split4(p.out, off + c, make_float4((oh[c] + ol[c]) * f, (oh[c + 1] + ol[c + 1]) * f,
+                                                                     (oh[c + 2] + ol[c + 2]) * f, (oh[c + 3] + ol[c + 3]) * f));
                     }
                 }
             }
             tc_fence_before();
-            wt_bar(1);   // the accumulators (and, backward, the P / dS planes) are reused by the next window
+            wt_bar();   // the accumulators, the exchange slots (and, backward, the planes) are reused by the next window
         }
         if (BWD) {
-            // fold the per-thread rows of sum dS into the head's table (entry of (i, j) = bbase_i - sub_j)
+            // fold the per-thread columns of sum dS into the head's table (entry of (i, j) = bbase_i - sub_j)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c * 32 < n) {
+            for (int c = 0; c < 2; ++c) {
+                if (64 * h + c * 32 < n) {
                     float ac[32];
                     tmem_ld_32x32(tacc + c * 32, ac);
                     tmem_ld_wait();
-                    if (t < n) {
+                    if (r < n) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int jj = c * 32 + j;
-                            if (jj < n && ac[j] != 0.f)
+                            if (64 * h + jj < n && ac[j] != 0.f)
                                 atomicAdd(&sm.sdB[bbase - (((jj >> 4) * WT_S2 + ((jj >> 2) & 3)) * WT_S2 + (jj & 3))], ac[j]);
                         }
                     }
@@ -448,7 +467,7 @@ __global__ void __launch_bounds__(256, 1) window_attention_tc_kernel(const WinTc
     tc_fence_before();
     __syncthreads();
     if (BWD)
-        for (int i = tid; i < nb; i += 256)
+        for (int i = tid; i < nb; i += 384)
             if (sm.sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sm.sdB[i]);
     if (warp == 0) tmem_dealloc<TM_COLS>(tmem);
 }

@@ -6,7 +6,7 @@ Same registry name / class name / constructor (`cls(hypes["model"]["args"])`), s
 opencood/models/airv2x_cobevt.py:15-156 of the reference. The torch.nn layers below are parameter containers only
 (names + default init); their forward is never called. forward() in eval mode is the inference path; in train mode
 (grad enabled) it is wired to autograd through the fused forward_train / backward_train of the engine, and train_step()
-is the fused fast path (dropout disabled, explicitly); no CPU fallback.
+is the fused fast path (nn.Dropout as counter-based Philox masks); no CPU fallback.
 """
 import torch
 import torch.nn as nn
@@ -128,7 +128,9 @@ class Airv2xCoBEVT(Airv2xWhere2com):
         if args["obj_head"]:
             self.obj_head = nn.Conv2d(self.outC, args["anchor_number"], kernel_size=1)
         self.precision = precision
-        self.dropout = "error"   # "off": train with nn.Dropout disabled (the kernels implement dropout = identity)
+        # nn.Dropout(fax_fusion.drop_out) in train mode: "on" = counter-based Philox masks (csrc/dropout.cu), seeded per step
+        # from torch's default CPU generator (torch.manual_seed controls the run); "off" = disabled
+        self.dropout = "on"
         self._engine = None
         self._last_aux = None
 
@@ -154,12 +156,11 @@ class Airv2xCoBEVT(Airv2xWhere2com):
         lidar = self._lidar(data_dict, dev, layout)
         if self.training and torch.is_grad_enabled():
             # reference training loop (tools/train.py:216-221): model(batch) -> criterion -> loss.backward()
-            if float(self.args["fax_fusion"].get("drop_out", 0.0)) > 0 and self.dropout != "off":
-                raise NotImplementedError("fax_fusion.drop_out > 0: set model.dropout = \"off\" to train with dropout disabled")
             names = [n for n, p in self.named_parameters() if p.requires_grad]
             params = [p for n, p in self.named_parameters() if p.requires_grad]
             eng = self.engine
-            heads = _FusionStep.apply(self, lambda: eng.forward_train(self._param_dict(), lidar, layout), names, *params)
+            drop = self._dropout_state(None)
+            heads = _FusionStep.apply(self, lambda: eng.forward_train(self._param_dict(), lidar, layout, drop), names, *params)
         else:
             heads, _ = self.engine.forward(self._param_dict(), lidar, layout, self.training)
         A, K = self.args["anchor_number"], self.args["num_class"]
@@ -177,14 +178,29 @@ class Airv2xCoBEVT(Airv2xWhere2com):
             g[n] = p.grad
         return g
 
-    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, dropout="error"):
+    def _dropout_state(self, dropout):
+        """dropout: None -> self.dropout; "on" (a fresh seed from torch's default CPU generator), "off", an int seed, or a
+        ready ops.Dropout. Returns ops.Dropout or None."""
+        from ... import ops
+        p = float(self.args["fax_fusion"].get("drop_out", 0.0))
+        mode = self.dropout if dropout is None else dropout
+        if isinstance(mode, ops.Dropout):
+            return mode
+        if p <= 0.0 or mode == "off":
+            return None
+        if mode == "on":
+            return ops.Dropout(p, int(torch.randint(0, 2 ** 62, (1,)).item()))
+        if isinstance(mode, int):
+            return ops.Dropout(p, mode)
+        raise ValueError("dropout must be 'on', 'off', an int seed or an ops.Dropout, got %r" % (mode,))
+
+    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, dropout=None):
         """forward (train-mode BatchNorm) + PointPillarLossMultiClass + backward of the whole CoBEVT path on the CUDA
         kernels; parameter gradients land in p.grad, returns the device tensor [reg, cls, obj] (float64).
-        The reference applies nn.Dropout(fax_fusion.drop_out) in train mode (non-deterministic, no parity possible): the
-        kernels implement dropout = identity, so a yaml with drop_out > 0 needs the explicit dropout="off"."""
+        nn.Dropout(fax_fusion.drop_out) of the fusion network runs as counter-based masks (see _dropout_state); the state
+        used is kept in self.last_dropout (tests export its masks to the oracle)."""
         assert self.training, "train_step() needs model.train()"
-        if float(self.args["fax_fusion"].get("drop_out", 0.0)) > 0 and dropout != "off":
-            raise NotImplementedError("fax_fusion.drop_out > 0: pass dropout=\"off\" to train with dropout disabled")
+        drop = self.last_dropout = self._dropout_state(dropout)
         dev = next(self.parameters()).device
         layout = self._layout(data_dict, dev)
         if "key_mask" not in layout:
@@ -195,7 +211,7 @@ class Airv2xCoBEVT(Airv2xWhere2com):
         labels = self.prepare_labels(label_dict, dev)
         P = self._param_dict()
         eng = self.engine
-        heads = eng.forward_train(P, lidar, layout)
+        heads = eng.forward_train(P, lidar, layout, drop)
         loss3, dheads = eng.loss(heads, labels, cls_weight, reg_coe)
         eng.backward_train(P, dheads, self._grad_buffers())
         return loss3

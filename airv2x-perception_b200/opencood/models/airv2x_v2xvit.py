@@ -5,7 +5,7 @@ Same registry name / class name / constructor (`cls(hypes["model"]["args"])`), s
 for the shipped yaml, including the unused `prior_feed` and the frozen sinusoid table of the RTE embedding), same
 `forward(data_dict) -> {"psm","rm","obj","comm_rate"}` as opencood/models/airv2x_v2xvit.py:19-167 of the reference.
 The torch.nn layers below are parameter containers only; their forward is never called. forward() is the eval path,
-train_step() the fused training step (dropout disabled); no CPU fallback.
+train_step() the fused training step (nn.Dropout as counter-based Philox masks); no CPU fallback.
 """
 import math
 
@@ -147,7 +147,9 @@ class Airv2xV2XVit(Airv2xWhere2com):
         if args["obj_head"]:
             self.obj_head = nn.Conv2d(self.outC, args["anchor_number"], kernel_size=1)
         self.precision = precision
-        self.dropout = "error"   # "off": train with nn.Dropout disabled (the kernels implement dropout = identity)
+        # nn.Dropout (cav_att / pwindow_att / feed_forward `dropout`) in train mode: "on" = counter-based Philox masks
+        # (csrc/dropout.cu), seeded per step from torch's default CPU generator; "off" = disabled
+        self.dropout = "on"
         self._engine = None
         self._last_aux = None
 
@@ -170,12 +172,10 @@ class Airv2xV2XVit(Airv2xWhere2com):
         eng = self.engine
         if self.training and torch.is_grad_enabled():
             # reference training loop (tools/train.py:216-221): model(batch) -> criterion -> loss.backward()
-            if max(self._dropouts()) > 0 and self.dropout != "off":
-                raise NotImplementedError("transformer.encoder dropout > 0: set model.dropout = \"off\" to train with "
-                                          "dropout disabled")
             names = [n for n, p in self.named_parameters() if p.requires_grad]
             params = [p for n, p in self.named_parameters() if p.requires_grad]
-            heads = _FusionStep.apply(self, lambda: eng.forward_train(self._param_dict(), lidar, layout, prior, scm),
+            drops = self._dropout_state(None)
+            heads = _FusionStep.apply(self, lambda: eng.forward_train(self._param_dict(), lidar, layout, prior, scm, drops),
                                       names, *params)
             aux = eng.last_aux
         else:
@@ -201,16 +201,38 @@ class Airv2xV2XVit(Airv2xWhere2com):
         return [float(enc["cav_att_config"].get("dropout", 0.0)), float(enc["pwindow_att_config"].get("dropout", 0.0)),
                 float(enc["feed_forward"].get("dropout", 0.0))]
 
-    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, dropout="error"):
+    def _dropout_state(self, dropout):
+        """dropout: None -> self.dropout; "on" (fresh seed from torch's default CPU generator), "off", or an int seed.
+        Returns None or the (cav, pwindow, ffn) ops.Dropout states: one seed, disjoint site-id ranges, own rates."""
+        from ... import ops
+        mode = self.dropout if dropout is None else dropout
+        ps = self._dropouts()
+        if isinstance(mode, tuple):
+            return mode
+        if max(ps) <= 0.0 or mode == "off":
+            return None
+        if mode == "on":
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        elif isinstance(mode, int):
+            seed = mode
+        else:
+            raise ValueError("dropout must be 'on', 'off' or an int seed, got %r" % (mode,))
+        out = []
+        for k, p in enumerate(ps):
+            d = ops.Dropout(p, seed) if p > 0 else None
+            if d is not None:
+                d.n_sites = 1000 * k
+            out.append(d)
+        return tuple(out)
+
+    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, dropout=None):
         """forward (train-mode BatchNorm) + PointPillarLossMultiClass + backward of the whole V2X-ViT path on the CUDA
         kernels; parameter gradients land in p.grad, returns the device tensor [reg, cls, obj] (float64).
-        The reference applies nn.Dropout (cav_att / pwindow_att / feed_forward `dropout`) in train mode, which is
-        non-deterministic and has no parity target: the kernels implement dropout = identity, so a yaml with a dropout
-        > 0 needs the explicit dropout="off". The RTE embedding table receives a gradient as it does in the reference
+        nn.Dropout (cav_att / pwindow_att / feed_forward `dropout`) runs as counter-based masks (see _dropout_state; the
+        states used are kept in self.last_dropout). The RTE embedding table receives a gradient as it does in the reference
         (`emb.requires_grad = False` at v2xvit_basic.py:53 sets a module attribute, the weight stays trainable)."""
         assert self.training, "train_step() needs model.train()"
-        if max(self._dropouts()) > 0 and dropout != "off":
-            raise NotImplementedError("transformer.encoder dropout > 0: pass dropout=\"off\" to train with dropout disabled")
+        drops = self.last_dropout = self._dropout_state(dropout)
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("Airv2xV2XVit (B200) needs its parameters on a CUDA device; there is no CPU path")
@@ -219,7 +241,7 @@ class Airv2xV2XVit(Airv2xWhere2com):
         labels = self.prepare_labels(label_dict, dev)
         P = self._param_dict()
         eng = self.engine
-        heads = eng.forward_train(P, lidar, layout, data_dict["prior_encoding"], data_dict["spatial_correction_matrix"])
+        heads = eng.forward_train(P, lidar, layout, data_dict["prior_encoding"], data_dict["spatial_correction_matrix"], drops)
         loss3, dheads = eng.loss(heads, labels, cls_weight, reg_coe)
         eng.backward_train(P, dheads, self._grad_buffers())
         return loss3

@@ -638,6 +638,45 @@ def gelu_fwd(x, out):
     return out
 
 
+class Dropout:
+    """one training step's dropout state: rate p, the step's 64-bit seed, and a running site counter (every nn.Dropout
+    call site of the forward takes the next id; the backward looks the id up again)"""
+
+    def __init__(self, p, seed):
+        self.p, self.seed, self.n_sites = float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+
+    def site(self):
+        self.n_sites += 1
+        return self.n_sites - 1
+
+
+def dropout_apply(y, drop, site, out, residual=None, write_hi=True):
+    """out (Act) = residual + y * keep / (1 - p); y / residual dense fp32 tensors; drop None or p == 0: plain copy / add"""
+    p = drop.p if drop is not None else 0.0
+    call("a2x_dropout_apply", _ptr(y), _ptr(residual), c_ll(y.numel()), ctypes.c_ulonglong(drop.seed if drop else 0),
+         ctypes.c_uint(site), c_f(p), _op_planes(out, write_hi), stream_ptr())
+    return out
+
+
+def gelu_dropout_fwd(x, drop, site, out):
+    call("a2x_gelu_dropout_fwd", _ptr(x), c_ll(x.numel()), ctypes.c_ulonglong(drop.seed), ctypes.c_uint(site), c_f(drop.p),
+         _op(out), stream_ptr())
+    return out
+
+
+def gelu_dropout_bwd(dy, x, drop, site, out):
+    call("a2x_gelu_dropout_bwd", _ptr(dy), _ptr(x), c_ll(x.numel()), ctypes.c_ulonglong(drop.seed), ctypes.c_uint(site),
+         c_f(drop.p), _op(out), stream_ptr())
+    return out
+
+
+def dropout_mask(n, drop, site):
+    """uint8 keep flags of a site (test hook: identical masks for the oracle)"""
+    m = torch.empty(n, dtype=torch.uint8, device="cuda")
+    call("a2x_dropout_mask", c_ll(n), ctypes.c_ulonglong(drop.seed), ctypes.c_uint(site), c_f(drop.p), _ptr(m), stream_ptr())
+    return m
+
+
 def gelu_bwd(dy, x, out):
     call("a2x_gelu_bwd", _ptr(dy), _ptr(x), c_ll(x.numel()), _op(out), stream_ptr())
     return out

@@ -230,10 +230,14 @@ class V2XViTEngine(CoBEVTEngine):
         return fused
 
     # ------------------------------------------------------------------ training step
-    def forward_train(self, P, lidar, layout, prior, scm):
-        """Train-mode forward (batch-statistic BatchNorm in the encoder, dropout = identity) keeping what the backward
-        needs: per sublayer the residual input, the LayerNorm output, the projected q|k|v tensors, the attention outputs,
-        the three window branches with the split-attention statistics, the FFN pre-activation and hidden activation."""
+    def forward_train(self, P, lidar, layout, prior, scm, drops=None):
+        """Train-mode forward (batch-statistic BatchNorm in the encoder) keeping what the backward needs: per sublayer the
+        residual input, the LayerNorm output, the projected q|k|v tensors, the attention outputs, the three window
+        branches with the split-attention statistics, the FFN pre-activation and hidden activation.
+        drops: None (nn.Dropout disabled) or (cav, pwindow, ffn) ops.Dropout states (each None when its rate is 0) for
+        HGTCavAttention.drop_out (hmsa.py:155), BaseWindowAttention.to_out's Dropout (mswin.py:47) and FeedForward's two
+        Dropouts (base_transformer.py:22,24); masks are regenerated from (seed, site) in the backward."""
+        dropc, dropw, dropf = drops if drops is not None else (None, None, None)
         self._begin_step()
         rec = []
         W = self._pack_weights(P)
@@ -292,9 +296,17 @@ class V2XViTEngine(CoBEVTEngine):
             for b in range(B):
                 s, e = starts[b], starts[b] + record_len[b]
                 ops.hgt_attention_fwd(qkv[s:e], types_dev[s:e], kmask[s:e], ca["heads"], ca["dim_head"], att.narrow_n(s, e - s))
-            for s, e, t in runs:
-                ops.linear_fwd(att.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], Act(X[s:e]),
-                               bias=P["%s.a_linears.%d.bias" % (f, t)], accumulate=True)
+            if dropc is None:
+                for s, e, t in runs:
+                    ops.linear_fwd(att.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], Act(X[s:e]),
+                                   bias=P["%s.a_linears.%d.bias" % (f, t)], accumulate=True)
+            else:   # x += dropout(a_linear(att))
+                tmp = self._buf("vit.tmp", X.shape)
+                for s, e, t in runs:
+                    ops.linear_fwd(att.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], Act(tmp[s:e]),
+                                   bias=P["%s.a_linears.%d.bias" % (f, t)])
+                sv["site_h"] = dropc.site()
+                ops.dropout_apply(tmp, dropc, sv["site_h"], Act(X), residual=X)
             # pyramid window attention + split attention
             sv["xin_p"] = self._buf(tag + "xin_p", X.shape)
             sv["xin_p"].copy_(X)
@@ -310,6 +322,9 @@ class V2XViTEngine(CoBEVTEngine):
                 ops.window_attention_fwd(wqkv, table, None, N, 1, hh, dh, ws, False, watt)
                 win = self._buf(tag + "win%d" % lv, (N, h, w, C))
                 ops.linear_fwd(watt, W[bp_l + ".to_out.0.weight"], Act(win), bias=P[bp_l + ".to_out.0.bias"])
+                if dropw is not None:
+                    sv.setdefault("site_w", []).append(dropw.site())
+                    ops.dropout_apply(win, dropw, sv["site_w"][-1], Act(win))
                 sv["wqkv"].append(wqkv)
                 sv["watt"].append(watt)
                 sv["win"].append(win)
@@ -326,8 +341,16 @@ class V2XViTEngine(CoBEVTEngine):
             pre = sv["hpre"] = self._buf(tag + "hpre", (N, h, w, enc["feed_forward"]["mlp_dim"]))
             ops.linear_fwd(ln, W[lp + ".1.fn.net.0.weight"], Act(pre), bias=P[lp + ".1.fn.net.0.bias"])
             hid = sv["hid"] = self._act(tag + "hid", pre.shape)
-            ops.gelu_fwd(pre, hid)
-            ops.linear_fwd(hid, W[lp + ".1.fn.net.3.weight"], Act(X), bias=P[lp + ".1.fn.net.3.bias"], accumulate=True)
+            if dropf is None:
+                ops.gelu_fwd(pre, hid)
+                ops.linear_fwd(hid, W[lp + ".1.fn.net.3.weight"], Act(X), bias=P[lp + ".1.fn.net.3.bias"], accumulate=True)
+            else:   # x += dropout(W2 dropout(gelu(pre)) + b2)
+                sv["site_f1"] = dropf.site()
+                ops.gelu_dropout_fwd(pre, dropf, sv["site_f1"], hid)
+                tmp = self._buf("vit.tmp", X.shape)
+                ops.linear_fwd(hid, W[lp + ".1.fn.net.3.weight"], Act(tmp), bias=P[lp + ".1.fn.net.3.bias"])
+                sv["site_f2"] = dropf.site()
+                ops.dropout_apply(tmp, dropf, sv["site_f2"], Act(X), residual=X)
             layers.append(sv)
         fused = self._act("vit.fused", (B, h, w, C))
         ones = self._buf("vit.ones", (B,), torch.int32)
@@ -336,7 +359,8 @@ class V2XViTEngine(CoBEVTEngine):
         heads = self._buf("heads.out", (B, h, w, HEAD_PAD))
         ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
         self.saved = dict(rec=rec, W=W, layers=layers, fused=fused, y1=y1, y2=y2, cat=cat, layout=layout, B=B, runs=runs,
-                          starts=starts, types_dev=types_dev, kmask=kmask, theta=theta, rte_idx=rte_idx)
+                          starts=starts, types_dev=types_dev, kmask=kmask, theta=theta, rte_idx=rte_idx,
+                          drops=(dropc, dropw, dropf))
         return heads
 
     def backward_train(self, P, dheads, grads):
@@ -344,6 +368,7 @@ class V2XViTEngine(CoBEVTEngine):
         `prior_feed` stays zero, as autograd leaves it in the reference)."""
         S = self.saved
         W, layout, B, runs, starts = S["W"], S["layout"], S["B"], S["runs"], S["starts"]
+        dropc, dropw, dropf = S["drops"]
         enc = self.enc
         ca, pw = enc["cav_att_config"], enc["pwindow_att_config"]
         record_len = layout["record_len"]
@@ -410,13 +435,21 @@ class V2XViTEngine(CoBEVTEngine):
             sv = S["layers"][d]
             # ---- feed forward
             pre = lp + ".1"
-            dXs = split_of(dX, "bwd.dXs")
+            if dropf is None:
+                dXs, g_out = split_of(dX, "bwd.dXs"), dX
+            else:
+                dXs = self._act("bwd.dXs", dX.shape)
+                ops.dropout_apply(dX, dropf, sv["site_f2"], dXs)
+                g_out = dXs.hi
             lin_wgrad(sv["hid"], dXs, pre + ".fn.net.3.weight")
-            col_sums(dX, C, [(grads[pre + ".fn.net.3.bias"], 0)])
+            col_sums(g_out, C, [(grads[pre + ".fn.net.3.bias"], 0)])
             d_hid = self._buf("bwd.d_hid", sv["hid"].shape)
             ops.conv_dgrad(dXs, W[pre + ".fn.net.3.weight"], 1, 1, d_hid)
             d_pre = self._act("bwd.d_pre", sv["hid"].shape)
-            ops.gelu_bwd(d_hid, sv["hpre"], d_pre)
+            if dropf is None:
+                ops.gelu_bwd(d_hid, sv["hpre"], d_pre)
+            else:
+                ops.gelu_dropout_bwd(d_hid, sv["hpre"], dropf, sv["site_f1"], d_pre)
             lin_wgrad(sv["ln_f"], d_pre, pre + ".fn.net.0.weight")
             col_sums(d_pre.hi, d_pre.shape[3], [(grads[pre + ".fn.net.0.bias"], 0)])
             ops.conv_dgrad(d_pre, W[pre + ".fn.net.0.weight"], 1, 1, d_ln)
@@ -433,6 +466,8 @@ class V2XViTEngine(CoBEVTEngine):
                                grads[sp + ".fc2.weight"])
             for lv, (hh, dhd, ws) in enumerate(zip(pw["heads"], pw["dim_head"], pw["window_size"])):
                 bp_l = "%s.fn.pwmsa.%d" % (pwp, lv)
+                if dropw is not None:   # d(to_out output) = d(branch) through the branch's dropout mask
+                    ops.dropout_apply(dwin[lv].hi, dropw, sv["site_w"][lv], dwin[lv])
                 lin_wgrad(sv["watt"][lv], dwin[lv], bp_l + ".to_out.0.weight")
                 col_sums(dwin[lv].hi, C, [(grads[bp_l + ".to_out.0.bias"], 0)])
                 d_att = self._buf("bwd.d_att", (N, h, w, C))
@@ -448,14 +483,19 @@ class V2XViTEngine(CoBEVTEngine):
                 ops.conv_dgrad(dqs, W[bp_l + ".to_qkv.weight"], 1, 1, d_ln, accumulate=lv > 0)
             ln_bwd(sv["xin_p"], d_ln, pwp + ".norm", dX)
             # ---- HGT multi-agent attention
-            dXs = split_of(dX, "bwd.dXs")
+            if dropc is None:
+                dXs, g_out = split_of(dX, "bwd.dXs"), dX
+            else:
+                dXs = self._act("bwd.dXs", dX.shape)
+                ops.dropout_apply(dX, dropc, sv["site_h"], dXs)
+                g_out = dXs.hi
             d_att = self._buf("bwd.d_att", (N, h, w, C))
             asums = self._zeroed("hgt.asums", 2 * 2 * C, torch.float64).view(2, 2 * C)
             for t in range(2):  # an agent type absent from the batch gets a zero gradient
                 dwp_for("%s.a_linears.%d.weight" % (f, t), C, C)
             for s, e, t in runs:
                 lin_wgrad(sv["hatt"].narrow_n(s, e - s), dXs.narrow_n(s, e - s), "%s.a_linears.%d.weight" % (f, t))
-                ops.channel_stats(dX[s:e], asums[t])
+                ops.channel_stats(g_out[s:e], asums[t])
                 ops.conv_dgrad(dXs.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], 1, 1, d_att[s:e])
             for t in range(2):
                 unpack.append(ops.sums_unpack_job(asums[t], grads["%s.a_linears.%d.bias" % (f, t)], 0))

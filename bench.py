@@ -281,6 +281,11 @@ class Workload:
     def train_step(self, dd=None, lab=None):
         return self.model.train_step(dd or self.dd_dev, lab or self.lab_dev, self.cw, self.rc)
 
+    @property
+    def dropout_note(self):
+        d = getattr(self.model, "dropout", None)
+        return None if d is None else "nn.Dropout of the transformer fusion: %s" % d
+
 
 def time_steps(torch, fn, n, warm):
     for _ in range(warm):

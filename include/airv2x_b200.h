@@ -186,6 +186,23 @@ int a2x_layernorm_bwd(const float* x, int x_cs, const float* dy, int dy_cs, long
                       float eps, float* dx_accum, int dx_cs, double* dgamma, double* dbeta, a2x_stream_t stream);
 int a2x_gelu_fwd(const float* x, long long n, const a2x_output* y, a2x_stream_t stream);
 int a2x_gelu_bwd(const float* dy, const float* x, long long n, const a2x_output* dx, a2x_stream_t stream);
+/* nn.Dropout of the transformer fusion networks in train mode (opencood/models/cobevt_modules/base_transformer.py:27-56,
+ * swap_fusion_modules.py:43, v2xvit_modules/base_transformer.py:17-46, hmsa.py:18,155, mswin.py:47): counter-based
+ * (Philox4x32-10) keep flags, a pure function of (seed, site, element index), regenerated by the backward kernels.
+ *   a2x_dropout_apply      out = (residual ? residual : 0) + y * keep / (1 - p)      (dense tensors of n elements, n % 8 == 0;
+ *                          residual may alias out->hi: the fused "x += dropout(linear(...))" of PreNormResidual; the
+ *                          backward calls it on the stream gradient to get d(linear output))
+ *   a2x_gelu_dropout_fwd   y  = gelu(x) * keep / (1 - p)                              (FeedForward: Linear, GELU, Dropout)
+ *   a2x_gelu_dropout_bwd   dx = dy * keep / (1 - p) * gelu'(x)
+ *   a2x_dropout_mask       the keep flags (uint8) of a site: for tests that feed identical masks to the oracle
+ * p = 0 turns the mask off (plain copy / GELU). */
+int a2x_dropout_apply(const float* y, const float* residual, long long n, unsigned long long seed, unsigned int site, float p,
+                      const a2x_output* out, a2x_stream_t stream);
+int a2x_gelu_dropout_fwd(const float* x, long long n, unsigned long long seed, unsigned int site, float p, const a2x_output* y,
+                         a2x_stream_t stream);
+int a2x_gelu_dropout_bwd(const float* dy, const float* x, long long n, unsigned long long seed, unsigned int site, float p,
+                         const a2x_output* dx, a2x_stream_t stream);
+int a2x_dropout_mask(long long n, unsigned long long seed, unsigned int site, float p, unsigned char* mask, a2x_stream_t stream);
 int a2x_window_attention_bwd(const float* qkv, const float* dout, const float* bias_table, const int* key_mask, int B,
                              int L, int H, int W, int heads, int dim_head, int window, int grid_mode, float scale,
                              float* dqkv, float* dbias_table, a2x_stream_t stream);

@@ -68,39 +68,68 @@ def window_attention(sd, pre, x, mask, dim_head):
     return out.reshape(b, X, Y, L, w1, w2, d).permute(0, 3, 1, 2, 4, 5, 6)
 
 
-def feed_forward(sd, pre, x):
-    """base_transformer.py:16-28 (dropout is identity in eval / p handled by the caller in train)"""
+class MaskedDropout:
+    """nn.Dropout with GIVEN keep masks (test hook): the reference draws a fresh Bernoulli mask per call; a parity test
+    feeds the masks the implementation under test used. masks: flat uint8 tensors in call order, each laid out like the
+    implementation's token tensor [b*L, H, W, C]; `part` maps a [b, L, C, H, W] tensor to the layout of the tensor being
+    dropped (the window / grid partition of the caller)."""
+
+    def __init__(self, p, masks):
+        self.p, self.masks, self.i = float(p), list(masks), 0
+
+    def __call__(self, t, part, bLHW):
+        b, L, H, W = bLHW
+        m = self.masks[self.i]
+        self.i += 1
+        m5 = m.reshape(b, L, H, W, -1).permute(0, 1, 4, 2, 3).to(t.dtype)
+        return t * part(m5) / (1.0 - self.p)
+
+
+def feed_forward(sd, pre, x, drop=None):
+    """base_transformer.py:16-28: Linear, GELU, Dropout, Linear, Dropout (drop: callable or None = identity)"""
     x = F.gelu(F.linear(x, sd[pre + ".net.0.weight"], sd[pre + ".net.0.bias"]))
-    return F.linear(x, sd[pre + ".net.3.weight"], sd[pre + ".net.3.bias"])
+    if drop is not None:
+        x = drop(x)
+    x = F.linear(x, sd[pre + ".net.3.weight"], sd[pre + ".net.3.bias"])
+    return drop(x) if drop is not None else x
 
 
 def _ln(sd, pre, x):
     return F.layer_norm(x, (x.shape[-1],), sd[pre + ".weight"], sd[pre + ".bias"], 1e-5)
 
 
-def swap_fusion_block(sd, pre, x, mask, w, dim_head):
-    """x: [b, L, d, H, W]; mask: [b, H, W, 1, L]; SwapFusionBlockMask.forward :155-195"""
+def swap_fusion_block(sd, pre, x, mask, w, dim_head, dropout=None):
+    """x: [b, L, d, H, W]; mask: [b, H, W, 1, L]; SwapFusionBlockMask.forward :155-195. dropout: MaskedDropout or None;
+    call order = the module's: Attention.to_out's Dropout (:43), FeedForward's two (base_transformer.py:32,34), per
+    window then grid half."""
     b, L, d, H, W = x.shape
     X, Y = H // w, W // w
+    part_w = lambda t: t.reshape(b, L, t.shape[2], X, w, Y, w).permute(0, 1, 3, 5, 4, 6, 2)
+    part_g = lambda t: t.reshape(b, L, t.shape[2], w, X, w, Y).permute(0, 1, 4, 6, 3, 5, 2)
+    dw = (lambda t: dropout(t, part_w, (b, L, H, W))) if dropout is not None else None
+    dg = (lambda t: dropout(t, part_g, (b, L, H, W))) if dropout is not None else None
+    ident = lambda t: t
     # window partition: (x w1) (y w2)
-    xw = x.reshape(b, L, d, X, w, Y, w).permute(0, 1, 3, 5, 4, 6, 2)               # b L X Y w1 w2 d
+    xw = part_w(x)                                                                 # b L X Y w1 w2 d
     mw = mask.reshape(b, X, w, Y, w, 1, L).permute(0, 1, 3, 2, 4, 5, 6) if mask is not None else None
-    xw = window_attention(sd, pre + ".window_attention.fn", _ln(sd, pre + ".window_attention.norm", xw), mw, dim_head) + xw
-    xw = feed_forward(sd, pre + ".window_ffd.fn", _ln(sd, pre + ".window_ffd.norm", xw)) + xw
+    xw = (dw or ident)(window_attention(sd, pre + ".window_attention.fn", _ln(sd, pre + ".window_attention.norm", xw), mw,
+                                        dim_head)) + xw
+    xw = feed_forward(sd, pre + ".window_ffd.fn", _ln(sd, pre + ".window_ffd.norm", xw), dw) + xw
     x = xw.permute(0, 1, 6, 2, 4, 3, 5).reshape(b, L, d, H, W)
     # grid partition: (w1 x) (w2 y)
-    xg = x.reshape(b, L, d, w, X, w, Y).permute(0, 1, 4, 6, 3, 5, 2)               # b L X Y w1 w2 d
+    xg = part_g(x)                                                                 # b L X Y w1 w2 d
     mg = mask.reshape(b, w, X, w, Y, 1, L).permute(0, 2, 4, 1, 3, 5, 6) if mask is not None else None
-    xg = window_attention(sd, pre + ".grid_attention.fn", _ln(sd, pre + ".grid_attention.norm", xg), mg, dim_head) + xg
-    xg = feed_forward(sd, pre + ".grid_ffd.fn", _ln(sd, pre + ".grid_ffd.norm", xg)) + xg
+    xg = (dg or ident)(window_attention(sd, pre + ".grid_attention.fn", _ln(sd, pre + ".grid_attention.norm", xg), mg,
+                                        dim_head)) + xg
+    xg = feed_forward(sd, pre + ".grid_ffd.fn", _ln(sd, pre + ".grid_ffd.norm", xg), dg) + xg
     return xg.permute(0, 1, 6, 4, 2, 5, 3).reshape(b, L, d, H, W)
 
 
-def swap_fusion_encoder(sd, fa, x, mask, pre="fusion_net", keep=None):
+def swap_fusion_encoder(sd, fa, x, mask, pre="fusion_net", keep=None, dropout=None):
     """SwapFusionEncoder.forward :277-280"""
     for i in range(fa["depth"]):
         x = swap_fusion_block(sd, "%s.layers.%d" % (pre, i), x, mask if fa.get("mask", False) else None,
-                              fa["window_size"], fa["dim_head"])
+                              fa["window_size"], fa["dim_head"], dropout)
         if keep is not None:
             keep["block%d" % i] = x
     x = x.mean(1).permute(0, 2, 3, 1)                                              # b h w d  (padded agents included)
@@ -117,8 +146,9 @@ def naive_compressor(sd, x, training, buffers, pre="naive_compressor"):
     return x
 
 
-def cobevt_forward(sd, args, data_dict, training=False, keep=None):
-    """models/airv2x_cobevt.py:112-156 (task == det; dropout = identity, i.e. eval mode or drop_out 0)."""
+def cobevt_forward(sd, args, data_dict, training=False, keep=None, dropout=None):
+    """models/airv2x_cobevt.py:112-156 (task == det). dropout: None = nn.Dropout is the identity (eval mode / drop_out 0),
+    or a MaskedDropout carrying the keep masks of every nn.Dropout call of the fusion network."""
     buffers = {}
     sf, record_len = O.extract_features(sd, args, data_dict, training, buffers, keep)
     feat = O.backbone_forward(sd, args["base_bev_backbone"], sf, training, buffers)
@@ -132,7 +162,7 @@ def cobevt_forward(sd, args, data_dict, training=False, keep=None):
         keep["regroup"] = x
     H, W = x.shape[3], x.shape[4]
     com_mask = mask[:, None, None, None, :].expand(-1, H, W, 1, -1)                 # b h w 1 l
-    fused = swap_fusion_encoder(sd, args["fax_fusion"], x, com_mask, keep=keep)
+    fused = swap_fusion_encoder(sd, args["fax_fusion"], x, com_mask, keep=keep, dropout=dropout)
     if keep is not None:
         keep["fused_feature"] = fused
     out = {"psm": F.conv2d(fused, sd["cls_head.weight"], sd["cls_head.bias"]),

@@ -95,8 +95,8 @@ def sttf(x, scm, discrete_ratio, downsample_rate):
     return torch.cat([xc[:, :1], cav], 1).permute(0, 1, 3, 4, 2)
 
 
-def hgt_attention(sd, pre, x, mask, prior, heads, dim_head, num_types=2):
-    """hmsa.py:117-158. x (B,L,H,W,C) normalised; mask (B,H,W,1,L); prior (B,L,H,W,3)"""
+def hgt_attention(sd, pre, x, mask, prior, heads, dim_head, num_types=2, drop=None):
+    """hmsa.py:117-158. x (B,L,H,W,C) normalised; mask (B,H,W,1,L); prior (B,L,H,W,3); drop: the nn.Dropout of :155"""
     B, L, H, W, C = x.shape
     types = prior[:, :, 0, 0, 2].to(torch.int)
 
@@ -120,11 +120,12 @@ def hgt_attention(sd, pre, x, mask, prior, heads, dim_head, num_types=2):
     v_msg = torch.einsum("bmijpc,bmhwjp->bmhwijc", w_msg, v)
     out = torch.einsum("bmhwij,bmhwijc->bmhwic", att, v_msg)
     out = out.permute(0, 4, 2, 3, 1, 5).reshape(B, L, H, W, heads * dim_head)
-    return typed("a_linears", out)
+    out = typed("a_linears", out)
+    return drop(out) if drop is not None else out
 
 
-def base_window_attention(sd, pre, x, heads, dim_head, ws):
-    """mswin.py:23-108 (relative_pos_embedding = True)"""
+def base_window_attention(sd, pre, x, heads, dim_head, ws, drop=None):
+    """mswin.py:23-108 (relative_pos_embedding = True); drop: to_out's nn.Dropout (:47)"""
     B, L, H, W, C = x.shape
     nh, nw = H // ws, W // ws
     q, k, v = F.linear(x, sd[pre + ".to_qkv.weight"]).chunk(3, -1)
@@ -140,7 +141,8 @@ def base_window_attention(sd, pre, x, heads, dim_head, ws):
     dots = dots + sd[pre + ".pos_embedding"][rel[:, :, 0], rel[:, :, 1]]
     out = dots.softmax(-1) @ v
     out = out.reshape(B, L, heads, nh, nw, ws, ws, dim_head).permute(0, 1, 3, 5, 4, 6, 2, 7).reshape(B, L, H, W, heads * dim_head)
-    return F.linear(out, sd[pre + ".to_out.0.weight"], sd[pre + ".to_out.0.bias"])
+    out = F.linear(out, sd[pre + ".to_out.0.weight"], sd[pre + ".to_out.0.bias"])
+    return drop(out) if drop is not None else out
 
 
 def split_attn(sd, pre, wins):
@@ -154,16 +156,39 @@ def split_attn(sd, pre, wins):
     return sw * a[..., 0:C] + mw * a[..., C:2 * C] + bw * a[..., 2 * C:]
 
 
-def pyramid_window_attention(sd, pre, x, cfg):
-    wins = [base_window_attention(sd, "%s.pwmsa.%d" % (pre, i), x, h, d, ws)
+def pyramid_window_attention(sd, pre, x, cfg, drop=None):
+    wins = [base_window_attention(sd, "%s.pwmsa.%d" % (pre, i), x, h, d, ws, drop)
             for i, (h, d, ws) in enumerate(zip(cfg["heads"], cfg["dim_head"], cfg["window_size"]))]
     if cfg["fusion_method"] == "split_attn":
         return split_attn(sd, pre + ".split_attn", wins)
     return sum(wins) / len(wins)
 
 
-def v2x_encoder(sd, enc, x, mask, scm, pre="fusion_net.encoder", keep=None):
+class MaskedDropouts:
+    """test hook: the three nn.Dropout groups of the encoder (HGT output, window branches, feed forward) with GIVEN keep
+    masks, consumed in call order; each mask is laid out like the tensor it drops, (B, L, H, W, C) flattened."""
+
+    def __init__(self, ps, masks):
+        """ps = (p_cav, p_window, p_ffn); masks = {"cav": [...], "win": [...], "ffn": [...]} (uint8 tensors)"""
+        self.ps, self.masks, self.i = ps, masks, {"cav": 0, "win": 0, "ffn": 0}
+
+    def fn(self, group):
+        p = self.ps[("cav", "win", "ffn").index(group)]
+        if p <= 0:
+            return None
+
+        def apply(t):
+            m = self.masks[group][self.i[group]]
+            self.i[group] += 1
+            return t * m.reshape(t.shape).to(t.dtype) / (1.0 - p)
+        return apply
+
+
+def v2x_encoder(sd, enc, x, mask, scm, pre="fusion_net.encoder", keep=None, dropouts=None):
     """V2XTEncoder.forward v2xvit_basic.py:174-200 + V2XTransformer (:211-213). x (B,L,H,W,C+3)"""
+    d_cav = dropouts.fn("cav") if dropouts is not None else None
+    d_win = dropouts.fn("win") if dropouts is not None else None
+    d_ffn = dropouts.fn("ffn") if dropouts is not None else None
     prior = x[..., -3:]
     x = x[..., :-3]
     ca, pw = enc["cav_att_config"], enc["pwindow_att_config"]
@@ -181,15 +206,16 @@ def v2x_encoder(sd, enc, x, mask, scm, pre="fusion_net.encoder", keep=None):
         for blk in range(enc["num_blocks"]):
             bp = "%s.0.layers.%d" % (lp, blk)
             assert ca["use_hetero"]
-            x = hgt_attention(sd, bp + ".0.fn", _ln(sd, bp + ".0.norm", x), com, prior, ca["heads"], ca["dim_head"]) + x
-            x = pyramid_window_attention(sd, bp + ".1.fn", _ln(sd, bp + ".1.norm", x), pw) + x
-        x = CO.feed_forward(sd, lp + ".1.fn", _ln(sd, lp + ".1.norm", x)) + x
+            x = hgt_attention(sd, bp + ".0.fn", _ln(sd, bp + ".0.norm", x), com, prior, ca["heads"], ca["dim_head"],
+                              drop=d_cav) + x
+            x = pyramid_window_attention(sd, bp + ".1.fn", _ln(sd, bp + ".1.norm", x), pw, d_win) + x
+        x = CO.feed_forward(sd, lp + ".1.fn", _ln(sd, lp + ".1.norm", x), d_ffn) + x
         if keep is not None:
             keep["layer%d" % d] = x
     return x[:, 0]
 
 
-def v2xvit_forward(sd, args, data_dict, training=False, keep=None):
+def v2xvit_forward(sd, args, data_dict, training=False, keep=None, dropouts=None):
     """models/airv2x_v2xvit.py:108-167 (task == det; eval mode: dropout = identity)."""
     buffers = {}
     mf = args["modality_fusion"]
@@ -202,7 +228,8 @@ def v2xvit_forward(sd, args, data_dict, training=False, keep=None):
     x, mask = CO.regroup(feat, record_len.tolist(), L)                              # (B,L,C,H,W)
     prior = data_dict["prior_encoding"][:, :, :, None, None].expand(-1, -1, -1, x.shape[3], x.shape[4]).to(x.dtype)
     x = torch.cat([x, prior], 2).permute(0, 1, 3, 4, 2).contiguous()
-    fused = v2x_encoder(sd, args["transformer"]["encoder"], x, mask, data_dict["spatial_correction_matrix"], keep=keep)
+    fused = v2x_encoder(sd, args["transformer"]["encoder"], x, mask, data_dict["spatial_correction_matrix"], keep=keep,
+                        dropouts=dropouts)
     fused = fused.permute(0, 3, 1, 2).contiguous()
     if keep is not None:
         keep["fused_feature"] = fused

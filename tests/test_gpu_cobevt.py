@@ -332,6 +332,86 @@ def test_train_step_matches_oracle_autograd():
         assert float((q.grad - g_step[n]).abs().max()) <= 2e-3 * float(g_step[n].abs().max()) + 1e-7, n
 
 
+def test_dropout_kernels_and_train_step_with_identical_masks(ops):
+    """nn.Dropout of the fusion network (swap_fusion_modules.py:43, base_transformer.py:32,34) as counter-based masks:
+    (i) the keep rate of the exported masks is 1 - p (binomial bounds) and sites / seeds give independent masks;
+    (ii) dropout_apply / gelu_dropout fwd / bwd equal the torch expressions under the exported mask; (iii) the CoBEVT
+    training step with the shipped drop_out = 0.1 equals torch autograd through the oracle fed the SAME masks."""
+    import json
+
+    import a2x_import
+    import w2c_common as C
+    from oracle import w2c_oracle as O
+
+    # (i) statistics
+    d = ops.Dropout(0.1, 12345)
+    n = 1 << 20
+    m0, m1 = ops.dropout_mask(n, d, 0).float(), ops.dropout_mask(n, d, 1).float()
+    m2 = ops.dropout_mask(n, ops.Dropout(0.1, 12346), 0).float()
+    sig = (0.1 * 0.9 / n) ** 0.5
+    for m in (m0, m1, m2):
+        assert abs(float(m.mean()) - 0.9) < 5 * sig
+    assert abs(float((m0 * m1).mean()) - 0.81) < 1e-3 and abs(float((m0 * m2).mean()) - 0.81) < 1e-3   # independent
+    assert abs(float((m0[:-1] * m0[1:]).mean()) - 0.81) < 1e-3                                          # no lag-1 correlation
+    # (ii) kernels == torch under the exported mask
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 6, 8, 64, generator=g).cuda()
+    r = torch.randn(4, 6, 8, 64, generator=g).cuda()
+    d3 = ops.Dropout(0.3, 777)
+    mk = ops.dropout_mask(x.numel(), d3, 5).view(x.shape).float()
+    out = ops.Act.empty(x.shape, "cuda", True)
+    ops.dropout_apply(x, d3, 5, out, residual=r)
+    assert torch.allclose(out.hi, r + x * mk / 0.7, rtol=1e-6, atol=1e-6)
+    assert torch.equal(out.b16[0], out.hi.to(torch.bfloat16))
+    ops.gelu_dropout_fwd(x, d3, 5, out)
+    assert torch.allclose(out.hi, F.gelu(x) * mk / 0.7, rtol=1e-5, atol=1e-6)
+    xx = x.clone().requires_grad_(True)
+    (F.gelu(xx) * mk / 0.7).backward(r)
+    ops.gelu_dropout_bwd(r, x, d3, 5, out)
+    assert torch.allclose(out.hi, xx.grad, rtol=1e-4, atol=1e-5)
+    # (iii) the training step with dropout ON
+    M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+    cfg, gold = CC.load_small()
+    args = json.loads(json.dumps(cfg["model_args"]))
+    p_drop = float(args["fax_fusion"]["drop_out"])
+    assert p_drop == 0.1                                   # the shipped yaml value
+    model = M.Airv2xCoBEVT(args)
+    sd = CC.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    dd = CC.golden_scene(cfg, gold)
+    H, W = gold["eval_psm"].shape[2:]
+    labels = O.make_labels(5, 1, H, W, args["anchor_number"])
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout=4242)
+    loss_off = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout="off")
+    assert abs(float(loss3.sum()) - float(loss_off.sum())) > 1e-4 * abs(float(loss_off.sum()))      # dropout does something
+    loss3b = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout=4242)
+    assert torch.equal(loss3, loss3b) or torch.allclose(loss3, loss3b, rtol=1e-6)                   # same seed, same step
+    drop = model.last_dropout
+    L, d_model, mlp = model.max_cav_num, args["fax_fusion"]["input_dim"], args["fax_fusion"]["mlp_dim"]
+    n_tok = L * H * W
+    widths = []
+    for _ in range(args["fax_fusion"]["depth"]):
+        for _ in range(2):
+            widths += [d_model, mlp, d_model]              # to_out, gelu, net.3
+    assert drop.n_sites == len(widths)
+    masks = [ops.dropout_mask(n_tok * c, drop, s).cpu() for s, c in enumerate(widths)]
+    pp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in sd.items()}
+    torch.set_num_threads(8)
+    out_o, _ = CO.cobevt_forward(pp, args, dd, training=True, dropout=CO.MaskedDropout(p_drop, masks))
+    loss = O.point_pillar_loss_multiclass(out_o, labels, args["num_class"], cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])[0]
+    loss.backward()
+    assert abs(float(loss3.sum()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
+    errs = {}
+    for nme, q in model.named_parameters():
+        if pp[nme].grad is not None:
+            errs[nme] = float((q.grad.cpu() - pp[nme].grad).norm() / (pp[nme].grad.norm() + 1e-30))
+    fusion = {k: e for k, e in errs.items() if k.startswith("fusion_net") or "head" in k}
+    assert len(fusion) > 60 and max(fusion.values()) < 2e-2, sorted(fusion.items(), key=lambda kv: -kv[1])[:5]
+    assert float(np.median(list(fusion.values()))) < 2e-3
+
+
 def test_ragged_multi_scene_batch_matches_oracle(small):
     """B = 3 ragged scenes (4, 2 and 3 agents): per-type collate, scene-major regrouping to L slots with the per-scene
     key mask, window / grid attention per scene — against the oracle on the CPU"""

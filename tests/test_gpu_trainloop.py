@@ -65,7 +65,7 @@ def test_training_reduces_the_loss_and_resume_restores_state(tmp_path):
 
 
 def test_cobevt_trainer_step():
-    """the same caller drives the transformer-fusion models (dropout off passed through to train_step)"""
+    """the same caller drives the transformer-fusion models with the shipped yaml unmodified: nn.Dropout(0.1) on"""
     import a2x_import
     import cobevt_common as CC
 
@@ -78,9 +78,9 @@ def test_cobevt_trainer_step():
     box, mask, cls = LO.synth_gt(cfg["postprocess"], 6, n_gt=8)
     batch = dict(dd, object_bbx_center=box[None], object_bbx_mask=mask[None], object_class_ids=cls[None])
     tr = TL.Trainer(model, hypes_of(cfg))
-    with pytest.raises(NotImplementedError):
-        tr.step(batch)                                       # the yaml's drop_out 0.1 needs the explicit opt-out
-    losses = [float(tr.step(batch, dropout="off").sum()) for _ in range(12)]
+    assert model.dropout == "on" and float(cfg["model_args"]["fax_fusion"]["drop_out"]) == 0.1
+    losses = [float(tr.step(batch).sum()) for _ in range(12)]
+    assert model.last_dropout is not None and model.last_dropout.n_sites == 18
     print("loss", " ".join("%.3f" % v for v in losses))
     assert all(np.isfinite(losses)) and np.mean(losses[-3:]) < 0.8 * np.mean(losses[:2])
 

@@ -234,7 +234,7 @@ def test_split_attn_and_rte_backward(ops):
 
 
 def test_train_step_matches_oracle_autograd():
-    """V2X-ViT training step (train-mode BatchNorm, dropout off): loss and every parameter gradient against torch autograd
+    """V2X-ViT training step (train-mode BatchNorm, nn.Dropout off; the dropout-on step is the next test): loss and every parameter gradient against torch autograd
     through the oracle (pinned to the real reference in eval mode). Fusion-network / head gradients are tight; encoder
     gradients pass ReLU / max gates (see tests/test_gpu_model.py) -> norm-wise bounds. `prior_feed` is unused: zero grads."""
     import json
@@ -253,9 +253,6 @@ def test_train_step_matches_oracle_autograd():
     dd = VC.golden_scene(cfg, gold)
     H, W = gold["eval_psm"].shape[2:]
     labels = O.make_labels(5, 1, H, W, args["anchor_number"])
-    if max(model._dropouts()) > 0:
-        with pytest.raises(NotImplementedError):
-            model.train_step(C.to_device(dd, "cuda"), labels)
     loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"],
                              dropout="off")
     p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
@@ -280,8 +277,6 @@ def test_train_step_matches_oracle_autograd():
     # reference-style use (tools/train.py:216-221): model(batch) -> the reference's loss (torch ops) -> loss.backward()
     g_step = {n: q.grad.clone() for n, q in model.named_parameters()}
     model.zero_grad()
-    with pytest.raises(NotImplementedError):   # yaml dropout > 0 needs the explicit opt-out
-        model(C.to_device(dd, "cuda"))
     model.dropout = "off"
     out2 = model(C.to_device(dd, "cuda"))
     cpu_out = {k: out2[k].cpu() for k in ("psm", "rm", "obj")}
@@ -334,3 +329,60 @@ def test_ragged_multi_scene_batch_matches_oracle(small):
     for k in ("psm", "rm", "obj"):
         assert float((out[k].cpu() - ora[k]).abs().max()) < TOL, k
     assert out["comm_rate"] == ora["comm_rate"]
+
+
+def test_train_step_with_dropout_matches_oracle_under_identical_masks():
+    """The shipped yaml trains with nn.Dropout(0.3) in HGTCavAttention (hmsa.py:155), the window branches (mswin.py:47)
+    and the feed forward (base_transformer.py:22,24). The kernels draw counter-based masks; exported (a2x_dropout_mask) and
+    fed to the oracle, loss and gradients must agree like in the dropout-off test. Valid agents only (max_cav = #agents),
+    so the mask layout [N, H, W, C] is the oracle's (1, L, H, W, C)."""
+    import json
+
+    import a2x_import
+    import w2c_common as C
+    from oracle import w2c_oracle as O
+
+    M = a2x_import.pkg("opencood.models.airv2x_v2xvit")
+    ops = a2x_import.pkg("ops")
+    cfg, gold = VC.load_small()
+    args = json.loads(json.dumps(cfg["model_args"]))
+    model = M.Airv2xV2XVit(args)
+    ps = tuple(model._dropouts())
+    assert ps == (0.3, 0.3, 0.3)                       # the shipped yaml values
+    sd = VC.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    dd = VC.golden_scene(cfg, gold)
+    H, W = gold["eval_psm"].shape[2:]
+    labels = O.make_labels(5, 1, H, W, args["anchor_number"])
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout=991)
+    loss_off = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout="off")
+    assert abs(float(loss3.sum()) - float(loss_off.sum())) > 1e-4 * abs(float(loss_off.sum()))
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout=991)
+    dc, dw, df = model.last_dropout
+    n_agents = len([a for a in gold["agents"]])
+    enc = args["transformer"]["encoder"]
+    Cc, mlp, depth = enc["cav_att_config"]["dim"], enc["feed_forward"]["mlp_dim"], enc["depth"]
+    n_tok = n_agents * H * W
+    assert dc.n_sites == depth and dw.n_sites == 1000 + 3 * depth and df.n_sites == 2000 + 2 * depth
+    masks = {"cav": [ops.dropout_mask(n_tok * Cc, dc, s).cpu() for s in range(depth)],
+             "win": [ops.dropout_mask(n_tok * Cc, dw, 1000 + s).cpu() for s in range(3 * depth)],
+             "ffn": [ops.dropout_mask(n_tok * (mlp if s % 2 == 0 else Cc), df, 2000 + s).cpu() for s in range(2 * depth)]}
+    a5 = json.loads(json.dumps(args))
+    agents = [str(a) for a in gold["agents"]]
+    a5["max_cav"] = {t: sum(1 for a in agents if a == t) for t in O.AGENT_TYPES}
+    dd5 = dict(dd)
+    dd5["prior_encoding"], dd5["spatial_correction_matrix"] = dd["prior_encoding"][:, :n_agents], dd["spatial_correction_matrix"][:, :n_agents]
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    torch.set_num_threads(8)
+    out, _ = VO.v2xvit_forward(p, a5, dd5, training=True, dropouts=VO.MaskedDropouts(ps, masks))
+    loss = O.point_pillar_loss_multiclass(out, labels, args["num_class"], cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])[0]
+    loss.backward()
+    assert abs(float(loss3.sum()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
+    errs = {}
+    for n, q in model.named_parameters():
+        if p[n].grad is not None:
+            errs[n] = float((q.grad.cpu() - p[n].grad).norm() / (p[n].grad.norm() + 1e-30))
+    fusion = {n: e for n, e in errs.items() if n.startswith("fusion_net") or "head" in n}
+    assert len(fusion) > 100 and max(fusion.values()) < 2e-2, sorted(fusion.items(), key=lambda kv: -kv[1])[:5]
+    assert float(np.median(list(fusion.values()))) < 2e-3
