@@ -11,3 +11,29 @@ def pkg(sub=None):
     if _ROOT not in sys.path:
         sys.path.insert(0, _ROOT)
     return importlib.import_module(PKG_NAME + ("." + sub if sub else ""))
+
+
+MODEL_NAMES = ("airv2x_where2com", "airv2x_cobevt", "airv2x_v2xvit", "point_pillar_where2comm", "point_pillar_cobevt",
+               "point_pillar_v2xvit")
+
+
+def install(names=MODEL_NAMES):
+    """Register the B200 drop-in modules under the reference's registry paths, so that the UNMODIFIED
+    `opencood.tools.train_utils.create_model(hypes)` (train_utils.py:288-325: `importlib.import_module("opencood.models." +
+    core_method)` + class-name match) returns them. Also publishes the package under the importable alias
+    `airv2x_perception_b200` (the directory name has a hyphen). Returns the previous sys.modules entries for uninstall()."""
+    prev = {}
+    for n in names:
+        key = "opencood.models." + n
+        prev[key] = sys.modules.get(key)
+        sys.modules[key] = pkg("opencood.models." + n)
+    sys.modules.setdefault("airv2x_perception_b200", pkg())
+    return prev
+
+
+def uninstall(prev):
+    for key, mod in prev.items():
+        if mod is None:
+            sys.modules.pop(key, None)
+        else:
+            sys.modules[key] = mod

@@ -71,22 +71,20 @@ class _SwapFusionEncoderParams(nn.Module):
                                       nn.Linear(fa["input_dim"], fa["input_dim"]), nn.Identity())
 
 
-class _FusionStep(torch.autograd.Function):
-    """Autograd boundary of the transformer-fusion models: inputs are the trainable parameters, the output is the NHWC
-    head-logit tensor; backward runs the engine's backward_train and hands one gradient per parameter to autograd."""
+def fusion_step(model, run_forward, names, params, out_shape):
+    """Autograd boundary of the transformer-fusion models = the torch.library ops of torch_ops.py: inputs are the
+    trainable parameters, the output is the NHWC head-logit tensor; the backward op runs the engine's backward_train and
+    hands one gradient per parameter to autograd."""
+    from ... import torch_ops
 
-    @staticmethod
-    def forward(ctx, model, run_forward, names, *params):
-        ctx.model, ctx.names = model, names
-        return run_forward()
-
-    @staticmethod
-    def backward(ctx, dheads):
-        model = ctx.model
+    def run_backward(dheads):
         P = model._param_dict()
-        grads = {n: torch.zeros_like(P[n]) for n in ctx.names}
-        model.engine.backward_train(P, dheads.contiguous(), grads)
-        return (None, None, None) + tuple(grads[n] for n in ctx.names)
+        grads = {n: torch.zeros_like(P[n]) for n in names}
+        model.engine.backward_train(P, dheads, grads)
+        return [grads[n] for n in names]
+
+    key = torch_ops.bind(model, run_forward, run_backward)
+    return torch.ops.a2x.fused_forward(key, params, out_shape)
 
 
 class Airv2xCoBEVT(Airv2xWhere2com):
@@ -160,7 +158,8 @@ class Airv2xCoBEVT(Airv2xWhere2com):
             params = [p for n, p in self.named_parameters() if p.requires_grad]
             eng = self.engine
             drop = self._dropout_state(None)
-            heads = _FusionStep.apply(self, lambda: eng.forward_train(self._param_dict(), lidar, layout, drop), names, *params)
+            heads = fusion_step(self, lambda: eng.forward_train(self._param_dict(), lidar, layout, drop), names, params,
+                                self._heads_shape(layout))
         else:
             heads, _ = self.engine.forward(self._param_dict(), lidar, layout, self.training)
         A, K = self.args["anchor_number"], self.args["num_class"]

@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from ...v2xvit_engine import V2XViTEngine
 from ...w2c_engine import AGENT_TYPES, TYPE_PREFIX
-from .airv2x_cobevt import _FusionStep
+from .airv2x_cobevt import fusion_step
 from .airv2x_where2com import Airv2xWhere2com, _backbone_params, _PillarVFEParams, _shrink_params
 
 
@@ -175,8 +175,8 @@ class Airv2xV2XVit(Airv2xWhere2com):
             names = [n for n, p in self.named_parameters() if p.requires_grad]
             params = [p for n, p in self.named_parameters() if p.requires_grad]
             drops = self._dropout_state(None)
-            heads = _FusionStep.apply(self, lambda: eng.forward_train(self._param_dict(), lidar, layout, prior, scm, drops),
-                                      names, *params)
+            heads = fusion_step(self, lambda: eng.forward_train(self._param_dict(), lidar, layout, prior, scm, drops),
+                                names, params, self._heads_shape(layout))
             aux = eng.last_aux
         else:
             heads, aux = eng.forward(self._param_dict(), lidar, layout, self.training, prior=prior, scm=scm)

@@ -78,28 +78,6 @@ def _comm_params(cfg):
     return fusion
 
 
-class _Step(torch.autograd.Function):
-    """Autograd boundary: inputs are all trainable parameters, outputs are the NHWC head logits."""
-
-    @staticmethod
-    def forward(ctx, model, lidar, layout, k_list, names, *params):
-        P = model._param_dict()
-        heads, aux = model.engine.forward(P, lidar, layout, model.training, k_list)
-        ctx.model = model
-        ctx.names = names
-        ctx.aux = aux
-        model._last_aux = aux
-        return heads
-
-    @staticmethod
-    def backward(ctx, dheads):
-        model = ctx.model
-        P = model._param_dict()
-        grads = {n: torch.zeros_like(P[n]) for n in ctx.names}
-        model.engine.backward(P, dheads.contiguous(), grads)
-        return (None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
-
-
 class Airv2xWhere2com(nn.Module):
     def __init__(self, args, precision="split3"):
         super().__init__()
@@ -269,10 +247,30 @@ class Airv2xWhere2com(nn.Module):
         names = [n for n, p in self.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
         params = [p for n, p in self.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
         if self.training and torch.is_grad_enabled():
-            heads = _Step.apply(self, lidar, layout, k_list, names, *params)
+            # autograd boundary = the torch.library ops a2x::fused_forward / a2x::fused_backward (torch_ops.py): inputs
+            # are the trainable parameters, the output is the NHWC head-logit tensor
+            from ... import torch_ops
+            eng = self.engine
+
+            def run_forward():
+                h, self._last_aux = eng.forward(self._param_dict(), lidar, layout, True, k_list)
+                return h
+
+            def run_backward(dheads):
+                P = self._param_dict()
+                grads = {n: torch.zeros_like(P[n]) for n in names}
+                eng.backward(P, dheads, grads)
+                return [grads[n] for n in names]
+
+            key = torch_ops.bind(self, run_forward, run_backward)
+            heads = torch.ops.a2x.fused_forward(key, params, self._heads_shape(layout))
         else:
             heads, self._last_aux = self.engine.forward(self._param_dict(), lidar, layout, self.training, k_list)
         return self._output_dict(heads, layout)
+
+    def _heads_shape(self, layout):
+        """[B, H/2, W/2, HEAD_PAD] of the fused head-logit tensor (what the ops' fake implementation returns)"""
+        return [len(layout["record_len"]), layout["ny"] // 2, layout["nx"] // 2, HEAD_PAD]
 
     # ------------------------------------------------------------------ fused training step (public fast path)
     def _grad_buffers(self):

@@ -6,7 +6,9 @@
  * performs no hidden allocation (callers pass outputs and workspaces) and never synchronises the device.
  * Activations are fp32 NHWC ("pixel-major": [n][h][w][c], c contiguous) with an explicit pixel stride
  * (`*_cs`, elements) so that channel slices of a wider buffer (the 384-channel concat) can be read/written in
- * place. Dense contractions run as tcgen05.mma.kind::tf32 (fp32 storage, fp32 accumulate).
+ * place. Dense contractions run as tcgen05.mma.kind::f16 on bf16 split operands (v = h + l; h*h + l*h + h*l, three
+ * MMAs into one fp32 TMEM accumulator: fp32-equivalent to ~1e-4 on the logits); a2x_output / a2x_operand carry the two
+ * bf16 planes next to the fp32 value.
  *
  * Each section cites the reference interface it replaces (paths relative to the reference repo root).
  */

@@ -195,9 +195,13 @@ def test_eval_matches_reference_golden(small):
     for k in ("psm", "rm", "obj"):
         assert out[k].shape == gold["eval_" + k].shape
         assert np.abs(out[k].cpu().numpy() - gold["eval_" + k]).max() < TOL, k
+    # train mode with grad enabled is the autograd-bridged path (torch.library ops; nn.Dropout(0.1) on, like the reference)
     model.train()
-    with pytest.raises(NotImplementedError):
-        model(C.to_device(dd, "cuda"))
+    tr = model(C.to_device(dd, "cuda"))
+    assert tr["psm"].requires_grad and tr["psm"].shape == out["psm"].shape
+    tr["psm"].sum().backward()
+    assert all(p.grad is not None for p in model.parameters() if p.requires_grad)
+    model.zero_grad()
     model.eval()
 
 

@@ -341,3 +341,39 @@ def test_absent_agent_type_gets_zero_gradient(small):
     model.train_step(C.to_device(dd2, "cuda"), labels, 1.0, 2.0)
     assert all(float(p.grad.abs().max()) == 0.0 for p in drone)
     assert all(float(p.grad.abs().max()) > 0 for n, p in model.named_parameters() if n.startswith("rsu_models"))
+
+
+def test_torch_library_ops_schema_fake_autograd_and_autocast(small):
+    """§8b-ii: the autograd boundary is a pair of torch.library ops (a2x::fused_forward / a2x::fused_backward): the schema,
+    the fake (Meta) implementation and the autograd registration pass torch.library.opcheck; the op traces under
+    FakeTensorMode without touching the GPU; an autocast region leaves the fp32 contract intact."""
+    import a2x_import
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    TO = a2x_import.pkg("torch_ops")
+    cfg, gold, model, sd, dd = small
+    model.load_state_dict(sd)
+    model.train()
+    random.seed(3)
+    out = model(C.to_device(dd, "cuda"))                     # binds the per-call closures of this model
+    assert out["psm"].requires_grad and out["psm"].grad_fn is not None
+    names = [n for n, p in model.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
+    params = [p for n, p in model.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
+    key = id(model)
+    shape = [1] + list(out["psm"].shape[2:]) + [64]
+    random.seed(3)
+    torch.library.opcheck(torch.ops.a2x.fused_forward, (key, params, shape),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    with FakeTensorMode(allow_non_fake_inputs=True):
+        fake = torch.ops.a2x.fused_forward(key, [torch.empty_like(p) for p in params], shape)
+        assert tuple(fake.shape) == tuple(shape) and fake.dtype == torch.float32
+        g = torch.ops.a2x.fused_backward(key, fake, [torch.empty_like(p) for p in params])
+        assert [tuple(t.shape) for t in g] == [tuple(p.shape) for p in params]
+    random.seed(3)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out2 = model(C.to_device(dd, "cuda"))
+    assert out2["psm"].dtype == torch.float32 and torch.equal(out2["psm"], out["psm"])
+    out2["psm"].sum().backward()
+    assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in params)
+    with pytest.raises(Exception):                            # no CPU implementation is registered
+        torch.ops.a2x.fused_forward(key, [p.detach().cpu() for p in params], shape)
