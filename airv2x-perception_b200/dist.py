@@ -5,24 +5,84 @@ import torch.distributed as dist
 
 
 class GradAverager:
-    """Flat-buffer all-reduce of parameter gradients (one collective per step instead of one per tensor)."""
+    """Gradient average for scene-parallel training (the reference's DDP, tools/train.py:161-163) without staging copies:
+    every `p.grad` is a VIEW of one flat fp32 buffer (the fused step overwrites the views in place), so the exchange is one
+    NCCL all-reduce (op = AVG) per bucket on the buffer itself.
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+    Two buckets, ordered by when the fused backward finalises them (see W2CEngine.backward): bucket 0 = everything except
+    the level-0 block and the PillarVFE encoders (97 % of the bytes) is complete while the level-0 backward still runs, so
+    `start(0)` launches its all-reduce asynchronously there (ProcessGroupNCCL's own stream; inside a CUDA-graph capture it
+    becomes a forked branch of the graph) and `finish()` reduces the small rest and joins. `late(name)` decides the split;
+    with no predicate there is one bucket and `__call__()` = start + finish after the step."""
+
+    def __init__(self, params, late=None, names=None):
+        params = list(params)
+        names = list(names) if names is not None else [None] * len(params)
+        pairs = [(n, p) for n, p in zip(names, params) if p.requires_grad]
+        early = [(n, p) for n, p in pairs if late is None or not late(n)]
+        tail = [(n, p) for n, p in pairs if late is not None and late(n)]
+        self.params = [p for _, p in early + tail]
         self.flat = None
+        self.split = sum(p.numel() for _, p in early)
+        self._work = None
+        if self.params:
+            self._attach()
+
+    def _attach(self):
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, device=dev, dtype=dt)
+        pos = 0
+        for p in self.params:
+            view = self.flat[pos:pos + p.numel()].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            pos += p.numel()
+
+    @staticmethod
+    def active():
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    @property
+    def nbytes(self):
+        return 0 if self.flat is None else self.flat.numel() * self.flat.element_size()
+
+    def _check_views(self):
+        """an optimizer's zero_grad(set_to_none=True) drops the views: re-attach (their content is rewritten by the step)"""
+        if self.flat is None or any(p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or
+                                    p.grad.data_ptr() >= self.flat.data_ptr() + self.nbytes for p in self.params[:1] + self.params[-1:]):
+            self._attach()
+
+    def _reduce(self, t, async_op):
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        w = dist.all_reduce(t, async_op=False)      # gloo (CPU tests) has no AVG
+        t.div_(dist.get_world_size())
+        return w
+
+    def start(self, bucket=0):
+        """launch the all-reduce of the early bucket (asynchronous w.r.t. the current stream)"""
+        if not self.active() or self.split == 0:
+            return
+        self._work = self._reduce(self.flat[:self.split], True)
+
+    def finish(self):
+        if not self.active():
+            return
+        if self.split < self.flat.numel():
+            self._reduce(self.flat[self.split:], False)
+        if self._work is not None:
+            self._work.wait()          # the current stream waits for the early bucket (no host block)
+        self._work = None
 
     def __call__(self):
-        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        if not self.active():
             return
-        grads = [p.grad for p in self.params if p.grad is not None]
-        sizes = [g.numel() for g in grads]
-        if self.flat is None or self.flat.numel() != sum(sizes):
-            self.flat = torch.empty(sum(sizes), device=grads[0].device, dtype=grads[0].dtype)
-        views = list(self.flat.split(sizes))
-        torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
-        dist.all_reduce(self.flat)
-        self.flat.div_(dist.get_world_size())
-        torch._foreach_copy_([g.view(-1) for g in grads], views)
+        self._check_views()
+        if self._work is None:
+            self.start()
+        self.finish()
 
 
 # ---------------------------------------------------------------------------------------------------------------------

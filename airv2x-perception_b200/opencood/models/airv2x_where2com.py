@@ -284,6 +284,18 @@ class Airv2xWhere2com(nn.Module):
             g[n] = p.grad
         return g
 
+    def attach_grad_sync(self):
+        """Scene-parallel training (one process per GPU, the reference wraps the model in DDP: tools/train.py:161-163):
+        back every p.grad by one flat buffer and average it over the ranks INSIDE the fused step, the bulk of it overlapped
+        with the level-0 backward (dist.GradAverager). Call once, before the first step (it is part of the captured CUDA
+        graph); a no-op when torch.distributed is not initialised with world_size > 1."""
+        from ... import dist as D
+        pairs = [(n, p) for n, p in self.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
+        late = lambda n: n.startswith(("backbone.blocks.0.", "veh_models.", "rsu_models.", "drone_models."))
+        self.grad_sync = D.GradAverager([p for _, p in pairs], late=late, names=[n for n, _ in pairs])
+        self.__dict__.pop("_graphs", None)       # graphs captured before hold the old gradient pointers
+        return self.grad_sync
+
     def prepare_labels(self, label_dict, device):
         """label tensors of the reference's collate (fp64 targets / pos_equal_one, int64 class_ids:
         data_utils/post_processor/voxel_postprocessor.py:392-430) -> device fp32 / int32, contiguous."""
@@ -304,7 +316,7 @@ class Airv2xWhere2com(nn.Module):
         P = self._param_dict()
         heads, self._last_aux = self.engine.forward(P, lidar, layout, True, k_list)
         loss3, dheads = self.engine.loss(heads, labels, cls_weight, reg_coe)
-        self.engine.backward(P, dheads, self._grad_buffers())
+        self.engine.backward(P, dheads, self._grad_buffers(), sync=self.__dict__.get("grad_sync"))
         self._last_layout = layout
         return loss3
 

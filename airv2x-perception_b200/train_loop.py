@@ -108,7 +108,13 @@ class Trainer:
         self.epoch = 0
         # scene-parallel training (one process per GPU, tools/train.py:161-163 wraps the model in DDP): one flat all-reduce
         # of the gradients per step; a no-op unless torch.distributed is initialised with world_size > 1
-        self.average_grads = GradAverager(model.parameters())
+        # (GradAverager: p.grad become views of one flat buffer); models with attach_grad_sync() reduce INSIDE their fused
+        # step, overlapped with the tail of the backward
+        if hasattr(model, "attach_grad_sync") and type(model).__name__ == "Airv2xWhere2com":
+            model.attach_grad_sync()
+            self.average_grads = lambda: None
+        else:
+            self.average_grads = GradAverager(model.parameters())
 
     def labels(self, batch):
         if "label_dict" in batch:

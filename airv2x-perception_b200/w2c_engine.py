@@ -592,8 +592,11 @@ class W2CEngine:
         if self.use_side_stream and self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
 
-    def backward(self, P, dheads, grads):
-        """dheads: [B,h,w,32] gradient w.r.t. the head logits. grads: dict name -> fp32 tensor (written)."""
+    def backward(self, P, dheads, grads, sync=None):
+        """dheads: [B,h,w,32] gradient w.r.t. the head logits. grads: dict name -> fp32 tensor (written).
+        sync: dist.GradAverager whose flat buffer backs `grads` (scene-parallel training): the all-reduce of every gradient
+        except the level-0 block's and the PillarVFE's starts as soon as those are final and runs beside the level-0
+        backward; the rest is reduced at the end."""
         S = self.saved
         assert S is not None, "backward() needs a train-mode forward first"
         W, rec = S["W"], S["rec"]
@@ -718,6 +721,15 @@ class W2CEngine:
         nlev = len(levels)
         for i in range(nlev - 1, 0, -1):
             block_bwd("B", i, d_levels[i], d_levels[i - 1], True)
+        n_early = 0
+        if sync is not None and sync.active() and self.use_side_stream:
+            # everything but blocks.0 / PillarVFE is final once the re-layout of the weight gradients issued so far has run:
+            # launch their all-reduce from the side stream (ordered after those GEMMs and, through the fork, after the BN /
+            # bias gradients on the main stream), beside the level-0 backward
+            with self._on_side():
+                ops.unpack_wgrads_batched(self._job_table("unpack.early", unpack))
+                sync.start()
+            n_early = len(unpack)
         # level 0: d(x0m) -> mask -> d(x0) ; block 0 ran in pass "A" (shared)
         d_x0 = self._buf("bwd.d_x0", S["x0"].shape)
         ops.relu_bwd(d_levels[0], None, Act(d_x0), mask=S["mask"])
@@ -746,7 +758,11 @@ class W2CEngine:
                         grads[pre + ".linear.weight"], grads[pre + ".norm.weight"], grads[pre + ".norm.bias"],
                         seg=r["seg"])
         with self._on_side():  # ordered after every weight-gradient GEMM (and, through the fork, the main stream so far)
-            ops.unpack_wgrads_batched(self._job_table("unpack", unpack))
+            ops.unpack_wgrads_batched(self._job_table("unpack", unpack[n_early:]))
         if self.use_side_stream and self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
+        if sync is not None and sync.active():
+            if n_early == 0:
+                sync.start()
+            sync.finish()
         return grads

@@ -2,11 +2,11 @@
 """bench.py — scenes/sec (forward + backward) of the collaborative-perception hot path on B200.
 
     python bench.py --gpus N --steps K --warmup W            # headline: BASELINE.json configs[1] (= --config 2)
-    python bench.py --config {1,2,3,4,5} ...                  # the other BASELINE configs, same JSON contract
+    python bench.py --config {2,3,4,5} ...                    # the other BASELINE configs, same JSON contract
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm (oracle port) on the host CPUs
 
   config 2 (default)  airv2x_intermediate_where2com.yaml, 5 agents (2 veh, 2 rsu, 1 drone) x 60k points, 200 x 704 BEV
-  config 1            point_pillar_where2comm (legacy registry name), 2 agents x 8k points, 128 x 128 BEV
+  (config 1, point_pillar_where2comm at 2 agents x 8k points / 128 x 128, is the CPU-runnable parity case: tests/, not a bench line)
   config 3            airv2x_intermediate_v2xvit.yaml, 5 agents x 60k points
   config 4            airv2x_intermediate_cobevt.yaml (FuseBEVT), 5 agents x 60k points on one GPU; under torchrun the
                       agent-per-GPU mode (N agents = N ranks, one exchange of the BEV maps) is timed as well
@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="split3", choices=["split3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -403,6 +403,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs 3/4/5, sustained and agent-parallel blocks")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--post-grad-sync", action="store_true", help="N > 1: all-reduce the gradients after the step (no overlap)")
     args = ap.parse_args()
     spec = WORKLOADS[args.config]
     cfg = load_config(spec["cfg"])
@@ -451,8 +452,18 @@ def main():
         model.eval()
     else:
         model.train()
-    # data-parallel over scenes (the reference's DDP, tools/train.py:161-163): average parameter gradients
-    allreduce_grads = a2x_import.pkg("dist").GradAverager(model.parameters())
+    # data-parallel over scenes (the reference's DDP, tools/train.py:161-163): average parameter gradients. Where2comm
+    # reduces INSIDE its fused step (two buckets, the big one overlapped with the level-0 backward, all of it part of the
+    # captured CUDA graph); the transformer models reduce one flat buffer after their step.
+    grad_sync = "none (1 GPU)"
+    allreduce_grads = lambda: None
+    if world > 1 and not W.legacy:
+        if args.config in (2, 5) and not args.post_grad_sync:
+            model.attach_grad_sync()
+            grad_sync = "in-step: 2 buckets on one flat gradient buffer, NCCL AVG, bucket 0 overlapped with the level-0 backward"
+        else:
+            allreduce_grads = a2x_import.pkg("dist").GradAverager(p for p in model.parameters() if p.requires_grad)
+            grad_sync = "after the step: one NCCL AVG all-reduce of the flat gradient buffer"
 
     if W.legacy:
         def step(dd, lab):
@@ -489,6 +500,17 @@ def main():
             ms = float(t.item())
         return ms, last
 
+    try:
+        step(dd_dev, lab_dev)
+    except Exception as ex:   # e.g. a driver / NCCL combination that cannot capture collectives: reduce after the step
+        if world > 1 and model.__dict__.get("grad_sync") is not None:
+            sys.stderr.write("in-step gradient sync failed (%r): falling back to the post-step all-reduce\n" % (ex,))
+            model.grad_sync = None
+            model.__dict__.pop("_graphs", None)
+            allreduce_grads = a2x_import.pkg("dist").GradAverager(p for p in model.parameters() if p.requires_grad)
+            grad_sync = "after the step (in-step capture failed: %s)" % repr(ex)[:120]
+        else:
+            raise
     for _ in range(max(args.warmup, 3)):
         step(dd_dev, lab_dev)
     sync_all()
@@ -544,7 +566,8 @@ def main():
                            "step i, loss D2H read one step late" if graphed else
                            ("model(host dicts) [eval forward: the legacy models' training step is reported by config 2-5]"
                             if W.legacy else "model.train_step(host dicts)")},
-            "gpu_launches": int(launches), "loss": loss_val, "label_positives": W.n_pos, "clocks": clk.summary()}
+            "gpu_launches": int(launches), "loss": loss_val, "label_positives": W.n_pos, "grad_sync": grad_sync,
+            "clocks": clk.summary()}
     if args.config == 2 and not args.no_extra:
         # sustained: the same graph-replayed step for >= 3 s, SM clock / throttle reasons sampled over the whole loop
         n_sus = max(50, int(3200.0 / ms))

@@ -22,8 +22,18 @@ def _worker(rank, world, port, q):
     params[0].grad = torch.full((5, 3), float(rank + 1))
     params[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
     avg = D.GradAverager(params)
+    assert params[0].grad.data_ptr() == avg.flat.data_ptr()          # p.grad are views of ONE flat buffer: no staging copies
     avg()
     avg()  # idempotent on already-averaged gradients
+    # two buckets (the in-step protocol of W2CEngine.backward): start() the early one, finish() reduces the rest and joins
+    q2 = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2))]
+    b = D.GradAverager(q2, late=lambda n: n == "b", names=["a", "b", "c"])
+    assert b.split == 6 and b.flat.numel() == 9 and q2[1].grad.data_ptr() == b.flat[6:].data_ptr()   # late params at the tail
+    for i, p in enumerate(q2):
+        p.grad.fill_(float((rank + 1) * (i + 1)))
+    b.start()
+    b.finish()
+    assert all(torch.allclose(p.grad, torch.full_like(p.grad, 1.5 * (i + 1))) for i, p in enumerate(q2))
     q.put((rank, params[0].grad.clone(), params[1].grad.clone()))
     dist.destroy_process_group()
 

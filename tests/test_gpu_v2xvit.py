@@ -355,10 +355,11 @@ def test_train_step_with_dropout_matches_oracle_under_identical_masks():
     dd = VC.golden_scene(cfg, gold)
     H, W = gold["eval_psm"].shape[2:]
     labels = O.make_labels(5, 1, H, W, args["anchor_number"])
-    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout=991)
-    loss_off = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout="off")
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout=991).clone()
+    loss_off = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout="off").clone()
     assert abs(float(loss3.sum()) - float(loss_off.sum())) > 1e-4 * abs(float(loss_off.sum()))
-    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout=991)
+    model.load_state_dict(sd)
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"], dropout=991).clone()
     dc, dw, df = model.last_dropout
     n_agents = len([a for a in gold["agents"]])
     enc = args["transformer"]["encoder"]
