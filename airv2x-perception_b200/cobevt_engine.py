@@ -105,30 +105,30 @@ class CoBEVTEngine(W2CEngine):
                 w = P[name]
                 co, ci = w.shape[0], w.shape[1]
                 W[name] = self._packed(name, (9, co, ci), (9, ci, co))
-                jobs.append(ops.conv_pack_job(w, W[name]))
+                jobs.append(ops.conv_pack_job(w, W[name], f32=not self.split))
             name = "backbone.deblocks.%d.0.weight" % i
             w = P[name]
             s = self.up_strides[i]
             ci, co = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (1, s * s * co, ci), (s * s, ci, co))
-            jobs.append(ops.deconv_pack_job(w, W[name]))
+            jobs.append(ops.deconv_pack_job(w, W[name], f32=not self.split))
         for idx, k in ((0, self.shrink_k0), (2, 3)):
             name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
             w = P[name]
             co, ci = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (k * k, co, ci), (k * k, ci, co))
-            jobs.append(ops.conv_pack_job(w, W[name]))
+            jobs.append(ops.conv_pack_job(w, W[name], f32=not self.split))
         if self.compression:
             for name in self._compressor_convs():
                 w = P[name + ".weight"]
                 co, ci = w.shape[0], w.shape[1]
                 W[name] = self._packed(name, (9, co, ci), (9, ci, co))
-                jobs.append(ops.conv_pack_job(w, W[name]))
+                jobs.append(ops.conv_pack_job(w, W[name], f32=not self.split))
         for name in self._linear_names():  # nn.Linear [out, in] == 1x1 conv OIHW [out, in, 1, 1]
             w = P[name]
             co, ci = w.shape
             W[name] = self._packed(name, (1, co, ci), (1, ci, co))
-            jobs.append(ops.conv_pack_job(w.view(co, ci, 1, 1), W[name]))
+            jobs.append(ops.conv_pack_job(w.view(co, ci, 1, 1), W[name], f32=not self.split))
         fresh = ("packed", "heads") not in self.bufs
         hp = self._packed("heads", (1, HEAD_PAD, self.c_shrink), (1, self.c_shrink, HEAD_PAD))
         hb = self._buf("heads.b", (HEAD_PAD,))
@@ -136,7 +136,7 @@ class CoBEVTEngine(W2CEngine):
             for t in (hp.f32, hp.f16, hp.d32, hp.d16, hb):
                 t.zero_()
         for name, row0 in self._head_rows():
-            jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0))
+            jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0, f32=not self.split))
             jobs.append(ops.copy_pack_job(P[name + ".bias"], hb, row0))
         W["heads"] = hp
         W["heads.bias"] = hb

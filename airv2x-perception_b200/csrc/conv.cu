@@ -489,38 +489,58 @@ __global__ void unpack_deconv_dw_kernel(const float* __restrict__ dwp, int cin, 
 // The per-layer pack / unpack kernels above move a few hundred KB each: launch latency, not bandwidth, is what they
 // cost inside the step. These two kernels walk a device-resident job table instead (<= 128 jobs, staged in smem).
 __global__ void __launch_bounds__(256) pack_batched_kernel(const a2x_pack_job* __restrict__ jobs, int njobs) {
+    // Every weight is written in TWO layouts (forward operand [tap][co][ci], data-gradient operand [tap][ci][co]); each
+    // layout gets its own sweep with the DESTINATION index fastest over the threads, so all stores coalesce (the strided
+    // reads of the 29 MB of parameters are served by L2). Null f32 / d32 pointers (split mode: only the bf16 planes feed
+    // the GEMMs) skip those planes.
     __shared__ a2x_pack_job sj[128];
     for (int i = threadIdx.x; i < njobs; i += blockDim.x) sj[i] = jobs[i];
     __syncthreads();
     const long long total = sj[njobs - 1].elem_begin + sj[njobs - 1].elems;
-    int j = 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        while (i >= sj[j].elem_begin + sj[j].elems) ++j;  // i grows monotonically per thread
-        const a2x_pack_job& J = sj[j];
-        const long long e = i - J.elem_begin;
-        if (J.kind == 2) {  // plain vector copy (fused head bias)
-            J.f32[J.row0 + e] = J.src[e];
-            continue;
-        }
-        if (J.kind == 0) {  // conv OIHW [rows][cin][kk] -> [tap][row0 + co][ci] and [tap][ci][row0 + co]
-            const int cin = J.b, rows = J.a, kk = J.kk;
-            const int ci = (int)(e % cin);
-            const int co = (int)((e / cin) % rows);
-            const int tap = (int)(e / ((long long)cin * rows));
-            const float w = J.src[((long long)co * cin + ci) * kk + tap];
-            const long long plane = (long long)kk * J.cout_pad * cin;
-            put_w(J.f32, (__nv_bfloat16*)J.f16, plane, ((long long)tap * J.cout_pad + J.row0 + co) * cin + ci, w);
-            put_w(J.d32, (__nv_bfloat16*)J.d16, plane, ((long long)tap * cin + ci) * J.cout_pad + J.row0 + co, w);
-        } else {  // deconv [ci][co][i][j] -> [(ij, co)][ci] and [ij][ci][co]
-            const int cin = J.a, cout = J.b, ss = J.kk;
-            const int ij = (int)(e % ss);
-            const int co = (int)((e / ss) % cout);
-            const int ci = (int)(e / ((long long)ss * cout));
-            const float w = J.src[e];
-            const long long plane = (long long)cin * cout * ss;
-            put_w(J.f32, (__nv_bfloat16*)J.f16, plane, ((long long)ij * cout + co) * cin + ci, w);
-            put_w(J.d32, (__nv_bfloat16*)J.d16, plane, ((long long)ij * cin + ci) * cout + co, w);
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        int j = 0;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            while (i >= sj[j].elem_begin + sj[j].elems) ++j;  // i grows monotonically per thread
+            const a2x_pack_job& J = sj[j];
+            const long long e = i - J.elem_begin;
+            if (J.kind == 2) {  // plain vector copy (fused head bias)
+                if (sweep == 0) J.f32[J.row0 + e] = J.src[e];
+                continue;
+            }
+            if (J.kind == 0) {  // conv OIHW [rows][cin][kk] -> [tap][row0 + co][ci] and [tap][ci][row0 + co]
+                const int cin = J.b, rows = J.a, kk = J.kk;
+                const long long plane = (long long)kk * J.cout_pad * cin;
+                if (sweep == 0) {
+                    const int ci = (int)(e % cin);
+                    const int co = (int)((e / cin) % rows);
+                    const int tap = (int)(e / ((long long)cin * rows));
+                    const float w = J.src[((long long)co * cin + ci) * kk + tap];
+                    put_w(J.f32, (__nv_bfloat16*)J.f16, plane, ((long long)tap * J.cout_pad + J.row0 + co) * cin + ci, w);
+                } else {
+                    const int co = (int)(e % rows);
+                    const int ci = (int)((e / rows) % cin);
+                    const int tap = (int)(e / ((long long)cin * rows));
+                    const float w = J.src[((long long)co * cin + ci) * kk + tap];
+                    put_w(J.d32, (__nv_bfloat16*)J.d16, plane, ((long long)tap * cin + ci) * J.cout_pad + J.row0 + co, w);
+                }
+            } else {  // deconv [ci][co][i][j] -> [(ij, co)][ci] and [ij][ci][co]
+                const int cin = J.a, cout = J.b, ss = J.kk;
+                const long long plane = (long long)cin * cout * ss;
+                if (sweep == 0) {
+                    const int ci = (int)(e % cin);
+                    const int co = (int)((e / cin) % cout);
+                    const int ij = (int)(e / ((long long)cin * cout));
+                    const float w = J.src[((long long)ci * cout + co) * ss + ij];
+                    put_w(J.f32, (__nv_bfloat16*)J.f16, plane, ((long long)ij * cout + co) * cin + ci, w);
+                } else {
+                    const int co = (int)(e % cout);
+                    const int ci = (int)((e / cout) % cin);
+                    const int ij = (int)(e / ((long long)cin * cout));
+                    const float w = J.src[((long long)ci * cout + co) * ss + ij];
+                    put_w(J.d32, (__nv_bfloat16*)J.d16, plane, ((long long)ij * cin + ci) * cout + co, w);
+                }
+            }
         }
     }
 }

@@ -6,6 +6,10 @@
 //
 // Head layout here: NHWC [B,H,W,heads_cs] with channels [0, A*K) = psm (a*K+k), [A*K, A*K+7A) = rm (a*7+j),
 // [A*K+7A, A*K+8A) = obj — exactly the reference's permute(0,2,3,1) views of psm / rm / obj.
+//
+// LEGACY = true: PointPillarLoss of the legacy `point_pillar_*` models (opencood/loss/point_pillar_loss.py:77-215): one
+// logit per anchor (K = 1, target = pos_equal_one), the focal term is divided by B once (the multi-class variant divides
+// twice), the same smooth-L1, no objectness head ([0, A) = psm, [A, 8A) = rm).
 #include "../../include/airv2x_b200.h"
 #include "a2x_host.h"
 
@@ -22,6 +26,7 @@ __global__ void count_pos_kernel(const float* __restrict__ pos, long long per_sa
 }
 
 // one thread per (b, h, w); A anchors, K classes
+template <bool LEGACY>
 __global__ void __launch_bounds__(256) det_loss_kernel(const float* __restrict__ heads, int cs, int A, int K,
                                                        const float* __restrict__ targets,   // [B,HW,A*7]
                                                        const float* __restrict__ pos,       // [B,HW,A]
@@ -41,7 +46,7 @@ __global__ void __launch_bounds__(256) det_loss_kernel(const float* __restrict__
         for (int a = 0; a < A; ++a) {
             const float pm = pos[p * A + a];
             const bool is_pos = pm > 0.f;
-            const int cid = class_ids[p * A + a];
+            const int cid = LEGACY ? (is_pos ? 0 : -1) : class_ids[p * A + a];
             // ---- classification: sigmoid focal loss, weight 1/max(npos,1) for every anchor
             for (int k = 0; k < K; ++k) {
                 const float x = hrow[a * K + k];
@@ -55,7 +60,7 @@ __global__ void __launch_bounds__(256) det_loss_kernel(const float* __restrict__
                 if (drow) {
                     const float dpt = (1.f - 2.f * t) * pr * (1.f - pr);
                     const float g = wn * (aw * 2.f * pt * dpt * bce + fw * (pr - t));
-                    drow[a * K + k] = g * cls_weight / ((float)B * (float)B);
+                    drow[a * K + k] = g * cls_weight / (LEGACY ? (float)B : (float)B * (float)B);
                 }
             }
             // ---- regression: smooth-L1 with sin-difference on yaw, positives only
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(256) det_loss_kernel(const float* __restrict__
                 }
             }
             // ---- objectness BCE (mean over all B*H*W*A)
-            {
+            if (!LEGACY) {
                 const float o = hrow[A * K + A * 7 + a];
                 const float s = 1.f / (1.f + expf(-o));
                 const float l = -(pm * logf(s + 1e-6f) + (1.f - pm) * logf(1.f - s + 1e-6f));
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(256) det_loss_kernel(const float* __restrict__
             }
         }
         if (drow) {
-            for (int c = A * K + A * 8; c < dcs; ++c) drow[c] = 0.f;
+            for (int c = A * K + A * (LEGACY ? 7 : 8); c < dcs; ++c) drow[c] = 0.f;
         }
     }
     // block reduce
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(256) det_loss_kernel(const float* __restrict__
             o += red[2][i];
         }
         atomicAdd(&loss3[0], r * reg_coe / B);
-        atomicAdd(&loss3[1], c * cls_weight / ((double)B * B));
+        atomicAdd(&loss3[1], c * cls_weight / (LEGACY ? (double)B : (double)B * B));
         atomicAdd(&loss3[2], o * obj_norm);
     }
 }
@@ -134,12 +139,33 @@ extern "C" {
 
 /* loss3[0..2] = (reg, cls, obj) terms (doubles, zeroed here); total = their sum. dheads may be NULL (value only).
  * npos_ws: B floats of workspace. */
+static int det_loss_launch(bool legacy, const float* heads, int heads_cs, int B, long long HW, int A, int K, const float* targets,
+                           const float* pos_equal_one, const int* class_ids, float cls_weight, float reg_coe, float* npos_ws,
+                           float* dheads, int dheads_cs, double* loss3, a2x_stream_t stream);
+
 int a2x_det_loss(const float* heads, int heads_cs, int B, long long HW, int A, int K, const float* targets,
                  const float* pos_equal_one, const int* class_ids, float cls_weight, float reg_coe, float* npos_ws,
                  float* dheads, int dheads_cs, double* loss3, a2x_stream_t stream) {
-    A2X_REQUIRE(heads && targets && pos_equal_one && class_ids && npos_ws && loss3 && B > 0 && HW > 0 && A > 0 && K > 0,
+    A2X_REQUIRE(class_ids, "det_loss: bad args");
+    return det_loss_launch(false, heads, heads_cs, B, HW, A, K, targets, pos_equal_one, class_ids, cls_weight, reg_coe, npos_ws,
+                           dheads, dheads_cs, loss3, stream);
+}
+
+/* PointPillarLoss of the legacy models: loss3 = (reg, conf, 0) */
+int a2x_det_loss_legacy(const float* heads, int heads_cs, int B, long long HW, int A, const float* targets,
+                        const float* pos_equal_one, float cls_weight, float reg_coe, float* npos_ws, float* dheads,
+                        int dheads_cs, double* loss3, a2x_stream_t stream) {
+    return det_loss_launch(true, heads, heads_cs, B, HW, A, 1, targets, pos_equal_one, nullptr, cls_weight, reg_coe, npos_ws,
+                           dheads, dheads_cs, loss3, stream);
+}
+
+static int det_loss_launch(bool legacy, const float* heads, int heads_cs, int B, long long HW, int A, int K, const float* targets,
+                           const float* pos_equal_one, const int* class_ids, float cls_weight, float reg_coe, float* npos_ws,
+                           float* dheads, int dheads_cs, double* loss3, a2x_stream_t stream) {
+    A2X_REQUIRE(heads && targets && pos_equal_one && npos_ws && loss3 && B > 0 && HW > 0 && A > 0 && K > 0,
                 "det_loss: bad args");
-    A2X_REQUIRE(heads_cs >= A * K + 8 * A && (!dheads || dheads_cs >= A * K + 8 * A), "det_loss: head stride too small");
+    const int need = A * K + (legacy ? 7 : 8) * A;
+    A2X_REQUIRE(heads_cs >= need && (!dheads || dheads_cs >= need), "det_loss: head stride too small");
     cudaStream_t st = (cudaStream_t)stream;
     A2X_CHECK_CUDA(cudaMemsetAsync(npos_ws, 0, sizeof(float) * B, st));
     A2X_CHECK_CUDA(cudaMemsetAsync(loss3, 0, sizeof(double) * 3, st));
@@ -148,8 +174,12 @@ int a2x_det_loss(const float* heads, int heads_cs, int B, long long HW, int A, i
     A2X_LAUNCHED();
     long long blocks = (B * HW + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    det_loss_kernel<<<(int)blocks, 256, 0, st>>>(heads, heads_cs, A, K, targets, pos_equal_one, class_ids, npos_ws, B, HW,
-                                                cls_weight, reg_coe, dheads, dheads_cs, loss3);
+    if (legacy)
+        det_loss_kernel<true><<<(int)blocks, 256, 0, st>>>(heads, heads_cs, A, K, targets, pos_equal_one, class_ids, npos_ws, B,
+                                                          HW, cls_weight, reg_coe, dheads, dheads_cs, loss3);
+    else
+        det_loss_kernel<false><<<(int)blocks, 256, 0, st>>>(heads, heads_cs, A, K, targets, pos_equal_one, class_ids, npos_ws, B,
+                                                           HW, cls_weight, reg_coe, dheads, dheads_cs, loss3);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -4,14 +4,17 @@ Same registry name / class name / constructor, same `hypes_yaml` keys (`pillar_v
 `base_bev_backbone`, `shrink_header`, `where2comm_fusion`, `head_dim`, `anchor_number`, `compression`), same
 `state_dict` keys and shapes (8 057 386 parameters for V2XR_where2comm.yaml), same
 `forward(data_dict) -> {"psm","rm","com","mask","each_mask","comm_rate"}` as opencood/models/point_pillar_where2comm.py
-of the reference (input: `data_dict["processed_lidar"]`, `record_len`, `pairwise_t_matrix`). Parameter containers only;
-eval-mode forward in this round; no CPU fallback.
+of the reference (input: `data_dict["processed_lidar"]`, `record_len`, `pairwise_t_matrix`). Parameter containers only.
+Eval forward, train-mode forward wired to autograd (torch.library ops, so the reference's loop `model(batch)` ->
+PointPillarLoss -> `loss.backward()` works) and the fused `train_step` (forward + PointPillarLoss kernel + backward); no
+CPU fallback.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 
 from ...ppw2c_engine import LegacyW2CEngine
+from ...w2c_engine import HEAD_PAD
 from .airv2x_where2com import _backbone_params, _comm_params, _PillarVFEParams
 
 
@@ -68,10 +71,7 @@ class PointPillarWhere2comm(nn.Module):
         d.update({n: b for n, b in self.named_buffers()})
         return d
 
-    def forward(self, data_dict):
-        dev = next(self.parameters()).device
-        if dev.type != "cuda":
-            raise RuntimeError("PointPillarWhere2comm (B200) needs its parameters on a CUDA device; there is no CPU path")
+    def _inputs(self, data_dict, dev):
         lid = data_dict[self.modality]
         r = data_dict["record_len"]
         record_len = [int(v) for v in (r.tolist() if torch.is_tensor(r) else r)]
@@ -89,7 +89,39 @@ class PointPillarWhere2comm(nn.Module):
         lidar = {"voxel_features": lid["voxel_features"].to(device=dev, dtype=torch.float32).contiguous(),
                  "voxel_num_points": lid["voxel_num_points"].to(device=dev, dtype=torch.int32).contiguous(),
                  "voxel_coords": lid["voxel_coords"].to(device=dev, dtype=torch.int32).contiguous()}
-        heads, aux = self.engine.forward(self._param_dict(), lidar, layout, self.training)
+        return lidar, layout
+
+    def forward(self, data_dict):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PointPillarWhere2comm (B200) needs its parameters on a CUDA device; there is no CPU path")
+        lidar, layout = self._inputs(data_dict, dev)
+        record_len = layout["record_len"]
+        eng = self.engine
+        if self.training and torch.is_grad_enabled():
+            # reference training loop: model(batch) -> PointPillarLoss -> loss.backward(); autograd boundary = torch_ops
+            from ... import torch_ops
+            names = [n for n, p in self.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
+            params = [p for n, p in self.named_parameters() if p.requires_grad and not n.startswith("fusion_net")]
+            st = {}
+
+            def run_forward():
+                h, st["aux"] = eng.forward(self._param_dict(), lidar, layout, True)
+                return h
+
+            def run_backward(dheads):
+                P = self._param_dict()
+                grads = {n: torch.zeros_like(P[n]) for n in names}
+                eng.backward(P, dheads, grads)
+                return [grads[n] for n in names]
+
+            s = self.engine.shrink_stride
+            hh, ww = layout["ny"] // 2, layout["nx"] // 2
+            shape = [len(record_len), (hh - 1) // s + 1, (ww - 1) // s + 1, HEAD_PAD]
+            heads = torch.ops.a2x.fused_forward(torch_ops.bind(self, run_forward, run_backward), params, shape)
+            aux = st["aux"]
+        else:
+            heads, aux = eng.forward(self._param_dict(), lidar, layout, self.training)
         A = self.args["anchor_number"]
         nchw = heads.permute(0, 3, 1, 2)
         rl = torch.tensor(record_len, dtype=torch.float32, device=dev)
@@ -99,3 +131,31 @@ class PointPillarWhere2comm(nn.Module):
             com = (aux["ones"] / (rl * aux["hw"])).sum() / len(record_len)
         return {"psm": nchw[:, :A], "rm": nchw[:, A:8 * A], "com": com, "mask": 0, "each_mask": 0,
                 "comm_rate": int(aux["comm_rate"].item())}
+
+    def _grad_buffers(self):
+        g = {}
+        for n, p in self.named_parameters():
+            if n.startswith("fusion_net") or not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            g[n] = p.grad
+        return g
+
+    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, k_list=None):
+        """forward (train-mode BatchNorm, top-K communication mask) + PointPillarLoss (loss/point_pillar_loss.py:77-215) +
+        backward in one call on the CUDA kernels; label_dict = the legacy collate's {"targets" [B,H,W,7A], "pos_equal_one"
+        [B,H,W,A]}. Parameter gradients land in p.grad; returns the device tensor [reg, conf, 0] (float64), total = .sum()."""
+        assert self.training, "train_step() needs model.train()"
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("PointPillarWhere2comm (B200) needs its parameters on a CUDA device; there is no CPU path")
+        lidar, layout = self._inputs(data_dict, dev)
+        labels = {"targets": label_dict["targets"].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(),
+                  "pos_equal_one": label_dict["pos_equal_one"].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()}
+        P = self._param_dict()
+        eng = self.engine
+        heads, self._last_aux = eng.forward(P, lidar, layout, True, k_list)
+        loss3, dheads = eng.loss(heads, labels, cls_weight, reg_coe)
+        eng.backward(P, dheads, self._grad_buffers())
+        return loss3

@@ -102,17 +102,23 @@ class UnpackJob(ctypes.Structure):
                 ("elems", ctypes.c_longlong)]
 
 
-def conv_pack_job(w, pk, row0=0):
-    """OIHW parameter `w` -> rows [row0, row0 + cout) of the PackedW `pk` (cout_pad = pk.f32.shape[1])"""
+PACK_F32_PLANES = True   # engines in split (bf16 x 3) mode set False: the fp32 weight planes feed no GEMM there
+
+
+def conv_pack_job(w, pk, row0=0, f32=None):
+    """OIHW parameter `w` -> rows [row0, row0 + cout) of the PackedW `pk` (cout_pad = pk.f32.shape[1]); f32 False: only
+    the bf16 planes are written"""
     cout, cin, k, _ = w.shape
-    return PackJob(w.data_ptr(), pk.f32.data_ptr(), pk.f16.data_ptr(), pk.d32.data_ptr(), pk.d16.data_ptr(), 0, cout, cin,
-                   k * k, pk.f32.shape[1], row0, 0, k * k * cout * cin)
+    f32 = PACK_F32_PLANES if f32 is None else f32
+    return PackJob(w.data_ptr(), pk.f32.data_ptr() if f32 else None, pk.f16.data_ptr(), pk.d32.data_ptr() if f32 else None,
+                   pk.d16.data_ptr(), 0, cout, cin, k * k, pk.f32.shape[1], row0, 0, k * k * cout * cin)
 
 
-def deconv_pack_job(w, pk):
+def deconv_pack_job(w, pk, f32=None):
     cin, cout, s, _ = w.shape
-    return PackJob(w.data_ptr(), pk.f32.data_ptr(), pk.f16.data_ptr(), pk.d32.data_ptr(), pk.d16.data_ptr(), 1, cin, cout,
-                   s * s, 0, 0, 0, cin * cout * s * s)
+    f32 = PACK_F32_PLANES if f32 is None else f32
+    return PackJob(w.data_ptr(), pk.f32.data_ptr() if f32 else None, pk.f16.data_ptr(), pk.d32.data_ptr() if f32 else None,
+                   pk.d16.data_ptr(), 1, cin, cout, s * s, 0, 0, 0, cin * cout * s * s)
 
 
 def copy_pack_job(src, dst, row0):
@@ -556,8 +562,13 @@ def att_fuse_bwd(x, dout, dx):
     call("a2x_att_fuse_bwd", _ptr(x), _ptr(dout), c_int(n), c_int(h * w), c_int(c), _ptr(dx), stream_ptr())
 
 
-def det_loss(heads, A, K, targets, pos, class_ids, cls_weight, reg_coe, npos_ws, dheads, loss3):
+def det_loss(heads, A, K, targets, pos, class_ids, cls_weight, reg_coe, npos_ws, dheads, loss3, legacy=False):
     B, H, W, cs = heads.shape[0], heads.shape[1], heads.shape[2], _cs(heads)
+    if legacy:   # PointPillarLoss of the legacy point_pillar_* models (K = 1, no objectness)
+        call("a2x_det_loss_legacy", _ptr(heads), c_int(cs), c_int(B), c_ll(H * W), c_int(A), _ptr(targets), _ptr(pos),
+             c_f(cls_weight), c_f(reg_coe), _ptr(npos_ws), _ptr(dheads), c_int(_cs(dheads) if dheads is not None else 0),
+             _ptr(loss3), stream_ptr())
+        return
     call("a2x_det_loss", _ptr(heads), c_int(cs), c_int(B), c_ll(H * W), c_int(A), c_int(K), _ptr(targets), _ptr(pos),
          _ptr(class_ids), c_f(cls_weight), c_f(reg_coe), _ptr(npos_ws), _ptr(dheads),
          c_int(_cs(dheads) if dheads is not None else 0), _ptr(loss3), stream_ptr())

@@ -3,7 +3,9 @@
 Same kernels as the airv2x Where2comm engine; what differs (models/point_pillar_where2comm.py:26-151): ONE PillarVFE
 for all agents (`pillar_vfe.*`), the backbone evaluated once before the fusion, a 3x3 stride-2 shrink header — so the
 communication mask lives at half the resolution of the level-0 features and is bilinearly resized
-(where2comm_fuse.py:230-236) — and 1-class heads without objectness. Eval-mode forward in this round.
+(where2comm_fuse.py:230-236) — and 1-class heads without objectness. forward() / backward() / loss() are the parent's:
+the differences are class attributes (shrink geometry, BatchNorm update counts, head rows, PointPillarLoss) and the
+single-encoder _encode below, so the legacy model trains on the same kernels (fused PointPillarLoss, a2x_det_loss_legacy).
 """
 import torch
 
@@ -13,6 +15,15 @@ from .w2c_engine import HEAD_PAD, W2CEngine
 
 
 class LegacyW2CEngine(W2CEngine):
+    shrink_k0 = 3
+    # the backbone runs once, then its blocks again inside the fusion (point_pillar_where2comm.py:118-146): block 0 (shared
+    # here) sees 2 running-stat updates, everything else 1 per pass
+    upd_block0, upd_pass_a, upd_pass_b = 2, 1, 1
+    legacy_loss = True
+
+    def _head_rows(self):
+        return (("cls_head", 0), ("reg_head", self.A))
+
     def __init__(self, args, device, precision="split3"):  # noqa
         assert precision in ("split3", "tf32"), precision
         self.args = args
@@ -46,6 +57,7 @@ class LegacyW2CEngine(W2CEngine):
         self.side = None
         self.use_side_stream = True
         self.fuse_bn_bwd_reduce = False
+        self.k_on_device = False
 
     def _pack_weights(self, P):
         W, jobs = {}, []
@@ -55,19 +67,19 @@ class LegacyW2CEngine(W2CEngine):
                 w = P[name]
                 co, ci = w.shape[0], w.shape[1]
                 W[name] = self._packed(name, (9, co, ci), (9, ci, co))
-                jobs.append(ops.conv_pack_job(w, W[name]))
+                jobs.append(ops.conv_pack_job(w, W[name], f32=not self.split))
             name = "backbone.deblocks.%d.0.weight" % i
             w = P[name]
             s = self.up_strides[i]
             ci, co = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (1, s * s * co, ci), (s * s, ci, co))
-            jobs.append(ops.deconv_pack_job(w, W[name]))
+            jobs.append(ops.deconv_pack_job(w, W[name], f32=not self.split))
         for idx in (0, 2):
             name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
             w = P[name]
             co, ci = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (9, co, ci), (9, ci, co))
-            jobs.append(ops.conv_pack_job(w, W[name]))
+            jobs.append(ops.conv_pack_job(w, W[name], f32=not self.split))
         fresh = ("packed", "heads") not in self.bufs
         hp = self._packed("heads", (1, HEAD_PAD, self.c_shrink), (1, self.c_shrink, HEAD_PAD))
         hb = self._buf("heads.b", (HEAD_PAD,))
@@ -75,7 +87,7 @@ class LegacyW2CEngine(W2CEngine):
             for t in (hp.f32, hp.f16, hp.d32, hp.d16, hb):
                 t.zero_()
         for name, row0 in (("cls_head", 0), ("reg_head", self.A)):
-            jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0))
+            jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0, f32=not self.split))
             jobs.append(ops.copy_pack_job(P[name + ".bias"], hb, row0))
         W["heads"] = hp
         W["heads.bias"] = hb
@@ -95,11 +107,27 @@ class LegacyW2CEngine(W2CEngine):
         self._canvas_nz = nzc
         geom = ops.pfn_geom(self.args["voxel_size"], self.args["lidar_range"], nx, ny)
         pre = "pillar_vfe.pfn_layers.0"
+        vox, num, coords = lidar["voxel_features"], lidar["voxel_num_points"], lidar["voxel_coords"]
+        w = P[pre + ".linear.weight"]
         scale, shift = self._buf("pfn.scale", (64,)), self._buf("pfn.shift", (64,))
-        ops.bn_eval_affine(P[pre + ".norm.weight"], P[pre + ".norm.bias"], P[pre + ".norm.running_mean"],
-                           P[pre + ".norm.running_var"], scale, shift)
-        ops.pfn_scatter(lidar["voxel_features"], lidar["voxel_num_points"], lidar["voxel_coords"], geom,
-                        P[pre + ".linear.weight"], scale, shift, layout["identity_map"], canvas, nz=nzc, write_hi=hi)
+        amap = layout["identity_map"]
+        if training:   # batch statistics over all M*32 rows from the moments (PFNLayer, airv2x_pillar_vfe.py:27-49 = pillar_vfe.py)
+            mean, invstd = self._buf("pfn.mean", (64,)), self._buf("pfn.invstd", (64,))
+            moments = self._buf("pfn.moments", (65,), torch.float64)
+            ops.pfn_moments(vox, num, coords, geom, moments)
+            rows = vox.shape[0] * 32
+            ops.pfn_stats_finalize(moments, rows, w, P[pre + ".norm.weight"], P[pre + ".norm.bias"], 1,
+                                   P[pre + ".norm.running_mean"], P[pre + ".norm.running_var"], scale, shift, mean, invstd)
+            amax = self._buf("pfn.amax", (vox.shape[0], 64), torch.uint8)
+            ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax, nz=nzc, write_hi=hi)
+            if record is not None:
+                record.append(dict(kind="pfn", type="all", vox=vox, num=num, coords=coords, geom=geom, pre=pre, scale=scale,
+                                   shift=shift, mean=mean, invstd=invstd, amap=amap, amax=amax, moments=moments, rows=rows,
+                                   seg=None))
+        else:
+            ops.bn_eval_affine(P[pre + ".norm.weight"], P[pre + ".norm.bias"], P[pre + ".norm.running_mean"],
+                               P[pre + ".norm.running_var"], scale, shift)
+            ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, nz=nzc, write_hi=hi)
         return canvas
 
     def _shrink_heads(self, P, W, cat, tag, heads_only_cls=False):
@@ -115,68 +143,3 @@ class LegacyW2CEngine(W2CEngine):
         heads = self._buf(tag + ".heads", (n, ho, wo, HEAD_PAD))
         ops.conv_fwd(y2, W["heads"], 1, 1, Act(heads), shift=W["heads.bias"])
         return y1, y2, heads
-
-    def forward(self, P, lidar, layout, training, k_list=None):
-        if training:
-            raise NotImplementedError("point_pillar_where2comm on the B200 kernels is eval-only in this round")
-        self._begin_step()
-        W = self._pack_weights(P)
-        record_len = layout["record_len"]
-        B, N = len(record_len), layout["n_total"]
-        canvas = self._encode(P, lidar, layout, False, None)
-        nz = self._buf("comm_rate", (1,), torch.int64)
-        nz.copy_(self._canvas_nz)
-        x0 = self._block(P, W, 0, canvas, False, 0, "A", None)
-        h2, w2 = x0.shape[1], x0.shape[2]
-        catA = self._act("A.cat", (N, h2, w2, self.c_cat))
-        xa = x0
-        for i in range(len(self.layer_nums)):
-            if i > 0:
-                xa = self._block(P, W, i, xa, False, 0, "A", None)
-            c0 = sum(self.up_filters[:i])
-            with self._on_side():
-                self._deblock(P, W, i, xa, catA.slice_c(c0, c0 + self.up_filters[i]), False, 0, "A", None)
-        self._join_side()
-        _, _, headsA = self._shrink_heads(P, W, catA, "A")
-        hm, wm = headsA.shape[1], headsA.shape[2]
-        mask_lo = self._buf("mask.lo", (N, hm, wm))
-        ones = self._buf("mask.ones", (B,))
-        thr = float(self.comm["threshold"])
-        if self.fully:
-            mask_lo.fill_(1.0)
-            ones.fill_(float("nan"))
-        else:
-            conf, smooth = self._buf("conf", (N, hm, wm)), self._buf("smooth", (N, hm, wm))
-            ops.comm_confidence(headsA, self.A * self.K, conf)
-            gs = self.comm.get("gaussian_smooth")
-            if thr:
-                ops.comm_smooth_mask(conf, P.get("fusion_net.naive_communication.gaussian_filter.weight"),
-                                     P.get("fusion_net.naive_communication.gaussian_filter.bias"),
-                                     gs["k_size"] if gs else 0, N, hm, wm, thr, True, smooth, mask_lo)
-            else:
-                mask_lo.fill_(1.0)
-            ones.zero_()
-            ops.comm_rate_ego(mask_lo, hm * wm, B, layout["scene_start"], layout["scene_len"], ones)
-        if (hm, wm) != (h2, w2):
-            mask = self._buf("mask", (N, h2, w2))
-            ops.resize_bilinear(mask_lo, mask)
-        else:
-            mask = mask_lo
-        x0m = self._act("B.x0m", x0.shape)
-        ops.affine_act(x0.hi, None, None, False, x0m, mask=mask)
-        catB = self._act("B.cat", (B, h2, w2, self.c_cat))
-        xb = x0m
-        for i in range(len(self.layer_nums)):
-            if i > 0:
-                xb = self._block(P, W, i, xb, False, 0, "B", None)
-            fused = self._act("B.fuse%d" % i, (B,) + tuple(xb.shape[1:]))
-            pos = 0
-            for b, n in enumerate(record_len):
-                ops.att_fuse_fwd(xb.hi[pos:pos + n], fused.narrow_n(b, 1))
-                pos += n
-            c0 = sum(self.up_filters[:i])
-            with self._on_side():
-                self._deblock(P, W, i, fused, catB.slice_c(c0, c0 + self.up_filters[i]), False, 0, "B", None)
-        self._join_side()
-        _, _, heads = self._shrink_heads(P, W, catB, "B")
-        return heads, dict(comm_rate=nz, ones=ones, hw=hm * wm)

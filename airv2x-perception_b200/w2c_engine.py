@@ -24,6 +24,19 @@ HEAD_PAD = 64  # fused head GEMM width (cls | reg | obj | zero pad); 64 keeps sp
 
 
 class W2CEngine:
+    # What differs between the airv2x model and the legacy `point_pillar_where2comm` (LegacyW2CEngine overrides):
+    shrink_k0 = 1        # kernel of shrink_conv.layers.0.double_conv.0 (airv2x yaml: 1x1 s1; legacy yamls: 3x3 s2)
+    shrink_stride = 1
+    # BatchNorm running-stat updates per training step. airv2x evaluates the backbone twice back to back and its blocks a
+    # third time inside the fusion (airv2x_where2com.py:119,124, where2comm_fuse.py:218): block 0 (shared here) 3, the other
+    # un-masked layers 2, the masked pass 1. The legacy model evaluates the backbone once (point_pillar_where2comm.py:118).
+    upd_block0, upd_pass_a, upd_pass_b = 3, 2, 1
+    legacy_loss = False  # PointPillarLoss (1 class, no objectness) instead of PointPillarLossMultiClass
+
+    def _head_rows(self):
+        nc, nr = self.A * self.K, 7 * self.A
+        return (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr))
+
     def __init__(self, args, device, precision="split3"):
         assert precision in ("split3", "tf32"), precision
         self.args = args
@@ -124,19 +137,19 @@ class W2CEngine:
                 w = P[name]
                 co, ci = w.shape[0], w.shape[1]
                 W[name] = self._packed(name, (9, co, ci), (9, ci, co))
-                jobs.append(ops.conv_pack_job(w, W[name]))
+                jobs.append(ops.conv_pack_job(w, W[name], f32=not self.split))
             name = "backbone.deblocks.%d.0.weight" % i
             w = P[name]
             s = self.up_strides[i]
             ci, co = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (1, s * s * co, ci), (s * s, ci, co))
-            jobs.append(ops.deconv_pack_job(w, W[name]))
+            jobs.append(ops.deconv_pack_job(w, W[name], f32=not self.split))
         for idx, k in ((0, 1), (2, 3)):
             name = "shrink_conv.layers.0.double_conv.%d.weight" % idx
             w = P[name]
             co, ci = w.shape[0], w.shape[1]
             W[name] = self._packed(name, (k * k, co, ci), (k * k, ci, co))
-            jobs.append(ops.conv_pack_job(w, W[name]))
+            jobs.append(ops.conv_pack_job(w, W[name], f32=not self.split))
         nc, nr = self.A * self.K, 7 * self.A
         fresh = ("packed", "heads") not in self.bufs
         hp = self._packed("heads", (1, HEAD_PAD, self.c_shrink), (1, self.c_shrink, HEAD_PAD))
@@ -145,7 +158,7 @@ class W2CEngine:
             for t in (hp.f32, hp.f16, hp.d32, hp.d16, hb):
                 t.zero_()
         for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
-            jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0))
+            jobs.append(ops.conv_pack_job(P[name + ".weight"], hp, row0, f32=not self.split))
             jobs.append(ops.copy_pack_job(P[name + ".bias"], hb, row0))
         W["heads"] = hp
         W["heads.bias"] = hb
@@ -154,7 +167,7 @@ class W2CEngine:
 
     def _job_table(self, name, jobs):
         """device job table cached by the pointers it refers to (stable across steps: one upload)"""
-        key = tuple((j.src, j.dst if hasattr(j, "dst") else j.f32) for j in jobs)
+        key = tuple((j.src, j.dst if hasattr(j, "dst") else (j.f32 or j.f16)) for j in jobs)
         ent = self.bufs.get(("jobs", name))
         if ent is None or ent[0] != key:
             ent = (key, ops.JobTable(jobs, self.device))
@@ -357,7 +370,7 @@ class W2CEngine:
         # ---- pass A: un-masked backbone on every agent map (single-agent confidence for the mask)
         # block 0 is shared with the fusion pass; in train mode its BNs see 3 identical running-stat updates
         # (airv2x_where2com.py:119,124 + where2comm_fuse.py:218), the other pass-A BNs 2.
-        x0 = self._block(P, W, 0, canvas, training, 3, "A", rec)
+        x0 = self._block(P, W, 0, canvas, training, self.upd_block0, "A", rec)
         h2, w2 = x0.shape[1], x0.shape[2]
         catA = self._act("A.cat", (N, h2, w2, self.c_cat))
         xa = x0
@@ -365,24 +378,25 @@ class W2CEngine:
         # fewer 128-pixel tiles than the GPU has SMs: the HBM-bound 1x1 deblock GEMMs fill the idle ones)
         for i in range(len(self.layer_nums)):
             if i > 0:
-                xa = self._block(P, W, i, xa, training, 2, "A", None, need_hi=False)
+                xa = self._block(P, W, i, xa, training, self.upd_pass_a, "A", None, need_hi=False)
             c0 = sum(self.up_filters[:i])
             with self._on_side():
-                self._deblock(P, W, i, xa, catA.slice_c(c0, c0 + self.up_filters[i]), training, 2, "A", None)
+                self._deblock(P, W, i, xa, catA.slice_c(c0, c0 + self.up_filters[i]), training, self.upd_pass_a, "A", None)
         self._join_side()
         _, _, headsA = self._shrink_heads(P, W, catA, "A")
 
-        # ---- communication mask (where2comm_fuse.py:83-149)
-        hw = h2 * w2
-        mask = self._buf("mask", (N, h2, w2))
+        # ---- communication mask (where2comm_fuse.py:83-149), at the resolution of the head map: the legacy model's
+        # stride-2 shrink header halves it, and the mask is resized bilinearly to the level-0 features (:230-236)
+        hm, wm = headsA.shape[1], headsA.shape[2]
+        hw = hm * wm
+        mask_lo = self._buf("mask" if (hm, wm) == (h2, w2) else "mask.lo", (N, hm, wm))
         ones = self._buf("mask.ones", (B,))
         if self.fully:
-            mask.fill_(1.0)
+            mask_lo.fill_(1.0)
             ones.fill_(float("nan"))
         else:
-            assert headsA.shape[1] == h2 and headsA.shape[2] == w2, "mask interpolation not implemented"
-            conf = self._buf("conf", (N, h2, w2))
-            smooth = self._buf("smooth", (N, h2, w2))
+            conf = self._buf("conf", (N, hm, wm))
+            smooth = self._buf("smooth", (N, hm, wm))
             ops.comm_confidence(headsA, self.A * self.K, conf)
             gs = self.comm.get("gaussian_smooth")
             ksz = gs["k_size"] if gs else 0
@@ -397,13 +411,18 @@ class W2CEngine:
                 k_dev = self._buf("k_dev", (N,), torch.int32)
                 if not self.k_on_device:  # pipelined mode stages K with the other inputs (no H2D inside the graph)
                     k_dev.copy_(k_host, non_blocking=True)
-                ops.comm_smooth_mask(conf, gw, gb, ksz, N, h2, w2, thr, False, smooth, mask)
-                ops.comm_topk_mask(smooth, N, hw, k_dev, mask)
+                ops.comm_smooth_mask(conf, gw, gb, ksz, N, hm, wm, thr, False, smooth, mask_lo)
+                ops.comm_topk_mask(smooth, N, hw, k_dev, mask_lo)
             elif thr:
-                ops.comm_smooth_mask(conf, gw, gb, ksz, N, h2, w2, thr, True, smooth, mask)
+                ops.comm_smooth_mask(conf, gw, gb, ksz, N, hm, wm, thr, True, smooth, mask_lo)
             else:
-                mask.fill_(1.0)
-            ops.comm_rate_ego(mask, hw, B, layout["scene_start"], layout["scene_len"], ones)
+                mask_lo.fill_(1.0)
+            ops.comm_rate_ego(mask_lo, hw, B, layout["scene_start"], layout["scene_len"], ones)
+        if (hm, wm) != (h2, w2):
+            mask = self._buf("mask", (N, h2, w2))
+            ops.resize_bilinear(mask_lo, mask)
+        else:
+            mask = mask_lo
 
         # ---- pass B: masked multi-scale fusion (where2comm_fuse.py:214-262)
         x0m = self._act("B.x0m", x0.shape)
@@ -413,7 +432,7 @@ class W2CEngine:
         levels = []
         for i in range(len(self.layer_nums)):
             if i > 0:
-                xb = self._block(P, W, i, xb, training, 1, "B", rec)
+                xb = self._block(P, W, i, xb, training, self.upd_pass_b, "B", rec)
             n_, hh, ww, cc = xb.shape
             fused = self._act("B.fuse%d" % i, (B, hh, ww, cc))
             xfull = self._full(xb, "B.xfull%d" % i)
@@ -424,7 +443,7 @@ class W2CEngine:
             levels.append(dict(x=xb, xfull=xfull, fused=fused))
             c0 = sum(self.up_filters[:i])
             with self._on_side():
-                self._deblock(P, W, i, fused, catB.slice_c(c0, c0 + self.up_filters[i]), training, 1, "B", rec)
+                self._deblock(P, W, i, fused, catB.slice_c(c0, c0 + self.up_filters[i]), training, self.upd_pass_b, "B", rec)
         self._join_side()
         y1, y2, heads = self._shrink_heads(P, W, catB, "B")
         if training:
@@ -559,8 +578,8 @@ class W2CEngine:
         dheads = self._buf("dheads", heads.shape) if want_grad else None
         loss3 = self._buf("loss3", (3,), torch.float64)
         npos = self._buf("npos", (B,))
-        ops.det_loss(heads, self.A, self.K, labels["targets"], labels["pos_equal_one"], labels["class_ids"],
-                     float(cls_weight), float(reg_coe), npos, dheads, loss3)
+        ops.det_loss(heads, self.A, self.K, labels["targets"], labels["pos_equal_one"], labels.get("class_ids"),
+                     float(cls_weight), float(reg_coe), npos, dheads, loss3, legacy=self.legacy_loss)
         return loss3, dheads
 
     # ------------------------------------------------------------------ backward
@@ -624,10 +643,9 @@ class W2CEngine:
         ops.affine_act(dheads, None, None, False, dh)
         with self._on_side():
             dwp = wgrad_conv(S["y2"], dh, "heads", 1, 1)
-            for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+            for name, row0 in self._head_rows():
                 unpack.append(ops.conv_unpack_job(dwp, grads[name + ".weight"], row0))
-            bias_grad(dheads, HEAD_PAD, [(grads["cls_head.bias"], 0), (grads["reg_head.bias"], nc),
-                                         (grads["obj_head.bias"], nc + nr)])
+            bias_grad(dheads, HEAD_PAD, [(grads[name + ".bias"], row0) for name, row0 in self._head_rows()])
         d_y2 = self._buf("bwd.d_y2", S["y2"].shape)
         ops.conv_dgrad(dh, W["heads"], 1, 1, d_y2)
 
@@ -647,11 +665,11 @@ class W2CEngine:
         ops.relu_bwd(d_y1, S["y1"].hi, g1)
         n1 = "shrink_conv.layers.0.double_conv.0"
         with self._on_side():
-            dwp = wgrad_conv(S["catB"], g1, n1 + ".weight", 1, 1)
+            dwp = wgrad_conv(S["catB"], g1, n1 + ".weight", self.shrink_k0, self.shrink_stride)
             unpack.append(ops.conv_unpack_job(dwp, grads[n1 + ".weight"]))
             bias_grad(g1, self.c_shrink, [(grads[n1 + ".bias"], 0)])
-        d_cat = self._buf("bwd.d_cat", (B, h2, w2, self.c_cat))
-        ops.conv_dgrad(g1, W[n1 + ".weight"], 1, 1, d_cat)
+        d_cat = self._buf("bwd.d_cat", S["catB"].shape)
+        ops.conv_dgrad(g1, W[n1 + ".weight"], self.shrink_k0, self.shrink_stride, d_cat)
 
         # ---- deblocks (pass B) -> d(fused_i); fusion backward -> d(x_i) for every agent
         levels = S["levels"]

@@ -389,6 +389,39 @@ def agent_parallel_block(torch, dist, dev, rank, world, precision):
     return res
 
 
+def agent_parallel_children(world, precision, timeout_s=420):
+    """every rank starts `bench.py --agent-parallel-child` (same RANK / LOCAL_RANK, another rendezvous port); rank 0's
+    child prints the block"""
+    env = dict(os.environ)
+    env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 23)
+    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)     # the child group hosts its own store on rank 0
+    cmd = [sys.executable, os.path.abspath(__file__), "--agent-parallel-child", "--gpus", str(world), "--precision", precision]
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"error": "agent-parallel child processes did not finish within %d s" % timeout_s}
+    for ln in reversed(r.stdout.splitlines()):
+        if ln.startswith("AGENT_PARALLEL "):
+            return json.loads(ln[len("AGENT_PARALLEL "):])
+    return {"error": "child rc=%d: %s" % (r.returncode, (r.stderr or "")[-300:])} if int(os.environ.get("RANK", "0")) == 0 else {}
+
+
+def agent_parallel_child(args):
+    import datetime
+
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    blk = agent_parallel_block(torch, dist, dev, rank, world, args.precision)
+    if rank == 0:
+        print("AGENT_PARALLEL " + json.dumps(blk))
+    dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -404,7 +437,10 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the configs 3/4/5, sustained and agent-parallel blocks")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--post-grad-sync", action="store_true", help="N > 1: all-reduce the gradients after the step (no overlap)")
+    ap.add_argument("--agent-parallel-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.agent_parallel_child:
+        return agent_parallel_child(args)
     spec = WORKLOADS[args.config]
     cfg = load_config(spec["cfg"])
     rank = int(os.environ.get("RANK", "0"))
@@ -442,7 +478,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))   # fail, never hang
     libmod = a2x_import.pkg("_lib")
     lib = libmod.load()
     W = Workload(args.config, torch, dev, seed=rank, precision=args.precision)
@@ -583,7 +620,10 @@ def main():
         torch.cuda.empty_cache()
         line["extra"] = extra_configs(torch, dev, args.precision)
     if world > 1 and args.config in (2, 4) and not args.no_extra:
-        blk = agent_parallel_block(torch, dist, dev, rank, world, args.precision)
+        # agents one per GPU (north_star / config 4): measured in CHILD processes with their own process group and a hard
+        # timeout, so that nothing there can take the headline line down
+        sync_all()
+        blk = agent_parallel_children(world, args.precision)
         if rank == 0:
             line["agent_parallel"] = blk
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:
@@ -608,8 +648,11 @@ def roofline_pass(model, libmod, dd, lab, cw, rc, precision, torch):
         peak, src = 1400.0, "fallback (B200_PROFILING.md sustained)"
     libmod.PROFILE = []
     side, model.engine.use_side_stream = model.engine.use_side_stream, False  # serialise: clean per-kernel durations
+    gsync = model.__dict__.pop("grad_sync", None)   # rank 0 alone runs this step: no collective inside it
     model.train_step(dd, lab, cw, rc)
     torch.cuda.synchronize()
+    if gsync is not None:
+        model.grad_sync = gsync
     model.engine.use_side_stream = side
     prof, libmod.PROFILE = libmod.PROFILE, None
     groups = {}

@@ -467,6 +467,12 @@ int a2x_att_fuse_bwd(const float* x, const float* dout, int n_agents, int hw, in
 int a2x_det_loss(const float* heads, int heads_cs, int B, long long HW, int A, int K, const float* targets,
                  const float* pos_equal_one, const int* class_ids, float cls_weight, float reg_coe, float* npos_ws,
                  float* dheads, int dheads_cs, double* loss3, a2x_stream_t stream);
+/* Replace PointPillarLoss.forward of the legacy `point_pillar_*` models (opencood/loss/point_pillar_loss.py:77-215): one
+ * logit per anchor, focal term / B once, the same smooth-L1 with sin-difference, no objectness; heads [psm(A) | rm(7A)],
+ * loss3 = (reg, conf, 0). */
+int a2x_det_loss_legacy(const float* heads, int heads_cs, int B, long long HW, int A, const float* targets,
+                        const float* pos_equal_one, float cls_weight, float reg_coe, float* npos_ws, float* dheads,
+                        int dheads_cs, double* loss3, a2x_stream_t stream);
 
 #ifdef __cplusplus
 }

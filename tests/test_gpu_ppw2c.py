@@ -39,3 +39,78 @@ def test_eval_matches_reference_golden():
         assert np.abs(out[k].cpu().numpy() - gold["eval_" + k]).max() < 1e-3, k
     assert abs(float(out["com"]) - float(gold["eval_com"])) < 1e-6
     assert out["comm_rate"] == int(gold["eval_comm_rate"]) and out["mask"] == 0
+
+
+def test_train_step_matches_reference_golden():
+    """The legacy model's training step on the kernels (train-mode BatchNorm with the 2 / 1 / 1 running-stat updates of
+    point_pillar_where2comm.py:118-146, top-K mask at half resolution resized bilinearly, fused PointPillarLoss, full
+    backward) against the run of the REAL reference recorded by scripts/make_golden_legacy_train.py and against the oracle
+    with the kernel's top-K tie-breaks teacher-forced (see tests/test_gpu_model.py for why)."""
+    import os
+    import random
+    import sys
+
+    import a2x_import
+    from oracle import w2c_oracle as O
+
+    sys.path.insert(0, os.path.join(T.ROOT, "scripts"))
+    import make_golden_legacy_train as G
+
+    M = a2x_import.pkg("opencood.models.point_pillar_where2comm")
+    cfg, gold = T.load()
+    tg = np.load(os.path.join(T.GOLD, "ppw2c_train_small.npz"))
+    args = cfg["model_args"]
+    model = M.PointPillarWhere2comm(args)
+    sd = T.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    dd = T.golden_scene(cfg, gold)
+    H, W = tg["train_psm"].shape[2:]
+    lab = G.labels(H, W, args["anchor_number"])
+    k_seed = int(tg["k_seed"])
+    random.seed(k_seed)
+    loss3 = model.train_step(C.to_device(dd, "cuda"), lab, 1.0, 2.0).clone()
+    assert float(loss3[2]) == 0.0                                     # no objectness term in PointPillarLoss
+    mask_lo = C.engine_buf(model, "mask.lo").cpu().clone()
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "gaussian" not in k else v.clone())
+         for k, v in sd.items()}
+    keep = {"mask_override": mask_lo}
+    torch.set_num_threads(8)
+    random.seed(k_seed)
+    out, bufs = O.pp_where2comm_forward(p, args, dd, training=True, keep=keep)
+    loss = O.point_pillar_loss(out, lab, 1.0, 2.0)[0]
+    loss.backward()
+    flips = C.check_mask_ties(mask_lo, keep)
+    heads = C.engine_buf(model, "B.heads").permute(0, 3, 1, 2).cpu()
+    A = args["anchor_number"]
+    assert float((heads[:, :A] - out["psm"].detach()).abs().max()) < 1e-3
+    assert float((heads[:, A:8 * A] - out["rm"].detach()).abs().max()) < 1e-3
+    assert abs(float(loss3.sum()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
+    if flips == 0:
+        assert np.abs(heads[:, :A].numpy() - tg["train_psm"]).max() < 1e-3
+        assert abs(float(loss3.sum()) - float(tg["loss"])) < 1e-3 * float(tg["loss"])
+    errs = {}
+    for n, q in model.named_parameters():
+        if p[n].grad is None:
+            continue
+        errs[n] = float((q.grad.cpu() - p[n].grad).norm() / (p[n].grad.norm() + 1e-30))
+    assert len(errs) == 77
+    for n in ("cls_head.weight", "cls_head.bias", "reg_head.weight", "reg_head.bias"):
+        assert errs[n] < 1e-3, (n, errs[n])
+    assert max(errs.values()) < 0.15 and float(np.median(list(errs.values()))) < 0.05, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    # running statistics: block 0 twice, everything else once per pass (the oracle applies the reference's update counts)
+    for n, b in model.named_buffers():
+        if n in bufs and (flips == 0 or ".blocks.0." in n or "pfn_layers" in n):
+            assert float((b.cpu() - bufs[n]).abs().max()) < 1e-4, n
+    # the reference's own loop: model(batch) -> PointPillarLoss (torch ops) -> loss.backward()
+    g_step = {n: q.grad.clone() for n, q in model.named_parameters() if q.grad is not None}
+    model.load_state_dict(sd)
+    model.zero_grad()
+    random.seed(k_seed)
+    o2 = model(C.to_device(dd, "cuda"))
+    l2 = O.point_pillar_loss({"psm": o2["psm"].cpu(), "rm": o2["rm"].cpu()}, lab, 1.0, 2.0)[0]
+    assert abs(float(l2.detach()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
+    l2.backward()
+    for n, q in model.named_parameters():
+        if n in g_step:
+            assert float((q.grad - g_step[n]).abs().max()) <= 2e-3 * float(g_step[n].abs().max()) + 1e-7, n
