@@ -66,7 +66,7 @@ static int launch_tg(const TgParams& p, int n_col_tiles, cudaStream_t st) {
     int n_tiles = p.n_img * p.tiles_h * p.tiles_w * n_col_tiles;
     const int cap = g_debug[8] > 0 ? g_debug[8] : 148;  // persistent: one CTA per SM
     dim3 grid(n_tiles < cap ? n_tiles : cap, 1, 1);
-    tapgemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(p);
+    tapgemm_kernel<BN, STAGES><<<grid, 64 + TG_EPW * 32, L::TOTAL, st>>>(p);
     A2X_LAUNCHED();
     A2X_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -684,6 +684,7 @@ int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_w
     p.scale = scale;
     p.shift = shift;
     p.relu = relu;
+    if (g_debug[9]) p.relu = 77;  // debug: skip the epilogue stores (epilogue cost experiments)
     p.accumulate = accumulate;
     p.stats = stats;
     p.stat_c = s->cout;

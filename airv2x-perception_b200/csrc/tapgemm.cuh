@@ -27,6 +27,12 @@ constexpr int TG_BM = 128;  // pixels per tile (UMMA M)
 constexpr int TG_A_BYTES = TG_BM * 128;
 constexpr int TG_MAX_TAPS = 27;  // 9 window taps x 3 split products
 constexpr int TG_MAX_MAPS = 12;  // 4 parity views x {hi fp32, h16, l16}
+// Epilogue stores go through a per-warp shared-memory transpose: a thread owns one pixel ROW of the accumulator, so direct
+// stores would put 32 lanes on 32 different 128-byte lines, 16 bytes each (partial sectors: measured 3-4x slower than the
+// MMAs of a 1x1 / stride-2 tile). The transposed mapping gives every store instruction full 32-byte sectors: 4 lanes x 16 B
+// of one pixel's 16 fp32 columns, 2 lanes x 16 B of its 16 bf16 columns.
+constexpr int TG_XP_STRIDE = 20;                       // floats per row of the [32 pixels][16 columns] tile (+4 pad: conflict-free)
+constexpr int TG_XP_BYTES = 32 * TG_XP_STRIDE * 4;     // 2560 B per epilogue warp
 
 struct TgTap {
     int16_t map;   // which A tensor map
@@ -65,6 +71,8 @@ struct TgParams {
     int stat_c;
 };
 
+constexpr int TG_EPW = 8;   // epilogue warps of tapgemm_kernel: two per TMEM lane quadrant, alternating 32-column chunks
+
 template <int BN, int STAGES>
 struct TgSmem {
     static constexpr int B_BYTES = BN * 128;
@@ -72,7 +80,8 @@ struct TgSmem {
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int NBAR = 2 * STAGES + 4;  // full/empty per stage + tmem_full[2] + tmem_empty[2]
     static constexpr int STAT_OFF = BAR_OFF + NBAR * 8 + 16;
-    static constexpr int TOTAL = STAT_OFF + 4 * 2 * BN * 4 + 1024;  // [4 warps][2][BN] stats + alignment slack
+    static constexpr int XP_OFF = STAT_OFF + 4 * 2 * BN * 4;         // [4 warps][2][BN] stats, then the store-transpose tiles
+    static constexpr int TOTAL = XP_OFF + TG_EPW * TG_XP_BYTES + 1024;    // + alignment slack
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                      : (2 * BN <= 256) ? 256 : 512;  // two accumulator buffers
 };
@@ -116,17 +125,35 @@ struct TgEpi {
 };
 
 // Drain one 128 x BN accumulator (TMEM buffer at `tacc`) for the tile at (img, h0, w0), column offset n0.
-// Called by the 4 epilogue warps (128 threads); `q` = warp % 4 selects the TMEM lane quadrant.
-template <int BN>
+// Called by the EPW epilogue warps (EPW = 4: one per TMEM lane quadrant `q` = warp % 4; EPW = 8: two per quadrant, warp
+// half `qh` takes the 32-column chunks j = qh, qh + 2, ...). `et` = thread index among the epilogue threads.
+template <int BN, int EPW = 4>
 __device__ __forceinline__ void tg_epilogue(const TgEpi& e, uint32_t tacc, int q, int lane, int et, int img, int h0,
-                                            int w0, int tw_log2, int n0, float* sstat) {
+                                            int w0, int tw_log2, int n0, float* sstat, float* sT, int qh = 0) {
     const int row = q * 32 + lane;
     const int h = h0 + (row >> tw_log2);
     const int w = w0 + (row & ((1 << tw_log2) - 1));
     const bool valid = (h < e.gh) && (w < e.gw);
     const long long obase = (long long)img * e.osn + (long long)h * e.osh + (long long)w * e.osw;
+    // transposed store mappings (see TG_XP_STRIDE): the pixels this lane stores are fixed per tile
+    long long offA[4], offB[2];
+    unsigned validA = 0, validB = 0;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int prow = q * 32 + 8 * jj + (lane >> 2);
+        const int ph = h0 + (prow >> tw_log2), pw = w0 + (prow & ((1 << tw_log2) - 1));
+        validA |= (ph < e.gh && pw < e.gw ? 1u : 0u) << jj;
+        offA[jj] = (long long)img * e.osn + (long long)ph * e.osh + (long long)pw * e.osw + 4 * (lane & 3);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+        const int prow = q * 32 + 16 * jj + (lane >> 1);
+        const int ph = h0 + (prow >> tw_log2), pw = w0 + (prow & ((1 << tw_log2) - 1));
+        validB |= (ph < e.gh && pw < e.gw ? 1u : 0u) << jj;
+        offB[jj] = (long long)img * e.osn + (long long)ph * e.osh + (long long)pw * e.osw + 8 * (lane & 1);
+    }
 #pragma unroll 1
-    for (int j = 0; j < BN / 32; ++j) {
+    for (int j = qh; j < BN / 32; j += EPW / 4) {
         const int c0 = n0 + j * 32;
         if (c0 >= e.ncols) break;
         float v[32];
@@ -142,30 +169,106 @@ __device__ __forceinline__ void tg_epilogue(const TgEpi& e, uint32_t tacc, int q
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += __ldg(e.shift + cc + i);
         }
-        if (valid && e.relu != 77) {  // relu == 77: debug switch, skip the stores (epilogue cost experiment)
-            const long long off =
-                obase + (long long)(sub / e.sub_s) * e.sub_sh + (long long)(sub % e.sub_s) * e.sub_sw + cc;
-            if (e.accumulate) {
-                const float4* o4 = reinterpret_cast<const float4*>(e.out.hi + off);
+        const bool do_store = e.relu != 77;  // relu == 77: debug switch, skip the stores (epilogue cost experiment)
+        const long long sub_off = (long long)(sub / e.sub_s) * e.sub_sh + (long long)(sub % e.sub_s) * e.sub_sw + cc;
+        if (e.out.b16 == nullptr) {
+            // fp32 output only (data gradients): a thread's eight 16-byte stores cover one 128-byte line back to back and are
+            // merged on the way out; the direct row stores measured faster than the transpose here
+            if (valid && do_store) {
+                const long long off = obase + sub_off;
+                if (e.accumulate) {
+                    const float4* o4 = reinterpret_cast<const float4*>(e.out.hi + off);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 prev = o4[i];
-                    v[4 * i] += prev.x;
-                    v[4 * i + 1] += prev.y;
-                    v[4 * i + 2] += prev.z;
-                    v[4 * i + 3] += prev.w;
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 prev = o4[i];
+                        v[4 * i] += prev.x;
+                        v[4 * i + 1] += prev.y;
+                        v[4 * i + 2] += prev.z;
+                        v[4 * i + 3] += prev.w;
+                    }
+                }
+                if (e.relu == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                } else if (e.relu == 2) {  // exact (erf) GELU: nn.GELU() of the transformer feed-forward layers
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(e.out.hi + off + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+        } else {
+            // activation first when there is no residual (thread-per-row domain); with a residual it follows the add below
+            if (!e.accumulate) {
+                if (e.relu == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                } else if (e.relu == 2) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
                 }
             }
-            if (e.relu == 1) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            } else if (e.relu == 2) {  // exact (erf) GELU: nn.GELU() of the transformer feed-forward layers
+            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(sT + lane * TG_XP_STRIDE + 4 * i) =
+                        make_float4(v[16 * half + 4 * i], v[16 * half + 4 * i + 1], v[16 * half + 4 * i + 2], v[16 * half + 4 * i + 3]);
+                __syncwarp();
+                if (e.out.hi != nullptr) {
+                    // fp32 plane: lane -> (pixel 8 jj + lane / 4, columns 4 (lane % 4) .. + 3): 64 contiguous bytes per pixel
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int p = 8 * jj + (lane >> 2), f4 = lane & 3;
+                        const bool pvalid = (validA >> jj) & 1u;
+                        const long long poff = offA[jj] + sub_off + 16 * half;
+                        float4 x = *reinterpret_cast<const float4*>(sT + p * TG_XP_STRIDE + 4 * f4);
+                        if (e.accumulate) {
+                            if (pvalid) {
+                                const float4 prev = *reinterpret_cast<const float4*>(e.out.hi + poff);
+                                x.x += prev.x; x.y += prev.y; x.z += prev.z; x.w += prev.w;
+                            }
+                            if (e.relu == 1) {
+                                x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+                            } else if (e.relu == 2) {
+                                x.x = 0.5f * x.x * (1.f + erff(x.x * 0.70710678118654752f));
+                                x.y = 0.5f * x.y * (1.f + erff(x.y * 0.70710678118654752f));
+                                x.z = 0.5f * x.z * (1.f + erff(x.z * 0.70710678118654752f));
+                                x.w = 0.5f * x.w * (1.f + erff(x.w * 0.70710678118654752f));
+                            }
+                            *reinterpret_cast<float4*>(sT + p * TG_XP_STRIDE + 4 * f4) = x;   // the planes below split the sum
+                        }
+                        if (pvalid && do_store) *reinterpret_cast<float4*>(e.out.hi + poff) = x;
+                    }
+                    if (e.accumulate) __syncwarp();
+                }
+                // bf16 planes: lane -> (pixel 16 jj + lane / 2, columns 8 (lane % 2) .. + 7): one full 32-byte sector per pixel
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int p = 16 * jj + (lane >> 1), h8 = lane & 1;
+                    const bool pvalid = (validB >> jj) & 1u;
+                    const long long poff = offB[jj] + sub_off + 16 * half;
+                    const float4 a = *reinterpret_cast<const float4*>(sT + p * TG_XP_STRIDE + 8 * h8);
+                    const float4 b = *reinterpret_cast<const float4*>(sT + p * TG_XP_STRIDE + 8 * h8 + 4);
+                    __nv_bfloat162 h01 = __floats2bfloat162_rn(a.x, a.y), h23 = __floats2bfloat162_rn(a.z, a.w);
+                    __nv_bfloat162 h45 = __floats2bfloat162_rn(b.x, b.y), h67 = __floats2bfloat162_rn(b.z, b.w);
+                    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                    const float2 f45 = __bfloat1622float2(h45), f67 = __bfloat1622float2(h67);
+                    __nv_bfloat162 l01 = __floats2bfloat162_rn(a.x - f01.x, a.y - f01.y), l23 = __floats2bfloat162_rn(a.z - f23.x, a.w - f23.y);
+                    __nv_bfloat162 l45 = __floats2bfloat162_rn(b.x - f45.x, b.y - f45.y), l67 = __floats2bfloat162_rn(b.z - f67.x, b.w - f67.y);
+                    uint4 hp, lp;
+                    hp.x = *reinterpret_cast<uint32_t*>(&h01); hp.y = *reinterpret_cast<uint32_t*>(&h23);
+                    hp.z = *reinterpret_cast<uint32_t*>(&h45); hp.w = *reinterpret_cast<uint32_t*>(&h67);
+                    lp.x = *reinterpret_cast<uint32_t*>(&l01); lp.y = *reinterpret_cast<uint32_t*>(&l23);
+                    lp.z = *reinterpret_cast<uint32_t*>(&l45); lp.w = *reinterpret_cast<uint32_t*>(&l67);
+                    if (pvalid && do_store) {
+                        *reinterpret_cast<uint4*>(e.out.b16 + poff) = hp;
+                        *reinterpret_cast<uint4*>(e.out.b16 + e.out.ps + poff) = lp;
+                    }
+                }
+                __syncwarp();   // the tile is rewritten by the next half / chunk
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                store_split4(e.out, off + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
         }
         if (e.stats != nullptr) {  // warp-uniform
             float sq[32];
@@ -199,8 +302,8 @@ __device__ __forceinline__ void tg_epilogue(const TgEpi& e, uint32_t tacc, int q
         }
     }
     if (e.stats != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < BN; i += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(EPW * 32) : "memory");
+        for (int i = et; i < BN; i += EPW * 32) {
             const int col = n0 + i;
             if (col < e.ncols) {
                 const int ch = col % e.sub_c;
@@ -210,14 +313,14 @@ __device__ __forceinline__ void tg_epilogue(const TgEpi& e, uint32_t tacc, int q
                 atomicAdd(&e.stats[e.stat_c + ch], (double)t2);
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // sstat is reused by the next tile
+        asm volatile("bar.sync 1, %0;" ::"n"(EPW * 32) : "memory");  // sstat is reused by the next tile
     }
 }
 
 // Persistent: gridDim.x CTAs loop over (pixel tile, column tile) pairs; the smem ring runs across tiles and the
 // TMEM accumulator is double buffered, so the epilogue of tile i overlaps the MMAs of tile i + 1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ TgParams p) {
+__global__ void __launch_bounds__(64 + TG_EPW * 32) tapgemm_kernel(const __grid_constant__ TgParams p) {
     using L = TgSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -243,7 +346,7 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], 4);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty[b], TG_EPW);  // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -337,8 +440,9 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
             }
         }
     } else {
-        // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
+        // epilogue warps 2..9 -> TMEM lane quadrant (warp % 4), column-chunk half (warp - 2) / 4
         const int q = warp & 3;
+        const int qh = (warp - 2) >> 2;
         const int et = threadIdx.x - 64;
         TgEpi e;
         e.out = p.out; e.osn = p.osn; e.osh = p.osh; e.osw = p.osw; e.sub_c = p.sub_c; e.sub_s = p.sub_s;
@@ -356,7 +460,8 @@ __global__ void __launch_bounds__(192) tapgemm_kernel(const __grid_constant__ Tg
             const int buf = it & 1;
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            tg_epilogue<BN>(e, tmem_base + buf * BN, q, lane, et, img, th_i * TH, tw_i * TW, p.tw_log2, n0, sstat);
+            tg_epilogue<BN, TG_EPW>(e, tmem_base + buf * BN, q, lane, et, img, th_i * TH, tw_i * TW, p.tw_log2, n0, sstat,
+                                    reinterpret_cast<float*>(smem + L::XP_OFF + (warp - 2) * TG_XP_BYTES), qh);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);

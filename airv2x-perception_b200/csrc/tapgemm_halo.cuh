@@ -47,7 +47,8 @@ struct ThSmem {
     static constexpr int BAR_OFF = OFF_B + NB * B_BYTES;
     static constexpr int NBAR = 2 * TH_NA + 2 * NB + 4;
     static constexpr int STAT_OFF = BAR_OFF + NBAR * 8 + 16;
-    static constexpr int TOTAL = STAT_OFF + 4 * 2 * BN * 4 + 1024;
+    static constexpr int XP_OFF = STAT_OFF + 4 * 2 * BN * 4;
+    static constexpr int TOTAL = XP_OFF + 4 * TG_XP_BYTES + 1024;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                      : (2 * BN <= 256) ? 256 : 512;
 };
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(192) tapgemm_halo_kernel(const __grid_constant
             const int buf = it & 1;
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            tg_epilogue<BN>(e, tmem_base + buf * BN, q, lane, et, img, th_i * 16, tw_i * 8, 3, n0, sstat);
+            tg_epilogue<BN>(e, tmem_base + buf * BN, q, lane, et, img, th_i * 16, tw_i * 8, 3, n0, sstat,
+                            reinterpret_cast<float*>(smem + L::XP_OFF + q * TG_XP_BYTES));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
