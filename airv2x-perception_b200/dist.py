@@ -185,6 +185,8 @@ class AgentParallelCoBEVT:
         A, K = m.args["anchor_number"], m.args["num_class"]
         nc, nr = A * K, 7 * A
         nchw = heads.permute(0, 3, 1, 2)
+        # bytes this rank puts on the wire per scene: its shrunk fp32 map, read once by every peer
+        self.wire_bytes = int(heads.shape[1] * heads.shape[2] * eng.c_shrink * 4) * (self.world - 1)
         return {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A]}
 
 
@@ -254,4 +256,19 @@ class AgentParallelWhere2comm:
         lidar["raw"]["ego_flags"] = lay["ego_flags"]
         heads, aux = m.engine.forward_agent_parallel(m._param_dict(), lidar, lay, self.rank, self.world, buf, exchange, done)
         m._last_aux = aux
+        self._buf = buf
         return m._output_dict(heads, {"record_len": [self.world]})
+
+    @property
+    def wire_bytes(self):
+        """bytes this rank put on the wire in the last call, per peer x (world - 1): the NCCL transport gathers the whole
+        fixed-capacity buffer; the peer transport reads only the records the communication mask selected (header count x
+        (index + 64-float row)) plus the dense deeper levels. Reads one header word (host sync): call it outside timed loops."""
+        m = self.model
+        lay = self._state[0]
+        reg = m.engine.ap_regions(lay["ny"] // 2, lay["nx"] // 2)
+        if self.transport == "nccl":
+            return int(reg["total"] * 4) * (self.world - 1)
+        count = int(self._buf[reg["hdr"][0]:reg["hdr"][0] + 1].view(torch.int32).item())
+        dense = sum(v[1] for k, v in reg.items() if k.startswith("lvl"))
+        return int(64 * 4 + count * (4 + m.engine.num_filters[0] * 4) + dense * 4) * (self.world - 1)

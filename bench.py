@@ -419,7 +419,10 @@ def agent_parallel_child(args):
     blk = agent_parallel_block(torch, dist, dev, rank, world, args.precision)
     if rank == 0:
         print("AGENT_PARALLEL " + json.dumps(blk))
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -632,8 +635,11 @@ def main():
                                 "sample": r["sample"]}
     if rank == 0:
         print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # the step graph holds NCCL work: tearing the process group down under it was seen to hang at interpreter exit
+        sync_all()
+        os._exit(0)
 
 
 def roofline_pass(model, libmod, dd, lab, cw, rc, precision, torch):
