@@ -307,7 +307,8 @@ class Airv2xWhere2com(nn.Module):
     def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, k_list=None):
         """forward (train-mode BN) + PointPillarLossMultiClass + backward in one call, all on the CUDA kernels.
         Inputs may live on the host (pinned memory -> async H2D here) or on the device. Parameter gradients land
-        in p.grad; returns the device tensor [reg, cls, obj] loss terms (float64) — total = .sum()."""
+        in p.grad; returns the device tensor [reg, cls, obj] loss terms (float64) — total = .sum(). The tensor is the
+        engine's persistent buffer (a CUDA-graph replay writes it in place): `.clone()` it to keep a value across steps."""
         assert self.training, "train_step() needs model.train()"
         dev = next(self.parameters()).device
         layout = self._layout(data_dict, dev)
@@ -449,9 +450,14 @@ class Airv2xWhere2com(nn.Module):
         dd["raw_points"]["points"] = pts
         dd["raw_points"]["offsets"] = offs
         rng_state = random.getstate()  # warm-up / capture must not consume the caller's top-K random stream
+        # ... nor move the BatchNorm running statistics: the eager warm-up steps below really run (twice) on this batch
+        bn_state = {n: b.clone() for n, b in self.named_buffers()}
         for _ in range(2):  # eager warm-up: every buffer / stream / attribute exists before capture
             self.train_step(dd, labels, cw, rc)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            for n, b in self.named_buffers():
+                b.copy_(bn_state[n])
         from ... import _lib
 
         lib = _lib.load()
