@@ -183,6 +183,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
+// 8-column variant
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // the store twin of tmem_ld_32x32: thread t of the warp writes 32 consecutive fp32 columns of TMEM lane (base_lane + t)
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {

@@ -495,7 +495,7 @@ int a2x_window_attention_fwd(const float* qkv, const float* bias_table, const in
         const int num_windows = B * (H / window) * (W / window);
         const int smem_tc = wt_smem_bytes(n, false);
         A2X_CHECK_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
-        window_attention_tc_kernel<false><<<wt_grid(num_windows, heads, 1), 384, smem_tc, st>>>(q, num_windows);
+        window_attention_tc_kernel<false><<<wt_grid(num_windows, heads, 1), WT_THREADS, smem_tc, st>>>(q, num_windows);
         A2X_LAUNCHED();
         A2X_CHECK_CUDA(cudaGetLastError());
         return 0;
@@ -1096,7 +1096,7 @@ int a2x_window_attention_bwd_split(const float* qkv, const float* dout, const fl
         const int num_windows = B * (H / window) * (W / window);
         const int smem_tc = a2x::wt_smem_bytes(n, true);
         A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
-        a2x::window_attention_tc_kernel<true><<<a2x::wt_grid(num_windows, heads, 1), 384, smem_tc, st0>>>(q, num_windows);
+        a2x::window_attention_tc_kernel<true><<<a2x::wt_grid(num_windows, heads, 1), a2x::WT_THREADS, smem_tc, st0>>>(q, num_windows);
         A2X_LAUNCHED();
         A2X_CHECK_CUDA(cudaGetLastError());
         return 0;

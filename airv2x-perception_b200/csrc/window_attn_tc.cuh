@@ -5,8 +5,8 @@
 //
 // A persistent CTA owns one head and walks over windows. Two warpgroups: the LOADER (warps 4-7) gathers the q / k / v (/ dO)
 // rows of the next window from global memory, splits them and fills one of two tile buffers; the COMPUTE group (warps
-// 0-7: threads r and r + 128 share token r = TMEM lane r and take 64 score columns / 16 output features each, exchanging
-// the row max / sum / D through shared memory) issues the MMAs, runs the softmax and the epilogue. full / empty mbarriers
+// 0-7: WT_NS = 2 threads r, r + 128 share token r = TMEM lane r and take 64 score columns / 16 output features each,
+// exchanging the row max / sum / D through shared memory) issues the MMAs, runs the softmax and the epilogue. full / empty mbarriers
 // per buffer (empty is arrived by tcgen05.commit of the window's last MMA), so global latency is off the compute path.
 // Every operand is the bf16 split pair of an fp32 row, kept side by side in ONE 128-byte shared-memory row
 // [hi(32) | lo(32)] with the 128-byte swizzle, so a tile is simply 128 rows x 128 B and the UMMA descriptors decide how
@@ -32,7 +32,11 @@ namespace a2x {
 constexpr int WT_W = 4;             // window edge
 constexpr int WT_S2 = 2 * WT_W - 1;
 constexpr int WT_DH = 32;
-constexpr int WT_AUX = 4096 + 4096 + 2 * 1024 + 256 + 3072;   // bias | bias gradient | token tables (2) | barriers, TMEM slot | row max / sum / D exchange
+constexpr int WT_NS = 2;                    // compute threads per score row (4 measured no faster: the chain is sync / MMA latency)
+constexpr int WT_CPT = 128 / WT_NS;         // score columns per thread
+constexpr int WT_DPT = WT_DH / WT_NS;       // output features per thread
+constexpr int WT_THREADS = 128 * (WT_NS + 1);
+constexpr int WT_AUX = 4096 + 4096 + 2 * 1024 + 256 + 3 * WT_NS * 512;   // bias | bias gradient | token tables (2) | barriers, TMEM slot | row max / sum / D exchange
 
 struct WinTcParams {
     const float* qkv;      // [B*L][H][W][3*D]
@@ -89,7 +93,7 @@ __device__ __forceinline__ long long wt_token(const WinTcParams& p, int b, int x
 }
 
 __device__ __forceinline__ void wt_bar_load() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-__device__ __forceinline__ void wt_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void wt_bar() { asm volatile("bar.sync 1, %0;" ::"n"(128 * WT_NS) : "memory"); }
 
 // NT tensors' rows (32 floats each, tensor k at `src[k]` + token * rs[k]) -> [hi | lo] tiles at tile0 + toff[k].
 // ALL global loads of the window are issued before the first conversion (n * 4 <= 512 items of 32 B per tensor for the
@@ -98,31 +102,38 @@ template <int NT>
 __device__ __forceinline__ void wt_load_tiles(uint8_t* tile0, const uint32_t (&toff)[NT], const float* const (&src)[NT],
                                               const long long (&rs)[NT], const float (&scale)[NT],
                                               const long long* sTok, int n, int tl) {
-    float4 a[NT][4], b[NT][4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int idx = tl + it * 128;
-        if (idx < n * 4) {
-            const long long tok = sTok[idx >> 2];
-#pragma unroll
-            for (int k = 0; k < NT; ++k) {
-                const float4* g = reinterpret_cast<const float4*>(src[k] + tok * rs[k] + (idx & 3) * 8);
-                a[k][it] = __ldg(g);
-                b[k][it] = __ldg(g + 1);
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < NT; ++k) {
+    for (int k0 = 0; k0 < NT; k0 += 2) {      // two tensors (16 float4 registers) in flight at a time
+        float4 a[2][4], b[2][4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int idx = tl + it * 128;
             if (idx < n * 4) {
-                float4 x = a[k][it], y = b[k][it];
-                const float sc = scale[k];
-                x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
-                y.x *= sc; y.y *= sc; y.z *= sc; y.w *= sc;
-                wt_store8_hl(tile0 + toff[k], idx >> 2, idx & 3, x, y);
+                const long long tok = sTok[idx >> 2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (k0 + k < NT) {
+                        const float4* g = reinterpret_cast<const float4*>(src[k0 + k] + tok * rs[k0 + k] + (idx & 3) * 8);
+                        a[k][it] = __ldg(g);
+                        b[k][it] = __ldg(g + 1);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k0 + k < NT) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int idx = tl + it * 128;
+                    if (idx < n * 4) {
+                        float4 x = a[k][it], y = b[k][it];
+                        const float sc = scale[k0 + k];
+                        x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
+                        y.x *= sc; y.y *= sc; y.z *= sc; y.w *= sc;
+                        wt_store8_hl(tile0 + toff[k0 + k], idx >> 2, idx & 3, x, y);
+                    }
+                }
             }
         }
     }
@@ -156,25 +167,31 @@ __device__ __forceinline__ void wt_mma_pv(uint32_t tacc, uint32_t plane_addr, ui
     }
 }
 
-// this thread's half (columns 64 h .. 64 h + 63) of score row r from TMEM (+ relative-position bias, key mask) -> s[64];
-// returns the maximum over the half
+// this thread's share (columns CPT h .. CPT h + CPT - 1) of score row r from TMEM (+ relative-position bias, key mask)
+// -> s[CPT]; returns the maximum over the share
 __device__ __forceinline__ float wt_scores(uint32_t trow, int n, int r, int h, uint32_t kmask, const float* sB, int L, float* s) {
-    const int j0 = 64 * h;
-    if (j0 < n) tmem_ld_32x32(trow + j0, s);
-    if (j0 + 32 < n) tmem_ld_32x32(trow + j0 + 32, s + 32);
+    const int j0 = WT_CPT * h;
+#pragma unroll
+    for (int c = 0; c < WT_CPT / 32; ++c)
+        if (j0 + 32 * c < n) tmem_ld_32x32(trow + j0 + 32 * c, s + 32 * c);
     tmem_ld_wait();
     const int li = r >> 4, i1 = (r >> 2) & 3, i2 = r & 3;
-    const int base = ((li + L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - 4 * h * WT_S2 * WT_S2;
+    const int base = ((li + L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - (WT_CPT / 16) * h * WT_S2 * WT_S2;
     float m = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < 64; ++jj) {
+    for (int jj = 0; jj < WT_CPT; ++jj) {
         const int sub = ((jj >> 4) * WT_S2 + ((jj >> 2) & 3)) * WT_S2 + (jj & 3);
-        const bool ok = j0 + jj < n && ((kmask >> (4 * h + (jj >> 4))) & 1u);
+        const bool ok = j0 + jj < n && ((kmask >> ((WT_CPT / 16) * h + (jj >> 4))) & 1u);
         const float v = ok ? s[jj] + sB[base - sub] : -INFINITY;
         s[jj] = v;
         m = fmaxf(m, v);
     }
     return m;
+}
+
+__device__ __forceinline__ void wt_tmem_ld_dpt(uint32_t taddr, float* v) {
+    if constexpr (WT_DPT == 16) tmem_ld_32x16(taddr, v);
+    else tmem_ld_32x8(taddr, v);
 }
 
 __device__ __forceinline__ uint32_t wt_kmask(const WinTcParams& p, int b) {
@@ -196,7 +213,7 @@ struct WtSmem {
     long long* sTok;      // [2][128]
     uint64_t *full, *empty, *mma;
     uint32_t* tmem_slot;
-    float* sEx;           // [3][2][128]: row max | row sum | D, one value per (half, row)
+    float* sEx;           // [3][NS][128]: row max | row sum | D, one value per (column share, row)
 };
 __device__ __forceinline__ WtSmem wt_carve(uint8_t* raw, int tiles_bytes) {
     WtSmem w;
@@ -214,7 +231,7 @@ __device__ __forceinline__ WtSmem wt_carve(uint8_t* raw, int tiles_bytes) {
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTcParams p, int num_windows) {
+__global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(const WinTcParams p, int num_windows) {
     extern __shared__ uint8_t wt_raw[];
     const int n = p.L * 16;
     const uint32_t TS = (uint32_t)n * 128;
@@ -227,7 +244,7 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
     const int head = blockIdx.x % p.heads;
     const int G = gridDim.x / p.heads;
     const int nb = (2 * p.L - 1) * WT_S2 * WT_S2;
-    for (int i = tid; i < nb; i += 384) {
+    for (int i = tid; i < nb; i += WT_THREADS) {
         sm.sB[i] = p.bias[i * p.heads + head];
         sm.sdB[i] = 0.f;
     }
@@ -246,9 +263,9 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
     tc_fence_after();
     const uint32_t tmem = *sm.tmem_slot;
 
-    if (warp >= 8) {
+    if (warp >= 4 * WT_NS) {
         // ------------------------------------------------------------------ loader warpgroup
-        const int tl = tid - 256;
+        const int tl = tid - 128 * WT_NS;
         int it = 0;
         for (int win = blockIdx.x / p.heads; win < num_windows; win += G, ++it) {
             const int buf = it & 1;
@@ -263,7 +280,7 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
                 const float* const src[4] = {q0, q0 + D, q0 + 2 * D, p.dout + head * WT_DH};
                 const long long rs[4] = {3LL * D, 3LL * D, 3LL * D, (long long)D};
                 const float sc[4] = {p.scale, 1.f, 1.f, 1.f};
-                wt_load_tiles<4>(tb, toff, src, rs, sc, sm.sTok + buf * 128, n, tl);
+                wt_load_tiles<4>(tb, toff, src, rs, sc, sm.sTok + buf * 128, n, tl);   // loads of 2 tensors in flight at a time
             } else {
                 const uint32_t toff[3] = {0, TS, 4 * TS};
                 const float* const src[3] = {q0, q0 + D, q0 + 2 * D};
@@ -275,24 +292,24 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
             mbar_arrive(&sm.full[buf]);
         }
     } else {
-        // ------------------------------------------------------------------ compute warpgroups (two threads per row)
+        // ------------------------------------------------------------------ compute warpgroups (WT_NS threads per row)
         const int r = tid & 127, h = tid >> 7;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)n, 0, 0);
         const int nk = n >> 4;
         const int li = r >> 4, i1 = (r >> 2) & 3, i2 = r & 3;
-        const int bbase = ((li + p.L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - 4 * h * WT_S2 * WT_S2;
-        const uint32_t tacc = trow + 256 + 64 * h;   // backward: this thread's 64 columns of sum_windows dS (bias gradient)
-        float* exM = sm.sEx;            // [2][128] row max
-        float* exS = sm.sEx + 256;      // row sum
-        float* exD = sm.sEx + 512;      // D
-        const bool live = 64 * h < n;   // this half holds keys (n <= 64: the second half idles through the barriers)
+        const int bbase = ((li + p.L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - (WT_CPT / 16) * h * WT_S2 * WT_S2;
+        const uint32_t tacc = trow + 256 + WT_CPT * h;   // backward: this thread's columns of sum_windows dS (bias gradient)
+        float* exM = sm.sEx;                       // [NS][128] row max
+        float* exS = sm.sEx + WT_NS * 128;         // row sum
+        float* exD = sm.sEx + 2 * WT_NS * 128;     // D
+        const bool live = WT_CPT * h < n;          // this share holds keys (small n: the other shares idle through the barriers)
         if (BWD) {
             float z[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) z[j] = 0.f;
-            tmem_st_32x32(tacc, z);
-            tmem_st_32x32(tacc + 32, z);
+#pragma unroll
+            for (int c = 0; c < WT_CPT / 32; ++c) tmem_st_32x32(tacc + 32 * c, z);
             tmem_st_wait();
         }
         uint32_t ph = 0;
@@ -314,13 +331,15 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
             mbar_wait(sm.mma, ph);
             ph ^= 1;
             tc_fence_after();
-            float s[64];
+            float s[WT_CPT];
             exM[h * 128 + r] = wt_scores(trow, n, r, h, kmask, sm.sB, p.L, s);
             wt_bar();
-            const float m = fmaxf(exM[r], exM[128 + r]);
+            float m = exM[r];
+#pragma unroll
+            for (int k = 1; k < WT_NS; ++k) m = fmaxf(m, exM[k * 128 + r]);
             float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
+            for (int j = 0; j < WT_CPT; ++j) {
                 s[j] = __expf(s[j] - m);
                 sum += s[j];
             }
@@ -329,8 +348,8 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
                 // every thread has read its S columns and the S MMAs have retired: P may overwrite Q / K, O may overwrite S
                 if (r < n && live) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (64 * h + c * 8 < n) wt_store8_planes(tb, TS, r, 8 * h + c, s + c * 8);   // tiles have n rows: no row >= n
+                    for (int c = 0; c < WT_CPT / 8; ++c)
+                        if (WT_CPT * h + c * 8 < n) wt_store8_planes(tb, TS, r, (WT_CPT / 8) * h + c, s + c * 8);   // tiles have n rows: no row >= n
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -341,41 +360,47 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
                     umma_commit(sm.mma);
                     umma_commit(&sm.empty[buf]);
                 }
-                const float inv = 1.f / (exS[r] + exS[128 + r]);
+                float tot = exS[r];
+#pragma unroll
+                for (int k = 1; k < WT_NS; ++k) tot += exS[k * 128 + r];
+                const float inv = 1.f / tot;
                 mbar_wait(sm.mma, ph);
                 ph ^= 1;
                 tc_fence_after();
-                float oh[16], ol[16];          // features 16 h .. 16 h + 15: (P Vh) and (P Vl) halves of the accumulator
-                tmem_ld_32x16(trow + 16 * h, oh);
-                tmem_ld_32x16(trow + 32 + 16 * h, ol);
+                float oh[WT_DPT], ol[WT_DPT];  // features DPT h .. DPT h + DPT - 1: (P Vh) and (P Vl) halves of the accumulator
+                wt_tmem_ld_dpt(trow + WT_DPT * h, oh);
+                wt_tmem_ld_dpt(trow + 32 + WT_DPT * h, ol);
                 tmem_ld_wait();
                 if (r < n) {
-                    const long long off = tok * D + head * WT_DH + 16 * h;
+                    const long long off = tok * D + head * WT_DH + WT_DPT * h;
 #pragma unroll
-                    for (int c = 0; c < 16; c += 4)
+                    for (int c = 0; c < WT_DPT; c += 4)
                         store_split4(p.out, off + c, make_float4((oh[c] + ol[c]) * inv, (oh[c + 1] + ol[c + 1]) * inv,
                                                                  (oh[c + 2] + ol[c + 2]) * inv, (oh[c + 3] + ol[c + 3]) * inv));
                 }
             } else {
                 wt_bar();
-                const float inv = 1.f / (exS[r] + exS[128 + r]);
+                float tot = exS[r];
 #pragma unroll
-                for (int j = 0; j < 64; ++j) s[j] *= inv;                        // P
+                for (int k = 1; k < WT_NS; ++k) tot += exS[k * 128 + r];
+                const float inv = 1.f / tot;
+#pragma unroll
+                for (int j = 0; j < WT_CPT; ++j) s[j] *= inv;                    // P
                 if (r < n && live) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (64 * h + c * 8 < n) wt_store8_planes(tP, TS, r, 8 * h + c, s + c * 8);
+                    for (int c = 0; c < WT_CPT / 8; ++c)
+                        if (WT_CPT * h + c * 8 < n) wt_store8_planes(tP, TS, r, (WT_CPT / 8) * h + c, s + c * 8);
                 }
-                float Dv = 0.f;                                                   // this half of D_i = sum_j P_ij dP_ij
+                float Dv = 0.f;                                                   // this share of D_i = sum_j P_ij dP_ij
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (64 * h + c * 32 < n) {
+                for (int c = 0; c < WT_CPT / 32; ++c) {
+                    if (WT_CPT * h + c * 32 < n) {
                         float dp[32];
-                        tmem_ld_32x32(trow + 128 + 64 * h + c * 32, dp);
+                        tmem_ld_32x32(trow + 128 + WT_CPT * h + c * 32, dp);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (64 * h + c * 32 + j < n) Dv = fmaf(s[c * 32 + j], dp[j], Dv);   // TMEM columns >= n are stale (may be NaN)
+                            if (WT_CPT * h + c * 32 + j < n) Dv = fmaf(s[c * 32 + j], dp[j], Dv);   // TMEM columns >= n are stale (may be NaN)
                     }
                 }
                 exD[h * 128 + r] = Dv;
@@ -387,27 +412,29 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
                     wt_mma_pv(tmem, smem_u32(tP), tb_a + 3 * TS, TS, nk, 1);      // dV = P^T dO  -> columns [0, 64) (S is in registers)
                     umma_commit(sm.mma);
                 }
-                Dv = exD[r] + exD[128 + r];
+                Dv = exD[r];
+#pragma unroll
+                for (int k = 1; k < WT_NS; ++k) Dv += exD[k * 128 + r];
                 mbar_wait(sm.mma, ph);                                            // dV done: the planes may take dS
                 ph ^= 1;
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (64 * h + c * 32 < n) {
+                for (int c = 0; c < WT_CPT / 32; ++c) {
+                    if (WT_CPT * h + c * 32 < n) {
                         float dp[32], ac[32];
-                        tmem_ld_32x32(trow + 128 + 64 * h + c * 32, dp);
+                        tmem_ld_32x32(trow + 128 + WT_CPT * h + c * 32, dp);
                         tmem_ld_32x32(tacc + c * 32, ac);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float ds = 64 * h + c * 32 + j < n ? s[c * 32 + j] * (dp[j] - Dv) : 0.f;   // dS_ij (0 at masked keys)
+                            const float ds = WT_CPT * h + c * 32 + j < n ? s[c * 32 + j] * (dp[j] - Dv) : 0.f;   // dS_ij (0 at masked keys)
                             dp[j] = ds;
                             ac[j] += ds;
                         }
                         tmem_st_32x32(tacc + c * 32, ac);
                         if (r < n)
 #pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) wt_store8_planes(tP, TS, r, 8 * h + c * 4 + c8, dp + c8 * 8);
+                            for (int c8 = 0; c8 < 4; ++c8) wt_store8_planes(tP, TS, r, (WT_CPT / 8) * h + c * 4 + c8, dp + c8 * 8);
                     }
                 }
                 tmem_st_wait();
@@ -427,15 +454,15 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
                 tc_fence_after();
 #pragma unroll
                 for (int part = 0; part < 3; ++part) {                            // 0: dV, 1: dK, 2: dQ
-                    float oh[16], ol[16];
-                    tmem_ld_32x16(trow + part * 64 + 16 * h, oh);
-                    tmem_ld_32x16(trow + part * 64 + 32 + 16 * h, ol);
+                    float oh[WT_DPT], ol[WT_DPT];
+                    wt_tmem_ld_dpt(trow + part * 64 + WT_DPT * h, oh);
+                    wt_tmem_ld_dpt(trow + part * 64 + 32 + WT_DPT * h, ol);
                     tmem_ld_wait();
                     if (r < n) {
                         const float f = part == 2 ? p.scale : 1.f;
-                        const long long off = tok * (3 * D) + (2 - part) * D + head * WT_DH + 16 * h;
+                        const long long off = tok * (3 * D) + (2 - part) * D + head * WT_DH + WT_DPT * h;
 #pragma unroll
-                        for (int c = 0; c < 16; c += 4)
+                        for (int c = 0; c < WT_DPT; c += 4)
                             store_split4(p.out, off + c, make_float4((oh[c] + ol[c]) * f, (oh[c + 1] + ol[c + 1]) * f,
                                                                      (oh[c + 2] + ol[c + 2]) * f, (oh[c + 3] + ol[c + 3]) * f));
                     }
@@ -447,8 +474,8 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
         if (BWD) {
             // fold the per-thread columns of sum dS into the head's table (entry of (i, j) = bbase_i - sub_j)
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (64 * h + c * 32 < n) {
+            for (int c = 0; c < WT_CPT / 32; ++c) {
+                if (WT_CPT * h + c * 32 < n) {
                     float ac[32];
                     tmem_ld_32x32(tacc + c * 32, ac);
                     tmem_ld_wait();
@@ -456,7 +483,7 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int jj = c * 32 + j;
-                            if (64 * h + jj < n && ac[j] != 0.f)
+                            if (WT_CPT * h + jj < n && ac[j] != 0.f)
                                 atomicAdd(&sm.sdB[bbase - (((jj >> 4) * WT_S2 + ((jj >> 2) & 3)) * WT_S2 + (jj & 3))], ac[j]);
                         }
                     }
@@ -467,7 +494,7 @@ __global__ void __launch_bounds__(384, 1) window_attention_tc_kernel(const WinTc
     tc_fence_before();
     __syncthreads();
     if (BWD)
-        for (int i = tid; i < nb; i += 384)
+        for (int i = tid; i < nb; i += WT_THREADS)
             if (sm.sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sm.sdB[i]);
     if (warp == 0) tmem_dealloc<TM_COLS>(tmem);
 }

@@ -310,6 +310,9 @@ class Airv2xWhere2com(nn.Module):
         in p.grad; returns the device tensor [reg, cls, obj] loss terms (float64) — total = .sum(). The tensor is the
         engine's persistent buffer (a CUDA-graph replay writes it in place): `.clone()` it to keep a value across steps."""
         assert self.training, "train_step() needs model.train()"
+        if self.args.get("backbone_fix", False):
+            raise NotImplementedError("backbone_fix: true freezes everything but fusion_net (airv2x_where2com.py:84-92), which "
+                                      "has no trainable parameter on this path: there is nothing to train")
         dev = next(self.parameters()).device
         layout = self._layout(data_dict, dev)
         lidar = self._lidar(data_dict, dev, layout)
