@@ -72,7 +72,12 @@ class PointPillarWhere2comm(nn.Module):
         return d
 
     def _inputs(self, data_dict, dev):
-        lid = data_dict[self.modality]
+        """-> (lidar dict, layout). B200 extension of the boundary (like the airv2x models): data_dict["raw_points"] =
+        {"points" [sum P, 4] f32 ego-frame clouds in agent order, "offsets" int32 [N+1], "preprocess": hypes["preprocess"],
+        "filter": True -> the dataset's mask_ego_points (ego = first agent of a scene) + mask_points_by_range on the GPU}
+        instead of the CPU-voxelised `processed_lidar`; voxelisation then runs on the GPU, bit-exact."""
+        raw = data_dict.get("raw_points")
+        lid = None if raw is not None else data_dict[self.modality]
         r = data_dict["record_len"]
         record_len = [int(v) for v in (r.tolist() if torch.is_tensor(r) else r)]
         key = tuple(record_len)
@@ -86,6 +91,17 @@ class PointPillarWhere2comm(nn.Module):
                               scene_start=torch.tensor(start, dtype=torch.int32, device=dev),
                               scene_len=torch.tensor(record_len, dtype=torch.int32, device=dev))
         layout = cache[key]
+        if raw is not None:
+            pre = raw["preprocess"]
+            starts = set(int(v) for v in np.concatenate([[0], np.cumsum(record_len)[:-1]]))
+            ego = torch.tensor([1 if i in starts else 0 for i in range(layout["n_total"])], dtype=torch.uint8, device=dev)
+            return {"raw": {"points": raw["points"].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(),
+                            "offsets": raw["offsets"].to(device=dev, dtype=torch.int32, non_blocking=True).contiguous(),
+                            "voxel_size": pre["args"]["voxel_size"], "lidar_range": pre["cav_lidar_range"],
+                            "max_points": pre["args"]["max_points_per_voxel"],
+                            "max_voxels": pre["args"]["max_voxel_train" if self.training else "max_voxel_test"],
+                            "filter": bool(raw.get("filter", False)), "transforms": None,
+                            "ego_flags": ego if raw.get("filter", False) else None}}, layout
         lidar = {"voxel_features": lid["voxel_features"].to(device=dev, dtype=torch.float32).contiguous(),
                  "voxel_num_points": lid["voxel_num_points"].to(device=dev, dtype=torch.int32).contiguous(),
                  "voxel_coords": lid["voxel_coords"].to(device=dev, dtype=torch.int32).contiguous()}

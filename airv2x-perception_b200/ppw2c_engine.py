@@ -107,6 +107,14 @@ class LegacyW2CEngine(W2CEngine):
         self._canvas_nz = nzc
         geom = ops.pfn_geom(self.args["voxel_size"], self.args["lidar_range"], nx, ny)
         pre = "pillar_vfe.pfn_layers.0"
+        seg = None
+        if "raw" in lidar:   # raw clouds: voxelise on the GPU (shared per-agent slabs, one segment list over all agents)
+            raw = dict(lidar["raw"])
+            raw["types"] = ["vehicle"] * n_total
+            lay = dict(layout)
+            lay["agent_map"] = {"vehicle": layout["identity_map"]}
+            lidar = self._voxelize(raw, lay)["vehicle"]
+            seg = lidar["seg"]
         vox, num, coords = lidar["voxel_features"], lidar["voxel_num_points"], lidar["voxel_coords"]
         w = P[pre + ".linear.weight"]
         scale, shift = self._buf("pfn.scale", (64,)), self._buf("pfn.shift", (64,))
@@ -114,20 +122,21 @@ class LegacyW2CEngine(W2CEngine):
         if training:   # batch statistics over all M*32 rows from the moments (PFNLayer, airv2x_pillar_vfe.py:27-49 = pillar_vfe.py)
             mean, invstd = self._buf("pfn.mean", (64,)), self._buf("pfn.invstd", (64,))
             moments = self._buf("pfn.moments", (65,), torch.float64)
-            ops.pfn_moments(vox, num, coords, geom, moments)
+            ops.pfn_moments(vox, num, coords, geom, moments, seg=seg)
             rows = vox.shape[0] * 32
             ops.pfn_stats_finalize(moments, rows, w, P[pre + ".norm.weight"], P[pre + ".norm.bias"], 1,
-                                   P[pre + ".norm.running_mean"], P[pre + ".norm.running_var"], scale, shift, mean, invstd)
+                                   P[pre + ".norm.running_mean"], P[pre + ".norm.running_var"], scale, shift, mean, invstd,
+                                   seg=seg)
             amax = self._buf("pfn.amax", (vox.shape[0], 64), torch.uint8)
-            ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax, nz=nzc, write_hi=hi)
+            ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax, nz=nzc, write_hi=hi, seg=seg)
             if record is not None:
                 record.append(dict(kind="pfn", type="all", vox=vox, num=num, coords=coords, geom=geom, pre=pre, scale=scale,
                                    shift=shift, mean=mean, invstd=invstd, amap=amap, amax=amax, moments=moments, rows=rows,
-                                   seg=None))
+                                   seg=seg))
         else:
             ops.bn_eval_affine(P[pre + ".norm.weight"], P[pre + ".norm.bias"], P[pre + ".norm.running_mean"],
                                P[pre + ".norm.running_var"], scale, shift)
-            ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, nz=nzc, write_hi=hi)
+            ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, nz=nzc, write_hi=hi, seg=seg)
         return canvas
 
     def _shrink_heads(self, P, W, cat, tag, heads_only_cls=False):

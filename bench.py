@@ -2,11 +2,12 @@
 """bench.py — scenes/sec (forward + backward) of the collaborative-perception hot path on B200.
 
     python bench.py --gpus N --steps K --warmup W            # headline: BASELINE.json configs[1] (= --config 2)
-    python bench.py --config {2,3,4,5} ...                    # the other BASELINE configs, same JSON contract
+    python bench.py --config {1,2,3,4,5} ...                  # the other BASELINE configs, same JSON contract
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm (oracle port) on the host CPUs
 
   config 2 (default)  airv2x_intermediate_where2com.yaml, 5 agents (2 veh, 2 rsu, 1 drone) x 60k points, 200 x 704 BEV
-  (config 1, point_pillar_where2comm at 2 agents x 8k points / 128 x 128, is the CPU-runnable parity case: tests/, not a bench line)
+  config 1            point_pillar_where2comm (legacy registry name), 2 agents x 8k points, 128 x 128 BEV, train step with
+                      PointPillarLoss (the reference's CPU-runnable plumbing case)
   config 3            airv2x_intermediate_v2xvit.yaml, 5 agents x 60k points
   config 4            airv2x_intermediate_cobevt.yaml (FuseBEVT), 5 agents x 60k points on one GPU; under torchrun the
                       agent-per-GPU mode (N agents = N ranks, one exchange of the BEV maps) is timed as well
@@ -123,8 +124,9 @@ WORKLOADS = {
             workload="airv2x_intermediate_where2com.yaml with the lidar range set to +-100.8 m (504x504 BEV, config 5's "
                      "grid), lidar branch only, 5 agents x 60k pts, train-mode fwd + loss + bwd"),
     1: dict(cfg="ppw2c_small_config.json", module="point_pillar_where2comm", cls="PointPillarWhere2comm",
-            agents=["vehicle", "vehicle"], n_points=8000, metric="scenes/sec point_pillar_where2comm 2-agent 8k-pt",
-            workload="point_pillar_where2comm (legacy registry name), 2 agents x 8k pts, 128x128 BEV (PR1 plumbing case)"),
+            agents=["vehicle", "vehicle"], n_points=8000, metric="scenes/sec (fwd+bwd) point_pillar_where2comm 2-agent 8k-pt",
+            workload="point_pillar_where2comm (legacy registry name, V2XR_where2comm.yaml args), 2 agents x 8k pts, 128x128 BEV, "
+                     "train-mode fwd + PointPillarLoss + bwd (BASELINE config 1: the reference's CPU-runnable plumbing case)"),
 }
 
 
@@ -253,6 +255,8 @@ class Workload:
         pts, offs = make_raw_scene(self.cfg, seed, self.agents, w["n_points"])
         self.pts, self.offs = pts, offs
         self.dd_host = data_dict_from_raw(pts, offs, self.cfg, torch, pin=True, agents=self.agents)
+        if self.legacy:
+            self.dd_host["record_len"] = torch.tensor([len(self.agents)], dtype=torch.int32)
         self.dd_dev = {k: (dict(v) if isinstance(v, dict) else v) for k, v in self.dd_host.items()}
         self.dd_dev["raw_points"] = dict(self.dd_host["raw_points"])
         self.dd_dev["raw_points"]["points"] = self.dd_host["raw_points"]["points"].to(dev)
@@ -270,12 +274,13 @@ class Workload:
         # labels: planted boxes -> GPU anchor-target assignment (what train_loop.Trainer does per batch)
         pp = self.cfg["postprocess"]
         TA = a2x_import.pkg("labels").TargetAssigner
-        box, mask, cls = synth_boxes(3 + seed, pp["anchor_args"]["cav_lidar_range"])
+        box, mask, cls = synth_boxes(3 + seed, pp["anchor_args"]["cav_lidar_range"], n_gt=6 if self.legacy else 20)
         lab = TA(pp, dev)(box[None], mask[None], cls[None])
         self.n_pos = int(lab["pos_equal_one"].sum().item())
-        self.lab_dev = {k: lab[k] for k in ("targets", "pos_equal_one", "class_ids")}
+        self.lab_dev = {k: lab[k] for k in (("targets", "pos_equal_one") if self.legacy else ("targets", "pos_equal_one", "class_ids"))}
         self.lab_host = {k: v.cpu().pin_memory() for k, v in self.lab_dev.items()}
-        self.cw, self.rc = self.cfg["loss_args"]["cls_weight"], self.cfg["loss_args"]["reg"]
+        la = self.cfg.get("loss_args", {"cls_weight": 1.0, "reg": 2.0})
+        self.cw, self.rc = la["cls_weight"], la["reg"]
         self.h2d_bytes = int(pts.nbytes + offs.nbytes + sum(v.numel() * v.element_size() for v in self.lab_host.values()))
 
     def train_step(self, dd=None, lab=None):
@@ -431,7 +436,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="split3", choices=["split3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -452,8 +457,9 @@ def main():
     metric = spec["metric"]
     graphed = args.config == 2 and not args.no_graph
     config = {"workload": spec["workload"],
-              "labels": "20 planted boxes -> labels.TargetAssigner (GPU generate_label_airv2x)",
-              "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
+              "labels": "%d planted boxes -> labels.TargetAssigner (GPU generate_label_airv2x)" % (6 if args.config == 1 else 20),
+              "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush" if args.config != 1 else
+                    "config 1 is the small plumbing case (launch-bound, working set < L2): not a bandwidth claim",
               "launch": "cuda-graph replay of the fused step" if graphed else "eager"}
 
     if args.impl == "reference":
@@ -488,16 +494,13 @@ def main():
     W = Workload(args.config, torch, dev, seed=rank, precision=args.precision)
     model = W.model
     dd_dev, lab_dev, dd_host, lab_host, cw, rc = W.dd_dev, W.lab_dev, W.dd_host, W.lab_host, W.cw, W.rc
-    if W.legacy:
-        model.eval()
-    else:
-        model.train()
+    model.train()
     # data-parallel over scenes (the reference's DDP, tools/train.py:161-163): average parameter gradients. Where2comm
     # reduces INSIDE its fused step (two buckets, the big one overlapped with the level-0 backward, all of it part of the
     # captured CUDA graph); the transformer models reduce one flat buffer after their step.
     grad_sync = "none (1 GPU)"
     allreduce_grads = lambda: None
-    if world > 1 and not W.legacy:
+    if world > 1:
         if args.config in (2, 5) and not args.post_grad_sync:
             model.attach_grad_sync()
             grad_sync = "in-step: 2 buckets on one flat gradient buffer, NCCL AVG, bucket 0 overlapped with the level-0 backward"
@@ -505,17 +508,12 @@ def main():
             allreduce_grads = a2x_import.pkg("dist").GradAverager(p for p in model.parameters() if p.requires_grad)
             grad_sync = "after the step: one NCCL AVG all-reduce of the flat gradient buffer"
 
-    if W.legacy:
-        def step(dd, lab):
-            with torch.no_grad():
-                return model(dd)["psm"].sum().double().reshape(1)
-    else:
-        step_fn = model.train_step_graphed if graphed else model.train_step
+    step_fn = model.train_step_graphed if graphed else model.train_step
 
-        def step(dd, lab):
-            loss3 = step_fn(dd, lab, cw, rc)
-            allreduce_grads()
-            return loss3
+    def step(dd, lab):
+        loss3 = step_fn(dd, lab, cw, rc)
+        allreduce_grads()
+        return loss3
 
     def sync_all():
         if world > 1:
@@ -601,11 +599,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16x3 (3-pass bf16-split tensor-core GEMMs, fp32 accumulate, fp32-equivalent to 1e-4; fp32 elsewhere)"
             if args.precision == "split3" else "tf32", "data": "synthetic", "config": config,
             "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "scenes/s", "h2d_bytes_per_step": W.h2d_bytes,
-                    "d2h_bytes_per_step": 24 if not W.legacy else 8, "ms_per_step": ms_e2e,
+                    "d2h_bytes_per_step": 24, "ms_per_step": ms_e2e,
                     "api": "model.stage_inputs(host dicts) + model.train_step_staged().result(): H2D of step i+1 overlaps "
-                           "step i, loss D2H read one step late" if graphed else
-                           ("model(host dicts) [eval forward: the legacy models' training step is reported by config 2-5]"
-                            if W.legacy else "model.train_step(host dicts)")},
+                           "step i, loss D2H read one step late" if graphed else "model.train_step(host dicts)"},
             "gpu_launches": int(launches), "loss": loss_val, "label_positives": W.n_pos, "grad_sync": grad_sync,
             "clocks": clk.summary()}
     if args.config == 2 and not args.no_extra:

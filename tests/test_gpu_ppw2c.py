@@ -114,3 +114,48 @@ def test_train_step_matches_reference_golden():
     for n, q in model.named_parameters():
         if n in g_step:
             assert float((q.grad - g_step[n]).abs().max()) <= 2e-3 * float(g_step[n].abs().max()) + 1e-7, n
+
+
+def test_raw_point_boundary_equals_voxel_dict_boundary():
+    """raw ego-frame clouds in (GPU voxeliser + the dataset's point filters) == the CPU-voxelised `processed_lidar` dict,
+    eval logits and the training step's loss, for the legacy model"""
+    import random
+
+    import a2x_import
+    from oracle import w2c_oracle as O
+
+    M = a2x_import.pkg("opencood.models.point_pillar_where2comm")
+    cfg, gold = T.load()
+    model = M.PointPillarWhere2comm(cfg["model_args"])
+    sd = T.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().eval()
+    pre = cfg["preprocess"]
+    n_agents, n_points, seed = int(gold["n_agents"]), int(gold["n_points"]), int(gold["scene_seed"])
+    clouds = [O.synth_points(seed * 100 + k, n_points, pre["cav_lidar_range"], sigma_xy=(8.0, 8.0)) for k in range(n_agents)]
+    offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    raw = {"raw_points": {"points": torch.from_numpy(np.concatenate(clouds, 0)), "offsets": torch.from_numpy(offs),
+                          "preprocess": pre, "filter": True},
+           "record_len": torch.tensor([n_agents], dtype=torch.int32)}
+    dd = T.golden_scene(cfg, gold)
+    with torch.no_grad():
+        a = model(raw)
+        b = model(C.to_device(dd, "cuda"))
+    for k in ("psm", "rm"):
+        assert torch.equal(a[k], b[k]), k
+    assert a["comm_rate"] == b["comm_rate"]
+    # training step: same loss through both boundaries (the train cap of the voxeliser is not hit at this size). The two
+    # boundaries list the pillars in different orders (cell order vs first-seen order), so the train-mode BatchNorm batch
+    # sums round differently: fp32 summation-order tolerance, not bit equality
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(T.ROOT, "scripts"))
+    import make_golden_legacy_train as G
+    model.train()
+    lab = G.labels(a["psm"].shape[2], a["psm"].shape[3], cfg["model_args"]["anchor_number"])
+    random.seed(3)
+    l_raw = model.train_step(raw, lab, 1.0, 2.0).clone()
+    model.load_state_dict(sd)
+    random.seed(3)
+    l_dd = model.train_step(C.to_device(dd, "cuda"), lab, 1.0, 2.0).clone()
+    assert torch.allclose(l_raw, l_dd, rtol=1e-4)
