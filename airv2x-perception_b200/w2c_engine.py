@@ -11,6 +11,7 @@ memory, streams and tiny parameter concatenations. Mirrors
 opencood/models/airv2x_where2com.py:117-179 and where2comm_modules/where2comm_fuse.py:198-263 with the redundant
 second backbone evaluation (airv2x_where2com.py:124) folded into a repeated running-stat update.
 """
+import os
 import random
 
 import torch
@@ -74,8 +75,9 @@ class W2CEngine:
         self.side = None  # second stream: weight gradients run beside the data-gradient chain (fills idle SMs)
         self.use_side_stream = True
         # BN backward pass 1 inside the producing data-gradient epilogue: correct (tests) but measured SLOWER on B200
-        # (8.79 vs 8.24 ms per step: the dgrad epilogue is on the critical path, the separate pass overlaps) -> off
-        self.fuse_bn_bwd_reduce = False
+        # (round 1: 8.79 vs 8.24 ms per step; round 2 with the 8-warp transposed epilogue: 7.21 vs 6.80 ms — the dgrad
+        # epilogue is on the critical path, the separate pass overlaps) -> off unless A2X_FUSE_BN_BWD=1
+        self.fuse_bn_bwd_reduce = os.environ.get("A2X_FUSE_BN_BWD", "0") == "1"
         self.k_on_device = False
 
     # ------------------------------------------------------------------ buffers
