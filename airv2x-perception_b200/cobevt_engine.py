@@ -285,9 +285,8 @@ class CoBEVTEngine(W2CEngine):
             for part, grid_mode in (("window", False), ("grid", True)):
                 pa, pf = self._sub(i, part, "attention"), self._sub(i, part, "ffd")
                 tag = "%d%s" % (i, part[0])
-                # attention sublayer
-                xin = self._buf("sv.xin.a" + tag, X.shape)
-                xin.copy_(X)
+                # attention sublayer: x_new = x + dropout(to_out(att)) in the GEMM epilogue, written to a fresh buffer so that
+                # the sublayer's input (LayerNorm backward needs it) is kept without a copy
                 ln = self._act("sv.ln.a" + tag, X.shape)
                 ops.layernorm_fwd(X, P[pa + ".norm.weight"], P[pa + ".norm.bias"], ln)
                 qkv = self._buf("sv.qkv." + tag, X.shape[:3] + (3 * d,))
@@ -295,18 +294,12 @@ class CoBEVTEngine(W2CEngine):
                 att = self._act("sv.att." + tag, X.shape)
                 ops.window_attention_fwd(qkv, P[pa + ".fn.relative_position_bias_table.weight"], key_mask, B, self.L,
                                          self.heads, self.fa["dim_head"], self.fa["window_size"], grid_mode, att)
-                site_o = None
-                if drop is None:
-                    ops.linear_fwd(att, W[pa + ".fn.to_out.0.weight"], Act(X), accumulate=True)
-                else:   # x += dropout(to_out(att))
-                    tmp = self._buf("fax.tmp", X.shape)
-                    ops.linear_fwd(att, W[pa + ".fn.to_out.0.weight"], Act(tmp))
-                    site_o = drop.site()
-                    ops.dropout_apply(tmp, drop, site_o, Act(X), residual=X)
-                subs.append(dict(kind="att", pre=pa, xin=xin, ln=ln, qkv=qkv, att=att, grid=grid_mode, site_o=site_o))
-                # feed-forward sublayer (pre-activation kept in fp32: GELU' needs it)
-                xin = self._buf("sv.xin.f" + tag, X.shape)
-                xin.copy_(X)
+                site_o = drop.site() if drop is not None else None
+                Xn = self._buf("sv.x.a" + tag, X.shape)
+                ops.linear_dropout_residual_fwd(att, W[pa + ".fn.to_out.0.weight"], Xn, residual=X, drop=drop, site=site_o or 0)
+                subs.append(dict(kind="att", pre=pa, xin=X, ln=ln, qkv=qkv, att=att, grid=grid_mode, site_o=site_o))
+                X = Xn
+                # feed-forward sublayer (pre-activation kept in fp32: GELU' needs it): x_new = x + dropout(W2 dropout(gelu(pre)) + b2)
                 ln = self._act("sv.ln.f" + tag, X.shape)
                 ops.layernorm_fwd(X, P[pf + ".norm.weight"], P[pf + ".norm.bias"], ln)
                 pre = self._buf("sv.pre." + tag, X.shape[:3] + (self.fa["mlp_dim"],))
@@ -315,15 +308,15 @@ class CoBEVTEngine(W2CEngine):
                 site_h = site_o = None
                 if drop is None:
                     ops.gelu_fwd(pre, hid)
-                    ops.linear_fwd(hid, W[pf + ".fn.net.3.weight"], Act(X), bias=P[pf + ".fn.net.3.bias"], accumulate=True)
-                else:   # x += dropout(W2 dropout(gelu(pre)) + b2)
+                else:
                     site_h = drop.site()
                     ops.gelu_dropout_fwd(pre, drop, site_h, hid)
-                    tmp = self._buf("fax.tmp", X.shape)
-                    ops.linear_fwd(hid, W[pf + ".fn.net.3.weight"], Act(tmp), bias=P[pf + ".fn.net.3.bias"])
                     site_o = drop.site()
-                    ops.dropout_apply(tmp, drop, site_o, Act(X), residual=X)
-                subs.append(dict(kind="ffn", pre=pf, xin=xin, ln=ln, hpre=pre, hid=hid, site_h=site_h, site_o=site_o))
+                Xn = self._buf("sv.x.f" + tag, X.shape)
+                ops.linear_dropout_residual_fwd(hid, W[pf + ".fn.net.3.weight"], Xn, bias=P[pf + ".fn.net.3.bias"], residual=X,
+                                                drop=drop, site=site_o or 0)
+                subs.append(dict(kind="ffn", pre=pf, xin=X, ln=ln, hpre=pre, hid=hid, site_h=site_h, site_o=site_o))
+                X = Xn
         m = self._act("fax.mean", (B, h2, w2, d))
         ops.agent_mean_layernorm(X, B, self.L, P["fusion_net.mlp_head.2.weight"], P["fusion_net.mlp_head.2.bias"], m)
         fused = self._act("fax.fused", (B, h2, w2, d))

@@ -585,6 +585,11 @@ static int grid_for(long long total) {
 
 using namespace a2x;
 
+static int conv2d_fwd_impl(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
+                           const float* scale, const float* shift, int relu, int accumulate, double* stats,
+                           const float* residual, unsigned long long seed, unsigned int site, float drop_p,
+                           long long elem0, a2x_stream_t stream);
+
 extern "C" {
 
 int a2x_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, float* w_fwd, void* w_fwd16,
@@ -653,6 +658,28 @@ int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weig
 int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
                       const float* scale, const float* shift, int relu, int accumulate, double* stats,
                       a2x_stream_t stream) {
+    return conv2d_fwd_impl(s, x, w, y, scale, shift, relu, accumulate, stats, nullptr, 0ull, 0u, 0.f, 0, stream);
+}
+
+int a2x_linear_dropout_residual_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, float* y, int y_cs,
+                                    const float* bias, const float* residual, unsigned long long seed, unsigned int site,
+                                    float p, long long elem_offset, a2x_stream_t stream) {
+    A2X_REQUIRE(s && s->ksize == 1 && s->stride == 1 && y && y_cs == s->cout && p >= 0.f && p < 1.f && elem_offset >= 0 &&
+                    elem_offset % 8 == 0,
+                "linear_dropout_residual_fwd: a token-wise linear (ksize 1, stride 1) with a dense fp32 output, 0 <= p < 1, "
+                "elem_offset a multiple of 8");
+    a2x_output out{};
+    out.hi = y;
+    out.cs = y_cs;
+    return conv2d_fwd_impl(s, x, w, &out, nullptr, bias, 0, 0, nullptr, residual, seed, site, p, elem_offset, stream);
+}
+
+}  // extern "C"
+
+static int conv2d_fwd_impl(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
+                           const float* scale, const float* shift, int relu, int accumulate, double* stats,
+                           const float* residual, unsigned long long seed, unsigned int site, float drop_p,
+                           long long elem0, a2x_stream_t stream) {
     if (int r = check_shape(s, false)) return r;
     A2X_REQUIRE(relu >= 0 && relu <= 2, "conv2d_fwd: activation must be 0 (none), 1 (ReLU) or 2 (GELU)");
     if (int r = check_operand(x, s->cin, "conv2d_fwd x")) return r;
@@ -663,6 +690,8 @@ int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_w
     const int kk = s->ksize * s->ksize;
     A2X_REQUIRE(!stats || (!scale && !shift && !relu && !accumulate),
                 "conv2d_fwd: fused statistics are of the raw conv output");
+    A2X_REQUIRE((!residual && drop_p == 0.f) || (s->ksize == 1 && !y->b16 && !relu && !accumulate),
+                "conv2d_fwd: the dropout / residual epilogue is the fp32-only token-wise linear one");
     if (s->ksize == 3 && s->stride == 1 && g_debug[7] != 1)
         return run_halo(x, s->n, s->h, s->w, s->cin, s->cout, w, +1, y, scale, shift, relu, accumulate, stats,
                         (cudaStream_t)stream);
@@ -688,8 +717,16 @@ int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_w
     p.accumulate = accumulate;
     p.stats = stats;
     p.stat_c = s->cout;
+    p.res = residual;
+    p.drop.seed = seed;
+    p.drop_elem0 = elem0;
+    p.drop.site = site;
+    p.drop.thresh = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;   // same rounding as dropout.cu
+    p.drop.scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     return run_tg(p, ho, wo, s->n, s->cout, (cudaStream_t)stream);
 }
+
+extern "C" {
 
 int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
                      int accumulate, a2x_stream_t stream) {

@@ -20,6 +20,7 @@
 //  airv2x_where2com.py:59-69).
 #pragma once
 #include "a2x_ptx.cuh"
+#include "philox.cuh"
 
 namespace a2x {
 
@@ -69,6 +70,11 @@ struct TgParams {
     // fused BatchNorm batch statistics of the raw result: stats[ch] += sum, stats[stat_c + ch] += sum of squares
     double* stats;
     int stat_c;
+    // x + dropout(linear(y) + bias) of the transformer sublayers in ONE epilogue (fp32-only outputs): `res` is the residual
+    // (same addressing as the output, may be a different buffer), drop.thresh != 0 turns the Philox mask on
+    const float* res;
+    DropArgs drop;
+    long long drop_elem0;   // mask element index of the output's element 0 (the output may be a slice of the site's tensor)
 };
 
 constexpr int TG_EPW = 8;   // epilogue warps of tapgemm_kernel: two per TMEM lane quadrant, alternating 32-column chunks
@@ -122,6 +128,9 @@ struct TgEpi {
     const float* bshift;
     const float* bmean;
     const float* binvstd;
+    const float* res;       // residual read from here instead of the output's own fp32 plane (fp32-only outputs)
+    DropArgs drop;          // thresh != 0: v *= keep / (1 - p) before the residual add
+    long long drop_elem0;   // mask element index = drop_elem0 + output offset
 };
 
 // Drain one 128 x BN accumulator (TMEM buffer at `tacc`) for the tile at (img, h0, w0), column offset n0.
@@ -176,8 +185,17 @@ __device__ __forceinline__ void tg_epilogue(const TgEpi& e, uint32_t tacc, int q
             // merged on the way out; the direct row stores measured faster than the transpose here
             if (valid && do_store) {
                 const long long off = obase + sub_off;
-                if (e.accumulate) {
-                    const float4* o4 = reinterpret_cast<const float4*>(e.out.hi + off);
+                if (e.drop.thresh != 0) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float m[8];
+                        drop_mult8(e.drop, ((e.drop_elem0 + off) >> 3) + g, m);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[8 * g + k] *= m[k];
+                    }
+                }
+                if (e.accumulate || e.res != nullptr) {
+                    const float4* o4 = reinterpret_cast<const float4*>((e.res != nullptr ? e.res : e.out.hi) + off);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 prev = o4[i];
@@ -448,6 +466,7 @@ __global__ void __launch_bounds__(64 + TG_EPW * 32) tapgemm_kernel(const __grid_
         e.out = p.out; e.osn = p.osn; e.osh = p.osh; e.osw = p.osw; e.sub_c = p.sub_c; e.sub_s = p.sub_s;
         e.sub_sh = p.sub_sh; e.sub_sw = p.sub_sw; e.ncols = p.ncols; e.scale = p.scale; e.shift = p.shift;
         e.relu = p.relu; e.accumulate = p.accumulate; e.stats = p.stats; e.stat_c = p.stat_c; e.gh = p.gh; e.gw = p.gw;
+        e.res = p.res; e.drop = p.drop; e.drop_elem0 = p.drop_elem0;
         e.bz = nullptr; e.bscale = e.bshift = e.bmean = e.binvstd = nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {

@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(192) tapgemm_halo_kernel(const __grid_constant
         e.out = p.out; e.osn = p.osn; e.osh = p.osh; e.osw = p.osw; e.sub_c = 1 << 30; e.sub_s = 1;
         e.sub_sh = 0; e.sub_sw = 0; e.ncols = p.ncols; e.scale = p.scale; e.shift = p.shift;
         e.relu = p.relu; e.accumulate = p.accumulate; e.stats = p.stats; e.stat_c = p.stat_c; e.gh = p.gh; e.gw = p.gw;
+        e.res = nullptr; e.drop.thresh = 0; e.drop_elem0 = 0;
         e.bz = p.bz; e.bscale = p.bscale; e.bshift = p.bshift; e.bmean = p.bmean; e.binvstd = p.binvstd;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {

@@ -253,6 +253,20 @@ def linear_fwd(x, w, out, bias=None, act=0, accumulate=False):
     return conv_fwd(x, w, 1, 1, out, shift=bias, relu=act, accumulate=accumulate)
 
 
+def linear_dropout_residual_fwd(x, w, y, bias=None, residual=None, drop=None, site=0, elem_offset=0):
+    """y (dense fp32 tensor) = residual + dropout(x W^T + bias) in the GEMM epilogue; the mask is the one
+    dropout_mask(.., drop, site) exports, element elem_offset + i for y's element i (y a slice of the site's tensor).
+    residual may be y itself; drop None: no dropout."""
+    n, h, ww, cin = x.shape
+    cout = w.f32.shape[1]
+    assert y.is_contiguous() and y.shape[3] == cout and (residual is None or residual.shape == y.shape)
+    sh = _shape(n, h, ww, cin, cout, 1, 1)
+    call("a2x_linear_dropout_residual_fwd", ctypes.byref(sh), _op(x), ctypes.byref(w.fwd), _ptr(y), c_int(cout), _ptr(bias),
+         _ptr(residual), ctypes.c_ulonglong(drop.seed if drop is not None else 0), ctypes.c_uint(site),
+         c_f(drop.p if drop is not None else 0.0), c_ll(elem_offset), stream_ptr())
+    return y
+
+
 # transformer fusion token kernels --------------------------------------------------------------------------------
 def _rows(t):
     return t.shape[0] * t.shape[1] * t.shape[2]

@@ -284,8 +284,6 @@ class V2XViTEngine(CoBEVTEngine):
             tag = "sv%d." % d
             sv = {}
             # HGT multi-agent attention
-            sv["xin_h"] = self._buf(tag + "xin_h", X.shape)
-            sv["xin_h"].copy_(X)
             ln = sv["ln_h"] = self._act(tag + "ln_h", X.shape)
             ops.layernorm_fwd(X, P[hg + ".norm.weight"], P[hg + ".norm.bias"], ln)
             qkv = sv["hqkv"] = self._buf(tag + "hqkv", (N, h, w, 5 * C))
@@ -296,17 +294,17 @@ class V2XViTEngine(CoBEVTEngine):
             for b in range(B):
                 s, e = starts[b], starts[b] + record_len[b]
                 ops.hgt_attention_fwd(qkv[s:e], types_dev[s:e], kmask[s:e], ca["heads"], ca["dim_head"], att.narrow_n(s, e - s))
-            if dropc is None:
-                for s, e, t in runs:
-                    ops.linear_fwd(att.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], Act(X[s:e]),
-                                   bias=P["%s.a_linears.%d.bias" % (f, t)], accumulate=True)
-            else:   # x += dropout(a_linear(att))
-                tmp = self._buf("vit.tmp", X.shape)
-                for s, e, t in runs:
-                    ops.linear_fwd(att.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], Act(tmp[s:e]),
-                                   bias=P["%s.a_linears.%d.bias" % (f, t)])
+            # x_new = x + dropout(a_linear(att)) in the GEMM epilogue, into a fresh buffer: the sublayer input is kept (LayerNorm
+            # backward) without a copy; the per-type slices index the site's mask by their offset in the whole tensor
+            if dropc is not None:
                 sv["site_h"] = dropc.site()
-                ops.dropout_apply(tmp, dropc, sv["site_h"], Act(X), residual=X)
+            Xn = self._buf(tag + "x_h", X.shape)
+            for s, e, t in runs:
+                ops.linear_dropout_residual_fwd(att.narrow_n(s, e - s), W["%s.a_linears.%d.weight" % (f, t)], Xn[s:e],
+                                                bias=P["%s.a_linears.%d.bias" % (f, t)], residual=X[s:e], drop=dropc,
+                                                site=sv.get("site_h", 0), elem_offset=s * h * w * C)
+            sv["xin_h"] = X
+            X = Xn
             # pyramid window attention + split attention
             sv["xin_p"] = self._buf(tag + "xin_p", X.shape)
             sv["xin_p"].copy_(X)
@@ -321,10 +319,10 @@ class V2XViTEngine(CoBEVTEngine):
                 watt = self._act(tag + "watt%d" % lv, X.shape)
                 ops.window_attention_fwd(wqkv, table, None, N, 1, hh, dh, ws, False, watt)
                 win = self._buf(tag + "win%d" % lv, (N, h, w, C))
-                ops.linear_fwd(watt, W[bp_l + ".to_out.0.weight"], Act(win), bias=P[bp_l + ".to_out.0.bias"])
                 if dropw is not None:
                     sv.setdefault("site_w", []).append(dropw.site())
-                    ops.dropout_apply(win, dropw, sv["site_w"][-1], Act(win))
+                ops.linear_dropout_residual_fwd(watt, W[bp_l + ".to_out.0.weight"], win, bias=P[bp_l + ".to_out.0.bias"],
+                                                drop=dropw, site=sv["site_w"][-1] if dropw is not None else 0)
                 sv["wqkv"].append(wqkv)
                 sv["watt"].append(watt)
                 sv["win"].append(win)
@@ -334,8 +332,6 @@ class V2XViTEngine(CoBEVTEngine):
             ops.split_attn_fuse(sv["win"][0], sv["win"][1], sv["win"][2], P[sp + ".fc1.weight"], P[sp + ".bn1.weight"],
                                 P[sp + ".bn1.bias"], P[sp + ".fc2.weight"], sv["sa_sums"], sv["sa_w"], X)
             # feed forward (pre-activation kept in fp32: GELU' needs it)
-            sv["xin_f"] = self._buf(tag + "xin_f", X.shape)
-            sv["xin_f"].copy_(X)
             ln = sv["ln_f"] = self._act(tag + "ln_f", X.shape)
             ops.layernorm_fwd(X, P[lp + ".1.norm.weight"], P[lp + ".1.norm.bias"], ln)
             pre = sv["hpre"] = self._buf(tag + "hpre", (N, h, w, enc["feed_forward"]["mlp_dim"]))
@@ -343,14 +339,15 @@ class V2XViTEngine(CoBEVTEngine):
             hid = sv["hid"] = self._act(tag + "hid", pre.shape)
             if dropf is None:
                 ops.gelu_fwd(pre, hid)
-                ops.linear_fwd(hid, W[lp + ".1.fn.net.3.weight"], Act(X), bias=P[lp + ".1.fn.net.3.bias"], accumulate=True)
-            else:   # x += dropout(W2 dropout(gelu(pre)) + b2)
+            else:   # x_new = x + dropout(W2 dropout(gelu(pre)) + b2)
                 sv["site_f1"] = dropf.site()
                 ops.gelu_dropout_fwd(pre, dropf, sv["site_f1"], hid)
-                tmp = self._buf("vit.tmp", X.shape)
-                ops.linear_fwd(hid, W[lp + ".1.fn.net.3.weight"], Act(tmp), bias=P[lp + ".1.fn.net.3.bias"])
                 sv["site_f2"] = dropf.site()
-                ops.dropout_apply(tmp, dropf, sv["site_f2"], Act(X), residual=X)
+            Xn = self._buf(tag + "x_f", X.shape)
+            ops.linear_dropout_residual_fwd(hid, W[lp + ".1.fn.net.3.weight"], Xn, bias=P[lp + ".1.fn.net.3.bias"], residual=X,
+                                            drop=dropf, site=sv.get("site_f2", 0))
+            sv["xin_f"] = X
+            X = Xn
             layers.append(sv)
         fused = self._act("vit.fused", (B, h, w, C))
         ones = self._buf("vit.ones", (B,), torch.int32)

@@ -121,6 +121,15 @@ int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weig
 int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
                       const float* scale, const float* shift, int act, int accumulate, double* stats,
                       a2x_stream_t stream);
+/* y = residual + dropout(x W^T + bias): the residual sublayers of the transformer fusion networks in train mode
+ * (PreNormResidual around Attention.to_out = Linear + Dropout, swap_fusion_modules.py:40-45,127; FeedForward's second
+ * Linear + Dropout, cobevt_modules/base_transformer.py:27-41; v2xvit_modules/base_transformer.py:17-46) in the GEMM's
+ * epilogue. ksize = stride = 1; y dense fp32 [n][h][w][cout] (y_cs == cout). The mask element of y's element i is
+ * elem_offset + i of the site (a2x_dropout_mask exports it): elem_offset != 0 when y is a slice of the site's tensor
+ * (the per-type a_linears of HGT, hmsa.py:150-156). residual may be null or alias y; p == 0: no dropout. */
+int a2x_linear_dropout_residual_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, float* y, int y_cs,
+                                    const float* bias, const float* residual, unsigned long long seed, unsigned int site,
+                                    float p, long long elem_offset, a2x_stream_t stream);
 /* dx (+)= conv_transpose(dy, w)   (dx: fp32 NHWC, pixel stride dx_cs) */
 int a2x_conv2d_dgrad(const a2x_conv_shape* s, const a2x_operand* dy, const a2x_weights* w, float* dx, int dx_cs,
                      int accumulate, a2x_stream_t stream);

@@ -374,6 +374,30 @@ def test_dropout_kernels_and_train_step_with_identical_masks(ops):
     (F.gelu(xx) * mk / 0.7).backward(r)
     ops.gelu_dropout_bwd(r, x, d3, 5, out)
     assert torch.allclose(out.hi, xx.grad, rtol=1e-4, atol=1e-5)
+    # (ii-b) x + dropout(linear(y) + bias) in the GEMM epilogue == the two-pass form under the exported mask, also when the
+    # output is a slice of the site's tensor (elem_offset) and without residual
+    tok = torch.randn(3, 10, 24, 128, generator=g).cuda()
+    wl, bl = (torch.randn(64, 128, generator=g) * 0.1).cuda(), torch.randn(64, generator=g).cuda()
+    res = torch.randn(3, 10, 24, 64, generator=g).cuda()
+    pw = ops.pack_conv_weight(wl.view(64, 128, 1, 1))
+    mk = ops.dropout_mask(res.numel(), d3, 9).view(res.shape).float()
+    lin = ops.Act.empty(res.shape, "cuda", False)
+    ops.linear_fwd(ops.split(tok), pw, lin, bias=bl)
+    want = res + lin.hi * mk / 0.7
+    y = torch.empty_like(res)
+    ops.linear_dropout_residual_fwd(ops.split(tok), pw, y, bias=bl, residual=res, drop=d3, site=9)
+    assert torch.allclose(y, want, rtol=1e-6, atol=1e-6)
+    y2 = torch.zeros_like(res)
+    ops.linear_dropout_residual_fwd(ops.split(tok).narrow_n(1, 2), pw, y2[1:3], bias=bl, residual=res[1:3], drop=d3, site=9,
+                                    elem_offset=res[0].numel())
+    assert torch.equal(y2[1:3], y[1:3]) and float(y2[0].abs().max()) == 0.0
+    ops.linear_dropout_residual_fwd(ops.split(tok), pw, y2, bias=bl, drop=d3, site=9)
+    assert torch.allclose(y2, lin.hi * mk / 0.7, rtol=1e-6, atol=1e-6)
+    ops.linear_dropout_residual_fwd(ops.split(tok), pw, y2, bias=bl, residual=res)              # no dropout: plain residual
+    assert torch.allclose(y2, res + lin.hi, rtol=1e-6, atol=1e-6)
+    yy = res.clone()
+    ops.linear_dropout_residual_fwd(ops.split(tok), pw, yy, bias=bl, residual=yy, drop=d3, site=9)   # residual aliases the output
+    assert torch.equal(yy, y)
     # (iii) the training step with dropout ON
     M = a2x_import.pkg("opencood.models.airv2x_cobevt")
     cfg, gold = CC.load_small()
