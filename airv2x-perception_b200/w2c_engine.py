@@ -311,13 +311,15 @@ class W2CEngine:
         # split mode: the canvas only feeds the block-0 tap-GEMM, which reads the bf16 planes -> the fp32 plane is neither
         # cleared nor written, and `spatial_features.count_nonzero()` (airv2x_where2com.py:122) is counted by the scatter
         hi = canvas.b16 is None
-        if hi:
-            canvas.hi.zero_()
-        else:
-            canvas.b16.zero_()
         nzc = self._buf("canvas.nz", (1,), torch.int64)
-        nzc.zero_()
+        with self._on_side():   # the clears (180 MB of canvas planes) run beside the voxeliser / PFN statistics; joined before the scatter
+            if hi:
+                canvas.hi.zero_()
+            else:
+                canvas.b16.zero_()
+            nzc.zero_()
         self._canvas_nz = nzc
+        joined = False
         if "raw" in lidar:
             lidar = self._voxelize(lidar["raw"], layout)
         for t in AGENT_TYPES:
@@ -344,6 +346,9 @@ class W2CEngine:
                                        P[pre + ".norm.running_mean"], P[pre + ".norm.running_var"], scale, shift, mean,
                                        invstd, seg=seg)
                 amax = self._buf("pfn.%s.amax" % t, (vox.shape[0], 64), torch.uint8)
+                if not joined:
+                    self._join_side()
+                    joined = True
                 ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, amax=amax, seg=seg, nz=nzc, write_hi=hi)
                 if record is not None:
                     record.append(dict(kind="pfn", type=t, vox=vox, num=num, coords=coords, geom=geom, pre=pre,
@@ -352,7 +357,12 @@ class W2CEngine:
             else:
                 ops.bn_eval_affine(P[pre + ".norm.weight"], P[pre + ".norm.bias"], P[pre + ".norm.running_mean"],
                                    P[pre + ".norm.running_var"], scale, shift)
+                if not joined:
+                    self._join_side()
+                    joined = True
                 ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, seg=seg, nz=nzc, write_hi=hi)
+        if not joined:
+            self._join_side()
         return canvas
 
     # ------------------------------------------------------------------ forward
@@ -362,10 +372,12 @@ class W2CEngine:
         Returns heads [B, H/2, W/2, 32] (NHWC, channels cls|reg|obj|pad) and an aux dict of device scalars."""
         self._begin_step()
         rec = [] if training else None
-        W = self._pack_weights(P)
+        with self._on_side():   # the weight re-layout (0.1 ms) runs beside the voxeliser / PFN; _encode joins before its scatter
+            W = self._pack_weights(P)
         record_len = layout["record_len"]
         B, N = len(record_len), layout["n_total"]
         canvas = self._encode(P, lidar, layout, training, rec)
+        self._join_side()   # the packed weights (a subclass's _encode may not have joined)
         nz = self._buf("comm_rate", (1,), torch.int64)
         nz.copy_(self._canvas_nz)
 
