@@ -253,15 +253,29 @@ class CoBEVTEngine(W2CEngine):
             with self._on_side():
                 self._deblock(P, W, i, x, cat.slice_c(c0, c0 + self.up_filters[i]), True, 1, "E", rec)
         self._join_side()
-        assert not self.compression, "NaiveCompressor training is not implemented"
         assert self.shrink_k0 == 1 and self.shrink_stride == 1, "training of the legacy shrink header is not implemented"
         y1 = self._act("E.s1", (N, h2, w2, self.c_shrink))
-        y2 = self._buf("E.s2", (N, h2, w2, self.c_shrink))
         ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,
                      shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
-        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, Act(y2),
+        if not self.compression:
+            y2 = self._buf("E.s2", (N, h2, w2, self.c_shrink))
+            ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, Act(y2),
+                         shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
+            return y1, y2, cat
+        # NaiveCompressor in train mode (naive_compress.py:10-42): 3 x [conv3x3 + bias -> BatchNorm(batch statistics) ->
+        # ReLU]. The batch mean absorbs the conv bias, so the layer is the bias-free conv + BN of the backbone blocks (the
+        # bias gradient is exactly zero); only the running mean sees the bias: momentum * bias on top of the bias-free update.
+        y2a = self._act("E.s2c", (N, h2, w2, self.c_shrink))
+        ops.conv_fwd(y1, W["shrink_conv.layers.0.double_conv.2.weight"], 3, 1, y2a,
                      shift=P["shrink_conv.layers.0.double_conv.2.bias"], relu=True)
-        return y1, y2, cat
+        x = y2a
+        convs = self._compressor_convs()
+        for li, (conv, bn) in enumerate(convs.items()):
+            x = self._conv_bn_relu(P, {conv + ".weight": W[conv]}, conv + ".weight", bn, x, 1, True, 1, "cmp%d" % li, rec,
+                                   need_hi=li == len(convs) - 1)
+            P[bn + ".running_mean"].add_(P[conv + ".bias"], alpha=0.01)   # BatchNorm2d(momentum=0.01), naive_compress.py:20
+        self._cmp_in = y2a
+        return y1, x.hi, cat
 
     def forward_train(self, P, lidar, layout, drop=None):
         """Train-mode forward (batch-statistic BatchNorm in the encoder) that keeps what the backward needs: per sublayer
@@ -324,7 +338,7 @@ class CoBEVTEngine(W2CEngine):
         heads = self._buf("heads.out", (B, h2, w2, HEAD_PAD))
         ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
         self.saved = dict(rec=rec, W=W, subs=subs, X=X, m=m, fused=fused, y1=y1, y2=y2, cat=cat, layout=layout,
-                          key_mask=key_mask, B=B, drop=drop)
+                          key_mask=key_mask, B=B, drop=drop, cmp_in=self._cmp_in if self.compression else None)
         return heads
 
     def backward_train(self, P, dheads, grads):
@@ -452,6 +466,25 @@ class CoBEVTEngine(W2CEngine):
             for out, c0 in outs:
                 unpack.append(ops.sums_unpack_job(sums, out, c0))
 
+        if S.get("cmp_in") is not None:
+            # ---- NaiveCompressor, last layer first: d_y2 is the gradient w.r.t. its output; y2 becomes the shrink output
+            dy = d_y2
+            for li in (2, 1, 0):
+                r = next(q for q in rec if q["kind"] == "conv" and q["tag"] == "cmp%d" % li)
+                conv = r["conv"][:-len(".weight")]
+                dz = self._act("bwd.dz." + r["tag"], r["z"].shape)
+                sums = self._zeroed(r["tag"] + ".bsums", ops.bn_bwd_sums_len(r["z"].shape[3]), torch.float64)
+                ops.bn_relu_bwd(dy, r["z"], r["scale"], r["shift"], r["mean"], r["invstd"], sums, dz,
+                                grads[r["bn"] + ".weight"], grads[r["bn"] + ".bias"], write_hi=False)
+                cout, cin = r["z"].shape[3], r["x"].shape[3]
+                dwp = zero_f32(conv + ".dwp", 9 * cout * cin).view(9, cout, cin)
+                ops.conv_wgrad(r["x"], dz, 3, 1, dwp)
+                unpack.append(ops.conv_unpack_job(dwp, grads[r["conv"]]))
+                grads[conv + ".bias"].zero_()   # absorbed by the batch mean
+                dprev = self._buf("bwd.dprev." + r["tag"], r["x"].shape)
+                ops.conv_dgrad(dz, W[conv], 3, 1, dprev)
+                dy = dprev
+            d_y2, y2 = dy, S["cmp_in"].hi
         # ---- shrink header
         g2 = self._act("bwd.g2", y2.shape)
         ops.relu_bwd(d_y2, y2, g2)  # y2 is a plain fp32 tensor here

@@ -337,6 +337,59 @@ def test_train_step_matches_oracle_autograd():
         assert float((q.grad - g_step[n]).abs().max()) <= 2e-3 * float(g_step[n].abs().max()) + 1e-7, n
 
 
+def test_train_step_with_naive_compressor_matches_oracle_autograd():
+    """a10 in training: `compression: 2` puts NaiveCompressor (3 x conv3x3 + bias + BatchNorm(batch statistics) + ReLU,
+    common_modules/naive_compress.py:10-42; its train mode is pinned to the real module by
+    scripts/make_golden_compressor_train.py) between the shrink header and the fusion. Loss, the compressor's parameter
+    gradients and its running statistics against torch autograd through the oracle; the conv biases are absorbed by the
+    batch mean (gradient exactly zero here, ~1e-9 of rounding in autograd)."""
+    import json
+
+    import a2x_import
+    import w2c_common as C
+    from oracle import w2c_oracle as O
+
+    M = a2x_import.pkg("opencood.models.airv2x_cobevt")
+    cfg, gold = CC.load_small()
+    args = json.loads(json.dumps(cfg["model_args"]))
+    args["fax_fusion"]["drop_out"] = 0.0
+    args["compression"] = 2
+    model = M.Airv2xCoBEVT(args)
+    sd = CC.golden_state_dict_compressed(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    dd = CC.golden_scene(cfg, gold)
+    H, W = gold["eval_psm"].shape[2:]
+    labels = O.make_labels(5, 1, H, W, args["anchor_number"])
+    loss3 = model.train_step(C.to_device(dd, "cuda"), labels, cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    torch.set_num_threads(8)
+    out, bufs = CO.cobevt_forward(p, args, dd, training=True)
+    loss = O.point_pillar_loss_multiclass(out, labels, args["num_class"], cfg["loss_args"]["cls_weight"], cfg["loss_args"]["reg"])[0]
+    loss.backward()
+    assert abs(float(loss3.sum()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
+    errs, scale = {}, 0.0
+    for n, q in model.named_parameters():
+        ref = p[n].grad
+        if ref is None:
+            continue
+        if n.startswith("naive_compressor") and n.endswith(".bias") and n.split(".")[-2] in ("0", "3"):   # conv biases
+            w_ref = p[n[:-len("bias")] + "weight"].grad
+            assert float(q.grad.abs().max()) == 0.0 and float(ref.abs().max()) < 1e-5 * float(w_ref.abs().max()), n
+            continue
+        errs[n] = float((q.grad.cpu() - ref).norm() / (ref.norm() + 1e-30))
+    cmp_ = {n: e for n, e in errs.items() if n.startswith("naive_compressor")}
+    assert len(cmp_) == 9 and max(cmp_.values()) < 5e-2, sorted(cmp_.items(), key=lambda kv: -kv[1])
+    fusion = {n: e for n, e in errs.items() if n.startswith("fusion_net") or "head" in n}
+    assert max(fusion.values()) < 2e-2 and float(np.median(list(fusion.values()))) < 2e-3
+    assert max(errs.values()) < 0.15 and float(np.median(list(errs.values()))) < 0.05, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    msd = model.state_dict()
+    for k, v in bufs.items():
+        if k.startswith("naive_compressor") and "num_batches" not in k:
+            assert float((msd[k].cpu() - v).abs().max()) < 1e-5 + 1e-4 * float(v.abs().max()), k
+
+
 def test_dropout_kernels_and_train_step_with_identical_masks(ops):
     """nn.Dropout of the fusion network (swap_fusion_modules.py:43, base_transformer.py:32,34) as counter-based masks:
     (i) the keep rate of the exported masks is 1 - p (binomial bounds) and sites / seeds give independent masks;
