@@ -253,9 +253,10 @@ class CoBEVTEngine(W2CEngine):
             with self._on_side():
                 self._deblock(P, W, i, x, cat.slice_c(c0, c0 + self.up_filters[i]), True, 1, "E", rec)
         self._join_side()
-        assert self.shrink_k0 == 1 and self.shrink_stride == 1, "training of the legacy shrink header is not implemented"
+        s = self.shrink_stride      # airv2x yamls: 1x1 stride 1; legacy yamls: 3x3 stride 2 (or 1)
+        h2, w2 = (h2 - 1) // s + 1, (w2 - 1) // s + 1
         y1 = self._act("E.s1", (N, h2, w2, self.c_shrink))
-        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], 1, 1, y1,
+        ops.conv_fwd(cat, W["shrink_conv.layers.0.double_conv.0.weight"], self.shrink_k0, s, y1,
                      shift=P["shrink_conv.layers.0.double_conv.0.bias"], relu=True)
         if not self.compression:
             y2 = self._buf("E.s2", (N, h2, w2, self.c_shrink))
@@ -381,9 +382,9 @@ class CoBEVTEngine(W2CEngine):
         dh = split_of(dheads, "bwd.dheads")
         dwp = zero_f32("heads.dwp", HEAD_PAD * self.c_shrink).view(1, HEAD_PAD, self.c_shrink)
         ops.conv_wgrad(S["fused"], dh, 1, 1, dwp)
-        for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+        for name, row0 in self._head_rows():
             unpack.append(ops.conv_unpack_job(dwp, grads[name + ".weight"], row0))
-        col_sums(dheads, HEAD_PAD, [(grads["cls_head.bias"], 0), (grads["reg_head.bias"], nc), (grads["obj_head.bias"], nc + nr)])
+        col_sums(dheads, HEAD_PAD, [(grads[name + ".bias"], row0) for name, row0 in self._head_rows()])
         d_fused = self._buf("bwd.d_fused", S["fused"].shape)
         ops.conv_dgrad(dh, W["heads"], 1, 1, d_fused)
         dfs = split_of(d_fused, "bwd.dfs")
@@ -497,12 +498,13 @@ class CoBEVTEngine(W2CEngine):
         ops.conv_dgrad(g2, W[n2 + ".weight"], 3, 1, d_y1)
         g1 = self._act("bwd.g1", y1.shape)
         ops.relu_bwd(d_y1, y1.hi, g1)
-        dwp = zero_f32(n1 + ".dwp", self.c_shrink * self.c_cat).view(1, self.c_shrink, self.c_cat)
-        ops.conv_wgrad(cat, g1, 1, 1, dwp)
+        k0, s0 = self.shrink_k0, self.shrink_stride
+        dwp = zero_f32(n1 + ".dwp", k0 * k0 * self.c_shrink * self.c_cat).view(k0 * k0, self.c_shrink, self.c_cat)
+        ops.conv_wgrad(cat, g1, k0, s0, dwp)
         unpack.append(ops.conv_unpack_job(dwp, grads[n1 + ".weight"]))
         col_sums(g1.hi, self.c_shrink, [(grads[n1 + ".bias"], 0)])
         d_cat = self._buf("bwd.d_cat", cat.shape)
-        ops.conv_dgrad(g1, W[n1 + ".weight"], 1, 1, d_cat)
+        ops.conv_dgrad(g1, W[n1 + ".weight"], k0, s0, d_cat)
         # ---- backbone: deblocks, then blocks deep -> shallow
         by_tag = {r["tag"]: r for r in rec if r["kind"] == "conv"}
         deconvs = {r["level"]: r for r in rec if r["kind"] == "deconv"}

@@ -996,6 +996,183 @@ __global__ void __launch_bounds__(128) window_attention_small_bwd_kernel(const W
     }
 }
 
+// Windows too large for the n x n probability matrix in shared memory (128 < n <= 256 tokens: the 16 x 16 windows of the
+// legacy V2X-ViT pyramid, v2xvit_modules/mswin.py:66-82 with window_size [4, 8, 16]). Nothing n x n is stored: the scores
+// are recomputed from the rows. Phase A (thread = query i; K, V in shared memory): row maximum, 1 / row sum, D_i =
+// sum_j P_ij (dO_i . V_j), then dQ_i. Phase B (thread = key j; scaled Q, dO in shared memory, the row statistics of phase
+// A): dV_j = sum_i P_ij dO_i, then dK_j = sum_i dS_ij Q_i and the bias gradient. A fallback for the small legacy maps, not
+// a tuned kernel: 3 + 2 sweeps of n dot products per thread.
+template <int DH>
+__global__ void __launch_bounds__(256) window_attention_bwd_large_kernel(const WinAttBwdParams p) {
+    extern __shared__ float sm[];
+    const int ww = p.w * p.w;
+    const int n = p.L * ww;
+    constexpr int RS = DH + 4;
+    float* sA = sm;                 // phase A: K       phase B: q * scale
+    float* sC = sA + n * RS;        // phase A: V       phase B: dO
+    float* sM = sC + n * RS;        // [n] row maximum
+    float* sL = sM + n;             // [n] 1 / row sum
+    float* sD = sL + n;             // [n] D_i
+    const int nb = (2 * p.L - 1) * (2 * p.w - 1) * (2 * p.w - 1);
+    float* sB = sD + n;             // [nb] bias of this head
+    float* sdB = sB + nb;           // [nb] bias gradient of this CTA
+    int* sTok = reinterpret_cast<int*>(sdB + nb);
+    const int D = p.heads * DH;
+    const int X = p.H / p.w, Y = p.W / p.w;
+    const int head = blockIdx.x % p.heads;
+    int win = blockIdx.x / p.heads;
+    const int y = win % Y;
+    win /= Y;
+    const int x = win % X;
+    const int b = win / X;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int l = t / ww, r = t - l * ww;
+        const int w1 = r / p.w, w2 = r - w1 * p.w;
+        const int ph = p.grid_mode ? w1 * X + x : x * p.w + w1;
+        const int pw = p.grid_mode ? w2 * Y + y : y * p.w + w2;
+        sTok[t] = ((b * p.L + l) * p.H + ph) * p.W + pw;
+    }
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        sB[i] = p.bias[i * p.heads + head];
+        sdB[i] = 0.f;
+    }
+    __syncthreads();
+    auto load_pair = [&](const float* a_base, long long a_rs, float a_scale, const float* c_base, long long c_rs) {
+        for (int i = threadIdx.x; i < n * (DH / 4); i += blockDim.x) {
+            const int t = i / (DH / 4), c = (i - t * (DH / 4)) * 4;
+            float4 a4 = *reinterpret_cast<const float4*>(a_base + (long long)sTok[t] * a_rs + head * DH + c);
+            a4.x *= a_scale; a4.y *= a_scale; a4.z *= a_scale; a4.w *= a_scale;
+            *reinterpret_cast<float4*>(sA + t * RS + c) = a4;
+            *reinterpret_cast<float4*>(sC + t * RS + c) =
+                *reinterpret_cast<const float4*>(c_base + (long long)sTok[t] * c_rs + head * DH + c);
+        }
+    };
+    auto dot = [&](const float* row, const float (&v)[DH]) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(row + c);
+            acc = fmaf(t.x, v[c], acc);
+            acc = fmaf(t.y, v[c + 1], acc);
+            acc = fmaf(t.z, v[c + 2], acc);
+            acc = fmaf(t.w, v[c + 3], acc);
+        }
+        return acc;
+    };
+    auto load_row = [&](const float* g, float scale, float (&v)[DH]) {
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(g + c);
+            v[c] = t.x * scale; v[c + 1] = t.y * scale; v[c + 2] = t.z * scale; v[c + 3] = t.w * scale;
+        }
+    };
+    auto store_row = [&](long long off, const float (&v)[DH], float scale) {
+#pragma unroll
+        for (int c = 0; c < DH; c += 4)
+            store_split4(p.dqkv, off + c, make_float4(v[c] * scale, v[c + 1] * scale, v[c + 2] * scale, v[c + 3] * scale));
+    };
+    const int s2 = 2 * p.w - 1;
+    auto valid_key = [&](int lj) { return p.key_mask == nullptr || p.key_mask[b * p.L + lj] != 0; };
+    // relative-position table entry of (query i, key j)
+    auto bias_idx = [&](int i, int j) {
+        const int li = i / ww, ri = i - li * ww, i1 = ri / p.w, i2 = ri - i1 * p.w;
+        const int lj = j / ww, rj = j - lj * ww, k1 = rj / p.w, k2 = rj - k1 * p.w;
+        return ((li - lj + p.L - 1) * s2 + (i1 - k1 + p.w - 1)) * s2 + (i2 - k2 + p.w - 1);
+    };
+    const int me = threadIdx.x;
+    // ---------------------------------------------------------------- phase A: thread = query i
+    load_pair(p.qkv + D, 3LL * D, 1.f, p.qkv + 2 * D, 3LL * D);   // K, V
+    __syncthreads();
+    if (me < n) {
+        const int i = me;
+        float q[DH], go[DH];
+        load_row(p.qkv + (long long)sTok[i] * (3 * D) + head * DH, p.scale, q);
+        load_row(p.dout + (long long)sTok[i] * D + head * DH, 1.f, go);
+        float m = -INFINITY;
+        for (int j = 0; j < n; ++j)
+            if (valid_key(j / ww)) m = fmaxf(m, dot(sA + j * RS, q) + sB[bias_idx(i, j)]);
+        float sum = 0.f, Dv = 0.f;
+        for (int j = 0; j < n; ++j) {
+            if (!valid_key(j / ww)) continue;
+            const float e = __expf(dot(sA + j * RS, q) + sB[bias_idx(i, j)] - m);
+            sum += e;
+            Dv = fmaf(e, dot(sC + j * RS, go), Dv);
+        }
+        const float inv = 1.f / sum;
+        Dv *= inv;
+        sM[i] = m;
+        sL[i] = inv;
+        sD[i] = Dv;
+        float dq[DH];
+#pragma unroll
+        for (int c = 0; c < DH; ++c) dq[c] = 0.f;
+        for (int j = 0; j < n; ++j) {
+            if (!valid_key(j / ww)) continue;
+            const float pij = __expf(dot(sA + j * RS, q) + sB[bias_idx(i, j)] - m) * inv;
+            const float ds = pij * (dot(sC + j * RS, go) - Dv);
+#pragma unroll
+            for (int c = 0; c < DH; c += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(sA + j * RS + c);
+                dq[c] = fmaf(ds, t.x, dq[c]);
+                dq[c + 1] = fmaf(ds, t.y, dq[c + 1]);
+                dq[c + 2] = fmaf(ds, t.z, dq[c + 2]);
+                dq[c + 3] = fmaf(ds, t.w, dq[c + 3]);
+            }
+        }
+        store_row((long long)sTok[i] * (3 * D) + head * DH, dq, p.scale);
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- phase B: thread = key j
+    load_pair(p.qkv, 3LL * D, p.scale, p.dout, (long long)D);     // q * scale, dO
+    __syncthreads();
+    if (me < n) {
+        const int j = me;
+        const bool ok = valid_key(j / ww);
+        float k[DH], acc[DH];
+        load_row(p.qkv + (long long)sTok[j] * (3 * D) + D + head * DH, 1.f, k);
+#pragma unroll
+        for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+        if (ok) {
+            for (int i = 0; i < n; ++i) {                              // dV_j = sum_i P_ij dO_i
+                const float pij = __expf(dot(sA + i * RS, k) + sB[bias_idx(i, j)] - sM[i]) * sL[i];
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(sC + i * RS + c);
+                    acc[c] = fmaf(pij, t.x, acc[c]);
+                    acc[c + 1] = fmaf(pij, t.y, acc[c + 1]);
+                    acc[c + 2] = fmaf(pij, t.z, acc[c + 2]);
+                    acc[c + 3] = fmaf(pij, t.w, acc[c + 3]);
+                }
+            }
+        }
+        store_row((long long)sTok[j] * (3 * D) + 2 * D + head * DH, acc, 1.f);
+        float v[DH];
+        load_row(p.qkv + (long long)sTok[j] * (3 * D) + 2 * D + head * DH, 1.f, v);
+#pragma unroll
+        for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+        if (ok) {
+            for (int i = 0; i < n; ++i) {                              // dK_j = sum_i dS_ij (scale Q_i), bias gradient
+                const int bi = bias_idx(i, j);
+                const float pij = __expf(dot(sA + i * RS, k) + sB[bi] - sM[i]) * sL[i];
+                const float ds = pij * (dot(sC + i * RS, v) - sD[i]);
+                atomicAdd(&sdB[bi], ds);
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(sA + i * RS + c);
+                    acc[c] = fmaf(ds, t.x, acc[c]);
+                    acc[c + 1] = fmaf(ds, t.y, acc[c + 1]);
+                    acc[c + 2] = fmaf(ds, t.z, acc[c + 2]);
+                    acc[c + 3] = fmaf(ds, t.w, acc[c + 3]);
+                }
+            }
+        }
+        store_row((long long)sTok[j] * (3 * D) + D + head * DH, acc, 1.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (sdB[i] != 0.f) atomicAdd(&p.dbias[i * p.heads + head], sdB[i]);
+}
+
 }  // namespace a2x
 
 extern "C" {
@@ -1102,9 +1279,29 @@ int a2x_window_attention_bwd_split(const float* qkv, const float* dout, const fl
         return 0;
     }
     const size_t smem = (size_t)(4 * n * (dim_head + 4) + n * (n + 1) + 2 * nb + n) * sizeof(float);
-    A2X_REQUIRE(smem <= 200 * 1024, "window_attention_bwd: window of %d tokens does not fit shared memory", n);
     const long long grid = (long long)B * (H / window) * (W / window) * heads;
     cudaStream_t st = (cudaStream_t)stream;
+    if (smem > 200 * 1024) {  // the n x n matrix does not fit: recompute-from-rows kernel (n <= 256)
+        const size_t sml = (size_t)(2 * n * (dim_head + 4) + 3 * n + 2 * nb + n) * sizeof(float);
+        A2X_REQUIRE(n <= 256 && sml <= 200 * 1024, "window_attention_bwd: window of %d tokens does not fit shared memory", n);
+#define A2X_WAL(DH)                                                                                                   \
+    do {                                                                                                              \
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_bwd_large_kernel<DH>,                               \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));                  \
+        a2x::window_attention_bwd_large_kernel<DH><<<(unsigned)grid, 256, sml, st>>>(p);                              \
+    } while (0)
+        if (dim_head == 16) A2X_WAL(16);
+        else if (dim_head == 32) A2X_WAL(32);
+        else if (dim_head == 64) A2X_WAL(64);
+        else {
+            a2x::set_error("window_attention_bwd: dim_head %d not in {16, 32, 64}", dim_head);
+            return 1;
+        }
+#undef A2X_WAL
+        A2X_LAUNCHED();
+        A2X_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (dim_head == 32) {
         A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::window_attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         a2x::window_attention_bwd_kernel<32><<<(unsigned)grid, 128, smem, st>>>(p);

@@ -4,15 +4,17 @@ Same registry name / class name / constructor, same `hypes_yaml` keys (`pillar_v
 `base_bev_backbone`, `shrink_header`, `compression`, `fax_fusion`, `max_cav`, `anchor_number`), same `state_dict` keys
 and shapes (10 513 344 parameters for V2XR_cobevt.yaml), same
 `forward(data_dict) -> {"psm","rm","mask","each_mask","comm_rate"}` as opencood/models/point_pillar_cobevt.py:14-128 of
-the reference (input: `data_dict["processed_lidar"]`, `record_len`). Parameter containers only; eval-mode forward in this
-round; no CPU fallback.
+the reference (input: `data_dict["processed_lidar"]`, `record_len`). Parameter containers only; eval forward, the
+reference-style training loop (`model(batch)` with grad enabled -> PointPillarLoss -> `loss.backward()`) and the fused
+`train_step()`; no CPU fallback.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 
 from ...pplegacy_engine import LegacyCoBEVTEngine
-from .airv2x_cobevt import _SwapFusionEncoderParams
+from ...w2c_engine import HEAD_PAD
+from .airv2x_cobevt import Airv2xCoBEVT, _SwapFusionEncoderParams, fusion_step
 from .airv2x_where2com import _backbone_params, _PillarVFEParams
 from .point_pillar_where2comm import _legacy_shrink_params
 
@@ -97,6 +99,60 @@ class _LegacyFusionModel(nn.Module):
                  "voxel_coords": lid["voxel_coords"].to(device=dev, dtype=torch.int32).contiguous()}
         return lidar, cache[key]
 
+    # ------------------------------------------------------------------ training
+    dropout = "on"   # nn.Dropout of the fusion network in train mode: counter-based masks ("off" disables; see _dropout_state)
+
+    def _heads_shape(self, layout):
+        s = int(self.args["shrink_header"]["stride"][0])
+        h, w = layout["ny"] // 2, layout["nx"] // 2
+        return [len(layout["record_len"]), (h - 1) // s + 1, (w - 1) // s + 1, HEAD_PAD]
+
+    def _grad_buffers(self):
+        g = {}
+        for n, p in self.named_parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            g[n] = p.grad
+        return g
+
+    def _check_trainable(self):
+        if self.args.get("backbone_fix", False):
+            raise NotImplementedError("%s: training with backbone_fix (frozen encoder) is not implemented" % type(self).__name__)
+
+    def _forward_train(self, P, lidar, layout, data_dict, drop):
+        raise NotImplementedError
+
+    def _train_forward_autograd(self, data_dict):
+        """reference training loop (tools/train.py:216-221): model(batch) -> criterion -> loss.backward(); the autograd
+        boundary is the torch.library op pair of torch_ops.py"""
+        self._check_trainable()
+        lidar, layout = self._inputs(data_dict)
+        names = [n for n, p in self.named_parameters() if p.requires_grad]
+        params = [p for n, p in self.named_parameters() if p.requires_grad]
+        drop = self._dropout_state(None)
+        heads = fusion_step(self, lambda: self._forward_train(self._param_dict(), lidar, layout, data_dict, drop), names, params,
+                            self._heads_shape(layout))
+        return self._outputs(heads, {"comm_rate": self.engine._canvas_nz})
+
+    def train_step(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0, dropout=None):
+        """forward (train-mode BatchNorm) + PointPillarLoss (loss/point_pillar_loss.py:77-215) + backward in one call on the
+        CUDA kernels; label_dict = the legacy collate's {"targets" [B,H,W,7A], "pos_equal_one" [B,H,W,A]}. Parameter
+        gradients land in p.grad; returns the device tensor [reg, conf, 0] (float64), total = .sum(). nn.Dropout of the
+        fusion network runs as counter-based masks (dropout: None -> self.dropout; "on", "off" or an int seed)."""
+        assert self.training, "train_step() needs model.train()"
+        self._check_trainable()
+        drop = self.last_dropout = self._dropout_state(dropout)
+        lidar, layout = self._inputs(data_dict)
+        dev = next(self.parameters()).device
+        labels = {"targets": label_dict["targets"].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous(),
+                  "pos_equal_one": label_dict["pos_equal_one"].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()}
+        P = self._param_dict()
+        eng = self.engine
+        heads = self._forward_train(P, lidar, layout, data_dict, drop)
+        loss3, dheads = eng.loss(heads, labels, cls_weight, reg_coe)
+        eng.backward_train(P, dheads, self._grad_buffers())
+        return loss3
+
     def _outputs(self, heads, aux):
         A = self.args["anchor_number"]
         nchw = heads.permute(0, 3, 1, 2)
@@ -113,7 +169,14 @@ class PointPillarCoBEVT(_LegacyFusionModel):
         self.fusion_net = _SwapFusionEncoderParams(args["fax_fusion"])
         self._init_heads(args)
 
+    _dropout_state = Airv2xCoBEVT._dropout_state     # fax_fusion.drop_out, same keys as the airv2x yaml
+
+    def _forward_train(self, P, lidar, layout, data_dict, drop):
+        return self.engine.forward_train(P, lidar, layout, drop)
+
     def forward(self, data_dict):
+        if self.training and torch.is_grad_enabled():
+            return self._train_forward_autograd(data_dict)
         lidar, layout = self._inputs(data_dict)
         heads, aux = self.engine.forward(self._param_dict(), lidar, layout, self.training)
         return self._outputs(heads, aux)

@@ -4,7 +4,9 @@
 Same kernels as the airv2x engines; what differs from them: ONE PillarVFE for all agents (`pillar_vfe.*`), the legacy
 3x3 stride-2 shrink header, `max_cav` an int, 1-class heads without objectness, an optional NaiveCompressor; the V2X-ViT
 variant warps every agent's map into the ego frame with `pairwise_t_matrix[b, 0]` (warp_affine_simple, align_corners
-False) before the transformer and feeds it a zero prior encoding and identity spatial correction. Eval-mode forward.
+False) before the transformer and feeds it a zero prior encoding and identity spatial correction. Eval forward and the
+training step (forward_train / loss = PointPillarLoss / backward_train, inherited from the airv2x engines: the legacy
+shrink header, head rows and pre-warp are parameters of those).
 """
 import torch
 
@@ -48,6 +50,7 @@ def _legacy_common(self, args, device, precision):
     self.saved = None
     self.side = None
     self.use_side_stream = False
+    self.legacy_loss = True     # PointPillarLoss (loss/point_pillar_loss.py:77-215), not the multi-class loss
 
 
 class LegacyCoBEVTEngine(CoBEVTEngine):
@@ -66,7 +69,8 @@ class LegacyCoBEVTEngine(CoBEVTEngine):
 
     def forward(self, P, lidar, layout, training, k_list=None):
         if training:
-            raise NotImplementedError("point_pillar_cobevt on the B200 kernels is eval-only in this round")
+            raise NotImplementedError("PointPillarCoBEVT: train-mode forward under torch.no_grad() is not implemented "
+                                      "(model.eval() for inference; model(batch) with grad enabled or train_step() for training)")
         self._begin_step()
         W = self._pack_weights(P)
         feat = self.encode(P, W, lidar, layout)
@@ -95,9 +99,23 @@ class LegacyV2XViTEngine(V2XViTEngine):
     def _head_rows(self):
         return (("cls_head", 0), ("reg_head", self.A))
 
+    def _ego_theta(self, pairwise, layout):
+        """warp_affine_simple(regroup_feature[b], pairwise_t_matrix[b, ego = 0]) (point_pillar_v2xvit.py:140-166). H, W of
+        the normalisation are the pillar canvas', downsample_rate is 1 there (:118-119)"""
+        record_len = layout["record_len"]
+        theta_all = warp.normalize_pairwise(pairwise, layout["ny"], layout["nx"], 1, self.discrete_ratio)   # [B, L, L, 2, 3]
+        return torch.stack([theta_all[b, 0, l] for b in range(len(record_len)) for l in range(record_len[b])]).to(self.device)
+
+    def forward_train(self, P, lidar, layout, pairwise, drops=None):
+        B = len(layout["record_len"])
+        prior = torch.zeros(B, self.L, 3)
+        scm = torch.eye(4, dtype=torch.float64).repeat(B, self.L, 1, 1)
+        return super().forward_train(P, lidar, layout, prior, scm, drops, pre_warp=self._ego_theta(pairwise, layout))
+
     def forward(self, P, lidar, layout, training, pairwise=None):
         if training:
-            raise NotImplementedError("point_pillar_v2xvit on the B200 kernels is eval-only in this round")
+            raise NotImplementedError("PointPillarV2XVit: train-mode forward under torch.no_grad() is not implemented "
+                                      "(model.eval() for inference; model(batch) with grad enabled or train_step() for training)")
         self._begin_step()
         W = self._pack_weights(P)
         feat = self.encode(P, W, lidar, layout)
@@ -105,11 +123,7 @@ class LegacyV2XViTEngine(V2XViTEngine):
         nz.copy_(self._canvas_nz)
         record_len = layout["record_len"]
         B, (N, h, w, C) = len(record_len), feat.shape
-        # warp_affine_simple(regroup_feature[b], pairwise_t_matrix[b, ego = 0]) (point_pillar_v2xvit.py:140-166). H, W
-        # of the normalisation are the pillar canvas', downsample_rate is 1 there (:118-119)
-        ny, nx = self._last_canvas.shape[1], self._last_canvas.shape[2]
-        theta_all = warp.normalize_pairwise(pairwise, ny, nx, 1, self.discrete_ratio)            # [B, L, L, 2, 3]
-        theta = torch.stack([theta_all[b, 0, l] for b in range(B) for l in range(record_len[b])]).to(self.device)
+        theta = self._ego_theta(pairwise, layout)
         warped = self._buf("pp.warped", feat.shape)
         ops.warp_affine_fwd(feat, theta, Act(warped), align_corners=False)
         prior = torch.zeros(B, self.L, 3)

@@ -230,13 +230,15 @@ class V2XViTEngine(CoBEVTEngine):
         return fused
 
     # ------------------------------------------------------------------ training step
-    def forward_train(self, P, lidar, layout, prior, scm, drops=None):
+    def forward_train(self, P, lidar, layout, prior, scm, drops=None, pre_warp=None):
         """Train-mode forward (batch-statistic BatchNorm in the encoder) keeping what the backward needs: per sublayer the
         residual input, the LayerNorm output, the projected q|k|v tensors, the attention outputs, the three window
         branches with the split-attention statistics, the FFN pre-activation and hidden activation.
         drops: None (nn.Dropout disabled) or (cav, pwindow, ffn) ops.Dropout states (each None when its rate is 0) for
         HGTCavAttention.drop_out (hmsa.py:155), BaseWindowAttention.to_out's Dropout (mswin.py:47) and FeedForward's two
-        Dropouts (base_transformer.py:22,24); masks are regenerated from (seed, site) in the backward."""
+        Dropouts (base_transformer.py:22,24); masks are regenerated from (seed, site) in the backward.
+        pre_warp: [N, 2, 3] normalised affine maps applied to the shrunk features before the transformer (the legacy
+        point_pillar_v2xvit resamples every agent's map into the ego frame first, point_pillar_v2xvit.py:140-166) or None."""
         dropc, dropw, dropf = drops if drops is not None else (None, None, None)
         self._begin_step()
         rec = []
@@ -257,7 +259,10 @@ class V2XViTEngine(CoBEVTEngine):
         assert all(t in (0, 1) for t in types), "prior_encoding[..., 2] (agent type) must be 0 or 1 (hmsa.py:8)"
         types_dev = torch.tensor(types, dtype=torch.int32, device=dev)
         X = self._buf("vit.x", (N, h, w, C))
-        X.copy_(y2)
+        if pre_warp is not None:
+            ops.warp_affine_fwd(y2, pre_warp, Act(X), align_corners=False)
+        else:
+            X.copy_(y2)
         rte_idx = None
         if ca["use_RTE"]:
             rte_idx = torch.tensor([int(prior[b, l, 1]) * ca["RTE_ratio"] for b, l in valid], dtype=torch.int32, device=dev)
@@ -357,7 +362,7 @@ class V2XViTEngine(CoBEVTEngine):
         ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
         self.saved = dict(rec=rec, W=W, layers=layers, fused=fused, y1=y1, y2=y2, cat=cat, layout=layout, B=B, runs=runs,
                           starts=starts, types_dev=types_dev, kmask=kmask, theta=theta, rte_idx=rte_idx,
-                          drops=(dropc, dropw, dropf))
+                          drops=(dropc, dropw, dropf), pre_warp=pre_warp)
         return heads
 
     def backward_train(self, P, dheads, grads):
@@ -416,9 +421,9 @@ class V2XViTEngine(CoBEVTEngine):
         dh = split_of(dheads, "bwd.dheads")
         dwp = zero_f32(HEAD_PAD * self.c_shrink).view(1, HEAD_PAD, self.c_shrink)
         ops.conv_wgrad(S["fused"], dh, 1, 1, dwp)
-        for name, row0 in (("cls_head", 0), ("reg_head", nc), ("obj_head", nc + nr)):
+        for name, row0 in self._head_rows():
             unpack.append(ops.conv_unpack_job(dwp, grads[name + ".weight"], row0))
-        col_sums(dheads, HEAD_PAD, [(grads["cls_head.bias"], 0), (grads["reg_head.bias"], nc), (grads["obj_head.bias"], nc + nr)])
+        col_sums(dheads, HEAD_PAD, [(grads[name + ".bias"], row0) for name, row0 in self._head_rows()])
         d_fused = self._buf("bwd.d_fused", S["fused"].shape)
         ops.conv_dgrad(dh, W["heads"], 1, 1, d_fused)
         dX = self._buf("bwd.dX", (N, h, w, C))
@@ -540,6 +545,11 @@ class V2XViTEngine(CoBEVTEngine):
         for n in ("fusion_net.encoder.prior_feed.weight", "fusion_net.encoder.prior_feed.bias"):
             if n in grads:
                 grads[n].zero_()
+        if S.get("pre_warp") is not None:   # the legacy model's ego-frame resampling, transposed
+            d_y2 = self._buf("bwd.d_y2", (N, h, w, C))
+            d_y2.zero_()
+            ops.warp_affine_bwd(d_pre_warp, S["pre_warp"], d_y2, align_corners=False)
+            d_pre_warp = d_y2
         self._encoder_backward(P, S, d_pre_warp, grads, unpack)
         for lo in range(0, len(unpack), 128):
             ops.unpack_wgrads_batched(self._job_table("unpack%d" % lo, unpack[lo:lo + 128]))

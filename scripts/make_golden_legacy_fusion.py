@@ -1,6 +1,7 @@
 """Generate tests/golden/pp{cobevt,v2xvit}_small.npz: the REAL reference `point_pillar_cobevt` / `point_pillar_v2xvit`
-(V2XR_cobevt.yaml / V2XR_v2xvit.yaml args; 3 agents, 8k points, 128 x 128 pillars) on the CPU, eval mode, checked against
-the oracle restatements. One neighbour gets a non-identity pairwise pose so the V2X-ViT ego-warp is exercised.
+(V2XR_cobevt.yaml / V2XR_v2xvit.yaml args; 3 agents, 8k points, 128 x 128 pillars) on the CPU, eval mode AND train mode
+(forward, PointPillarLoss, every parameter gradient, running statistics; dropout p = 0), checked against the oracle
+restatements. One neighbour gets a non-identity pairwise pose so the V2X-ViT ego-warp is exercised.
 
     python scripts/make_golden_legacy_fusion.py
 """
@@ -30,6 +31,15 @@ def pairwise(L):
     t[0, 0, 1, 0, 3], t[0, 0, 1, 1, 3] = 4.8, -1.6
     t[0, 0, 2, 0, 3], t[0, 0, 2, 1, 3] = -3.2, 2.4
     return t
+
+
+def train_labels(H, W, A, seed=99):
+    """20 planted positives with regression targets (the legacy collate's label_dict: loss/point_pillar_loss.py:77-100)"""
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.zeros(1, H, W, A, dtype=torch.float64)
+    pos.view(-1)[torch.randperm(H * W * A, generator=g)[:20]] = 1.0
+    tg = 0.3 * torch.randn(1, H, W, 7 * A, generator=g, dtype=torch.float64) * pos.repeat_interleave(7, -1)
+    return {"pos_equal_one": pos, "targets": tg}
 
 
 def jsonable(o):
@@ -79,6 +89,44 @@ def run(name, yaml_rel, oracle_forward):
         out["eval_" + k] = ref[k].numpy()
     assert ref["comm_rate"] == ora["comm_rate"]
     out["eval_comm_rate"] = int(ref["comm_rate"])
+    # ---- train mode (batch-statistic BatchNorm; every nn.Dropout of the real model set to p = 0, which is what the
+    # oracle's legacy forwards restate): forward, the reference's own PointPillarLoss, all parameter gradients and the
+    # updated running statistics, real reference vs oracle
+    from opencood.loss.point_pillar_loss import PointPillarLoss
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model.train()
+    model.zero_grad()
+    tr = model({k: (v.clone() if torch.is_tensor(v) else v) for k, v in dd.items()})
+    lab = train_labels(tr["psm"].shape[2], tr["psm"].shape[3], args["anchor_number"])
+    crit = PointPillarLoss({"cls_weight": 1.0, "reg": 2.0})
+    loss_ref = crit({"psm": tr["psm"], "rm": tr["rm"]}, {k: v.float() for k, v in lab.items()})
+    loss_ref.backward()
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    to, bufs = oracle_forward(p, args, dd, training=True)
+    loss_ora = O.point_pillar_loss(to, lab, 1.0, 2.0)[0]
+    loss_ora.backward()
+    print("  train: psm ref-vs-oracle %.3e, loss %.6f vs %.6f" % (float((tr["psm"] - to["psm"]).abs().max()), float(loss_ref), float(loss_ora)))
+    assert float((tr["psm"] - to["psm"]).abs().max()) < 5e-5 and abs(float(loss_ref) - float(loss_ora)) < 1e-5 * abs(float(loss_ref))
+    worst, n_grads, names, norms = 0.0, 0, [], []
+    for n, q in model.named_parameters():
+        if q.grad is None:
+            assert p[n].grad is None or float(p[n].grad.abs().max()) == 0.0, n
+            continue
+        e = float((q.grad - p[n].grad).norm() / (q.grad.norm() + 1e-30))
+        if q.grad.norm() > 1e-6:
+            worst = max(worst, e)
+        n_grads += 1
+        names.append(n)
+        norms.append(float(q.grad.norm()))
+    rs = max(float((model.state_dict()[k] - v).abs().max()) for k, v in bufs.items() if "num_batches" not in k)
+    print("  train: %d parameter gradients, worst norm-wise difference %.3e; running statistics %.3e" % (n_grads, worst, rs))
+    assert worst < 2e-3 and rs < 1e-5
+    out["train_loss"] = float(loss_ref)
+    out["train_psm"] = tr["psm"].detach().numpy()
+    out["train_grad_names"] = np.array(names)
+    out["train_grad_norms"] = np.array(norms)
     cfg = {"model_args": jsonable(args), "preprocess": jsonable(hypes["preprocess"]), "postprocess": jsonable(hypes["postprocess"]),
            "source": "opencood/hypes_yaml/%s (cav_lidar_range %s, voxel_size [0.4, 0.4, 4])" % (yaml_rel, RANGE)}
     json.dump(cfg, open(os.path.join(ROOT, "tests", "golden", name + "_small_config.json"), "w"), indent=1)

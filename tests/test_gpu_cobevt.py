@@ -250,7 +250,9 @@ def test_layernorm_gelu_backward(ops):
 @pytest.mark.parametrize("case", [(2, 7, 8, 8, 8, 32, 4), (1, 3, 4, 8, 4, 16, 2),
                                   (1, 8, 8, 8, 8, 32, 4), (2, 2, 8, 8, 4, 32, 4), (1, 5, 4, 12, 8, 32, 4), (1, 7, 48, 64, 8, 32, 4),
                                   # small windows (V2X-ViT pyramid): 128 / n windows per CTA
-                                  (3, 1, 8, 12, 16, 16, 2), (2, 1, 8, 16, 8, 32, 4), (2, 1, 12, 8, 4, 64, 4), (1, 1, 4, 12, 8, 32, 4)])
+                                  (3, 1, 8, 12, 16, 16, 2), (2, 1, 8, 16, 8, 32, 4), (2, 1, 12, 8, 4, 64, 4), (1, 1, 4, 12, 8, 32, 4),
+                                  # 16 x 16 windows of the legacy V2X-ViT pyramid (256 tokens: recompute-from-rows kernel), 3 agents x 64
+                                  (2, 1, 16, 32, 4, 64, 16), (1, 3, 8, 16, 2, 32, 8)])
 @pytest.mark.parametrize("grid_mode", [False, True])
 def test_window_attention_backward(ops, case, grid_mode):
     """dq, dk, dv and the relative-position-bias gradient == torch autograd of the attention core"""

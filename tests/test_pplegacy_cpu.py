@@ -51,6 +51,27 @@ def pairwise(L):
     return t
 
 
+def train_labels(H, W, A, seed=99):
+    """the planted labels of scripts/make_golden_legacy_fusion.py (train-mode pin)"""
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.zeros(1, H, W, A, dtype=torch.float64)
+    pos.view(-1)[torch.randperm(H * W * A, generator=g)[:20]] = 1.0
+    tg = 0.3 * torch.randn(1, H, W, 7 * A, generator=g, dtype=torch.float64) * pos.repeat_interleave(7, -1)
+    return {"pos_equal_one": pos, "targets": tg}
+
+
+def oracle_train(name, sd, cfg, gold):
+    """train-mode forward + PointPillarLoss + autograd through the oracle: (loss, logits, {name: grad}, running stats)"""
+    args = cfg["model_args"]
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    torch.set_num_threads(8)
+    out, bufs = CASES[name][3](p, args, golden_scene(cfg, gold), training=True)
+    lab = train_labels(out["psm"].shape[2], out["psm"].shape[3], args["anchor_number"])
+    loss = O.point_pillar_loss(out, lab, 1.0, 2.0)[0]
+    loss.backward()
+    return loss.detach(), out, {k: v.grad for k, v in p.items() if torch.is_tensor(v) and v.grad is not None}, bufs, lab
+
+
 def golden_scene(cfg, gold):
     dd = O.make_scene_legacy(cfg["preprocess"], int(gold["n_agents"]), int(gold["n_points"]), int(gold["scene_seed"]),
                              cfg["preprocess"]["args"]["max_voxel_test"])
@@ -73,3 +94,16 @@ def test_oracle_and_registry_surface(name):
     assert out["comm_rate"] == int(gold["eval_comm_rate"])
     with pytest.raises(RuntimeError, match="CUDA"):
         model(golden_scene(cfg, gold))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_train_mode_matches_reference_golden(name):
+    """train mode (batch-statistic BatchNorm, dropout p = 0): the oracle's loss, logits and every parameter-gradient norm
+    against the values recorded from the REAL reference model + the reference's PointPillarLoss"""
+    model, cfg, gold = build(name)
+    loss, out, grads, _, _ = oracle_train(name, golden_state_dict(model, gold), cfg, gold)
+    assert abs(float(loss) - float(gold["train_loss"])) < 1e-5 * abs(float(gold["train_loss"]))
+    assert np.abs(out["psm"].detach().numpy() - gold["train_psm"]).max() < 5e-5
+    for n, ref in zip(gold["train_grad_names"], gold["train_grad_norms"]):
+        got = float(grads[str(n)].norm())
+        assert abs(got - float(ref)) < 2e-3 * float(ref) + 1e-6, (n, got, float(ref))
