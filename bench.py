@@ -484,6 +484,12 @@ def main():
 
     import a2x_import
 
+    # stdout carries exactly ONE line, the JSON: anything a library prints there meanwhile (NCCL's "NCCL version ..." line
+    # at NCCL_DEBUG=VERSION goes to stdout whatever NCCL_DEBUG_FILE says) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -629,6 +635,8 @@ def main():
         r = run_reference(argparse.Namespace(steps=1, warmup=0), cfg)
         line["cpu_baseline"] = {"value": r["value"], "unit": "scenes/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line))
     sys.stdout.flush()
