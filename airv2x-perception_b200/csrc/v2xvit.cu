@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(256) hgt_attention_kernel(const float* __restr
 // sums[a][c] += sum_p (w0 + w1 + w2)[a][p][c]      (global average pool numerator)
 __global__ void __launch_bounds__(256) split_pool_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
                                                          const float* __restrict__ w2, long long pix, int C,
-                                                         int chunks, float* __restrict__ sums) {
-    // grid = (chunks, agents); blockDim = C/4 * rows
+                                                         int chunks, float* __restrict__ partials) {
+    // grid = (chunks, agents); blockDim = C/4 * rows. Every block stores its partial sum [C] at partials[a][chunk]: no
+    // atomics, so that the pooled vector (reduced in chunk order by split_weights_kernel) is bit-reproducible
     const int q = C >> 2;
     const int cq = threadIdx.x % q, prow = threadIdx.x / q, ppb = blockDim.x / q;
     const int a = blockIdx.y;
@@ -183,21 +184,26 @@ __global__ void __launch_bounds__(256) split_pool_kernel(const float* __restrict
             const float4 v = red4[r * q + threadIdx.x];
             t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
-        float* o = sums + (long long)a * C + threadIdx.x * 4;
-        atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+        *reinterpret_cast<float4*>(partials + ((long long)a * chunks + blockIdx.x) * C + threadIdx.x * 4) = t;
     }
 }
 
 // per agent: g = sums / pix; h = relu(LN(fc1 g)); a = fc2 h ([3C]); wts[r][c] = softmax_r a[r*C + c]
-__global__ void split_weights_kernel(const float* __restrict__ sums, float inv_pix, const float* __restrict__ fc1,
-                                     const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                                     const float* __restrict__ fc2, int C, float* __restrict__ wts) {
+__global__ void split_weights_kernel(const float* __restrict__ partials, int chunks, float* __restrict__ sums, float inv_pix,
+                                     const float* __restrict__ fc1, const float* __restrict__ ln_g,
+                                     const float* __restrict__ ln_b, const float* __restrict__ fc2, int C,
+                                     float* __restrict__ wts) {
     extern __shared__ float sm[];
     float* g = sm;          // [C]
     float* h = sm + C;      // [C]
     float* red = h + C;     // [2]
     const int a = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) g[c] = sums[(long long)a * C + c] * inv_pix;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;      // fixed chunk order: deterministic
+        for (int k = 0; k < chunks; ++k) s += partials[((long long)a * chunks + k) * C + c];
+        sums[(long long)a * C + c] = s;   // kept for the backward
+        g[c] = s * inv_pix;
+    }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
@@ -333,17 +339,16 @@ int a2x_hgt_attention_fwd(const float* qkv, const int* types_dev, const float* k
 
 int a2x_split_attn_fuse(const float* w0, const float* w1, const float* w2, int n_agents, long long pix, int C,
                         const float* fc1, const float* ln_gamma, const float* ln_beta, const float* fc2,
-                        float* sums_ws, float* weights_ws, float* x_inout, a2x_stream_t stream) {
-    A2X_REQUIRE(w0 && w1 && w2 && fc1 && ln_gamma && ln_beta && fc2 && sums_ws && weights_ws && x_inout && n_agents > 0 &&
-                    pix > 0 && C > 0 && C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0,
+                        float* sums_ws, float* partials_ws, float* weights_ws, float* x_inout, a2x_stream_t stream) {
+    A2X_REQUIRE(w0 && w1 && w2 && fc1 && ln_gamma && ln_beta && fc2 && sums_ws && partials_ws && weights_ws && x_inout &&
+                    n_agents > 0 && pix > 0 && C > 0 && C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0,
                 "split_attn_fuse: bad args (C/4 must divide 256)");
     cudaStream_t st = (cudaStream_t)stream;
-    A2X_CHECK_CUDA(cudaMemsetAsync(sums_ws, 0, (size_t)n_agents * C * sizeof(float), st));
-    const int chunks = 148 * 2 / n_agents > 0 ? 148 * 2 / n_agents : 1;
-    split_pool_kernel<<<dim3(chunks, n_agents), 256, 256 * sizeof(float4), st>>>(w0, w1, w2, pix, C, chunks, sums_ws);
+    const int chunks = A2X_SPLIT_ATTN_CHUNKS;   // fixed: the pooled sums do not depend on the number of agents in the call
+    split_pool_kernel<<<dim3(chunks, n_agents), 256, 256 * sizeof(float4), st>>>(w0, w1, w2, pix, C, chunks, partials_ws);
     A2X_LAUNCHED();
-    split_weights_kernel<<<n_agents, 256, (2 * C + 2) * sizeof(float), st>>>(sums_ws, 1.0f / (float)pix, fc1, ln_gamma,
-                                                                           ln_beta, fc2, C, weights_ws);
+    split_weights_kernel<<<n_agents, 256, (2 * C + 2) * sizeof(float), st>>>(partials_ws, chunks, sums_ws, 1.0f / (float)pix,
+                                                                           fc1, ln_gamma, ln_beta, fc2, C, weights_ws);
     A2X_LAUNCHED();
     const long long total4 = (long long)n_agents * pix * (C / 4);
     split_combine_kernel<<<vx_grid(total4), 256, 0, st>>>(w0, w1, w2, weights_ws, x_inout, pix, C, total4);

@@ -190,6 +190,50 @@ class AgentParallelCoBEVT:
         return {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A]}
 
 
+class AgentParallelV2XVit(AgentParallelCoBEVT):
+    """Airv2xV2XVit (BASELINE config 3) with the agents of ONE scene sharded one per rank: per-agent encoders in parallel,
+    one all-gather of the shrunk maps (the path's only exchange: v2xvit fuses after `regroup`, airv2x_v2xvit.py:117-140),
+    replicated V2XTransformer. Every rank returns the fused output, bit-equal to the single-GPU one. NCCL transport (the
+    peer-memory pull is fused into CoBEVT's regroup kernel; V2X-ViT's first consumer is the RTE / STTF copy)."""
+
+    def __init__(self, model, agent_types, transport="nccl", group=None):
+        assert transport == "nccl", "AgentParallelV2XVit: NCCL transport only"
+        super().__init__(model, agent_types, transport, group)
+
+    def __call__(self, points, preprocess, prior, scm):
+        """points: [P, 4] cloud of THIS rank's agent; prior [1, L, 3] / scm [1, L, 4, 4]: the scene's prior encoding and
+        spatial correction matrices (replicated on every rank, as data_dict carries them)."""
+        from .ops import Act
+        from .w2c_engine import HEAD_PAD
+        from . import ops
+
+        m = self.model
+        assert not m.training, "agent-parallel mode is inference only"
+        dev = next(m.parameters()).device
+        if not hasattr(self, "_lay"):
+            self._lay = self._layouts(dev)
+        lay, glob = self._lay
+        dd = dict(self.per_rank[self.rank])
+        pts = points.to(device=dev, dtype=torch.float32)
+        dd["raw_points"] = {"points": pts, "offsets": torch.tensor([0, pts.shape[0]], dtype=torch.int32),
+                            "preprocess": preprocess, "filter": True}
+        lidar = m._lidar(dd, dev, lay)
+        lidar["raw"]["ego_flags"] = lay["ego_flags"]
+        eng, P = m.engine, m._param_dict()
+        eng._begin_step()
+        W = eng._pack_weights(P)
+        local = eng.encode(P, W, lidar, lay)
+        feat = gather_agent_maps(local, self.group)
+        fused = eng.fusion(P, W, feat, glob, prior, scm)
+        heads = eng._buf("heads.out", (fused.shape[0], feat.shape[1], feat.shape[2], HEAD_PAD))
+        ops.linear_fwd(fused, W["heads"], Act(heads), bias=W["heads.bias"])
+        A, K = m.args["anchor_number"], m.args["num_class"]
+        nc, nr = A * K, 7 * A
+        nchw = heads.permute(0, 3, 1, 2)
+        self.wire_bytes = int(heads.shape[1] * heads.shape[2] * eng.c_shrink * 4) * (self.world - 1)
+        return {"psm": nchw[:, :nc], "rm": nchw[:, nc:nc + nr], "obj": nchw[:, nc + nr:nc + nr + A]}
+
+
 class AgentParallelWhere2comm:
     """Airv2xWhere2com inference with the agents of ONE scene sharded one per rank (rank 0 = ego). Each rank publishes
     the level-0 cells its communication mask selected (warp-ballot compaction, `a2x_mask_compact`) and its dense deeper

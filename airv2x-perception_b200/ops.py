@@ -644,11 +644,20 @@ def hgt_attention_fwd(qkv, types, key_mask, heads, dim_head, out):
     return out
 
 
+SPLIT_ATTN_CHUNKS = 64   # A2X_SPLIT_ATTN_CHUNKS
+_split_partials = {}
+
+
 def split_attn_fuse(w0, w1, w2, fc1, ln_g, ln_b, fc2, sums_ws, weights_ws, x):
-    """x (dense [n, h, w, C]) += split-attention mix of the three window branches"""
+    """x (dense [n, h, w, C]) += split-attention mix of the three window branches; sums_ws [n, C] receives the pooled sums.
+    The per-chunk scratch of the deterministic pooling is cached here per (device, n, C)."""
     n, h, w, c = x.shape
+    key = (x.device, n, c)
+    part = _split_partials.get(key)
+    if part is None:
+        part = _split_partials[key] = torch.empty(n * SPLIT_ATTN_CHUNKS * c, device=x.device, dtype=torch.float32)
     call("a2x_split_attn_fuse", _ptr(w0), _ptr(w1), _ptr(w2), c_int(n), c_ll(h * w), c_int(c), _ptr(fc1), _ptr(ln_g),
-         _ptr(ln_b), _ptr(fc2), _ptr(sums_ws), _ptr(weights_ws), _ptr(x), stream_ptr())
+         _ptr(ln_b), _ptr(fc2), _ptr(sums_ws), _ptr(part), _ptr(weights_ws), _ptr(x), stream_ptr())
 
 
 # transformer fusion backward ----------------------------------------------------------------------------------------

@@ -336,7 +336,8 @@ def agent_parallel_block(torch, dist, dev, rank, world, precision):
     D = a2x_import.pkg("dist")
     order = {"vehicle": 0, "rsu": 1, "drone": 2}
     res = {}
-    for name, which, cls_ap in (("config4_cobevt", 4, "AgentParallelCoBEVT"), ("config2_where2comm", 2, "AgentParallelWhere2comm")):
+    for name, which, cls_ap in (("config4_cobevt", 4, "AgentParallelCoBEVT"), ("config2_where2comm", 2, "AgentParallelWhere2comm"),
+                                ("config3_v2xvit", 3, "AgentParallelV2XVit")):
         try:
             base = (["vehicle"] * 3 + ["rsu"] * 3 + ["drone"] * 2)
             agents = sorted([base[(i * 3) % 8] if world < 8 else base[i] for i in range(world)], key=lambda t: order[t]) \
@@ -375,10 +376,11 @@ def agent_parallel_block(torch, dist, dev, rank, world, precision):
                 single = {k: v.clone() for k, v in single.items() if k in ("psm", "rm", "obj")}
                 blk = {"agents": agents, "ms_single_gpu": ms_single}
                 mine = torch.from_numpy(w.pts[w.offs[rank]:w.offs[rank + 1]])
-                for transport in ("nccl", "peer"):
+                for transport in (("nccl", "peer") if which != 3 else ("nccl",)):
                     try:
                         ap = getattr(D, cls_ap)(w.model, agents, transport=transport)
-                        out, ms = timed(lambda: ap(mine, w.cfg["preprocess"]))
+                        extra = (w.dd_dev["prior_encoding"], w.dd_dev["spatial_correction_matrix"]) if which == 3 else ()
+                        out, ms = timed(lambda: ap(mine, w.cfg["preprocess"], *extra))
                         exact = all(torch.equal(out[k], single[k]) for k in ("psm", "rm", "obj"))
                         ok = torch.tensor([1 if exact else 0], device=dev)
                         dist.all_reduce(ok, op=dist.ReduceOp.MIN)

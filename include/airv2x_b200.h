@@ -238,10 +238,13 @@ int a2x_hgt_fold(const float* const* qw, const float* const* qb, const float* co
 int a2x_hgt_attention_fwd(const float* qkv, const int* types_dev, const float* key_mask, int n_agents, long long pix,
                           int heads, int dim_head, float scale, const a2x_output* out, a2x_stream_t stream);
 /* SplitAttn over the three pyramid-window branches + residual (split_attn.py:28-63):
- * x += sum_r softmax_r(fc2 relu(LN(fc1 mean_p(w0+w1+w2))))[r] * w_r. sums_ws: [n][C], weights_ws: [n][3][C]. */
+ * x += sum_r softmax_r(fc2 relu(LN(fc1 mean_p(w0+w1+w2))))[r] * w_r. sums_ws: [n][C] (written: the pooled sums, kept for
+ * the backward), partials_ws: [n][A2X_SPLIT_ATTN_CHUNKS][C] scratch (per-chunk sums reduced in a fixed order: the result
+ * is bit-reproducible and independent of how many agents share the call), weights_ws: [n][3][C]. */
+#define A2X_SPLIT_ATTN_CHUNKS 64
 int a2x_split_attn_fuse(const float* w0, const float* w1, const float* w2, int n_agents, long long pix, int C,
                         const float* fc1, const float* ln_gamma, const float* ln_beta, const float* fc2,
-                        float* sums_ws, float* weights_ws, float* x_inout, a2x_stream_t stream);
+                        float* sums_ws, float* partials_ws, float* weights_ws, float* x_inout, a2x_stream_t stream);
 
 /* Backward of the V2X-ViT kernels. hgt_attention_bwd: dqkv [n][pix][5C] (every slot written) from dout [n][pix][C].
  * hgt_fold_bwd: gradients of the fused projection (dw_fold [2][5C][C], db_fold [2][5C]) -> typed q/k/v linears (written)
