@@ -153,6 +153,61 @@ __global__ void __launch_bounds__(256) hgt_attention_kernel(const float* __restr
     }
 }
 
+// Cooperative variant (the one launched): a GROUP of DH / 4 lanes owns one (pixel, head) and every lane 4 of its DH
+// features. The thread-per-(pixel, agent, head) kernel above fetches a 128-byte row per thread with float4 loads — 32
+// different lines per request: ncu showed the L1 data pipe at 95 % of peak with the issue slots 8 % active and DRAM at a third
+// of its rate. Here the group stages the pixel's 5 n rows (q, k'(0), k'(1), v'(0), v'(1) of every agent: each read ONCE,
+// consecutive lanes = consecutive 16-byte chunks) in shared memory, dot products are reduced with log2(DH / 4) shuffles,
+// and every output row is stored by the group as one contiguous line.
+template <int DH>
+__global__ void __launch_bounds__(128) hgt_attention_coop_kernel(const float* __restrict__ qkv, const int* __restrict__ types,
+                                                                 const float* __restrict__ mask, int n, long long pix,
+                                                                 int heads, float scale, SplitOut out) {
+    constexpr int LPG = DH / 4;          // lanes per group
+    constexpr int GPB = 128 / LPG;       // groups per block
+    extern __shared__ float hsm[];       // [GPB][5 n][DH]
+    const int C = heads * DH;
+    const int g = threadIdx.x / LPG, s = threadIdx.x % LPG;
+    const long long G = (long long)blockIdx.x * GPB + g;
+    const int m = (int)(G % heads);
+    const long long p = G / heads;
+    const bool valid = p < pix;
+    float* my = hsm + (long long)g * (5 * n * DH);
+    const unsigned gmask = (LPG == 32 ? 0xffffffffu : ((1u << LPG) - 1u)) << ((threadIdx.x & 31) / LPG * LPG);
+    if (valid) {
+        for (int r = 0; r < 5 * n; ++r) {
+            const int a = r / 5, slot = r - a * 5;
+            *reinterpret_cast<float4*>(my + r * DH + 4 * s) =
+                *reinterpret_cast<const float4*>(qkv + ((long long)a * pix + p) * 5 * C + slot * C + m * DH + 4 * s);
+        }
+    }
+    __syncwarp(gmask);
+    if (!valid) return;
+    for (int i = 0; i < n; ++i) {
+        const int ti = types[i];
+        float4 q = *reinterpret_cast<const float4*>(my + (i * 5) * DH + 4 * s);
+        q.x *= scale; q.y *= scale; q.z *= scale; q.w *= scale;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float mx = -INFINITY, den = 0.f;
+        for (int j = 0; j < n; ++j) {
+            if (mask[(long long)j * pix + p] == 0.f) continue;       // group-uniform
+            const float4 k = *reinterpret_cast<const float4*>(my + (j * 5 + 1 + ti) * DH + 4 * s);
+            float d = fmaf(q.x, k.x, fmaf(q.y, k.y, fmaf(q.z, k.z, q.w * k.w)));
+#pragma unroll
+            for (int o = LPG / 2; o > 0; o >>= 1) d += __shfl_xor_sync(gmask, d, o);
+            const float mn = fmaxf(mx, d);
+            const float corr = __expf(mx - mn), e = __expf(d - mn);
+            den = den * corr + e;
+            const float4 v = *reinterpret_cast<const float4*>(my + (j * 5 + 3 + ti) * DH + 4 * s);
+            acc.x = fmaf(acc.x, corr, e * v.x); acc.y = fmaf(acc.y, corr, e * v.y);
+            acc.z = fmaf(acc.z, corr, e * v.z); acc.w = fmaf(acc.w, corr, e * v.w);
+            mx = mn;
+        }
+        const float inv = 1.f / den;  // no valid key -> NaN, like softmax over an all -inf row in the reference
+        store_split4(out, ((long long)i * pix + p) * C + m * DH + 4 * s, make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- split attention
 // sums[a][c] += sum_p (w0 + w1 + w2)[a][p][c]      (global average pool numerator)
 __global__ void __launch_bounds__(256) split_pool_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
@@ -323,8 +378,25 @@ int a2x_hgt_attention_fwd(const float* qkv, const int* types_dev, const float* k
     A2X_REQUIRE(out->cs == heads * dim_head, "hgt_attention_fwd: dense [.., heads*dim_head] output expected");
     SplitOut o;
     o.hi = out->hi; o.b16 = (__nv_bfloat16*)out->b16; o.ps = out->b16_plane;
-    const int g = vx_grid(pix * n_agents * heads);
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t csm = (size_t)(128 / (dim_head / 4)) * 5 * n_agents * dim_head * sizeof(float);   // [groups][5 n][DH]
+    if (csm <= 200 * 1024 && (dim_head == 16 || dim_head == 32 || dim_head == 64)) {
+        const long long groups = pix * heads, gpb = 128 / (dim_head / 4);
+        const unsigned blocks = (unsigned)((groups + gpb - 1) / gpb);
+#define A2X_HGT(DH)                                                                                                   \
+    do {                                                                                                              \
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(hgt_attention_coop_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm)); \
+        hgt_attention_coop_kernel<DH><<<blocks, 128, csm, st>>>(qkv, types_dev, key_mask, n_agents, pix, heads, scale, o); \
+    } while (0)
+        if (dim_head == 16) A2X_HGT(16);
+        else if (dim_head == 32) A2X_HGT(32);
+        else A2X_HGT(64);
+#undef A2X_HGT
+        A2X_LAUNCHED();
+        A2X_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const int g = vx_grid(pix * n_agents * heads);
     if (dim_head == 16) hgt_attention_kernel<16><<<g, 256, 0, st>>>(qkv, types_dev, key_mask, n_agents, pix, heads, scale, o);
     else if (dim_head == 32) hgt_attention_kernel<32><<<g, 256, 0, st>>>(qkv, types_dev, key_mask, n_agents, pix, heads, scale, o);
     else if (dim_head == 64) hgt_attention_kernel<64><<<g, 256, 0, st>>>(qkv, types_dev, key_mask, n_agents, pix, heads, scale, o);
@@ -482,6 +554,109 @@ __global__ void __launch_bounds__(128) hgt_attention_bwd_kernel(const float* __r
                     *reinterpret_cast<float4*>(dvo + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
                 }
             }
+        }
+    }
+}
+
+// Cooperative variant (the one launched), same layout of work as hgt_attention_coop_kernel: a group of DH / 4 lanes owns
+// one (pixel, head), stages the pixel's 6 n rows (q, k'(0), k'(1), v'(0), v'(1), dO of every agent: each read ONCE, coalesced)
+// in shared memory, keeps P and dS of the n x n agent pairs in a small per-group slab, reduces the dot products with
+// shuffles and stores every gradient row as one contiguous line. Phase A, per query agent i: P_i., dS_i., dq_i. Phase B, per
+// key agent j and query type ty: dk'_ty(j) = sum_{i of type ty} dS_ij (scale q_i), dv'_ty(j) = sum P_ij dO_i.
+template <int DH>
+__global__ void __launch_bounds__(128) hgt_attention_bwd_coop_kernel(const float* __restrict__ qkv, const int* __restrict__ types,
+                                                                     const float* __restrict__ mask,
+                                                                     const float* __restrict__ dout, int n, long long pix,
+                                                                     int heads, float scale, float* __restrict__ dqkv) {
+    constexpr int LPG = DH / 4;
+    constexpr int GPB = 128 / LPG;
+    extern __shared__ float hsm[];       // [GPB][6 n][DH] rows, then [GPB][2][n][n] P | dS
+    const int C = heads * DH;
+    const int g = threadIdx.x / LPG, s = threadIdx.x % LPG;
+    const long long G = (long long)blockIdx.x * GPB + g;
+    const int m = (int)(G % heads);
+    const long long p = G / heads;
+    const bool valid = p < pix;
+    float* my = hsm + (long long)g * (6 * n * DH);
+    float* sP = hsm + (long long)GPB * (6 * n * DH) + (long long)g * (2 * n * n);
+    float* sS = sP + n * n;
+    const unsigned gmask = (LPG == 32 ? 0xffffffffu : ((1u << LPG) - 1u)) << ((threadIdx.x & 31) / LPG * LPG);
+    if (valid) {
+        for (int r = 0; r < 6 * n; ++r) {
+            const int a = r / 6, slot = r - a * 6;
+            const float* src = slot < 5 ? qkv + ((long long)a * pix + p) * 5 * C + slot * C + m * DH + 4 * s
+                                        : dout + ((long long)a * pix + p) * C + m * DH + 4 * s;
+            *reinterpret_cast<float4*>(my + r * DH + 4 * s) = *reinterpret_cast<const float4*>(src);
+        }
+    }
+    __syncwarp(gmask);
+    if (!valid) return;
+    auto row = [&](int a, int slot) { return *reinterpret_cast<const float4*>(my + (a * 6 + slot) * DH + 4 * s); };
+    auto gsum = [&](float v) {
+#pragma unroll
+        for (int o = LPG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    };
+    // ---- phase A
+    for (int i = 0; i < n; ++i) {
+        const int ti = types[i];
+        float4 q = row(i, 0);
+        q.x *= scale; q.y *= scale; q.z *= scale; q.w *= scale;
+        const float4 go = row(i, 5);
+        float mx = -INFINITY;
+        for (int j = 0; j < n; ++j) {
+            float a = -INFINITY, bsum = 0.f;
+            if (mask[(long long)j * pix + p] != 0.f) {       // group-uniform
+                const float4 k = row(j, 1 + ti), v = row(j, 3 + ti);
+                a = gsum(fmaf(q.x, k.x, fmaf(q.y, k.y, fmaf(q.z, k.z, q.w * k.w))));
+                bsum = gsum(fmaf(go.x, v.x, fmaf(go.y, v.y, fmaf(go.z, v.z, go.w * v.w))));
+                mx = fmaxf(mx, a);
+            }
+            if (s == 0) {
+                sP[i * n + j] = a;
+                sS[i * n + j] = bsum;
+            }
+        }
+        __syncwarp(gmask);
+        float l = 0.f;
+        for (int j = 0; j < n; ++j) l += expf(sP[i * n + j] - mx);
+        const float inv = 1.f / l;
+        float Dv = 0.f;
+        for (int j = 0; j < n; ++j) Dv = fmaf(expf(sP[i * n + j] - mx) * inv, sS[i * n + j], Dv);
+        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp(gmask);       // every lane has read the raw scores before lane 0 overwrites them
+        for (int j = 0; j < n; ++j) {
+            const float pj = expf(sP[i * n + j] - mx) * inv;
+            const float ds = pj * (sS[i * n + j] - Dv);
+            __syncwarp(gmask);
+            if (s == 0) {
+                sP[i * n + j] = pj;
+                sS[i * n + j] = ds;
+            }
+            if (pj == 0.f) continue;                          // group-uniform (same values in every lane)
+            const float4 k = row(j, 1 + ti);
+            dq.x = fmaf(ds, k.x, dq.x); dq.y = fmaf(ds, k.y, dq.y); dq.z = fmaf(ds, k.z, dq.z); dq.w = fmaf(ds, k.w, dq.w);
+        }
+        *reinterpret_cast<float4*>(dqkv + ((long long)i * pix + p) * 5 * C + m * DH + 4 * s) =
+            make_float4(dq.x * scale, dq.y * scale, dq.z * scale, dq.w * scale);
+    }
+    __syncwarp(gmask);
+    // ---- phase B
+    for (int j = 0; j < n; ++j) {
+        for (int ty = 0; ty < 2; ++ty) {
+            float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
+            for (int i = 0; i < n; ++i) {
+                if (types[i] != ty) continue;
+                const float pj = sP[i * n + j];
+                if (pj == 0.f) continue;
+                const float ds = sS[i * n + j] * scale;       // s = (q * scale) . k'
+                const float4 q = row(i, 0), go = row(i, 5);
+                dk.x = fmaf(ds, q.x, dk.x); dk.y = fmaf(ds, q.y, dk.y); dk.z = fmaf(ds, q.z, dk.z); dk.w = fmaf(ds, q.w, dk.w);
+                dv.x = fmaf(pj, go.x, dv.x); dv.y = fmaf(pj, go.y, dv.y); dv.z = fmaf(pj, go.z, dv.z); dv.w = fmaf(pj, go.w, dv.w);
+            }
+            float* dko = dqkv + ((long long)j * pix + p) * 5 * C + (1 + ty) * C + m * DH + 4 * s;
+            *reinterpret_cast<float4*>(dko) = dk;
+            *reinterpret_cast<float4*>(dko + 2 * C) = dv;
         }
     }
 }
@@ -713,6 +888,25 @@ int a2x_hgt_attention_bwd(const float* qkv, const int* types_dev, const float* k
     A2X_REQUIRE(qkv && types_dev && key_mask && dout && dqkv && n_agents > 0 && n_agents <= a2x::HGT_MAX_AGENTS && pix > 0,
                 "hgt_attention_bwd: bad args (at most 12 agents)");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dim_head == 16 || dim_head == 32 || dim_head == 64) {
+        const long long gpb = 128 / (dim_head / 4), groups = pix * heads;
+        const size_t csm = (size_t)gpb * (6 * n_agents * dim_head + 2 * n_agents * n_agents) * sizeof(float);
+        if (csm <= 200 * 1024) {
+            const unsigned blocks = (unsigned)((groups + gpb - 1) / gpb);
+#define A2X_HGTB(DH)                                                                                                  \
+    do {                                                                                                              \
+        A2X_CHECK_CUDA(cudaFuncSetAttribute(a2x::hgt_attention_bwd_coop_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm)); \
+        a2x::hgt_attention_bwd_coop_kernel<DH><<<blocks, 128, csm, st>>>(qkv, types_dev, key_mask, dout, n_agents, pix, heads, scale, dqkv); \
+    } while (0)
+            if (dim_head == 16) A2X_HGTB(16);
+            else if (dim_head == 32) A2X_HGTB(32);
+            else A2X_HGTB(64);
+#undef A2X_HGTB
+            A2X_LAUNCHED();
+            A2X_CHECK_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     long long b = (pix * heads + 127) / 128;
     if (b > 148 * 16) b = 148 * 16;
     const size_t smem = (size_t)2 * n_agents * n_agents * 128 * sizeof(float);

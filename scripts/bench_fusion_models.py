@@ -83,7 +83,7 @@ def main():
         g = groups.setdefault(name, [0.0, 0])
         g[0] += a.elapsed_time(b)
         g[1] += 1
-    top = sorted(((k, round(v[0], 3), v[1]) for k, v in groups.items()), key=lambda x: -x[1])[:10]
+    top = sorted(((k, round(v[0], 3), v[1]) for k, v in groups.items()), key=lambda x: -x[1])[:24]
     print(json.dumps({"metric": "scenes/sec (eval fwd) %s %d-agent 60k-pt" % (which, len(types)), "value": 1000.0 / ms,
                       "ms_per_scene": ms, "agents": types, "train_step": train, "top_calls_ms": top}))
 
