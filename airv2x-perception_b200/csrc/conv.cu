@@ -133,8 +133,9 @@ static int check_shape(const a2x_conv_shape* s, bool transposed) {
             return 1;
         }
     } else {
-        if (!((s->ksize == 1 && s->stride == 1) || (s->ksize == 3 && (s->stride == 1 || s->stride == 2)))) {
-            set_error("conv needs (k=1,s=1) or (k=3,s in {1,2}), got k=%d s=%d", s->ksize, s->stride);
+        if (!((s->ksize == 1 && s->stride == 1) || (s->ksize == 3 && (s->stride == 1 || s->stride == 2)) ||
+              (s->ksize == 7 && s->stride == 2))) {
+            set_error("conv needs (k=1,s=1), (k=3,s in {1,2}) or the forward-only stem (k=7,s=2), got k=%d s=%d", s->ksize, s->stride);
             return 1;
         }
     }
@@ -594,7 +595,7 @@ extern "C" {
 
 int a2x_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, float* w_fwd, void* w_fwd16,
                          float* w_dgrad, void* w_dgrad16, a2x_stream_t stream) {
-    A2X_REQUIRE(w_oihw && cout > 0 && cin > 0 && (ksize == 1 || ksize == 3) && cout_pad >= cout, "bad pack args");
+    A2X_REQUIRE(w_oihw && cout > 0 && cin > 0 && (ksize == 1 || ksize == 3 || ksize == 7) && cout_pad >= cout, "bad pack args");
     const int kk = ksize * ksize;
     pack_conv_w_kernel<<<grid_for((long long)kk * cout_pad * cin), 256, 0, (cudaStream_t)stream>>>(
         w_oihw, cout, cin, kk, cout_pad, w_fwd, (__nv_bfloat16*)w_fwd16, w_dgrad, (__nv_bfloat16*)w_dgrad16);
@@ -690,6 +691,49 @@ static int conv2d_fwd_impl(const a2x_conv_shape* s, const a2x_operand* x, const 
     const int kk = s->ksize * s->ksize;
     A2X_REQUIRE(!stats || (!scale && !shift && !relu && !accumulate),
                 "conv2d_fwd: fused statistics are of the raw conv output");
+    if (s->ksize == 7) {
+        // 7x7 stride-2 padding-3 stem (BevEncode.conv1, sub_modules/lss_submodule.py:318): input row 2i + r - 3 = 2 (i + a) + hp
+        // is row i + a of parity view hp, a in {-2..1}: 49 taps over the four parity views of the stride-2 path, run as
+        // groups of 9 taps (x 3 split products = the kernel's tap table) accumulating into the fp32 output
+        A2X_REQUIRE(!scale && !shift && !relu && !accumulate && !stats && !residual && drop_p == 0.f && y->hi && !y->b16,
+                    "conv2d_fwd: the 7x7 stem writes the raw fp32 convolution only");
+        TgTap all[49];
+        int nt = 0;
+        for (int r = 0; r < 7; ++r)
+            for (int cc = 0; cc < 7; ++cc) {
+                const int oh = r - 3, ow = cc - 3;
+                const int hp = oh & 1, wp = ow & 1;            // parity of the input row / column (two's complement: -3 & 1 = 1)
+                TgTap t{};
+                t.map = (int16_t)(hp * 2 + wp);
+                t.dh = (int16_t)((oh - hp) / 2);
+                t.dw = (int16_t)((ow - wp) / 2);
+                t.dx = 0;
+                t.btap = r * 7 + cc;
+                all[nt++] = t;
+            }
+        for (int g0 = 0; g0 < 49; g0 += 9) {
+            TgParams p{};
+            p.tw_log2 = pick_tw_log2(ho, wo, TG_BM, 4, 7);
+            const int TW = 1 << p.tw_log2, TH = TG_BM >> p.tw_log2;
+            if (int r = build_fwd_maps(s, x, p.amap, TW, TH, 0, p.amap + 4, p.amap + 8)) return r;
+            const int ng = 49 - g0 < 9 ? 49 - g0 : 9;
+            for (int i = 0; i < ng; ++i) p.taps[i] = all[g0 + i];
+            p.ntaps = ng;
+            const int bn = bn_for(s->cout);
+            if (int r = make_w_map(&p.bmap, w->w32, kk, s->cout, s->cin, bn)) return r;
+            if (x->b16) {
+                p.ntaps = expand_split_taps(p.taps, p.ntaps, 4, kk);
+                if (int r = make_w_map(&p.bmap16, w->w16, 2 * kk, s->cout, s->cin, bn, 1)) return r;
+            }
+            p.kchunks32 = s->cin / 32;
+            p.kchunks16 = s->cin / 64;
+            set_plain_out(p, y, ho, wo, 1, 0, 0);
+            p.accumulate = g0 > 0;
+            p.stat_c = s->cout;
+            if (int r = run_tg(p, ho, wo, s->n, s->cout, (cudaStream_t)stream)) return r;
+        }
+        return 0;
+    }
     A2X_REQUIRE((!residual && drop_p == 0.f) || (s->ksize == 1 && !y->b16 && !relu && !accumulate),
                 "conv2d_fwd: the dropout / residual epilogue is the fp32-only token-wise linear one");
     if (s->ksize == 3 && s->stride == 1 && g_debug[7] != 1)

@@ -117,7 +117,9 @@ int a2x_conv2d_fwd(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weig
                    const float* scale, const float* shift, int relu, double* stats, a2x_stream_t stream);
 /* Same with act in {0 none, 1 ReLU, 2 GELU(erf)} and accumulate != 0: y = act(scale*conv + shift + y_previous)
  * (residual add in the epilogue). With ksize == 1 this is the token-wise nn.Linear of the transformer fusion
- * networks (cobevt_modules/swap_fusion_modules.py:40-45, base_transformer.py:16-28): rows = n*h*w tokens. */
+ * networks (cobevt_modules/swap_fusion_modules.py:40-45, base_transformer.py:16-28): rows = n*h*w tokens.
+ * ksize == 7 with stride == 2 (padding 3) is the forward-only stem of BevEncode (sub_modules/lss_submodule.py:318):
+ * raw fp32 output only (no scale / shift / act / accumulate / stats), weights packed with ksize 7. */
 int a2x_conv2d_fwd_ex(const a2x_conv_shape* s, const a2x_operand* x, const a2x_weights* w, const a2x_output* y,
                       const float* scale, const float* shift, int act, int accumulate, double* stats,
                       a2x_stream_t stream);

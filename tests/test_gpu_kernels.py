@@ -293,6 +293,20 @@ def test_conv_epilogue_batch_statistics(ops, case):
     assert float((stats - ref).abs().max() / ref.abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("case", [(2, 48, 80, 64, 64), (1, 21, 45, 128, 32), (3, 8, 8, 64, 96)])
+def test_conv7x7_stride2_stem(ops, case):
+    """7x7 stride-2 padding-3 conv (BevEncode.conv1, sub_modules/lss_submodule.py:318) as 49 taps over the four stride-2
+    parity views, six accumulating launches; odd sizes, borders (taps reaching 3 pixels outside) == F.conv2d"""
+    n, h, w, cin, cout = case
+    g = _g(41)
+    x, wt = rnd(g, n, cin, h, w), rnd(g, cout, cin, 7, 7) * 0.05
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = ops.Act(torch.full((n, ho, wo, cout), 7.0, device="cuda"))
+    ops.conv_fwd(ops.split(nhwc(x)), ops.pack_conv_weight(wt), 7, 2, y)
+    ref = F.conv2d(x.double(), wt.double(), stride=2, padding=3).permute(0, 2, 3, 1).float()
+    assert ref.shape == y.hi.shape and rel(y.hi, ref) < 2e-5
+
+
 def test_deconv_epilogue_batch_statistics(ops):
     g = _g(13)
     n, h, w, cin, cout, s = 2, 5, 9, 256, 128, 4

@@ -70,3 +70,40 @@ def test_full_size_properties():
     kept = kept.view(B * N, ls.D, ls.fH, ls.fW).cuda()
     mass = torch.einsum("ndhw,nchw->c", (depth * kept).double(), f1.double())
     assert float((a.double().sum((0, 2, 3)) - mass).abs().max()) < 1e-6 * float(mass.abs().max()) + 1e-3
+
+
+def test_bevencode_eval_matches_reference_golden():
+    """BevEncode (sub_modules/lss_submodule.py:312-349) on the tap-GEMM kernels — 7x7 stride-2 stem as 49 taps over the parity
+    views, BasicBlock residual adds in the GEMM epilogue, bilinear x4 / x2 (align_corners=True) on the ego-warp kernel —
+    against the output recorded from the REAL reference module and, everywhere, against the oracle. Tolerance 1e-3."""
+    import os
+
+    import a2x_import
+    from oracle import bevencode_oracle as BO, w2c_oracle as O
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(os.path.join(root, "tests", "golden", "bevencode_small.npz"))
+    in_c, out_c, H, W, seed = int(g["in_c"]), int(g["out_c"]), int(g["h"]), int(g["w"]), int(g["seed"])
+    L = a2x_import.pkg("lss")
+    m = L.BevEncode(in_c, out_c)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = m.state_dict()
+    sd.update(O.det_init_state_dict(shapes, seed=seed))
+    m.load_state_dict(sd)                       # same keys and shapes as the reference module (strict)
+    x = torch.randn(2, in_c, H, W, generator=torch.Generator().manual_seed(seed + 1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.eval()(x)
+    m.cuda().eval()
+    out = m(x.cuda())
+    assert tuple(out.shape) == (2, out_c, H, W)
+    err_g = float(np.abs(out[:, ::8, ::4, ::4].cpu().numpy() - g["eval_out"]).max())
+    with torch.no_grad():
+        ora = BO.bev_encode({k: v.cpu() for k, v in m.state_dict().items()}, x, training=False)
+    err_o = float((out.cpu() - ora).abs().max())
+    print("BevEncode: vs golden %.2e, vs oracle %.2e (|out| max %.2f)" % (err_g, err_o, float(ora.abs().max())))
+    assert err_g < 1e-3 and err_o < 1e-3
+    out2 = L.BevEncode(in_c, 5).cuda().eval()(x.cuda())          # an output width that is not a multiple of 32
+    assert tuple(out2.shape) == (2, 5, H, W)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(x.cuda())
