@@ -216,3 +216,29 @@ class BevEncode(torch.nn.Module):
             o = ops.Act(torch.empty(B, H, W, cpad, device=dev))
             ops.conv_fwd(v, ops.pack_conv_weight(last.weight.detach(), cout_pad=cpad), 1, 1, o, shift=bias)
             return o.hi[..., :self.outC].permute(0, 3, 1, 2)
+
+
+class CameraBranch(torch.nn.Module):
+    """LiftSplatShootEncoder (common_modules/airv2x_encoder.py:30-335) with the image trunk as a pluggable library call:
+    imgs -> trunk -> (depth distribution [B*N, D, fH, fW], image features [B*N, C, fH, fW]) -> lift + voxel pooling
+    (a2x_lift_splat_fwd) -> BevEncode (tap-GEMM kernels) -> {"spatial_features": [B, bevout, ny, nx]}.
+    `trunk` is any callable / nn.Module with CamEncode's contract (sub_modules/lss_submodule.py:50-190): the reference's is
+    EfficientNet-b0 with downloaded weights, not available offline, so it is not built here and its parity is unpinned.
+    args: the yaml's camera block (grid_conf, data_aug_conf.final_dim, img_downsample, img_features, bevout_feature)."""
+
+    def __init__(self, args, agent_type, trunk, device="cuda"):
+        super().__init__()
+        self.agent_type = agent_type
+        self.trunk = trunk
+        self.ls = LiftSplat(args["grid_conf"], args["data_aug_conf"]["final_dim"], args["img_downsample"], device)
+        self.bevencode = BevEncode(args["img_features"], args["bevout_feature"])
+        assert self.ls.nx[2] == 1, "one z bin: the pooled map has img_features channels (BevEncode's inC)"
+
+    def forward(self, data_dict):
+        cam = data_dict[self.agent_type]["batch_merged_cam_inputs"]
+        imgs = cam["imgs"]
+        depth, feat = self.trunk(imgs)
+        geom = self.ls.geometry(cam["rots"], cam["trans"], cam["intrinsics"], cam["post_rots"], cam["post_trans"])
+        bev = self.ls(depth, feat, geom)
+        x = self.bevencode(bev)
+        return {"spatial_features": x, "spatial_features_3d": x.unsqueeze(2)}

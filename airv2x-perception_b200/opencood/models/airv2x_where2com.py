@@ -196,6 +196,21 @@ class Airv2xWhere2com(nn.Module):
                     scene_len=torch.tensor(record_len, dtype=torch.int32, device=device))
 
     def _lidar(self, data_dict, device, layout):
+        """the engine's input dict: voxels (or raw clouds) per agent type, plus — B200 extension for the camera + lidar
+        configs — `data_dict[type]["camera_bev"]` = [n_type, 64, ny, nx], the `spatial_features` of that type's camera encoder
+        (lss.CameraBranch = LiftSplatShootEncoder with a pluggable image trunk), averaged with the pillar canvas as the
+        reference's fuse_bev does (common_modules/airv2x_base_model.py:167-177). Eval forward only."""
+        out = self._lidar_inputs(data_dict, device, layout)
+        cam = {}
+        for t in layout["agent_map"]:
+            v = data_dict.get(t, {}).get("camera_bev") if isinstance(data_dict.get(t), dict) else None
+            if v is not None:
+                cam[t] = v.to(device=device, dtype=torch.float32).permute(0, 2, 3, 1).contiguous()
+        if cam:
+            out["camera_bev"] = cam
+        return out
+
+    def _lidar_inputs(self, data_dict, device, layout):
         raw = data_dict.get("raw_points")
         if raw is not None:
             # B200 extension of the boundary: raw per-agent clouds instead of CPU-voxelised pillars.

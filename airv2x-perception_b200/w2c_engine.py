@@ -310,12 +310,15 @@ class W2CEngine:
         canvas = self._act("canvas", (n_total, ny, nx, 64))
         # split mode: the canvas only feeds the block-0 tap-GEMM, which reads the bf16 planes -> the fp32 plane is neither
         # cleared nor written, and `spatial_features.count_nonzero()` (airv2x_where2com.py:122) is counted by the scatter
-        hi = canvas.b16 is None
+        cam = lidar.get("camera_bev")      # {type: [n_type, ny, nx, 64]}: camera-encoder BEV maps to average with the pillars'
+        if cam and training:
+            raise NotImplementedError("camera + lidar fusion (fuse_bev) is implemented for the eval forward only")
+        hi = canvas.b16 is None or bool(cam)
         nzc = self._buf("canvas.nz", (1,), torch.int64)
         with self._on_side():   # the clears (180 MB of canvas planes) run beside the voxeliser / PFN statistics; joined before the scatter
             if hi:
                 canvas.hi.zero_()
-            else:
+            if canvas.b16 is not None:
                 canvas.b16.zero_()
             nzc.zero_()
         self._canvas_nz = nzc
@@ -363,6 +366,22 @@ class W2CEngine:
                 ops.pfn_scatter(vox, num, coords, geom, w, scale, shift, amap, canvas, seg=seg, nz=nzc, write_hi=hi)
         if not joined:
             self._join_side()
+        if cam:
+            # fuse_bev (common_modules/airv2x_base_model.py:167-177): the mean over the type's modality encoders of
+            # `spatial_features` = 0.5 * (pillar canvas + camera BEV), per agent of that type; comm_rate counts the fused map
+            half = self._buf("cam.half", (64,))
+            half.fill_(0.5)
+            tmp = self._buf("cam.tmp", (1, ny, nx, 64))
+            for t, bev in cam.items():
+                rows = layout.setdefault("agent_map_host", {}).get(t)
+                if rows is None:
+                    rows = layout["agent_map_host"][t] = [int(v) for v in layout["agent_map"][t].tolist()]
+                assert tuple(bev.shape) == (len(rows), ny, nx, 64), "camera_bev[%s] must be [n_%s, ny, nx, 64] (NHWC)" % (t, t)
+                for i, r in enumerate(rows):
+                    ops.dropout_apply(bev[i:i + 1], None, 0, Act(tmp), residual=canvas.hi[r:r + 1])    # pillars + camera
+                    ops.affine_act(tmp, half, None, False, canvas.narrow_n(r, 1))                      # * 0.5 -> fp32 + split planes
+            nzc.zero_()
+            ops.count_nonzero(canvas.hi, nzc)
         return canvas
 
     # ------------------------------------------------------------------ forward

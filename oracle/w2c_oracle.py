@@ -76,8 +76,10 @@ def scatter(pillar_features, coords, nx, ny, n_agents):
 
 
 # --------------------------------------------------------------------------------------------------- a7 extract
-def extract_features(sd, args, data_dict, training, buffers, keep=None):
-    """models/common_modules/airv2x_base_model.py:101-248 (per-type encoders, repack to scene-major)."""
+def extract_features(sd, args, data_dict, training, buffers, keep=None, camera_bev=None):
+    """models/common_modules/airv2x_base_model.py:101-248 (per-type encoders, repack to scene-major).
+    camera_bev: {type: [n_type, 64, ny, nx]} outputs of that type's camera encoder (LiftSplatShootEncoder): `fuse_bev`
+    (:167-177) averages the modalities' `spatial_features` per agent type."""
     per_type = {}
     for t in AGENT_TYPES:
         if t not in args["collaborators"] or len(data_dict[t]["batch_idxs"]) == 0:
@@ -90,6 +92,8 @@ def extract_features(sd, args, data_dict, training, buffers, keep=None):
         nx, ny, _ = [int(v) for v in la["point_pillar_scatter"]["grid_size"]]
         n_agents = int(lid["voxel_coords"][:, 0].max().item()) + 1
         per_type[t] = scatter(pf, lid["voxel_coords"], nx, ny, n_agents)
+        if camera_bev is not None and t in camera_bev:
+            per_type[t] = torch.stack([per_type[t], camera_bev[t]], 0).mean(0)
         if keep is not None:
             keep["pillar_features_" + t] = pf
     bsz = max(len(data_dict[t]["batch_idxs"]) for t in AGENT_TYPES)
@@ -232,11 +236,11 @@ def where2comm_fusion(sd, args, spatial_features, psm_single, record_len, traini
 
 
 # --------------------------------------------------------------------------------------------------- model forward
-def where2com_forward(sd, args, data_dict, training=False, keep=None):
+def where2com_forward(sd, args, data_dict, training=False, keep=None, camera_bev=None):
     """models/airv2x_where2com.py:117-179 (task == det). Returns (output_dict, updated BN buffers)."""
     buffers = {}
     mf = args["modality_fusion"]
-    sf, record_len = extract_features(sd, args, data_dict, training, buffers, keep)
+    sf, record_len = extract_features(sd, args, data_dict, training, buffers, keep, camera_bev)
     if keep is not None:
         keep["spatial_features"] = sf
         keep["record_len"] = record_len

@@ -107,3 +107,42 @@ def test_bevencode_eval_matches_reference_golden():
     m.train()
     with pytest.raises(NotImplementedError):
         m(x.cuda())
+
+
+def test_camera_branch_matches_oracle_composition():
+    """lss.CameraBranch = LiftSplatShootEncoder.forward (common_modules/airv2x_encoder.py:308-335) with a pluggable trunk:
+    geometry -> lift + voxel pooling -> BevEncode, against the oracle's composition of the same pieces (each pinned to the
+    real reference). The stub trunk returns a seeded depth distribution and feature map."""
+    import a2x_import
+    from oracle import bevencode_oracle as BO, w2c_oracle as O
+
+    L = a2x_import.pkg("lss")
+    grid = {"xbound": [-16.0, 16.0, 0.5], "ybound": [-12.0, 12.0, 0.5], "zbound": [-10.0, 10.0, 20.0], "ddiscr": [2, 30, 24], "mode": "LID"}
+    final_dim, down, camC, outC, B, N = [64, 96], 8, 64, 64, 2, 3
+    args = {"grid_conf": grid, "data_aug_conf": {"final_dim": final_dim}, "img_downsample": down, "img_features": camC,
+            "bevout_feature": outC}
+    fr = LO.create_frustum(final_dim, down, grid["ddiscr"], grid["mode"])
+    D, fH, fW = fr.shape[:3]
+    gen = torch.Generator().manual_seed(5)
+    depth = torch.softmax(torch.randn(B * N, D, fH, fW, generator=gen) * 2, 1)
+    feat = torch.randn(B * N, camC, fH, fW, generator=gen)
+    rig = LO.synth_cameras(B, N, 9, final_dim)
+    branch = L.CameraBranch(args, "vehicle", lambda imgs: (depth.cuda(), feat.cuda()))
+    shapes = {k: tuple(v.shape) for k, v in branch.bevencode.state_dict().items()}
+    sd = branch.bevencode.state_dict()
+    sd.update(O.det_init_state_dict(shapes, seed=3))
+    branch.bevencode.load_state_dict(sd)
+    branch.cuda().eval()
+    dd = {"vehicle": {"batch_merged_cam_inputs": {"imgs": torch.zeros(B, N, 3, *final_dim), "rots": rig[0], "trans": rig[1],
+                                                  "intrinsics": rig[2], "post_rots": rig[3], "post_trans": rig[4]}}}
+    out = branch(dd)["spatial_features"]
+    dx, bx, nx = LO.gen_dx_bx(grid["xbound"], grid["ybound"], grid["zbound"])
+    geom = LO.get_geometry(fr, *rig)
+    x = LO.lift(depth, feat).view(B, N, camC, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+    pooled = LO.voxel_pooling_exact(geom, x, dx, bx, nx).float()
+    with torch.no_grad():
+        ref = BO.bev_encode({k: v.cpu() for k, v in branch.bevencode.state_dict().items()}, pooled, training=False)
+    assert tuple(out.shape) == tuple(ref.shape) == (B, outC, 48, 64)
+    err = float((out.cpu() - ref).abs().max())
+    print("CameraBranch vs oracle composition: %.2e (|ref| max %.2f)" % (err, float(ref.abs().max())))
+    assert err < 1e-3

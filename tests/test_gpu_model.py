@@ -377,3 +377,49 @@ def test_torch_library_ops_schema_fake_autograd_and_autocast(small):
     assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in params)
     with pytest.raises(Exception):                            # no CPU implementation is registered
         torch.ops.a2x.fused_forward(key, [p.detach().cpu() for p in params], shape)
+
+
+def test_camera_lidar_fuse_bev_eval(small):
+    """camera + lidar configs: `data_dict[type]["camera_bev"]` (the camera encoder's spatial_features) is averaged with the
+    pillar canvas per agent type — fuse_bev, common_modules/airv2x_base_model.py:167-177 — before the backbone. Eval logits
+    and comm_rate against the oracle fed the same camera maps; the training paths refuse."""
+    cfg, gold, model, sd, dd = small
+    model.load_state_dict(sd)
+    model.eval()
+    args = cfg["model_args"]
+    g = torch.Generator().manual_seed(11)
+    cam = {}
+    dd = {k: (dict(v) if isinstance(v, dict) else v) for k, v in dd.items()}
+    for t in O.AGENT_TYPES:
+        n = int(sum(dd[t]["record_len"])) if t in dd and len(dd[t]["batch_idxs"]) else 0
+        if n == 0:
+            continue
+        nx, ny, _ = [int(v) for v in args[t]["lidar"]["point_pillar_scatter"]["grid_size"]]
+        cam[t] = torch.relu(torch.randn(n, 64, ny, nx, generator=g)) * 0.3      # a ReLU-sparse map, like BevEncode's input side
+        dd[t]["camera_bev"] = cam[t]
+    assert len(cam) >= 2
+    keep = {}
+    with torch.no_grad():
+        out = model(C.to_device(dd, "cuda"))
+        out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items()}   # views of the engine's output buffer
+        mask_gpu = C.engine_buf(model, "mask").cpu().clone()
+        ref, _ = O.where2com_forward(sd, args, dd, training=False, keep=keep, camera_bev=cam)
+        # dense camera maps put many confidence values next to the communication threshold: a mask pixel may flip under
+        # 1e-4 perturbations; require that only such pixels differ, then compare with the oracle using the CUDA mask
+        own = keep["mask"].reshape(mask_gpu.shape)
+        diff = own != mask_gpu
+        thr = float(args["where2com_fusion"]["communication"]["threshold"])
+        if int(diff.sum()):
+            assert float((keep["smooth"].reshape(mask_gpu.shape)[diff] - thr).abs().max()) < 1e-4
+            ref, _ = O.where2com_forward(sd, args, dd, training=False, keep={"mask_override": mask_gpu}, camera_bev=cam)
+        base = model(C.to_device({k: ({kk: vv for kk, vv in v.items() if kk != "camera_bev"} if isinstance(v, dict) else v)
+                                  for k, v in dd.items()}, "cuda"))
+    print("fuse_bev: %d mask pixels flipped near the threshold" % int(diff.sum()))
+    for k in ("psm", "rm", "obj"):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < TOL, k
+    assert abs(out["comm_rate"] - ref["comm_rate"]) <= 2
+    assert float((out["psm"] - base["psm"]).abs().max()) > 1e-2          # the camera maps do change the result
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model.train_step(C.to_device(dd, "cuda"), O.make_labels(5, 1, out["psm"].shape[2], out["psm"].shape[3], args["anchor_number"]))
+    model.eval()
