@@ -341,7 +341,10 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream
     p.lbo_bytes = g_debug[2] > 0 ? (uint32_t)g_debug[2] : (uint32_t)WG_ATOM_BYTES;
     p.sbo_bytes = g_debug[3] > 0 ? (uint32_t)g_debug[3] : 512u;
     p.layout = g_debug[5] > 0 ? (uint32_t)g_debug[5] : 1u;
-    const int bn = p.cb >= 128 ? 128 : (p.cb >= 64 ? 64 : 32);
+    // one tap (1x1 conv = the token-wise linears), split mode, wide b side: 256-column tiles halve the re-reads of the A
+    // operand (these launches are bound by operand traffic: 761 MB of DRAM reads for 504 MB of operands at 128 x 128)
+    const bool wide = split && p.ntaps == 1 && p.cb % 256 == 0 && g_debug[4] != 1;
+    const int bn = wide ? 256 : p.cb >= 128 ? 128 : (p.cb >= 64 ? 64 : 32);
     const int tpc = (p.ntaps % 3 == 0 && bn <= 128) ? 3 : 1;
     p.n_tiles_b = (p.cb + bn - 1) / bn;
     const int tiles_a = (p.ca + 127) / 128;
@@ -349,7 +352,7 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream
     const int total_tiles = n_img * p.tiles_h * p.tiles_w;
     const int sms = 148;
     const int blocks_mn = tiles_a * p.n_tiles_b * tap_groups;
-    int ksplit = (tpc * bn > 256) ? sms / blocks_mn : (2 * sms + blocks_mn - 1) / blocks_mn;  // 512 TMEM columns => 1 CTA / SM
+    int ksplit = (tpc * bn >= 256) ? sms / blocks_mn : (2 * sms + blocks_mn - 1) / blocks_mn;  // 512 TMEM columns / 192 KB of stages => 1 CTA / SM
     if (ksplit > total_tiles) ksplit = total_tiles;
     if (ksplit < 1) ksplit = 1;
     p.tiles_per_cta = (total_tiles + ksplit - 1) / ksplit;
@@ -359,6 +362,7 @@ static int run_wg(WgParams& p, int gh, int gw, int n_img, bool split, cudaStream
             if (bn == 128) return launch_wg<128, 3, 3, true>(p, ksplit, tiles_a, tap_groups, st);
             if (bn == 64) return launch_wg<64, 3, 4, true>(p, ksplit, tiles_a, tap_groups, st);
         } else {
+            if (bn == 256) return launch_wg<256, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
             if (bn == 128) return launch_wg<128, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
             if (bn == 64) return launch_wg<64, 1, 4, true>(p, ksplit, tiles_a, tap_groups, st);
         }
