@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(64 + TG_EPW * 32) tapgemm_kernel(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                int t = tile % tiles_m;
-                const int n0 = (tile / tiles_m) * BN;
+                int t = tile / tiles_n;                      // column tile fastest: the CTAs that share a pixel tile run together,
+                const int n0 = (tile % tiles_n) * BN;        // so its A operand is fetched from HBM once (wide linears: 3 - 5 column tiles)
                 const int tw_i = t % p.tiles_w;
                 t /= p.tiles_w;
                 const int th_i = t % p.tiles_h;
@@ -470,8 +470,8 @@ __global__ void __launch_bounds__(64 + TG_EPW * 32) tapgemm_kernel(const __grid_
         e.bz = nullptr; e.bscale = e.bshift = e.bmean = e.binvstd = nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            int t = tile % tiles_m;
-            const int n0 = (tile / tiles_m) * BN;
+            int t = tile / tiles_n;
+            const int n0 = (tile % tiles_n) * BN;
             const int tw_i = t % p.tiles_w;
             t /= p.tiles_w;
             const int th_i = t % p.tiles_h;
