@@ -409,7 +409,8 @@ class CoBEVTEngine(W2CEngine):
                 dXs, g_out = split_of(dX, "bwd.dXs"), dX
             else:   # gradient w.r.t. the sublayer's last linear = stream gradient through that site's dropout mask
                 dXs = self._act("bwd.dXs", dX.shape)
-                ops.dropout_apply(dX, drop, sl["site_o"], dXs)
+                # the fp32 plane is only read by the bias gradient of the feed-forward's second linear (to_out has no bias)
+                ops.dropout_apply(dX, drop, sl["site_o"], dXs, write_hi=sl["kind"] == "ffn")
                 g_out = dXs.hi
             if sl["kind"] == "ffn":
                 lin_wgrad(sl["hid"], dXs, pre + ".fn.net.3.weight")

@@ -24,35 +24,57 @@ __device__ __forceinline__ float gelu_df(float x) {
 template <int MODE>
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ y, const float* __restrict__ aux,
                                                       const float* res, long long n8, DropArgs d, SplitOut out) {
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n8; g += (long long)gridDim.x * blockDim.x) {
-        float m[8];
-        if (d.thresh != 0) {
-            drop_mult8(d, g, m);
-        } else {
+    // U independent groups of 8 elements per thread and iteration: all loads of the iteration are issued before the first
+    // use (the one-group loop was latency-bound: 2.3x off the HBM rate with two loads in flight per thread)
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; g0 < n8; g0 += stride * U) {
+        float4 ya[U], yb[U], xa[U], xb[U];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) m[k] = 1.f;
-        }
-        const float4 a = reinterpret_cast<const float4*>(y)[2 * g], b = reinterpret_cast<const float4*>(y)[2 * g + 1];
-        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        if (MODE == 1) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = gelu_f(v[k]) * m[k];
-        } else if (MODE == 2) {
-            const float4 p = reinterpret_cast<const float4*>(aux)[2 * g], q = reinterpret_cast<const float4*>(aux)[2 * g + 1];
-            const float x[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = v[k] * m[k] * gelu_df(x[k]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] *= m[k];
-            if (res != nullptr) {
-                const float4 p = reinterpret_cast<const float4*>(res)[2 * g], q = reinterpret_cast<const float4*>(res)[2 * g + 1];
-                v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
-                v[4] += q.x; v[5] += q.y; v[6] += q.z; v[7] += q.w;
+        for (int u = 0; u < U; ++u) {
+            const long long g = g0 + u * stride;
+            if (g < n8) {
+                ya[u] = reinterpret_cast<const float4*>(y)[2 * g];
+                yb[u] = reinterpret_cast<const float4*>(y)[2 * g + 1];
+                if (MODE == 2) {
+                    xa[u] = reinterpret_cast<const float4*>(aux)[2 * g];
+                    xb[u] = reinterpret_cast<const float4*>(aux)[2 * g + 1];
+                } else if (MODE == 0 && res != nullptr) {
+                    xa[u] = reinterpret_cast<const float4*>(res)[2 * g];
+                    xb[u] = reinterpret_cast<const float4*>(res)[2 * g + 1];
+                }
             }
         }
-        store_split4(out, 8 * g, make_float4(v[0], v[1], v[2], v[3]));
-        store_split4(out, 8 * g + 4, make_float4(v[4], v[5], v[6], v[7]));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long g = g0 + u * stride;
+            if (g >= n8) break;
+            float m[8];
+            if (d.thresh != 0) {
+                drop_mult8(d, g, m);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) m[k] = 1.f;
+            }
+            float v[8] = {ya[u].x, ya[u].y, ya[u].z, ya[u].w, yb[u].x, yb[u].y, yb[u].z, yb[u].w};
+            if (MODE == 1) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = gelu_f(v[k]) * m[k];
+            } else if (MODE == 2) {
+                const float x[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = v[k] * m[k] * gelu_df(x[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] *= m[k];
+                if (res != nullptr) {
+                    v[0] += xa[u].x; v[1] += xa[u].y; v[2] += xa[u].z; v[3] += xa[u].w;
+                    v[4] += xb[u].x; v[5] += xb[u].y; v[6] += xb[u].z; v[7] += xb[u].w;
+                }
+            }
+            store_split4(out, 8 * g, make_float4(v[0], v[1], v[2], v[3]));
+            store_split4(out, 8 * g + 4, make_float4(v[4], v[5], v[6], v[7]));
+        }
     }
 }
 
