@@ -5,8 +5,11 @@
 //
 // A persistent CTA owns one head and walks over windows. Two warpgroups: the LOADER (warps 4-7) gathers the q / k / v (/ dO)
 // rows of the next window from global memory, splits them and fills one of two tile buffers; the COMPUTE group (warps
-// 0-7: WT_NS = 2 threads r, r + 128 share token r = TMEM lane r and take 64 score columns / 16 output features each,
-// exchanging the row max / sum / D through shared memory) issues the MMAs, runs the softmax and the epilogue. full / empty mbarriers
+// 0-7: WT_NS = 2 threads r, r + 128 share token r = TMEM lane r; thread h takes the 16-column key groups (one agent's 4 x 4
+// tokens) g = 2 k + h and 16 output features, exchanging the row max / sum / D through shared memory) issues the MMAs,
+// runs the softmax and the epilogue. Keys beyond the last valid agent (the padding of the agent axis) are never touched:
+// the score / probability / gradient tiles have ne = 16 (last valid agent + 1) columns, K / V rows beyond ne are not loaded,
+// and the interleaved group ownership splits the remaining agents evenly between the two threads of a row. full / empty mbarriers
 // per buffer (empty is arrived by tcgen05.commit of the window's last MMA), so global latency is off the compute path.
 // Every operand is the bf16 split pair of an fp32 row, kept side by side in ONE 128-byte shared-memory row
 // [hi(32) | lo(32)] with the 128-byte swizzle, so a tile is simply 128 rows x 128 B and the UMMA descriptors decide how
@@ -34,6 +37,9 @@ constexpr int WT_S2 = 2 * WT_W - 1;
 constexpr int WT_DH = 32;
 constexpr int WT_NS = 2;                    // compute threads per score row (4 measured no faster: the chain is sync / MMA latency)
 constexpr int WT_CPT = 128 / WT_NS;         // score columns per thread
+constexpr int WT_GPT = WT_CPT / 16;         // 16-column key groups (one agent's 4 x 4 tokens) per thread: share h owns the
+                                            // groups g = WT_NS k + h, so that the valid agents (a prefix) split evenly between
+                                            // the threads of a row; register slot 16 k + i <-> key column 16 (WT_NS k + h) + i
 constexpr int WT_DPT = WT_DH / WT_NS;       // output features per thread
 constexpr int WT_THREADS = 128 * (WT_NS + 1);
 constexpr int WT_AUX = 4096 + 4096 + 2 * 1024 + 256 + 3 * WT_NS * 512;   // bias | bias gradient | token tables (2) | barriers, TMEM slot | row max / sum / D exchange
@@ -101,18 +107,18 @@ __device__ __forceinline__ void wt_bar() { asm volatile("bar.sync 1, %0;" ::"n"(
 template <int NT>
 __device__ __forceinline__ void wt_load_tiles(uint8_t* tile0, const uint32_t (&toff)[NT], const float* const (&src)[NT],
                                               const long long (&rs)[NT], const float (&scale)[NT],
-                                              const long long* sTok, int n, int tl) {
+                                              const long long* sTok, const int (&nrows)[NT], int tl) {
 #pragma unroll
     for (int k0 = 0; k0 < NT; k0 += 2) {      // two tensors (16 float4 registers) in flight at a time
         float4 a[2][4], b[2][4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int idx = tl + it * 128;
-            if (idx < n * 4) {
-                const long long tok = sTok[idx >> 2];
+            {
+                const long long tok = sTok[idx >> 2];      // all 128 slots of the table hold a valid token index
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    if (k0 + k < NT) {
+                    if (k0 + k < NT && idx < nrows[k0 + k] * 4) {
                         const float4* g = reinterpret_cast<const float4*>(src[k0 + k] + tok * rs[k0 + k] + (idx & 3) * 8);
                         a[k][it] = __ldg(g);
                         b[k][it] = __ldg(g + 1);
@@ -126,7 +132,7 @@ __device__ __forceinline__ void wt_load_tiles(uint8_t* tile0, const uint32_t (&t
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int idx = tl + it * 128;
-                    if (idx < n * 4) {
+                    if (idx < nrows[k0 + k] * 4) {
                         float4 x = a[k][it], y = b[k][it];
                         const float sc = scale[k0 + k];
                         x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
@@ -167,24 +173,38 @@ __device__ __forceinline__ void wt_mma_pv(uint32_t tacc, uint32_t plane_addr, ui
     }
 }
 
-// this thread's share (columns CPT h .. CPT h + CPT - 1) of score row r from TMEM (+ relative-position bias, key mask)
-// -> s[CPT]; returns the maximum over the share
-__device__ __forceinline__ float wt_scores(uint32_t trow, int n, int r, int h, uint32_t kmask, const float* sB, int L, float* s) {
-    const int j0 = WT_CPT * h;
+// this thread's share (key groups g = WT_NS k + h < n / 16) of score row r from TMEM (+ relative-position bias) -> s[CPT];
+// groups of masked agents and groups beyond n get -inf without touching TMEM or the table. Returns the maximum over the
+// share; `gv` = bit k set when group k holds keys.
+__device__ __forceinline__ float wt_scores(uint32_t trow, int n, int r, int h, uint32_t kmask, const float* sB, int L, float* s,
+                                           uint32_t& gv) {
+    gv = 0;
 #pragma unroll
-    for (int c = 0; c < WT_CPT / 32; ++c)
-        if (j0 + 32 * c < n) tmem_ld_32x32(trow + j0 + 32 * c, s + 32 * c);
+    for (int k = 0; k < WT_GPT; ++k) {
+        const int g = WT_NS * k + h;
+        if (16 * g < n && ((kmask >> g) & 1u)) {
+            tmem_ld_32x16(trow + 16 * g, s + 16 * k);
+            gv |= 1u << k;
+        }
+    }
     tmem_ld_wait();
     const int li = r >> 4, i1 = (r >> 2) & 3, i2 = r & 3;
-    const int base = ((li + L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - (WT_CPT / 16) * h * WT_S2 * WT_S2;
+    const int base = ((li + L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - h * WT_S2 * WT_S2;
     float m = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < WT_CPT; ++jj) {
-        const int sub = ((jj >> 4) * WT_S2 + ((jj >> 2) & 3)) * WT_S2 + (jj & 3);
-        const bool ok = j0 + jj < n && ((kmask >> ((WT_CPT / 16) * h + (jj >> 4))) & 1u);
-        const float v = ok ? s[jj] + sB[base - sub] : -INFINITY;
-        s[jj] = v;
-        m = fmaxf(m, v);
+    for (int k = 0; k < WT_GPT; ++k) {
+        if ((gv >> k) & 1u) {      // uniform over the CTA's threads of this share
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int sub = ((WT_NS * k) * WT_S2 + ((i >> 2) & 3)) * WT_S2 + (i & 3);
+                const float v = s[16 * k + i] + sB[base - sub];
+                s[16 * k + i] = v;
+                m = fmaxf(m, v);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s[16 * k + i] = -INFINITY;
+        }
     }
     return m;
 }
@@ -194,6 +214,12 @@ __device__ __forceinline__ void wt_tmem_ld_dpt(uint32_t taddr, float* v) {
     else tmem_ld_32x8(taddr, v);
 }
 
+// keys beyond the last valid agent are never touched (padded agents trail: CoBEVT's key mask is the padding of the agent
+// axis): the score / probability / gradient tiles have ne = 16 * (highest valid agent + 1) columns instead of n
+__device__ __forceinline__ int wt_keys(uint32_t kmask, int L) {
+    const uint32_t m = kmask & (L >= 32 ? 0xffffffffu : ((1u << L) - 1u));
+    return m == 0 ? 16 : 16 * (32 - __clz(m));
+}
 __device__ __forceinline__ uint32_t wt_kmask(const WinTcParams& p, int b) {
     if (p.key_mask == nullptr) return 0xffffffffu;
     uint32_t k = 0;
@@ -267,12 +293,17 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
         // ------------------------------------------------------------------ loader warpgroup
         const int tl = tid - 128 * WT_NS;
         int it = 0;
+        int lb = -1, lne = n;      // scene of the previous window, its effective key count
         for (int win = blockIdx.x / p.heads; win < num_windows; win += G, ++it) {
             const int buf = it & 1;
             uint8_t* tb = sm.base + buf * BUF_TILES * TS;
             const int y = win % Y, x = (win / Y) % X, b = win / (Y * X);
             mbar_wait(&sm.empty[buf], ((it >> 1) & 1) ^ 1);     // the MMAs that read this buffer have retired
-            if (tl < n) sm.sTok[buf * 128 + tl] = wt_token(p, b, x, y, X, Y, tl);
+            sm.sTok[buf * 128 + tl] = wt_token(p, b, x, y, X, Y, tl < n ? tl : 0);
+            if (b != lb) {
+                lne = wt_keys(wt_kmask(p, b), p.L);
+                lb = b;
+            }
             wt_bar_load();
             const float* q0 = p.qkv + head * WT_DH;
             if (BWD) {
@@ -280,13 +311,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
                 const float* const src[4] = {q0, q0 + D, q0 + 2 * D, p.dout + head * WT_DH};
                 const long long rs[4] = {3LL * D, 3LL * D, 3LL * D, (long long)D};
                 const float sc[4] = {p.scale, 1.f, 1.f, 1.f};
-                wt_load_tiles<4>(tb, toff, src, rs, sc, sm.sTok + buf * 128, n, tl);   // loads of 2 tensors in flight at a time
+                const int nr[4] = {n, lne, lne, n};   // K / V rows of the trailing masked agents are not needed
+                wt_load_tiles<4>(tb, toff, src, rs, sc, sm.sTok + buf * 128, nr, tl);   // loads of 2 tensors in flight at a time
             } else {
                 const uint32_t toff[3] = {0, TS, 4 * TS};
                 const float* const src[3] = {q0, q0 + D, q0 + 2 * D};
                 const long long rs[3] = {3LL * D, 3LL * D, 3LL * D};
                 const float sc[3] = {p.scale, 1.f, 1.f};
-                wt_load_tiles<3>(tb, toff, src, rs, sc, sm.sTok + buf * 128, n, tl);
+                const int nr[3] = {n, lne, lne};
+                wt_load_tiles<3>(tb, toff, src, rs, sc, sm.sTok + buf * 128, nr, tl);
             }
             fence_proxy_async();
             mbar_arrive(&sm.full[buf]);
@@ -295,21 +328,20 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
         // ------------------------------------------------------------------ compute warpgroups (WT_NS threads per row)
         const int r = tid & 127, h = tid >> 7;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)n, 0, 0);
-        const int nk = n >> 4;
+        const int nkq = n >> 4;                       // k-steps over the QUERIES (dV = P^T dO, dK = dS^T Q)
         const int li = r >> 4, i1 = (r >> 2) & 3, i2 = r & 3;
-        const int bbase = ((li + p.L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - (WT_CPT / 16) * h * WT_S2 * WT_S2;
-        const uint32_t tacc = trow + 256 + WT_CPT * h;   // backward: this thread's columns of sum_windows dS (bias gradient)
+        const int bbase = ((li + p.L - 1) * WT_S2 + (i1 + WT_W - 1)) * WT_S2 + (i2 + WT_W - 1) - h * WT_S2 * WT_S2;
+        const uint32_t tacc = trow + 256;   // backward: sum_windows dS (bias gradient); this thread's groups at + 16 (WT_NS k + h)
         float* exM = sm.sEx;                       // [NS][128] row max
         float* exS = sm.sEx + WT_NS * 128;         // row sum
         float* exD = sm.sEx + 2 * WT_NS * 128;     // D
-        const bool live = WT_CPT * h < n;          // this share holds keys (small n: the other shares idle through the barriers)
+        int ne = n;                                   // effective key count of the current scene (wt_keys)
         if (BWD) {
             float z[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) z[j] = 0.f;
 #pragma unroll
-            for (int c = 0; c < WT_CPT / 32; ++c) tmem_st_32x32(tacc + 32 * c, z);
+            for (int k = 0; k < WT_GPT; ++k) tmem_st_32x16(tacc + 16 * (WT_NS * k + h), z);
             tmem_st_wait();
         }
         uint32_t ph = 0;
@@ -323,8 +355,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
             const int b = win / (Y * X);
             if (b != b_seen) {          // L dependent global loads: once per scene, not per window (forward 0.89 -> 0.82 ms)
                 kmask = wt_kmask(p, b);
+                ne = wt_keys(kmask, p.L);
                 b_seen = b;
             }
+            const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)ne, 0, 0);
+            const int nk = ne >> 4;                   // k-steps over the KEYS (O = P V, dQ = dS K)
             mbar_wait(&sm.full[buf], (it >> 1) & 1);
             const long long tok = r < n ? sm.sTok[buf * 128 + r] : 0;
             if (tid == 0) {
@@ -337,24 +372,38 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
             ph ^= 1;
             tc_fence_after();
             float s[WT_CPT];
-            exM[h * 128 + r] = wt_scores(trow, n, r, h, kmask, sm.sB, p.L, s);
+            uint32_t gv;      // bit k: key group WT_NS k + h holds valid keys (the others: masked agent, or beyond ne)
+            exM[h * 128 + r] = wt_scores(trow, ne, r, h, kmask, sm.sB, p.L, s, gv);
             wt_bar();
             float m = exM[r];
 #pragma unroll
             for (int k = 1; k < WT_NS; ++k) m = fmaxf(m, exM[k * 128 + r]);
             float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < WT_CPT; ++j) {
-                s[j] = __expf(s[j] - m);
-                sum += s[j];
+            for (int k = 0; k < WT_GPT; ++k) {
+                if ((gv >> k) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        s[16 * k + i] = __expf(s[16 * k + i] - m);
+                        sum += s[16 * k + i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s[16 * k + i] = 0.f;
+                }
             }
             exS[h * 128 + r] = sum;
             if (!BWD) {
                 // every thread has read its S columns and the S MMAs have retired: P may overwrite Q / K, O may overwrite S
-                if (r < n && live) {
+                if (r < n) {   // tiles have n rows: no row >= n; masked groups below ne store their zeros (the MMA reads them)
 #pragma unroll
-                    for (int c = 0; c < WT_CPT / 8; ++c)
-                        if (WT_CPT * h + c * 8 < n) wt_store8_planes(tb, TS, r, (WT_CPT / 8) * h + c, s + c * 8);   // tiles have n rows: no row >= n
+                    for (int k = 0; k < WT_GPT; ++k) {
+                        const int g = WT_NS * k + h;
+                        if (16 * g < ne) {
+                            wt_store8_planes(tb, TS, r, 2 * g, s + 16 * k);
+                            wt_store8_planes(tb, TS, r, 2 * g + 1, s + 16 * k + 8);
+                        }
+                    }
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -391,21 +440,25 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
                 const float inv = 1.f / tot;
 #pragma unroll
                 for (int j = 0; j < WT_CPT; ++j) s[j] *= inv;                    // P
-                if (r < n && live) {
+                if (r < n) {
 #pragma unroll
-                    for (int c = 0; c < WT_CPT / 8; ++c)
-                        if (WT_CPT * h + c * 8 < n) wt_store8_planes(tP, TS, r, (WT_CPT / 8) * h + c, s + c * 8);
+                    for (int k = 0; k < WT_GPT; ++k) {
+                        const int g = WT_NS * k + h;
+                        if (16 * g < ne) {      // masked groups below ne store their zeros (the MMAs read them)
+                            wt_store8_planes(tP, TS, r, 2 * g, s + 16 * k);
+                            wt_store8_planes(tP, TS, r, 2 * g + 1, s + 16 * k + 8);
+                        }
+                    }
                 }
                 float Dv = 0.f;                                                   // this share of D_i = sum_j P_ij dP_ij
 #pragma unroll
-                for (int c = 0; c < WT_CPT / 32; ++c) {
-                    if (WT_CPT * h + c * 32 < n) {
-                        float dp[32];
-                        tmem_ld_32x32(trow + 128 + WT_CPT * h + c * 32, dp);
+                for (int k = 0; k < WT_GPT; ++k) {
+                    if ((gv >> k) & 1u) {       // P = 0 elsewhere; dP columns of masked / absent groups are never read
+                        float dp[16];
+                        tmem_ld_32x16(trow + 128 + 16 * (WT_NS * k + h), dp);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (WT_CPT * h + c * 32 + j < n) Dv = fmaf(s[c * 32 + j], dp[j], Dv);   // TMEM columns >= n are stale (may be NaN)
+                        for (int i = 0; i < 16; ++i) Dv = fmaf(s[16 * k + i], dp[i], Dv);
                     }
                 }
                 exD[h * 128 + r] = Dv;
@@ -414,7 +467,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
                 wt_bar();
                 if (tid == 0) {
                     tc_fence_after();
-                    wt_mma_pv(tmem, smem_u32(tP), tb_a + 3 * TS, TS, nk, 1);      // dV = P^T dO  -> columns [0, 64) (S is in registers)
+                    wt_mma_pv(tmem, smem_u32(tP), tb_a + 3 * TS, TS, nkq, 1);     // dV = P^T dO  -> columns [0, 64) (S is in registers)
                     umma_commit(sm.mma);
                 }
                 Dv = exD[r];
@@ -424,22 +477,30 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
                 ph ^= 1;
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < WT_CPT / 32; ++c) {
-                    if (WT_CPT * h + c * 32 < n) {
-                        float dp[32], ac[32];
-                        tmem_ld_32x32(trow + 128 + WT_CPT * h + c * 32, dp);
-                        tmem_ld_32x32(tacc + c * 32, ac);
+                for (int k = 0; k < WT_GPT; ++k) {
+                    const int g = WT_NS * k + h;
+                    if ((gv >> k) & 1u) {
+                        float dp[16], ac[16];
+                        tmem_ld_32x16(trow + 128 + 16 * g, dp);
+                        tmem_ld_32x16(tacc + 16 * g, ac);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float ds = WT_CPT * h + c * 32 + j < n ? s[c * 32 + j] * (dp[j] - Dv) : 0.f;   // dS_ij (0 at masked keys)
-                            dp[j] = ds;
-                            ac[j] += ds;
+                        for (int i = 0; i < 16; ++i) {
+                            const float ds = s[16 * k + i] * (dp[i] - Dv);         // dS_ij
+                            dp[i] = ds;
+                            ac[i] += ds;
                         }
-                        tmem_st_32x32(tacc + c * 32, ac);
-                        if (r < n)
+                        tmem_st_32x16(tacc + 16 * g, ac);
+                        if (r < n) {
+                            wt_store8_planes(tP, TS, r, 2 * g, dp);
+                            wt_store8_planes(tP, TS, r, 2 * g + 1, dp + 8);
+                        }
+                    } else if (16 * g < ne && r < n) {                          // a masked agent among the valid ones: dS = 0
+                        float zz[8];
 #pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) wt_store8_planes(tP, TS, r, (WT_CPT / 8) * h + c * 4 + c8, dp + c8 * 8);
+                        for (int i = 0; i < 8; ++i) zz[i] = 0.f;
+                        wt_store8_planes(tP, TS, r, 2 * g, zz);
+                        wt_store8_planes(tP, TS, r, 2 * g + 1, zz);
                     }
                 }
                 tmem_st_wait();
@@ -449,7 +510,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
                 if (tid == 0) {
                     tc_fence_after();
                     const uint32_t pa = smem_u32(tP);
-                    wt_mma_pv(tmem + 64, pa, tb_a, TS, nk, 1);                    // dK = dS^T (scale Q)
+                    wt_mma_pv(tmem + 64, pa, tb_a, TS, nkq, 1);                   // dK = dS^T (scale Q)
                     wt_mma_pv(tmem + 128, pa, tb_a + TS, TS, nk, 0);              // dQ = dS K (scaled below); dP has been consumed
                     umma_commit(sm.mma);
                     umma_commit(&sm.empty[buf]);
@@ -465,11 +526,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
                     tmem_ld_wait();
                     if (r < n) {
                         const float f = part == 2 ? p.scale : 1.f;
+                        const bool keep = part == 2 || r < ne;   // dV / dK rows of the trailing masked keys: zero (their accumulator rows are stale)
                         const long long off = tok * (3 * D) + (2 - part) * D + head * WT_DH + WT_DPT * h;
 #pragma unroll
                         for (int c = 0; c < WT_DPT; c += 4)
-                            store_split4(p.out, off + c, make_float4((oh[c] + ol[c]) * f, (oh[c + 1] + ol[c + 1]) * f,
-                                                                     (oh[c + 2] + ol[c + 2]) * f, (oh[c + 3] + ol[c + 3]) * f));
+                            store_split4(p.out, off + c,
+                                         keep ? make_float4((oh[c] + ol[c]) * f, (oh[c + 1] + ol[c + 1]) * f,
+                                                            (oh[c + 2] + ol[c + 2]) * f, (oh[c + 3] + ol[c + 3]) * f)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f));
                     }
                 }
             }
@@ -479,18 +543,17 @@ __global__ void __launch_bounds__(WT_THREADS, 1) window_attention_tc_kernel(cons
         if (BWD) {
             // fold the per-thread columns of sum dS into the head's table (entry of (i, j) = bbase_i - sub_j)
 #pragma unroll
-            for (int c = 0; c < WT_CPT / 32; ++c) {
-                if (WT_CPT * h + c * 32 < n) {
-                    float ac[32];
-                    tmem_ld_32x32(tacc + c * 32, ac);
+            for (int k = 0; k < WT_GPT; ++k) {
+                const int g = WT_NS * k + h;
+                if (16 * g < n) {
+                    float ac[16];
+                    tmem_ld_32x16(tacc + 16 * g, ac);
                     tmem_ld_wait();
                     if (r < n) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int jj = c * 32 + j;
-                            if (WT_CPT * h + jj < n && ac[j] != 0.f)
-                                atomicAdd(&sm.sdB[bbase - (((jj >> 4) * WT_S2 + ((jj >> 2) & 3)) * WT_S2 + (jj & 3))], ac[j]);
-                        }
+                        for (int i = 0; i < 16; ++i)
+                            if (ac[i] != 0.f)
+                                atomicAdd(&sm.sdB[bbase - (((WT_NS * k) * WT_S2 + ((i >> 2) & 3)) * WT_S2 + (i & 3))], ac[i]);
                     }
                 }
             }
