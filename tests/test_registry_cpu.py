@@ -72,3 +72,23 @@ def test_real_create_model_dispatches_to_the_b200_module(name, yaml_rel, cls, tm
     finally:
         a2x_import.uninstall(prev)
         sys.modules.pop("opencood.models." + name, None)
+
+
+def test_bevencode_state_dict_matches_the_reference_module():
+    """`lss.BevEncode(inC, outC)` (the camera branch's BEV encoder on the tap-GEMM kernels) has the key names, order and
+    shapes of the REAL `opencood.models.sub_modules.lss_submodule.BevEncode`: a state_dict of the reference module loads
+    with strict=True, and the seeded initialisation of the golden fixture (order dependent) is reproduced."""
+    import a2x_import
+
+    ref_import.install()
+    from opencood.models.sub_modules.lss_submodule import BevEncode as RefBevEncode
+
+    ref = RefBevEncode(64, 64)
+    mine = a2x_import.pkg("lss").BevEncode(64, 64)
+    rsd, msd = ref.state_dict(), mine.state_dict()
+    assert list(rsd.keys()) == list(msd.keys())
+    assert all(tuple(rsd[k].shape) == tuple(msd[k].shape) for k in rsd)
+    mine.load_state_dict(rsd, strict=True)
+    assert sum(p.numel() for p in ref.parameters()) == sum(p.numel() for p in mine.parameters())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mine.eval()(torch.zeros(1, 64, 16, 16))
