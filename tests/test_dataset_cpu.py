@@ -1,0 +1,232 @@
+"""CPU (-m "not gpu"): the dataset side (`airv2x-perception_b200/intermediate_fusion_dataset.py`).
+
+* everywhere: the batches it builds from the seeded synthetic scenes equal what the REAL reference class produced for the
+  same scenes (tests/golden/dataset.npz, written by scripts/make_golden_dataset.py): bookkeeping, ground-truth boxes,
+  camera geometry, and — with the raw clouds pushed through the restated point filters + sequential voxeliser
+  (oracle/voxelize.py, the checker) — the voxel tensors; the anchor positives the boxes lead to equal the reference's
+  label maps;
+* where /root/reference exists: the same comparison live against the reference class for the configurations the fixture
+  does not hold (other ego types, `proj_first: false`, no shuffle), and every helper against the function it restates.
+"""
+import copy
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import a2x_import  # noqa: E402
+import dataset_common as DC  # noqa: E402
+import make_golden_dataset as MGD  # noqa: E402
+from oracle import labels_oracle as LO, postprocess_oracle as PO, ref_import  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+needs_reference = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def DS():
+    return a2x_import.pkg("intermediate_fusion_dataset")
+
+
+@pytest.fixture(scope="module")
+def hypes():
+    return json.load(open(os.path.join(GOLD, "dataset_config.json")))
+
+
+@pytest.mark.parametrize("name", sorted(MGD.CASES))
+def test_batches_equal_the_reference_fixture(DS, hypes, name):
+    train, specs = MGD.CASES[name]
+    gold = np.load(os.path.join(GOLD, "dataset.npz"))
+    scenes = [DC.synth_scene(DS, **kw) for kw in specs]
+    ds, items, batch = MGD.run_ours(DS, hypes, train, scenes, seed=5)
+    o = batch["ego"]
+    for k in ("record_len", "prior_encoding", "object_bbx_mask"):
+        g = gold["%s/%s" % (name, k)]
+        assert o[k].numpy().dtype == g.dtype and np.array_equal(o[k].numpy(), g), k
+    for k, tol in (("pairwise_t_matrix_collab", 1e-6), ("img_pairwise_t_matrix_collab", 1e-6),
+                   ("spatial_correction_matrix", 1e-12), ("object_bbx_center", 1e-9)):
+        g = gold["%s/%s" % (name, k)]
+        assert o[k].numpy().dtype == g.dtype and o[k].shape == g.shape and np.abs(o[k].numpy() - g).max() <= tol, k
+    assert [i for ids in o["object_ids"] for i in ids] == gold[name + "/object_ids"].tolist()
+    assert [i for ids in o["class_ids"] for i in ids] == gold[name + "/class_ids"].tolist()
+    # the padded class ids line up with the boxes
+    for b, ids in enumerate(o["class_ids"]):
+        assert o["object_class_ids"][b, :len(ids)].tolist() == ids and int(o["object_class_ids"][b, len(ids):].abs().sum()) == 0
+    vox = MGD.voxelise_like_the_reference(o, hypes, train)
+    for t in ("vehicle", "rsu", "drone"):
+        assert np.array_equal(o[t]["record_len"].numpy(), gold["%s/%s/record_len" % (name, t)])
+        assert list(o[t]["batch_idxs"]) == gold["%s/%s/batch_idxs" % (name, t)].tolist()
+        assert o[t]["batch_merged_lidar_features_torch"] is None
+        key = "%s/%s/voxel_coords" % (name, t)
+        assert (key in gold.files) == (vox[t] is not None)
+        if vox[t] is not None:
+            assert np.array_equal(vox[t]["voxel_coords"], gold[key])
+            assert np.array_equal(vox[t]["voxel_num_points"], gold["%s/%s/voxel_num_points" % (name, t)])
+            assert np.array_equal(vox[t]["voxel_features"].astype(np.float64).sum(axis=(1, 2)), gold["%s/%s/voxel_sum" % (name, t)])
+        for k, c in o[t]["batch_merged_cam_inputs"].items():
+            if k == "imgs":
+                g = gold["%s/%s/cam_imgs_mean" % (name, t)]
+                assert np.abs(c.numpy().astype(np.float64).mean(axis=(2, 3, 4)) - g).max() < 1e-6
+            else:
+                g = gold["%s/%s/cam_%s" % (name, t, k)]
+                assert c.numpy().dtype == g.dtype and np.abs(c.numpy() - g).max() <= 1e-6, (t, k)
+    # chain: the boxes this dataset emits -> anchor targets == the reference's label maps (positives)
+    pp = hypes["postprocess"]
+    anchors = PO.generate_anchor_box(pp["anchor_args"], pp["order"])
+    pos = []
+    for b in range(len(scenes)):
+        lab = LO.generate_label(o["object_bbx_center"][b].numpy(), o["object_bbx_mask"][b].numpy(),
+                                o["object_class_ids"][b].numpy(), anchors, pp["target_args"]["pos_threshold"],
+                                pp["target_args"]["neg_threshold"])
+        pos.append(lab["pos_equal_one"])
+    assert np.array_equal(np.flatnonzero(np.stack(pos).reshape(-1)), gold[name + "/pos_idx"])
+    # raw_points: scene-major offsets over the kept agents, one pose per agent, clouds untouched apart from the shuffle
+    raw = o["raw_points"]
+    n = int(o["record_len"].sum())
+    assert raw["offsets"].dtype == torch.int32 and raw["offsets"].shape == (n + 1,) and raw["transforms"].shape == (n, 4, 4)
+    assert raw["points"].dtype == torch.float32 and raw["points"].shape == (int(raw["offsets"][-1]), 4)
+    assert raw["filter"] is True and raw["preprocess"] is hypes["preprocess"]
+
+
+def test_shuffle_is_a_permutation_and_off_keeps_the_order(DS, hypes):
+    scene = DC.synth_scene(DS, seed=3, n_veh=2, n_rsu=1, n_drone=0, far=False, cameras=False, n_pts=500)
+    _, items, b0 = MGD.run_ours(DS, hypes, True, [scene], seed=1, shuffle=False)
+    _, _, b1 = MGD.run_ours(DS, hypes, True, [scene], seed=1, shuffle=True)
+    _, _, b2 = MGD.run_ours(DS, hypes, True, [scene], seed=1, shuffle=True)
+    p0, p1 = b0["ego"]["raw_points"]["points"].numpy(), b1["ego"]["raw_points"]["points"].numpy()
+    assert torch.equal(b1["ego"]["raw_points"]["points"], b2["ego"]["raw_points"]["points"])       # seeded
+    offs = b0["ego"]["raw_points"]["offsets"].numpy()
+    first = [r for r in scene.values() if r["ego"]][0]["lidar_np"]
+    assert np.array_equal(p0[offs[0]:offs[1]], first)
+    assert not np.array_equal(p0, p1)
+    for a in range(len(offs) - 1):
+        s0, s1 = p0[offs[a]:offs[a + 1]], p1[offs[a]:offs[a + 1]]
+        assert np.array_equal(s0[np.lexsort(s0.T)], s1[np.lexsort(s1.T)])
+
+
+def test_pairwise_matrices_are_consistent(DS, hypes):
+    h = copy.deepcopy(hypes)
+    h["fusion"]["args"]["proj_first"] = False
+    scene = DC.synth_scene(DS, seed=8, cameras=False, n_pts=50)
+    ds, items, batch = MGD.run_ours(DS, h, False, [scene], seed=0)
+    pair = batch["ego"]["pairwise_t_matrix_collab"][0].double().numpy()
+    n, L = int(batch["ego"]["record_len"][0]), ds.max_cav_num
+    assert pair.shape == (L, L, 4, 4) and not pair[n:].any() and not pair[:, n:].any()
+    tf = items[0]["ego"]
+    ts = tf["transformation_matrix_veh_list"] + tf["transformation_matrix_rsu_list"] + tf["transformation_matrix_drone_list"]
+    for i in range(n):
+        assert np.allclose(pair[i, i], np.eye(4))
+        for j in range(n):
+            assert np.allclose(pair[i, j] @ pair[j, i], np.eye(4), atol=1e-4)
+            assert np.allclose(ts[j] @ pair[i, j], ts[i], atol=1e-3)        # T_j . (i -> j) = T_i
+    # without proj_first the clouds are not projected: identity poses go to the GPU
+    assert torch.equal(batch["ego"]["raw_points"]["transforms"], torch.eye(4, dtype=torch.float64).expand(n, 4, 4))
+
+
+def test_objects_outside_the_range_or_straddling_it_are_dropped(DS):
+    rng = [-140.8, -40, -3, 140.8, 40, 1]
+    mk = lambda x, y: {"location": [x, y, -1.5, 0, 30.0, 0], "center": [0, 0, 0.7], "extent": [2.0, 0.9, 0.75], "class": 2}  # noqa: E731
+    objs = {1: mk(10, 5), 2: mk(140.0, 0), 3: mk(300, 0), 4: mk(0, 39.9), 5: mk(-100, -20)}
+    boxes, ids, cls = DS.project_world_objects(objs, [0, 0, 0, 0, 0, 0], rng, "hwl")
+    assert ids == [1, 5] and cls == [2, 2] and boxes.shape == (2, 7)
+    assert np.allclose(boxes[0], [10, 5, -0.8, 1.5, 1.8, 4.0, np.radians(30.0)], atol=1e-9)
+    assert DS.project_world_objects({}, [0] * 6, rng, "hwl")[0].shape == (0, 7)
+
+
+def test_nearest_agents_keeps_input_order_and_breaks_ties_like_a_heap(DS):
+    d = [("a", 5.0), ("b", 1.0), ("c", 5.0), ("d", 0.5), ("e", 9.0)]
+    assert DS.nearest_agents(d, 3) == ([0, 1, 3], ["a", "b", "d"])
+    assert DS.nearest_agents(d, 9) == ([0, 1, 2, 3, 4], ["a", "b", "c", "d", "e"])
+    assert DS.nearest_agents(d, 0) == ([], [])
+
+
+def test_an_agent_with_an_empty_cloud_supervises_nothing(DS, hypes):
+    scene = DC.synth_scene(DS, seed=4, n_veh=2, n_rsu=0, n_drone=0, far=False, cameras=False, n_pts=200)
+    empty = DC.synth_scene(DS, seed=4, n_veh=2, n_rsu=0, n_drone=0, far=False, cameras=False, n_pts=200, empty_cloud_agent=1)
+    _, _, full = MGD.run_ours(DS, hypes, False, [scene], seed=0)
+    _, _, part = MGD.run_ours(DS, hypes, False, [empty], seed=0)
+    ego_only = [r for r in scene.values() if r["ego"]][0]["params"]["objects"]
+    assert set(part["ego"]["object_ids"][0]) <= set(ego_only) and set(part["ego"]["object_ids"][0]) <= set(full["ego"]["object_ids"][0])
+    offs = part["ego"]["raw_points"]["offsets"].tolist()
+    assert offs[2] == offs[1] and int(part["ego"]["record_len"][0]) == 2        # the agent stays in the batch, with 0 points
+
+
+def test_a_dataset_without_a_source_raises(DS, hypes):
+    ds = DS.IntermediateFusionDatasetAirv2x(hypes, False, True)
+    with pytest.raises(NotImplementedError):
+        ds[0]
+    with pytest.raises(TypeError):
+        len(ds)
+
+
+# ------------------------------------------------------------------------------------------- live against the reference
+@pytest.fixture(scope="module")
+def ref_env(tmp_path_factory):
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path_factory.mktemp("refcwd")))
+    try:
+        IFD = MGD.reference_env()
+        yield IFD, ref_import.load_hypes(MGD.YAML)
+    finally:
+        os.chdir(cwd)
+
+
+@needs_reference
+@pytest.mark.parametrize("variant", ["ego_rsu", "ego_drone", "no_proj_first", "no_shuffle_eval"])
+def test_live_against_the_reference_class(DS, ref_env, variant, monkeypatch):
+    IFD, hypes0 = ref_env
+    h = copy.deepcopy(hypes0)
+    train, kw = True, {}
+    if variant.startswith("ego_"):
+        h["ego_type"] = variant[4:]
+    elif variant == "no_proj_first":
+        h["fusion"]["args"]["proj_first"] = False
+    else:
+        train, kw = False, {"shuffle": False}
+        monkeypatch.setattr(IFD, "shuffle_points", lambda p: p)
+    scenes = [DC.synth_scene(DS, seed=41, n_pts=800), DC.synth_scene(DS, seed=42, n_veh=1, n_rsu=2, n_drone=0, n_pts=800)]
+    ref = MGD.reference_dataset(IFD, h, train)
+    _, ref_batch = MGD.run_reference(ref, scenes, seed=9)
+    _, _, ours = MGD.run_ours(DS, h, train, scenes, seed=9, **kw)
+    assert MGD.compare(ref_batch, ours, h, train) < 1e-9
+
+
+@needs_reference
+def test_helpers_against_the_functions_they_restate(DS, ref_env):
+    from opencood.utils import airv2x_utils, box_utils, camera_utils, transformation_utils as TU
+    g = np.random.default_rng(0)
+    for _ in range(20):
+        a = list(g.uniform(-100, 100, 3)) + list(g.uniform(-180, 180, 3))
+        b = list(g.uniform(-100, 100, 3)) + list(g.uniform(-180, 180, 3))
+        assert np.array_equal(DS.pose_to_matrix(a), TU.x_to_world(a))
+        assert np.array_equal(DS.relative_pose_matrix(a, b), TU.x1_to_x2(a, b))
+        assert DS.abs_world_pose(a, b) == TU.get_abs_world_pose(a, b)
+        d = [(i, float(x)) for i, x in enumerate(g.integers(0, 6, 9))]            # many ties
+        k = int(g.integers(1, 10))
+        assert DS.nearest_agents(d, k) == tuple(airv2x_utils.get_smallest_k_indices(d, k))
+        c2l = np.eye(4, dtype=np.float32)
+        c2l[:3, :] = g.normal(size=(3, 4)).astype(np.float32)
+        assert np.array_equal(DS.camera_to_lss(c2l), camera_utils.ue4_to_lss(c2l))
+    corners = g.normal(size=(6, 8, 3)) * 3
+    for order in ("hwl", "lwh"):
+        assert np.array_equal(DS.corners_to_boxes(corners, order), box_utils.corner_to_center(corners, order))
+        boxes = np.concatenate([g.uniform(-50, 50, (6, 3)), g.uniform(1, 5, (6, 3)), g.uniform(-3.2, 3.2, (6, 1))], axis=1)
+        assert np.array_equal(DS.boxes_to_corners_f32(boxes, order), box_utils.boxes_to_corners_3d(boxes, order))
+    conf = {"resize_lim": [0.6, 0.7], "final_dim": [360, 640], "rot_lim": [-5.0, 5.0], "H": 720, "W": 1280,
+            "rand_flip": True, "bot_pct_lim": [0.0, 0.05]}
+    for is_train in (True, False):
+        np.random.seed(3)
+        mine = [DS.sample_augmentation(conf, is_train) for _ in range(4)]
+        np.random.seed(3)
+        theirs = [camera_utils.sample_augmentation(conf, is_train) for _ in range(4)]
+        assert mine == theirs
+        for resize, dims, crop, flip, rotate in mine:
+            rot, tran = DS.post_homography(resize, crop, flip, rotate)
+            _, r2, t2 = camera_utils.img_transform([], torch.eye(2), torch.zeros(2), resize, dims, crop, flip, rotate)
+            assert torch.equal(rot[:2, :2], r2) and torch.equal(tran[:2], t2) and float(rot[2, 2]) == 1.0

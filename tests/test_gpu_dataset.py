@@ -1,0 +1,95 @@
+"""GPU (-m gpu): the dataset side feeds the kernels. A batch collated by
+`intermediate_fusion_dataset.IntermediateFusionDatasetAirv2x` (raw sensor-frame clouds + poses + padded boxes) must give the
+model what the reference's CPU pipeline gives it: the same logits as the reference-layout voxel dict built from the same
+clouds by the restated filters + sequential voxeliser (oracle = checker), and a training step through `Trainer` whose GPU
+anchor targets equal the label oracle's on the dataset's boxes. Integer work bit-exact, logits `torch.equal`."""
+import copy
+import json
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import w2c_common as C
+import dataset_common as DC
+from oracle import labels_oracle as LO, postprocess_oracle as PO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import make_golden_dataset as MGD  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    import a2x_import
+
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    DS = a2x_import.pkg("intermediate_fusion_dataset")
+    cfg, gold = C.load_small()
+    hypes = json.load(open(os.path.join(ROOT, "tests", "golden", "dataset_config.json")))
+    hypes = dict(hypes, preprocess=cfg["preprocess"], postprocess=cfg["postprocess"])      # the small grid of the fixtures
+    model = M.Airv2xWhere2com(cfg["model_args"])
+    model.load_state_dict(C.golden_state_dict(model, gold))
+    model.cuda()
+    kw = dict(cameras=False, n_pts=6000, obj_span=(20.0, 9.0), agent_spread=0.15, pts_sigma=(12.0, 6.0))
+    scenes = [DC.synth_scene(DS, seed=51, n_veh=2, n_rsu=1, n_drone=1, **kw),
+              DC.synth_scene(DS, seed=52, n_veh=1, n_rsu=0, n_drone=2, far=False, **kw)]
+    return DS, cfg, hypes, model, scenes
+
+
+def _voxel_dict(ours, hypes, train):
+    vox = MGD.voxelise_like_the_reference(ours, hypes, train)
+    dd = {"record_len": ours["record_len"]}
+    for t in ("vehicle", "rsu", "drone"):
+        dd[t] = {"batch_merged_lidar_features_torch": (None if vox[t] is None else
+                                                       {k: torch.from_numpy(v) for k, v in vox[t].items()}),
+                 "record_len": ours[t]["record_len"], "batch_idxs": ours[t]["batch_idxs"]}
+    return dd
+
+
+def test_dataset_batch_gives_the_logits_of_the_reference_voxel_dict():
+    DS, cfg, hypes, model, scenes = _setup()
+    _, _, batch = MGD.run_ours(DS, hypes, False, scenes, seed=2)
+    ours = batch["ego"]
+    assert ours["record_len"].tolist() == [4, 3]
+    model.eval()
+    with torch.no_grad():
+        a = model(ours)
+        b = model(C.to_device(_voxel_dict(ours, hypes, False), "cuda"))
+    for k in ("psm", "rm", "obj"):
+        assert a[k].shape[0] == 2 and torch.equal(a[k], b[k]), k
+    assert a["comm_rate"] == b["comm_rate"] and a["comm_rate"] > 0
+
+
+def test_trainer_step_on_a_dataset_batch():
+    import a2x_import
+
+    DS, cfg, hypes, model, scenes = _setup()
+    TL = a2x_import.pkg("train_loop")
+    th = dict(hypes, loss={"args": cfg["loss_args"]},
+              optimizer={"core_method": "Adam", "lr": 0.002, "args": {"eps": 1e-10, "weight_decay": 1e-4}},
+              lr_scheduler={"core_method": "multistep", "gamma": 0.1, "step_size": [10, 25, 40]})
+    _, _, batch = MGD.run_ours(DS, hypes, True, scenes, seed=2)
+    ours = batch["ego"]
+    assert int(ours["object_bbx_mask"].sum()) >= 6
+    tr = TL.Trainer(model, th)
+    lab = tr.labels(ours)
+    pp = hypes["postprocess"]
+    anchors = PO.generate_anchor_box(pp["anchor_args"], pp["order"])
+    for b in range(2):
+        ref = LO.generate_label(ours["object_bbx_center"][b].numpy(), ours["object_bbx_mask"][b].numpy(),
+                                ours["object_class_ids"][b].numpy(), anchors, pp["target_args"]["pos_threshold"],
+                                pp["target_args"]["neg_threshold"])
+        assert np.array_equal(lab["pos_equal_one"][b].cpu().numpy(), ref["pos_equal_one"])
+        assert np.array_equal(lab["neg_equal_one"][b].cpu().numpy(), ref["neg_equal_one"])
+        assert np.abs(lab["targets"][b].cpu().numpy() - ref["targets"]).max() < 1e-5
+    assert float(lab["pos_equal_one"].sum()) > 0
+    random.seed(4)
+    losses = [float(tr.step(copy.copy(ours)).sum()) for _ in range(8)]
+    assert all(np.isfinite(losses)) and min(losses[4:]) < losses[0]
+    for p in model.parameters():
+        assert p.grad is None or bool(torch.isfinite(p.grad).all())
