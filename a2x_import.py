@@ -15,18 +15,25 @@ def pkg(sub=None):
 
 MODEL_NAMES = ("airv2x_where2com", "airv2x_cobevt", "airv2x_v2xvit", "point_pillar_where2comm", "point_pillar_cobevt",
                "point_pillar_v2xvit")
+LOSS_NAMES = ("point_pillar_loss_multiclass", "point_pillar_loss")
 
 
-def install(names=MODEL_NAMES):
+def install(names=MODEL_NAMES, losses=LOSS_NAMES):
     """Register the B200 drop-in modules under the reference's registry paths, so that the UNMODIFIED
     `opencood.tools.train_utils.create_model(hypes)` (train_utils.py:288-325: `importlib.import_module("opencood.models." +
     core_method)` + class-name match) returns them. Also publishes the package under the importable alias
-    `airv2x_perception_b200` (the directory name has a hyphen). Returns the previous sys.modules entries for uninstall()."""
+    `airv2x_perception_b200` (the directory name has a hyphen). `losses`: likewise `opencood.loss.<name>` for
+    `train_utils.create_loss(hypes)` (train_utils.py:328-368) -> the criterion classes on the fused loss kernel.
+    Returns the previous sys.modules entries for uninstall()."""
     prev = {}
     for n in names:
         key = "opencood.models." + n
         prev[key] = sys.modules.get(key)
         sys.modules[key] = pkg("opencood.models." + n)
+    for n in losses or ():
+        key = "opencood.loss." + n
+        prev[key] = sys.modules.get(key)
+        sys.modules[key] = pkg("opencood.loss." + n)
     sys.modules.setdefault("airv2x_perception_b200", pkg())
     return prev
 

@@ -92,3 +92,35 @@ def test_bevencode_state_dict_matches_the_reference_module():
     assert sum(p.numel() for p in ref.parameters()) == sum(p.numel() for p in mine.parameters())
     with pytest.raises(RuntimeError, match="CUDA"):
         mine.eval()(torch.zeros(1, 64, 16, 16))
+
+
+@pytest.mark.parametrize("yaml_rel,cls", [("airv2x/lidar/det/airv2x_intermediate_where2com.yaml", "PointPillarLossMultiClass"),
+                                          ("V2X-R/LiDAR/V2XR_where2comm.yaml", "PointPillarLoss")])
+def test_real_create_loss_dispatches_to_the_b200_criterion(yaml_rel, cls, tmp_path):
+    """the UNMODIFIED `train_utils.create_loss(hypes)` (train_utils.py:328-368) returns the criterion on the fused loss
+    kernel once `a2x_import.install()` has registered `opencood.loss.<core_method>`; constructor keys as shipped"""
+    import a2x_import
+
+    hypes = _load(yaml_rel, tmp_path)
+    from opencood.tools import train_utils
+
+    name = (hypes["loss"][hypes["task"]] if hypes.get("task") else hypes["loss"])["core_method"]
+    sys.modules.pop("opencood.loss." + name, None)
+    real = train_utils.create_loss(hypes)
+    assert type(real).__name__ == cls and type(real).__module__ == "opencood.loss." + name
+    prev = a2x_import.install()
+    try:
+        ours = train_utils.create_loss(hypes)
+        assert type(ours).__name__ == cls and type(ours).__module__.startswith("airv2x-perception_b200.")
+        assert ours.cls_weight == real.cls_weight and ours.reg_coe == real.reg_coe
+        assert hasattr(ours, "logging") and ours.loss_dict == {}
+        if cls == "PointPillarLossMultiClass":
+            assert ours.cls_num == real.cls_num
+        z = torch.zeros(1, 2, 4, 4)
+        with pytest.raises(RuntimeError, match="CUDA"):      # no CPU path
+            ours({"psm": z, "rm": torch.zeros(1, 14, 4, 4), "obj": z},
+                 {"targets": torch.zeros(1, 4, 4, 14), "pos_equal_one": torch.zeros(1, 4, 4, 2),
+                  "class_ids": torch.zeros(1, 4, 4, 2, dtype=torch.int64)})
+    finally:
+        a2x_import.uninstall(prev)
+        sys.modules.pop("opencood.loss." + name, None)
