@@ -93,3 +93,41 @@ def test_legacy_criterion_matches_the_oracle_with_autograd(setup):
     ref_vals, ref_grads = _oracle(O.point_pillar_loss, outs, lab, 1.0, 2.0)
     _check(total, {k: v.grad for k, v in outs.items()}, ref_vals, ref_grads)
     assert "Loss:" in crit.logging(0, 0, 1)
+
+
+def test_reference_loop_with_the_criterion_equals_the_fused_step():
+    """tools/train.py:216-226 as written — `model(batch)` -> `criterion(output, label_dict)` -> `loss.backward()` — with both
+    objects from this repo (torch.library forward/backward ops + the fused criterion) lands on the same loss and the same
+    parameter gradients as the one-call `model.train_step` (same kernels, same order of the top-K draws)."""
+    import random
+
+    import a2x_import
+    import w2c_common as C
+
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    cfg, gold = C.load_small()
+    model = M.Airv2xWhere2com(cfg["model_args"])
+    sd = C.golden_state_dict(model, gold)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    dd = C.to_device(C.golden_scene(cfg, gold), "cuda")
+    H, W = gold["train_psm"].shape[2:]
+    labels = O.make_labels(int(gold["label_seed"]), 1, H, W, cfg["model_args"]["anchor_number"])
+    la = cfg["loss_args"]
+    crit = a2x_import.pkg("opencood.loss.point_pillar_loss_multiclass").PointPillarLossMultiClass(
+        {"cls_weight": la["cls_weight"], "reg": la["reg"], "num_class": cfg["model_args"]["num_class"]})
+    random.seed(7)
+    out = model(dd)
+    loss = crit(out, labels)
+    model.zero_grad()
+    loss.backward()
+    g_auto = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    assert len(g_auto) > 50
+    model.load_state_dict(sd)
+    random.seed(7)
+    loss3 = model.train_step(dd, labels, la["cls_weight"], la["reg"])
+    assert abs(float(loss) - float(loss3.sum())) <= 1e-6 * abs(float(loss3.sum()))
+    for n, p in model.named_parameters():
+        if n in g_auto:
+            scale = float(p.grad.abs().max())
+            assert float((g_auto[n] - p.grad).abs().max()) <= 1e-4 * scale + 1e-7, n
