@@ -15,8 +15,8 @@
 
 The boundary towards the disk is `retrieve_base_data(idx)` (`basedataset.py:217-303`): a `source` sequence / callable yields
 the per-agent records it returns (`ego`, `agent_type`, `distance_to_ego`, `time_delay`, `params`, `lidar_np`, `cameras`);
-`agent_pose_params` restates the pose half of `reform_param` (`basedataset.py:305-532`) for sources that hold metadata
-dicts. Scanning the AirV2X directory tree / reading .pcd files is outside the path (out of scope).
+without one the AirV2X directory tree under `params["root_dir"]` is scanned like the reference does (`airv2x_scenes.py`).
+`agent_pose_params` restates the pose half of `reform_param` (`basedataset.py:305-532`) for in-memory sources.
 
 Host logic only (numpy / torch CPU tensors): no kernel work happens here and nothing here imports `oracle/`.
 """
@@ -198,17 +198,34 @@ _IMG_MEAN = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
 _IMG_STD = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
 
 
-def _image_tensor(img, resize_dims, crop, flip, rotate):
-    """PIL image -> normalised [3,H,W] tensor (resize, crop, flip, rotate as `img_transform` :64-72; `normalize_img`
-    :136-143 = ToTensor + ImageNet mean / std)"""
+def _augment_pil(img, resize_dims, crop, flip, rotate):
+    """resize, crop, flip, rotate of `img_transform` (utils/camera_utils.py:64-72), PIL's default resampling per mode"""
     from PIL import Image
     img = img.resize(resize_dims).crop(crop)
     if flip:
         img = img.transpose(method=Image.FLIP_LEFT_RIGHT)
-    img = img.rotate(rotate)
+    return img.rotate(rotate)
+
+
+def _image_tensor(img, resize_dims, crop, flip, rotate):
+    """PIL image -> normalised [3,H,W] tensor (`normalize_img` :136-143 = ToTensor + ImageNet mean / std)"""
+    img = _augment_pil(img, resize_dims, crop, flip, rotate)
     a = np.array(img.convert("RGB") if img.mode != "RGB" else img, dtype=np.uint8)       # a writable copy
     t = torch.from_numpy(a).permute(2, 0, 1).to(torch.float32).div(255)
     return (t - _IMG_MEAN) / _IMG_STD
+
+
+def _depth_tensor(depth_img, resize_dims, crop, flip, rotate):
+    """CARLA depth PNG (24-bit value in R + 256 G + 65536 B, full scale 1000 m) -> 16-bit image -> the colour image's
+    augmentation -> [1,H,W] metres (`decode_depth_carla` :145-166, `pil_depth_to_tensor` :192-210)"""
+    from PIL import Image
+    d = np.array(depth_img).astype(np.uint32)
+    d = (d[:, :, 0] + d[:, :, 1] * 256 + d[:, :, 2] * 256 * 256).astype(np.float64) / (256 * 256 * 256 - 1) * 1000
+    pil = Image.fromarray(np.clip(d * 65535 / 1000, 0, 65535).astype(np.uint16))      # uint16 -> mode "I;16"
+    pil = _augment_pil(pil, resize_dims, crop, flip, rotate)
+    if pil.mode != "I;16":
+        raise ValueError("depth image lost its 16-bit mode in the augmentation")
+    return torch.from_numpy(np.array(pil, dtype=np.float32) * 1000 / 65535.0).unsqueeze(0)
 
 
 # ----------------------------------------------------------------------------------------------------- the dataset
@@ -223,6 +240,12 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
 
     def __init__(self, params, visualize=False, train=True, source=None, shuffle=True, pin_memory=False):
         self.params, self.visualize, self.train, self.training = params, visualize, train, train
+        if source is None:      # the reference's behaviour: scan params["root_dir"] / ["validate_dir"] (basedataset.py:73-207)
+            import os
+            root = params.get("root_dir" if train else "validate_dir")
+            if root and os.path.isdir(root):
+                from .airv2x_scenes import AirV2XScenes
+                source = AirV2XScenes(params, train)
         self.source, self.shuffle, self.pin_memory = source, shuffle, pin_memory
         fa = params["fusion"]["args"]
         assert "proj_first" in fa
@@ -252,8 +275,8 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
 
     def retrieve_base_data(self, idx):
         if self.source is None:
-            raise NotImplementedError("scanning the AirV2X directory tree is outside the hot path: pass source= (a sequence "
-                                      "or callable yielding what basedataset.retrieve_base_data returns)")
+            raise NotImplementedError("no scene source: params['root_dir'] / ['validate_dir'] is not a directory and no source= "
+                                      "(a sequence or callable yielding what basedataset.retrieve_base_data returns) was given")
         rec = self.source(idx) if callable(self.source) else self.source[idx]
         if isinstance(rec, tuple):
             return rec
@@ -269,8 +292,7 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
         cams = rec.get("cameras") or []
         if not cams:
             return None
-        if rec.get("depth"):
-            raise NotImplementedError("depth-supervised camera inputs are outside the path")
+        depth = rec.get("depth") or []           # optional 4th image channel: metric depth for the depth-supervised lift
         n = len(cams)
         ext = np.asarray(rec["params"]["delay_extrinsic"]).reshape(n, 4, 4)
         intr = np.asarray(rec["params"]["delay_intrinsic"]).reshape(n, 3, 3)
@@ -279,7 +301,10 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
             c2l = camera_to_lss(ext[i])
             resize, dims, crop, flip, rotate = sample_augmentation(self.aug_conf[rec["agent_type"]], self.train)
             rot, tran = post_homography(resize, crop, flip, rotate)
-            out["imgs"].append(_image_tensor(img, dims, crop, flip, rotate))
+            planes = [_image_tensor(img, dims, crop, flip, rotate)]
+            if depth:
+                planes.append(_depth_tensor(depth[i], dims, crop, flip, rotate))
+            out["imgs"].append(torch.cat(planes, dim=0))
             out["intrinsics"].append(torch.from_numpy(intr[i]))
             out["extrinsics"].append(torch.from_numpy(c2l))
             out["rots"].append(torch.from_numpy(c2l[:3, :3]))

@@ -18,7 +18,7 @@ def _pose(rng, centre, spread, z):
 
 
 def synth_scene(ds_mod, seed, n_veh=3, n_rsu=2, n_drone=2, n_obj=40, n_pts=3000, far=True, cameras=True,
-                empty_cloud_agent=None, cur_ego_pose_flag=True, obj_span=(130.0, 36.0), agent_spread=1.0, pts_sigma=(35.0, 15.0)):
+                empty_cloud_agent=None, cur_ego_pose_flag=True, depth=False, obj_span=(130.0, 36.0), agent_spread=1.0, pts_sigma=(35.0, 15.0)):
     """-> OrderedDict cav_id -> record. `ds_mod` = the module under test (its pose helpers build the transforms; the
     reference's own `x1_to_x2` is compared with them separately)."""
     rng = np.random.default_rng(seed)
@@ -81,9 +81,10 @@ def synth_scene(ds_mod, seed, n_veh=3, n_rsu=2, n_drone=2, n_obj=40, n_pts=3000,
             ext[:3, 3] = [1.2, 0.0, 0.4]
             params["delay_extrinsic"] = ext[None]
             params["delay_intrinsic"] = np.array([[[640.0, 0, 640.0], [0, 640.0, 360.0], [0, 0, 1.0]]], dtype=np.float32)
+            rec["depth"] = ([Image.fromarray(rng.integers(0, 256, (72, 128, 3), dtype=np.uint8)).resize((1280, 720), Image.NEAREST)]
+                            if depth else [])
         else:
-            rec["cameras"] = []
-        rec["depth"] = []
+            rec["cameras"], rec["depth"] = [], []
         rec["params"] = params
         rec["lidar_np"] = cloud
         rec["dynamic_seg_label"] = np.zeros((2, 2), dtype=np.int64) + slot

@@ -178,7 +178,7 @@ def ref_env(tmp_path_factory):
 
 
 @needs_reference
-@pytest.mark.parametrize("variant", ["ego_rsu", "ego_drone", "no_proj_first", "no_shuffle_eval"])
+@pytest.mark.parametrize("variant", ["ego_rsu", "ego_drone", "no_proj_first", "no_shuffle_eval", "depth"])
 def test_live_against_the_reference_class(DS, ref_env, variant, monkeypatch):
     IFD, hypes0 = ref_env
     h = copy.deepcopy(hypes0)
@@ -187,10 +187,13 @@ def test_live_against_the_reference_class(DS, ref_env, variant, monkeypatch):
         h["ego_type"] = variant[4:]
     elif variant == "no_proj_first":
         h["fusion"]["args"]["proj_first"] = False
+    elif variant == "depth":
+        pass
     else:
         train, kw = False, {"shuffle": False}
         monkeypatch.setattr(IFD, "shuffle_points", lambda p: p)
-    scenes = [DC.synth_scene(DS, seed=41, n_pts=800), DC.synth_scene(DS, seed=42, n_veh=1, n_rsu=2, n_drone=0, n_pts=800)]
+    d = variant == "depth"
+    scenes = [DC.synth_scene(DS, seed=41, n_pts=800, depth=d), DC.synth_scene(DS, seed=42, n_veh=1, n_rsu=2, n_drone=0, n_pts=800, depth=d)]
     ref = MGD.reference_dataset(IFD, h, train)
     _, ref_batch = MGD.run_reference(ref, scenes, seed=9)
     _, _, ours = MGD.run_ours(DS, h, train, scenes, seed=9, **kw)
