@@ -482,10 +482,43 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
         out["ego"]["transformation_matrix"] = torch.from_numpy(np.identity(4)).float()
         return out
 
+    def generate_gt_bbx(self, data_dict):
+        """ground truth of the evaluation (`generate_gt_bbx_airv2x`, data_utils/post_processor/base_postprocessor.py:118-205):
+        the ego's valid boxes as [m,8,3] fp32 corners, restricted to the boxes whose 8 corners lie inside the x / y
+        detection range, with their class labels and track ids. The corner arithmetic is the reference's tensor path
+        (`boxes_to_corners_3d` on a float64 tensor: extents in fp64, the z-rotation as an fp32 matmul, centre added last)."""
+        ego = data_dict["ego"] if "ego" in data_dict else data_dict
+        box, mask = torch.as_tensor(ego["object_bbx_center"]), torch.as_tensor(ego["object_bbx_mask"])
+        b = box[mask == 1].double().cpu()
+        ids, classes = list(ego["object_ids"][0]), list(ego["class_ids"][0])
+        if self.order == "hwl":
+            b = b[:, [0, 1, 2, 5, 4, 3, 6]]
+        half = b.new_tensor(_CORNER_SIGNS) / 2
+        c = b[:, None, 3:6].repeat(1, 8, 1) * half[None]
+        cos, sin = torch.cos(b[:, 6]), torch.sin(b[:, 6])
+        zero, one = torch.zeros_like(cos), torch.ones_like(cos)
+        rot = torch.stack((cos, sin, zero, -sin, cos, zero, zero, zero, one), dim=1).view(-1, 3, 3).float()
+        corners = torch.matmul(c.float(), rot)
+        corners += b[:, None, 0:3]
+        first = {}
+        for i, oid in enumerate(ids):
+            first.setdefault(oid, i)
+        sel = list(first.values())
+        corners, classes, ids = corners[sel], [classes[i] for i in sel], [ids[i] for i in sel]
+        lo = torch.Tensor(self.gt_range[:2]).reshape(1, 1, -1)
+        hi = torch.Tensor(self.gt_range[3:5]).reshape(1, 1, -1)
+        keep = torch.all(torch.all(corners[:, :, :2] >= lo, dim=-1) & torch.all(corners[:, :, :2] <= hi, dim=-1), dim=-1)
+        idx = keep.nonzero(as_tuple=True)[0].tolist()
+        return corners[keep], [classes[i] for i in idx], [ids[i] for i in idx]
+
     def post_process(self, data_dict, output_dict):
-        """:913-938, predictions: GPU decode + rotated NMS of the ego's output (`postprocess.DetPostprocessor`)"""
+        """:913-938: (pred_box_tensor, pred_score, pred_labels, pred_boxes3d, gt_box_tensor, gt_class_labels, gt_track_ids);
+        predictions = GPU decode + rotated NMS of the ego's output (`postprocess.DetPostprocessor`)"""
         from .postprocess import DetPostprocessor
-        dev = output_dict["ego"]["psm"].device if "ego" in output_dict else output_dict["psm"].device
+        out = output_dict["ego"] if "ego" in output_dict else output_dict
+        dev = out["psm"].device
         if self._post is None or self._post[0] != dev:
             self._post = (dev, DetPostprocessor(self.params["postprocess"], dev))
-        return self._post[1](output_dict["ego"] if "ego" in output_dict else output_dict)
+        pred = self._post[1](out)
+        gt, classes, tracks = self.generate_gt_bbx(data_dict)
+        return (*pred, gt.to(dev), classes, tracks)

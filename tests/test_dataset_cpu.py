@@ -233,3 +233,21 @@ def test_helpers_against_the_functions_they_restate(DS, ref_env):
             rot, tran = DS.post_homography(resize, crop, flip, rotate)
             _, r2, t2 = camera_utils.img_transform([], torch.eye(2), torch.zeros(2), resize, dims, crop, flip, rotate)
             assert torch.equal(rot[:2, :2], r2) and torch.equal(tran[:2], t2) and float(rot[2, 2]) == 1.0
+
+
+@needs_reference
+def test_ground_truth_boxes_of_the_evaluation_against_the_reference(DS, ref_env):
+    """`generate_gt_bbx` == the reference's `generate_gt_bbx_airv2x` on the reference's own test collate"""
+    IFD, hypes = ref_env
+    scenes = [DC.synth_scene(DS, seed=61, n_obj=80, n_pts=300, cameras=True)]
+    ref = MGD.reference_dataset(IFD, hypes, False)
+    items, _ = MGD.run_reference(ref, scenes, seed=1)
+    ref_batch = ref.collate_batch_test(items)
+    gt_ref, cls_ref, ids_ref = ref.post_processor.generate_gt_bbx_airv2x(ref_batch)
+    ds, my_items, _ = MGD.run_ours(DS, hypes, False, scenes, seed=1)
+    mine = ds.collate_batch_test(my_items)
+    assert torch.equal(mine["ego"]["anchor_box"], ref_batch["ego"]["anchor_box"])
+    assert torch.equal(mine["ego"]["transformation_matrix"], ref_batch["ego"]["transformation_matrix"])
+    gt, cls, ids = ds.generate_gt_bbx(mine)
+    assert gt.dtype == gt_ref.dtype and gt.shape == gt_ref.shape and gt.shape[0] > 10
+    assert torch.equal(gt, gt_ref) and cls == cls_ref and ids == ids_ref
