@@ -161,3 +161,40 @@ class Trainer:
     def resume(self, saved_path):
         self.epoch, _ = load_saved_model(saved_path, self.model, None, self.optimizer, self.scheduler)
         return self.epoch
+
+
+class Evaluator:
+    """The evaluation loop of `tools/inference_multi_scenario.py:330-432` / `tools/inference_utils.py:99-134` for the
+    intermediate-fusion models: eval forward -> `dataset.post_process` (GPU decode + rotated NMS, ground truth of the ego) ->
+    TP / FP bookkeeping at IoU 0.3 / 0.5 / 0.7 (`caluclate_tp_fp`, utils/eval_utils_opv2v.py:41-95) -> VOC AP
+    (`eval_final_results` :155-189; like the reference's call, detections stay in frame order unless `global_sort`).
+    `scenario_of(batch)` groups the statistics like the reference's per-scenario timestamp key (default: one group)."""
+
+    def __init__(self, model, dataset, ious=(0.3, 0.5, 0.7), scenario_of=None):
+        self.model, self.dataset, self.ious = model, dataset, tuple(ious)
+        self.scenario_of = scenario_of or (lambda batch: "all")
+        self.stats, self.comm_rates = {}, []
+
+    def step(self, batch):
+        """batch: the collated dict of `collate_batch_test` ({"ego": ...}); returns this sample's predictions"""
+        from .postprocess import calculate_tp_fp
+        self.model.eval()
+        with torch.no_grad():
+            out = self.model(batch["ego"])
+        pred_box, score, labels, boxes3d, gt_box, gt_cls, gt_ids = self.dataset.post_process(batch, {"ego": out})
+        if "comm_rate" in out:
+            self.comm_rates.append(float(out["comm_rate"]))
+        st = self.stats.setdefault(self.scenario_of(batch), {t: {"tp": [], "fp": [], "gt": 0, "score": []} for t in self.ious})
+        if pred_box is not None and pred_box.shape[0] > 0:   # the reference skips a frame without detections (:366-367)
+            for t in self.ious:
+                calculate_tp_fp(pred_box, score, gt_box, st, t)
+        return pred_box, score, labels, boxes3d, gt_box
+
+    def summary(self, global_sort=False):
+        """{scenario: {iou: AP}} plus the mean communication rate"""
+        from .postprocess import calculate_ap
+        out = {}
+        for name, st in self.stats.items():
+            out[name] = {t: (calculate_ap(st, t, global_sort)[0] if st[t]["gt"] > 0 and st[t]["tp"] else 0.0) for t in self.ious}
+        out["comm_rate"] = sum(self.comm_rates) / len(self.comm_rates) if self.comm_rates else 0
+        return out

@@ -93,3 +93,48 @@ def test_trainer_step_on_a_dataset_batch():
     assert all(np.isfinite(losses)) and min(losses[4:]) < losses[0]
     for p in model.parameters():
         assert p.grad is None or bool(torch.isfinite(p.grad).all())
+
+
+def test_evaluator_over_dataset_batches_matches_the_oracle_chain():
+    """eval loop (tools/inference_multi_scenario.py:330-432): dataset test collate -> eval forward -> GPU decode + NMS ->
+    TP / FP -> AP, against the reference's python loops (oracle) fed with the same logits and the same ground truth.
+    The objectness bias is shifted so that ~150 of the 4096 anchors pass the gate (random weights pass nearly all)."""
+    import a2x_import
+
+    DS, cfg, hypes, model, scenes = _setup()
+    TL = a2x_import.pkg("train_loop")
+    pp = hypes["postprocess"]
+    np.random.seed(2)
+    ds = DS.IntermediateFusionDatasetAirv2x(hypes, False, False, source=scenes)
+    batches = [ds.collate_batch_test([ds[i]]) for i in range(len(scenes))]
+    model.eval()
+    with torch.no_grad():
+        obj = model(batches[0]["ego"])["obj"].reshape(-1).sort(descending=True)[0]
+        thr = float(pp["target_args"]["obj_threshold"])
+        model.obj_head.bias.add_(float(np.log(thr / (1 - thr)) - 0.5 * (obj[149] + obj[150])))
+    ev = TL.Evaluator(model, ds)
+    stat_o = {t: {"tp": [], "fp": [], "gt": 0, "score": []} for t in (0.3, 0.5, 0.7)}
+    n_gt, tie_free = 0, True
+    for batch in batches:
+        pred_box, score, labels, boxes3d, gt_box = ev.step(batch)
+        assert gt_box.shape[0] == int(batch["ego"]["object_bbx_mask"].sum()) > 0 and gt_box.shape[1:] == (8, 3)
+        n_gt += gt_box.shape[0]
+        with torch.no_grad():
+            out = model(batch["ego"])
+        oc, osc, ol, ob, oi = PO.post_process({k: out[k].cpu() for k in ("psm", "rm", "obj")}, pp)
+        assert oc is not None and pred_box.shape[0] == oc.shape[0] > 0
+        gaps = np.diff(np.sort(osc.numpy()))
+        tie_free = tie_free and (gaps.size == 0 or float(gaps.min()) > 2e-4)
+        for t in stat_o:
+            PO.tp_fp(oc, osc, gt_box.cpu(), stat_o, t)
+    res = ev.summary()
+    for t in (0.3, 0.5, 0.7):
+        st = ev.stats["all"][t]
+        assert st["gt"] == n_gt == stat_o[t]["gt"]
+        assert sum(st["tp"]) == sum(stat_o[t]["tp"]) and sum(st["fp"]) == sum(stat_o[t]["fp"]), t
+        if tie_free:
+            assert st["tp"] == stat_o[t]["tp"] and abs(res["all"][t] - PO.calculate_ap(stat_o, t)) < 1e-9
+        else:
+            assert abs(res["all"][t] - PO.calculate_ap(stat_o, t)) < 2e-2
+        assert 0.0 <= res["all"][t] <= 1.0
+    assert res["comm_rate"] > 0
