@@ -210,6 +210,13 @@ class Airv2xWhere2com(nn.Module):
             out["camera_bev"] = cam
         return out
 
+    @staticmethod
+    def _all_agents_flag(layout):
+        """body-box flag of every agent (sensor-frame clouds): one persistent tensor per layout (stable under graph replay)"""
+        if "all_flags" not in layout:
+            layout["all_flags"] = torch.ones_like(layout["ego_flags"])
+        return layout["all_flags"]
+
     def _lidar_inputs(self, data_dict, device, layout):
         raw = data_dict.get("raw_points")
         if raw is not None:
@@ -239,7 +246,7 @@ class Airv2xWhere2com(nn.Module):
                             "max_voxels": mv, "filter": bool(raw.get("filter", False)),
                             "transforms": xf,
                             "ego_flags": (None if not raw.get("filter", False) else
-                                          torch.ones_like(layout["ego_flags"]) if xf is not None else layout["ego_flags"])}}
+                                          self._all_agents_flag(layout) if xf is not None else layout["ego_flags"])}}
         out = {}
         for t in layout["agent_map"]:
             d = data_dict[t]["batch_merged_lidar_features_torch"]
@@ -342,25 +349,29 @@ class Airv2xWhere2com(nn.Module):
     # ------------------------------------------------------------------ CUDA-graph replay of the fused step
     def train_step_graphed(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0):
         """train_step() captured once into a CUDA graph (raw-point input only): per step the host copies the clouds /
-        labels into static buffers (pinned -> device), draws the top-K sizes and replays ~360 kernel launches with one
-        cudaGraphLaunch. Falls back to capture again when the agent layout or the cloud capacity changes."""
+        labels (and, for sensor-frame clouds, the agent -> ego poses) into static buffers (pinned -> device), draws the top-K
+        sizes and replays ~250 kernel launches with one cudaGraphLaunch. Captures again when the agent layout or the cloud
+        capacity changes."""
         assert self.training and data_dict.get("raw_points") is not None, "graphed step needs raw_points input"
         import random as _random
 
         dev = next(self.parameters()).device
         raw = data_dict["raw_points"]
-        if raw.get("transforms") is not None:
-            raise NotImplementedError("CUDA-graph replay takes ego-frame clouds; use train_step() with raw_points['transforms']")
         layout = self._layout(data_dict, dev)
         P = int(raw["points"].shape[0])
         graphs = self.__dict__.setdefault("_graphs", {})
-        key = (id(layout), float(cls_weight), float(reg_coe))
+        # sensor-frame clouds + poses (the dataset's batches) replay their own graph: the projection is part of the
+        # captured voxeliser launch and reads the poses from a static [N,4,4] buffer refreshed before every replay
+        key = (id(layout), float(cls_weight), float(reg_coe), raw.get("transforms") is not None)
         st = graphs.get(key)
         if st is None or st["cap"] < P:
             st = self._capture(data_dict, label_dict, cls_weight, reg_coe, layout, dev, max(P, int(P * 1.1)))
             graphs[key] = st
         st["points"][:P].copy_(raw["points"], non_blocking=True)
         st["offsets"].copy_(raw["offsets"], non_blocking=True)
+        if st["transforms"] is not None:
+            st["transforms"].copy_(torch.as_tensor(raw["transforms"]).to(torch.float32).reshape(st["transforms"].shape),
+                                   non_blocking=True)
         for k in ("targets", "pos_equal_one", "class_ids"):
             st["labels"][k].copy_(label_dict[k].reshape(st["labels"][k].shape), non_blocking=True)
         eng = self.engine
@@ -383,11 +394,11 @@ class Airv2xWhere2com(nn.Module):
         dev = next(self.parameters()).device
         raw = data_dict["raw_points"]
         if raw.get("transforms") is not None:
-            raise NotImplementedError("CUDA-graph replay takes ego-frame clouds; use train_step() with raw_points['transforms']")
+            raise NotImplementedError("the pipelined staging takes ego-frame clouds; use train_step_graphed() with raw_points['transforms']")
         layout = self._layout(data_dict, dev)
         P = int(raw["points"].shape[0])
         graphs = self.__dict__.setdefault("_graphs", {})
-        key = (id(layout), float(cls_weight), float(reg_coe))
+        key = (id(layout), float(cls_weight), float(reg_coe), False)          # the graph train_step_graphed uses too
         st = graphs.get(key)
         if st is None or st["cap"] < P:
             st = self._capture(data_dict, label_dict, cls_weight, reg_coe, layout, dev, max(P, int(P * 1.1)))
@@ -467,6 +478,10 @@ class Airv2xWhere2com(nn.Module):
         dd["raw_points"] = dict(raw)
         dd["raw_points"]["points"] = pts
         dd["raw_points"]["offsets"] = offs
+        xf = None
+        if raw.get("transforms") is not None:  # static pose buffer: _lidar_inputs passes a device fp32 tensor through as is
+            xf = torch.as_tensor(raw["transforms"]).to(device=dev, dtype=torch.float32).reshape(layout["n_total"], 4, 4).contiguous().clone()
+            dd["raw_points"]["transforms"] = xf
         rng_state = random.getstate()  # warm-up / capture must not consume the caller's top-K random stream
         # ... nor move the BatchNorm running statistics: the eager warm-up steps below really run (twice) on this batch
         bn_state = {n: b.clone() for n, b in self.named_buffers()}
@@ -491,7 +506,7 @@ class Airv2xWhere2com(nn.Module):
             self.engine.k_on_device = False
         self.launches_per_step = int(lib.a2x_launch_count() - l0)  # kernels of this library inside one replay
         random.setstate(rng_state)
-        return dict(graph=g, points=pts, offsets=offs, labels=labels, loss3=loss3, aux=self._last_aux, cap=cap,
+        return dict(graph=g, points=pts, offsets=offs, transforms=xf, labels=labels, loss3=loss3, aux=self._last_aux, cap=cap,
                     hw=self._last_aux["hw"], k_free_graph=True)
 
     def _output_dict(self, heads, layout):

@@ -126,7 +126,7 @@ class Trainer:
         model.train()
         labels = self.labels(batch)
         data = {k: v for k, v in batch.items() if k not in ("label_dict", "object_bbx_center", "object_bbx_mask", "object_class_ids")}
-        graphed = self.graph and data.get("raw_points") is not None and data["raw_points"].get("transforms") is None \
+        graphed = self.graph and data.get("raw_points") is not None \
             and hasattr(model, "train_step_graphed") and type(model).__name__ == "Airv2xWhere2com"
         if graphed:
             loss3 = model.train_step_graphed(data, labels, self.cls_weight, self.reg_coe)

@@ -138,3 +138,41 @@ def test_evaluator_over_dataset_batches_matches_the_oracle_chain():
             assert abs(res["all"][t] - PO.calculate_ap(stat_o, t)) < 2e-2
         assert 0.0 <= res["all"][t] <= 1.0
     assert res["comm_rate"] > 0
+
+
+def test_graphed_step_on_dataset_batches_matches_eager():
+    """the CUDA-graph replay takes the dataset's sensor-frame clouds + poses (static pose buffer refreshed per step):
+    same loss and gradients as the eager fused step over changing scenes of one layout, different point counts included"""
+    import a2x_import
+
+    DS, cfg, hypes, model, _ = _setup()
+    M = a2x_import.pkg("opencood.models.airv2x_where2com")
+    TL = a2x_import.pkg("train_loop")
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    eager = model.train()
+    graphed = M.Airv2xWhere2com(cfg["model_args"])
+    graphed.load_state_dict(sd)
+    graphed.cuda().train()
+    assigner = a2x_import.pkg("labels").TargetAssigner(hypes["postprocess"], "cuda")
+    kw = dict(cameras=False, obj_span=(20.0, 9.0), agent_spread=0.15, pts_sigma=(12.0, 6.0), n_veh=2, n_rsu=1, n_drone=1)
+    for step, (seed, npts) in enumerate([(71, 6000), (72, 6000), (73, 5200)]):
+        scenes = [DC.synth_scene(DS, seed=seed, n_pts=npts, **kw), DC.synth_scene(DS, seed=seed + 10, n_pts=npts, **kw)]
+        _, _, batch = MGD.run_ours(DS, hypes, True, scenes, seed=step)
+        ours = batch["ego"]
+        assert ours["record_len"].tolist() == [4, 4] and ours["raw_points"]["transforms"] is not None
+        labels = assigner(ours["object_bbx_center"], ours["object_bbx_mask"], ours["object_class_ids"])
+        random.seed(200 + step)
+        l_e = eager.train_step(ours, labels, 1.0, 2.0).clone()
+        random.seed(200 + step)
+        l_g = graphed.train_step_graphed(ours, labels, 1.0, 2.0).clone()
+        assert torch.allclose(l_e, l_g, rtol=1e-6, atol=1e-9), (step, l_e, l_g)
+        for (n, pe), (_, pg) in zip(eager.named_parameters(), graphed.named_parameters()):
+            if pe.grad is not None:
+                assert torch.allclose(pe.grad, pg.grad, rtol=1e-4, atol=1e-6 * float(pe.grad.abs().max()) + 1e-12), (step, n)
+    assert len(graphed._graphs) == 1 and graphed.launches_per_step > 200
+    # and the Trainer takes that path for dataset batches
+    th = dict(hypes, loss={"args": cfg["loss_args"]},
+              optimizer={"core_method": "Adam", "lr": 0.002, "args": {"eps": 1e-10, "weight_decay": 1e-4}},
+              lr_scheduler={"core_method": "multistep", "gamma": 0.1, "step_size": [10, 25, 40]})
+    tr = TL.Trainer(graphed, th)
+    assert bool(torch.isfinite(tr.step(ours)).all()) and len(graphed._graphs) >= 1
