@@ -347,6 +347,8 @@ class Airv2xWhere2com(nn.Module):
         return loss3
 
     # ------------------------------------------------------------------ CUDA-graph replay of the fused step
+    max_graphs = 32   # captured step graphs kept per model (one per agent layout x loss weights x input frame)
+
     def train_step_graphed(self, data_dict, label_dict, cls_weight=1.0, reg_coe=2.0):
         """train_step() captured once into a CUDA graph (raw-point input only): per step the host copies the clouds /
         labels (and, for sensor-frame clouds, the agent -> ego poses) into static buffers (pinned -> device), draws the top-K
@@ -366,7 +368,10 @@ class Airv2xWhere2com(nn.Module):
         st = graphs.get(key)
         if st is None or st["cap"] < P:
             st = self._capture(data_dict, label_dict, cls_weight, reg_coe, layout, dev, max(P, int(P * 1.1)))
+            graphs.pop(key, None)
             graphs[key] = st
+            while len(graphs) > self.max_graphs:      # a dataset with many agent layouts: drop the oldest captures
+                graphs.pop(next(iter(graphs)))
         st["points"][:P].copy_(raw["points"], non_blocking=True)
         st["offsets"].copy_(raw["offsets"], non_blocking=True)
         if st["transforms"] is not None:

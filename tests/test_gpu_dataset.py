@@ -176,3 +176,40 @@ def test_graphed_step_on_dataset_batches_matches_eager():
               lr_scheduler={"core_method": "multistep", "gamma": 0.1, "step_size": [10, 25, 40]})
     tr = TL.Trainer(graphed, th)
     assert bool(torch.isfinite(tr.step(ours)).all()) and len(graphed._graphs) >= 1
+
+
+@pytest.mark.parametrize("name", ["cobevt", "v2xvit"])
+def test_dataset_batch_feeds_the_transformer_fusion_models(name):
+    """the same batch layout drives Airv2xCoBEVT / Airv2xV2XVit (they read `prior_encoding` / `spatial_correction_matrix` of
+    the dataset's collate as well): logits equal to the reference-layout voxel dict of the same clouds"""
+    import a2x_import
+
+    if name == "cobevt":
+        import cobevt_common as CC
+        cfg, gold = CC.load_small()
+        model = a2x_import.pkg("opencood.models.airv2x_cobevt").Airv2xCoBEVT(cfg["model_args"])
+        model.load_state_dict(CC.golden_state_dict(model, gold))
+    else:
+        import v2xvit_common as VC
+        cfg, gold = VC.load_small()
+        model = a2x_import.pkg("opencood.models.airv2x_v2xvit").Airv2xV2XVit(cfg["model_args"])
+        model.load_state_dict(VC.golden_state_dict(model, gold))
+    model.cuda().eval()
+    DS = a2x_import.pkg("intermediate_fusion_dataset")
+    hypes = json.load(open(os.path.join(ROOT, "tests", "golden", "dataset_config.json")))
+    hypes = dict(hypes, preprocess=cfg["preprocess"], postprocess=cfg["postprocess"],
+                 train_params=dict(hypes["train_params"], max_cav=cfg["model_args"]["max_cav"]))
+    scene = DC.synth_scene(DS, seed=81, n_veh=2, n_rsu=1, n_drone=1, cameras=False, n_pts=6000, obj_span=(20.0, 9.0),
+                           agent_spread=0.15, pts_sigma=(12.0, 6.0))
+    _, _, batch = MGD.run_ours(DS, hypes, False, [scene], seed=3)
+    ours = batch["ego"]
+    L = sum(cfg["model_args"]["max_cav"].values())
+    assert ours["prior_encoding"].shape == (1, L, 3) and ours["spatial_correction_matrix"].shape == (1, L, 4, 4)
+    ref = _voxel_dict(ours, hypes, False)
+    for k in ("prior_encoding", "spatial_correction_matrix", "pairwise_t_matrix_collab"):
+        ref[k] = ours[k]
+    with torch.no_grad():
+        a = model(ours)
+        b = model(C.to_device(ref, "cuda"))
+    for k in ("psm", "rm", "obj"):
+        assert torch.equal(a[k], b[k]) and bool(torch.isfinite(a[k]).all()), k
