@@ -74,8 +74,8 @@ def read_pcd(path):
         elif mode == "ascii":
             raw = np.loadtxt(f, dtype=np.float64, ndmin=2)[:n]
             rec = np.zeros(raw.shape[0], dtype=dt)
-            for i, name in enumerate(fields):
-                rec[name] = raw[:, i].astype(dt[name]) if dt[name].kind != "f" or name != "rgb" else raw[:, i].astype(np.float32)
+            for i, name in enumerate(fields):        # a float `rgb` keeps its bit pattern: 10 significant digits round-trip fp32
+                rec[name] = raw[:, i].astype(dt[name])
         else:
             raise NotImplementedError("%s: PCD DATA %s" % (path, mode))
     out = np.zeros((rec.shape[0], 4), dtype=np.float32)

@@ -52,6 +52,18 @@ def test_pcd_reader_round_trips_binary_and_ascii(tmp_path):
                 "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS 3\nDATA ascii\n1 2 3 0.5\n-4.5 5 6 0.25\n7 8 -9 1\n")
     assert np.array_equal(S.read_pcd(str(tmp_path / "a.pcd")),
                           np.array([[1, 2, 3, 0.5], [-4.5, 5, 6, 0.25], [7, 8, -9, 1]], dtype=np.float32))
+    # ascii with the packed float rgb (denormals for r < 128) and with an unsigned rgb
+    r = np.array([0, 1, 127, 128, 255], dtype=np.uint32)
+    for kind, col in (("F", ["%.10g" % v for v in (r << 16).view(np.float32)]), ("U", [str(int(v)) for v in (r << 16) | 0x1234])):
+        with open(tmp_path / "c.pcd", "w") as f:
+            f.write("VERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F %s\nCOUNT 1 1 1 1\nWIDTH 5\nHEIGHT 1\nPOINTS 5\nDATA ascii\n" % kind)
+            for i in range(5):
+                f.write("%d 0 0 %s\n" % (i, col[i]))
+        assert np.array_equal(S.read_pcd(str(tmp_path / "c.pcd"))[:, 3], r.astype(np.float32) / 255.0), kind
+    with open(tmp_path / "z.pcd", "w") as f:
+        f.write("VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary_compressed\n")
+    with pytest.raises(NotImplementedError):
+        S.read_pcd(str(tmp_path / "z.pcd"))
 
 
 def test_scan_orders_agents_and_counts_samples(hypes):
