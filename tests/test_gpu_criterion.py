@@ -5,7 +5,6 @@ autograd on the CPU. Tolerances: value 1e-4 relative, gradients 1e-6 + 1e-4 rela
 import json
 import os
 
-import numpy as np
 import pytest
 import torch
 

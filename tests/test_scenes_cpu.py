@@ -14,7 +14,6 @@ from unittest.mock import MagicMock
 
 import numpy as np
 import pytest
-import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
