@@ -39,8 +39,44 @@ _PCD_TYPES = {("F", 4): "f4", ("F", 8): "f8", ("U", 1): "u1", ("U", 2): "u2", ("
               ("I", 2): "i2", ("I", 4): "i4"}
 
 
+def lzf_decompress(src, out_len):
+    """LZF (liblzf, the codec of PCD `DATA binary_compressed`): control byte < 32 = literal run of ctrl + 1 bytes; otherwise
+    a back reference of length (ctrl >> 5) + 2 (7 = extended by the next byte) at distance ((ctrl & 31) << 8 | next) + 1."""
+    src = memoryview(src)
+    out = bytearray(out_len)
+    i, o, n = 0, 0, len(src)
+    while i < n:
+        ctrl = src[i]
+        i += 1
+        if ctrl < 32:
+            run = ctrl + 1
+            out[o:o + run] = src[i:i + run]
+            i += run
+            o += run
+            continue
+        length = ctrl >> 5
+        if length == 7:
+            length += src[i]
+            i += 1
+        length += 2
+        ref = o - (((ctrl & 31) << 8) | src[i]) - 1
+        i += 1
+        if ref < 0 or o + length > out_len:
+            raise ValueError("corrupt LZF stream")
+        if ref + length <= o:
+            out[o:o + length] = out[ref:ref + length]
+        else:                                   # overlapping copy = a repeating pattern of period o - ref
+            period = o - ref
+            chunk = bytes(out[ref:o])
+            out[o:o + length] = (chunk * (length // period + 1))[:length]
+        o += length
+    if o != out_len:
+        raise ValueError("LZF stream ends at %d of %d bytes" % (o, out_len))
+    return bytes(out)
+
+
 def read_pcd(path):
-    """PCD v0.7 (ascii / binary) -> [n, 4] float32 (x, y, z, intensity). Intensity = red channel / 255 of the packed `rgb`
+    """PCD v0.7 (ascii / binary / binary_compressed) -> [n, 4] float32 (x, y, z, intensity). Intensity = red channel / 255 of the packed `rgb`
     field (how open3d exposes `colors[:, 0]` for the clouds the simulator saved), or an `intensity` field if present."""
     with open(path, "rb") as f:
         fields, sizes, types, counts, n, mode = [], [], [], [], None, None
@@ -76,6 +112,14 @@ def read_pcd(path):
             rec = np.zeros(raw.shape[0], dtype=dt)
             for i, name in enumerate(fields):        # a float `rgb` keeps its bit pattern: 10 significant digits round-trip fp32
                 rec[name] = raw[:, i].astype(dt[name])
+        elif mode == "binary_compressed":     # two uint32 sizes, LZF payload, fields stored one after the other (SoA)
+            csize, usize = np.frombuffer(f.read(8), dtype="<u4")
+            flat = lzf_decompress(f.read(int(csize)), int(usize))
+            rec = np.zeros(n, dtype=dt)
+            pos = 0
+            for name in fields:
+                rec[name] = np.frombuffer(flat, dtype=dt[name], count=n, offset=pos)
+                pos += n * dt[name].itemsize
         else:
             raise NotImplementedError("%s: PCD DATA %s" % (path, mode))
     out = np.zeros((rec.shape[0], 4), dtype=np.float32)
@@ -230,6 +274,10 @@ class AirV2XScenes:
         return out
 
     def __getitem__(self, idx):
+        if idx < 0:
+            idx += len(self)
+        if not 0 <= idx < len(self):
+            raise IndexError("sample %d of %d" % (idx, len(self)))
         s = next(i for i, end in enumerate(self.len_record) if idx < end)
         agents = self.scenarios[s]
         t_index = idx if s == 0 else idx - self.len_record[s - 1]

@@ -76,3 +76,58 @@ def write_tree(root, seed=0, n_scenarios=2, n_timestamps=3, n_pts=600, img_hw=(3
                 with open(os.path.join(d, "vector_map.json"), "w") as f:
                     f.write("{}")
     return root
+
+
+def lzf_compress(data):
+    """a small greedy LZF encoder (longest match in the last 8191 bytes, O(n * window): test-sized inputs only)"""
+    data = bytes(data)
+    out, lit, i, n = bytearray(), bytearray(), 0, len(data)
+
+    def flush():
+        for k in range(0, len(lit), 32):
+            chunk = lit[k:k + 32]
+            out.append(len(chunk) - 1)
+            out.extend(chunk)
+        lit.clear()
+    while i < n:
+        best, dist = 0, 0
+        if i + 3 <= n:
+            start = max(0, i - 8191)
+            j = data.rfind(data[i:i + 3], start, i + 2)
+            while j != -1 and j < i:
+                m = 3
+                while i + m < n and m < 264 and data[j + m] == data[i + m]:
+                    m += 1
+                if m > best:
+                    best, dist = m, i - j
+                j = data.rfind(data[i:i + 3], start, j + 2) if j > start else -1
+        if best >= 3:
+            flush()
+            length, off = best - 2, dist - 1
+            if length < 7:
+                out.append((length << 5) | (off >> 8))
+            else:
+                out.append((7 << 5) | (off >> 8))
+                out.append(length - 7)
+            out.append(off & 255)
+            i += best
+        else:
+            lit.append(data[i])
+            i += 1
+    flush()
+    return bytes(out)
+
+
+def write_pcd_compressed(path, cloud):
+    """DATA binary_compressed: the fields one after the other, LZF-compressed, preceded by the two sizes"""
+    n = cloud.shape[0]
+    r = np.clip(np.round(cloud[:, 3] * 255), 0, 255).astype(np.uint32)
+    flat = b"".join([cloud[:, 0].astype("<f4").tobytes(), cloud[:, 1].astype("<f4").tobytes(),
+                     cloud[:, 2].astype("<f4").tobytes(), (r << 16).astype("<u4").tobytes()])
+    comp = lzf_compress(flat)
+    head = ("VERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\n"
+            "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary_compressed\n" % (n, n))
+    with open(path, "wb") as f:
+        f.write(head.encode("ascii"))
+        f.write(np.array([len(comp), len(flat)], dtype="<u4").tobytes())
+        f.write(comp)

@@ -59,10 +59,23 @@ def test_pcd_reader_round_trips_binary_and_ascii(tmp_path):
             for i in range(5):
                 f.write("%d 0 0 %s\n" % (i, col[i]))
         assert np.array_equal(S.read_pcd(str(tmp_path / "c.pcd"))[:, 3], r.astype(np.float32) / 255.0), kind
-    with open(tmp_path / "z.pcd", "w") as f:
-        f.write("VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary_compressed\n")
+    # binary_compressed (LZF): a cloud with repeated values (back references, overlapping runs) and the decoder alone
+    rep = np.repeat(cloud[:40], 5, axis=0)
+    rep[:, 2] = 0.25
+    SC.write_pcd_compressed(str(tmp_path / "z.pcd"), rep)
+    assert np.array_equal(S.read_pcd(str(tmp_path / "z.pcd")), rep)
+    for blob in (b"", b"a", b"abcabcabcabcabcabcabcabcabc" * 20, bytes(300), bytes(g.integers(0, 4, 5000, dtype=np.uint8)),
+                 bytes(g.integers(0, 256, 3000, dtype=np.uint8))):
+        comp = SC.lzf_compress(blob)
+        assert S.lzf_decompress(comp, len(blob)) == blob
+        if len(blob) >= 300 and len(set(blob)) <= 4:
+            assert len(comp) < len(blob) // 2                    # the encoder really emits back references
+    with pytest.raises(ValueError):
+        S.lzf_decompress(b"\x20\x05", 10)                       # reference before the start of the output
+    with open(tmp_path / "q.pcd", "w") as f:
+        f.write("VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA quantum\n")
     with pytest.raises(NotImplementedError):
-        S.read_pcd(str(tmp_path / "z.pcd"))
+        S.read_pcd(str(tmp_path / "q.pcd"))
 
 
 def test_scan_orders_agents_and_counts_samples(hypes):
