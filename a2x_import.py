@@ -44,3 +44,21 @@ def uninstall(prev):
             sys.modules.pop(key, None)
         else:
             sys.modules[key] = mod
+
+
+def install_dataset(name="IntermediateFusionDatasetAirv2x"):
+    """Make the UNMODIFIED `opencood.data_utils.datasets.build_dataset(hypes, visualize, train)` (datasets/__init__.py:94-106:
+    a lookup of `fusion.core_method` in the module's `__all__` dict) return this repo's dataset class. Needs the reference
+    package importable; returns the previous entry (pass it to `uninstall_dataset`)."""
+    import opencood.data_utils.datasets as D
+    prev = D.__all__.get(name)
+    D.__all__[name] = getattr(pkg("intermediate_fusion_dataset"), name)
+    return prev
+
+
+def uninstall_dataset(prev, name="IntermediateFusionDatasetAirv2x"):
+    import opencood.data_utils.datasets as D
+    if prev is None:
+        D.__all__.pop(name, None)
+    else:
+        D.__all__[name] = prev

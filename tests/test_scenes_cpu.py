@@ -156,3 +156,24 @@ def test_live_against_the_reference_dataset_on_a_directory(hypes, train, delay, 
     assert MGD.compare(ref.collate_batch_train(ref_items), mine.collate_batch_train(my_items), full, train) < 1e-9
     if train:   # the ego is re-drawn per sample: more than one vehicle was the ego over the six samples
         assert len({a["ego"]["ego_id"] for a in ref_items}) > 1
+
+
+@needs_reference
+def test_real_build_dataset_dispatches_to_the_b200_dataset(hypes, tmp_path, monkeypatch):
+    """the UNMODIFIED `build_dataset(hypes, visualize, train)` returns this repo's class after `a2x_import.install_dataset()`
+    and that object scans the directory the yaml names"""
+    monkeypatch.chdir(tmp_path)
+    MGD.reference_env()
+    from opencood.data_utils.datasets import build_dataset
+    full = ref_import.load_hypes(MGD.YAML)
+    full.update(root_dir=hypes["root_dir"], validate_dir=hypes["validate_dir"])
+    prev = a2x_import.install_dataset()
+    try:
+        ds = build_dataset(full, visualize=False, train=False)
+        assert type(ds).__module__.startswith("airv2x-perception_b200.") and type(ds).__name__ == "IntermediateFusionDatasetAirv2x"
+        assert len(ds) == 6 and ds.collate_batch_test([ds[1]])["ego"]["record_len"].tolist() == [6]
+    finally:
+        a2x_import.uninstall_dataset(prev)
+    assert build_dataset.__module__ == "opencood.data_utils.datasets"
+    import opencood.data_utils.datasets as D
+    assert D.__all__["IntermediateFusionDatasetAirv2x"].__module__.startswith("opencood.")
