@@ -22,6 +22,7 @@ Host logic only (numpy / torch CPU tensors): no kernel work happens here and not
 """
 import heapq
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -241,7 +242,6 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
     def __init__(self, params, visualize=False, train=True, source=None, shuffle=True, pin_memory=False):
         self.params, self.visualize, self.train, self.training = params, visualize, train, train
         if source is None:      # the reference's behaviour: scan params["root_dir"] / ["validate_dir"] (basedataset.py:73-207)
-            import os
             root = params.get("root_dir" if train else "validate_dir")
             if root and os.path.isdir(root):
                 from .airv2x_scenes import AirV2XScenes
