@@ -124,28 +124,39 @@ def corners_to_boxes(corners, order):
     return np.concatenate([centre] + dims + [yaw], axis=1).reshape(len(c), 7)
 
 
-def project_world_objects(objects, ego_lidar_pose, lidar_range, order):
+def project_world_objects(objects, ego_lidar_pose, lidar_range, order, cache=None):
     """World-frame objects `{id: {"location": [x,y,z,roll,yaw,pitch], "center", "extent", "class"}}` -> boxes in the ego
     lidar frame that lie inside `lidar_range` with all 8 corners: (boxes [n,7] f64, ids, classes), in dict order
     (`project_world_objects_airv2x`, utils/box_utils.py:576-647; the range test runs on fp32 corners like
-    `mask_boxes_outside_range_numpy` :433-472)."""
+    `mask_boxes_outside_range_numpy` :433-472).
+    `cache` (a dict that lives for ONE ego pose / range, i.e. one scene): an object record that several agents list — the
+    agents of a timestamp share one objects.pkl — is projected once; the per-object arithmetic does not depend on which
+    other objects are in the call, so the values are those of the uncached evaluation."""
     ids = list(objects.keys())
     if not ids:
         return np.zeros((0, 7)), [], []
-    world_to_ego = np.linalg.inv(pose_to_matrix(ego_lidar_pose))
-    corners = np.empty((len(ids), 8, 3))
-    for i, oid in enumerate(ids):
-        o = objects[oid]
-        loc, ctr = o["location"], o["center"]
-        pose = [loc[0] + ctr[0], loc[1] + ctr[1], loc[2] + ctr[2], loc[3], loc[4], loc[5]]
-        local = np.r_[(_CORNER_SIGNS * np.asarray(o["extent"], dtype=np.float64)[None, :3]).T, [np.ones(8)]]   # [4,8]
-        corners[i] = np.dot(np.dot(world_to_ego, pose_to_matrix(pose)), local).T[:, :3]
-    boxes = corners_to_boxes(corners, order)
-    c32 = boxes_to_corners_f32(boxes, order).astype(np.float64)
-    lo, hi = np.asarray(lidar_range[0:3], dtype=np.float64), np.asarray(lidar_range[3:6], dtype=np.float64)
-    keep = ((c32 >= lo) & (c32 <= hi)).all(axis=2).sum(axis=1) >= 8
-    sel = np.flatnonzero(keep)
-    return boxes[sel], [ids[i] for i in sel], [objects[ids[i]]["class"] for i in sel]
+    cache = {} if cache is None else cache
+    todo = [oid for oid in ids if id(objects[oid]) not in cache]
+    if todo:
+        world_to_ego = cache.get("world_to_ego")
+        if world_to_ego is None:
+            world_to_ego = cache["world_to_ego"] = np.linalg.inv(pose_to_matrix(ego_lidar_pose))
+        corners = np.empty((len(todo), 8, 3))
+        for i, oid in enumerate(todo):
+            o = objects[oid]
+            loc, ctr = o["location"], o["center"]
+            pose = [loc[0] + ctr[0], loc[1] + ctr[1], loc[2] + ctr[2], loc[3], loc[4], loc[5]]
+            local = np.r_[(_CORNER_SIGNS * np.asarray(o["extent"], dtype=np.float64)[None, :3]).T, [np.ones(8)]]   # [4,8]
+            corners[i] = np.dot(np.dot(world_to_ego, pose_to_matrix(pose)), local).T[:, :3]
+        boxes = corners_to_boxes(corners, order)
+        c32 = boxes_to_corners_f32(boxes, order).astype(np.float64)
+        lo, hi = np.asarray(lidar_range[0:3], dtype=np.float64), np.asarray(lidar_range[3:6], dtype=np.float64)
+        keep = ((c32 >= lo) & (c32 <= hi)).all(axis=2).sum(axis=1) >= 8
+        for i, oid in enumerate(todo):      # the record itself is kept alive next to its result: id() stays unique
+            cache[id(objects[oid])] = (objects[oid], boxes[i], bool(keep[i]))
+    sel = [oid for oid in ids if cache[id(objects[oid])][2]]
+    out = np.stack([cache[id(objects[oid])][1] for oid in sel]) if sel else np.zeros((0, 7))
+    return out, sel, [objects[oid]["class"] for oid in sel]
 
 
 # ----------------------------------------------------------------------------------------------------- cameras
@@ -313,10 +324,10 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
             out["post_trans"].append(tran)
         return {k: torch.stack(v) for k, v in out.items()}
 
-    def get_item_single_car(self, rec, ego_pose):
+    def get_item_single_car(self, rec, ego_pose, cache=None):
         """ground truth of this agent's surroundings in the ego frame + its raw cloud (:456-618). The cloud is NOT filtered
         or projected here: it is handed to the GPU with `transformation_matrix`."""
-        boxes, ids, classes = project_world_objects(rec["params"]["objects"], ego_pose, self.gt_range, self.order)
+        boxes, ids, classes = project_world_objects(rec["params"]["objects"], ego_pose, self.gt_range, self.order, cache)
         if len(ids) > self.max_num:     # the reference writes into a [max_num, 7] array (base_postprocessor.py:614-621)
             raise IndexError("more than max_num = %d objects around one agent" % self.max_num)
         cam = self._cam_inputs(rec)
@@ -354,12 +365,12 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
                 ego_id, ego_pose = cid, rec["params"]["delay_ego_lidar_pose"]
                 break
         per_type = {t: [] for t in MODEL_ORDER}
-        ego_rec = None
+        ego_rec, projected = None, {}           # object records shared between agents are projected once per scene
         for cid, rec in base_data_dict.items():
             t = rec["agent_type"]
             if rec["distance_to_ego"] > COM_RANGE[t]:
                 continue
-            item = self.get_item_single_car(rec, ego_pose)
+            item = self.get_item_single_car(rec, ego_pose, projected)
             item.update(cav_id=cid, distance=rec["distance_to_ego"],
                         velocity=rec["params"]["odometry"]["ego_speed"] / 30.0, time_delay=float(rec["time_delay"]),
                         spatial_correction_matrix=np.asarray(rec["params"]["spatial_correction_matrix"]))
