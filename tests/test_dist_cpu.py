@@ -98,3 +98,54 @@ def test_agent_parallel_plan_and_gather_world2():
     for _, out in res:
         assert out.shape == (2, 2, 3, 4)
         assert torch.equal(out[0], torch.full((2, 3, 4), 1.0)) and torch.equal(out[1], torch.full((2, 3, 4), 2.0))
+
+
+def _dataset_worker(rank, world, port, q, tree):
+    """scene-parallel input side: every rank builds the dataset on the same directory, a DistributedSampler hands each rank
+    its shard, the ranks' batches are collated independently and the union covers every sample exactly once"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import json
+
+    import a2x_import
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    DS = a2x_import.pkg("intermediate_fusion_dataset")
+    hypes = json.load(open(os.path.join(ROOT, "tests", "golden", "dataset_config.json")))
+    hypes.update(root_dir=tree, validate_dir=tree, task="det")
+    ds = DS.IntermediateFusionDatasetAirv2x(hypes, False, train=False)
+    sampler = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=False)
+    loader = torch.utils.data.DataLoader(ds, batch_size=1, sampler=sampler, collate_fn=ds.collate_batch_train, num_workers=0)
+    seen, agents = [], 0
+    for batch in loader:
+        ego = batch["ego"]
+        seen.append((ego["scenario_index_list"][0], ego["timestamp_key_list"][0]))
+        agents += int(ego["record_len"].sum())
+        assert ego["raw_points"]["offsets"][-1] == 600 * int(ego["record_len"].sum())
+    total = torch.tensor([agents], dtype=torch.int64)
+    dist.all_reduce(total)
+    q.put((rank, seen, int(total)))
+    dist.destroy_process_group()
+
+
+def test_dataset_shards_over_two_ranks(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenes_common as SC
+
+    tree = SC.write_tree(str(tmp_path / "tree"), seed=9, late_agent=False)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dataset_worker, args=(r, 2, port, q, tree)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, s0, t0), (_, s1, t1) = res
+    assert len(s0) == len(s1) == 3 and not set(s0) & set(s1)
+    assert sorted(s0 + s1) == [(s, t) for s in (0, 1) for t in (0, 5, 10)]
+    assert t0 == t1 == 6 * 6            # six agents in every one of the six samples, summed over the ranks
