@@ -69,3 +69,23 @@ def test_every_entry_point_is_documented():
     prefixes = [m.group(1) for m in re.finditer(r"(a2x_[a-z0-9_]+_)\*", doc)]
     missing = [n for n in names if n not in known and not any(n.startswith(p) for p in prefixes)]
     assert len(names) > 70 and not missing, missing
+
+
+def test_header_is_plain_c_and_cpp(tmp_path):
+    """the boundary is a C ABI: include/airv2x_b200.h compiles as C99 (-pedantic, no warnings) and as C++17 with no
+    dependency beyond the standard headers (no torch / CUDA types in any signature)"""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    src = tmp_path / "h.c"
+    src.write_text('#include "airv2x_b200.h"\nint (*probe)(void) = a2x_version;\nint main(void) { return probe == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only"],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(os.path.join(inc, "airv2x_b200.h")).read()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S) and "cuda_runtime" not in text
