@@ -164,6 +164,72 @@ def compare(ref_batch, ours_batch, hypes, train):
     return dev
 
 
+TREE_SEED, TREE_ORDER = 6, [0, 4, 2, 5, 1, 3]
+WILD = {"seed": 20, "async": True, "async_mode": "sim", "async_overhead": 100, "loc_err": True, "xyz_std": 0.2, "ryp_std": 0.2,
+        "data_size": 0, "transmission_speed": 27, "backbone_delay": 0}
+
+
+def tree_hypes(hypes, tree):
+    """training on a directory with one timestamp of communication delay, localisation noise and the delayed ego pose"""
+    h = copy.deepcopy(hypes)
+    h.update(root_dir=tree, validate_dir=tree, task="det", wild_setting=dict(WILD))
+    h["fusion"]["args"]["cur_ego_pose_flag"] = False
+    return h
+
+
+def run_tree(ds, order=TREE_ORDER, seed=3):
+    import random
+    random.seed(seed)
+    np.random.seed(seed)
+    items = [ds[i] for i in order]
+    return items, ds.collate_batch_train(items)
+
+
+def tree_case(IFD, DS, hypes):
+    """the reference's FULL path — its own `__init__` directory scan, `retrieve_base_data`, `reform_param`, ego re-draw, time
+    delay, localisation noise — on the seeded synthetic tree of tests/scenes_common.py, recorded for the machines that have
+    no reference tree (open3d's reader replaced by this repo's `read_pcd`: the .pcd decoding itself stays unpinned)"""
+    import shutil
+    import tempfile
+    from unittest.mock import MagicMock
+
+    import scenes_common as SC
+    from opencood.utils import pcd_utils
+    S = a2x_import.pkg("airv2x_scenes")
+    tmp = tempfile.mkdtemp(prefix="a2x_tree_")
+    try:
+        tree = SC.write_tree(os.path.join(tmp, "tree"), seed=TREE_SEED, late_agent=False)
+        h = tree_hypes(hypes, tree)
+
+        def fake_read(path):
+            c = S.read_pcd(path)
+            return MagicMock(points=c[:, :3].astype(np.float64), colors=np.stack([c[:, 3]] * 3, axis=1).astype(np.float64))
+        pcd_utils.o3d.io.read_point_cloud = fake_read
+        ref = IFD.IntermediateFusionDatasetAirv2x(h, False, True)
+        ref.pre_processor = _OraclePreprocessor(h["preprocess"], True)
+        ref_items, ref_batch = run_tree(ref)
+        mine = DS.IntermediateFusionDatasetAirv2x(h, False, True, source=S.AirV2XScenes(h, True, load_cameras=True, load_seg=True))
+        my_items, my_batch = run_tree(mine)
+        dev = compare(ref_batch, my_batch, h, True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    r = ref_batch["ego"]
+    print("tree: %d samples, egos %s, record_len %s, box deviation %.1e: reference == ours"
+          % (len(ref_items), [a["ego"]["ego_id"] for a in ref_items], r["record_len"].tolist(), dev))
+    out = {"tree/ego_ids": np.array([a["ego"]["ego_id"] for a in ref_items], dtype=np.int64),
+           "tree/timestamp_keys": np.array([a["ego"]["timestamp_key"] for a in ref_items], dtype=np.int64),
+           "tree/object_ids": np.array([i for ids in r["object_ids"] for i in ids], dtype=np.int64)}
+    for k in ("record_len", "pairwise_t_matrix_collab", "prior_encoding", "spatial_correction_matrix", "object_bbx_center",
+              "object_bbx_mask"):
+        out["tree/" + k] = r[k].numpy()
+    for t in ("vehicle", "rsu", "drone"):
+        v = r[t]["batch_merged_lidar_features_torch"]
+        out["tree/%s/record_len" % t] = r[t]["record_len"].numpy()
+        out["tree/%s/voxel_coords" % t] = v["voxel_coords"].numpy().astype(np.int32)
+        out["tree/%s/voxel_sum" % t] = v["voxel_features"].numpy().astype(np.float64).sum(axis=(1, 2))
+    return out
+
+
 def main():
     IFD = reference_env()
     DS = a2x_import.pkg("intermediate_fusion_dataset")
@@ -199,6 +265,7 @@ def main():
                     out["%s/%s/cam_%s" % (name, t, k)] = c.numpy()
                 else:
                     out["%s/%s/cam_imgs_mean" % (name, t)] = c.numpy().astype(np.float64).mean(axis=(2, 3, 4))
+    out.update(tree_case(IFD, DS, hypes))
     import json
     keys = ("fusion", "preprocess", "postprocess", "train_params", "collaborators", "active_sensors", "ego_type")
     with open(os.path.join(ROOT, "tests", "golden", "dataset_config.json"), "w") as f:   # the yaml keys the dataset reads

@@ -105,6 +105,36 @@ def test_dataset_scans_the_directory_when_no_source_is_given(hypes):
     assert batch["vehicle"]["record_len"].tolist() == [2, 3] and batch["drone"]["batch_idxs"] == [0, 1]
 
 
+def test_directory_pipeline_equals_the_recorded_reference_run(hypes, tmp_path):
+    """runs everywhere: this repo's scan + retrieval + assembly on the seeded tree against what the REAL reference (its own
+    `__init__` scan, `retrieve_base_data`, `reform_param`; training mode, one timestamp of delay, localisation noise, delayed
+    ego pose) produced for the same tree when scripts/make_golden_dataset.py recorded it"""
+    S = a2x_import.pkg("airv2x_scenes")
+    DS = a2x_import.pkg("intermediate_fusion_dataset")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "dataset.npz"))
+    tree = SC.write_tree(str(tmp_path / "tree"), seed=MGD.TREE_SEED, late_agent=False)
+    h = MGD.tree_hypes(hypes, tree)
+    ds = DS.IntermediateFusionDatasetAirv2x(h, False, True, source=S.AirV2XScenes(h, True, load_cameras=True, load_seg=True))
+    items, batch = MGD.run_tree(ds)
+    o = batch["ego"]
+    assert [a["ego"]["ego_id"] for a in items] == gold["tree/ego_ids"].tolist()
+    assert [a["ego"]["timestamp_key"] for a in items] == gold["tree/timestamp_keys"].tolist()
+    assert len(set(gold["tree/ego_ids"].tolist())) > 1                      # the ego really was re-drawn
+    assert [i for ids in o["object_ids"] for i in ids] == gold["tree/object_ids"].tolist()
+    for k in ("record_len", "prior_encoding", "object_bbx_mask"):
+        assert np.array_equal(o[k].numpy(), gold["tree/" + k]), k
+    assert float(o["prior_encoding"][:, 1:, 1].max()) == 1.0                # the delayed agents carry their time delay
+    for k, tol in (("pairwise_t_matrix_collab", 1e-6), ("spatial_correction_matrix", 1e-12), ("object_bbx_center", 1e-9)):
+        assert np.abs(o[k].numpy() - gold["tree/" + k]).max() <= tol, k
+    corr = gold["tree/spatial_correction_matrix"]
+    assert np.allclose(corr[:, 0], np.eye(4)) and not np.allclose(corr[:, 1:6], np.eye(4))   # delayed ego pose: real corrections
+    vox = MGD.voxelise_like_the_reference(o, h, True)
+    for t in ("vehicle", "rsu", "drone"):
+        assert np.array_equal(o[t]["record_len"].numpy(), gold["tree/%s/record_len" % t])
+        assert np.array_equal(vox[t]["voxel_coords"], gold["tree/%s/voxel_coords" % t])
+        assert np.array_equal(vox[t]["voxel_features"].astype(np.float64).sum(axis=(1, 2)), gold["tree/%s/voxel_sum" % t])
+
+
 @needs_reference
 @pytest.mark.parametrize("train,delay", [(False, False), (True, False), (True, True)])
 def test_live_against_the_reference_dataset_on_a_directory(hypes, train, delay, tmp_path, monkeypatch):
