@@ -18,7 +18,7 @@ the per-agent records it returns (`ego`, `agent_type`, `distance_to_ego`, `time_
 without one the AirV2X directory tree under `params["root_dir"]` is scanned like the reference does (`airv2x_scenes.py`).
 `agent_pose_params` restates the pose half of `reform_param` (`basedataset.py:305-532`) for in-memory sources.
 
-Host logic only (numpy / torch CPU tensors): no kernel work happens here and nothing here imports `oracle/`.
+Host logic only (numpy / torch CPU tensors): no kernel work happens here; the checker under `oracle/` is not used.
 """
 import heapq
 import math
