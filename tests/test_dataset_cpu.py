@@ -251,3 +251,23 @@ def test_ground_truth_boxes_of_the_evaluation_against_the_reference(DS, ref_env)
     gt, cls, ids = ds.generate_gt_bbx(mine)
     assert gt.dtype == gt_ref.dtype and gt.shape == gt_ref.shape and gt.shape[0] > 10
     assert torch.equal(gt, gt_ref) and cls == cls_ref and ids == ids_ref
+
+
+@needs_reference
+def test_random_scene_shapes_live_against_the_reference(DS, ref_env):
+    """seeded fuzz over agent counts per type (above and below `max_cav`), `max_cav` itself, object counts down to zero,
+    agents beyond the communication range, depth images, train / eval: every batch equal to the reference's
+    (40 such configurations were run when this was written; eight are kept here)"""
+    IFD, hypes0 = ref_env
+    g = np.random.default_rng(0)
+    for it in range(8):
+        h = copy.deepcopy(hypes0)
+        h["train_params"]["max_cav"] = {"vehicle": int(g.integers(1, 6)), "rsu": int(g.integers(1, 4)), "drone": int(g.integers(1, 3))}
+        train = bool(g.integers(0, 2))
+        kw = dict(seed=1000 + it, n_veh=int(g.integers(1, 8)), n_rsu=int(g.integers(0, 6)), n_drone=int(g.integers(0, 4)),
+                  n_obj=int(g.choice([0, 1, 5, 40, 90])), n_pts=int(g.choice([50, 400])), far=bool(g.integers(0, 2)),
+                  depth=bool(g.integers(0, 2)))
+        scenes = [DC.synth_scene(DS, **kw), DC.synth_scene(DS, **dict(kw, seed=2000 + it, n_rsu=int(g.integers(0, 3))))]
+        _, ref_batch = MGD.run_reference(MGD.reference_dataset(IFD, h, train), scenes, seed=it)
+        _, _, ours = MGD.run_ours(DS, h, train, scenes, seed=it)
+        assert MGD.compare(ref_batch, ours, h, train) < 1e-9, (it, kw)
