@@ -36,10 +36,63 @@ def setup_optimizer(hypes, model):
     return cls(params, lr=cfg["lr"], **kw)
 
 
-def setup_lr_scheduler(hypes, optimizer, init_epoch=None):
-    """train_utils.py:393-452 (step / multistep / exponential; the timm cosine schedule is outside the path)"""
+class CosineWarmupLR:
+    """`timm.scheduler.cosine_lr.CosineLRScheduler(optimizer, t_initial, lr_min, warmup_lr_init, warmup_t, cycle_limit=1,
+    t_in_epochs=False)` as `setup_lr_schedular` builds it for `cosineannealwarm` (train_utils.py:430-447; the shipped
+    V2X-R yamls). timm is not a dependency here: the schedule is restated from its published implementation (linear warm-up
+    from `warmup_lr_init`, then lr_min + (lr - lr_min) (1 + cos(pi t / t_initial)) / 2, lr_min after one cycle) — parity with
+    timm itself is unpinned. Like timm's object, constructing it sets the learning rate to `warmup_lr_init`, and because the
+    schedule counts UPDATES (`t_in_epochs=False`) the epoch-level `step(epoch)` that `tools/train.py:289` issues changes
+    nothing: only `step_update(num_updates)` moves the rate (the reference's loop never calls it, so the shipped yaml trains
+    at the constant warm-up rate; `Trainer(per_iteration_schedule=True)` calls it once per step)."""
+
+    def __init__(self, optimizer, t_initial, lr_min, warmup_lr_init, warmup_t):
+        import math
+        self._math = math
+        self.optimizer = optimizer
+        self.t_initial, self.lr_min, self.warmup_lr_init, self.warmup_t = int(t_initial), lr_min, warmup_lr_init, int(warmup_t)
+        for g in optimizer.param_groups:
+            g.setdefault("initial_lr", g["lr"])
+        self.base_values = [g["initial_lr"] for g in optimizer.param_groups]
+        self.num_updates = 0
+        if self.warmup_t:
+            self._set([self.warmup_lr_init for _ in self.base_values])
+
+    def _set(self, values):
+        for g, v in zip(self.optimizer.param_groups, values):
+            g["lr"] = v
+
+    def lr_at(self, t):
+        if t < self.warmup_t:
+            return [self.warmup_lr_init + t * (v - self.warmup_lr_init) / self.warmup_t for v in self.base_values]
+        if t // self.t_initial >= 1:                         # cycle_limit = 1
+            return [self.lr_min for _ in self.base_values]
+        c = 0.5 * (1 + self._math.cos(self._math.pi * (t % self.t_initial) / self.t_initial))
+        return [self.lr_min + (v - self.lr_min) * c for v in self.base_values]
+
+    def step(self, epoch=None, metric=None):
+        """epoch-level call: a schedule in updates ignores it (timm `_get_values(epoch, on_epoch=True)` -> None)"""
+
+    def step_update(self, num_updates, metric=None):
+        self.num_updates = int(num_updates)
+        self._set(self.lr_at(self.num_updates))
+
+    def state_dict(self):
+        return {k: v for k, v in self.__dict__.items() if k not in ("optimizer", "_math")}
+
+    def load_state_dict(self, state):
+        self.__dict__.update(state)
+
+
+def setup_lr_scheduler(hypes, optimizer, init_epoch=None, n_iter_per_epoch=None):
+    """train_utils.py:393-452: step / multistep / exponential on torch's schedulers, cosineannealwarm on `CosineWarmupLR`"""
     cfg = hypes["lr_scheduler"]
     m = cfg["core_method"]
+    if m == "cosineannealwarm":
+        if not n_iter_per_epoch:
+            raise ValueError("lr_scheduler cosineannealwarm counts updates: pass n_iter_per_epoch (len(train_loader), train.py:177-184)")
+        return CosineWarmupLR(optimizer, cfg["epoches"] * n_iter_per_epoch, cfg["lr_min"], cfg["warmup_lr"],
+                              cfg["warmup_epoches"] * n_iter_per_epoch)
     if m == "step":
         sch = torch.optim.lr_scheduler.StepLR(optimizer, step_size=cfg["step_size"], gamma=cfg["gamma"])
     elif m == "multistep":
@@ -94,14 +147,15 @@ class Trainer:
     `object_bbx_center [B,max_num,7]`, `object_bbx_mask [B,max_num]`, `object_class_ids [B,max_num]` (the tensors the
     dataset hands to `generate_label_airv2x`) — or a ready `label_dict`. Returns the device tensor [reg, cls, obj]."""
 
-    def __init__(self, model, hypes, graph=True):
+    def __init__(self, model, hypes, graph=True, n_iter_per_epoch=None, per_iteration_schedule=False):
         self.model, self.hypes = model, hypes
+        self.iteration, self.per_iteration_schedule = 0, per_iteration_schedule
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("Trainer (B200) needs the model on a CUDA device; there is no CPU path")
         self.assigner = TargetAssigner(hypes["postprocess"], dev)
         self.optimizer = setup_optimizer(hypes, model)
-        self.scheduler = setup_lr_scheduler(hypes, self.optimizer)
+        self.scheduler = setup_lr_scheduler(hypes, self.optimizer, n_iter_per_epoch=n_iter_per_epoch)
         la = hypes["loss"]["args"]
         self.cls_weight, self.reg_coe = float(la["cls_weight"]), float(la["reg"])
         self.graph = graph
@@ -133,7 +187,10 @@ class Trainer:
         else:
             loss3 = model.train_step(data, labels, self.cls_weight, self.reg_coe, **kw)
         self.average_grads()                        # gradients were written into p.grad by the fused step
+        if self.per_iteration_schedule and hasattr(self.scheduler, "step_update"):
+            self.scheduler.step_update(self.iteration)
         self.optimizer.step()
+        self.iteration += 1
         return loss3
 
     def end_epoch(self, saved_path=None):
@@ -160,6 +217,8 @@ class Trainer:
 
     def resume(self, saved_path):
         self.epoch, _ = load_saved_model(saved_path, self.model, None, self.optimizer, self.scheduler)
+        if hasattr(self.scheduler, "num_updates") and self.scheduler.num_updates:
+            self.iteration = self.scheduler.num_updates + 1          # an update-counting schedule continues where it stopped
         return self.epoch
 
 

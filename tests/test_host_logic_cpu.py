@@ -120,3 +120,58 @@ def test_checkpoint_resume_helpers(tmp_path):
     assert type(o).__name__ == "Adam" and o.defaults["eps"] == 1e-10 and o.defaults["weight_decay"] == 1e-4
     s = TL.setup_lr_scheduler(hypes, o, init_epoch=11)
     assert abs(o.param_groups[0]["lr"] - 0.0002) < 1e-12 and s.last_epoch == 11
+
+
+def test_cosine_warmup_schedule_of_the_legacy_yamls(pkg):
+    """`lr_scheduler: cosineannealwarm` (V2XR_*.yaml): the update-counting cosine schedule with linear warm-up that
+    `setup_lr_schedular` builds on timm (train_utils.py:430-447) — closed-form values, timm's construction side effect (the
+    rate starts at `warmup_lr`), its no-op epoch step, state round trip"""
+    import math
+
+    import pytest
+    import torch
+
+    import a2x_import
+
+    TL = a2x_import.pkg("train_loop")
+    hypes = {"lr_scheduler": {"core_method": "cosineannealwarm", "epoches": 4, "warmup_lr": 2e-5, "warmup_epoches": 1, "lr_min": 5e-6}}
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = torch.optim.Adam([p], lr=2e-3)
+    with pytest.raises(ValueError):
+        TL.setup_lr_scheduler(hypes, opt)
+    sch = TL.setup_lr_scheduler(hypes, opt, n_iter_per_epoch=10)
+    lr = lambda: opt.param_groups[0]["lr"]  # noqa: E731
+    assert lr() == 2e-5 and opt.param_groups[0]["initial_lr"] == 2e-3          # constructing it drops the rate to warmup_lr
+    for e in range(3):
+        sch.step(e)                                                          # the epoch-level call of tools/train.py:289
+    assert lr() == 2e-5
+    sch.step_update(5)
+    assert abs(lr() - (2e-5 + 5 * (2e-3 - 2e-5) / 10)) < 1e-12                 # linear warm-up over 10 updates
+    sch.step_update(10)
+    assert abs(lr() - (5e-6 + (2e-3 - 5e-6) * 0.5 * (1 + math.cos(math.pi * 10 / 40)))) < 1e-12
+    sch.step_update(20)
+    assert abs(lr() - (5e-6 + (2e-3 - 5e-6) * 0.5)) < 1e-12                    # half way: the mean of lr and lr_min
+    sch.step_update(39)
+    assert 5e-6 < lr() < 2e-5
+    sch.step_update(40)
+    assert lr() == 5e-6
+    sch.step_update(400)
+    assert lr() == 5e-6                                                      # one cycle only
+    lrs = []
+    for t in range(41):
+        sch.step_update(t)
+        lrs.append(lr())
+    # rises through the warm-up, then (no warm-up prefix: the cosine is evaluated at t, not t - warmup_t) falls to lr_min
+    assert all(a < b for a, b in zip(lrs[:9], lrs[1:10])) and all(a > b for a, b in zip(lrs[10:40], lrs[11:41]))
+    state = sch.state_dict()
+    assert "optimizer" not in state and state["num_updates"] == 40
+    opt2 = torch.optim.Adam([torch.nn.Parameter(torch.zeros(3))], lr=2e-3)
+    sch2 = TL.setup_lr_scheduler(hypes, opt2, n_iter_per_epoch=10)
+    sch2.load_state_dict(state)
+    sch2.step_update(20)
+    assert abs(opt2.param_groups[0]["lr"] - (5e-6 + (2e-3 - 5e-6) * 0.5)) < 1e-12
+    # the other schedules are torch's own
+    for m, cls in (("step", "StepLR"), ("multistep", "MultiStepLR"), ("exponential", "ExponentialLR")):
+        s = TL.setup_lr_scheduler({"lr_scheduler": {"core_method": m, "gamma": 0.1, "step_size": [1, 2] if m == "multistep" else 2}},
+                                  torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1e-3))
+        assert type(s).__name__ == cls
