@@ -89,3 +89,20 @@ def test_header_is_plain_c_and_cpp(tmp_path):
         assert r.returncode == 0, r.stderr
     text = open(os.path.join(inc, "airv2x_b200.h")).read()
     assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S) and "cuda_runtime" not in text
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch, tmp_path):
+    """no silent fallback: without the built library (and no way to build it) loading raises, and so does every op"""
+    import pytest
+
+    import a2x_import
+
+    libm = a2x_import.pkg("_lib")
+    bld = a2x_import.pkg("build")
+    monkeypatch.setattr(libm, "_lib", None)
+    monkeypatch.setattr(libm, "LIB_PATH", str(tmp_path / "libairv2x_b200.so"))
+    monkeypatch.setattr(bld, "build", lambda *a, **k: None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        libm.load()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        libm.call("a2x_version")
