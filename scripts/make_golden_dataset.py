@@ -230,7 +230,9 @@ def tree_case(IFD, DS, hypes):
     return out
 
 
-def main():
+def main(dst_dir=None):
+    """dst_dir: where to write dataset.npz / dataset_config.json (default: tests/golden)"""
+    dst_dir = dst_dir or os.path.join(ROOT, "tests", "golden")
     IFD = reference_env()
     DS = a2x_import.pkg("intermediate_fusion_dataset")
     import dataset_common as DC
@@ -268,9 +270,9 @@ def main():
     out.update(tree_case(IFD, DS, hypes))
     import json
     keys = ("fusion", "preprocess", "postprocess", "train_params", "collaborators", "active_sensors", "ego_type")
-    with open(os.path.join(ROOT, "tests", "golden", "dataset_config.json"), "w") as f:   # the yaml keys the dataset reads
+    with open(os.path.join(dst_dir, "dataset_config.json"), "w") as f:   # the yaml keys the dataset reads
         json.dump({k: hypes[k] for k in keys}, f, default=lambda o: o.tolist())
-    dst = os.path.join(ROOT, "tests", "golden", "dataset.npz")
+    dst = os.path.join(dst_dir, "dataset.npz")
     np.savez_compressed(dst, **out)
     print("wrote %s (%.0f kB)" % (dst, os.path.getsize(dst) / 1e3))
 

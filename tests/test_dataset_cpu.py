@@ -271,3 +271,15 @@ def test_random_scene_shapes_live_against_the_reference(DS, ref_env):
         _, ref_batch = MGD.run_reference(MGD.reference_dataset(IFD, h, train), scenes, seed=it)
         _, _, ours = MGD.run_ours(DS, h, train, scenes, seed=it)
         assert MGD.compare(ref_batch, ours, h, train) < 1e-9, (it, kw)
+
+
+@needs_reference
+def test_the_committed_fixture_is_what_the_reference_produces_today(ref_env, tmp_path):
+    """scripts/make_golden_dataset.py re-run against the reference tree reproduces tests/golden/dataset.npz array for array
+    (and dataset_config.json), i.e. the fixture the portable tests rely on is the reference's output, not a stale copy"""
+    MGD.main(str(tmp_path))
+    new, old = np.load(str(tmp_path / "dataset.npz")), np.load(os.path.join(GOLD, "dataset.npz"))
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        assert new[k].dtype == old[k].dtype and np.array_equal(new[k], old[k]), k
+    assert json.load(open(tmp_path / "dataset_config.json")) == json.load(open(os.path.join(GOLD, "dataset_config.json")))
