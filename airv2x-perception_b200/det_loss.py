@@ -80,8 +80,25 @@ class _Criterion(torch.nn.Module):
         self.reg_coe = args["reg"]
         self.loss_dict = {}
         self._terms = {}
+        self._assigner = None
+
+    def _targets(self, target_dict, device):
+        """`label_dict` of this repo's dataset = the padded boxes (+ the yaml's postprocess block) instead of label maps: the
+        anchor targets are assigned here, on the GPU (`labels.TargetAssigner`, one per postprocess block and device), so
+        the reference's loop — `criterion(output_dict, batch_data["ego"]["label_dict"])`, tools/train.py:222-226 — runs
+        unmodified on this dataset. A `label_dict` that already holds `targets` (the reference's dataset) passes through."""
+        if "targets" in target_dict:
+            return target_dict
+        from .labels import TargetAssigner
+        import json
+        key = (str(device), json.dumps(target_dict["postprocess"], sort_keys=True, default=str))   # content: to_device() rebuilds the dict
+        if self._assigner is None or self._assigner[0] != key:
+            self._assigner = (key, TargetAssigner(target_dict["postprocess"], device))
+        return self._assigner[1](target_dict["object_bbx_center"], target_dict["object_bbx_mask"],
+                                 target_dict["object_class_ids"])
 
     def _call(self, output_dict, target_dict, prefix, K):
+        target_dict = self._targets(target_dict, output_dict["psm" + prefix].device)
         psm, rm = output_dict["psm" + prefix], output_dict["rm" + prefix]
         obj = None if self.legacy else output_dict["obj" + prefix]
         A = rm.shape[1] // 7

@@ -454,6 +454,10 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
                "timestamp_key_list": [e["timestamp_key"] for e in egos],
                "metadata_path_list": [e["metadata_path"] for e in egos],
                "ego_lidar_pose_list": [e["ego_lidar_pose"] for e in egos]}
+        # what `criterion(output_dict, batch["ego"]["label_dict"])` of tools/train.py:222-226 receives: the boxes, from which
+        # this repo's criterion assigns the anchor targets on the GPU (det_loss._Criterion._targets)
+        out["label_dict"] = {"object_bbx_center": out["object_bbx_center"], "object_bbx_mask": out["object_bbx_mask"],
+                             "object_class_ids": out["object_class_ids"], "postprocess": self.params["postprocess"]}
         if all("dynamic_seg_label" in e and "static_seg_label" in e for e in egos):
             out["seg_label_dict"] = {k: torch.from_numpy(np.array([e[k] for e in egos]))
                                      for k in ("dynamic_seg_label", "static_seg_label")}

@@ -171,7 +171,7 @@ class Trainer:
             self.average_grads = GradAverager(model.parameters())
 
     def labels(self, batch):
-        if "label_dict" in batch:
+        if "label_dict" in batch and "targets" in batch["label_dict"]:      # ready label maps (the reference's dataset)
             return batch["label_dict"]
         return self.assigner(batch["object_bbx_center"], batch["object_bbx_mask"], batch["object_class_ids"])
 

@@ -92,6 +92,10 @@ def test_batches_equal_the_reference_fixture(DS, hypes, name):
     assert raw["offsets"].dtype == torch.int32 and raw["offsets"].shape == (n + 1,) and raw["transforms"].shape == (n, 4, 4)
     assert raw["points"].dtype == torch.float32 and raw["points"].shape == (int(raw["offsets"][-1]), 4)
     assert raw["filter"] is True and raw["preprocess"] is hypes["preprocess"]
+    # the label_dict the reference's loop hands to the criterion: the same padded boxes + the yaml's postprocess block
+    lab = o["label_dict"]
+    assert lab["object_bbx_center"] is o["object_bbx_center"] and lab["object_bbx_mask"] is o["object_bbx_mask"]
+    assert lab["object_class_ids"] is o["object_class_ids"] and lab["postprocess"] is hypes["postprocess"] and "targets" not in lab
 
 
 def test_shuffle_is_a_permutation_and_off_keeps_the_order(DS, hypes):
