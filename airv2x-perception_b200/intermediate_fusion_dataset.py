@@ -368,6 +368,8 @@ class IntermediateFusionDatasetAirv2x(torch.utils.data.Dataset):
         ego_rec, projected = None, {}           # object records shared between agents are projected once per scene
         for cid, rec in base_data_dict.items():
             t = rec["agent_type"]
+            if t not in self.collaborators:     # not a collaborator of this yaml: the models hold no encoder for it (the
+                continue                        # reference counts such an agent and then mis-pads / fails in np.tile)
             if rec["distance_to_ego"] > COM_RANGE[t]:
                 continue
             item = self.get_item_single_car(rec, ego_pose, projected)

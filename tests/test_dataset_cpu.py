@@ -161,6 +161,17 @@ def test_an_agent_with_an_empty_cloud_supervises_nothing(DS, hypes):
     assert offs[2] == offs[1] and int(part["ego"]["record_len"][0]) == 2        # the agent stays in the batch, with 0 points
 
 
+def test_agents_outside_the_yamls_collaborators_are_left_out(DS, hypes):
+    h = copy.deepcopy(hypes)
+    h["collaborators"] = ["vehicle", "rsu"]
+    scene = DC.synth_scene(DS, seed=6, n_veh=2, n_rsu=1, n_drone=2, far=False, cameras=False, n_pts=100)
+    ds, items, batch = MGD.run_ours(DS, h, False, [scene], seed=0)
+    o = batch["ego"]
+    assert ds.max_cav_num == 10 and o["record_len"].tolist() == [3] and o["drone"]["record_len"].tolist() == [0]
+    assert o["raw_points"]["offsets"].tolist() == [0, 100, 200, 300] and o["prior_encoding"].shape == (1, 10, 3)
+    assert o["drone"]["batch_idxs"] == [] and o["pairwise_t_matrix_collab"].shape == (1, 10, 10, 4, 4)
+
+
 def test_a_dataset_without_a_source_raises(DS, hypes):
     ds = DS.IntermediateFusionDatasetAirv2x(hypes, False, True)
     with pytest.raises(NotImplementedError):
