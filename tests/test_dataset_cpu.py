@@ -295,6 +295,10 @@ def test_the_committed_fixture_is_what_the_reference_produces_today(ref_env, tmp
     MGD.main(str(tmp_path))
     new, old = np.load(str(tmp_path / "dataset.npz")), np.load(os.path.join(GOLD, "dataset.npz"))
     assert sorted(new.files) == sorted(old.files)
-    for k in old.files:
-        assert new[k].dtype == old[k].dtype and np.array_equal(new[k], old[k]), k
+    for k in old.files:     # equal here; another CPU model may move the reference's float results by an ulp
+        assert new[k].dtype == old[k].dtype and new[k].shape == old[k].shape, k
+        if old[k].dtype.kind == "f":
+            assert old[k].size == 0 or float(np.abs(new[k].astype(np.float64) - old[k].astype(np.float64)).max()) <= 1e-6, k
+        else:
+            assert np.array_equal(new[k], old[k]), k
     assert json.load(open(tmp_path / "dataset_config.json")) == json.load(open(os.path.join(GOLD, "dataset_config.json")))
