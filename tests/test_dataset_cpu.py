@@ -68,7 +68,8 @@ def test_batches_equal_the_reference_fixture(DS, hypes, name):
         if vox[t] is not None:
             assert np.array_equal(vox[t]["voxel_coords"], gold[key])
             assert np.array_equal(vox[t]["voxel_num_points"], gold["%s/%s/voxel_num_points" % (name, t)])
-            assert np.array_equal(vox[t]["voxel_features"].astype(np.float64).sum(axis=(1, 2)), gold["%s/%s/voxel_sum" % (name, t)])
+            assert np.allclose(vox[t]["voxel_features"].astype(np.float64).sum(axis=(1, 2)), gold["%s/%s/voxel_sum" % (name, t)],
+                               rtol=1e-6, atol=1e-3)      # equal on the machine that recorded it; an fp32 ulp elsewhere
         for k, c in o[t]["batch_merged_cam_inputs"].items():
             if k == "imgs":
                 g = gold["%s/%s/cam_imgs_mean" % (name, t)]

@@ -132,7 +132,8 @@ def test_directory_pipeline_equals_the_recorded_reference_run(hypes, tmp_path):
     for t in ("vehicle", "rsu", "drone"):
         assert np.array_equal(o[t]["record_len"].numpy(), gold["tree/%s/record_len" % t])
         assert np.array_equal(vox[t]["voxel_coords"], gold["tree/%s/voxel_coords" % t])
-        assert np.array_equal(vox[t]["voxel_features"].astype(np.float64).sum(axis=(1, 2)), gold["tree/%s/voxel_sum" % t])
+        assert np.allclose(vox[t]["voxel_features"].astype(np.float64).sum(axis=(1, 2)), gold["tree/%s/voxel_sum" % t],
+                           rtol=1e-6, atol=1e-3)
 
 
 @needs_reference
