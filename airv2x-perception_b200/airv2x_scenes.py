@@ -50,11 +50,15 @@ def lzf_decompress(src, out_len):
         i += 1
         if ctrl < 32:
             run = ctrl + 1
+            if i + run > n or o + run > out_len:
+                raise ValueError("corrupt LZF stream")
             out[o:o + run] = src[i:i + run]
             i += run
             o += run
             continue
         length = ctrl >> 5
+        if i + (2 if length == 7 else 1) > n:
+            raise ValueError("corrupt LZF stream")
         if length == 7:
             length += src[i]
             i += 1

@@ -208,3 +208,21 @@ def test_real_build_dataset_dispatches_to_the_b200_dataset(hypes, tmp_path, monk
     assert build_dataset.__module__ == "opencood.data_utils.datasets"
     import opencood.data_utils.datasets as D
     assert D.__all__["IntermediateFusionDatasetAirv2x"].__module__.startswith("opencood.")
+
+
+def test_lzf_round_trip_property():
+    """hypothesis: decode(encode(x)) == x for arbitrary byte strings (low-entropy ones exercise long / overlapping
+    back references); truncated streams raise instead of returning short output"""
+    from hypothesis import given, settings, strategies as st
+
+    S = a2x_import.pkg("airv2x_scenes")
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.one_of(st.binary(max_size=600), st.lists(st.sampled_from([0, 1, 255]), max_size=900).map(bytes)))
+    def check(blob):
+        comp = SC.lzf_compress(blob)
+        assert S.lzf_decompress(comp, len(blob)) == blob
+        if len(comp) > 1:
+            with pytest.raises(ValueError):
+                S.lzf_decompress(comp[:-1], len(blob))
+    check()
