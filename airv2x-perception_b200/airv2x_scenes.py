@@ -25,6 +25,7 @@ import math
 import os
 import pickle
 import random
+import re
 from collections import OrderedDict
 
 import numpy as np
@@ -35,6 +36,7 @@ _CAMERAS = {"vehicle": ["front", "front_left", "front_right", "rear", "rear_left
             "rsu": ["back", "front", "left", "right"], "drone": ["bev"]}            # utils/airv2x_utils.py:37-118
 _STATIC_MAPS = ["map_static_background.png", "map_static_lane.png", "map_static_road.png"]
 _DYNAMIC_MAPS = ["map_dynamic_bev_layer_%d.png" % i for i in range(7)]
+_INDEXED = re.compile(r"^[A-Za-z]+_\d+$")          # timestamp_000010, agent_001514
 _PCD_TYPES = {("F", 4): "f4", ("F", 8): "f8", ("U", 1): "u1", ("U", 2): "u2", ("U", 4): "u4", ("I", 1): "i1",
               ("I", 2): "i2", ("I", 4): "i4"}
 
@@ -200,13 +202,13 @@ class AirV2XScenes:
         """agent id -> timestamp id -> file record, agents in first-seen order (`parse_seq` + `convert2opv2v`)"""
         agents = OrderedDict()
         for ts_path in sorted(os.path.join(folder, t) for t in os.listdir(folder)):
-            if not os.path.isdir(ts_path):
-                continue
+            if not os.path.isdir(ts_path) or not _INDEXED.match(os.path.basename(ts_path)):
+                continue                          # stray files / folders (the reference's int(name.split("_")[1]) would raise)
             ts = int(os.path.basename(ts_path).split("_")[1])
             for a_path in sorted(os.path.join(ts_path, a) for a in os.listdir(ts_path)):
-                if os.path.isfile(a_path):
-                    continue
                 meta_path = os.path.join(a_path, "metadata.pkl")
+                if os.path.isfile(a_path) or not _INDEXED.match(os.path.basename(a_path)) or not os.path.isfile(meta_path):
+                    continue
                 kind = self._pickle(meta_path)["agent_type"]
                 if kind not in _CAMERAS:
                     raise ValueError("Unknown agent type: %s" % kind)

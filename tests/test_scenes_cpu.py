@@ -80,6 +80,10 @@ def test_pcd_reader_round_trips_binary_and_ascii(tmp_path):
 
 def test_scan_orders_agents_and_counts_samples(hypes):
     S = a2x_import.pkg("airv2x_scenes")
+    first = sorted(os.listdir(hypes["root_dir"]))[0]                    # stray entries in the tree are ignored by the scan
+    os.makedirs(os.path.join(hypes["root_dir"], first, "logs"), exist_ok=True)
+    os.makedirs(os.path.join(hypes["root_dir"], first, "timestamp_000000", "agent_000099"), exist_ok=True)   # no metadata
+    open(os.path.join(hypes["root_dir"], first, "notes.txt"), "w").close()
     src = S.AirV2XScenes(hypes, train=False)
     assert len(src) == 6 and src.len_record == [3, 6]
     # ids sorted by path, the leading RSU moved behind the first vehicle; vehicle 35 appears at the 2nd timestamp in scenario 0
