@@ -11,7 +11,8 @@ What differs from the reference, on purpose:
     sample: 4 + 4 loads per agent and `__getitem__`);
   * camera / depth PNGs are decoded only when `"cam"` is an active sensor and the segmentation maps only for the
     segmentation task — a lidar detection sample then touches one .pcd and one pickle per agent;
-  * an agent that does not exist at the sample's timestamp is skipped (the reference drops into pdb, :576-586);
+  * an agent that does not exist at the sample's timestamp is skipped (the reference drops into pdb, :576-586); entries of
+    the tree that are not `<word>_<number>` folders, and agent folders without a metadata.pkl, are ignored by the scan;
   * .pcd files are read by `read_pcd` below (open3d, which the reference calls, is not a dependency here): x, y, z and the
     first colour channel as intensity, as `pcd_to_np` returns them (utils/pcd_utils.py:43-82). Parity of this reader with
     open3d is UNPINNED (open3d absent in the build container); everything else is pinned live against the reference class
