@@ -86,7 +86,7 @@ def read_pcd(path):
     """PCD v0.7 (ascii / binary / binary_compressed) -> [n, 4] float32 (x, y, z, intensity). Intensity = red channel / 255 of the packed `rgb`
     field (how open3d exposes `colors[:, 0]` for the clouds the simulator saved), or an `intensity` field if present."""
     with open(path, "rb") as f:
-        fields, sizes, types, counts, n, mode = [], [], [], [], None, None
+        fields, sizes, types, counts, n, mode, wh = [], [], [], [], None, None, [None, 1]
         while True:
             line = f.readline()
             if not line:
@@ -105,9 +105,19 @@ def read_pcd(path):
                 counts = [int(v) for v in tok[1:]]
             elif key == "POINTS":
                 n = int(tok[1])
+            elif key == "WIDTH":
+                wh[0] = int(tok[1])
+            elif key == "HEIGHT":
+                wh[1] = int(tok[1])
             elif key == "DATA":
                 mode = tok[1].lower()
                 break
+        if n is None:                            # POINTS is optional in old files: WIDTH x HEIGHT
+            if wh[0] is None:
+                raise ValueError("%s: PCD header without POINTS / WIDTH" % path)
+            n = wh[0] * wh[1]
+        if not fields or len(sizes) != len(fields) or len(types) != len(fields) or any(a not in fields for a in "xyz"):
+            raise ValueError("%s: PCD header needs FIELDS x y z with SIZE / TYPE entries" % path)
         counts = counts or [1] * len(fields)
         if any(c != 1 for c in counts):
             raise NotImplementedError("%s: multi-count PCD fields" % path)

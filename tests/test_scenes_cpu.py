@@ -72,6 +72,16 @@ def test_pcd_reader_round_trips_binary_and_ascii(tmp_path):
             assert len(comp) < len(blob) // 2                    # the encoder really emits back references
     with pytest.raises(ValueError):
         S.lzf_decompress(b"\x20\x05", 10)                       # reference before the start of the output
+    with open(tmp_path / "w.pcd", "w") as f:                      # no POINTS line: WIDTH x HEIGHT; extra fields are carried along
+        f.write("VERSION 0.7\nFIELDS x y z normal_x intensity\nSIZE 4 4 4 4 4\nTYPE F F F F F\nWIDTH 2\nHEIGHT 1\nDATA ascii\n"
+                "1 2 3 9 0.5\n4 5 6 9 0.75\n")
+    assert np.array_equal(S.read_pcd(str(tmp_path / "w.pcd")), np.array([[1, 2, 3, 0.5], [4, 5, 6, 0.75]], dtype=np.float32))
+    for bad in ("VERSION 0.7\nFIELDS x y\nSIZE 4 4\nTYPE F F\nPOINTS 1\nDATA ascii\n1 2\n",
+                "VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nDATA ascii\n1 2 3\n"):
+        with open(tmp_path / "bad.pcd", "w") as f:
+            f.write(bad)
+        with pytest.raises(ValueError):
+            S.read_pcd(str(tmp_path / "bad.pcd"))
     with open(tmp_path / "q.pcd", "w") as f:
         f.write("VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA quantum\n")
     with pytest.raises(NotImplementedError):
